@@ -1,0 +1,391 @@
+"""ctypes binding of the CPU oracle (oracle/linemod_oracle.cpp).
+
+TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module; the product package never does.  PARITY UNPINNED: see the header of
+linemod_oracle.cpp -- the reference's hot path (OpenCV 2.4.x objdetect/linemod.cpp, entered at
+/root/reference/src/rgbdDetector.cpp:31-34) is not vendored and cannot be built here.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liblinemod_oracle.so")
+
+TYPE_8UC3, TYPE_16UC1, TYPE_8UC1 = 0, 1, 2
+COLOR_GRADIENT, DEPTH_NORMAL = 0, 1
+
+
+class OrcImage(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("rows", C.c_int32), ("cols", C.c_int32), ("type", C.c_int32),
+                ("step", C.c_size_t)]
+
+
+class OrcModality(C.Structure):
+    _fields_ = [("type", C.c_int32), ("weak_threshold", C.c_float), ("strong_threshold", C.c_float),
+                ("distance_threshold", C.c_int32), ("difference_threshold", C.c_int32),
+                ("extract_threshold", C.c_int32), ("num_features", C.c_int32)]
+
+
+MATCH_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("template_id", "<i4"), ("class_index", "<i4"),
+                        ("similarity", "<f4")])
+CAND_DTYPE = np.dtype([("class_index", "<i4"), ("template_id", "<i4"), ("pos", "<i4"), ("raw", "<i4")])
+
+
+def build(force=False):
+    """Compile the oracle with oracle/Makefile (g++ only; no GPU, no reference sources needed)."""
+    src = os.path.join(_HERE, "linemod_oracle.cpp")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.POINTER(C.c_int32), C.c_int, C.POINTER(OrcModality), C.c_int]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_last_error.restype = C.c_char_p
+        L.orc_last_error.argtypes = [C.c_void_p]
+        L.orc_set_threads.argtypes = [C.c_void_p, C.c_int]
+        L.orc_max_threads.restype = C.c_int
+        for n in ("orc_set_similarity_lut", "orc_get_similarity_lut", "orc_set_normal_lut", "orc_get_normal_lut"):
+            getattr(L, n).argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_add_template.restype = C.c_int
+        L.orc_add_template.argtypes = [C.c_void_p, C.POINTER(OrcImage), C.c_int, C.c_char_p, C.POINTER(OrcImage),
+                                       C.POINTER(C.c_int32)]
+        L.orc_add_synthetic_template.restype = C.c_int
+        L.orc_add_synthetic_template.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_num_classes.argtypes = [C.c_void_p]
+        L.orc_num_templates.argtypes = [C.c_void_p, C.c_char_p]
+        L.orc_class_id.restype = C.c_char_p
+        L.orc_class_id.argtypes = [C.c_void_p, C.c_int]
+        L.orc_get_template.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_build_front.argtypes = [C.c_void_p, C.POINTER(OrcImage), C.c_int, C.POINTER(OrcImage), C.c_int]
+        L.orc_match_only.restype = C.c_long
+        L.orc_match_only.argtypes = [C.c_void_p, C.c_float, C.POINTER(C.c_char_p), C.c_int, C.c_int,
+                                     C.POINTER(C.c_void_p)]
+        L.orc_match.restype = C.c_long
+        L.orc_match.argtypes = [C.c_void_p, C.POINTER(OrcImage), C.c_int, C.c_float, C.POINTER(C.c_char_p), C.c_int,
+                                C.POINTER(OrcImage), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.orc_free.argtypes = [C.c_void_p]
+        L.orc_last_presort.restype = C.c_long
+        L.orc_last_presort.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_last_candidates.restype = C.c_long
+        L.orc_last_candidates.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_coarse_map.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p]
+        L.orc_debug_fetch.restype = C.c_long
+        L.orc_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_level_geometry.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_size_t)]
+        L.orc_sort_unique.restype = C.c_long
+        L.orc_sort_unique.argtypes = [C.c_void_p, C.c_long]
+        L.orc_prim_phase_deg.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.orc_prim_cg_quantize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _img(a):
+    """numpy array (possibly a strided view with contiguous rows) -> (OrcImage, keepalive)."""
+    if a.dtype == np.uint8 and a.ndim == 3 and a.shape[2] == 3:
+        t = TYPE_8UC3
+    elif a.dtype == np.uint16 and a.ndim == 2:
+        t = TYPE_16UC1
+    elif a.dtype == np.uint8 and a.ndim == 2:
+        t = TYPE_8UC1
+    else:
+        raise TypeError("unsupported image %s %s" % (a.dtype, a.shape))
+    if a.strides[1] != a.itemsize * (3 if t == TYPE_8UC3 else 1):
+        a = np.ascontiguousarray(a)
+    return OrcImage(a.ctypes.data, a.shape[0], a.shape[1], t, a.strides[0]), a
+
+
+def _img_array(images):
+    keep = [_img(a) for a in images]
+    arr = (OrcImage * max(1, len(keep)))(*[k[0] for k in keep])
+    return arr, keep
+
+
+def color_gradient(weak=10.0, num_features=63, strong=55.0):
+    return OrcModality(COLOR_GRADIENT, weak, strong, 2000, 50, 2, num_features)
+
+
+def depth_normal(distance=2000, difference=50, num_features=63, extract=2):
+    return OrcModality(DEPTH_NORMAL, 10.0, 55.0, distance, difference, extract, num_features)
+
+
+class Stage:
+    QUANTIZED, SPREAD, RESPONSE, LINEAR, MAGNITUDE, QUANT_RAW = range(6)
+
+
+class OracleDetector:
+    """CPU restatement of cv::linemod::Detector (the surface used at /root/reference/src/renderer.cpp:179-185,308
+    and src/rgbdDetector.cpp:31-34)."""
+
+    def __init__(self, modalities=None, T=(5, 8)):
+        if modalities is None:
+            modalities = [color_gradient(), depth_normal()]
+        self.modalities = list(modalities)
+        self.T = list(T)
+        Ta = (C.c_int32 * len(self.T))(*self.T)
+        Ma = (OrcModality * len(self.modalities))(*self.modalities)
+        self._h = C.c_void_p(lib().orc_create(Ta, len(self.T), Ma, len(self.modalities)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_destroy(self._h)
+            self._h = None
+
+    # -- configuration
+    def set_threads(self, n):
+        lib().orc_set_threads(self._h, int(n))
+
+    @staticmethod
+    def max_threads():
+        return lib().orc_max_threads()
+
+    def set_similarity_lut(self, lut):
+        lut = np.ascontiguousarray(lut, dtype=np.uint8)
+        assert lut.size == 256
+        lib().orc_set_similarity_lut(self._h, lut.ctypes.data)
+
+    def similarity_lut(self):
+        out = np.empty(256, np.uint8)
+        lib().orc_get_similarity_lut(self._h, out.ctypes.data)
+        return out
+
+    def set_normal_lut(self, lut):
+        lut = np.ascontiguousarray(lut, dtype=np.uint8)
+        assert lut.size == 8000
+        lib().orc_set_normal_lut(self._h, lut.ctypes.data)
+
+    def normal_lut(self):
+        out = np.empty(8000, np.uint8)
+        lib().orc_get_normal_lut(self._h, out.ctypes.data)
+        return out
+
+    def _err(self):
+        return lib().orc_last_error(self._h).decode()
+
+    # -- templates
+    def add_template(self, sources, class_id, mask=None):
+        arr, keep = _img_array(sources)
+        bb = (C.c_int32 * 4)()
+        mimg = None
+        if mask is not None:
+            m, mk = _img(mask)
+            mimg = C.pointer(m)
+        r = lib().orc_add_template(self._h, arr, len(sources), class_id.encode(), mimg, bb)
+        if r == -2:
+            raise ValueError(self._err())
+        return r, tuple(bb)
+
+    def add_synthetic_template(self, class_id, templates):
+        """templates: list (L*M) of (width, height, pyramid_level, features[n,3] int)."""
+        hdr = np.array([[t[0], t[1], t[2], len(t[3])] for t in templates], np.int32)
+        feats = np.concatenate([np.asarray(t[3], np.int32).reshape(-1, 3) for t in templates]).astype(np.int32)
+        feats = np.ascontiguousarray(feats)
+        r = lib().orc_add_synthetic_template(self._h, class_id.encode(), len(templates), hdr.ctypes.data,
+                                             feats.ctypes.data)
+        if r < 0:
+            raise ValueError(self._err())
+        return r
+
+    def class_ids(self):
+        return [lib().orc_class_id(self._h, i).decode() for i in range(lib().orc_num_classes(self._h))]
+
+    def num_templates(self, class_id=None):
+        return lib().orc_num_templates(self._h, class_id.encode() if class_id is not None else None)
+
+    def get_template(self, class_id, template_id):
+        n_t = len(self.T) * len(self.modalities)
+        hdr = np.zeros((n_t, 4), np.int32)
+        total = lib().orc_get_template(self._h, class_id.encode(), template_id, hdr.ctypes.data, None)
+        if total < 0:
+            raise KeyError((class_id, template_id))
+        feats = np.zeros((max(total, 1), 3), np.int32)
+        lib().orc_get_template(self._h, class_id.encode(), template_id, hdr.ctypes.data, feats.ctypes.data)
+        out, k = [], 0
+        for i in range(n_t):
+            nf = int(hdr[i, 3])
+            out.append((int(hdr[i, 0]), int(hdr[i, 1]), int(hdr[i, 2]), feats[k:k + nf].copy()))
+            k += nf
+        return out
+
+    # -- matching
+    def build_front(self, sources, masks=()):
+        arr, keep = _img_array(sources)
+        marr, mkeep = _img_array(masks)
+        if lib().orc_build_front(self._h, arr, len(sources), marr, len(masks)) != 0:
+            raise ValueError(self._err())
+
+    @staticmethod
+    def _ids(class_ids):
+        ids = [c.encode() for c in class_ids]
+        return (C.c_char_p * max(1, len(ids)))(*ids), len(ids)
+
+    def _take(self, n, out):
+        if n < 0:
+            raise ValueError(self._err())
+        res = np.empty(n, MATCH_DTYPE)
+        if n:
+            C.memmove(res.ctypes.data, out, n * MATCH_DTYPE.itemsize)
+        lib().orc_free(out)
+        return res
+
+    def match_only(self, threshold, class_ids=(), keep_candidates=False):
+        ids, n_ids = self._ids(class_ids)
+        out = C.c_void_p()
+        n = lib().orc_match_only(self._h, threshold, ids, n_ids, int(keep_candidates), C.byref(out))
+        return self._take(n, out)
+
+    def match(self, sources, threshold, class_ids=(), masks=(), keep_candidates=False):
+        arr, keep = _img_array(sources)
+        marr, mkeep = _img_array(masks)
+        ids, n_ids = self._ids(class_ids)
+        out = C.c_void_p()
+        n = lib().orc_match(self._h, arr, len(sources), threshold, ids, n_ids, marr, len(masks),
+                            int(keep_candidates), C.byref(out))
+        return self._take(n, out)
+
+    def last_presort(self):
+        n = lib().orc_last_presort(self._h, None)
+        res = np.empty(n, MATCH_DTYPE)
+        lib().orc_last_presort(self._h, res.ctypes.data)
+        return res
+
+    def last_candidates(self):
+        n = lib().orc_last_candidates(self._h, None)
+        res = np.empty(n, CAND_DTYPE)
+        lib().orc_last_candidates(self._h, res.ctypes.data)
+        return res
+
+    def geometry(self, level, modality=0):
+        g = (C.c_int32 * 5)()
+        ps = C.c_size_t()
+        if lib().orc_level_geometry(self._h, level, modality, g, C.byref(ps)) != 0:
+            raise ValueError("no front end built")
+        return dict(rows=g[0], cols=g[1], T=g[2], W=g[3], H=g[4], plane_stride=ps.value)
+
+    def coarse_map(self, class_id, template_id):
+        g = self.geometry(len(self.T) - 1)
+        out = np.zeros((g["H"], g["W"]), np.uint16)
+        if lib().orc_coarse_map(self._h, class_id.encode(), template_id, out.ctypes.data) != 0:
+            raise KeyError((class_id, template_id))
+        return out
+
+    def fetch(self, stage, level, modality):
+        n = lib().orc_debug_fetch(self._h, stage, level, modality, None)
+        if n < 0:
+            raise ValueError("bad tap")
+        buf = np.empty(n, np.uint8)
+        lib().orc_debug_fetch(self._h, stage, level, modality, buf.ctypes.data)
+        g = self.geometry(level, modality)
+        if stage in (Stage.QUANTIZED, Stage.SPREAD, Stage.QUANT_RAW):
+            return buf.reshape(g["rows"], g["cols"])
+        if stage == Stage.RESPONSE:
+            return buf.reshape(8, g["rows"], g["cols"])
+        if stage == Stage.LINEAR:
+            return buf.reshape(8, g["plane_stride"])
+        if stage == Stage.MAGNITUDE:
+            return buf.view(np.float32).reshape(g["rows"], g["cols"]) if n else np.zeros((0, 0), np.float32)
+        raise ValueError(stage)
+
+
+def sort_unique(recs):
+    """The tail of Detector::match (std::sort + std::unique with Match::operator< / ==), in libstdc++."""
+    recs = np.ascontiguousarray(recs, dtype=MATCH_DTYPE).copy()
+    n = lib().orc_sort_unique(recs.ctypes.data, len(recs))
+    return recs[:n]
+
+
+# -- primitives (pinned against cv2 in tests/test_oracle_primitives.py)
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def prim_gaussian7(src):
+    src = np.ascontiguousarray(src)
+    ch = 1 if src.ndim == 2 else src.shape[2]
+    dst = np.empty_like(src)
+    lib().orc_prim_gaussian7(_p(src), src.shape[0], src.shape[1], ch, _p(dst))
+    return dst
+
+
+def prim_sobel3(src):
+    src = np.ascontiguousarray(src)
+    ch = 1 if src.ndim == 2 else src.shape[2]
+    dx = np.empty(src.shape, np.int16)
+    dy = np.empty(src.shape, np.int16)
+    lib().orc_prim_sobel3(_p(src), src.shape[0], src.shape[1], ch, _p(dx), _p(dy))
+    return dx, dy
+
+
+def prim_phase_deg(x, y):
+    x = np.ascontiguousarray(x, np.float32)
+    y = np.ascontiguousarray(y, np.float32)
+    out = np.empty_like(x)
+    lib().orc_prim_phase_deg(_p(x), _p(y), x.size, _p(out))
+    return out
+
+
+def prim_pyrdown(src):
+    src = np.ascontiguousarray(src)
+    ch = 1 if src.ndim == 2 else src.shape[2]
+    shp = (src.shape[0] // 2, src.shape[1] // 2) + ((ch,) if src.ndim == 3 else ())
+    dst = np.empty(shp, np.uint8)
+    lib().orc_prim_pyrdown(_p(src), src.shape[0], src.shape[1], ch, _p(dst))
+    return dst
+
+
+def prim_nn_half(src):
+    src = np.ascontiguousarray(src)
+    dst = np.empty((src.shape[0] // 2, src.shape[1] // 2), np.uint8)
+    lib().orc_prim_nn_half(_p(src), src.shape[0], src.shape[1], _p(dst))
+    return dst
+
+
+def prim_median5(src):
+    src = np.ascontiguousarray(src)
+    dst = np.empty_like(src)
+    lib().orc_prim_median5(_p(src), src.shape[0], src.shape[1], _p(dst))
+    return dst
+
+
+def prim_erode3(src, iterations=1):
+    src = np.ascontiguousarray(src)
+    dst = np.empty_like(src)
+    lib().orc_prim_erode3(_p(src), src.shape[0], src.shape[1], iterations, _p(dst))
+    return dst
+
+
+def prim_distance_c3(src):
+    src = np.ascontiguousarray(src)
+    dst = np.empty(src.shape, np.float32)
+    lib().orc_prim_distance_c3(_p(src), src.shape[0], src.shape[1], _p(dst))
+    return dst
+
+
+def prim_cg_quantize(bgr, weak=10.0):
+    bgr = np.ascontiguousarray(bgr)
+    r, c = bgr.shape[:2]
+    mag = np.empty((r, c), np.float32)
+    q = np.empty((r, c), np.uint8)
+    ang = np.empty((r, c), np.float32)
+    lib().orc_prim_cg_quantize(_p(bgr), r, c, float(weak), _p(mag), _p(q), _p(ang))
+    return mag, q, ang
+
+
+def prim_spread(src, T):
+    src = np.ascontiguousarray(src)
+    dst = np.empty_like(src)
+    lib().orc_prim_spread(_p(src), src.shape[0], src.shape[1], T, _p(dst))
+    return dst
