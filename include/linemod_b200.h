@@ -1,0 +1,221 @@
+/*
+ * linemod_b200.h -- C ABI of the B200-native LINEMOD matcher (liblinemod_b200.so).
+ *
+ * Drop-in boundary for the one call the reference ROS package makes into its matcher,
+ *     rgbdDetector::linemod_detection -> cv::linemod::Detector::match      /root/reference/src/rgbdDetector.cpp:31-34
+ * plus the Detector calls around it (construction, addTemplate, read/readClass, write/writeClass, getTemplates,
+ * classIds).  Every entry point below names the reference call site it replaces.  Plain pointers and sizes only;
+ * images are borrowed host memory described by lm_image (rows may be strided, exactly like the cropped ROI
+ * `mat_rgb(crop)` the service passes, src/linemod_ensenso_detect_3_mult_detect_service.cpp:324-326).
+ *
+ * All compute runs in hand-written sm_100a CUDA kernels; there is no CPU fallback: lm_create fails with
+ * LM_E_CUDA when no CUDA device is usable.
+ *
+ * Error convention: functions return LM_OK (0) or a negative LM_E_* code; the message of the last failure on the
+ * calling thread is lm_last_error().  (The reference's OpenCV raises cv::Exception from CV_Assert at the same
+ * conditions; the C++ facade include/linemod_b200.hpp rethrows.)
+ *
+ * Threading: one CUDA stream + workspace per lm_detector.  Calls on one handle must be serialised by the caller;
+ * distinct handles are independent.
+ */
+#ifndef LINEMOD_B200_H_
+#define LINEMOD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LM_OK 0
+#define LM_E_INVALID (-1)   /* bad argument / violated CV_Assert-style precondition */
+#define LM_E_CUDA (-2)      /* CUDA runtime failure or no device */
+#define LM_E_IO (-3)        /* file could not be read / written / parsed */
+#define LM_E_NOTFOUND (-4)  /* unknown class id / template id */
+#define LM_E_STATE (-5)     /* call sequence error (e.g. debug fetch before any match) */
+
+#define LM_MAX_MODALITIES 4
+#define LM_MAX_LEVELS 4
+#define LM_MAX_FEATURES 63 /* per template, modality and level: u8 accumulation of responses <= 4 stays exact */
+
+/* lm_image.type */
+#define LM_8UC3 0  /* BGR, ColorGradient source */
+#define LM_16UC1 1 /* depth in mm, DepthNormal source */
+#define LM_8UC1 2  /* mask (non-zero = keep) / quantised image */
+
+/* lm_modality_desc.type */
+#define LM_COLOR_GRADIENT 0
+#define LM_DEPTH_NORMAL 1
+
+typedef struct lm_detector lm_detector;
+
+typedef struct {
+  const void* data; /* host memory, caller-owned, borrowed for the duration of the call */
+  int32_t rows, cols, type;
+  size_t step; /* bytes between rows */
+} lm_image;
+
+typedef struct {
+  void* data; /* host memory, caller-owned, written by the library */
+  int32_t rows, cols, type;
+  size_t step;
+} lm_image_out;
+
+/* cv::linemod::ColorGradient(weak_threshold, num_features, strong_threshold) /
+ * cv::linemod::DepthNormal(distance_threshold, difference_threshold, num_features, extract_threshold);
+ * defaults as default-constructed at /root/reference/src/renderer.cpp:180-181. */
+typedef struct {
+  int32_t type;
+  float weak_threshold;   /* CG, default 10 */
+  float strong_threshold; /* CG, default 55 */
+  int32_t distance_threshold;   /* DN, default 2000 */
+  int32_t difference_threshold; /* DN, default 50 */
+  int32_t extract_threshold;    /* DN, default 2 */
+  int32_t num_features;         /* both, default 63 */
+} lm_modality_desc;
+
+/* cv::linemod::Match {x, y, similarity, class_id, template_id}; class_index indexes lm_class_id() (std::map order) */
+typedef struct {
+  int32_t x, y, template_id, class_index;
+  float similarity;
+} lm_match_rec;
+
+typedef struct {
+  int32_t x, y, width, height;
+} lm_rect;
+
+/* cv::linemod::Template header {width, height, pyramid_level} + feature count; features are (x, y, label) int triples */
+typedef struct {
+  int32_t width, height, pyramid_level, num_features;
+} lm_template_hdr;
+
+/* ------------------------------------------------------------------------------------------------ lifecycle */
+/* cv::linemod::Detector(modalities, T_pyramid)                       /root/reference/src/renderer.cpp:179-185 */
+int lm_create(const int32_t* T, int levels, const lm_modality_desc* mods, int M, lm_detector** out);
+/* readLinemod(): Detector::read(fs.root()) + readClass per "classes" entry   src/rgbdDetector.cpp:1668-1680 */
+int lm_create_from_yaml(const char* path, lm_detector** out);
+/* writeLinemod(): Detector::write + writeClass per class into one file       src/renderer.cpp:56-70 */
+int lm_write_yaml(const lm_detector* det, const char* path);
+/* Detector::readClasses(class_ids, format) / writeClasses(format), format default "templates_%s.yml.gz" */
+int lm_read_classes(lm_detector* det, const char* const* class_ids, int n_ids, const char* format);
+int lm_write_classes(const lm_detector* det, const char* format);
+void lm_destroy(lm_detector* det);
+const char* lm_last_error(void);
+/* Page-locked host memory for frames: lm_match copies such images to the device asynchronously without staging. */
+void* lm_alloc_pinned(size_t bytes);
+void lm_free_pinned(void* p);
+/* CUDA device the handle computes on (default: current device at lm_create) */
+int lm_device(const lm_detector* det);
+
+/* ------------------------------------------------------------------------------------------------ introspection */
+int lm_pyramid_levels(const lm_detector* det);                       /* Detector::pyramidLevels */
+int lm_get_T(const lm_detector* det, int level);                     /* Detector::getT */
+int lm_num_modalities(const lm_detector* det);                       /* Detector::getModalities().size() */
+int lm_get_modality(const lm_detector* det, int m, lm_modality_desc* out);
+int lm_num_classes(const lm_detector* det);                          /* Detector::numClasses */
+int lm_num_templates(const lm_detector* det, const char* class_id);  /* Detector::numTemplates([class_id]); NULL = all */
+const char* lm_class_id(const lm_detector* det, int class_index);    /* Detector::classIds()[i]   carmine_detect.cpp:319 */
+
+/* Detector::getTemplates(class_id, template_id)   ..._service.cpp:351,741-744.  hdr receives L*M headers (index
+ * l*M+m); feats (nullable) receives all (x,y,label) triples in the same order.  Returns the total feature count. */
+int lm_get_templates(const lm_detector* det, const char* class_id, int template_id, lm_template_hdr* hdr, int32_t* feats);
+
+/* ------------------------------------------------------------------------------------------------ training */
+/* Detector::addTemplate(sources, class_id, object_mask, &bounding_box)       src/renderer.cpp:308
+ * Quantisation runs on the GPU; feature selection (stable sort + scattered selection) on the host.
+ * Returns the new template_id (>= 0), -1 when some level lacks candidate features (not an error), < -1 = LM_E_* - 100. */
+int lm_add_template(lm_detector* det, const lm_image* sources, int n_sources, const char* class_id,
+                    const lm_image* object_mask /*nullable*/, lm_rect* bounding_box /*nullable*/);
+/* Host half of addTemplate on quantised maps the caller already holds (what the CUDA front end produces and
+ * lm_add_template downloads): quantized[l*M+m] is the level's LM_8UC1 quantisation, magnitudes[l*M+m] the f32
+ * gradient magnitude (ColorGradient entries only, tightly packed).  Runs extractTemplate / cropTemplates
+ * ([OCV] ColorGradientPyramid::extractTemplate, DepthNormalPyramid::extractTemplate).  No CUDA needed. */
+int lm_add_template_from_quantized(lm_detector* det, const lm_image* quantized, const float* const* magnitudes,
+                                   const char* class_id, const lm_image* object_mask /*nullable*/,
+                                   lm_rect* bounding_box /*nullable*/);
+/* Detector::addSyntheticTemplate(templates, class_id).  n_templates must be levels*M.  Returns template_id or LM_E_*. */
+int lm_add_synthetic_template(lm_detector* det, const char* class_id, int n_templates, const lm_template_hdr* hdr,
+                              const int32_t* feats);
+
+/* ------------------------------------------------------------------------------------------------ matching */
+/* Detector::match(sources, threshold, matches, class_ids, quantized_images, masks)   src/rgbdDetector.cpp:33
+ *   class_ids/n_ids   : empty = all classes in std::map order
+ *   masks/n_masks     : 0 or n_sources images (LM_8UC1)
+ *   quantized_out     : nullable; levels*M caller-allocated LM_8UC1 images (index l*M+m) of the level's size
+ *   out_matches/out_n : library-allocated, release with lm_free_matches
+ * Blocking; sorted and de-duplicated exactly like the reference (std::sort + std::unique on Match). */
+int lm_match(lm_detector* det, const lm_image* sources, int n_sources, float threshold, const char* const* class_ids,
+             int n_ids, const lm_image* masks, int n_masks, lm_image_out* quantized_out, lm_match_rec** out_matches,
+             size_t* out_n);
+/* The same over a batch of frames (sources[f*n_sources + m]); frames are pipelined over internal streams so that the
+ * host->device copy of frame f+1 overlaps the kernels of frame f.  out_offsets receives n_frames+1 prefix offsets
+ * into out_matches. */
+int lm_match_batch(lm_detector* det, const lm_image* sources, int n_frames, int n_sources, float threshold,
+                   const char* const* class_ids, int n_ids, lm_match_rec** out_matches, size_t* out_offsets);
+void lm_free_matches(lm_match_rec* matches);
+
+/* Device-resident variant for multi-GPU sharding and for callers that already hold the frame in HBM:
+ * sources are DEVICE pointers (tightly packed rows), work is enqueued on `stream` (a cudaStream_t) and nothing is
+ * synchronised.  The un-ordered survivor records stay in device memory: *d_records points at a header
+ * {uint32 count, uint32 capacity, uint32 overflow, uint32 pad} followed by `capacity` lm_raw_match records.
+ * lm_finalize_raw() (host) turns downloaded raw records (possibly concatenated from several template shards) into
+ * the reference's sorted / de-duplicated match list. */
+typedef struct {
+  uint32_t order_key; /* position of the template in the canonical (class, template_id) iteration order */
+  uint32_t coarse_pos; /* raster index r*W+c of the coarse candidate at the lowest pyramid level */
+  int32_t x, y;        /* position after local refinement */
+  uint32_t score;      /* raw integer similarity of the last evaluated level */
+  uint32_t nf;         /* number of features behind `score` (similarity = score*100/(4*nf) [+0.5 if levels==1]) */
+  int32_t template_id, class_index;
+} lm_raw_match;
+
+int lm_match_device(lm_detector* det, const void* const* d_sources, int n_sources, int rows, int cols, float threshold,
+                    const char* const* class_ids, int n_ids, void* stream, const void** d_records,
+                    size_t* record_bytes_capacity);
+int lm_finalize_raw(const lm_detector* det, const lm_raw_match* raw, size_t n_raw, lm_match_rec** out_matches,
+                    size_t* out_n);
+/* Template sharding (north-star multi-GPU layout): keep only templates whose canonical order index i satisfies
+ * i % world == rank on this handle; template_id / class_index / order_key stay global. */
+int lm_set_shard(lm_detector* det, int rank, int world);
+
+/* ------------------------------------------------------------------------------------------------ data tables */
+/* SIMILARITY_LUT[256] ([OCV] linemod.cpp) and NORMAL_LUT[20][20][20] ([OCV] normal_lut.i) are data, not code: both
+ * are recalled / regenerated here (DESIGN.md "LUTs"), so both are injectable.  Similarity entries must be <= 4. */
+int lm_set_similarity_lut(lm_detector* det, const uint8_t lut[256]);
+int lm_get_similarity_lut(const lm_detector* det, uint8_t lut[256]);
+int lm_set_normal_lut(lm_detector* det, const uint8_t lut[8000]);
+int lm_get_normal_lut(const lm_detector* det, uint8_t lut[8000]);
+
+/* ------------------------------------------------------------------------------------------------ parity taps */
+#define LM_STAGE_QUANTIZED 0 /* u8 [rows][cols], after mask                      (QuantizedPyramid::quantize) */
+#define LM_STAGE_SPREAD 1    /* u8 [rows][cols]                                  (spread) */
+#define LM_STAGE_RESPONSE 2  /* u8 [8][rows][cols]                               (computeResponseMaps) */
+#define LM_STAGE_LINEAR 3    /* u8 [8][plane_stride]                             (linearize, flat + zero tail) */
+#define LM_STAGE_MAGNITUDE 4 /* f32 [rows][cols], ColorGradient only             (quantizedOrientations) */
+#define LM_STAGE_QUANT_RAW 5 /* u8 [rows][cols], before mask */
+/* Copies a stage of the LAST lm_match / lm_build_front call to host memory. dst NULL = size query. Returns bytes. */
+long lm_debug_fetch(lm_detector* det, int stage, int level, int modality, void* dst);
+/* Front end only (quantise -> spread -> response -> linearize) without matching. */
+int lm_build_front(lm_detector* det, const lm_image* sources, int n_sources, const lm_image* masks, int n_masks);
+/* rows, cols, T, W, H of a level and the byte stride between orientation planes in LM_STAGE_LINEAR. */
+int lm_level_geometry(lm_detector* det, int level, int32_t out[5], size_t* plane_stride);
+/* Coarse u16 similarity map [H][W] of one template against the last front end (matchClass before thresholding). */
+int lm_debug_coarse_map(lm_detector* det, const char* class_id, int template_id, uint16_t* dst);
+/* Raw (unsorted, order-restored) matches of the last lm_match call, i.e. the list handed to std::sort. */
+long lm_debug_presort(lm_detector* det, lm_match_rec* dst /*nullable*/);
+
+/* ------------------------------------------------------------------------------------------------ measurement */
+/* Device time (ms, CUDA events on the detector's stream) of the stages of the LAST lm_match call:
+ * [0] H2D, [1] front end, [2] coarse similarity, [3] local refinement, [4] D2H; and kernel launches it made. */
+int lm_last_timings(const lm_detector* det, float ms[5], int* kernel_launches);
+/* Algorithmic bytes of the last match: [0] B_front [1] B_coarse [2] B_refine [3] B_out,
+ * and [4] coarse candidates, [5] template*position evals. */
+int lm_last_work(const lm_detector* det, uint64_t out[6]);
+/* Selects the coarse-similarity kernel variant (0 = default).  For A/B measurements in bench.py only. */
+int lm_set_option(lm_detector* det, const char* key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LINEMOD_B200_H_ */

@@ -1,0 +1,165 @@
+"""ctypes view of the C ABI in include/linemod_b200.h (liblinemod_b200.so, built in-tree by csrc/Makefile).
+
+This is the binding a maintainer of the reference would write for a Python caller; the C++ caller's binding is the
+header-only facade include/linemod_b200.hpp.  There is no fallback: if the shared library is
+missing the import fails loudly, and lm_create fails when no CUDA device is usable.
+"""
+import ctypes as C
+import os
+import weakref
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "liblinemod_b200.so")
+
+LM_OK, LM_E_INVALID, LM_E_CUDA, LM_E_IO, LM_E_NOTFOUND, LM_E_STATE = 0, -1, -2, -3, -4, -5
+LM_8UC3, LM_16UC1, LM_8UC1 = 0, 1, 2
+LM_COLOR_GRADIENT, LM_DEPTH_NORMAL = 0, 1
+LM_MAX_MODALITIES, LM_MAX_LEVELS, LM_MAX_FEATURES = 4, 4, 63
+
+
+class LmImage(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("rows", C.c_int32), ("cols", C.c_int32), ("type", C.c_int32),
+                ("step", C.c_size_t)]
+
+
+class LmModalityDesc(C.Structure):
+    _fields_ = [("type", C.c_int32), ("weak_threshold", C.c_float), ("strong_threshold", C.c_float),
+                ("distance_threshold", C.c_int32), ("difference_threshold", C.c_int32),
+                ("extract_threshold", C.c_int32), ("num_features", C.c_int32)]
+
+
+class LmRect(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("width", C.c_int32), ("height", C.c_int32)]
+
+
+MATCH_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("template_id", "<i4"), ("class_index", "<i4"),
+                        ("similarity", "<f4")])
+RAW_DTYPE = np.dtype([("order_key", "<u4"), ("coarse_pos", "<u4"), ("x", "<i4"), ("y", "<i4"), ("score", "<u4"),
+                      ("nf", "<u4"), ("template_id", "<i4"), ("class_index", "<i4")])
+HDR_DTYPE = np.dtype([("width", "<i4"), ("height", "<i4"), ("pyramid_level", "<i4"), ("num_features", "<i4")])
+RESULT_HEADER_BYTES = 16
+
+# every symbol include/linemod_b200.h declares (checked by tests/test_capi_symbols.py)
+EXPORTS = [
+    "lm_create", "lm_create_from_yaml", "lm_write_yaml", "lm_read_classes", "lm_write_classes", "lm_destroy",
+    "lm_last_error", "lm_alloc_pinned", "lm_free_pinned", "lm_device", "lm_pyramid_levels", "lm_get_T",
+    "lm_num_modalities", "lm_get_modality", "lm_num_classes", "lm_num_templates", "lm_class_id", "lm_get_templates",
+    "lm_add_template", "lm_add_template_from_quantized", "lm_add_synthetic_template", "lm_match", "lm_match_batch", "lm_free_matches",
+    "lm_match_device", "lm_finalize_raw", "lm_set_shard", "lm_set_similarity_lut", "lm_get_similarity_lut",
+    "lm_set_normal_lut", "lm_get_normal_lut", "lm_debug_fetch", "lm_build_front", "lm_level_geometry",
+    "lm_debug_coarse_map", "lm_debug_presort", "lm_last_timings", "lm_last_work", "lm_set_option",
+]
+
+_lib = None
+
+
+class LinemodError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("linemod_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+def lib():
+    """Loads liblinemod_b200.so.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: build it with `make -C %s` (or __graft_entry__.build()); "
+                          "there is no CPU fallback" % (LIB_PATH, os.path.join(_PKG, "csrc")))
+    L = C.CDLL(LIB_PATH)
+    vp, ci, cp = C.c_void_p, C.c_int, C.c_char_p
+    L.lm_create.argtypes = [C.POINTER(C.c_int32), ci, C.POINTER(LmModalityDesc), ci, C.POINTER(vp)]
+    L.lm_create_from_yaml.argtypes = [cp, C.POINTER(vp)]
+    L.lm_write_yaml.argtypes = [vp, cp]
+    L.lm_read_classes.argtypes = [vp, C.POINTER(cp), ci, cp]
+    L.lm_write_classes.argtypes = [vp, cp]
+    L.lm_destroy.argtypes = [vp]
+    L.lm_destroy.restype = None
+    L.lm_last_error.restype = cp
+    L.lm_alloc_pinned.argtypes = [C.c_size_t]
+    L.lm_alloc_pinned.restype = vp
+    L.lm_free_pinned.argtypes = [vp]
+    L.lm_free_pinned.restype = None
+    for n in ("lm_device", "lm_pyramid_levels", "lm_num_modalities", "lm_num_classes"):
+        getattr(L, n).argtypes = [vp]
+    L.lm_get_T.argtypes = [vp, ci]
+    L.lm_get_modality.argtypes = [vp, ci, C.POINTER(LmModalityDesc)]
+    L.lm_num_templates.argtypes = [vp, cp]
+    L.lm_class_id.argtypes = [vp, ci]
+    L.lm_class_id.restype = cp
+    L.lm_get_templates.argtypes = [vp, cp, ci, vp, vp]
+    L.lm_add_template.argtypes = [vp, C.POINTER(LmImage), ci, cp, C.POINTER(LmImage), C.POINTER(LmRect)]
+    L.lm_add_template_from_quantized.argtypes = [vp, C.POINTER(LmImage), C.POINTER(vp), cp, C.POINTER(LmImage),
+                                                 C.POINTER(LmRect)]
+    L.lm_add_synthetic_template.argtypes = [vp, cp, ci, vp, vp]
+    L.lm_match.argtypes = [vp, C.POINTER(LmImage), ci, C.c_float, C.POINTER(cp), ci, C.POINTER(LmImage), ci,
+                           C.POINTER(LmImage), C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.lm_match_batch.argtypes = [vp, C.POINTER(LmImage), ci, ci, C.c_float, C.POINTER(cp), ci, C.POINTER(vp),
+                                 C.POINTER(C.c_size_t)]
+    L.lm_free_matches.argtypes = [vp]
+    L.lm_free_matches.restype = None
+    L.lm_match_device.argtypes = [vp, C.POINTER(vp), ci, ci, ci, C.c_float, C.POINTER(cp), ci, vp, C.POINTER(vp),
+                                  C.POINTER(C.c_size_t)]
+    L.lm_finalize_raw.argtypes = [vp, vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.lm_set_shard.argtypes = [vp, ci, ci]
+    for n in ("lm_set_similarity_lut", "lm_get_similarity_lut", "lm_set_normal_lut", "lm_get_normal_lut"):
+        getattr(L, n).argtypes = [vp, vp]
+    L.lm_debug_fetch.argtypes = [vp, ci, ci, ci, vp]
+    L.lm_debug_fetch.restype = C.c_long
+    L.lm_build_front.argtypes = [vp, C.POINTER(LmImage), ci, C.POINTER(LmImage), ci]
+    L.lm_level_geometry.argtypes = [vp, ci, C.POINTER(C.c_int32), C.POINTER(C.c_size_t)]
+    L.lm_debug_coarse_map.argtypes = [vp, cp, ci, vp]
+    L.lm_debug_presort.argtypes = [vp, vp]
+    L.lm_debug_presort.restype = C.c_long
+    L.lm_last_timings.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(ci)]
+    L.lm_last_work.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.lm_set_option.argtypes = [vp, cp, ci]
+    _lib = L
+    return L
+
+
+def last_error():
+    return lib().lm_last_error().decode(errors="replace")
+
+
+def check(rc):
+    if rc < 0:
+        raise LinemodError(rc, last_error())
+    return rc
+
+
+def image(a):
+    """numpy array -> (LmImage, keepalive).  Rows may be strided (an ROI view); pixels within a row must be packed."""
+    if a.dtype == np.uint8 and a.ndim == 3 and a.shape[2] == 3:
+        t, px = LM_8UC3, 3
+    elif a.dtype == np.uint16 and a.ndim == 2:
+        t, px = LM_16UC1, 2
+    elif a.dtype == np.uint8 and a.ndim == 2:
+        t, px = LM_8UC1, 1
+    else:
+        raise TypeError("unsupported image dtype/shape %s %s" % (a.dtype, a.shape))
+    if a.strides[1] != px or (a.ndim == 3 and a.strides[2] != 1) or a.strides[0] < a.shape[1] * px:
+        a = np.ascontiguousarray(a)
+    return LmImage(a.ctypes.data, a.shape[0], a.shape[1], t, a.strides[0]), a
+
+
+def image_array(images):
+    keep = [image(a) for a in images]
+    arr = (LmImage * max(1, len(keep)))(*[k[0] for k in keep])
+    return arr, keep
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked memory from lm_alloc_pinned (freed when the array is collected)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = lib().lm_alloc_pinned(n)
+    if not p:
+        raise MemoryError("lm_alloc_pinned(%d) failed: %s" % (n, last_error()))
+    buf = (C.c_uint8 * n).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    weakref.finalize(buf, lib().lm_free_pinned, p)
+    return arr

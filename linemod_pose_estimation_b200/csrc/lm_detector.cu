@@ -1,0 +1,1300 @@
+// lm_detector.cu -- host orchestration behind the C ABI (include/linemod_b200.h): workspaces, template packing,
+// the per-frame kernel sequence of Detector::match and the match-list finalisation.
+//
+// Reference surface mirrored: cv::linemod::Detector as driven by /root/reference/src/rgbdDetector.cpp:31-34 (match),
+// src/renderer.cpp:179-185,308 (construction, addTemplate), src/rgbdDetector.cpp:1668-1680 / src/renderer.cpp:56-70
+// (persistence).  Everything that touches pixels runs in the CUDA kernels of lm_frontend.cu / lm_match.cu; the host
+// only stages buffers, packs template records and orders the (few) surviving matches.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "lm_host.hpp"
+#include "lm_kernels.cuh"
+
+using namespace lm;
+using namespace lmk;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) return fail(LM_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                       __FILE__, __LINE__);                                               \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ buffers
+struct DevBuf {  // grow-only device allocation
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes, bool* grew = nullptr) {
+    if (grew) *grew = false;
+    if (bytes <= cap) return LM_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    CU(cudaMalloc(&p, want));
+    cap = want;
+    if (grew) *grew = true;
+    return LM_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf {  // grow-only page-locked host allocation
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return LM_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    CU(cudaMallocHost(&p, bytes + 256));
+    cap = bytes + 256;
+    return LM_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct LevelGeom {
+  int rows = 0, cols = 0, T = 0, W = 0, H = 0;
+  size_t plane_stride = 0;
+};
+static size_t plane_stride_of(int T, int W, int H) {
+  size_t wh = (size_t)W * H;
+  return ((size_t)T * T * wh + wh + 16 * (size_t)W + 16 + 15) & ~(size_t)15;  // same rule as the oracle (App. D-2)
+}
+static const size_t kLmSlack = 8192;  // tail slack: vector loads of partially filled passes may over-read
+
+// One in-flight frame: stream, events, device workspace, pinned staging.
+struct Lane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int rows = 0, cols = 0;     // geometry of the quantisation workspace
+  bool lm_ready = false;      // LM buffers sized + zero-tailed for (rows, cols)
+  bool front_valid = false;
+  bool debug_taps_written = false;
+  std::vector<LevelGeom> geom;
+  // per modality
+  DevBuf src[LM_MAX_MODALITIES];       // level-0 source (BGR / depth)
+  const void* src_ptr[LM_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr};  // own buffer or caller's device ptr
+  DevBuf mask0[LM_MAX_MODALITIES];
+  bool has_mask[LM_MAX_MODALITIES] = {false, false, false, false};
+  // per (level, modality)
+  DevBuf bgr[LM_MAX_LEVELS][LM_MAX_MODALITIES];       // CG pyramid sources for level >= 1
+  DevBuf smoothed[LM_MAX_MODALITIES], qunf[LM_MAX_MODALITIES], dn_raw[LM_MAX_MODALITIES];  // scratch, reused per level
+  DevBuf mag[LM_MAX_LEVELS][LM_MAX_MODALITIES];
+  DevBuf quant_raw[LM_MAX_LEVELS][LM_MAX_MODALITIES];
+  DevBuf quantized[LM_MAX_LEVELS][LM_MAX_MODALITIES];
+  DevBuf spread[LM_MAX_LEVELS][LM_MAX_MODALITIES], response[LM_MAX_LEVELS][LM_MAX_MODALITIES];  // parity taps only
+  DevBuf lmem[LM_MAX_LEVELS];                          // [M][8][plane_stride] + slack
+  // matching
+  DevBuf cand, result, raw_thr, work, work_order, dump;
+  uint32_t cand_cap = 0, out_cap = 0;
+  PinBuf stage_in, stage_out, stage_small;
+  // last-call bookkeeping
+  float ms[5] = {0, 0, 0, 0, 0};
+  int launches = 0;
+  uint64_t work_stats[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<lm_match_rec> presort;
+
+  int init() {
+    CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 6; ++i) CU(cudaEventCreate(&ev[i]));
+    return LM_OK;
+  }
+  void destroy() {
+    for (int m = 0; m < LM_MAX_MODALITIES; ++m) {
+      src[m].release(); mask0[m].release(); smoothed[m].release(); qunf[m].release(); dn_raw[m].release();
+      for (int l = 0; l < LM_MAX_LEVELS; ++l) {
+        bgr[l][m].release(); mag[l][m].release(); quant_raw[l][m].release(); quantized[l][m].release();
+        spread[l][m].release(); response[l][m].release();
+      }
+    }
+    for (int l = 0; l < LM_MAX_LEVELS; ++l) lmem[l].release();
+    cand.release(); result.release(); raw_thr.release(); work.release(); work_order.release(); dump.release();
+    stage_in.release(); stage_out.release(); stage_small.release();
+    for (int i = 0; i < 6; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+// Device-resident template records for one frame geometry.
+struct Pack {
+  uint64_t version = 0;
+  int rows = 0, cols = 0, shard_rank = 0, shard_world = 1;
+  int n = 0;        // templates on this shard
+  int max_P = 0;
+  DevBuf ctpl, foff, work_all, order_all;
+  DevBuf rtpl[LM_MAX_LEVELS], rfeats[LM_MAX_LEVELS];
+  std::vector<CoarseTpl> h_ctpl;
+  std::vector<uint64_t> coarse_bytes;   // per template: in-bounds features x positions (B_coarse)
+  uint64_t coarse_bytes_all = 0;
+  uint64_t refine_bytes_per_cand = 0;   // approximate (first template); exact per candidate is computed at finalise
+  std::vector<uint32_t> refine_nf;      // per template: sum over refine levels of features (x256 = bytes / candidate)
+  struct ClassRange { std::string id; int class_index; std::vector<uint32_t> local; std::vector<uint32_t> global_pos; };
+  std::vector<ClassRange> classes;      // canonical order
+  void release() {
+    ctpl.release(); foff.release(); work_all.release(); order_all.release();
+    for (int l = 0; l < LM_MAX_LEVELS; ++l) { rtpl[l].release(); rfeats[l].release(); }
+  }
+};
+
+struct lm_detector {
+  HostModel model;
+  int device = -1;
+  bool cuda_ready = false;
+  uint8_t sim_lut[256];
+  uint8_t normal_lut[8000];
+  DevBuf d_resp_all, d_normal_lut;
+  bool luts_dirty = true;
+  Lane lane[2];
+  Pack pack;
+  int shard_rank = 0, shard_world = 1;
+  int debug_taps = 0, coarse_variant = 0, timing = 1;
+  std::vector<std::string> class_id_cache;
+};
+
+// ------------------------------------------------------------------------------------------------ LUT defaults
+// SIMILARITY_LUT ([OCV] linemod.cpp): LUT[32*i + 16*h + v] = max over set bits b of v of max(0, 4 - |i - (4h+b)|).
+static void default_similarity_lut(uint8_t* lut) {
+  for (int i = 0; i < 8; ++i)
+    for (int h = 0; h < 2; ++h)
+      for (int v = 0; v < 16; ++v) {
+        int best = 0;
+        for (int b = 0; b < 4; ++b)
+          if (v & (1 << b)) best = std::max(best, std::max(0, 4 - std::abs(i - (4 * h + b))));
+        lut[32 * i + 16 * h + v] = (uint8_t)best;
+      }
+}
+// NORMAL_LUT stand-in ([OCV] normal_lut.i is not recoverable): 8 azimuthal sectors of (v1-10, v2-10).
+static void default_normal_lut(uint8_t* lut) {
+  for (int v3 = 0; v3 < 20; ++v3)
+    for (int v2 = 0; v2 < 20; ++v2)
+      for (int v1 = 0; v1 < 20; ++v1) {
+        double ang = std::atan2((double)(v2 - 10), (double)(v1 - 10)) * 180.0 / 3.14159265358979323846;
+        int s = (int)std::lround(ang / 45.0);
+        s = ((s % 8) + 8) % 8;
+        lut[(v3 * 20 + v2) * 20 + v1] = (uint8_t)(1 << s);
+      }
+}
+
+static int upload_luts(lm_detector* d) {
+  if (!d->luts_dirty) return LM_OK;
+  uint32_t resp_all[256];
+  for (int v = 0; v < 256; ++v) {
+    uint32_t packed = 0;
+    for (int ori = 0; ori < 8; ++ori) {
+      uint8_t r = std::max(d->sim_lut[32 * ori + (v & 15)], d->sim_lut[32 * ori + 16 + (v >> 4)]);
+      packed |= (uint32_t)r << (4 * ori);
+    }
+    resp_all[v] = packed;
+  }
+  if (d->d_resp_all.ensure(sizeof(resp_all)) != LM_OK) return LM_E_CUDA;
+  if (d->d_normal_lut.ensure(8000) != LM_OK) return LM_E_CUDA;
+  CU(cudaMemcpy(d->d_resp_all.p, resp_all, sizeof(resp_all), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d->d_normal_lut.p, d->normal_lut, 8000, cudaMemcpyHostToDevice));
+  d->luts_dirty = false;
+  for (int i = 0; i < 2; ++i) d->lane[i].front_valid = false;
+  return LM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+static size_t src_row_bytes(int type, int cols) { return type == LM_8UC3 ? (size_t)cols * 3 : (type == LM_16UC1 ? (size_t)cols * 2 : (size_t)cols); }
+static int expected_src_type(const lm_modality_desc& m) { return m.type == LM_COLOR_GRADIENT ? LM_8UC3 : LM_16UC1; }
+
+// Buffers needed by quantisation at (rows, cols); no divisibility requirements (addTemplate uses this alone).
+static int ensure_quant_ws(lm_detector* d, Lane& ln, int rows, int cols) {
+  const int L = d->model.levels(), M = d->model.M();
+  if (ln.rows != rows || ln.cols != cols) { ln.lm_ready = false; ln.front_valid = false; }
+  ln.rows = rows; ln.cols = cols;
+  for (int m = 0; m < M; ++m) {
+    const bool cg = d->model.mods[m].type == LM_COLOR_GRADIENT;
+    size_t n0 = (size_t)rows * cols;
+    if (ln.src[m].ensure(src_row_bytes(expected_src_type(d->model.mods[m]), cols) * rows) != LM_OK) return LM_E_CUDA;
+    if (cg) {
+      if (ln.smoothed[m].ensure(n0 * 3) != LM_OK || ln.qunf[m].ensure(n0) != LM_OK) return LM_E_CUDA;
+    } else if (ln.dn_raw[m].ensure(n0) != LM_OK) return LM_E_CUDA;
+    for (int l = 0; l < L; ++l) {
+      size_t n = (size_t)(rows >> l) * (cols >> l);
+      if (n == 0) return fail(LM_E_INVALID, "image too small for %d pyramid levels", L);
+      if (cg && l > 0 && ln.bgr[l][m].ensure(n * 3) != LM_OK) return LM_E_CUDA;
+      if (cg && ln.mag[l][m].ensure(n * sizeof(float)) != LM_OK) return LM_E_CUDA;
+      if (ln.quant_raw[l][m].ensure(n) != LM_OK || ln.quantized[l][m].ensure(n) != LM_OK) return LM_E_CUDA;
+    }
+  }
+  return LM_OK;
+}
+
+// Linear-memory buffers for matching at (rows, cols): enforces the reference's CV_Asserts on the geometry.
+static int ensure_lm_ws(lm_detector* d, Lane& ln, int rows, int cols) {
+  const int L = d->model.levels(), M = d->model.M();
+  if (ln.lm_ready && ln.rows == rows && ln.cols == cols && (int)ln.geom.size() == L) return LM_OK;
+  std::vector<LevelGeom> geom(L);
+  for (int l = 0; l < L; ++l) {
+    LevelGeom& g = geom[l];
+    g.rows = rows >> l; g.cols = cols >> l; g.T = d->model.T[l];
+    if (g.T < 1 || g.T > 32) return fail(LM_E_INVALID, "unsupported T=%d at level %d", g.T, l);
+    if (g.rows <= 0 || g.cols <= 0) return fail(LM_E_INVALID, "image too small for %d pyramid levels", L);
+    if (((size_t)g.rows * g.cols) % 16 != 0)
+      return fail(LM_E_INVALID, "(rows * cols) %% 16 != 0 at level %d (%dx%d)", l, g.cols, g.rows);  // computeResponseMaps
+    if (g.rows % g.T != 0 || g.cols % g.T != 0)
+      return fail(LM_E_INVALID, "rows %% T != 0 or cols %% T != 0 at level %d (%dx%d, T=%d)", l, g.cols, g.rows, g.T);  // linearize
+    if (g.cols > 4095 || g.rows > 4095) return fail(LM_E_INVALID, "images larger than 4095 px are not supported");
+    g.W = g.cols / g.T; g.H = g.rows / g.T;
+    g.plane_stride = plane_stride_of(g.T, g.W, g.H);
+  }
+  if (ensure_quant_ws(d, ln, rows, cols) != LM_OK) return LM_E_CUDA;
+  for (int l = 0; l < L; ++l) {
+    size_t bytes = (size_t)M * 8 * geom[l].plane_stride + kLmSlack;
+    if (ln.lmem[l].ensure(bytes) != LM_OK) return LM_E_CUDA;
+    CU(cudaMemsetAsync(ln.lmem[l].p, 0, ln.lmem[l].cap, ln.stream));  // zero tails (and slack) once per geometry
+  }
+  ln.geom.swap(geom);
+  ln.lm_ready = true;
+  ln.front_valid = false;
+  return LM_OK;
+}
+
+static int ensure_tap_ws(lm_detector* d, Lane& ln) {
+  const int L = d->model.levels(), M = d->model.M();
+  for (int l = 0; l < L; ++l)
+    for (int m = 0; m < M; ++m) {
+      size_t n = (size_t)ln.geom[l].rows * ln.geom[l].cols;
+      if (ln.spread[l][m].ensure(n) != LM_OK || ln.response[l][m].ensure(8 * n) != LM_OK) return LM_E_CUDA;
+    }
+  return LM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ uploads
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Host image -> tightly packed device buffer.  Pinned sources go straight to the copy engine; pageable ones are
+// packed into the lane's pinned staging area first (offset *stage_off, advanced).
+static int upload_image(Lane& ln, const lm_image& im, void* dst, size_t* stage_off) {
+  const size_t rb = src_row_bytes(im.type, im.cols);
+  const size_t total = rb * im.rows;
+  if (is_pinned(im.data)) {
+    CU(cudaMemcpy2DAsync(dst, rb, im.data, im.step, rb, im.rows, cudaMemcpyHostToDevice, ln.stream));
+    return LM_OK;
+  }
+  uint8_t* st = ln.stage_in.as<uint8_t>() + *stage_off;
+  if (im.step == rb) std::memcpy(st, im.data, total);
+  else
+    for (int y = 0; y < im.rows; ++y) std::memcpy(st + (size_t)y * rb, (const uint8_t*)im.data + (size_t)y * im.step, rb);
+  CU(cudaMemcpyAsync(dst, st, total, cudaMemcpyHostToDevice, ln.stream));
+  *stage_off += (total + 255) & ~(size_t)255;
+  return LM_OK;
+}
+
+static int check_sources(lm_detector* d, const lm_image* sources, int n_sources, const lm_image* masks, int n_masks) {
+  const int M = d->model.M();
+  if (n_sources != M) return fail(LM_E_INVALID, "sources.size() (%d) != modalities.size() (%d)", n_sources, M);
+  if (n_masks != 0 && n_masks != M) return fail(LM_E_INVALID, "masks.size() (%d) != modalities.size() (%d)", n_masks, M);
+  for (int m = 0; m < M; ++m) {
+    if (!sources[m].data) return fail(LM_E_INVALID, "source %d is empty", m);
+    if (sources[m].type != expected_src_type(d->model.mods[m]))
+      return fail(LM_E_INVALID, "source %d: %s needs a %s image", m, modality_name(d->model.mods[m].type),
+                  d->model.mods[m].type == LM_COLOR_GRADIENT ? "CV_8UC3" : "CV_16UC1");
+    if (sources[m].rows != sources[0].rows || sources[m].cols != sources[0].cols)
+      return fail(LM_E_INVALID, "sources differ in size");
+    if (sources[m].step < src_row_bytes(sources[m].type, sources[m].cols)) return fail(LM_E_INVALID, "source %d: step too small", m);
+    if (n_masks && masks[m].data) {
+      if (masks[m].type != LM_8UC1 || masks[m].rows != sources[m].rows || masks[m].cols != sources[m].cols)
+        return fail(LM_E_INVALID, "mask %d: size/type mismatch (mask.size() == source.size())", m);
+    }
+  }
+  return LM_OK;
+}
+
+static int upload_frame(lm_detector* d, Lane& ln, const lm_image* sources, const lm_image* masks, int n_masks) {
+  const int M = d->model.M();
+  size_t need = 0;
+  for (int m = 0; m < M; ++m) {
+    need += ((src_row_bytes(sources[m].type, sources[m].cols) * sources[m].rows) + 255) & ~(size_t)255;
+    if (n_masks && masks[m].data) need += (((size_t)masks[m].rows * masks[m].cols) + 255) & ~(size_t)255;
+  }
+  if (ln.stage_in.ensure(need) != LM_OK) return LM_E_CUDA;
+  size_t off = 0;
+  for (int m = 0; m < M; ++m) {
+    if (upload_image(ln, sources[m], ln.src[m].p, &off) != LM_OK) return LM_E_CUDA;
+    ln.src_ptr[m] = ln.src[m].p;
+    ln.has_mask[m] = n_masks && masks[m].data;
+    if (ln.has_mask[m]) {
+      if (ln.mask0[m].ensure((size_t)masks[m].rows * masks[m].cols) != LM_OK) return LM_E_CUDA;
+      if (upload_image(ln, masks[m], ln.mask0[m].p, &off) != LM_OK) return LM_E_CUDA;
+    }
+  }
+  return LM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ front end
+// [OCV] Modality::process + QuantizedPyramid::pyrDown for every level: fills quant_raw[l][m] (and mag[l][m]).
+static int run_quantize(lm_detector* d, Lane& ln, cudaStream_t s) {
+  const int L = d->model.levels(), M = d->model.M();
+  for (int m = 0; m < M; ++m) {
+    const lm_modality_desc& md = d->model.mods[m];
+    for (int l = 0; l < L; ++l) {
+      const int rows = ln.rows >> l, cols = ln.cols >> l;
+      if (md.type == LM_COLOR_GRADIENT) {
+        const uint8_t* src = l == 0 ? (const uint8_t*)ln.src_ptr[m] : ln.bgr[l][m].as<uint8_t>();
+        if (l > 0) {
+          const uint8_t* prev = l == 1 ? (const uint8_t*)ln.src_ptr[m] : ln.bgr[l - 1][m].as<uint8_t>();
+          launch_pyrdown_u8c3(prev, ln.rows >> (l - 1), ln.cols >> (l - 1), ln.bgr[l][m].as<uint8_t>(), s);
+          ++ln.launches;
+        }
+        launch_gauss7_u8c3(src, rows, cols, ln.smoothed[m].as<uint8_t>(), s);
+        launch_cg_grad(ln.smoothed[m].as<uint8_t>(), rows, cols, ln.mag[l][m].as<float>(), ln.qunf[m].as<uint8_t>(), s);
+        launch_cg_hysteresis(ln.qunf[m].as<uint8_t>(), ln.mag[l][m].as<float>(), rows, cols,
+                             md.weak_threshold * md.weak_threshold, ln.quant_raw[l][m].as<uint8_t>(), s);
+        ln.launches += 3;
+      } else {
+        if (l == 0) {
+          launch_dn_normals((const uint16_t*)ln.src_ptr[m], rows, cols, md.distance_threshold, md.difference_threshold,
+                            d->d_normal_lut.as<uint8_t>(), ln.dn_raw[m].as<uint8_t>(), s);
+          launch_median5_u8(ln.dn_raw[m].as<uint8_t>(), rows, cols, ln.quant_raw[0][m].as<uint8_t>(), s);
+          ln.launches += 2;
+        } else {
+          launch_nn_half_u8(ln.quant_raw[l - 1][m].as<uint8_t>(), ln.rows >> (l - 1), ln.cols >> (l - 1),
+                            ln.quant_raw[l][m].as<uint8_t>(), s);
+          ++ln.launches;
+        }
+      }
+    }
+  }
+  CU(cudaGetLastError());
+  return LM_OK;
+}
+
+// [OCV] Detector::match front half: quantize (mask) -> spread -> computeResponseMaps -> linearize per level/modality.
+static int run_front(lm_detector* d, Lane& ln, cudaStream_t s) {
+  const int L = d->model.levels(), M = d->model.M();
+  if (run_quantize(d, ln, s) != LM_OK) return LM_E_CUDA;
+  const bool taps = d->debug_taps != 0;
+  if (taps && ensure_tap_ws(d, ln) != LM_OK) return LM_E_CUDA;
+  for (int l = 0; l < L; ++l) {
+    const LevelGeom& g = ln.geom[l];
+    for (int m = 0; m < M; ++m) {
+      launch_spread_lm(ln.quant_raw[l][m].as<uint8_t>(), ln.has_mask[m] ? ln.mask0[m].as<uint8_t>() : nullptr, ln.cols, l,
+                       g.rows, g.cols, g.T, d->d_resp_all.as<uint32_t>(), ln.quantized[l][m].as<uint8_t>(),
+                       taps ? ln.spread[l][m].as<uint8_t>() : nullptr, taps ? ln.response[l][m].as<uint8_t>() : nullptr,
+                       ln.lmem[l].as<uint8_t>() + (size_t)m * 8 * g.plane_stride, g.plane_stride, s);
+      ++ln.launches;
+    }
+  }
+  CU(cudaGetLastError());
+  ln.front_valid = true;
+  ln.debug_taps_written = taps;
+  return LM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ template pack
+static int ensure_pack(lm_detector* d, const Lane& ln) {
+  Pack& pk = d->pack;
+  const HostModel& md = d->model;
+  if (pk.version == md.version && pk.rows == ln.rows && pk.cols == ln.cols && pk.shard_rank == d->shard_rank &&
+      pk.shard_world == d->shard_world)
+    return LM_OK;
+  // all lanes must be idle before the shared records are replaced
+  for (int i = 0; i < 2; ++i)
+    if (d->lane[i].stream) CU(cudaStreamSynchronize(d->lane[i].stream));
+  const int L = md.levels(), M = md.M();
+  const LevelGeom& gc = ln.geom[L - 1];
+  std::vector<CoarseTpl> ctpl;
+  std::vector<uint32_t> foff;
+  std::vector<RefineTpl> rtpl[LM_MAX_LEVELS];
+  std::vector<uint32_t> rfeats[LM_MAX_LEVELS];
+  pk.classes.clear(); pk.coarse_bytes.clear(); pk.refine_nf.clear();
+  pk.coarse_bytes_all = 0; pk.max_P = 0;
+  uint32_t canonical = 0;
+  int class_index = 0;
+  for (auto it = md.classes.begin(); it != md.classes.end(); ++it, ++class_index) {
+    Pack::ClassRange cr;
+    cr.id = it->first; cr.class_index = class_index;
+    const std::vector<TemplatePyramid>& tps = it->second;
+    for (size_t tid = 0; tid < tps.size(); ++tid, ++canonical) {
+      if ((int)(canonical % (uint32_t)d->shard_world) != d->shard_rank) continue;
+      const TemplatePyramid& tp = tps[tid];
+      if ((int)tp.size() != L * M) return fail(LM_E_INVALID, "template pyramid of class '%s' has %zu templates, expected %d", it->first.c_str(), tp.size(), L * M);
+      CoarseTpl ct;
+      std::memset(&ct, 0, sizeof(ct));
+      ct.feat_begin = (uint32_t)foff.size();
+      ct.order_key = canonical; ct.template_id = (int)tid; ct.class_index = class_index;
+      const int lowest = (L - 1) * M;
+      // [OCV] similarity(): geometry of the sliding window, from each modality's own template
+      uint64_t bytes = 0;
+      int P_all = -1;
+      for (int m = 0; m < M; ++m) {
+        const Template& t = tp[lowest + m];
+        ct.nf += (uint32_t)t.features.size();
+        int wf = (t.width - 1) / gc.T + 1, hf = (t.height - 1) / gc.T + 1;
+        int span_x = gc.W - wf, span_y = gc.H - hf;
+        int P = span_y * gc.W + span_x + 1;
+        if (P > gc.W * gc.H) P = gc.W * gc.H;
+        // cropTemplates gives every modality the same width/height, so P is shared; a hand-made pyramid that
+        // violates this is rejected rather than silently mis-scored.
+        if (m == 0) P_all = P;
+        else if (P != P_all) return fail(LM_E_INVALID, "class '%s' template %zu: modalities disagree on width/height", it->first.c_str(), tid);
+        std::vector<uint32_t> grp[4];
+        for (const Feature& f : t.features) {
+          if (f.x < 0 || f.x >= gc.cols || f.y < 0 || f.y >= gc.rows) continue;  // "Discard feature if out of bounds"
+          size_t a = (size_t)m * 8 * gc.plane_stride + (size_t)f.label * gc.plane_stride +
+                     (size_t)((f.y % gc.T) * gc.T + (f.x % gc.T)) * ((size_t)gc.W * gc.H) + (size_t)(f.y / gc.T) * gc.W + f.x / gc.T;
+          grp[(a & 15) >> 2].push_back((uint32_t)a);
+        }
+        for (int q = 0; q < 4; ++q) {
+          ct.cnt[m][q] = (uint8_t)grp[q].size();
+          foff.insert(foff.end(), grp[q].begin(), grp[q].end());
+          if (P > 0) bytes += (uint64_t)grp[q].size() * (uint64_t)P;
+        }
+      }
+      ct.P = P_all;
+      pk.max_P = std::max(pk.max_P, ct.P);
+      uint32_t rnf = 0;
+      for (int l = 0; l < L - 1; ++l) {
+        RefineTpl rt;
+        std::memset(&rt, 0, sizeof(rt));
+        rt.feat_begin = (uint32_t)rfeats[l].size();
+        rt.width = tp[l * M].width; rt.height = tp[l * M].height;
+        for (int m = 0; m < M; ++m) {
+          const Template& t = tp[l * M + m];
+          rt.cnt[m] = (uint16_t)t.features.size();
+          rt.nf += (uint32_t)t.features.size();
+          for (const Feature& f : t.features)
+            rfeats[l].push_back((uint32_t)(f.x + 4096) | ((uint32_t)(f.y + 4096) << 13) | ((uint32_t)f.label << 26));
+        }
+        rnf += rt.nf;
+        rtpl[l].push_back(rt);
+      }
+      cr.local.push_back((uint32_t)ctpl.size());
+      cr.global_pos.push_back(canonical);
+      ctpl.push_back(ct);
+      pk.coarse_bytes.push_back(bytes);
+      pk.coarse_bytes_all += bytes;
+      pk.refine_nf.push_back(rnf);
+    }
+    pk.classes.push_back(cr);
+  }
+  pk.n = (int)ctpl.size();
+  std::vector<uint32_t> work_all(pk.n), order_all(pk.n);
+  for (int i = 0; i < pk.n; ++i) { work_all[i] = (uint32_t)i; order_all[i] = ctpl[i].order_key; }
+  auto up = [&](DevBuf& b, const void* src, size_t bytes) -> int {
+    if (b.ensure(bytes + 64) != LM_OK) return LM_E_CUDA;
+    if (bytes) CU(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+    return LM_OK;
+  };
+  foff.resize(foff.size() + 8, 0);  // the 4-way unrolled loop never reads past the template, padding is for safety
+  if (up(pk.ctpl, ctpl.data(), ctpl.size() * sizeof(CoarseTpl)) != LM_OK) return LM_E_CUDA;
+  if (up(pk.foff, foff.data(), foff.size() * 4) != LM_OK) return LM_E_CUDA;
+  if (up(pk.work_all, work_all.data(), work_all.size() * 4) != LM_OK) return LM_E_CUDA;
+  if (up(pk.order_all, order_all.data(), order_all.size() * 4) != LM_OK) return LM_E_CUDA;
+  for (int l = 0; l < L - 1; ++l) {
+    if (up(pk.rtpl[l], rtpl[l].data(), rtpl[l].size() * sizeof(RefineTpl)) != LM_OK) return LM_E_CUDA;
+    if (up(pk.rfeats[l], rfeats[l].data(), rfeats[l].size() * 4) != LM_OK) return LM_E_CUDA;
+  }
+  pk.h_ctpl.swap(ctpl);
+  pk.version = md.version; pk.rows = ln.rows; pk.cols = ln.cols;
+  pk.shard_rank = d->shard_rank; pk.shard_world = d->shard_world;
+  return LM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ matching
+struct WorkList {
+  const uint32_t* d_work = nullptr;
+  const uint32_t* d_order = nullptr;
+  int n = 0;
+  uint64_t coarse_bytes = 0;
+};
+
+// [OCV] Detector::match: "if (class_ids.empty()) match all templates else only the requested class IDs" (in the
+// order requested, unknown ids skipped).
+static int build_worklist(lm_detector* d, Lane& ln, const char* const* class_ids, int n_ids, WorkList& wl) {
+  Pack& pk = d->pack;
+  if (n_ids == 0) {
+    wl.d_work = pk.work_all.as<uint32_t>(); wl.d_order = pk.order_all.as<uint32_t>();
+    wl.n = pk.n; wl.coarse_bytes = pk.coarse_bytes_all;
+    return LM_OK;
+  }
+  std::vector<uint32_t> work, order;
+  // order keys of a filtered run: position in the filtered iteration (a class may be listed more than once)
+  uint32_t base = 0;
+  for (int i = 0; i < n_ids; ++i) {
+    if (!class_ids[i]) return fail(LM_E_INVALID, "class_ids[%d] is NULL", i);
+    auto it = d->model.classes.find(class_ids[i]);
+    if (it == d->model.classes.end()) continue;
+    for (const Pack::ClassRange& cr : pk.classes)
+      if (cr.id == class_ids[i]) {
+        uint32_t first_global = 0;
+        // canonical position of this class's template 0
+        { uint32_t g = 0; for (auto jt = d->model.classes.begin(); jt != it; ++jt) g += (uint32_t)jt->second.size(); first_global = g; }
+        for (size_t k = 0; k < cr.local.size(); ++k) {
+          work.push_back(cr.local[k]);
+          order.push_back(base + (cr.global_pos[k] - first_global));
+          wl.coarse_bytes += pk.coarse_bytes[cr.local[k]];
+        }
+      }
+    base += (uint32_t)it->second.size();
+  }
+  wl.n = (int)work.size();
+  if (ln.work.ensure(work.size() * 4 + 64) != LM_OK || ln.work_order.ensure(order.size() * 4 + 64) != LM_OK) return LM_E_CUDA;
+  if (wl.n) {
+    // small, infrequent: synchronous copies keep the host vectors' lifetime trivial
+    CU(cudaMemcpyAsync(ln.work.p, work.data(), work.size() * 4, cudaMemcpyHostToDevice, ln.stream));
+    CU(cudaMemcpyAsync(ln.work_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ln.stream));
+    CU(cudaStreamSynchronize(ln.stream));
+  }
+  wl.d_work = ln.work.as<uint32_t>(); wl.d_order = ln.work_order.as<uint32_t>();
+  return LM_OK;
+}
+
+static const int kMaxNf = LM_MAX_FEATURES * LM_MAX_MODALITIES;
+static const size_t kFirstChunkRecords = 2048;  // records fetched together with the header in one D2H copy
+
+static int ensure_match_buffers(Lane& ln, uint32_t cand_cap, uint32_t out_cap) {
+  if (cand_cap > ln.cand_cap) {
+    if (ln.cand.ensure((size_t)cand_cap * sizeof(Cand)) != LM_OK) return LM_E_CUDA;
+    ln.cand_cap = cand_cap;
+  }
+  if (out_cap > ln.out_cap) {
+    if (ln.result.ensure(sizeof(ResultHeader) + (size_t)out_cap * sizeof(lm_raw_match)) != LM_OK) return LM_E_CUDA;
+    ln.out_cap = out_cap;
+  }
+  if (ln.raw_thr.ensure((kMaxNf + 1) * sizeof(int32_t)) != LM_OK) return LM_E_CUDA;
+  if (ln.stage_small.ensure(4096) != LM_OK) return LM_E_CUDA;
+  if (ln.stage_out.ensure(sizeof(ResultHeader) + (size_t)ln.out_cap * sizeof(lm_raw_match)) != LM_OK) return LM_E_CUDA;
+  return LM_OK;
+}
+
+// Enqueues coarse similarity + refinement on stream s.  The per-call scalars (raw thresholds, header reset) travel in
+// one small pinned block.
+static int enqueue_match(lm_detector* d, Lane& ln, const WorkList& wl, float threshold, cudaStream_t s,
+                         cudaEvent_t ev_mid) {
+  const HostModel& md = d->model;
+  const int L = md.levels(), M = md.M();
+  Pack& pk = d->pack;
+  // [OCV] matchClass: raw_threshold = (int)(2*nf + (threshold / 100.f) * (2*nf) + 0.5f), evaluated on the host in f32
+  uint8_t* small = ln.stage_small.as<uint8_t>();
+  ResultHeader* h = reinterpret_cast<ResultHeader*>(small);
+  h->count = 0; h->capacity = ln.out_cap; h->overflow = 0; h->n_cands = 0;
+  int32_t* thr = reinterpret_cast<int32_t*>(small + 64);
+  for (int nf = 0; nf <= kMaxNf; ++nf) thr[nf] = (int32_t)(2 * nf + (threshold / 100.f) * (2 * nf) + 0.5f);
+  CU(cudaMemcpyAsync(ln.result.p, h, sizeof(ResultHeader), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(ln.raw_thr.p, thr, (kMaxNf + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  const LevelGeom& gc = ln.geom[L - 1];
+  ResultHeader* d_hdr = ln.result.as<ResultHeader>();
+  lm_raw_match* d_out = reinterpret_cast<lm_raw_match*>(ln.result.as<uint8_t>() + sizeof(ResultHeader));
+  launch_similarity_coarse(ln.lmem[L - 1].as<uint8_t>(), pk.foff.as<uint32_t>(), pk.ctpl.as<CoarseTpl>(), wl.d_work, wl.n,
+                           pk.max_P, ln.raw_thr.as<int32_t>(), M, ln.cand.as<Cand>(), d_hdr, ln.cand_cap, nullptr, 0,
+                           d->coarse_variant, s);
+  if (wl.n > 0 && pk.max_P > 0) ++ln.launches;
+  if (ev_mid) CU(cudaEventRecord(ev_mid, s));
+  RefineParams rp;
+  std::memset(&rp, 0, sizeof(rp));
+  rp.levels = L; rp.M = M; rp.coarse_T = gc.T; rp.coarse_W = gc.W; rp.threshold = threshold;
+  for (int l = 0; l < L - 1; ++l) {
+    const LevelGeom& g = ln.geom[l];
+    rp.level[l].lm = ln.lmem[l].as<uint8_t>();
+    rp.level[l].tpl = pk.rtpl[l].as<RefineTpl>();
+    rp.level[l].feats = pk.rfeats[l].as<uint32_t>();
+    rp.level[l].plane_stride = g.plane_stride;
+    rp.level[l].rows = g.rows; rp.level[l].cols = g.cols; rp.level[l].T = g.T; rp.level[l].W = g.W;
+  }
+  launch_refine(rp, pk.ctpl.as<CoarseTpl>(), wl.d_order, ln.cand.as<Cand>(), ln.cand_cap, d_hdr, d_out, s);
+  ++ln.launches;
+  CU(cudaGetLastError());
+  return LM_OK;
+}
+
+// [OCV] Match::operator< and operator==
+static inline bool match_less(const lm_match_rec& a, const lm_match_rec& b) {
+  if (a.similarity != b.similarity) return a.similarity > b.similarity;
+  return a.template_id < b.template_id;
+}
+static inline bool match_equal(const lm_match_rec& a, const lm_match_rec& b) {
+  return a.x == b.x && a.y == b.y && a.similarity == b.similarity && a.class_index == b.class_index;
+}
+
+// Raw survivor records -> the reference's match list: restore matchClass's emission order (class iteration order,
+// template_id, coarse raster position), convert scores to percentages in f32 exactly as the reference does, then the
+// same libstdc++ std::sort + std::unique ([OCV] Detector::match tail).
+static void finalize_records(int levels, std::vector<lm_raw_match>& raw, std::vector<lm_match_rec>& presort,
+                             std::vector<lm_match_rec>& out) {
+  std::sort(raw.begin(), raw.end(), [](const lm_raw_match& a, const lm_raw_match& b) {
+    return a.order_key != b.order_key ? a.order_key < b.order_key : a.coarse_pos < b.coarse_pos;
+  });
+  presort.resize(raw.size());
+  for (size_t i = 0; i < raw.size(); ++i) {
+    const lm_raw_match& r = raw[i];
+    lm_match_rec m;
+    m.x = r.x; m.y = r.y; m.template_id = r.template_id; m.class_index = r.class_index;
+    float sim = ((int)r.score * 100.f) / (4 * (int)r.nf);
+    if (levels == 1) sim = sim + 0.5f;  // the coarse score carries +0.5f, refined scores do not (App. D-3)
+    m.similarity = sim;
+    presort[i] = m;
+  }
+  out = presort;
+  std::sort(out.begin(), out.end(), match_less);
+  out.erase(std::unique(out.begin(), out.end(), match_equal), out.end());
+}
+
+static int download_records(Lane& ln, cudaStream_t s, std::vector<lm_raw_match>& raw, bool* overflow, uint32_t* n_cands) {
+  const size_t first = std::min<size_t>(kFirstChunkRecords, ln.out_cap);
+  uint8_t* host = ln.stage_out.as<uint8_t>();
+  CU(cudaMemcpyAsync(host, ln.result.p, sizeof(ResultHeader) + first * sizeof(lm_raw_match), cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(ln.ev[5], s));
+  CU(cudaStreamSynchronize(s));
+  ResultHeader h = *reinterpret_cast<ResultHeader*>(host);
+  *overflow = h.overflow != 0 || h.count > h.capacity;
+  *n_cands = h.n_cands;
+  if (*overflow) return LM_OK;
+  if (h.count > first) {
+    CU(cudaMemcpyAsync(host + sizeof(ResultHeader) + first * sizeof(lm_raw_match),
+                       ln.result.as<uint8_t>() + sizeof(ResultHeader) + first * sizeof(lm_raw_match),
+                       (h.count - first) * sizeof(lm_raw_match), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  const lm_raw_match* recs = reinterpret_cast<const lm_raw_match*>(host + sizeof(ResultHeader));
+  raw.assign(recs, recs + h.count);
+  return LM_OK;
+}
+
+static void collect_timings(Lane& ln) {
+  for (int i = 0; i < 5; ++i) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, ln.ev[i], ln.ev[i + 1]) != cudaSuccess) { cudaGetLastError(); t = 0; }
+    ln.ms[i] = t;
+  }
+}
+
+// Matching on an already-built front end, with buffer growth + retry on overflow (exactness over speed there).
+static int match_front(lm_detector* d, Lane& ln, float threshold, const char* const* class_ids, int n_ids,
+                       std::vector<lm_match_rec>& out) {
+  int rc = ensure_pack(d, ln);
+  if (rc != LM_OK) return rc;
+  WorkList wl;
+  rc = build_worklist(d, ln, class_ids, n_ids, wl);
+  if (rc != LM_OK) return rc;
+  uint32_t cand_cap = std::max<uint32_t>(ln.cand_cap, 1u << 16), out_cap = std::max<uint32_t>(ln.out_cap, 1u << 14);
+  std::vector<lm_raw_match> raw;
+  for (int attempt = 0;; ++attempt) {
+    if (ensure_match_buffers(ln, cand_cap, out_cap) != LM_OK) return LM_E_CUDA;
+    if (attempt > 0) CU(cudaEventRecord(ln.ev[2], ln.stream));
+    if (enqueue_match(d, ln, wl, threshold, ln.stream, ln.ev[3]) != LM_OK) return LM_E_CUDA;
+    CU(cudaEventRecord(ln.ev[4], ln.stream));
+    bool overflow = false;
+    uint32_t n_cands = 0;
+    if (download_records(ln, ln.stream, raw, &overflow, &n_cands) != LM_OK) return LM_E_CUDA;
+    if (!overflow) {
+      ln.work_stats[1] = wl.coarse_bytes;
+      ln.work_stats[4] = n_cands;
+      ln.work_stats[5] = (uint64_t)wl.n * (uint64_t)(ln.geom.back().W * ln.geom.back().H);
+      break;
+    }
+    if (attempt >= 8) return fail(LM_E_CUDA, "match buffers overflowed repeatedly");
+    if (n_cands > ln.cand_cap) cand_cap = std::max<uint32_t>(n_cands + n_cands / 4, cand_cap * 2);
+    out_cap = std::max<uint32_t>(out_cap * 4, std::min<uint32_t>(n_cands + 1024, 1u << 26));
+  }
+  // B_refine: every candidate reads 256 bytes per feature of every refinement level -- survivors only
+  // would under-count, so use candidates x the mean per-template refine feature count of the work list.
+  uint64_t rsum = 0;
+  for (uint32_t v : d->pack.refine_nf) rsum += v;
+  ln.work_stats[2] = d->pack.n ? (uint64_t)((double)ln.work_stats[4] * ((double)rsum / d->pack.n) * 256.0) : 0;
+  ln.work_stats[3] = 20ull * raw.size();
+  finalize_records(d->model.levels(), raw, ln.presort, out);
+  return LM_OK;
+}
+
+static int copy_out(const std::vector<lm_match_rec>& v, lm_match_rec** out_matches, size_t* out_n) {
+  lm_match_rec* p = (lm_match_rec*)std::malloc(std::max<size_t>(1, v.size()) * sizeof(lm_match_rec));
+  if (!p) return fail(LM_E_INVALID, "out of host memory");
+  if (!v.empty()) std::memcpy(p, v.data(), v.size() * sizeof(lm_match_rec));
+  *out_matches = p; *out_n = v.size();
+  return LM_OK;
+}
+
+static int validate_template(const HostModel& md, int n_templates, const lm_template_hdr* hdr, const int32_t* feats) {
+  if (n_templates != md.levels() * md.M()) return fail(LM_E_INVALID, "template pyramid has %d templates, expected levels*modalities = %d", n_templates, md.levels() * md.M());
+  size_t k = 0;
+  for (int i = 0; i < n_templates; ++i) {
+    if (hdr[i].num_features < 0 || hdr[i].num_features > LM_MAX_FEATURES) return fail(LM_E_INVALID, "features.size() <= 63 violated (%d)", hdr[i].num_features);
+    for (int j = 0; j < hdr[i].num_features; ++j, ++k) {
+      int x = feats[3 * k], y = feats[3 * k + 1], label = feats[3 * k + 2];
+      if (label < 0 || label > 7) return fail(LM_E_INVALID, "feature label %d outside 0..7", label);
+      if (x < -4096 || x > 4095 || y < -4096 || y > 4095) return fail(LM_E_INVALID, "feature coordinate outside +-4095");
+    }
+  }
+  return LM_OK;
+}
+
+// Binds the handle to the current CUDA device on first use by a compute entry point.  Host-only calls (persistence,
+// template bookkeeping, lm_finalize_raw) never get here; everything that touches pixels does, and fails loudly when
+// no device is usable -- there is no CPU path.
+static int set_device(lm_detector* d) {
+  if (!d->cuda_ready) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      return fail(LM_E_CUDA, "no CUDA device available (%s); this library has no CPU path", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    CU(cudaGetDevice(&d->device));
+    for (int i = 0; i < 2; ++i)
+      if (d->lane[i].init() != LM_OK) return LM_E_CUDA;
+    d->cuda_ready = true;
+  }
+  CU(cudaSetDevice(d->device));
+  return LM_OK;
+}
+
+static int create_common(lm_detector* d) {
+  default_similarity_lut(d->sim_lut);
+  default_normal_lut(d->normal_lut);
+  d->luts_dirty = true;
+  return LM_OK;
+}
+
+static void refresh_class_cache(lm_detector* d) {
+  d->class_id_cache.clear();
+  for (auto& kv : d->model.classes) d->class_id_cache.push_back(kv.first);
+}
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* lm_last_error(void) { return g_err.c_str(); }
+
+void* lm_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void lm_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+int lm_create(const int32_t* T, int levels, const lm_modality_desc* mods, int M, lm_detector** out) {
+  if (!out) return fail(LM_E_INVALID, "out is NULL");
+  *out = nullptr;
+  if (levels < 1 || levels > LM_MAX_LEVELS || !T) return fail(LM_E_INVALID, "pyramid levels must be 1..%d", LM_MAX_LEVELS);
+  if (M < 1 || M > LM_MAX_MODALITIES || !mods) return fail(LM_E_INVALID, "modalities must be 1..%d", LM_MAX_MODALITIES);
+  for (int m = 0; m < M; ++m) {
+    if (mods[m].type != LM_COLOR_GRADIENT && mods[m].type != LM_DEPTH_NORMAL) return fail(LM_E_INVALID, "unknown modality type %d", mods[m].type);
+    if (mods[m].num_features < 1 || mods[m].num_features > LM_MAX_FEATURES) return fail(LM_E_INVALID, "num_features must be 1..63");
+  }
+  lm_detector* d = new lm_detector();
+  d->model.T.assign(T, T + levels);
+  d->model.mods.assign(mods, mods + M);
+  int rc = create_common(d);
+  if (rc != LM_OK) { delete d; return rc; }
+  *out = d;
+  return LM_OK;
+}
+
+int lm_create_from_yaml(const char* path, lm_detector** out) {
+  if (!out || !path) return fail(LM_E_INVALID, "NULL argument");
+  *out = nullptr;
+  lm_detector* d = new lm_detector();
+  std::string err;
+  if (!load_detector_yaml(path, d->model, err)) { delete d; return fail(LM_E_IO, "%s", err.c_str()); }
+  for (auto& kv : d->model.classes)
+    for (auto& tp : kv.second) {
+      if ((int)tp.size() != d->model.levels() * d->model.M()) { delete d; return fail(LM_E_IO, "%s: class '%s' has a template pyramid of the wrong size", path, kv.first.c_str()); }
+      for (auto& t : tp) if (t.features.size() > LM_MAX_FEATURES) { delete d; return fail(LM_E_IO, "%s: features.size() <= 63 violated", path); }
+    }
+  int rc = create_common(d);
+  if (rc != LM_OK) { delete d; return rc; }
+  refresh_class_cache(d);
+  *out = d;
+  return LM_OK;
+}
+
+int lm_write_yaml(const lm_detector* d, const char* path) {
+  if (!d || !path) return fail(LM_E_INVALID, "NULL argument");
+  std::string err;
+  if (!save_detector_yaml(d->model, path, err)) return fail(LM_E_IO, "%s", err.c_str());
+  return LM_OK;
+}
+
+static std::string format_name(const char* format, const std::string& id) {
+  char buf[4096];
+  snprintf(buf, sizeof(buf), format, id.c_str());
+  return buf;
+}
+
+int lm_read_classes(lm_detector* d, const char* const* class_ids, int n_ids, const char* format) {
+  if (!d || (n_ids && !class_ids)) return fail(LM_E_INVALID, "NULL argument");
+  const char* fmt = format ? format : "templates_%s.yml.gz";
+  for (int i = 0; i < n_ids; ++i) {
+    std::string err;
+    if (!load_class_file(format_name(fmt, class_ids[i]), d->model, err)) return fail(LM_E_IO, "%s", err.c_str());
+  }
+  refresh_class_cache(d);
+  return LM_OK;
+}
+
+int lm_write_classes(const lm_detector* d, const char* format) {
+  if (!d) return fail(LM_E_INVALID, "NULL argument");
+  const char* fmt = format ? format : "templates_%s.yml.gz";
+  for (auto& kv : d->model.classes) {
+    std::string err;
+    if (!save_class_file(d->model, kv.first, format_name(fmt, kv.first), err)) return fail(LM_E_IO, "%s", err.c_str());
+  }
+  return LM_OK;
+}
+
+void lm_destroy(lm_detector* d) {
+  if (!d) return;
+  if (d->cuda_ready) {
+    cudaSetDevice(d->device);
+    for (int i = 0; i < 2; ++i) {
+      if (d->lane[i].stream) cudaStreamSynchronize(d->lane[i].stream);
+      d->lane[i].destroy();
+    }
+    d->pack.release();
+    d->d_resp_all.release(); d->d_normal_lut.release();
+  }
+  delete d;
+}
+
+int lm_device(const lm_detector* d) { return d ? d->device : -1; }
+int lm_pyramid_levels(const lm_detector* d) { return d->model.levels(); }
+int lm_get_T(const lm_detector* d, int level) {
+  if (level < 0 || level >= d->model.levels()) return fail(LM_E_INVALID, "level out of range");
+  return d->model.T[level];
+}
+int lm_num_modalities(const lm_detector* d) { return d->model.M(); }
+int lm_get_modality(const lm_detector* d, int m, lm_modality_desc* out) {
+  if (m < 0 || m >= d->model.M() || !out) return fail(LM_E_INVALID, "modality out of range");
+  *out = d->model.mods[m];
+  return LM_OK;
+}
+int lm_num_classes(const lm_detector* d) { return (int)d->model.classes.size(); }
+int lm_num_templates(const lm_detector* d, const char* class_id) {
+  int n = 0;
+  if (class_id) {
+    auto it = d->model.classes.find(class_id);
+    return it == d->model.classes.end() ? 0 : (int)it->second.size();
+  }
+  for (auto& kv : d->model.classes) n += (int)kv.second.size();
+  return n;
+}
+const char* lm_class_id(const lm_detector* d, int class_index) {
+  if (d->class_id_cache.size() != d->model.classes.size()) refresh_class_cache(const_cast<lm_detector*>(d));
+  if (class_index < 0 || class_index >= (int)d->class_id_cache.size()) return nullptr;
+  return d->class_id_cache[class_index].c_str();
+}
+
+int lm_get_templates(const lm_detector* d, const char* class_id, int template_id, lm_template_hdr* hdr, int32_t* feats) {
+  if (!class_id) return fail(LM_E_INVALID, "class_id is NULL");
+  auto it = d->model.classes.find(class_id);
+  if (it == d->model.classes.end()) return fail(LM_E_NOTFOUND, "unknown class '%s'", class_id);
+  if (template_id < 0 || template_id >= (int)it->second.size()) return fail(LM_E_NOTFOUND, "class '%s' has no template %d", class_id, template_id);
+  const TemplatePyramid& tp = it->second[template_id];
+  int total = 0;
+  for (size_t i = 0; i < tp.size(); ++i) {
+    if (hdr) { hdr[i].width = tp[i].width; hdr[i].height = tp[i].height; hdr[i].pyramid_level = tp[i].pyramid_level; hdr[i].num_features = (int)tp[i].features.size(); }
+    for (const Feature& f : tp[i].features) {
+      if (feats) { feats[3 * total] = f.x; feats[3 * total + 1] = f.y; feats[3 * total + 2] = f.label; }
+      ++total;
+    }
+  }
+  return total;
+}
+
+int lm_add_synthetic_template(lm_detector* d, const char* class_id, int n_templates, const lm_template_hdr* hdr,
+                              const int32_t* feats) {
+  if (!d || !class_id || !hdr || !feats) return fail(LM_E_INVALID, "NULL argument");
+  int rc = validate_template(d->model, n_templates, hdr, feats);
+  if (rc != LM_OK) return rc;
+  TemplatePyramid tp((size_t)n_templates);
+  size_t k = 0;
+  for (int i = 0; i < n_templates; ++i) {
+    tp[i].width = hdr[i].width; tp[i].height = hdr[i].height; tp[i].pyramid_level = hdr[i].pyramid_level;
+    tp[i].features.resize(hdr[i].num_features);
+    for (int j = 0; j < hdr[i].num_features; ++j, ++k) {
+      tp[i].features[j].x = feats[3 * k]; tp[i].features[j].y = feats[3 * k + 1]; tp[i].features[j].label = feats[3 * k + 2];
+    }
+  }
+  std::vector<TemplatePyramid>& tps = d->model.classes[class_id];
+  tps.push_back(tp);
+  ++d->model.version;
+  refresh_class_cache(d);
+  return (int)tps.size() - 1;
+}
+
+int lm_add_template(lm_detector* d, const lm_image* sources, int n_sources, const char* class_id,
+                    const lm_image* object_mask, lm_rect* bounding_box) {
+  if (!d || !sources || !class_id) return fail(LM_E_INVALID, "NULL argument") - 100;
+  if (set_device(d) != LM_OK) return LM_E_CUDA - 100;
+  const int L = d->model.levels(), M = d->model.M();
+  int rc = check_sources(d, sources, n_sources, nullptr, 0);
+  if (rc != LM_OK) return rc - 100;
+  const int rows = sources[0].rows, cols = sources[0].cols;
+  const bool has_mask = object_mask && object_mask->data;
+  if (has_mask && (object_mask->type != LM_8UC1 || object_mask->rows != rows || object_mask->cols != cols))
+    return fail(LM_E_INVALID, "object_mask size/type mismatch") - 100;
+  Lane& ln = d->lane[0];
+  if (upload_luts(d) != LM_OK) return LM_E_CUDA - 100;
+  if (ensure_quant_ws(d, ln, rows, cols) != LM_OK) return LM_E_CUDA - 100;
+  ln.lm_ready = false; ln.front_valid = false;
+  if (upload_frame(d, ln, sources, nullptr, 0) != LM_OK) return LM_E_CUDA - 100;
+  ln.launches = 0;
+  if (run_quantize(d, ln, ln.stream) != LM_OK) return LM_E_CUDA - 100;
+  // download quantised maps (+ CG magnitudes) of every level
+  size_t total = 0;
+  std::vector<size_t> qoff((size_t)L * M), moff((size_t)L * M, 0);
+  for (int l = 0; l < L; ++l)
+    for (int m = 0; m < M; ++m) {
+      size_t n = (size_t)(rows >> l) * (cols >> l);
+      qoff[l * M + m] = total; total += (n + 255) & ~(size_t)255;
+      if (d->model.mods[m].type == LM_COLOR_GRADIENT) { moff[l * M + m] = total; total += (n * 4 + 255) & ~(size_t)255; }
+    }
+  if (ln.stage_out.ensure(total) != LM_OK) return LM_E_CUDA - 100;
+  uint8_t* host = ln.stage_out.as<uint8_t>();
+  for (int l = 0; l < L; ++l)
+    for (int m = 0; m < M; ++m) {
+      size_t n = (size_t)(rows >> l) * (cols >> l);
+      if (cudaMemcpyAsync(host + qoff[l * M + m], ln.quant_raw[l][m].p, n, cudaMemcpyDeviceToHost, ln.stream) != cudaSuccess) return fail(LM_E_CUDA, "D2H failed") - 100;
+      if (d->model.mods[m].type == LM_COLOR_GRADIENT &&
+          cudaMemcpyAsync(host + moff[l * M + m], ln.mag[l][m].p, n * 4, cudaMemcpyDeviceToHost, ln.stream) != cudaSuccess)
+        return fail(LM_E_CUDA, "D2H failed") - 100;
+    }
+  if (cudaStreamSynchronize(ln.stream) != cudaSuccess) return fail(LM_E_CUDA, "quantisation kernels failed: %s", cudaGetErrorString(cudaGetLastError())) - 100;
+
+  std::vector<lm_image> qimgs((size_t)L * M);
+  std::vector<const float*> mags((size_t)L * M, nullptr);
+  for (int l = 0; l < L; ++l)
+    for (int m = 0; m < M; ++m) {
+      lm_image& q = qimgs[l * M + m];
+      q.data = host + qoff[l * M + m]; q.rows = rows >> l; q.cols = cols >> l; q.type = LM_8UC1; q.step = (size_t)(cols >> l);
+      if (d->model.mods[m].type == LM_COLOR_GRADIENT) mags[l * M + m] = reinterpret_cast<const float*>(host + moff[l * M + m]);
+    }
+  int tid = lm_add_template_from_quantized(d, qimgs.data(), mags.data(), class_id, object_mask, bounding_box);
+  return tid < -1 ? tid - 100 : tid;
+}
+
+int lm_add_template_from_quantized(lm_detector* d, const lm_image* quantized, const float* const* magnitudes,
+                                   const char* class_id, const lm_image* object_mask, lm_rect* bounding_box) {
+  if (!d || !quantized || !magnitudes || !class_id) return fail(LM_E_INVALID, "NULL argument");
+  const int L = d->model.levels(), M = d->model.M();
+  const int rows = quantized[0].rows, cols = quantized[0].cols;
+  const bool has_mask = object_mask && object_mask->data;
+  if (has_mask && (object_mask->type != LM_8UC1 || object_mask->rows != rows || object_mask->cols != cols))
+    return fail(LM_E_INVALID, "object_mask size/type mismatch");
+  std::vector<std::vector<uint8_t> > qbuf((size_t)L * M);
+  for (int l = 0; l < L; ++l)
+    for (int m = 0; m < M; ++m) {
+      const lm_image& q = quantized[l * M + m];
+      if (!q.data || q.type != LM_8UC1 || q.rows != (rows >> l) || q.cols != (cols >> l)) return fail(LM_E_INVALID, "quantized[%d] must be a %dx%d CV_8UC1 image", l * M + m, cols >> l, rows >> l);
+      if (d->model.mods[m].type == LM_COLOR_GRADIENT && !magnitudes[l * M + m]) return fail(LM_E_INVALID, "magnitudes[%d] missing", l * M + m);
+      qbuf[l * M + m].resize((size_t)q.rows * q.cols);
+      for (int y = 0; y < q.rows; ++y) std::memcpy(&qbuf[l * M + m][(size_t)y * q.cols], (const uint8_t*)q.data + (size_t)y * q.step, q.cols);
+    }
+  // mask pyramid: [OCV] pyrDown() NN-resizes the mask, i.e. plain index decimation
+  std::vector<std::vector<uint8_t> > masks((size_t)L);
+  if (has_mask) {
+    masks[0].resize((size_t)rows * cols);
+    for (int y = 0; y < rows; ++y) std::memcpy(&masks[0][(size_t)y * cols], (const uint8_t*)object_mask->data + (size_t)y * object_mask->step, cols);
+    for (int l = 1; l < L; ++l) {
+      int pc = cols >> (l - 1), r = rows >> l, c = cols >> l;
+      masks[l].resize((size_t)r * c);
+      for (int y = 0; y < r; ++y)
+        for (int x = 0; x < c; ++x) masks[l][(size_t)y * c + x] = masks[l - 1][(size_t)(2 * y) * pc + 2 * x];
+    }
+  }
+  std::vector<TemplatePyramid>& tps = d->model.classes[class_id];  // the reference creates the class entry up front
+  refresh_class_cache(d);
+  ++d->model.version;
+  TemplatePyramid tp((size_t)L * M);
+  for (int m = 0; m < M; ++m) {
+    const lm_modality_desc& md = d->model.mods[m];
+    int nf = md.num_features, ext = md.extract_threshold;
+    for (int l = 0; l < L; ++l) {
+      if (l > 0) { nf /= 2; ext /= 2; }
+      const int r = rows >> l, c = cols >> l;
+      const uint8_t* mk = has_mask ? masks[l].data() : nullptr;
+      bool ok = md.type == LM_COLOR_GRADIENT
+                    ? extract_color_gradient(qbuf[l * M + m].data(), magnitudes[l * M + m], mk, r, c, md.strong_threshold, nf, l, tp[l * M + m])
+                    : extract_depth_normal(qbuf[l * M + m].data(), mk, r, c, nf, ext, l, tp[l * M + m]);
+      if (!ok) return -1;
+    }
+  }
+  lm_rect bb = crop_templates(tp);
+  if (bounding_box) *bounding_box = bb;
+  tps.push_back(tp);
+  return (int)tps.size() - 1;
+}
+
+int lm_set_shard(lm_detector* d, int rank, int world) {
+  if (!d || world < 1 || rank < 0 || rank >= world) return fail(LM_E_INVALID, "bad shard %d/%d", rank, world);
+  d->shard_rank = rank; d->shard_world = world;
+  return LM_OK;
+}
+
+int lm_set_similarity_lut(lm_detector* d, const uint8_t lut[256]) {
+  for (int i = 0; i < 256; ++i)
+    if (lut[i] > 4) return fail(LM_E_INVALID, "similarity LUT entries must be <= 4 (u8 accumulation of 63 features)");
+  std::memcpy(d->sim_lut, lut, 256);
+  d->luts_dirty = true;
+  return LM_OK;
+}
+int lm_get_similarity_lut(const lm_detector* d, uint8_t lut[256]) { std::memcpy(lut, d->sim_lut, 256); return LM_OK; }
+int lm_set_normal_lut(lm_detector* d, const uint8_t lut[8000]) { std::memcpy(d->normal_lut, lut, 8000); d->luts_dirty = true; return LM_OK; }
+int lm_get_normal_lut(const lm_detector* d, uint8_t lut[8000]) { std::memcpy(lut, d->normal_lut, 8000); return LM_OK; }
+
+int lm_set_option(lm_detector* d, const char* key, int value) {
+  if (!d || !key) return fail(LM_E_INVALID, "NULL argument");
+  std::string k(key);
+  if (k == "debug_taps") d->debug_taps = value;
+  else if (k == "coarse_variant") d->coarse_variant = value;
+  else if (k == "timing") d->timing = value;
+  else return fail(LM_E_INVALID, "unknown option '%s'", key);
+  return LM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- match
+static int front_from_host(lm_detector* d, Lane& ln, const lm_image* sources, int n_sources, const lm_image* masks, int n_masks) {
+  int rc = check_sources(d, sources, n_sources, masks, n_masks);
+  if (rc != LM_OK) return rc;
+  if (set_device(d) != LM_OK || upload_luts(d) != LM_OK) return LM_E_CUDA;
+  const int rows = sources[0].rows, cols = sources[0].cols;
+  rc = ensure_lm_ws(d, ln, rows, cols);
+  if (rc != LM_OK) return rc;
+  ln.launches = 0;
+  std::memset(ln.work_stats, 0, sizeof(ln.work_stats));
+  CU(cudaEventRecord(ln.ev[0], ln.stream));
+  if (upload_frame(d, ln, sources, masks, n_masks) != LM_OK) return LM_E_CUDA;
+  CU(cudaEventRecord(ln.ev[1], ln.stream));
+  if (run_front(d, ln, ln.stream) != LM_OK) return LM_E_CUDA;
+  CU(cudaEventRecord(ln.ev[2], ln.stream));
+  // B_front: sources read once + linear memories written once
+  uint64_t bf = 0;
+  for (int m = 0; m < n_sources; ++m) bf += src_row_bytes(sources[m].type, cols) * rows;
+  for (size_t l = 0; l < ln.geom.size(); ++l) bf += (uint64_t)n_sources * 8 * ln.geom[l].rows * ln.geom[l].cols;
+  ln.work_stats[0] = bf;
+  return LM_OK;
+}
+
+int lm_build_front(lm_detector* d, const lm_image* sources, int n_sources, const lm_image* masks, int n_masks) {
+  if (!d || !sources) return fail(LM_E_INVALID, "NULL argument");
+  Lane& ln = d->lane[0];
+  int rc = front_from_host(d, ln, sources, n_sources, masks, n_masks);
+  if (rc != LM_OK) return rc;
+  CU(cudaStreamSynchronize(ln.stream));
+  return LM_OK;
+}
+
+int lm_match(lm_detector* d, const lm_image* sources, int n_sources, float threshold, const char* const* class_ids,
+             int n_ids, const lm_image* masks, int n_masks, lm_image_out* quantized_out, lm_match_rec** out_matches,
+             size_t* out_n) {
+  if (!d || !sources || !out_matches || !out_n) return fail(LM_E_INVALID, "NULL argument");
+  *out_matches = nullptr; *out_n = 0;
+  Lane& ln = d->lane[0];
+  int rc = front_from_host(d, ln, sources, n_sources, masks, n_masks);
+  if (rc != LM_OK) return rc;
+  std::vector<lm_match_rec> out;
+  rc = match_front(d, ln, threshold, class_ids, n_ids, out);
+  if (rc != LM_OK) return rc;
+  collect_timings(ln);
+  if (quantized_out) {
+    const int L = d->model.levels(), M = d->model.M();
+    for (int l = 0; l < L; ++l)
+      for (int m = 0; m < M; ++m) {
+        lm_image_out& q = quantized_out[l * M + m];
+        const LevelGeom& g = ln.geom[l];
+        if (!q.data || q.rows != g.rows || q.cols != g.cols || q.type != LM_8UC1 || q.step < (size_t)g.cols)
+          return fail(LM_E_INVALID, "quantized_out[%d] must be a %dx%d CV_8UC1 image", l * M + m, g.cols, g.rows);
+        CU(cudaMemcpy2D(q.data, q.step, ln.quantized[l][m].p, g.cols, g.cols, g.rows, cudaMemcpyDeviceToHost));
+      }
+  }
+  return copy_out(out, out_matches, out_n);
+}
+
+int lm_match_batch(lm_detector* d, const lm_image* sources, int n_frames, int n_sources, float threshold,
+                   const char* const* class_ids, int n_ids, lm_match_rec** out_matches, size_t* out_offsets) {
+  if (!d || !sources || !out_matches || !out_offsets || n_frames < 0) return fail(LM_E_INVALID, "NULL argument");
+  *out_matches = nullptr;
+  std::vector<lm_match_rec> all;
+  out_offsets[0] = 0;
+  // Two lanes: while lane A's kernels run, lane B's frame is packed into pinned memory and copied.
+  struct Pending { bool busy = false; WorkList wl; } pend[2];
+  auto finish = [&](int li, int frame) -> int {
+    Lane& ln = d->lane[li];
+    std::vector<lm_raw_match> raw;
+    bool overflow = false;
+    uint32_t n_cands = 0;
+    if (download_records(ln, ln.stream, raw, &overflow, &n_cands) != LM_OK) return LM_E_CUDA;
+    std::vector<lm_match_rec> out;
+    if (overflow) {  // rare: redo this frame alone with growing buffers
+      int rc = match_front(d, ln, threshold, class_ids, n_ids, out);
+      if (rc != LM_OK) return rc;
+    } else finalize_records(d->model.levels(), raw, ln.presort, out);
+    all.insert(all.end(), out.begin(), out.end());
+    out_offsets[frame + 1] = all.size();
+    return LM_OK;
+  };
+  for (int f = 0; f < n_frames; ++f) {
+    const int li = f & 1;
+    Lane& ln = d->lane[li];
+    if (pend[li].busy) { int rc = finish(li, f - 2); if (rc != LM_OK) return rc; pend[li].busy = false; }
+    int rc = front_from_host(d, ln, sources + (size_t)f * n_sources, n_sources, nullptr, 0);
+    if (rc != LM_OK) return rc;
+    rc = ensure_pack(d, ln);
+    if (rc != LM_OK) return rc;
+    rc = build_worklist(d, ln, class_ids, n_ids, pend[li].wl);
+    if (rc != LM_OK) return rc;
+    if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
+    if (enqueue_match(d, ln, pend[li].wl, threshold, ln.stream, ln.ev[3]) != LM_OK) return LM_E_CUDA;
+    CU(cudaEventRecord(ln.ev[4], ln.stream));
+    pend[li].busy = true;
+  }
+  for (int f = std::max(0, n_frames - 2); f < n_frames; ++f)
+    if (pend[f & 1].busy) { int rc = finish(f & 1, f); if (rc != LM_OK) return rc; pend[f & 1].busy = false; }
+  size_t n = 0;
+  return copy_out(all, out_matches, &n);
+}
+
+void lm_free_matches(lm_match_rec* m) { std::free(m); }
+
+int lm_match_device(lm_detector* d, const void* const* d_sources, int n_sources, int rows, int cols, float threshold,
+                    const char* const* class_ids, int n_ids, void* stream, const void** d_records,
+                    size_t* record_bytes_capacity) {
+  if (!d || !d_sources || !d_records) return fail(LM_E_INVALID, "NULL argument");
+  if (n_sources != d->model.M()) return fail(LM_E_INVALID, "sources.size() (%d) != modalities.size() (%d)", n_sources, d->model.M());
+  if (set_device(d) != LM_OK || upload_luts(d) != LM_OK) return LM_E_CUDA;
+  Lane& ln = d->lane[0];
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = ensure_lm_ws(d, ln, rows, cols);
+  if (rc != LM_OK) return rc;
+  CU(cudaStreamSynchronize(ln.stream));  // workspace memsets were enqueued on the lane's own stream
+  for (int m = 0; m < n_sources; ++m) { ln.src_ptr[m] = d_sources[m]; ln.has_mask[m] = false; }
+  ln.launches = 0;
+  if (run_front(d, ln, s) != LM_OK) return LM_E_CUDA;
+  rc = ensure_pack(d, ln);
+  if (rc != LM_OK) return rc;
+  WorkList wl;
+  rc = build_worklist(d, ln, class_ids, n_ids, wl);
+  if (rc != LM_OK) return rc;
+  if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 18), std::max<uint32_t>(ln.out_cap, 1u << 16)) != LM_OK) return LM_E_CUDA;
+  if (enqueue_match(d, ln, wl, threshold, s, nullptr) != LM_OK) return LM_E_CUDA;
+  *d_records = ln.result.p;
+  if (record_bytes_capacity) *record_bytes_capacity = sizeof(ResultHeader) + (size_t)ln.out_cap * sizeof(lm_raw_match);
+  return LM_OK;
+}
+
+int lm_finalize_raw(const lm_detector* d, const lm_raw_match* raw, size_t n_raw, lm_match_rec** out_matches, size_t* out_n) {
+  if (!d || (!raw && n_raw) || !out_matches || !out_n) return fail(LM_E_INVALID, "NULL argument");
+  std::vector<lm_raw_match> r(raw, raw + n_raw);
+  std::vector<lm_match_rec> presort, out;
+  finalize_records(d->model.levels(), r, presort, out);
+  return copy_out(out, out_matches, out_n);
+}
+
+// ---------------------------------------------------------------------------------------------- parity taps
+int lm_level_geometry(lm_detector* d, int level, int32_t out[5], size_t* plane_stride) {
+  Lane& ln = d->lane[0];
+  if (!ln.lm_ready || level < 0 || level >= (int)ln.geom.size()) return fail(LM_E_STATE, "no front end built");
+  const LevelGeom& g = ln.geom[level];
+  out[0] = g.rows; out[1] = g.cols; out[2] = g.T; out[3] = g.W; out[4] = g.H;
+  if (plane_stride) *plane_stride = g.plane_stride;
+  return LM_OK;
+}
+
+long lm_debug_fetch(lm_detector* d, int stage, int level, int modality, void* dst) {
+  Lane& ln = d->lane[0];
+  if (!ln.front_valid) return fail(LM_E_STATE, "no front end built");
+  if (level < 0 || level >= d->model.levels() || modality < 0 || modality >= d->model.M()) return fail(LM_E_INVALID, "level/modality out of range");
+  if (set_device(d) != LM_OK) return LM_E_CUDA;
+  const LevelGeom& g = ln.geom[level];
+  const size_t n = (size_t)g.rows * g.cols;
+  const void* src = nullptr;
+  size_t bytes = 0;
+  switch (stage) {
+    case LM_STAGE_QUANTIZED: src = ln.quantized[level][modality].p; bytes = n; break;
+    case LM_STAGE_QUANT_RAW: src = ln.quant_raw[level][modality].p; bytes = n; break;
+    case LM_STAGE_MAGNITUDE:
+      if (d->model.mods[modality].type != LM_COLOR_GRADIENT) return fail(LM_E_INVALID, "magnitude exists for ColorGradient only");
+      src = ln.mag[level][modality].p; bytes = n * 4; break;
+    case LM_STAGE_SPREAD:
+    case LM_STAGE_RESPONSE:
+      if (!ln.debug_taps_written) return fail(LM_E_STATE, "enable lm_set_option(det, \"debug_taps\", 1) before matching");
+      src = stage == LM_STAGE_SPREAD ? ln.spread[level][modality].p : ln.response[level][modality].p;
+      bytes = stage == LM_STAGE_SPREAD ? n : 8 * n; break;
+    case LM_STAGE_LINEAR:
+      src = ln.lmem[level].as<uint8_t>() + (size_t)modality * 8 * g.plane_stride; bytes = 8 * g.plane_stride; break;
+    default: return fail(LM_E_INVALID, "unknown stage %d", stage);
+  }
+  if (dst) {
+    if (cudaStreamSynchronize(ln.stream) != cudaSuccess || cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+      return fail(LM_E_CUDA, "debug fetch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  return (long)bytes;
+}
+
+int lm_debug_coarse_map(lm_detector* d, const char* class_id, int template_id, uint16_t* dst) {
+  Lane& ln = d->lane[0];
+  if (!ln.front_valid) return fail(LM_E_STATE, "no front end built");
+  if (set_device(d) != LM_OK) return LM_E_CUDA;
+  int prc = ensure_pack(d, ln);
+  if (prc != LM_OK) return prc;
+  Pack& pk = d->pack;
+  int local = -1;
+  for (const Pack::ClassRange& cr : pk.classes)
+    if (cr.id == class_id)
+      for (size_t k = 0; k < cr.local.size(); ++k)
+        if (pk.h_ctpl[cr.local[k]].template_id == template_id) local = (int)cr.local[k];
+  if (local < 0) return fail(LM_E_NOTFOUND, "class '%s' template %d is not on this shard", class_id, template_id);
+  const LevelGeom& gc = ln.geom.back();
+  const int WH = gc.W * gc.H;
+  if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
+  if (ln.dump.ensure((size_t)WH * 2) != LM_OK || ln.work.ensure(64) != LM_OK) return LM_E_CUDA;
+  std::vector<int32_t> thr(kMaxNf + 1, 0x7fffffff);
+  uint32_t w = (uint32_t)local;
+  ResultHeader h = {0, ln.out_cap, 0, 0};
+  CU(cudaMemsetAsync(ln.dump.p, 0, (size_t)WH * 2, ln.stream));
+  CU(cudaMemcpyAsync(ln.work.p, &w, 4, cudaMemcpyHostToDevice, ln.stream));
+  CU(cudaMemcpyAsync(ln.raw_thr.p, thr.data(), thr.size() * 4, cudaMemcpyHostToDevice, ln.stream));
+  CU(cudaMemcpyAsync(ln.result.p, &h, sizeof(h), cudaMemcpyHostToDevice, ln.stream));
+  launch_similarity_coarse(ln.lmem[d->model.levels() - 1].as<uint8_t>(), pk.foff.as<uint32_t>(), pk.ctpl.as<CoarseTpl>(),
+                           ln.work.as<uint32_t>(), 1, pk.h_ctpl[local].P, ln.raw_thr.as<int32_t>(), d->model.M(),
+                           ln.cand.as<Cand>(), ln.result.as<ResultHeader>(), 0, ln.dump.as<uint16_t>(), WH,
+                           d->coarse_variant, ln.stream);
+  CU(cudaMemcpyAsync(dst, ln.dump.p, (size_t)WH * 2, cudaMemcpyDeviceToHost, ln.stream));
+  CU(cudaStreamSynchronize(ln.stream));
+  return LM_OK;
+}
+
+long lm_debug_presort(lm_detector* d, lm_match_rec* dst) {
+  Lane& ln = d->lane[0];
+  if (dst && !ln.presort.empty()) std::memcpy(dst, ln.presort.data(), ln.presort.size() * sizeof(lm_match_rec));
+  return (long)ln.presort.size();
+}
+
+int lm_last_timings(const lm_detector* d, float ms[5], int* kernel_launches) {
+  const Lane& ln = d->lane[0];
+  for (int i = 0; i < 5; ++i) ms[i] = ln.ms[i];
+  if (kernel_launches) *kernel_launches = ln.launches;
+  return LM_OK;
+}
+int lm_last_work(const lm_detector* d, uint64_t out[6]) {
+  for (int i = 0; i < 6; ++i) out[i] = d->lane[0].work_stats[i];
+  return LM_OK;
+}
+
+}  // extern "C"

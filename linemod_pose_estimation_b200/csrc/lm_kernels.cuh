@@ -1,0 +1,83 @@
+// lm_kernels.cuh -- device-side records and kernel launchers of the LINEMOD hot path (sm_100a).
+//
+// Kernel <-> reference function map ([OCV] = OpenCV 2.4.x modules/objdetect/src/linemod.cpp, the code behind
+// cv::linemod::Detector::match called at /root/reference/src/rgbdDetector.cpp:33):
+//   k_gauss7_u8c3, k_cg_grad, k_cg_hysteresis   [OCV] quantizedOrientations + hysteresisGradient   (SURVEY 8a a1,a2)
+//   k_pyrdown_u8c3                              [OCV] ColorGradientPyramid::pyrDown -> cv::pyrDown  (a3)
+//   k_dn_normals, k_median5_u8, k_nn_half_u8    [OCV] quantizedNormals, medianBlur(5), DepthNormalPyramid::pyrDown (a4,a5)
+//   k_spread_lm                                 [OCV] spread + computeResponseMaps + linearize      (a6,a7,a8)
+//   k_similarity_coarse                         [OCV] similarity + addSimilarities + matchClass coarse scan (a9-a12)
+//   k_refine                                    [OCV] similarityLocal + matchClass refinement loop  (a13)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/linemod_b200.h"
+
+namespace lmk {
+
+struct CoarseTpl {                        // one per template (canonical order), coarse (lowest) pyramid level
+  uint32_t feat_begin;                    // first entry in the coarse feature-offset array
+  uint8_t cnt[LM_MAX_MODALITIES][4];      // in-bounds features per modality, grouped by (offset & 15) >> 2
+  int32_t P;                              // template_positions = span_y*W + span_x + 1 (<= 0: nothing to score)
+  uint32_t nf;                            // sum over modalities of features.size() (threshold denominator)
+  uint32_t order_key;                     // canonical order index (class map order, then template_id)
+  int32_t template_id, class_index;
+};
+
+struct RefineTpl {                        // one per (level < L-1, template)
+  uint32_t feat_begin;                    // first entry in that level's packed feature array
+  uint16_t cnt[LM_MAX_MODALITIES];        // all features per modality
+  int32_t width, height;                  // of the level's first-modality template (clamp window)
+  uint32_t nf;                            // sum of features.size() over modalities
+};
+
+struct RefineLevel {
+  const uint8_t* lm;                      // [M][8][plane_stride]
+  const RefineTpl* tpl;
+  const uint32_t* feats;                  // (x + 4096) | (y + 4096) << 13 | label << 26
+  unsigned long long plane_stride;
+  int rows, cols, T, W;
+};
+
+struct RefineParams {
+  RefineLevel level[LM_MAX_LEVELS];       // index = pyramid level (only 0 .. L-2 used)
+  int levels, M, coarse_T, coarse_W;
+  float threshold;
+};
+
+struct Cand {                             // coarse candidate: raw score above the template's raw threshold
+  uint32_t tglob, pos, raw, pad;
+};
+
+struct ResultHeader {
+  uint32_t count, capacity, overflow, n_cands;
+};
+
+// ------------------------------------------------------------------------------------------------ front end
+void launch_gauss7_u8c3(const uint8_t* src, int rows, int cols, uint8_t* dst, cudaStream_t s);
+void launch_cg_grad(const uint8_t* smoothed, int rows, int cols, float* mag, uint8_t* qunf, cudaStream_t s);
+void launch_cg_hysteresis(const uint8_t* qunf, const float* mag, int rows, int cols, float threshold_sq, uint8_t* quant,
+                          cudaStream_t s);
+void launch_pyrdown_u8c3(const uint8_t* src, int rows, int cols, uint8_t* dst, cudaStream_t s);
+void launch_dn_normals(const uint16_t* depth, int rows, int cols, int distance_threshold, int difference_threshold,
+                       const uint8_t* normal_lut, uint8_t* out, cudaStream_t s);
+void launch_median5_u8(const uint8_t* src, int rows, int cols, uint8_t* dst, cudaStream_t s);
+void launch_nn_half_u8(const uint8_t* src, int rows, int cols, uint8_t* dst, cudaStream_t s);
+// mask0: level-0 mask (nullable) sampled at (y << level, x << level); resp_all: 256 x u32, 8 response nibbles per
+// spread value.  quantized_out always written; spread_out / response_out only when non-null (parity taps).
+void launch_spread_lm(const uint8_t* quant_raw, const uint8_t* mask0, int mask_cols0, int level, int rows, int cols,
+                      int T, const uint32_t* resp_all, uint8_t* quantized_out, uint8_t* spread_out,
+                      uint8_t* response_out, uint8_t* lm, size_t plane_stride, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------ matching
+// dump (nullable): u16 totals, [work index][W*H], written for every scored position (parity tap).
+void launch_similarity_coarse(const uint8_t* lmc, const uint32_t* foff, const CoarseTpl* tpl, const uint32_t* work,
+                              int n_work, int max_P, const int32_t* raw_thr_by_nf, int M, Cand* cand,
+                              ResultHeader* hdr, uint32_t cand_cap, uint16_t* dump, int dump_stride, int variant,
+                              cudaStream_t s);
+// work_order[i]: canonical order key of work item i (Cand::pad carries i).
+void launch_refine(const RefineParams& p, const CoarseTpl* ctpl, const uint32_t* work_order, const Cand* cand,
+                   uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* out, cudaStream_t s);
+
+}  // namespace lmk

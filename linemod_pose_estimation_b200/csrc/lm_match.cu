@@ -1,0 +1,259 @@
+// lm_match.cu -- the template-matching kernels of the LINEMOD hot path (sm_100a).
+//
+// k_similarity_coarse restates [OCV] similarity + addSimilarities + the coarse scan of Detector::matchClass
+// (OpenCV 2.4.x objdetect/linemod.cpp, reached from /root/reference/src/rgbdDetector.cpp:33); k_refine restates
+// [OCV] similarityLocal and matchClass's refinement loop.  Spec: SURVEY.md App. A.7-A.9, quirks App. D.
+//
+// The work is a byte gather-accumulate: S_t[j] = sum_f LM[a_f + j].  The linear memories of a frame (0.6 MB per
+// modality at 640x480) are shared by every template and stay L2/L1 resident; HBM only sees the template records.
+// Hence no tensor cores: the binding resources are L2->SM bandwidth and LSU issue, which the kernel feeds with
+// 128-bit loads.  Responses are <= 4 and a template has <= 63 features per modality, so four byte lanes packed in
+// a 32-bit register never carry into each other: plain integer adds are bit-identical to the reference's
+// _mm_add_epi8 (and to __vaddus4) at a quarter of the instruction count.
+#include "lm_kernels.cuh"
+
+namespace lmk {
+
+namespace {
+
+constexpr int kLanePos = 16;             // positions per lane and pass (one 128-bit load)
+constexpr int kWarpPos = 31 * kLanePos;  // positions per warp pass; lane 31 only supplies lane 30's tail bytes
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ uint4 ldg128(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// One feature's contribution to this lane's 16 positions.  `a` (warp-uniform) is the flat byte address of the first
+// position of the pass; Q = (a & 15) >> 2 is a compile-time constant because the packer groups a template's features
+// by it.  The lane loads the aligned 16 bytes below its window, takes the Q+1 following words from its right-hand
+// neighbour by shuffle, and realigns with byte permutes.
+template <int Q>
+__device__ __forceinline__ void add_feature(const uint8_t* __restrict__ lmc, uint32_t a, int lane, bool active,
+                                            uint32_t (&acc)[4]) {
+  const uint32_t base = a & ~15u;
+  const uint32_t sel = 0x3210u + 0x1111u * (a & 3u);
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (active) v = ldg128(lmc + base + lane * kLanePos);
+  uint32_t w[8];
+  w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+  w[4] = __shfl_down_sync(kFull, v.x, 1);
+  w[5] = Q >= 1 ? __shfl_down_sync(kFull, v.y, 1) : 0;
+  w[6] = Q >= 2 ? __shfl_down_sync(kFull, v.z, 1) : 0;
+  w[7] = Q >= 3 ? __shfl_down_sync(kFull, v.w, 1) : 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] += __byte_perm(w[Q + k], w[Q + k + 1], sel);
+}
+
+template <int Q>
+__device__ __forceinline__ void add_group(const uint8_t* __restrict__ lmc, const uint32_t* __restrict__ foff, int n,
+                                          uint32_t j0, int lane, bool active, uint32_t (&acc)[4]) {
+  int f = 0;
+  for (; f + 4 <= n; f += 4) {  // four independent loads in flight per lane
+    uint32_t a0 = foff[f] + j0, a1 = foff[f + 1] + j0, a2 = foff[f + 2] + j0, a3 = foff[f + 3] + j0;
+    add_feature<Q>(lmc, a0, lane, active, acc);
+    add_feature<Q>(lmc, a1, lane, active, acc);
+    add_feature<Q>(lmc, a2, lane, active, acc);
+    add_feature<Q>(lmc, a3, lane, active, acc);
+  }
+  for (; f < n; ++f) add_feature<Q>(lmc, foff[f] + j0, lane, active, acc);
+}
+
+// Coarse similarity of every (template, position) at the lowest pyramid level, thresholded in registers.
+// A warp owns one (template, 496-position pass) tile; tiles are dealt round-robin to a persistent grid.
+__global__ void __launch_bounds__(256) k_similarity_coarse(const uint8_t* __restrict__ lmc,
+                                                           const uint32_t* __restrict__ foff,
+                                                           const CoarseTpl* __restrict__ tpl,
+                                                           const uint32_t* __restrict__ work, int n_work,
+                                                           int passes_per_tpl, const int32_t* __restrict__ raw_thr_by_nf,
+                                                           int M, Cand* __restrict__ cand, ResultHeader* hdr,
+                                                           uint32_t cand_cap, uint16_t* __restrict__ dump,
+                                                           int dump_stride) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int n_tiles = n_work * passes_per_tpl;
+  for (int tile = warp; tile < n_tiles; tile += n_warps) {
+    const int wi = tile / passes_per_tpl;
+    const int pass = tile - wi * passes_per_tpl;
+    const uint32_t tg = work[wi];
+    const int t_P = tpl[tg].P;
+    const uint32_t t_feat_begin = tpl[tg].feat_begin, t_nf = tpl[tg].nf;
+    const int j0 = pass * kWarpPos;
+    if (j0 >= t_P) continue;
+    const int rem = min(t_P - j0, kWarpPos);            // positions of this pass
+    const bool active = lane * kLanePos < rem + kLanePos;  // lanes whose bytes somebody needs
+    uint32_t tot_lo[4] = {0, 0, 0, 0}, tot_hi[4] = {0, 0, 0, 0};  // u16 x 2 per word: bytes (0,2) and (1,3)
+    const uint32_t* fp = foff + t_feat_begin;
+    for (int m = 0; m < M; ++m) {
+      uint32_t acc[4] = {0, 0, 0, 0};
+      const uint32_t c4 = __ldg(reinterpret_cast<const uint32_t*>(tpl[tg].cnt) + m);  // 4 group sizes, one word
+      const int n0 = c4 & 255, n1 = (c4 >> 8) & 255, n2 = (c4 >> 16) & 255, n3 = c4 >> 24;
+      add_group<0>(lmc, fp, n0, (uint32_t)j0, lane, active, acc); fp += n0;
+      add_group<1>(lmc, fp, n1, (uint32_t)j0, lane, active, acc); fp += n1;
+      add_group<2>(lmc, fp, n2, (uint32_t)j0, lane, active, acc); fp += n2;
+      add_group<3>(lmc, fp, n3, (uint32_t)j0, lane, active, acc); fp += n3;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {  // [OCV] addSimilarities: widen u8 -> u16 and add the modality
+        tot_lo[k] += acc[k] & 0x00ff00ffu;
+        tot_hi[k] += (acc[k] >> 8) & 0x00ff00ffu;
+      }
+    }
+    const int thr = raw_thr_by_nf[t_nf];
+    const int first = lane * kLanePos;  // first position of this lane within the pass
+    bool hit = false;
+    if (first < rem) {
+      if (thr < 0) hit = true;
+      else {
+        const uint32_t thr2 = (uint32_t)min(thr, 0xffff) * 0x00010001u;
+        uint32_t any = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) any |= __vcmpgtu2(tot_lo[k], thr2) | __vcmpgtu2(tot_hi[k], thr2);
+        hit = any != 0;
+      }
+    }
+    if (dump != nullptr && first < rem) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int p = first + 4 * k + i;
+          uint32_t src = (i & 1) ? tot_hi[k] : tot_lo[k];
+          if (p < rem) dump[(size_t)wi * dump_stride + j0 + p] = (uint16_t)((i & 2) ? (src >> 16) : (src & 0xffffu));
+        }
+    }
+    if (hit) {  // rare: [OCV] matchClass raster scan, "raw_score > raw_threshold"
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int p = first + 4 * k + i;
+          uint32_t src = (i & 1) ? tot_hi[k] : tot_lo[k];
+          int raw = (int)((i & 2) ? (src >> 16) : (src & 0xffffu));
+          if (p < rem && raw > thr) {
+            uint32_t idx = atomicAdd(&hdr->n_cands, 1u);
+            if (idx < cand_cap) {
+              Cand c;
+              c.tglob = tg; c.pos = (uint32_t)(j0 + p); c.raw = (uint32_t)raw; c.pad = (uint32_t)wi;
+              cand[idx] = c;
+            }
+          }
+        }
+    }
+  }
+}
+
+// Local refinement of every coarse candidate up the pyramid.  One warp per candidate; lane -> (patch row = lane / 2,
+// 8 columns = lane % 2) of the 16 x 16 neighbourhood.
+__global__ void __launch_bounds__(256) k_refine(const RefineParams P, const CoarseTpl* __restrict__ ctpl,
+                                                const uint32_t* __restrict__ work_order, const Cand* __restrict__ cand,
+                                                uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_cands = min(hdr->n_cands, cand_cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && hdr->n_cands > cand_cap) hdr->overflow = 1;  // candidate list truncated
+  const int prow = lane >> 1, pcol0 = (lane & 1) * 8;
+  for (uint32_t ci = warp; ci < n_cands; ci += n_warps) {
+    const Cand c = cand[ci];
+    const uint32_t ct_nf = ctpl[c.tglob].nf;
+    const int cT = P.coarse_T;
+    const int coff = cT / 2 + (cT % 2 - 1);
+    int x = (int)(c.pos % (uint32_t)P.coarse_W) * cT + coff;
+    int y = (int)(c.pos / (uint32_t)P.coarse_W) * cT + coff;
+    uint32_t score = c.raw, nf = ct_nf;
+    bool alive = true;
+    for (int l = P.levels - 2; l >= 0 && alive; --l) {
+      const RefineLevel& L = P.level[l];
+      const RefineTpl* rtp = L.tpl + c.tglob;
+      const int rt_width = rtp->width, rt_height = rtp->height;
+      const uint32_t rt_nf = rtp->nf;
+      const int T = L.T, W = L.W;
+      const int border = 8 * T, off = T / 2 + (T % 2 - 1);
+      const int max_x = L.cols - rt_width - border, max_y = L.rows - rt_height - border;
+      x = x * 2 + 1; y = y * 2 + 1;
+      x = max(x, border); y = max(y, border);
+      x = min(x, max_x); y = min(y, max_y);
+      const int offset_x = (x / T - 8) * T, offset_y = (y / T - 8) * T;
+      const size_t WH = (size_t)W * (L.rows / T);
+      uint32_t tot[4] = {0, 0, 0, 0};  // 8 x u16: columns pcol0 .. pcol0+7 as (0,2),(1,3),(4,6),(5,7)
+      const uint32_t* fp = L.feats + rtp->feat_begin;
+      for (int m = 0; m < P.M; ++m) {
+        uint32_t a0 = 0, a1 = 0;
+        const uint8_t* lmm = L.lm + (size_t)m * 8 * L.plane_stride;
+        const int n = rtp->cnt[m];
+#pragma unroll 4
+        for (int f = 0; f < n; ++f) {
+          uint32_t pk = fp[f];
+          int fx = (int)(pk & 0x1fffu) - 4096 + offset_x, fy = (int)((pk >> 13) & 0x1fffu) - 4096 + offset_y;
+          if (fx < 0 || fy < 0 || fx >= L.cols || fy >= L.rows) continue;
+          int label = (int)(pk >> 26);
+          size_t addr = (size_t)label * L.plane_stride + (size_t)((fy % T) * T + (fx % T)) * WH + (size_t)(fy / T) * W +
+                        fx / T + (size_t)prow * W + pcol0;
+          const uint8_t* p = lmm + (addr & ~(size_t)3);
+          const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(addr & 3);
+          uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(p));
+          uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(p + 4));
+          uint32_t w2 = __ldg(reinterpret_cast<const uint32_t*>(p + 8));
+          a0 += __byte_perm(w0, w1, sel);
+          a1 += __byte_perm(w1, w2, sel);
+        }
+        fp += n;
+        tot[0] += a0 & 0x00ff00ffu; tot[1] += (a0 >> 8) & 0x00ff00ffu;
+        tot[2] += a1 & 0x00ff00ffu; tot[3] += (a1 >> 8) & 0x00ff00ffu;
+      }
+      // first maximum in raster order: key = score << 8 | (255 - raster index)
+      uint32_t best_key = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint32_t src = tot[(i >> 2) * 2 + (i & 1)];
+        uint32_t sc = (i & 2) ? (src >> 16) : (src & 0xffffu);
+        uint32_t key = (sc << 8) | (uint32_t)(255 - (prow * 16 + pcol0 + i));
+        best_key = max(best_key, key);
+      }
+      best_key = __reduce_max_sync(kFull, best_key);
+      const int best_score = (int)(best_key >> 8);
+      int best_r = -1, best_c = -1;
+      if (best_score > 0) {
+        int idx = 255 - (int)(best_key & 0xffu);
+        best_r = idx >> 4; best_c = idx & 15;
+      }
+      x = (x / T - 8 + best_c) * T + off;
+      y = (y / T - 8 + best_r) * T + off;
+      score = (uint32_t)best_score; nf = rt_nf;
+      float sim = __fdiv_rn(__fmul_rn((float)best_score, 100.f), (float)(4 * (int)nf));
+      if (sim < P.threshold) alive = false;  // [OCV] remove_if(MatchPredicate(threshold))
+    }
+    if (alive && lane == 0) {
+      uint32_t idx = atomicAdd(&hdr->count, 1u);
+      if (idx < hdr->capacity) {
+        lm_raw_match r;
+        r.order_key = work_order[c.pad]; r.coarse_pos = c.pos; r.x = x; r.y = y; r.score = score; r.nf = nf;
+        r.template_id = ctpl[c.tglob].template_id; r.class_index = ctpl[c.tglob].class_index;
+        out[idx] = r;
+      } else hdr->overflow = 1;
+    }
+  }
+}
+
+}  // namespace
+
+void launch_similarity_coarse(const uint8_t* lmc, const uint32_t* foff, const CoarseTpl* tpl, const uint32_t* work,
+                              int n_work, int max_P, const int32_t* raw_thr_by_nf, int M, Cand* cand,
+                              ResultHeader* hdr, uint32_t cand_cap, uint16_t* dump, int dump_stride, int variant,
+                              cudaStream_t s) {
+  (void)variant;
+  if (n_work <= 0 || max_P <= 0) return;
+  const int passes = (max_P + kWarpPos - 1) / kWarpPos;
+  const long long tiles = (long long)n_work * passes;
+  int blocks = (int)((tiles + 7) / 8);
+  const int persistent = 148 * 8;  // one wave of 8 resident CTAs (64 warps) per SM
+  if (blocks > persistent) blocks = persistent;
+  k_similarity_coarse<<<blocks, 256, 0, s>>>(lmc, foff, tpl, work, n_work, passes, raw_thr_by_nf, M, cand, hdr,
+                                             cand_cap, dump, dump_stride);
+}
+
+void launch_refine(const RefineParams& p, const CoarseTpl* ctpl, const uint32_t* work_order, const Cand* cand,
+                   uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* out, cudaStream_t s) {
+  k_refine<<<148 * 2, 256, 0, s>>>(p, ctpl, work_order, cand, cand_cap, hdr, out);
+}
+
+}  // namespace lmk

@@ -377,8 +377,10 @@ static void response_maps(const uint8_t* spread, size_t n, const uint8_t* lut, u
 
 // Flat layout of one orientation's linear memories: T*T rows of W*H bytes, followed by a zero tail so that every
 // read the reference can perform from an in-bounds feature stays inside defined memory.
-static inline size_t lm_pad(int W, int H) { return ((size_t)W * H + 16 * (size_t)W + 16 + 15) & ~(size_t)15; }
-static inline size_t lm_plane_stride(int T, int W, int H) { return (size_t)T * T * W * H + lm_pad(W, H); }
+static inline size_t lm_plane_stride(int T, int W, int H) {
+  size_t wh = (size_t)W * H;
+  return ((size_t)T * T * wh + wh + 16 * (size_t)W + 16 + 15) & ~(size_t)15;  // planes start 16-byte aligned
+}
 
 // [OCV] linearize (A.6)
 static void linearize_T(const uint8_t* resp, int rows, int cols, int T, uint8_t* plane) {
@@ -1097,6 +1099,11 @@ void orc_prim_erode3(const uint8_t* src, int rows, int cols, int iterations, uin
 void orc_prim_distance_c3(const uint8_t* src, int rows, int cols, float* dst) { distance_transform_c3(src, rows, cols, dst); }
 void orc_prim_cg_quantize(const uint8_t* bgr, int rows, int cols, float weak, float* magnitude, uint8_t* quantized, float* angle) {
   quantized_orientations(bgr, rows, cols, weak, magnitude, quantized, angle);
+}
+void orc_prim_dn_quantize(void* h, const uint16_t* depth, int rows, int cols, int distance_threshold, int difference_threshold,
+                          uint8_t* raw, uint8_t* out) {
+  quantized_normals_raw(depth, rows, cols, distance_threshold, difference_threshold, ((Detector*)h)->normal_lut, raw);
+  median5_u8(raw, rows, cols, out);
 }
 void orc_prim_spread(const uint8_t* src, int rows, int cols, int T, uint8_t* dst) { spread_T(src, rows, cols, T, dst); }
 

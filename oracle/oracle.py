@@ -384,6 +384,16 @@ def prim_cg_quantize(bgr, weak=10.0):
     return mag, q, ang
 
 
+def prim_dn_quantize(det, depth, distance=2000, difference=50):
+    """quantizedNormals (raw LUT output, and after the 5x5 median) with `det`'s NORMAL_LUT."""
+    depth = np.ascontiguousarray(depth, np.uint16)
+    raw = np.empty(depth.shape, np.uint8)
+    out = np.empty(depth.shape, np.uint8)
+    lib().orc_prim_dn_quantize(det._h, _p(depth), depth.shape[0], depth.shape[1], int(distance), int(difference),
+                               _p(raw), _p(out))
+    return raw, out
+
+
 def prim_spread(src, T):
     src = np.ascontiguousarray(src)
     dst = np.empty_like(src)
