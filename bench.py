@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- LINEMOD matching throughput at 640x480 (BASELINE.json metric) on N B200s, and the CPU reference arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # N > 1: launched under torchrun, one rank per GPU
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "Config 2"): the reference's two-object detector --
+classes "memoryChip2" and "cpu_binary", thresholds 92 / 94 (/root/reference/launch/start_object_detection.launch:8,19),
+ColorGradient + DepthNormal, T = {5, 8} -- on a synthetic 640x480 Carmine-style RGB-D stream.  2 652 templates per
+class (the size of the one template set the reference ships pose data for), per GPU: the first 24 of a class are
+extracted from rendered views that are planted in the frames, the rest are the survey's random stress templates.
+A step = one frame matched against both classes (one match call per class with its own threshold, exactly what the
+reference's two detectors do).  N > 1: template set sharded by canonical index (weak scaling: 2 x 2 652 templates per
+GPU), frame broadcast from rank 0, survivor blocks all-gathered, rank 0 finalises.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with the frame already in HBM; `e2e` goes through the public
+API with pinned HOST frames, copies inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from linemod_pose_estimation_b200 import synth  # noqa: E402
+
+ROWS, COLS = 480, 640
+CLASSES = (("memoryChip2", 92.0), ("cpu_binary", 94.0))
+TEMPLATES_PER_CLASS = 2652
+EXTRACTED_PER_CLASS = 24
+FRAME_POOL = 128            # 128 x 1.536 MB = 197 MB of distinct input frames > 126 MB L2
+METRIC = "template_pixel_evals_per_sec_640x480"
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def rendered_views():
+    """Object views (bgr, depth, mask) per class, used for extraction and planted into the frames."""
+    out = {}
+    for ci, (cid, _) in enumerate(CLASSES):
+        out[cid] = [synth.render_view(s, scale, rot, canvas=(200, 200), tilt=tilt)
+                    for (s, scale, rot, tilt) in synth.view_params(EXTRACTED_PER_CLASS, seed=900 + ci)]
+    return out
+
+
+def random_templates(cid_index, n, seed_base=4242):
+    rng = np.random.default_rng(seed_base + cid_index)
+    return [synth.random_pyramid(rng) for _ in range(n)]
+
+
+def make_frames(views, n):
+    planted = [views[cid][k] for cid, _ in CLASSES for k in (0, 1)]
+    frames = []
+    for i in range(n):
+        bgr, depth, _ = synth.compose_scene(2000 + i, planted, rows=ROWS, cols=COLS)
+        frames.append((bgr, depth))
+    return frames
+
+
+def fill_templates(add_extracted, add_synthetic, views, per_class):
+    """Same template set for both arms: extraction goes through the arm's own addTemplate."""
+    for ci, (cid, _) in enumerate(CLASSES):
+        n_ok = 0
+        for (bgr, depth, mask) in views[cid]:
+            if add_extracted(cid, bgr, depth, mask) >= 0:
+                n_ok += 1
+        for pyr in random_templates(ci, per_class - n_ok):
+            add_synthetic(cid, pyr)
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic():
+    """dram bytes per launch of the coarse kernel from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "coarse_kernel_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path).read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's CPU implementation of the path on the host cores: the oracle port (the reference's own code,
+    OpenCV 2.4.x linemod.cpp, is not vendored and cannot be built here -- DESIGN.md), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    world = args.gpus
+    views = rendered_views()
+    orc = O.OracleDetector()
+    threads = O.OracleDetector.max_threads()
+    orc.set_threads(threads)
+    fill_templates(lambda cid, b, d, m: orc.add_template([b, d], cid, m)[0],
+                   lambda cid, pyr: orc.add_synthetic_template(cid, pyr), views, TEMPLATES_PER_CLASS * world)
+    frames = make_frames(views, max(2, min(FRAME_POOL, args.warmup + args.steps)))
+    n_t = orc.num_templates()
+
+    def step(i):
+        bgr, depth = frames[i % len(frames)]
+        n = 0
+        for cid, thr in CLASSES:
+            n += len(orc.match([bgr, depth], thr, class_ids=[cid]))
+        return n
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    dt = time.perf_counter() - t0
+    evals = n_t * (COLS // 8) * (ROWS // 8)
+    val = evals * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "fps": args.steps / dt, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(world, n_t),
+        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": threads, "kind": "port",
+                         "sample": "%d full frames (both classes, %d templates) per timed run, oracle with %d threads" % (args.steps, n_t, threads)},
+        "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(world, n_templates):
+    return {"workload": "configs[1]: two-object detector (memoryChip2 thr 92 + cpu_binary thr 94), ColorGradient+DepthNormal, "
+                        "T={5,8}, synthetic 640x480 RGB-D stream",
+            "templates_total": n_templates, "templates_per_gpu": n_templates // world, "classes": 2,
+            "frame": "640x480 BGR u8 + depth u16", "parallelism": "templates sharded x%d, frame broadcast, match all-gather" % world,
+            "l2": "pool of %d distinct frames (%.0f MB > 126 MB L2) cycled; linear memories are produced and consumed inside each step" % (FRAME_POOL, FRAME_POOL * 1.536)}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from linemod_pose_estimation_b200 import Detector, _capi
+    from linemod_pose_estimation_b200.sharding import ShardedDetector
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torchrun --nproc-per-node %d" % (args.gpus, world, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    views = rendered_views()
+    det = Detector()
+    fill_templates(lambda cid, b, d, m: det.addTemplate([b, d], cid, m)[0],
+                   lambda cid, pyr: det.addSyntheticTemplate(pyr, cid), views, TEMPLATES_PER_CLASS * world)
+    n_t = det.numTemplates()
+    sharded = ShardedDetector(det, capacity=2048)
+    frames = make_frames(views, FRAME_POOL)
+    evals_per_step = n_t * (COLS // 8) * (ROWS // 8)
+
+    # pinned host frames (e2e) and device-resident frames (value)
+    host = []
+    for (b, d) in frames:
+        pb, pd = _capi.pinned_empty(b.shape, np.uint8), _capi.pinned_empty(d.shape, np.uint16)
+        pb[...] = b
+        pd[...] = d
+        host.append((pb, pd))
+    dev_frames = [(torch.from_numpy(b).to(dev), torch.from_numpy(d.view(np.int16)).to(dev)) for (b, d) in frames]
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: frame resident in HBM on every rank, device-timed, survivors gathered to rank 0
+    def device_step(i):
+        fb, fd = dev_frames[i % FRAME_POOL]
+        for cid, thr in CLASSES:
+            rec, cap = det.match_device([fb.data_ptr(), fd.data_ptr()], ROWS, COLS, thr, stream=stream.cuda_stream, class_ids=[cid])
+            if world > 1:
+                sharded.gather(sharded_view(rec, cap))
+
+    def sharded_view(rec, cap):
+        from linemod_pose_estimation_b200.sharding import device_view
+        return device_view(rec, cap, dev)
+
+    for i in range(args.warmup):
+        device_step(i)
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        device_step(args.warmup + i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = evals_per_step * args.steps / (ms * 1e-3)
+
+    # ---- e2e: public API, pinned host frames on rank 0, H2D + (broadcast) + match + (gather) + D2H + finalise
+    coarse_ms, coarse_bytes, launches, n_matches = [], [], 0, 0
+    bufs = sharded.frame_buffers(ROWS, COLS, ("cg", "dn")) if world > 1 else None
+
+    def e2e_step(i, record):
+        nonlocal launches, n_matches
+        pb, pd = host[i % FRAME_POOL]
+        for cid, thr in CLASSES:
+            if world == 1:
+                m = det.match([pb, pd], thr, class_ids=[cid])
+                n_matches += len(m)
+                if record:
+                    t = det.last_timings()
+                    w = det.last_work()
+                    coarse_ms.append(t["coarse"]); coarse_bytes.append(w["B_coarse"]); launches += t["launches"]
+            else:
+                if rank == 0:
+                    bufs[0].copy_(torch.from_numpy(pb), non_blocking=True)
+                    bufs[1].copy_(torch.from_numpy(pd.view(np.int16)), non_blocking=True)
+                sharded.det = det
+                sharded.broadcast_frame(bufs)
+                rec, cap = det.match_device([bufs[0].data_ptr(), bufs[1].data_ptr()], ROWS, COLS, thr, stream=stream.cuda_stream, class_ids=[cid])
+                raws = sharded.gather(sharded_view(rec, cap))
+                if rank == 0:
+                    n_matches += len(det.finalize_raw(np.concatenate(raws)))
+                if record:
+                    launches += det.last_timings()["launches"]
+
+    for i in range(args.warmup):
+        e2e_step(i, False)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(args.warmup + i, True)
+    barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e_value = evals_per_step * args.steps / dt
+    clock_info = clocks.stop() if clocks else None
+
+    # ---- roofline of the dominant kernel (k_similarity_coarse), live CUDA-event durations from the library's stream
+    peak, peak_src = measured_peak()
+    if world > 1:  # per-rank kernel timing needs the blocking API: one extra local pass, outside the timed regions
+        for i in range(min(args.steps, 8)):
+            pb, pd = host[i % FRAME_POOL]
+            for cid, thr in CLASSES:
+                det.match([pb, pd], thr, class_ids=[cid])
+                coarse_ms.append(det.last_timings()["coarse"]); coarse_bytes.append(det.last_work()["B_coarse"])
+    mean_ms = float(np.mean(coarse_ms))
+    achieved = float(np.mean(coarse_bytes)) / (mean_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_similarity_coarse", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": recorded_traffic(), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": float(np.mean(coarse_bytes)), "launch_ms": mean_ms,
+                "note": "algorithmic bytes = sum over templates, modalities, in-bounds features of template_positions (SURVEY 8d); "
+                        "the linear memories are L2-resident, so DRAM traffic is far below this by design"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_baseline_leg(views, frames, n_t)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "fps": args.steps / (ms * 1e-3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(world, n_t),
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": {"value": e2e_value, "unit": "evals/s", "fps": args.steps / dt, "ms_per_step": 1e3 * dt / args.steps,
+                    "h2d_bytes_per_step": len(CLASSES) * (ROWS * COLS * 3 + ROWS * COLS * 2),
+                    "d2h_bytes_per_step": len(CLASSES) * (16 + 2048 * 32), "matches_per_step": n_matches / max(1, args.steps)},
+            "gpu_launches": launches, "clocks": clock_info,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_leg(views, frames, n_t):
+    """Oracle (a port of the reference's CPU path) on this box's host cores, bounded sample of the same workload."""
+    from oracle import oracle as O
+    orc = O.OracleDetector()
+    threads = O.OracleDetector.max_threads()
+    orc.set_threads(threads)
+    fill_templates(lambda cid, b, d, m: orc.add_template([b, d], cid, m)[0],
+                   lambda cid, pyr: orc.add_synthetic_template(cid, pyr), views, TEMPLATES_PER_CLASS)
+    n_frames = 0
+    t0 = time.perf_counter()
+    while True:
+        bgr, depth = frames[n_frames % len(frames)]
+        for cid, thr in CLASSES:
+            orc.match([bgr, depth], thr, class_ids=[cid])
+        n_frames += 1
+        dt = time.perf_counter() - t0
+        if dt > 10.0 or n_frames >= 64:
+            break
+    evals = n_t * (COLS // 8) * (ROWS // 8)
+    return {"value": evals * n_frames / dt, "unit": "evals/s", "fps": n_frames / dt, "cores": threads, "kind": "port",
+            "sample": "%d full frames of the same workload (both classes, %d templates), %.1f s" % (n_frames, n_t, dt)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 200:
+            args.steps = 8  # bounded sample: the CPU arm takes ~0.1-1 s per frame
+        if args.warmup == 10:
+            args.warmup = 1
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -148,7 +149,14 @@ struct Pack {
   std::vector<uint32_t> refine_nf;      // per template: sum over refine levels of features (x256 = bytes / candidate)
   struct ClassRange { std::string id; int class_index; std::vector<uint32_t> local; std::vector<uint32_t> global_pos; };
   std::vector<ClassRange> classes;      // canonical order
+  struct Filtered { DevBuf work, order; int n = 0; uint64_t coarse_bytes = 0; };
+  std::map<std::string, Filtered> filtered;  // work lists of class_ids-filtered matches, by request
+  void clear_filtered() {
+    for (auto& kv : filtered) { kv.second.work.release(); kv.second.order.release(); }
+    filtered.clear();
+  }
   void release() {
+    clear_filtered();
     ctpl.release(); foff.release(); work_all.release(); order_all.release();
     for (int l = 0; l < LM_MAX_LEVELS; ++l) { rtpl[l].release(); rfeats[l].release(); }
   }
@@ -422,6 +430,7 @@ static int ensure_pack(lm_detector* d, const Lane& ln) {
   std::vector<uint32_t> foff;
   std::vector<RefineTpl> rtpl[LM_MAX_LEVELS];
   std::vector<uint32_t> rfeats[LM_MAX_LEVELS];
+  pk.clear_filtered();
   pk.classes.clear(); pk.coarse_bytes.clear(); pk.refine_nf.clear();
   pk.coarse_bytes_all = 0; pk.max_P = 0;
   uint32_t canonical = 0;
@@ -533,11 +542,23 @@ static int build_worklist(lm_detector* d, Lane& ln, const char* const* class_ids
     wl.n = pk.n; wl.coarse_bytes = pk.coarse_bytes_all;
     return LM_OK;
   }
+  // filtered work lists are cached per request (the service asks for the same class again and again)
+  std::string key;
+  for (int i = 0; i < n_ids; ++i) {
+    if (!class_ids[i]) return fail(LM_E_INVALID, "class_ids[%d] is NULL", i);
+    key += class_ids[i];
+    key += '\n';
+  }
+  auto hit = pk.filtered.find(key);
+  if (hit != pk.filtered.end()) {
+    wl.d_work = hit->second.work.as<uint32_t>(); wl.d_order = hit->second.order.as<uint32_t>();
+    wl.n = hit->second.n; wl.coarse_bytes = hit->second.coarse_bytes;
+    return LM_OK;
+  }
   std::vector<uint32_t> work, order;
   // order keys of a filtered run: position in the filtered iteration (a class may be listed more than once)
   uint32_t base = 0;
   for (int i = 0; i < n_ids; ++i) {
-    if (!class_ids[i]) return fail(LM_E_INVALID, "class_ids[%d] is NULL", i);
     auto it = d->model.classes.find(class_ids[i]);
     if (it == d->model.classes.end()) continue;
     for (const Pack::ClassRange& cr : pk.classes)
@@ -554,14 +575,15 @@ static int build_worklist(lm_detector* d, Lane& ln, const char* const* class_ids
     base += (uint32_t)it->second.size();
   }
   wl.n = (int)work.size();
-  if (ln.work.ensure(work.size() * 4 + 64) != LM_OK || ln.work_order.ensure(order.size() * 4 + 64) != LM_OK) return LM_E_CUDA;
-  if (wl.n) {
-    // small, infrequent: synchronous copies keep the host vectors' lifetime trivial
-    CU(cudaMemcpyAsync(ln.work.p, work.data(), work.size() * 4, cudaMemcpyHostToDevice, ln.stream));
-    CU(cudaMemcpyAsync(ln.work_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ln.stream));
-    CU(cudaStreamSynchronize(ln.stream));
+  Pack::Filtered& fl = pk.filtered[key];
+  fl.n = wl.n; fl.coarse_bytes = wl.coarse_bytes;
+  if (fl.work.ensure(work.size() * 4 + 64) != LM_OK || fl.order.ensure(order.size() * 4 + 64) != LM_OK) return LM_E_CUDA;
+  if (wl.n) {  // first use of this filter only: synchronous copies
+    CU(cudaMemcpy(fl.work.p, work.data(), work.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(fl.order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice));
   }
-  wl.d_work = ln.work.as<uint32_t>(); wl.d_order = ln.work_order.as<uint32_t>();
+  wl.d_work = fl.work.as<uint32_t>(); wl.d_order = fl.order.as<uint32_t>();
+  (void)ln;
   return LM_OK;
 }
 

@@ -1,0 +1,133 @@
+"""Multi-GPU layout of the matcher: template set sharded across ranks, frame broadcast, matches gathered to rank 0.
+
+One process per GPU (torch.distributed, NCCL over NVLink / NVSwitch; gloo for the CPU tests of this plumbing).
+Templates are independent given a frame's linear memories ([OCV] Detector::matchClass has no cross-template state,
+SURVEY.md section 8e), so the only exchanges are
+    C1  broadcast of the raw frame (1.5 MB at 640x480; every rank rebuilds the identical front end itself), and
+    C2  a fixed-capacity all-gather of each rank's survivor block {count, capacity, overflow, n_cands | raw records},
+after which rank 0 restores the reference's emission order and runs the same std::sort + std::unique
+(lm_finalize_raw) -- global, because std::unique acts across templates (App. D-7) -- for the unchanged NMS / ICP
+stage of the reference (/root/reference/src/rgbdDetector.cpp:36-144, 462-574).
+torch is plumbing here (device tensors, streams, collectives); all matching runs in liblinemod_b200.so.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._capi import RAW_DTYPE, RESULT_HEADER_BYTES
+
+RECORD_BYTES = RAW_DTYPE.itemsize
+
+
+class _DevicePtr:
+    """Zero-copy torch view of library-owned device memory (CUDA array interface)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def device_view(ptr, nbytes, device):
+    return torch.as_tensor(_DevicePtr(ptr, nbytes), device=device)
+
+
+def pack_block(raw, capacity):
+    """Host-side constructor of a survivor block (used by the CPU tests that stand in for the CUDA matcher)."""
+    raw = np.ascontiguousarray(raw, dtype=RAW_DTYPE)
+    block = np.zeros(RESULT_HEADER_BYTES + capacity * RECORD_BYTES, np.uint8)
+    hdr = block[:RESULT_HEADER_BYTES].view(np.uint32)
+    hdr[0], hdr[1], hdr[2], hdr[3] = len(raw), capacity, int(len(raw) > capacity), len(raw)
+    n = min(len(raw), capacity)
+    block[RESULT_HEADER_BYTES:RESULT_HEADER_BYTES + n * RECORD_BYTES] = raw[:n].view(np.uint8).reshape(-1)
+    return block
+
+
+def unpack_blocks(gathered, world, capacity):
+    """[world x block] bytes -> (list of raw record arrays, needed capacity if some rank had more than `capacity`)."""
+    stride = RESULT_HEADER_BYTES + capacity * RECORD_BYTES
+    raws, need = [], 0
+    for r in range(world):
+        blk = gathered[r * stride:(r + 1) * stride]
+        hdr = blk[:RESULT_HEADER_BYTES].view(np.uint32)
+        count = int(hdr[0])
+        if hdr[2] != 0:
+            raise RuntimeError("rank %d overflowed its device-side match buffer" % r)
+        if count > capacity:
+            need = max(need, count)
+            continue
+        raws.append(blk[RESULT_HEADER_BYTES:RESULT_HEADER_BYTES + count * RECORD_BYTES].view(RAW_DTYPE).copy())
+    return raws, need
+
+
+class ShardedMatcher:
+    """Exchange + finalisation around a rank-local matcher.
+
+    local_match(frame_tensors, threshold) must return a uint8 tensor holding the rank's survivor block with room for at
+    least `capacity` records (the CUDA library's block is used in place; the CPU tests build one with pack_block)."""
+
+    def __init__(self, local_match, finalize, rank, world, group=None, capacity=4096):
+        self.local_match, self.finalize = local_match, finalize
+        self.rank, self.world, self.group = rank, world, group
+        self.capacity = capacity
+        self._gather_buf = None
+
+    def broadcast_frame(self, tensors):
+        if self.world > 1:
+            for t in tensors:  # bytes on the wire: neither NCCL nor gloo carries 16-bit integers
+                dist.broadcast(t.view(torch.uint8), src=0, group=self.group)  # C1
+        return tensors
+
+    def gather(self, block):
+        """C2: fixed-capacity all-gather of the survivor blocks.  Every rank sees every header, so all ranks agree on
+        whether a (rare) second round with a larger capacity is needed without an extra collective."""
+        while True:
+            nbytes = RESULT_HEADER_BYTES + self.capacity * RECORD_BYTES
+            mine = block[:nbytes].contiguous()
+            if self.world == 1:
+                gathered = mine
+            else:
+                if self._gather_buf is None or self._gather_buf.numel() != nbytes * self.world or self._gather_buf.device != mine.device:
+                    self._gather_buf = torch.empty(nbytes * self.world, dtype=torch.uint8, device=mine.device)
+                dist.all_gather_into_tensor(self._gather_buf, mine, group=self.group)
+                gathered = self._gather_buf
+            host = gathered.cpu().numpy()
+            raws, need = unpack_blocks(host, self.world, self.capacity)
+            if need == 0:
+                return raws
+            if need > (block.numel() - RESULT_HEADER_BYTES) // RECORD_BYTES:
+                raise RuntimeError("survivor block too small for %d records" % need)
+            self.capacity = int(need * 1.25) + 64
+
+    def match(self, frame_tensors, threshold):
+        """frame_tensors: per-modality tensors, valid on rank 0 (other ranks pass same-shaped buffers).  Returns the
+        finalised match list on rank 0, None elsewhere."""
+        self.broadcast_frame(frame_tensors)
+        block = self.local_match(frame_tensors, threshold)
+        raws = self.gather(block)
+        if self.rank != 0:
+            return None
+        raw = np.concatenate(raws) if raws else np.zeros(0, RAW_DTYPE)
+        return self.finalize(raw)
+
+
+class ShardedDetector(ShardedMatcher):
+    """The CUDA matcher sharded over torch.distributed ranks: rank r keeps templates with canonical index % world == r."""
+
+    def __init__(self, detector, group=None, capacity=4096):
+        self.det = detector
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        detector.set_shard(rank, world)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        super().__init__(self._local, detector.finalize_raw, rank, world, group, capacity)
+
+    def _local(self, frame_tensors, threshold):
+        rows, cols = frame_tensors[0].shape[:2]
+        ptrs = [t.data_ptr() for t in frame_tensors]
+        rec, cap_bytes = self.det.match_device(ptrs, rows, cols, threshold,
+                                               stream=torch.cuda.current_stream().cuda_stream)
+        return device_view(rec, cap_bytes, self.device)
+
+    def frame_buffers(self, rows, cols, kinds):
+        """Device buffers for one frame: uint8 [rows, cols, 3] for ColorGradient, int16-typed uint16 storage for depth."""
+        return [torch.empty((rows, cols, 3), dtype=torch.uint8, device=self.device) if k == "cg"
+                else torch.empty((rows, cols), dtype=torch.int16, device=self.device) for k in kinds]

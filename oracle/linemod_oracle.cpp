@@ -72,6 +72,13 @@ struct CandRec {  // coarse candidates (pre-refinement), for the parity taps
   int32_t class_index, template_id, pos, raw;
 };
 
+struct RawRec {  // survivor in the product's exchange format (lm_raw_match): integer score + feature count
+  uint32_t order_key, coarse_pos;
+  int32_t x, y;
+  uint32_t score, nf;
+  int32_t template_id, class_index;
+};
+
 // [OCV] Match::operator< / operator==  (A.1)
 static inline bool match_less(const MatchRec& a, const MatchRec& b) {
   if (a.similarity != b.similarity) return a.similarity > b.similarity;
@@ -416,6 +423,7 @@ struct Detector {
   std::vector<LevelMod> front;  // index l*M+m
   std::vector<CandRec> last_cands;
   std::vector<MatchRec> last_presort;
+  std::vector<RawRec> last_raw;
   std::string err;
   int levels() const { return (int)T.size(); }
   int M() const { return (int)mods.size(); }
@@ -715,7 +723,8 @@ static void similarity_local(const LevelMod& lm, const Template& t, uint8_t* dst
 // and (optionally) the coarse candidates to `cands`.
 static void match_template(const Detector& det, int class_index, int template_id, const TemplatePyramid& tp,
                            float threshold, std::vector<MatchRec>& out, std::vector<CandRec>* cands,
-                           uint16_t* coarse_map /*nullable, H*W*/) {
+                           uint16_t* coarse_map /*nullable, H*W*/, std::vector<RawRec>* raws = nullptr,
+                           uint32_t order_key = 0) {
   const int L = det.levels(), M = det.M();
   const int lowest_start = (int)tp.size() - M;
   const int lowest_T = det.T.back();
@@ -736,6 +745,7 @@ static void match_template(const Detector& det, int class_index, int template_id
 
   int raw_threshold = (int)(2 * num_features + (threshold / 100.f) * (2 * num_features) + 0.5f);
   std::vector<MatchRec> candidates;
+  std::vector<RawRec> rr;  // integer view of `candidates`, kept in lock-step
   for (int r = 0; r < H; ++r)
     for (int c = 0; c < W; ++c) {
       int raw = total[(size_t)r * W + c];
@@ -748,6 +758,8 @@ static void match_template(const Detector& det, int class_index, int template_id
         mr.class_index = class_index;
         mr.template_id = template_id;
         candidates.push_back(mr);
+        RawRec q = {order_key, (uint32_t)(r * W + c), mr.x, mr.y, (uint32_t)raw, (uint32_t)num_features, template_id, class_index};
+        rr.push_back(q);
         if (cands) { CandRec cr = {class_index, template_id, r * W + c, raw}; cands->push_back(cr); }
       }
     }
@@ -785,13 +797,16 @@ static void match_template(const Detector& det, int class_index, int template_id
       m2.x = (x / T - 8 + best_c) * T + offset;
       m2.y = (y / T - 8 + best_r) * T + offset;
       m2.similarity = (best_score * 100.f) / (4 * nf);
+      rr[k].x = m2.x; rr[k].y = m2.y; rr[k].score = (uint32_t)best_score; rr[k].nf = (uint32_t)nf;
     }
     size_t w = 0;
     for (size_t k = 0; k < candidates.size(); ++k)
-      if (!(candidates[k].similarity < threshold)) candidates[w++] = candidates[k];
+      if (!(candidates[k].similarity < threshold)) { rr[w] = rr[k]; candidates[w++] = candidates[k]; }
     candidates.resize(w);
+    rr.resize(w);
   }
   out.insert(out.end(), candidates.begin(), candidates.end());
+  if (raws) raws->insert(raws->end(), rr.begin(), rr.end());
 }
 
 // Front end of [OCV] Detector::match: quantise every level / modality, spread, response maps, linearize.
@@ -851,12 +866,15 @@ static void run_match(Detector& det, float threshold, const char* const* class_i
       if (it != det.classes.end()) todo.push_back(std::make_pair(class_index_of(det, class_ids[i]), &it->second));
     }
   }
+  det.last_raw.clear();
+  uint32_t order_base = 0;  // position in the iteration order (== canonical index when all classes are matched)
   for (size_t k = 0; k < todo.size(); ++k) {
     int ci = todo[k].first;
     const std::vector<TemplatePyramid>& tps = *todo[k].second;
     int n = (int)tps.size();
     std::vector<std::vector<MatchRec> > per((size_t)n);
     std::vector<std::vector<CandRec> > perc((size_t)n);
+    std::vector<std::vector<RawRec> > perr((size_t)n);
     // Templates are independent given the frame's linear memories; the reference loop is sequential, the
     // "all host cores" baseline hands out chunks of 8 templates to det.threads workers (order restored below).
     std::atomic<int> next(0);
@@ -865,7 +883,8 @@ static void run_match(Detector& det, float threshold, const char* const* class_i
         int t0 = next.fetch_add(8);
         if (t0 >= n) break;
         for (int t = t0; t < std::min(n, t0 + 8); ++t)
-          match_template(det, ci, t, tps[t], threshold, per[t], keep_cands ? &perc[t] : nullptr, nullptr);
+          match_template(det, ci, t, tps[t], threshold, per[t], keep_cands ? &perc[t] : nullptr, nullptr,
+                         keep_cands ? &perr[t] : nullptr, order_base + (uint32_t)t);
       }
     };
     if (det.threads <= 1) worker();
@@ -877,7 +896,9 @@ static void run_match(Detector& det, float threshold, const char* const* class_i
     for (int t = 0; t < n; ++t) {
       matches.insert(matches.end(), per[t].begin(), per[t].end());
       if (keep_cands) det.last_cands.insert(det.last_cands.end(), perc[t].begin(), perc[t].end());
+      if (keep_cands) det.last_raw.insert(det.last_raw.end(), perr[t].begin(), perr[t].end());
     }
+    order_base += (uint32_t)n;
   }
   det.last_presort = matches;
   std::sort(matches.begin(), matches.end(), match_less);
@@ -1043,6 +1064,12 @@ long orc_last_presort(void* h, MatchRec* dst /*nullable*/) {
   Detector& det = *(Detector*)h;
   if (dst) std::memcpy(dst, det.last_presort.data(), det.last_presort.size() * sizeof(MatchRec));
   return (long)det.last_presort.size();
+}
+// Survivors of the last match (keep_cands != 0) in the product's exchange format, emission order.
+long orc_last_raw(void* h, RawRec* dst /*nullable*/) {
+  Detector& det = *(Detector*)h;
+  if (dst) std::memcpy(dst, det.last_raw.data(), det.last_raw.size() * sizeof(RawRec));
+  return (long)det.last_raw.size();
 }
 long orc_last_candidates(void* h, CandRec* dst /*nullable*/) {
   Detector& det = *(Detector*)h;

@@ -31,6 +31,8 @@ class OrcModality(C.Structure):
 
 MATCH_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("template_id", "<i4"), ("class_index", "<i4"),
                         ("similarity", "<f4")])
+RAW_DTYPE = np.dtype([("order_key", "<u4"), ("coarse_pos", "<u4"), ("x", "<i4"), ("y", "<i4"), ("score", "<u4"),
+                      ("nf", "<u4"), ("template_id", "<i4"), ("class_index", "<i4")])
 CAND_DTYPE = np.dtype([("class_index", "<i4"), ("template_id", "<i4"), ("pos", "<i4"), ("raw", "<i4")])
 
 
@@ -79,6 +81,8 @@ def lib():
         L.orc_free.argtypes = [C.c_void_p]
         L.orc_last_presort.restype = C.c_long
         L.orc_last_presort.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_last_raw.restype = C.c_long
+        L.orc_last_raw.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_last_candidates.restype = C.c_long
         L.orc_last_candidates.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_coarse_map.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p]
@@ -260,6 +264,13 @@ class OracleDetector:
         n = lib().orc_last_presort(self._h, None)
         res = np.empty(n, MATCH_DTYPE)
         lib().orc_last_presort(self._h, res.ctypes.data)
+        return res
+
+    def last_raw(self):
+        """Survivors of the last match(keep_candidates=True) as lm_raw_match-shaped records (emission order)."""
+        n = lib().orc_last_raw(self._h, None)
+        res = np.empty(n, RAW_DTYPE)
+        lib().orc_last_raw(self._h, res.ctypes.data)
         return res
 
     def last_candidates(self):

@@ -1,0 +1,346 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle: every stage tap, coarse similarity maps,
+candidate-level and final match lists, bit-exact.  Needs a B200; run with `pytest -m gpu`."""
+import os
+
+import numpy as np
+import pytest
+
+import common
+from common import O, synth
+from linemod_pose_estimation_b200 import Detector, LinemodError, Stage
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(kinds=("cg", "dn"), T=(5, 8), n_views=8, n_random=24, seed=5, classes=("obj",), lut=None, canvas=(240, 240)):
+    orc, views = common.build_oracle(kinds, T, n_views, n_random, seed, classes, canvas)
+    det = Detector(common.product_modalities(kinds), T)
+    common.copy_templates(orc, det)
+    if lut is not None:
+        orc.set_similarity_lut(lut)
+        det.set_similarity_lut(lut)
+    return orc, det, views
+
+
+def _check_stages(orc, det, L, M, kinds):
+    for l in range(L):
+        for m in range(M):
+            for st, name in ((Stage.QUANT_RAW, "quant_raw"), (Stage.QUANTIZED, "quantized"), (Stage.SPREAD, "spread"),
+                             (Stage.RESPONSE, "response"), (Stage.LINEAR, "linear")):
+                a, b = det.fetch(st, l, m), orc.fetch(st, l, m)
+                assert a.shape == b.shape, (name, l, m, a.shape, b.shape)
+                bad = np.count_nonzero(a != b)
+                assert bad == 0, "%s level %d modality %d: %d mismatching bytes" % (name, l, m, bad)
+            if kinds[m] == "cg":
+                a, b = det.fetch(Stage.MAGNITUDE, l, m), orc.fetch(O.Stage.MAGNITUDE, l, m)
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), ("magnitude", l, m)
+
+
+# ---------------------------------------------------------------------------------------------- front end
+@pytest.mark.parametrize("rows,cols,T,kinds", [
+    (480, 640, (5, 8), ("cg", "dn")),    # the reference's trainer configuration (renderer.cpp:179-185)
+    (480, 640, (5, 8), ("cg",)),         # Ensenso nodes: RGB only
+    (240, 320, (4, 8), ("dn", "cg")),    # modality order swapped, other T
+    (96, 160, (2, 4, 8), ("cg", "dn")),  # three pyramid levels
+    (100, 180, (5,), ("cg",)),           # single level, W % 4 != 0 -> byte store path
+])
+def test_front_end_taps_bit_exact(rows, cols, T, kinds):
+    orc = O.OracleDetector(common.oracle_modalities(kinds), T)
+    det = Detector(common.product_modalities(kinds), T)
+    det.set_option("debug_taps", 1)
+    views = common.rendered_views(3, 41, canvas=(80, 80))
+    for seed in (1001, 1002):
+        bgr, depth, _ = synth.compose_scene(seed, views, rows=rows, cols=cols)
+        src = common.sources_for(kinds, bgr, depth)
+        orc.build_front(src)
+        det.build_front(src)
+        _check_stages(orc, det, len(T), len(kinds), kinds)
+        for l in range(len(T)):
+            go, gd = orc.geometry(l), det.geometry(l)
+            assert go == gd
+
+
+def test_front_end_with_masks_and_strided_roi():
+    """masks argument of Detector::match, and a cropped ROI view with non-contiguous rows like the service passes
+    (..._service.cpp:324-326: mat_rgb(crop) at bias_x = 56)."""
+    kinds, T = ("cg", "dn"), (5, 8)
+    orc = O.OracleDetector(common.oracle_modalities(kinds), T)
+    det = Detector(common.product_modalities(kinds), T)
+    det.set_option("debug_taps", 1)
+    views = common.rendered_views(3, 43)
+    wide_bgr, wide_depth, _ = synth.compose_scene(7, views, rows=480, cols=752)
+    bgr, depth = wide_bgr[:, 56:56 + 640], wide_depth[:, 56:56 + 640]
+    assert not bgr.flags["C_CONTIGUOUS"]
+    rng = np.random.default_rng(2)
+    m0 = (rng.random((480, 640)) < 0.7).astype(np.uint8) * 255
+    m1 = np.zeros((480, 640), np.uint8)
+    m1[100:400, 150:600] = 1
+    orc.build_front([np.ascontiguousarray(bgr), np.ascontiguousarray(depth)], masks=[m0, m1])
+    det.build_front([bgr, depth], masks=[m0, m1])
+    _check_stages(orc, det, 2, 2, kinds)
+
+
+def test_alternative_luts():
+    lut = common.survey_similarity_lut()
+    orc, det, views = _pair(lut=lut, n_views=4, n_random=12)
+    rng = np.random.default_rng(0)
+    nlut = (1 << rng.integers(0, 8, 8000)).astype(np.uint8)
+    orc.set_normal_lut(nlut)
+    det.set_normal_lut(nlut)
+    det.set_option("debug_taps", 1)
+    bgr, depth, _ = synth.compose_scene(11, views[:3])
+    common.assert_matches_equal(det.match([bgr, depth], 80.0), orc.match([bgr, depth], 80.0))
+    _check_stages(orc, det, 2, 2, ("cg", "dn"))
+
+
+# ---------------------------------------------------------------------------------------------- matching
+def test_coarse_similarity_maps_bit_exact():
+    orc, det, views = _pair(n_views=8, n_random=120, seed=9)
+    bgr, depth, _ = synth.compose_scene(1001, views[:4])
+    orc.build_front([bgr, depth])
+    det.build_front([bgr, depth])
+    n = orc.num_templates("obj")
+    assert n >= 120
+    for tid in range(n):
+        a, b = det.coarse_map("obj", tid), orc.coarse_map("obj", tid)
+        assert np.array_equal(a, b), "coarse map of template %d differs in %d cells" % (tid, np.count_nonzero(a != b))
+
+
+@pytest.mark.parametrize("threshold", [92.0, 80.0, 60.0])
+def test_match_lists_identical(threshold):
+    orc, det, views = _pair(n_views=10, n_random=60, seed=13, classes=("cpu_binary", "memoryChip2"))
+    for seed in (1001, 2000, 2001):
+        bgr, depth, _ = synth.compose_scene(seed, views[:5])
+        want = orc.match([bgr, depth], threshold, keep_candidates=True)
+        got = det.match([bgr, depth], threshold)
+        common.assert_matches_equal(det.last_presort(), orc.last_presort(), "pre-sort list")
+        common.assert_matches_equal(got, want)
+        assert det.last_work()["candidates"] == len(orc.last_candidates())
+    assert len(want) > 0
+
+
+def test_golden_scene_fixture():
+    """CUDA path against the committed fixture (no oracle involved at run time)."""
+    G = np.load(os.path.join(common.GOLDEN, "oracle_scene.npz"))
+    det = Detector()
+    det.set_option("debug_taps", 1)
+    flat, k = G["templates_flat"], 0
+    for _ in range(int(G["n_templates"][0])):
+        pyr = []
+        for _ in range(4):
+            w, h, lvl, nf = flat[k:k + 4]
+            pyr.append((int(w), int(h), int(lvl), flat[k + 4:k + 4 + 3 * nf].reshape(-1, 3)))
+            k += 4 + 3 * nf
+        det.addSyntheticTemplate(pyr, "obj")
+    got = det.match([G["bgr"], G["depth"]], 80.0)
+    common.assert_matches_equal(got, G["matches"])
+    common.assert_matches_equal(det.last_presort(), G["presort"], "pre-sort list")
+    hashes = []
+    for l in range(2):
+        for m in range(2):
+            for st in (Stage.QUANTIZED, Stage.SPREAD, Stage.RESPONSE, Stage.LINEAR):
+                hashes.append("%d/%d/%d:%s" % (l, m, st, common.sha(det.fetch(st, l, m))))
+    assert hashes == list(G["stage_hashes"])
+
+
+def test_class_filter_order_and_unknown_ids():
+    orc, det, views = _pair(n_views=6, n_random=20, seed=17, classes=("a", "b", "c"))
+    bgr, depth, _ = synth.compose_scene(5, views[:4])
+    for ids in (["b"], ["c", "a"], ["a", "zzz", "a"], ["zzz"]):
+        common.assert_matches_equal(det.match([bgr, depth], 75.0, class_ids=ids), orc.match([bgr, depth], 75.0, class_ids=ids), str(ids))
+        common.assert_matches_equal(det.last_presort(), orc.last_presort(), "pre-sort " + str(ids))
+
+
+def test_single_modality_and_single_level():
+    for kinds, T in ((("cg",), (5, 8)), (("cg",), (8,)), (("dn",), (4, 8)), (("cg", "dn"), (8,))):
+        orc, det, views = _pair(kinds=kinds, T=T, n_views=6, n_random=30, seed=23)
+        bgr, depth, _ = synth.compose_scene(31, views[:3], rows=240, cols=320)
+        src = common.sources_for(kinds, bgr, depth)
+        thr = 70.0 if len(T) > 1 else 85.0
+        common.assert_matches_equal(det.match(src, thr), orc.match(src, thr), "%s %s" % (kinds, T))
+        common.assert_matches_equal(det.last_presort(), orc.last_presort(), "pre-sort %s %s" % (kinds, T))
+
+
+def test_three_levels():
+    orc, det, views = _pair(T=(2, 4, 8), n_views=6, n_random=20, seed=29, canvas=(160, 160))
+    bgr, depth, _ = synth.compose_scene(3, views[:3], rows=320, cols=480)
+    common.assert_matches_equal(det.match([bgr, depth], 70.0), orc.match([bgr, depth], 70.0))
+    common.assert_matches_equal(det.last_presort(), orc.last_presort(), "pre-sort")
+
+
+def test_edge_templates():
+    """Template larger than the image (P <= 0), features outside the image, the (width, height) spill corner,
+    negative coordinates, a template with one feature, an empty class."""
+    kinds, T = ("cg", "dn"), (5, 8)
+    orc = O.OracleDetector(common.oracle_modalities(kinds), T)
+    det = Detector(common.product_modalities(kinds), T)
+
+    def add(pyr):
+        orc.add_synthetic_template("obj", pyr)
+        det.addSyntheticTemplate(pyr, "obj")
+
+    rng = np.random.default_rng(1)
+    f = lambda pts: np.array(pts, np.int32)
+    add([(700, 500, 0, f([[0, 0, 1], [700, 500, 2]])), (700, 500, 0, f([[5, 5, 0]])),
+         (350, 250, 1, f([[0, 0, 1], [349, 249, 3]])), (350, 250, 1, f([[3, 3, 0]]))])          # bigger than 640x480
+    add([(120, 80, 0, f([[0, 0, 1], [120, 80, 2], [639, 479, 3], [640, 10, 1], [10, 480, 1], [-3, 4, 2]])),
+         (120, 80, 0, f([[60, 40, 4]])),
+         (60, 40, 1, f([[0, 0, 1], [60, 40, 2], [319, 239, 5], [320, 3, 1], [-1, -1, 0]])),
+         (60, 40, 1, f([[30, 20, 6]]))])                                                        # out-of-bounds features
+    add([(80, 80, 0, f([[80, 80, 7]])), (80, 80, 0, f([[0, 0, 0]])), (40, 40, 1, f([[40, 40, 7]])), (40, 40, 1, f([[0, 0, 0]]))])
+    add([(8, 8, 0, np.zeros((0, 3), np.int32)), (8, 8, 0, f([[1, 1, 1]])), (4, 4, 1, np.zeros((0, 3), np.int32)), (4, 4, 1, f([[1, 1, 1]]))])
+    for _ in range(10):
+        add(synth.random_pyramid(rng, T=T, M=2, wh_range=(8, 600)))
+    views = common.rendered_views(3, 47)
+    bgr, depth, _ = synth.compose_scene(13, views)
+    orc.build_front([bgr, depth])
+    det.build_front([bgr, depth])
+    for tid in range(orc.num_templates("obj")):
+        assert np.array_equal(det.coarse_map("obj", tid), orc.coarse_map("obj", tid)), tid
+    for thr in (50.0, 10.0):
+        common.assert_matches_equal(det.match([bgr, depth], thr), orc.match([bgr, depth], thr), "thr %g" % thr)
+        common.assert_matches_equal(det.last_presort(), orc.last_presort(), "pre-sort thr %g" % thr)
+
+
+def test_no_templates_and_empty_results():
+    det = Detector()
+    bgr = np.zeros((480, 640, 3), np.uint8)
+    depth = np.zeros((480, 640), np.uint16)
+    assert len(det.match([bgr, depth], 90.0)) == 0
+    rng = np.random.default_rng(0)
+    det.addSyntheticTemplate(synth.random_pyramid(rng), "obj")
+    assert len(det.match([bgr, depth], 90.0)) == 0  # flat black frame: no responses above threshold
+
+
+def test_geometry_asserts_like_the_reference():
+    det = Detector()
+    with pytest.raises(LinemodError) as e:  # linearize: rows % T == 0 (1024 % 5 = 4)
+        det.match([np.zeros((1024, 1280, 3), np.uint8), np.zeros((1024, 1280), np.uint16)], 90.0)
+    assert e.value.code == -1 and "% T" in str(e.value)
+
+
+def test_many_candidates_overflow_and_growth():
+    """A loose threshold on a big template set overflows the initial candidate / result buffers; the library must
+    grow and still return the exact list."""
+    orc, det, views = _pair(n_views=4, n_random=300, seed=37)
+    bgr, depth, _ = synth.compose_scene(21, views[:3])
+    want = orc.match([bgr, depth], 20.0, keep_candidates=True)
+    got = det.match([bgr, depth], 20.0)
+    assert len(orc.last_candidates()) > (1 << 16)
+    common.assert_matches_equal(got, want)
+
+
+def test_add_template_on_gpu_matches_oracle():
+    kinds, T = ("cg", "dn"), (5, 8)
+    orc = O.OracleDetector(common.oracle_modalities(kinds), T)
+    det = Detector(common.product_modalities(kinds), T)
+    ok = 0
+    for (bgr, depth, mask) in common.rendered_views(12, 53, canvas=(240, 256)):
+        wt, wbb = orc.add_template([bgr, depth], "obj", mask)
+        gt, gbb = det.addTemplate([bgr, depth], "obj", mask)
+        assert gt == wt
+        if wt >= 0:
+            ok += 1
+            assert tuple(gbb) == tuple(wbb)
+            for (a, b) in zip(det.getTemplates("obj", gt), orc.get_template("obj", wt)):
+                assert a[:3] == b[:3] and np.array_equal(a[3], b[3])
+    assert ok >= 6
+    # without a mask (whole image) as well
+    bgr, depth, _ = synth.compose_scene(3, [], rows=120, cols=160)
+    wt, _ = orc.add_template([bgr, depth], "scene", None)
+    gt, _ = det.addTemplate([bgr, depth], "scene", None)
+    assert gt == wt
+    if wt >= 0:
+        for (a, b) in zip(det.getTemplates("scene", gt), orc.get_template("scene", wt)):
+            assert np.array_equal(a[3], b[3])
+
+
+def test_batch_equals_single_and_quantized_images(tmp_path):
+    orc, det, views = _pair(n_views=6, n_random=40, seed=59)
+    frames = [list(synth.compose_scene(2000 + i, views[:4])[:2]) for i in range(5)]
+    singles = [det.match(f, 85.0) for f in frames]
+    batch = det.match_batch(frames, 85.0)
+    for a, b, f in zip(singles, batch, frames):
+        common.assert_matches_equal(b, a)
+        common.assert_matches_equal(a, orc.match(f, 85.0))
+    m, q = det.match(frames[0], 85.0, quantized_images=True)
+    for l in range(2):
+        for mod in range(2):
+            assert np.array_equal(q[l * 2 + mod], orc.fetch(O.Stage.QUANTIZED, l, mod)) or True
+    orc.match(frames[0], 85.0)
+    for l in range(2):
+        for mod in range(2):
+            assert np.array_equal(q[l * 2 + mod], orc.fetch(O.Stage.QUANTIZED, l, mod))
+    # persistence round trip keeps results identical
+    p = tmp_path / "t.yml"
+    det.write(p)
+    again = Detector.read(p)
+    common.assert_matches_equal(again.match(frames[1], 85.0), singles[1])
+
+
+# ---------------------------------------------------------------------------------------------- full size
+def test_full_size_properties_20k_templates():
+    """BASELINE config 4 size (20 000 templates, 640x480): too slow for the scalar oracle in a test, so parity is
+    checked through size-independent properties: determinism, shard-union == whole, class-split == whole, and the
+    oracle on a random sample of templates."""
+    rng = np.random.default_rng(99)
+    det = Detector()
+    pyrs = [synth.random_pyramid(rng) for _ in range(20000)]
+    for i, p in enumerate(pyrs):
+        det.addSyntheticTemplate(p, "c%02d" % (i % 15))
+    views = common.rendered_views(4, 61)
+    bgr, depth, _ = synth.compose_scene(1001, views)
+    thr = 62.0
+    whole = det.match([bgr, depth], thr)
+    assert len(whole) > 0
+    common.assert_matches_equal(det.match([bgr, depth], thr), whole, "determinism")
+    # union of class-filtered runs (std::map order) == whole, before the global sort
+    pre_whole = det.last_presort()
+    pre_parts = []
+    for cid in det.classIds():
+        det.match([bgr, depth], thr, class_ids=[cid])
+        pre_parts.append(det.last_presort())
+    common.assert_matches_equal(np.concatenate(pre_parts), pre_whole, "class split")
+    # oracle on a sample of templates
+    orc = O.OracleDetector()
+    sample = sorted(rng.choice(20000, 200, replace=False))
+    keep = {}
+    for k, i in enumerate(sample):
+        orc.add_synthetic_template("s", pyrs[i])
+        keep[k] = ("c%02d" % (i % 15), i // 15)
+    orc.match([bgr, depth], thr)
+    pre_o = orc.last_presort()
+    ids = det.classIds()
+    for k, (cid, tid) in keep.items():
+        a = pre_whole[(pre_whole["class_index"] == ids.index(cid)) & (pre_whole["template_id"] == tid)]
+        b = pre_o[pre_o["template_id"] == k]
+        assert len(a) == len(b) and np.array_equal(a["x"], b["x"]) and np.array_equal(a["y"], b["y"]) and \
+            np.array_equal(a["similarity"], b["similarity"]), (cid, tid)
+
+
+def test_shard_union_equals_whole():
+    """lm_set_shard + lm_match_device + lm_finalize_raw: four template shards evaluated one after another on one GPU
+    (the N-rank layout without the collective) reproduce the unsharded match list exactly."""
+    import torch
+    from linemod_pose_estimation_b200 import RAW_DTYPE
+    from linemod_pose_estimation_b200.sharding import device_view
+    orc, det, views = _pair(n_views=8, n_random=80, seed=67, classes=("a", "b"))
+    bgr, depth, _ = synth.compose_scene(77, views[:4])
+    want = orc.match([bgr, depth], 70.0)
+    dev = torch.device("cuda", 0)
+    d_bgr = torch.from_numpy(bgr).to(dev)
+    d_depth = torch.from_numpy(depth.view(np.int16)).to(dev)
+    raws = []
+    for rank in range(4):
+        shard = Detector()
+        common.copy_templates(orc, shard)
+        shard.set_shard(rank, 4)
+        rec, cap = shard.match_device([d_bgr.data_ptr(), d_depth.data_ptr()], 480, 640, 70.0,
+                                      stream=torch.cuda.current_stream().cuda_stream)
+        block = device_view(rec, cap, dev).cpu().numpy()
+        hdr = block[:16].view(np.uint32)
+        assert hdr[2] == 0, "overflow"
+        raws.append(block[16:16 + int(hdr[0]) * RAW_DTYPE.itemsize].view(RAW_DTYPE).copy())
+    assert all(len(r) > 0 for r in raws)
+    common.assert_matches_equal(det.finalize_raw(np.concatenate(raws)), want)
+    common.assert_matches_equal(det.match([bgr, depth], 70.0), want)

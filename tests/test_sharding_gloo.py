@@ -1,0 +1,95 @@
+"""Multi-rank plumbing of the sharded matcher (frame broadcast, fixed-capacity all-gather of survivor blocks,
+finalisation on rank 0) on CPU with torch.distributed / gloo, world_size 2.  The rank-local CUDA matcher is replaced
+by the oracle restricted to the rank's template shard (tests may use the oracle; the product never does); the
+exchange and lm_finalize_raw are the product's own code."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import common
+
+torch = pytest.importorskip("torch")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, capacity, out_dir):
+    sys.path.insert(0, common.ROOT)
+    sys.path.insert(0, os.path.join(common.ROOT, "tests"))
+    import torch.distributed as dist
+    from common import O, synth
+    from linemod_pose_estimation_b200 import Detector
+    from linemod_pose_estimation_b200.sharding import ShardedMatcher, pack_block
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        orc, views = common.build_oracle(n_views=6, n_random=40, seed=71, classes=("a", "b"))
+        det = Detector()                      # host-only use: template bookkeeping + lm_finalize_raw
+        common.copy_templates(orc, det)
+        if rank == 0:
+            bgr, depth, _ = synth.compose_scene(1001, views[:4], rows=240, cols=320)
+        else:
+            bgr, depth = np.zeros((240, 320, 3), np.uint8), np.zeros((240, 320), np.uint16)
+        frame = [torch.from_numpy(bgr), torch.from_numpy(depth.view(np.int16))]
+
+        def local_match(tensors, threshold):
+            b = tensors[0].numpy()
+            d = tensors[1].numpy().view(np.uint16)
+            orc.match([b, d], threshold, keep_candidates=True)
+            raw = orc.last_raw()
+            mine = raw[raw["order_key"] % world == rank]     # this rank's template shard
+            return torch.from_numpy(pack_block(mine, 1 << 14))
+
+        sm = ShardedMatcher(local_match, det.finalize_raw, rank, world, capacity=capacity)
+        got = sm.match(frame, 70.0)
+        if rank == 0:
+            want = orc.match([bgr, depth], 70.0)
+            assert len(want) > 4
+            common.assert_matches_equal(got, want)
+            np.save(os.path.join(out_dir, "ok_%d.npy" % capacity), np.array([len(got), sm.capacity]))
+        else:
+            assert got is None
+            assert np.array_equal(frame[0].numpy(), synth.compose_scene(1001, views[:4], rows=240, cols=320)[0])  # broadcast arrived
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("capacity", [4096, 2])
+def test_sharded_match_world2(tmp_path, capacity):
+    """capacity=2 forces the second, larger gather round."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, capacity, str(tmp_path)), nprocs=2, join=True)
+    res = np.load(os.path.join(str(tmp_path), "ok_%d.npy" % capacity))
+    assert res[0] > 4
+    if capacity == 2:
+        assert res[1] > 2
+
+
+def test_block_roundtrip():
+    from linemod_pose_estimation_b200 import RAW_DTYPE
+    from linemod_pose_estimation_b200.sharding import pack_block, unpack_blocks
+    rng = np.random.default_rng(0)
+    raws = []
+    for n in (0, 3, 10):
+        r = np.zeros(n, RAW_DTYPE)
+        r["order_key"] = rng.integers(0, 100, n)
+        r["score"] = rng.integers(0, 252, n)
+        raws.append(r)
+    blocks = np.concatenate([pack_block(r, 16) for r in raws])
+    out, need = unpack_blocks(blocks, 3, 16)
+    assert need == 0 and all(np.array_equal(a, b) for a, b in zip(out, raws))
+    blocks = np.concatenate([pack_block(r, 4) for r in raws])
+    out, need = unpack_blocks(np.concatenate([b for b in [pack_block(r, 16)[:16 + 4 * 32] for r in raws]]), 3, 4)
+    assert need == 10
