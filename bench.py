@@ -260,6 +260,7 @@ def run_ours(args):
 
     # ---- e2e: public API, pinned host frames on rank 0, H2D + (broadcast) + match + (gather) + D2H + finalise
     coarse_ms, coarse_bytes, launches, n_matches = [], [], 0, 0
+    stage_ms = {"h2d": [], "front": [], "coarse": [], "refine": [], "d2h": []}
     bufs = sharded.frame_buffers(ROWS, COLS, ("cg", "dn")) if world > 1 else None
 
     def e2e_step(i, record):
@@ -273,6 +274,8 @@ def run_ours(args):
                     t = det.last_timings()
                     w = det.last_work()
                     coarse_ms.append(t["coarse"]); coarse_bytes.append(w["B_coarse"]); launches += t["launches"]
+                    for k in stage_ms:
+                        stage_ms[k].append(t[k])
             else:
                 if rank == 0:
                     bufs[0].copy_(torch.from_numpy(pb), non_blocking=True)
@@ -331,6 +334,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": len(CLASSES) * (ROWS * COLS * 3 + ROWS * COLS * 2),
                     "d2h_bytes_per_step": len(CLASSES) * (16 + 2048 * 32), "matches_per_step": n_matches / max(1, args.steps)},
             "gpu_launches": launches, "clocks": clock_info,
+            "stage_ms_per_match_call": {k: float(np.mean(v)) for k, v in stage_ms.items() if v},
         }
         print(json.dumps(line))
     if world > 1:

@@ -89,6 +89,7 @@ def make_background(seed, rows=480, cols=640):
     depth = 800.0 + rng.uniform(-0.25, 0.25) * (xx - cols / 2) + rng.uniform(-0.25, 0.25) * (yy - rows / 2)
     for _ in range(int(rng.integers(3, 9))):
         w, h = rng.integers(30, 140, 2)
+        w, h = int(min(w, cols // 2)), int(min(h, rows // 2))
         x0, y0 = int(rng.integers(0, cols - w)), int(rng.integers(0, rows - h))
         colour = rng.uniform(20, 235, 3)
         period = rng.uniform(6, 20)
