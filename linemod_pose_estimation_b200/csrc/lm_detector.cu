@@ -173,7 +173,7 @@ struct lm_detector {
   Lane lane[2];
   Pack pack;
   int shard_rank = 0, shard_world = 1;
-  int debug_taps = 0, coarse_variant = 0, timing = 1;
+  int debug_taps = 0, coarse_variant = 0, timing = 1, frontend_variant = 0;
   std::vector<std::string> class_id_cache;
 };
 
@@ -256,7 +256,7 @@ static int ensure_lm_ws(lm_detector* d, Lane& ln, int rows, int cols) {
   for (int l = 0; l < L; ++l) {
     LevelGeom& g = geom[l];
     g.rows = rows >> l; g.cols = cols >> l; g.T = d->model.T[l];
-    if (g.T < 1 || g.T > 32) return fail(LM_E_INVALID, "unsupported T=%d at level %d", g.T, l);
+    if (g.T < 1 || g.T > 16) return fail(LM_E_INVALID, "unsupported T=%d at level %d (1..16)", g.T, l);
     if (g.rows <= 0 || g.cols <= 0) return fail(LM_E_INVALID, "image too small for %d pyramid levels", L);
     if (((size_t)g.rows * g.cols) % 16 != 0)
       return fail(LM_E_INVALID, "(rows * cols) %% 16 != 0 at level %d (%dx%d)", l, g.cols, g.rows);  // computeResponseMaps
@@ -356,7 +356,8 @@ static int upload_frame(lm_detector* d, Lane& ln, const lm_image* sources, const
 
 // ------------------------------------------------------------------------------------------------ front end
 // [OCV] Modality::process + QuantizedPyramid::pyrDown for every level: fills quant_raw[l][m] (and mag[l][m]).
-static int run_quantize(lm_detector* d, Lane& ln, cudaStream_t s) {
+// Stage-by-stage kernels (lm_frontend.cu): the A/B reference of the fused path, selected by option frontend_variant=1.
+static int run_quantize_staged(lm_detector* d, Lane& ln, cudaStream_t s) {
   const int L = d->model.levels(), M = d->model.M();
   for (int m = 0; m < M; ++m) {
     const lm_modality_desc& md = d->model.mods[m];
@@ -392,21 +393,92 @@ static int run_quantize(lm_detector* d, Lane& ln, cudaStream_t s) {
   return LM_OK;
 }
 
+// Production path (lm_frontend_fused.cu): per ColorGradient modality the pyrDown chain plus ONE launch covering every
+// level, per DepthNormal modality ONE launch.
+static int run_quantize(lm_detector* d, Lane& ln, cudaStream_t s) {
+  if (d->frontend_variant == 1) return run_quantize_staged(d, ln, s);
+  const int L = d->model.levels(), M = d->model.M();
+  for (int m = 0; m < M; ++m) {
+    const lm_modality_desc& md = d->model.mods[m];
+    if (md.type == LM_COLOR_GRADIENT) {
+      CgParams cp;
+      std::memset(&cp, 0, sizeof(cp));
+      cp.n_levels = L;
+      cp.thr_sq = md.weak_threshold * md.weak_threshold;
+      int total = 0;
+      for (int l = 0; l < L; ++l) {
+        const int rows = ln.rows >> l, cols = ln.cols >> l;
+        if (l > 0) {
+          const uint8_t* prev = l == 1 ? (const uint8_t*)ln.src_ptr[m] : ln.bgr[l - 1][m].as<uint8_t>();
+          launch_pyrdown_u8c3(prev, ln.rows >> (l - 1), ln.cols >> (l - 1), ln.bgr[l][m].as<uint8_t>(), s);
+          ++ln.launches;
+        }
+        CgLevel& lv = cp.lv[l];
+        lv.src = l == 0 ? (const uint8_t*)ln.src_ptr[m] : ln.bgr[l][m].as<uint8_t>();
+        lv.mag = ln.mag[l][m].as<float>();
+        lv.quant = ln.quant_raw[l][m].as<uint8_t>();
+        lv.rows = rows; lv.cols = cols; lv.block_begin = total;
+        total += cg_fused_blocks(rows, cols, &lv.blocks_x);
+      }
+      launch_cg_fused(cp, total, s);
+      ++ln.launches;
+    } else {
+      DnParams dp;
+      std::memset(&dp, 0, sizeof(dp));
+      dp.depth = (const uint16_t*)ln.src_ptr[m];
+      dp.lut = d->d_normal_lut.as<uint8_t>();
+      dp.rows = ln.rows; dp.cols = ln.cols; dp.n_levels = L;
+      dp.distance_threshold = md.distance_threshold; dp.difference_threshold = md.difference_threshold;
+      for (int l = 0; l < L; ++l) dp.quant[l] = ln.quant_raw[l][m].as<uint8_t>();
+      launch_dn_fused(dp, s);
+      ++ln.launches;
+    }
+  }
+  CU(cudaGetLastError());
+  return LM_OK;
+}
+
 // [OCV] Detector::match front half: quantize (mask) -> spread -> computeResponseMaps -> linearize per level/modality.
 static int run_front(lm_detector* d, Lane& ln, cudaStream_t s) {
   const int L = d->model.levels(), M = d->model.M();
   if (run_quantize(d, ln, s) != LM_OK) return LM_E_CUDA;
   const bool taps = d->debug_taps != 0;
   if (taps && ensure_tap_ws(d, ln) != LM_OK) return LM_E_CUDA;
-  for (int l = 0; l < L; ++l) {
-    const LevelGeom& g = ln.geom[l];
-    for (int m = 0; m < M; ++m) {
-      launch_spread_lm(ln.quant_raw[l][m].as<uint8_t>(), ln.has_mask[m] ? ln.mask0[m].as<uint8_t>() : nullptr, ln.cols, l,
-                       g.rows, g.cols, g.T, d->d_resp_all.as<uint32_t>(), ln.quantized[l][m].as<uint8_t>(),
-                       taps ? ln.spread[l][m].as<uint8_t>() : nullptr, taps ? ln.response[l][m].as<uint8_t>() : nullptr,
-                       ln.lmem[l].as<uint8_t>() + (size_t)m * 8 * g.plane_stride, g.plane_stride, s);
-      ++ln.launches;
+  if (d->frontend_variant == 1) {
+    for (int l = 0; l < L; ++l) {
+      const LevelGeom& g = ln.geom[l];
+      for (int m = 0; m < M; ++m) {
+        launch_spread_lm(ln.quant_raw[l][m].as<uint8_t>(), ln.has_mask[m] ? ln.mask0[m].as<uint8_t>() : nullptr, ln.cols, l,
+                         g.rows, g.cols, g.T, d->d_resp_all.as<uint32_t>(), ln.quantized[l][m].as<uint8_t>(),
+                         taps ? ln.spread[l][m].as<uint8_t>() : nullptr, taps ? ln.response[l][m].as<uint8_t>() : nullptr,
+                         ln.lmem[l].as<uint8_t>() + (size_t)m * 8 * g.plane_stride, g.plane_stride, s);
+        ++ln.launches;
+      }
     }
+  } else {
+    SpreadParams sp;
+    std::memset(&sp, 0, sizeof(sp));
+    sp.resp_all = d->d_resp_all.as<uint32_t>();
+    int total = 0, max_T = 1;
+    for (int l = 0; l < L; ++l) {
+      const LevelGeom& g = ln.geom[l];
+      max_T = std::max(max_T, g.T);
+      for (int m = 0; m < M; ++m) {
+        SpreadEntry& e = sp.e[sp.n++];
+        e.qraw = ln.quant_raw[l][m].as<uint8_t>();
+        e.mask0 = ln.has_mask[m] ? ln.mask0[m].as<uint8_t>() : nullptr;
+        e.quantized = ln.quantized[l][m].as<uint8_t>();
+        e.spread = taps ? ln.spread[l][m].as<uint8_t>() : nullptr;
+        e.response = taps ? ln.response[l][m].as<uint8_t>() : nullptr;
+        e.lm = ln.lmem[l].as<uint8_t>() + (size_t)m * 8 * g.plane_stride;
+        e.plane_stride = g.plane_stride;
+        e.rows = g.rows; e.cols = g.cols; e.T = g.T; e.W = g.W; e.H = g.H; e.level = l; e.mask_cols0 = ln.cols;
+        e.block_begin = total;
+        total += spread_all_blocks(g.W, g.H, &e.blocks_x);
+      }
+    }
+    if (!launch_spread_all(sp, total, max_T, s)) return fail(LM_E_INVALID, "T=%d needs too much shared memory", max_T);
+    ++ln.launches;
   }
   CU(cudaGetLastError());
   ln.front_valid = true;
@@ -1086,6 +1158,7 @@ int lm_set_option(lm_detector* d, const char* key, int value) {
   if (k == "debug_taps") d->debug_taps = value;
   else if (k == "coarse_variant") d->coarse_variant = value;
   else if (k == "timing") d->timing = value;
+  else if (k == "frontend_variant") { d->frontend_variant = value; for (int i = 0; i < 2; ++i) d->lane[i].front_valid = false; }
   else return fail(LM_E_INVALID, "unknown option '%s'", key);
   return LM_OK;
 }

@@ -70,6 +70,45 @@ void launch_spread_lm(const uint8_t* quant_raw, const uint8_t* mask0, int mask_c
                       int T, const uint32_t* resp_all, uint8_t* quantized_out, uint8_t* spread_out,
                       uint8_t* response_out, uint8_t* lm, size_t plane_stride, cudaStream_t s);
 
+// ------------------------------------------------------------------------------------------------ fused front end
+struct CgLevel {
+  const uint8_t* src;  // BGR source of this level (level >= 1: output of k_pyrdown_u8c3)
+  float* mag;          // [rows][cols] squared gradient magnitude (exact integer in f32)
+  uint8_t* quant;      // [rows][cols] one-hot quantised orientation (unmasked)
+  int rows, cols, block_begin, blocks_x;
+};
+struct CgParams {
+  CgLevel lv[LM_MAX_LEVELS];
+  int n_levels;
+  float thr_sq;  // weak_threshold^2
+};
+struct DnParams {
+  const uint16_t* depth;
+  const uint8_t* lut;  // NORMAL_LUT, 8000 bytes
+  uint8_t* quant[LM_MAX_LEVELS];
+  int rows, cols, n_levels, distance_threshold, difference_threshold;
+};
+struct SpreadEntry {
+  const uint8_t* qraw;   // unmasked quantisation of this (level, modality)
+  const uint8_t* mask0;  // level-0 mask or null
+  uint8_t* quantized;    // masked quantisation (Detector::match's quantized_images)
+  uint8_t* spread;       // parity tap or null
+  uint8_t* response;     // parity tap or null
+  uint8_t* lm;           // this modality's 8 orientation planes
+  unsigned long long plane_stride;
+  int rows, cols, T, W, H, level, mask_cols0, block_begin, blocks_x;
+};
+struct SpreadParams {
+  SpreadEntry e[LM_MAX_LEVELS * LM_MAX_MODALITIES];
+  const uint32_t* resp_all;
+  int n;
+};
+int cg_fused_blocks(int rows, int cols, int* blocks_x);
+void launch_cg_fused(const CgParams& p, int total_blocks, cudaStream_t s);
+void launch_dn_fused(const DnParams& p, cudaStream_t s);
+int spread_all_blocks(int W, int H, int* blocks_x);
+bool launch_spread_all(const SpreadParams& p, int total_blocks, int max_T, cudaStream_t s);
+
 // ------------------------------------------------------------------------------------------------ matching
 // dump (nullable): u16 totals, [work index][W*H], written for every scored position (parity tap).
 void launch_similarity_coarse(const uint8_t* lmc, const uint32_t* foff, const CoarseTpl* tpl, const uint32_t* work,

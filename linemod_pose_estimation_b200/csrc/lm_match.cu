@@ -16,49 +16,55 @@ namespace lmk {
 
 namespace {
 
-constexpr int kLanePos = 16;             // positions per lane and pass (one 128-bit load)
-constexpr int kWarpPos = 31 * kLanePos;  // positions per warp pass; lane 31 only supplies lane 30's tail bytes
+constexpr int kLanePos = 16;             // positions per lane and pass (one 128-bit window)
+constexpr int kWarpPos = 32 * kLanePos;  // positions per warp pass
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ uint4 ldg128(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ uint2 ldg64(const uint8_t* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ uint32_t ldg32(const uint8_t* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
 
-// One feature's contribution to this lane's 16 positions.  `a` (warp-uniform) is the flat byte address of the first
-// position of the pass; Q = (a & 15) >> 2 is a compile-time constant because the packer groups a template's features
-// by it.  The lane loads the aligned 16 bytes below its window, takes the Q+1 following words from its right-hand
-// neighbour by shuffle, and realigns with byte permutes.
+// One feature's contribution to this lane's 16 positions.  `a` is the flat byte address of the lane's first position;
+// Q = (a & 15) >> 2 is a compile-time constant because the packer groups a template's features by it.  The lane loads
+// the aligned 16 bytes at or below its window plus the Q+1 following words, and realigns with byte permutes.
 template <int Q>
-__device__ __forceinline__ void add_feature(const uint8_t* __restrict__ lmc, uint32_t a, int lane, bool active,
-                                            uint32_t (&acc)[4]) {
-  const uint32_t base = a & ~15u;
+__device__ __forceinline__ void add_feature(const uint8_t* __restrict__ lmc, uint32_t a, uint32_t (&acc)[4]) {
+  const uint8_t* p = lmc + (a & ~15u);
   const uint32_t sel = 0x3210u + 0x1111u * (a & 3u);
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (active) v = ldg128(lmc + base + lane * kLanePos);
   uint32_t w[8];
+  const uint4 v = ldg128(p);
   w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-  w[4] = __shfl_down_sync(kFull, v.x, 1);
-  w[5] = Q >= 1 ? __shfl_down_sync(kFull, v.y, 1) : 0;
-  w[6] = Q >= 2 ? __shfl_down_sync(kFull, v.z, 1) : 0;
-  w[7] = Q >= 3 ? __shfl_down_sync(kFull, v.w, 1) : 0;
+  if (Q == 0) {
+    w[4] = ldg32(p + 16);
+  } else if (Q == 1) {
+    const uint2 n = ldg64(p + 16);
+    w[4] = n.x; w[5] = n.y;
+  } else {
+    const uint4 n = ldg128(p + 16);
+    w[4] = n.x; w[5] = n.y; w[6] = n.z; w[7] = n.w;
+  }
 #pragma unroll
   for (int k = 0; k < 4; ++k) acc[k] += __byte_perm(w[Q + k], w[Q + k + 1], sel);
 }
 
 template <int Q>
 __device__ __forceinline__ void add_group(const uint8_t* __restrict__ lmc, const uint32_t* __restrict__ foff, int n,
-                                          uint32_t j0, int lane, bool active, uint32_t (&acc)[4]) {
+                                          uint32_t lane_off, uint32_t (&acc)[4]) {
   int f = 0;
-  for (; f + 4 <= n; f += 4) {  // four independent loads in flight per lane
-    uint32_t a0 = foff[f] + j0, a1 = foff[f + 1] + j0, a2 = foff[f + 2] + j0, a3 = foff[f + 3] + j0;
-    add_feature<Q>(lmc, a0, lane, active, acc);
-    add_feature<Q>(lmc, a1, lane, active, acc);
-    add_feature<Q>(lmc, a2, lane, active, acc);
-    add_feature<Q>(lmc, a3, lane, active, acc);
+  for (; f + 4 <= n; f += 4) {  // four independent window loads in flight per lane
+    const uint32_t a0 = foff[f] + lane_off, a1 = foff[f + 1] + lane_off, a2 = foff[f + 2] + lane_off,
+                   a3 = foff[f + 3] + lane_off;
+    add_feature<Q>(lmc, a0, acc);
+    add_feature<Q>(lmc, a1, acc);
+    add_feature<Q>(lmc, a2, acc);
+    add_feature<Q>(lmc, a3, acc);
   }
-  for (; f < n; ++f) add_feature<Q>(lmc, foff[f] + j0, lane, active, acc);
+  for (; f < n; ++f) add_feature<Q>(lmc, foff[f] + lane_off, acc);
 }
 
 // Coarse similarity of every (template, position) at the lowest pyramid level, thresholded in registers.
-// A warp owns one (template, 496-position pass) tile; tiles are dealt round-robin to a persistent grid.
+// A warp owns one (template, 512-position pass) tile; tiles are dealt round-robin to a persistent grid.  There are no
+// warp collectives in the hot loop: every lane fetches its own (unaligned) 16-byte window with two vector loads.
 __global__ void __launch_bounds__(256) k_similarity_coarse(const uint8_t* __restrict__ lmc,
                                                            const uint32_t* __restrict__ foff,
                                                            const CoarseTpl* __restrict__ tpl,
@@ -76,21 +82,23 @@ __global__ void __launch_bounds__(256) k_similarity_coarse(const uint8_t* __rest
     const int pass = tile - wi * passes_per_tpl;
     const uint32_t tg = work[wi];
     const int t_P = tpl[tg].P;
-    const uint32_t t_feat_begin = tpl[tg].feat_begin, t_nf = tpl[tg].nf;
     const int j0 = pass * kWarpPos;
     if (j0 >= t_P) continue;
-    const int rem = min(t_P - j0, kWarpPos);            // positions of this pass
-    const bool active = lane * kLanePos < rem + kLanePos;  // lanes whose bytes somebody needs
+    const int rem = min(t_P - j0, kWarpPos);  // positions of this pass
+    const int first = lane * kLanePos;        // first position of this lane within the pass
+    if (first >= rem) continue;               // lane has no position to score
+    const uint32_t t_feat_begin = tpl[tg].feat_begin, t_nf = tpl[tg].nf;
+    const uint32_t lane_off = (uint32_t)(j0 + first);
     uint32_t tot_lo[4] = {0, 0, 0, 0}, tot_hi[4] = {0, 0, 0, 0};  // u16 x 2 per word: bytes (0,2) and (1,3)
     const uint32_t* fp = foff + t_feat_begin;
     for (int m = 0; m < M; ++m) {
       uint32_t acc[4] = {0, 0, 0, 0};
       const uint32_t c4 = __ldg(reinterpret_cast<const uint32_t*>(tpl[tg].cnt) + m);  // 4 group sizes, one word
       const int n0 = c4 & 255, n1 = (c4 >> 8) & 255, n2 = (c4 >> 16) & 255, n3 = c4 >> 24;
-      add_group<0>(lmc, fp, n0, (uint32_t)j0, lane, active, acc); fp += n0;
-      add_group<1>(lmc, fp, n1, (uint32_t)j0, lane, active, acc); fp += n1;
-      add_group<2>(lmc, fp, n2, (uint32_t)j0, lane, active, acc); fp += n2;
-      add_group<3>(lmc, fp, n3, (uint32_t)j0, lane, active, acc); fp += n3;
+      add_group<0>(lmc, fp, n0, lane_off, acc); fp += n0;
+      add_group<1>(lmc, fp, n1, lane_off, acc); fp += n1;
+      add_group<2>(lmc, fp, n2, lane_off, acc); fp += n2;
+      add_group<3>(lmc, fp, n3, lane_off, acc); fp += n3;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {  // [OCV] addSimilarities: widen u8 -> u16 and add the modality
         tot_lo[k] += acc[k] & 0x00ff00ffu;
@@ -98,19 +106,15 @@ __global__ void __launch_bounds__(256) k_similarity_coarse(const uint8_t* __rest
       }
     }
     const int thr = raw_thr_by_nf[t_nf];
-    const int first = lane * kLanePos;  // first position of this lane within the pass
-    bool hit = false;
-    if (first < rem) {
-      if (thr < 0) hit = true;
-      else {
-        const uint32_t thr2 = (uint32_t)min(thr, 0xffff) * 0x00010001u;
-        uint32_t any = 0;
+    bool hit = thr < 0;
+    if (!hit) {
+      const uint32_t thr2 = (uint32_t)min(thr, 0xffff) * 0x00010001u;
+      uint32_t any = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) any |= __vcmpgtu2(tot_lo[k], thr2) | __vcmpgtu2(tot_hi[k], thr2);
-        hit = any != 0;
-      }
+      for (int k = 0; k < 4; ++k) any |= __vcmpgtu2(tot_lo[k], thr2) | __vcmpgtu2(tot_hi[k], thr2);
+      hit = any != 0;
     }
-    if (dump != nullptr && first < rem) {
+    if (dump != nullptr) {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -141,34 +145,35 @@ __global__ void __launch_bounds__(256) k_similarity_coarse(const uint8_t* __rest
   }
 }
 
-// Local refinement of every coarse candidate up the pyramid.  One warp per candidate; lane -> (patch row = lane / 2,
-// 8 columns = lane % 2) of the 16 x 16 neighbourhood.
-__global__ void __launch_bounds__(256) k_refine(const RefineParams P, const CoarseTpl* __restrict__ ctpl,
-                                                const uint32_t* __restrict__ work_order, const Cand* __restrict__ cand,
-                                                uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+// Local refinement of every coarse candidate up the pyramid.  One 8-warp block per candidate: the 16 x 16 patch is
+// mapped lane -> (row = lane / 2, 8 columns = lane % 2) in every warp, the template's features are dealt round-robin
+// to the warps (each keeps its own u8 accumulators), and the per-warp u16 partial sums meet in shared memory.
+constexpr int kRefineWarps = 8;
+
+__global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams P, const CoarseTpl* __restrict__ ctpl,
+                                                             const uint32_t* __restrict__ work_order,
+                                                             const Cand* __restrict__ cand, uint32_t cand_cap,
+                                                             ResultHeader* hdr, lm_raw_match* __restrict__ out) {
+  __shared__ uint32_t s_part[kRefineWarps][32][4];
+  __shared__ int s_state[4];  // x, y, alive, best_score
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n_cands = min(hdr->n_cands, cand_cap);
   if (blockIdx.x == 0 && threadIdx.x == 0 && hdr->n_cands > cand_cap) hdr->overflow = 1;  // candidate list truncated
   const int prow = lane >> 1, pcol0 = (lane & 1) * 8;
-  for (uint32_t ci = warp; ci < n_cands; ci += n_warps) {
+  for (uint32_t ci = blockIdx.x; ci < n_cands; ci += gridDim.x) {
     const Cand c = cand[ci];
-    const uint32_t ct_nf = ctpl[c.tglob].nf;
     const int cT = P.coarse_T;
     const int coff = cT / 2 + (cT % 2 - 1);
     int x = (int)(c.pos % (uint32_t)P.coarse_W) * cT + coff;
     int y = (int)(c.pos / (uint32_t)P.coarse_W) * cT + coff;
-    uint32_t score = c.raw, nf = ct_nf;
+    uint32_t score = c.raw, nf = ctpl[c.tglob].nf;
     bool alive = true;
     for (int l = P.levels - 2; l >= 0 && alive; --l) {
       const RefineLevel& L = P.level[l];
       const RefineTpl* rtp = L.tpl + c.tglob;
-      const int rt_width = rtp->width, rt_height = rtp->height;
-      const uint32_t rt_nf = rtp->nf;
       const int T = L.T, W = L.W;
       const int border = 8 * T, off = T / 2 + (T % 2 - 1);
-      const int max_x = L.cols - rt_width - border, max_y = L.rows - rt_height - border;
+      const int max_x = L.cols - rtp->width - border, max_y = L.rows - rtp->height - border;
       x = x * 2 + 1; y = y * 2 + 1;
       x = max(x, border); y = max(y, border);
       x = min(x, max_x); y = min(y, max_y);
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(256) k_refine(const RefineParams P, const Coar
         const uint8_t* lmm = L.lm + (size_t)m * 8 * L.plane_stride;
         const int n = rtp->cnt[m];
 #pragma unroll 4
-        for (int f = 0; f < n; ++f) {
+        for (int f = warp; f < n; f += kRefineWarps) {
           uint32_t pk = fp[f];
           int fx = (int)(pk & 0x1fffu) - 4096 + offset_x, fy = (int)((pk >> 13) & 0x1fffu) - 4096 + offset_y;
           if (fx < 0 || fy < 0 || fx >= L.cols || fy >= L.rows) continue;
@@ -190,9 +195,7 @@ __global__ void __launch_bounds__(256) k_refine(const RefineParams P, const Coar
                         fx / T + (size_t)prow * W + pcol0;
           const uint8_t* p = lmm + (addr & ~(size_t)3);
           const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(addr & 3);
-          uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(p));
-          uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(p + 4));
-          uint32_t w2 = __ldg(reinterpret_cast<const uint32_t*>(p + 8));
+          uint32_t w0 = ldg32(p), w1 = ldg32(p + 4), w2 = ldg32(p + 8);
           a0 += __byte_perm(w0, w1, sel);
           a1 += __byte_perm(w1, w2, sel);
         }
@@ -200,29 +203,47 @@ __global__ void __launch_bounds__(256) k_refine(const RefineParams P, const Coar
         tot[0] += a0 & 0x00ff00ffu; tot[1] += (a0 >> 8) & 0x00ff00ffu;
         tot[2] += a1 & 0x00ff00ffu; tot[3] += (a1 >> 8) & 0x00ff00ffu;
       }
-      // first maximum in raster order: key = score << 8 | (255 - raster index)
-      uint32_t best_key = 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        uint32_t src = tot[(i >> 2) * 2 + (i & 1)];
-        uint32_t sc = (i & 2) ? (src >> 16) : (src & 0xffffu);
-        uint32_t key = (sc << 8) | (uint32_t)(255 - (prow * 16 + pcol0 + i));
-        best_key = max(best_key, key);
+      for (int k = 0; k < 4; ++k) s_part[warp][lane][k] = tot[k];
+      __syncthreads();
+      if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t s = 0;
+#pragma unroll
+          for (int w = 0; w < kRefineWarps; ++w) s += s_part[w][lane][k];
+          tot[k] = s;
+        }
+        // first maximum in raster order: key = score << 8 | (255 - raster index)
+        uint32_t best_key = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint32_t src = tot[(i >> 2) * 2 + (i & 1)];
+          uint32_t sc = (i & 2) ? (src >> 16) : (src & 0xffffu);
+          uint32_t key = (sc << 8) | (uint32_t)(255 - (prow * 16 + pcol0 + i));
+          best_key = max(best_key, key);
+        }
+        best_key = __reduce_max_sync(kFull, best_key);
+        if (lane == 0) {
+          const int best_score = (int)(best_key >> 8);
+          int best_r = -1, best_c = -1;
+          if (best_score > 0) {
+            int idx = 255 - (int)(best_key & 0xffu);
+            best_r = idx >> 4; best_c = idx & 15;
+          }
+          const int nfl = (int)rtp->nf;
+          float sim = __fdiv_rn(__fmul_rn((float)best_score, 100.f), (float)(4 * nfl));
+          s_state[0] = (x / T - 8 + best_c) * T + off;
+          s_state[1] = (y / T - 8 + best_r) * T + off;
+          s_state[2] = (sim < P.threshold) ? 0 : 1;  // [OCV] remove_if(MatchPredicate(threshold))
+          s_state[3] = best_score;
+        }
       }
-      best_key = __reduce_max_sync(kFull, best_key);
-      const int best_score = (int)(best_key >> 8);
-      int best_r = -1, best_c = -1;
-      if (best_score > 0) {
-        int idx = 255 - (int)(best_key & 0xffu);
-        best_r = idx >> 4; best_c = idx & 15;
-      }
-      x = (x / T - 8 + best_c) * T + off;
-      y = (y / T - 8 + best_r) * T + off;
-      score = (uint32_t)best_score; nf = rt_nf;
-      float sim = __fdiv_rn(__fmul_rn((float)best_score, 100.f), (float)(4 * (int)nf));
-      if (sim < P.threshold) alive = false;  // [OCV] remove_if(MatchPredicate(threshold))
+      __syncthreads();
+      x = s_state[0]; y = s_state[1]; alive = s_state[2] != 0; score = (uint32_t)s_state[3]; nf = rtp->nf;
+      __syncthreads();  // s_state / s_part are rewritten by the next level
     }
-    if (alive && lane == 0) {
+    if (alive && threadIdx.x == 0) {
       uint32_t idx = atomicAdd(&hdr->count, 1u);
       if (idx < hdr->capacity) {
         lm_raw_match r;
@@ -245,7 +266,7 @@ void launch_similarity_coarse(const uint8_t* lmc, const uint32_t* foff, const Co
   const int passes = (max_P + kWarpPos - 1) / kWarpPos;
   const long long tiles = (long long)n_work * passes;
   int blocks = (int)((tiles + 7) / 8);
-  const int persistent = 148 * 8;  // one wave of 8 resident CTAs (64 warps) per SM
+  const int persistent = 148 * 8;  // up to 8 resident CTAs (64 warps) per SM
   if (blocks > persistent) blocks = persistent;
   k_similarity_coarse<<<blocks, 256, 0, s>>>(lmc, foff, tpl, work, n_work, passes, raw_thr_by_nf, M, cand, hdr,
                                              cand_cap, dump, dump_stride);
@@ -253,7 +274,7 @@ void launch_similarity_coarse(const uint8_t* lmc, const uint32_t* foff, const Co
 
 void launch_refine(const RefineParams& p, const CoarseTpl* ctpl, const uint32_t* work_order, const Cand* cand,
                    uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* out, cudaStream_t s) {
-  k_refine<<<148 * 2, 256, 0, s>>>(p, ctpl, work_order, cand, cand_cap, hdr, out);
+  k_refine<<<148 * 4, kRefineWarps * 32, 0, s>>>(p, ctpl, work_order, cand, cand_cap, hdr, out);
 }
 
 }  // namespace lmk

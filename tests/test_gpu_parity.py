@@ -53,8 +53,10 @@ def test_front_end_taps_bit_exact(rows, cols, T, kinds):
         bgr, depth, _ = synth.compose_scene(seed, views, rows=rows, cols=cols)
         src = common.sources_for(kinds, bgr, depth)
         orc.build_front(src)
-        det.build_front(src)
-        _check_stages(orc, det, len(T), len(kinds), kinds)
+        for variant in (0, 1):  # 0: fused production kernels, 1: stage-by-stage A/B reference kernels
+            det.set_option("frontend_variant", variant)
+            det.build_front(src)
+            _check_stages(orc, det, len(T), len(kinds), kinds)
         for l in range(len(T)):
             go, gd = orc.geometry(l), det.geometry(l)
             assert go == gd
