@@ -148,6 +148,19 @@ int lm_add_synthetic_template(lm_detector* det, const char* class_id, int n_temp
 int lm_match(lm_detector* det, const lm_image* sources, int n_sources, float threshold, const char* const* class_ids,
              int n_ids, const lm_image* masks, int n_masks, lm_image_out* quantized_out, lm_match_rec** out_matches,
              size_t* out_n);
+/* Several (class list, threshold) queries answered from ONE front end of the frame -- what the reference's service
+ * does with two detectors on the same image (object "memoryChip2" at 92, "cpu_binary" at 94,
+ * /root/reference/launch/start_object_detection.launch:8,19), without quantising the frame twice.
+ * out_offsets receives n_queries+1 prefix offsets into out_matches; each query's slice is sorted / de-duplicated
+ * exactly like a separate lm_match call with that class list and threshold. */
+typedef struct {
+  float threshold;
+  const char* const* class_ids; /* n_ids == 0: all classes */
+  int n_ids;
+} lm_query;
+int lm_match_multi(lm_detector* det, const lm_image* sources, int n_sources, const lm_query* queries, int n_queries,
+                   const lm_image* masks, int n_masks, lm_image_out* quantized_out, lm_match_rec** out_matches,
+                   size_t* out_offsets);
 /* The same over a batch of frames (sources[f*n_sources + m]); frames are pipelined over internal streams so that the
  * host->device copy of frame f+1 overlaps the kernels of frame f.  out_offsets receives n_frames+1 prefix offsets
  * into out_matches. */
@@ -173,6 +186,10 @@ typedef struct {
 int lm_match_device(lm_detector* det, const void* const* d_sources, int n_sources, int rows, int cols, float threshold,
                     const char* const* class_ids, int n_ids, void* stream, const void** d_records,
                     size_t* record_bytes_capacity);
+/* Multi-query form: region q (q < n_queries) starts at *d_records + q * *region_stride_bytes. */
+int lm_match_device_multi(lm_detector* det, const void* const* d_sources, int n_sources, int rows, int cols,
+                          const lm_query* queries, int n_queries, void* stream, const void** d_records,
+                          size_t* region_stride_bytes);
 int lm_finalize_raw(const lm_detector* det, const lm_raw_match* raw, size_t n_raw, lm_match_rec** out_matches,
                     size_t* out_n);
 /* Template sharding (north-star multi-GPU layout): keep only templates whose canonical order index i satisfies

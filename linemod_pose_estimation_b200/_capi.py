@@ -30,6 +30,10 @@ class LmModalityDesc(C.Structure):
                 ("extract_threshold", C.c_int32), ("num_features", C.c_int32)]
 
 
+class LmQuery(C.Structure):
+    _fields_ = [("threshold", C.c_float), ("class_ids", C.POINTER(C.c_char_p)), ("n_ids", C.c_int)]
+
+
 class LmRect(C.Structure):
     _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("width", C.c_int32), ("height", C.c_int32)]
 
@@ -46,8 +50,8 @@ EXPORTS = [
     "lm_create", "lm_create_from_yaml", "lm_write_yaml", "lm_read_classes", "lm_write_classes", "lm_destroy",
     "lm_last_error", "lm_alloc_pinned", "lm_free_pinned", "lm_device", "lm_pyramid_levels", "lm_get_T",
     "lm_num_modalities", "lm_get_modality", "lm_num_classes", "lm_num_templates", "lm_class_id", "lm_get_templates",
-    "lm_add_template", "lm_add_template_from_quantized", "lm_add_synthetic_template", "lm_match", "lm_match_batch", "lm_free_matches",
-    "lm_match_device", "lm_finalize_raw", "lm_set_shard", "lm_set_similarity_lut", "lm_get_similarity_lut",
+    "lm_add_template", "lm_add_template_from_quantized", "lm_add_synthetic_template", "lm_match", "lm_match_multi", "lm_match_batch", "lm_free_matches",
+    "lm_match_device", "lm_match_device_multi", "lm_finalize_raw", "lm_set_shard", "lm_set_similarity_lut", "lm_get_similarity_lut",
     "lm_set_normal_lut", "lm_get_normal_lut", "lm_debug_fetch", "lm_build_front", "lm_level_geometry",
     "lm_debug_coarse_map", "lm_debug_presort", "lm_last_timings", "lm_last_work", "lm_set_option",
 ]
@@ -97,6 +101,10 @@ def lib():
     L.lm_add_synthetic_template.argtypes = [vp, cp, ci, vp, vp]
     L.lm_match.argtypes = [vp, C.POINTER(LmImage), ci, C.c_float, C.POINTER(cp), ci, C.POINTER(LmImage), ci,
                            C.POINTER(LmImage), C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.lm_match_multi.argtypes = [vp, C.POINTER(LmImage), ci, C.POINTER(LmQuery), ci, C.POINTER(LmImage), ci,
+                                 C.POINTER(LmImage), C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.lm_match_device_multi.argtypes = [vp, C.POINTER(vp), ci, ci, ci, C.POINTER(LmQuery), ci, vp, C.POINTER(vp),
+                                        C.POINTER(C.c_size_t)]
     L.lm_match_batch.argtypes = [vp, C.POINTER(LmImage), ci, ci, C.c_float, C.POINTER(cp), ci, C.POINTER(vp),
                                  C.POINTER(C.c_size_t)]
     L.lm_free_matches.argtypes = [vp]
@@ -144,6 +152,20 @@ def image(a):
     if a.strides[1] != px or (a.ndim == 3 and a.strides[2] != 1) or a.strides[0] < a.shape[1] * px:
         a = np.ascontiguousarray(a)
     return LmImage(a.ctypes.data, a.shape[0], a.shape[1], t, a.strides[0]), a
+
+
+def query_array(queries):
+    """[(threshold, [class ids])] -> (LmQuery array, keepalive)."""
+    keep = []
+    arr = (LmQuery * max(1, len(queries)))()
+    for i, (thr, ids) in enumerate(queries):
+        enc = [c.encode() for c in ids]
+        ca = (C.c_char_p * max(1, len(enc)))(*enc)
+        keep.append((enc, ca))
+        arr[i].threshold = thr
+        arr[i].class_ids = ca
+        arr[i].n_ids = len(enc)
+    return arr, keep
 
 
 def image_array(images):

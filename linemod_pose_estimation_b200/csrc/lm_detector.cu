@@ -104,9 +104,10 @@ struct Lane {
   DevBuf spread[LM_MAX_LEVELS][LM_MAX_MODALITIES], response[LM_MAX_LEVELS][LM_MAX_MODALITIES];  // parity taps only
   DevBuf lmem[LM_MAX_LEVELS];                          // [M][8][plane_stride] + slack
   // matching
-  DevBuf cand, result, raw_thr, work, work_order, dump;
+  DevBuf cand, result, work, work_order, dump;
   uint32_t cand_cap = 0, out_cap = 0;
-  PinBuf stage_in, stage_out, stage_small;
+  int n_regions = 1;
+  PinBuf stage_in, stage_out;
   // last-call bookkeeping
   float ms[5] = {0, 0, 0, 0, 0};
   int launches = 0;
@@ -127,8 +128,8 @@ struct Lane {
       }
     }
     for (int l = 0; l < LM_MAX_LEVELS; ++l) lmem[l].release();
-    cand.release(); result.release(); raw_thr.release(); work.release(); work_order.release(); dump.release();
-    stage_in.release(); stage_out.release(); stage_small.release();
+    cand.release(); result.release(); work.release(); work_order.release(); dump.release();
+    stage_in.release(); stage_out.release();
     for (int i = 0; i < 6; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -659,44 +660,37 @@ static int build_worklist(lm_detector* d, Lane& ln, const char* const* class_ids
   return LM_OK;
 }
 
-static const int kMaxNf = LM_MAX_FEATURES * LM_MAX_MODALITIES;
-static const size_t kFirstChunkRecords = 2048;  // records fetched together with the header in one D2H copy
+static const size_t kFirstChunkRecords = 2048;  // records fetched together with each header in one D2H copy
+static const int kMaxQueries = 8;               // (class list, threshold) queries answered from one front end
 
-static int ensure_match_buffers(Lane& ln, uint32_t cand_cap, uint32_t out_cap) {
+static size_t region_stride(const Lane& ln) { return sizeof(ResultHeader) + (size_t)ln.out_cap * sizeof(lm_raw_match); }
+
+static int ensure_match_buffers(Lane& ln, uint32_t cand_cap, uint32_t out_cap, int n_q) {
   if (cand_cap > ln.cand_cap) {
     if (ln.cand.ensure((size_t)cand_cap * sizeof(Cand)) != LM_OK) return LM_E_CUDA;
     ln.cand_cap = cand_cap;
   }
-  if (out_cap > ln.out_cap) {
-    if (ln.result.ensure(sizeof(ResultHeader) + (size_t)out_cap * sizeof(lm_raw_match)) != LM_OK) return LM_E_CUDA;
-    ln.out_cap = out_cap;
-  }
-  if (ln.raw_thr.ensure((kMaxNf + 1) * sizeof(int32_t)) != LM_OK) return LM_E_CUDA;
-  if (ln.stage_small.ensure(4096) != LM_OK) return LM_E_CUDA;
-  if (ln.stage_out.ensure(sizeof(ResultHeader) + (size_t)ln.out_cap * sizeof(lm_raw_match)) != LM_OK) return LM_E_CUDA;
+  if (out_cap > ln.out_cap) ln.out_cap = out_cap;
+  if (n_q > ln.n_regions) ln.n_regions = n_q;
+  const size_t total = (size_t)ln.n_regions * region_stride(ln);
+  if (ln.result.ensure(total) != LM_OK) return LM_E_CUDA;
+  if (ln.stage_out.ensure(total) != LM_OK) return LM_E_CUDA;
   return LM_OK;
 }
 
-// Enqueues coarse similarity + refinement on stream s.  The per-call scalars (raw thresholds, header reset) travel in
-// one small pinned block.
-static int enqueue_match(lm_detector* d, Lane& ln, const WorkList& wl, float threshold, cudaStream_t s,
+// Enqueues coarse similarity + refinement of one query on stream s, into result region `qi`.
+static int enqueue_match(lm_detector* d, Lane& ln, const WorkList& wl, float threshold, int qi, cudaStream_t s,
                          cudaEvent_t ev_mid) {
   const HostModel& md = d->model;
   const int L = md.levels(), M = md.M();
   Pack& pk = d->pack;
-  // [OCV] matchClass: raw_threshold = (int)(2*nf + (threshold / 100.f) * (2*nf) + 0.5f), evaluated on the host in f32
-  uint8_t* small = ln.stage_small.as<uint8_t>();
-  ResultHeader* h = reinterpret_cast<ResultHeader*>(small);
-  h->count = 0; h->capacity = ln.out_cap; h->overflow = 0; h->n_cands = 0;
-  int32_t* thr = reinterpret_cast<int32_t*>(small + 64);
-  for (int nf = 0; nf <= kMaxNf; ++nf) thr[nf] = (int32_t)(2 * nf + (threshold / 100.f) * (2 * nf) + 0.5f);
-  CU(cudaMemcpyAsync(ln.result.p, h, sizeof(ResultHeader), cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpyAsync(ln.raw_thr.p, thr, (kMaxNf + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   const LevelGeom& gc = ln.geom[L - 1];
-  ResultHeader* d_hdr = ln.result.as<ResultHeader>();
-  lm_raw_match* d_out = reinterpret_cast<lm_raw_match*>(ln.result.as<uint8_t>() + sizeof(ResultHeader));
+  uint8_t* region = ln.result.as<uint8_t>() + (size_t)qi * region_stride(ln);
+  ResultHeader* d_hdr = reinterpret_cast<ResultHeader*>(region);
+  lm_raw_match* d_out = reinterpret_cast<lm_raw_match*>(region + sizeof(ResultHeader));
+  CU(cudaMemsetAsync(d_hdr, 0, sizeof(ResultHeader), s));
   launch_similarity_coarse(ln.lmem[L - 1].as<uint8_t>(), pk.foff.as<uint32_t>(), pk.ctpl.as<CoarseTpl>(), wl.d_work, wl.n,
-                           pk.max_P, ln.raw_thr.as<int32_t>(), M, ln.cand.as<Cand>(), d_hdr, ln.cand_cap, nullptr, 0,
+                           pk.max_P, threshold, M, ln.cand.as<Cand>(), d_hdr, ln.cand_cap, nullptr, 0,
                            d->coarse_variant, s);
   if (wl.n > 0 && pk.max_P > 0) ++ln.launches;
   if (ev_mid) CU(cudaEventRecord(ev_mid, s));
@@ -711,7 +705,7 @@ static int enqueue_match(lm_detector* d, Lane& ln, const WorkList& wl, float thr
     rp.level[l].plane_stride = g.plane_stride;
     rp.level[l].rows = g.rows; rp.level[l].cols = g.cols; rp.level[l].T = g.T; rp.level[l].W = g.W;
   }
-  launch_refine(rp, pk.ctpl.as<CoarseTpl>(), wl.d_order, ln.cand.as<Cand>(), ln.cand_cap, d_hdr, d_out, s);
+  launch_refine(rp, pk.ctpl.as<CoarseTpl>(), wl.d_order, ln.cand.as<Cand>(), ln.cand_cap, d_hdr, d_out, ln.out_cap, s);
   ++ln.launches;
   CU(cudaGetLastError());
   return LM_OK;
@@ -749,24 +743,33 @@ static void finalize_records(int levels, std::vector<lm_raw_match>& raw, std::ve
   out.erase(std::unique(out.begin(), out.end(), match_equal), out.end());
 }
 
-static int download_records(Lane& ln, cudaStream_t s, std::vector<lm_raw_match>& raw, bool* overflow, uint32_t* n_cands) {
+// One strided D2H copy brings every query's header + first records; long lists need a second copy.
+static int download_records(Lane& ln, cudaStream_t s, int n_q, std::vector<lm_raw_match>* raw, bool* overflow,
+                            uint32_t* n_cands) {
   const size_t first = std::min<size_t>(kFirstChunkRecords, ln.out_cap);
+  const size_t first_bytes = sizeof(ResultHeader) + first * sizeof(lm_raw_match);
+  const size_t stride = region_stride(ln);
   uint8_t* host = ln.stage_out.as<uint8_t>();
-  CU(cudaMemcpyAsync(host, ln.result.p, sizeof(ResultHeader) + first * sizeof(lm_raw_match), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpy2DAsync(host, stride, ln.result.p, stride, first_bytes, n_q, cudaMemcpyDeviceToHost, s));
   CU(cudaEventRecord(ln.ev[5], s));
   CU(cudaStreamSynchronize(s));
-  ResultHeader h = *reinterpret_cast<ResultHeader*>(host);
-  *overflow = h.overflow != 0 || h.count > h.capacity;
-  *n_cands = h.n_cands;
-  if (*overflow) return LM_OK;
-  if (h.count > first) {
-    CU(cudaMemcpyAsync(host + sizeof(ResultHeader) + first * sizeof(lm_raw_match),
-                       ln.result.as<uint8_t>() + sizeof(ResultHeader) + first * sizeof(lm_raw_match),
-                       (h.count - first) * sizeof(lm_raw_match), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+  *overflow = false;
+  for (int q = 0; q < n_q; ++q) {
+    ResultHeader h = *reinterpret_cast<ResultHeader*>(host + q * stride);
+    n_cands[q] = h.n_cands;
+    if (h.overflow != 0 || h.count > ln.out_cap) *overflow = true;
   }
-  const lm_raw_match* recs = reinterpret_cast<const lm_raw_match*>(host + sizeof(ResultHeader));
-  raw.assign(recs, recs + h.count);
+  if (*overflow) return LM_OK;
+  for (int q = 0; q < n_q; ++q) {
+    ResultHeader h = *reinterpret_cast<ResultHeader*>(host + q * stride);
+    if (h.count > first) {
+      CU(cudaMemcpyAsync(host + q * stride + first_bytes, ln.result.as<uint8_t>() + q * stride + first_bytes,
+                         (h.count - first) * sizeof(lm_raw_match), cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+    }
+    const lm_raw_match* recs = reinterpret_cast<const lm_raw_match*>(host + q * stride + sizeof(ResultHeader));
+    raw[q].assign(recs, recs + h.count);
+  }
   return LM_OK;
 }
 
@@ -778,41 +781,53 @@ static void collect_timings(Lane& ln) {
   }
 }
 
-// Matching on an already-built front end, with buffer growth + retry on overflow (exactness over speed there).
-static int match_front(lm_detector* d, Lane& ln, float threshold, const char* const* class_ids, int n_ids,
-                       std::vector<lm_match_rec>& out) {
+struct Query {
+  float threshold;
+  const char* const* class_ids;
+  int n_ids;
+};
+
+// Matching on an already-built front end: every query is a coarse + refinement pass over its class list; buffers grow
+// and the queries are re-run on overflow (exactness over speed there).
+static int match_front(lm_detector* d, Lane& ln, const Query* queries, int n_q, std::vector<lm_match_rec>* out) {
+  if (n_q < 1 || n_q > kMaxQueries) return fail(LM_E_INVALID, "number of queries must be 1..%d", kMaxQueries);
   int rc = ensure_pack(d, ln);
   if (rc != LM_OK) return rc;
-  WorkList wl;
-  rc = build_worklist(d, ln, class_ids, n_ids, wl);
-  if (rc != LM_OK) return rc;
+  WorkList wl[kMaxQueries];
+  for (int q = 0; q < n_q; ++q) {
+    rc = build_worklist(d, ln, queries[q].class_ids, queries[q].n_ids, wl[q]);
+    if (rc != LM_OK) return rc;
+  }
   uint32_t cand_cap = std::max<uint32_t>(ln.cand_cap, 1u << 16), out_cap = std::max<uint32_t>(ln.out_cap, 1u << 14);
-  std::vector<lm_raw_match> raw;
+  std::vector<lm_raw_match> raw[kMaxQueries];
+  uint32_t n_cands[kMaxQueries];
   for (int attempt = 0;; ++attempt) {
-    if (ensure_match_buffers(ln, cand_cap, out_cap) != LM_OK) return LM_E_CUDA;
+    if (ensure_match_buffers(ln, cand_cap, out_cap, n_q) != LM_OK) return LM_E_CUDA;
     if (attempt > 0) CU(cudaEventRecord(ln.ev[2], ln.stream));
-    if (enqueue_match(d, ln, wl, threshold, ln.stream, ln.ev[3]) != LM_OK) return LM_E_CUDA;
+    for (int q = 0; q < n_q; ++q)
+      if (enqueue_match(d, ln, wl[q], queries[q].threshold, q, ln.stream, q == 0 ? ln.ev[3] : nullptr) != LM_OK) return LM_E_CUDA;
     CU(cudaEventRecord(ln.ev[4], ln.stream));
     bool overflow = false;
-    uint32_t n_cands = 0;
-    if (download_records(ln, ln.stream, raw, &overflow, &n_cands) != LM_OK) return LM_E_CUDA;
-    if (!overflow) {
-      ln.work_stats[1] = wl.coarse_bytes;
-      ln.work_stats[4] = n_cands;
-      ln.work_stats[5] = (uint64_t)wl.n * (uint64_t)(ln.geom.back().W * ln.geom.back().H);
-      break;
-    }
+    if (download_records(ln, ln.stream, n_q, raw, &overflow, n_cands) != LM_OK) return LM_E_CUDA;
+    if (!overflow) break;
     if (attempt >= 8) return fail(LM_E_CUDA, "match buffers overflowed repeatedly");
-    if (n_cands > ln.cand_cap) cand_cap = std::max<uint32_t>(n_cands + n_cands / 4, cand_cap * 2);
-    out_cap = std::max<uint32_t>(out_cap * 4, std::min<uint32_t>(n_cands + 1024, 1u << 26));
+    uint32_t worst = 0;
+    for (int q = 0; q < n_q; ++q) worst = std::max(worst, n_cands[q]);
+    if (worst > ln.cand_cap) cand_cap = std::max<uint32_t>(worst + worst / 4, cand_cap * 2);
+    out_cap = std::max<uint32_t>(out_cap * 4, std::min<uint32_t>(worst + 1024, 1u << 26));
   }
-  // B_refine: every candidate reads 256 bytes per feature of every refinement level -- survivors only
-  // would under-count, so use candidates x the mean per-template refine feature count of the work list.
+  // work accounting: B_coarse from the pack; B_refine = candidates x refine features x 256 bytes
   uint64_t rsum = 0;
   for (uint32_t v : d->pack.refine_nf) rsum += v;
-  ln.work_stats[2] = d->pack.n ? (uint64_t)((double)ln.work_stats[4] * ((double)rsum / d->pack.n) * 256.0) : 0;
-  ln.work_stats[3] = 20ull * raw.size();
-  finalize_records(d->model.levels(), raw, ln.presort, out);
+  const double mean_rnf = d->pack.n ? (double)rsum / d->pack.n : 0.0;
+  for (int q = 0; q < n_q; ++q) {
+    ln.work_stats[1] += wl[q].coarse_bytes;
+    ln.work_stats[4] += n_cands[q];
+    ln.work_stats[5] += (uint64_t)wl[q].n * (uint64_t)(ln.geom.back().W * ln.geom.back().H);
+    ln.work_stats[2] += (uint64_t)((double)n_cands[q] * mean_rnf * 256.0);
+    ln.work_stats[3] += 20ull * raw[q].size();
+    finalize_records(d->model.levels(), raw[q], ln.presort, out[q]);
+  }
   return LM_OK;
 }
 
@@ -1195,16 +1210,28 @@ int lm_build_front(lm_detector* d, const lm_image* sources, int n_sources, const
   return LM_OK;
 }
 
-int lm_match(lm_detector* d, const lm_image* sources, int n_sources, float threshold, const char* const* class_ids,
-             int n_ids, const lm_image* masks, int n_masks, lm_image_out* quantized_out, lm_match_rec** out_matches,
-             size_t* out_n) {
-  if (!d || !sources || !out_matches || !out_n) return fail(LM_E_INVALID, "NULL argument");
-  *out_matches = nullptr; *out_n = 0;
-  Lane& ln = d->lane[0];
-  int rc = front_from_host(d, ln, sources, n_sources, masks, n_masks);
+static int to_queries(const lm_query* in, int n, Query* out) {
+  if (!in || n < 1 || n > kMaxQueries) return fail(LM_E_INVALID, "number of queries must be 1..%d", kMaxQueries);
+  for (int q = 0; q < n; ++q) {
+    if (in[q].n_ids < 0 || (in[q].n_ids > 0 && !in[q].class_ids)) return fail(LM_E_INVALID, "query %d: bad class id list", q);
+    out[q].threshold = in[q].threshold; out[q].class_ids = in[q].class_ids; out[q].n_ids = in[q].n_ids;
+  }
+  return LM_OK;
+}
+
+int lm_match_multi(lm_detector* d, const lm_image* sources, int n_sources, const lm_query* queries, int n_queries,
+                   const lm_image* masks, int n_masks, lm_image_out* quantized_out, lm_match_rec** out_matches,
+                   size_t* out_offsets) {
+  if (!d || !sources || !out_matches || !out_offsets) return fail(LM_E_INVALID, "NULL argument");
+  *out_matches = nullptr;
+  Query qs[kMaxQueries];
+  int rc = to_queries(queries, n_queries, qs);
   if (rc != LM_OK) return rc;
-  std::vector<lm_match_rec> out;
-  rc = match_front(d, ln, threshold, class_ids, n_ids, out);
+  Lane& ln = d->lane[0];
+  rc = front_from_host(d, ln, sources, n_sources, masks, n_masks);
+  if (rc != LM_OK) return rc;
+  std::vector<lm_match_rec> out[kMaxQueries];
+  rc = match_front(d, ln, qs, n_queries, out);
   if (rc != LM_OK) return rc;
   collect_timings(ln);
   if (quantized_out) {
@@ -1218,7 +1245,26 @@ int lm_match(lm_detector* d, const lm_image* sources, int n_sources, float thres
         CU(cudaMemcpy2D(q.data, q.step, ln.quantized[l][m].p, g.cols, g.cols, g.rows, cudaMemcpyDeviceToHost));
       }
   }
-  return copy_out(out, out_matches, out_n);
+  std::vector<lm_match_rec> all;
+  out_offsets[0] = 0;
+  for (int q = 0; q < n_queries; ++q) {
+    all.insert(all.end(), out[q].begin(), out[q].end());
+    out_offsets[q + 1] = all.size();
+  }
+  size_t n = 0;
+  return copy_out(all, out_matches, &n);
+}
+
+int lm_match(lm_detector* d, const lm_image* sources, int n_sources, float threshold, const char* const* class_ids,
+             int n_ids, const lm_image* masks, int n_masks, lm_image_out* quantized_out, lm_match_rec** out_matches,
+             size_t* out_n) {
+  if (!out_n) return fail(LM_E_INVALID, "NULL argument");
+  *out_n = 0;
+  lm_query q = {threshold, class_ids, n_ids};
+  size_t offs[2] = {0, 0};
+  int rc = lm_match_multi(d, sources, n_sources, &q, 1, masks, n_masks, quantized_out, out_matches, offs);
+  if (rc == LM_OK) *out_n = offs[1];
+  return rc;
 }
 
 int lm_match_batch(lm_detector* d, const lm_image* sources, int n_frames, int n_sources, float threshold,
@@ -1227,6 +1273,7 @@ int lm_match_batch(lm_detector* d, const lm_image* sources, int n_frames, int n_
   *out_matches = nullptr;
   std::vector<lm_match_rec> all;
   out_offsets[0] = 0;
+  const Query query = {threshold, class_ids, n_ids};
   // Two lanes: while lane A's kernels run, lane B's frame is packed into pinned memory and copied.
   struct Pending { bool busy = false; WorkList wl; } pend[2];
   auto finish = [&](int li, int frame) -> int {
@@ -1234,10 +1281,10 @@ int lm_match_batch(lm_detector* d, const lm_image* sources, int n_frames, int n_
     std::vector<lm_raw_match> raw;
     bool overflow = false;
     uint32_t n_cands = 0;
-    if (download_records(ln, ln.stream, raw, &overflow, &n_cands) != LM_OK) return LM_E_CUDA;
+    if (download_records(ln, ln.stream, 1, &raw, &overflow, &n_cands) != LM_OK) return LM_E_CUDA;
     std::vector<lm_match_rec> out;
     if (overflow) {  // rare: redo this frame alone with growing buffers
-      int rc = match_front(d, ln, threshold, class_ids, n_ids, out);
+      int rc = match_front(d, ln, &query, 1, &out);
       if (rc != LM_OK) return rc;
     } else finalize_records(d->model.levels(), raw, ln.presort, out);
     all.insert(all.end(), out.begin(), out.end());
@@ -1254,8 +1301,8 @@ int lm_match_batch(lm_detector* d, const lm_image* sources, int n_frames, int n_
     if (rc != LM_OK) return rc;
     rc = build_worklist(d, ln, class_ids, n_ids, pend[li].wl);
     if (rc != LM_OK) return rc;
-    if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
-    if (enqueue_match(d, ln, pend[li].wl, threshold, ln.stream, ln.ev[3]) != LM_OK) return LM_E_CUDA;
+    if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14), 1) != LM_OK) return LM_E_CUDA;
+    if (enqueue_match(d, ln, pend[li].wl, threshold, 0, ln.stream, ln.ev[3]) != LM_OK) return LM_E_CUDA;
     CU(cudaEventRecord(ln.ev[4], ln.stream));
     pend[li].busy = true;
   }
@@ -1267,30 +1314,44 @@ int lm_match_batch(lm_detector* d, const lm_image* sources, int n_frames, int n_
 
 void lm_free_matches(lm_match_rec* m) { std::free(m); }
 
-int lm_match_device(lm_detector* d, const void* const* d_sources, int n_sources, int rows, int cols, float threshold,
-                    const char* const* class_ids, int n_ids, void* stream, const void** d_records,
-                    size_t* record_bytes_capacity) {
+int lm_match_device_multi(lm_detector* d, const void* const* d_sources, int n_sources, int rows, int cols,
+                          const lm_query* queries, int n_queries, void* stream, const void** d_records,
+                          size_t* region_stride_bytes) {
   if (!d || !d_sources || !d_records) return fail(LM_E_INVALID, "NULL argument");
   if (n_sources != d->model.M()) return fail(LM_E_INVALID, "sources.size() (%d) != modalities.size() (%d)", n_sources, d->model.M());
+  Query qs[kMaxQueries];
+  int rc = to_queries(queries, n_queries, qs);
+  if (rc != LM_OK) return rc;
   if (set_device(d) != LM_OK || upload_luts(d) != LM_OK) return LM_E_CUDA;
   Lane& ln = d->lane[0];
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = ensure_lm_ws(d, ln, rows, cols);
+  const bool fresh_ws = !(ln.lm_ready && ln.rows == rows && ln.cols == cols);
+  rc = ensure_lm_ws(d, ln, rows, cols);
   if (rc != LM_OK) return rc;
-  CU(cudaStreamSynchronize(ln.stream));  // workspace memsets were enqueued on the lane's own stream
+  if (fresh_ws) CU(cudaStreamSynchronize(ln.stream));  // workspace memsets were enqueued on the lane's own stream
   for (int m = 0; m < n_sources; ++m) { ln.src_ptr[m] = d_sources[m]; ln.has_mask[m] = false; }
   ln.launches = 0;
   if (run_front(d, ln, s) != LM_OK) return LM_E_CUDA;
   rc = ensure_pack(d, ln);
   if (rc != LM_OK) return rc;
-  WorkList wl;
-  rc = build_worklist(d, ln, class_ids, n_ids, wl);
-  if (rc != LM_OK) return rc;
-  if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 18), std::max<uint32_t>(ln.out_cap, 1u << 16)) != LM_OK) return LM_E_CUDA;
-  if (enqueue_match(d, ln, wl, threshold, s, nullptr) != LM_OK) return LM_E_CUDA;
+  WorkList wl[kMaxQueries];
+  for (int q = 0; q < n_queries; ++q) {
+    rc = build_worklist(d, ln, qs[q].class_ids, qs[q].n_ids, wl[q]);
+    if (rc != LM_OK) return rc;
+  }
+  if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 18), std::max<uint32_t>(ln.out_cap, 1u << 14), n_queries) != LM_OK) return LM_E_CUDA;
+  for (int q = 0; q < n_queries; ++q)
+    if (enqueue_match(d, ln, wl[q], qs[q].threshold, q, s, nullptr) != LM_OK) return LM_E_CUDA;
   *d_records = ln.result.p;
-  if (record_bytes_capacity) *record_bytes_capacity = sizeof(ResultHeader) + (size_t)ln.out_cap * sizeof(lm_raw_match);
+  if (region_stride_bytes) *region_stride_bytes = region_stride(ln);
   return LM_OK;
+}
+
+int lm_match_device(lm_detector* d, const void* const* d_sources, int n_sources, int rows, int cols, float threshold,
+                    const char* const* class_ids, int n_ids, void* stream, const void** d_records,
+                    size_t* record_bytes_capacity) {
+  lm_query q = {threshold, class_ids, n_ids};
+  return lm_match_device_multi(d, d_sources, n_sources, rows, cols, &q, 1, stream, d_records, record_bytes_capacity);
 }
 
 int lm_finalize_raw(const lm_detector* d, const lm_raw_match* raw, size_t n_raw, lm_match_rec** out_matches, size_t* out_n) {
@@ -1357,17 +1418,15 @@ int lm_debug_coarse_map(lm_detector* d, const char* class_id, int template_id, u
   if (local < 0) return fail(LM_E_NOTFOUND, "class '%s' template %d is not on this shard", class_id, template_id);
   const LevelGeom& gc = ln.geom.back();
   const int WH = gc.W * gc.H;
-  if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
+  if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14), 1) != LM_OK) return LM_E_CUDA;
   if (ln.dump.ensure((size_t)WH * 2) != LM_OK || ln.work.ensure(64) != LM_OK) return LM_E_CUDA;
-  std::vector<int32_t> thr(kMaxNf + 1, 0x7fffffff);
   uint32_t w = (uint32_t)local;
-  ResultHeader h = {0, ln.out_cap, 0, 0};
   CU(cudaMemsetAsync(ln.dump.p, 0, (size_t)WH * 2, ln.stream));
   CU(cudaMemcpyAsync(ln.work.p, &w, 4, cudaMemcpyHostToDevice, ln.stream));
-  CU(cudaMemcpyAsync(ln.raw_thr.p, thr.data(), thr.size() * 4, cudaMemcpyHostToDevice, ln.stream));
-  CU(cudaMemcpyAsync(ln.result.p, &h, sizeof(h), cudaMemcpyHostToDevice, ln.stream));
+  CU(cudaMemsetAsync(ln.result.p, 0, sizeof(ResultHeader), ln.stream));
+  // threshold 1e30 -> raw threshold saturates: nothing becomes a candidate, the kernel only dumps its accumulators
   launch_similarity_coarse(ln.lmem[d->model.levels() - 1].as<uint8_t>(), pk.foff.as<uint32_t>(), pk.ctpl.as<CoarseTpl>(),
-                           ln.work.as<uint32_t>(), 1, pk.h_ctpl[local].P, ln.raw_thr.as<int32_t>(), d->model.M(),
+                           ln.work.as<uint32_t>(), 1, pk.h_ctpl[local].P, 1e30f, d->model.M(),
                            ln.cand.as<Cand>(), ln.result.as<ResultHeader>(), 0, ln.dump.as<uint16_t>(), WH,
                            d->coarse_variant, ln.stream);
   CU(cudaMemcpyAsync(dst, ln.dump.p, (size_t)WH * 2, cudaMemcpyDeviceToHost, ln.stream));

@@ -50,7 +50,7 @@ struct Cand {                             // coarse candidate: raw score above t
   uint32_t tglob, pos, raw, pad;
 };
 
-struct ResultHeader {
+struct ResultHeader {  // zeroed before every query; `capacity` is filled in by the host when a block leaves the GPU
   uint32_t count, capacity, overflow, n_cands;
 };
 
@@ -112,11 +112,11 @@ bool launch_spread_all(const SpreadParams& p, int total_blocks, int max_T, cudaS
 // ------------------------------------------------------------------------------------------------ matching
 // dump (nullable): u16 totals, [work index][W*H], written for every scored position (parity tap).
 void launch_similarity_coarse(const uint8_t* lmc, const uint32_t* foff, const CoarseTpl* tpl, const uint32_t* work,
-                              int n_work, int max_P, const int32_t* raw_thr_by_nf, int M, Cand* cand,
+                              int n_work, int max_P, float threshold, int M, Cand* cand,
                               ResultHeader* hdr, uint32_t cand_cap, uint16_t* dump, int dump_stride, int variant,
                               cudaStream_t s);
 // work_order[i]: canonical order key of work item i (Cand::pad carries i).
 void launch_refine(const RefineParams& p, const CoarseTpl* ctpl, const uint32_t* work_order, const Cand* cand,
-                   uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* out, cudaStream_t s);
+                   uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* out, uint32_t out_cap, cudaStream_t s);
 
 }  // namespace lmk

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) k_similarity_coarse(const uint8_t* __rest
                                                            const uint32_t* __restrict__ foff,
                                                            const CoarseTpl* __restrict__ tpl,
                                                            const uint32_t* __restrict__ work, int n_work,
-                                                           int passes_per_tpl, const int32_t* __restrict__ raw_thr_by_nf,
+                                                           int passes_per_tpl, float threshold,
                                                            int M, Cand* __restrict__ cand, ResultHeader* hdr,
                                                            uint32_t cand_cap, uint16_t* __restrict__ dump,
                                                            int dump_stride) {
@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(256) k_similarity_coarse(const uint8_t* __rest
         tot_hi[k] += (acc[k] >> 8) & 0x00ff00ffu;
       }
     }
-    const int thr = raw_thr_by_nf[t_nf];
+    // [OCV] matchClass: raw_threshold = (int)(2*nf + (threshold / 100.f) * (2*nf) + 0.5f), same f32 roundings
+    const float two_nf = (float)(2 * (int)t_nf);
+    const int thr = __float2int_rz(__fadd_rn(__fadd_rn(two_nf, __fmul_rn(__fdiv_rn(threshold, 100.f), two_nf)), 0.5f));
     bool hit = thr < 0;
     if (!hit) {
       const uint32_t thr2 = (uint32_t)min(thr, 0xffff) * 0x00010001u;
@@ -153,7 +155,8 @@ constexpr int kRefineWarps = 8;
 __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams P, const CoarseTpl* __restrict__ ctpl,
                                                              const uint32_t* __restrict__ work_order,
                                                              const Cand* __restrict__ cand, uint32_t cand_cap,
-                                                             ResultHeader* hdr, lm_raw_match* __restrict__ out) {
+                                                             ResultHeader* hdr, lm_raw_match* __restrict__ out,
+                                                             uint32_t out_cap) {
   __shared__ uint32_t s_part[kRefineWarps][32][4];
   __shared__ int s_state[4];  // x, y, alive, best_score
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams
     }
     if (alive && threadIdx.x == 0) {
       uint32_t idx = atomicAdd(&hdr->count, 1u);
-      if (idx < hdr->capacity) {
+      if (idx < out_cap) {
         lm_raw_match r;
         r.order_key = work_order[c.pad]; r.coarse_pos = c.pos; r.x = x; r.y = y; r.score = score; r.nf = nf;
         r.template_id = ctpl[c.tglob].template_id; r.class_index = ctpl[c.tglob].class_index;
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams
 }  // namespace
 
 void launch_similarity_coarse(const uint8_t* lmc, const uint32_t* foff, const CoarseTpl* tpl, const uint32_t* work,
-                              int n_work, int max_P, const int32_t* raw_thr_by_nf, int M, Cand* cand,
+                              int n_work, int max_P, float threshold, int M, Cand* cand,
                               ResultHeader* hdr, uint32_t cand_cap, uint16_t* dump, int dump_stride, int variant,
                               cudaStream_t s) {
   (void)variant;
@@ -268,13 +271,13 @@ void launch_similarity_coarse(const uint8_t* lmc, const uint32_t* foff, const Co
   int blocks = (int)((tiles + 7) / 8);
   const int persistent = 148 * 8;  // up to 8 resident CTAs (64 warps) per SM
   if (blocks > persistent) blocks = persistent;
-  k_similarity_coarse<<<blocks, 256, 0, s>>>(lmc, foff, tpl, work, n_work, passes, raw_thr_by_nf, M, cand, hdr,
+  k_similarity_coarse<<<blocks, 256, 0, s>>>(lmc, foff, tpl, work, n_work, passes, threshold, M, cand, hdr,
                                              cand_cap, dump, dump_stride);
 }
 
 void launch_refine(const RefineParams& p, const CoarseTpl* ctpl, const uint32_t* work_order, const Cand* cand,
-                   uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* out, cudaStream_t s) {
-  k_refine<<<148 * 4, kRefineWarps * 32, 0, s>>>(p, ctpl, work_order, cand, cand_cap, hdr, out);
+                   uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* out, uint32_t out_cap, cudaStream_t s) {
+  k_refine<<<148 * 4, kRefineWarps * 32, 0, s>>>(p, ctpl, work_order, cand, cand_cap, hdr, out, out_cap);
 }
 
 }  // namespace lmk

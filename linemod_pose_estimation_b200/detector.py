@@ -191,6 +191,29 @@ class Detector:
         res = self._take(out, n.value)
         return (res, qimgs) if quantized_images else res
 
+    def match_multi(self, sources, queries, masks=()):
+        """Several (threshold, class_ids) queries from one front end of the frame (lm_match_multi).
+        queries: [(threshold, [class ids])].  -> list of match arrays, one per query."""
+        arr, keep = image_array(sources)
+        marr, mkeep = image_array(masks)
+        qarr, qkeep = _capi.query_array(queries)
+        out = C.c_void_p()
+        offs = (C.c_size_t * (len(queries) + 1))()
+        check(lib().lm_match_multi(self._h, arr, len(sources), qarr, len(queries), marr, len(masks), None,
+                                   C.byref(out), offs))
+        allm = self._take(out, offs[len(queries)])
+        return [allm[offs[i]:offs[i + 1]] for i in range(len(queries))]
+
+    def match_device_multi(self, d_ptrs, rows, cols, queries, stream=0):
+        """Device-resident sources, several queries, asynchronous on `stream`.
+        -> (device pointer of region 0, byte stride between the per-query regions)."""
+        qarr, qkeep = _capi.query_array(queries)
+        ptrs = (C.c_void_p * len(d_ptrs))(*d_ptrs)
+        rec, stride = C.c_void_p(), C.c_size_t()
+        check(lib().lm_match_device_multi(self._h, ptrs, len(d_ptrs), rows, cols, qarr, len(queries),
+                                          C.c_void_p(stream), C.byref(rec), C.byref(stride)))
+        return rec.value, stride.value
+
     def match_batch(self, frames, threshold, class_ids=()):
         """frames: list of per-frame source lists.  -> list of match arrays (pipelined over two streams)."""
         flat = [s for f in frames for s in f]

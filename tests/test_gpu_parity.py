@@ -346,3 +346,17 @@ def test_shard_union_equals_whole():
     assert all(len(r) > 0 for r in raws)
     common.assert_matches_equal(det.finalize_raw(np.concatenate(raws)), want)
     common.assert_matches_equal(det.match([bgr, depth], 70.0), want)
+
+
+def test_match_multi_equals_separate_matches():
+    """lm_match_multi: several (class list, threshold) queries from one front end == separate match calls."""
+    orc, det, views = _pair(n_views=8, n_random=60, seed=73, classes=("cpu_binary", "memoryChip2"))
+    queries = [(92.0, ["memoryChip2"]), (74.0, ["cpu_binary"]), (60.0, []), (80.0, ["memoryChip2", "cpu_binary"])]
+    for seed in (2000, 2001):
+        bgr, depth, _ = synth.compose_scene(seed, views[:5])
+        got = det.match_multi([bgr, depth], queries)
+        assert len(got) == len(queries)
+        for g, (thr, ids) in zip(got, queries):
+            common.assert_matches_equal(g, orc.match([bgr, depth], thr, class_ids=ids), "query %s" % ((thr, ids),))
+            common.assert_matches_equal(g, det.match([bgr, depth], thr, class_ids=ids), "separate call %s" % ((thr, ids),))
+    assert sum(len(g) for g in got) > 0

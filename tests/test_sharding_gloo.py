@@ -43,21 +43,28 @@ def _worker(rank, world, port, capacity, out_dir):
             bgr, depth = np.zeros((240, 320, 3), np.uint8), np.zeros((240, 320), np.uint16)
         frame = [torch.from_numpy(bgr), torch.from_numpy(depth.view(np.int16))]
 
-        def local_match(tensors, threshold):
+        def local_match(tensors, queries):
             b = tensors[0].numpy()
             d = tensors[1].numpy().view(np.uint16)
-            orc.match([b, d], threshold, keep_candidates=True)
-            raw = orc.last_raw()
-            mine = raw[raw["order_key"] % world == rank]     # this rank's template shard
-            return torch.from_numpy(pack_block(mine, 1 << 14))
+            blocks = []
+            for thr, ids in queries:
+                orc.match([b, d], thr, class_ids=ids, keep_candidates=True)
+                raw = orc.last_raw()
+                # this rank's template shard: canonical index % world == rank ("b" alone starts at its own offset 0,
+                # so recover the canonical index from class + template id)
+                canon = raw["template_id"] + np.where(raw["class_index"] == 1, orc.num_templates("a"), 0)
+                blocks.append(torch.from_numpy(pack_block(raw[canon % world == rank], 1 << 14)))
+            return blocks
 
         sm = ShardedMatcher(local_match, det.finalize_raw, rank, world, capacity=capacity)
-        got = sm.match(frame, 70.0)
+        queries = [(70.0, []), (60.0, ["b"])]
+        got = sm.match(frame, queries)
         if rank == 0:
-            want = orc.match([bgr, depth], 70.0)
-            assert len(want) > 4
-            common.assert_matches_equal(got, want)
-            np.save(os.path.join(out_dir, "ok_%d.npy" % capacity), np.array([len(got), sm.capacity]))
+            for g, (thr, ids) in zip(got, queries):
+                want = orc.match([bgr, depth], thr, class_ids=ids)
+                assert len(want) > 1
+                common.assert_matches_equal(g, want)
+            np.save(os.path.join(out_dir, "ok_%d.npy" % capacity), np.array([len(got[0]), sm.capacity]))
         else:
             assert got is None
             assert np.array_equal(frame[0].numpy(), synth.compose_scene(1001, views[:4], rows=240, cols=320)[0])  # broadcast arrived
