@@ -262,7 +262,7 @@ def run_ours(args):
     dev_frames = [(torch.from_numpy(b).to(dev), torch.from_numpy(d.view(np.int16)).to(dev)) for (b, d) in frames]
     dev_ptrs = [(C.c_void_p * 2)(fb.data_ptr(), fd.data_ptr()) for (fb, fd) in dev_frames]
     stream = torch.cuda.current_stream()
-    rec, stride = C.c_void_p(), C.c_size_t()
+    rec, cap = C.c_void_p(), C.c_size_t()
 
     def barrier():
         torch.cuda.synchronize()
@@ -270,16 +270,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def enqueue_device(ptrs):
-        _capi.check(lib.lm_match_device_multi(det._h, ptrs, 2, ROWS, COLS, qarr, n_q, C.c_void_p(stream.cuda_stream),
-                                              C.byref(rec), C.byref(stride)))
-        return [device_view(rec.value + q * stride.value, stride.value, dev) for q in range(n_q)]
-
     # ---- value: frame resident in HBM on every rank, device-timed; survivors end in rank 0's HBM (all-gather)
     def device_step(i):
-        blocks = enqueue_device(dev_ptrs[i % FRAME_POOL])
+        _capi.check(lib.lm_match_device_multi(det._h, dev_ptrs[i % FRAME_POOL], 2, ROWS, COLS, qarr, n_q,
+                                              C.c_void_p(stream.cuda_stream), C.byref(rec), C.byref(cap)))
         if world > 1:
-            sharded.gather_async(blocks)
+            sharded.gather_async(device_view(rec.value, cap.value, dev))
 
     for i in range(args.warmup):
         device_step(i)
@@ -374,7 +370,7 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "evals/s", "fps": args.steps / dt, "ms_per_step": 1e3 * dt / args.steps,
                     "h2d_bytes_per_step": ROWS * COLS * 3 + ROWS * COLS * 2,
-                    "d2h_bytes_per_step": n_q * (16 + (2048 if world == 1 else sharded.capacity * world) * 32),
+                    "d2h_bytes_per_step": 16 + (1024 if world == 1 else sharded.capacity * world) * 32,
                     "matches_per_step": n_matches / max(1, args.steps)},
             "gpu_launches": launches_device + launches, "clocks": clock_info,
             "stage_ms_per_frame": {k: float(np.mean(v)) for k, v in stage_ms.items() if v},

@@ -175,7 +175,8 @@ void lm_free_matches(lm_match_rec* matches);
  * lm_finalize_raw() (host) turns downloaded raw records (possibly concatenated from several template shards) into
  * the reference's sorted / de-duplicated match list. */
 typedef struct {
-  uint32_t order_key; /* position of the template in the canonical (class, template_id) iteration order */
+  uint32_t order_key; /* bits 0-27: position of the template in the query's (class, template_id) iteration order;
+                         bits 28-31: index of the query within the request (0 for single-query calls) */
   uint32_t coarse_pos; /* raster index r*W+c of the coarse candidate at the lowest pyramid level */
   int32_t x, y;        /* position after local refinement */
   uint32_t score;      /* raw integer similarity of the last evaluated level */
@@ -186,10 +187,10 @@ typedef struct {
 int lm_match_device(lm_detector* det, const void* const* d_sources, int n_sources, int rows, int cols, float threshold,
                     const char* const* class_ids, int n_ids, void* stream, const void** d_records,
                     size_t* record_bytes_capacity);
-/* Multi-query form: region q (q < n_queries) starts at *d_records + q * *region_stride_bytes. */
+/* Multi-query form: one record block for the whole request; a record's query index is order_key >> 28. */
 int lm_match_device_multi(lm_detector* det, const void* const* d_sources, int n_sources, int rows, int cols,
                           const lm_query* queries, int n_queries, void* stream, const void** d_records,
-                          size_t* region_stride_bytes);
+                          size_t* record_bytes_capacity);
 int lm_finalize_raw(const lm_detector* det, const lm_raw_match* raw, size_t n_raw, lm_match_rec** out_matches,
                     size_t* out_n);
 /* Template sharding (north-star multi-GPU layout): keep only templates whose canonical order index i satisfies

@@ -106,7 +106,6 @@ struct Lane {
   // matching
   DevBuf cand, result, work, work_order, dump;
   uint32_t cand_cap = 0, out_cap = 0;
-  int n_regions = 1;
   PinBuf stage_in, stage_out;
   // last-call bookkeeping
   float ms[5] = {0, 0, 0, 0, 0};
@@ -141,7 +140,7 @@ struct Pack {
   int rows = 0, cols = 0, shard_rank = 0, shard_world = 1;
   int n = 0;        // templates on this shard
   int max_P = 0;
-  DevBuf ctpl, foff, work_all, order_all;
+  DevBuf ctpl, foff;
   DevBuf rtpl[LM_MAX_LEVELS], rfeats[LM_MAX_LEVELS];
   std::vector<CoarseTpl> h_ctpl;
   std::vector<uint64_t> coarse_bytes;   // per template: in-bounds features x positions (B_coarse)
@@ -150,15 +149,16 @@ struct Pack {
   std::vector<uint32_t> refine_nf;      // per template: sum over refine levels of features (x256 = bytes / candidate)
   struct ClassRange { std::string id; int class_index; std::vector<uint32_t> local; std::vector<uint32_t> global_pos; };
   std::vector<ClassRange> classes;      // canonical order
-  struct Filtered { DevBuf work, order; int n = 0; uint64_t coarse_bytes = 0; };
-  std::map<std::string, Filtered> filtered;  // work lists of class_ids-filtered matches, by request
+  // Device-side description of one (multi-query) request: work items and coarse tiles.  Cached by the class lists.
+  struct Plan { DevBuf items, tiles; int n_items = 0, n_tiles = 0; uint64_t coarse_bytes = 0, evals = 0; double refine_nf_sum = 0; };
+  std::map<std::string, Plan> plans;
   void clear_filtered() {
-    for (auto& kv : filtered) { kv.second.work.release(); kv.second.order.release(); }
-    filtered.clear();
+    for (auto& kv : plans) { kv.second.items.release(); kv.second.tiles.release(); }
+    plans.clear();
   }
   void release() {
     clear_filtered();
-    ctpl.release(); foff.release(); work_all.release(); order_all.release();
+    ctpl.release(); foff.release();
     for (int l = 0; l < LM_MAX_LEVELS; ++l) { rtpl[l].release(); rfeats[l].release(); }
   }
 };
@@ -576,8 +576,6 @@ static int ensure_pack(lm_detector* d, const Lane& ln) {
     pk.classes.push_back(cr);
   }
   pk.n = (int)ctpl.size();
-  std::vector<uint32_t> work_all(pk.n), order_all(pk.n);
-  for (int i = 0; i < pk.n; ++i) { work_all[i] = (uint32_t)i; order_all[i] = ctpl[i].order_key; }
   auto up = [&](DevBuf& b, const void* src, size_t bytes) -> int {
     if (b.ensure(bytes + 64) != LM_OK) return LM_E_CUDA;
     if (bytes) CU(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
@@ -586,8 +584,6 @@ static int ensure_pack(lm_detector* d, const Lane& ln) {
   foff.resize(foff.size() + 8, 0);  // the 4-way unrolled loop never reads past the template, padding is for safety
   if (up(pk.ctpl, ctpl.data(), ctpl.size() * sizeof(CoarseTpl)) != LM_OK) return LM_E_CUDA;
   if (up(pk.foff, foff.data(), foff.size() * 4) != LM_OK) return LM_E_CUDA;
-  if (up(pk.work_all, work_all.data(), work_all.size() * 4) != LM_OK) return LM_E_CUDA;
-  if (up(pk.order_all, order_all.data(), order_all.size() * 4) != LM_OK) return LM_E_CUDA;
   for (int l = 0; l < L - 1; ++l) {
     if (up(pk.rtpl[l], rtpl[l].data(), rtpl[l].size() * sizeof(RefineTpl)) != LM_OK) return LM_E_CUDA;
     if (up(pk.rfeats[l], rfeats[l].data(), rfeats[l].size() * 4) != LM_OK) return LM_E_CUDA;
@@ -599,104 +595,123 @@ static int ensure_pack(lm_detector* d, const Lane& ln) {
 }
 
 // ------------------------------------------------------------------------------------------------ matching
-struct WorkList {
-  const uint32_t* d_work = nullptr;
-  const uint32_t* d_order = nullptr;
-  int n = 0;
-  uint64_t coarse_bytes = 0;
+struct Query {
+  float threshold;
+  const char* const* class_ids;
+  int n_ids;
 };
 
+static const size_t kFirstChunkRecords = 1024;  // records fetched together with the header in one D2H copy
+static const int kMaxQueries = LM_MAX_QUERIES;  // (class list, threshold) queries answered from one front end
+
 // [OCV] Detector::match: "if (class_ids.empty()) match all templates else only the requested class IDs" (in the
-// order requested, unknown ids skipped).
-static int build_worklist(lm_detector* d, Lane& ln, const char* const* class_ids, int n_ids, WorkList& wl) {
+// order requested, unknown ids skipped) -- for every query of the request.  The plan lists the work items (template
+// + emission order key tagged with the query index) and the non-empty 512-position tiles of the coarse kernel,
+// heaviest first; it depends on the class lists only, so it is built once per distinct request and cached.
+static int get_plan(lm_detector* d, const Query* qs, int n_q, Pack::Plan** out) {
   Pack& pk = d->pack;
-  if (n_ids == 0) {
-    wl.d_work = pk.work_all.as<uint32_t>(); wl.d_order = pk.order_all.as<uint32_t>();
-    wl.n = pk.n; wl.coarse_bytes = pk.coarse_bytes_all;
-    return LM_OK;
-  }
-  // filtered work lists are cached per request (the service asks for the same class again and again)
   std::string key;
-  for (int i = 0; i < n_ids; ++i) {
-    if (!class_ids[i]) return fail(LM_E_INVALID, "class_ids[%d] is NULL", i);
-    key += class_ids[i];
-    key += '\n';
+  for (int q = 0; q < n_q; ++q) {
+    for (int i = 0; i < qs[q].n_ids; ++i) {
+      if (!qs[q].class_ids[i]) return fail(LM_E_INVALID, "class_ids[%d] is NULL", i);
+      key += qs[q].class_ids[i];
+      key += '\n';
+    }
+    key += '\x01';
   }
-  auto hit = pk.filtered.find(key);
-  if (hit != pk.filtered.end()) {
-    wl.d_work = hit->second.work.as<uint32_t>(); wl.d_order = hit->second.order.as<uint32_t>();
-    wl.n = hit->second.n; wl.coarse_bytes = hit->second.coarse_bytes;
-    return LM_OK;
-  }
-  std::vector<uint32_t> work, order;
-  // order keys of a filtered run: position in the filtered iteration (a class may be listed more than once)
-  uint32_t base = 0;
-  for (int i = 0; i < n_ids; ++i) {
-    auto it = d->model.classes.find(class_ids[i]);
-    if (it == d->model.classes.end()) continue;
-    for (const Pack::ClassRange& cr : pk.classes)
-      if (cr.id == class_ids[i]) {
-        uint32_t first_global = 0;
-        // canonical position of this class's template 0
-        { uint32_t g = 0; for (auto jt = d->model.classes.begin(); jt != it; ++jt) g += (uint32_t)jt->second.size(); first_global = g; }
-        for (size_t k = 0; k < cr.local.size(); ++k) {
-          work.push_back(cr.local[k]);
-          order.push_back(base + (cr.global_pos[k] - first_global));
-          wl.coarse_bytes += pk.coarse_bytes[cr.local[k]];
-        }
+  auto hit = pk.plans.find(key);
+  if (hit != pk.plans.end()) { *out = &hit->second; return LM_OK; }
+  std::vector<WorkItem> items;
+  struct Tile { uint2 t; uint64_t cost; };
+  std::vector<Tile> tiles;
+  Pack::Plan plan;
+  const int pass_pos = coarse_positions_per_pass();
+  auto add_class = [&](const Pack::ClassRange& cr, uint32_t base, uint32_t first_global, int q) {
+    for (size_t k = 0; k < cr.local.size(); ++k) {
+      const uint32_t local = cr.local[k];
+      WorkItem it;
+      it.tglob = local;
+      it.order = (base + (cr.global_pos[k] - first_global)) | ((uint32_t)q << 28);
+      const CoarseTpl& ct = pk.h_ctpl[local];
+      uint64_t nfeat = 0;
+      for (int m = 0; m < LM_MAX_MODALITIES; ++m) for (int g = 0; g < 4; ++g) nfeat += ct.cnt[m][g];
+      for (int pass = 0; pass * pass_pos < ct.P; ++pass) {
+        Tile t;
+        t.t.x = (uint32_t)items.size(); t.t.y = (uint32_t)pass;
+        t.cost = nfeat * (uint64_t)std::min(pass_pos, ct.P - pass * pass_pos);
+        tiles.push_back(t);
       }
-    base += (uint32_t)it->second.size();
+      items.push_back(it);
+      plan.coarse_bytes += pk.coarse_bytes[local];
+      plan.refine_nf_sum += pk.refine_nf[local];
+    }
+  };
+  for (int q = 0; q < n_q; ++q) {
+    if (qs[q].n_ids == 0) {
+      for (const Pack::ClassRange& cr : pk.classes) add_class(cr, 0, 0, q);  // order key = canonical index
+    } else {
+      uint32_t base = 0;  // position in the filtered iteration (a class may be listed more than once)
+      for (int i = 0; i < qs[q].n_ids; ++i) {
+        auto it = d->model.classes.find(qs[q].class_ids[i]);
+        if (it == d->model.classes.end()) continue;
+        uint32_t first_global = 0;
+        for (auto jt = d->model.classes.begin(); jt != it; ++jt) first_global += (uint32_t)jt->second.size();
+        for (const Pack::ClassRange& cr : pk.classes)
+          if (cr.id == qs[q].class_ids[i]) add_class(cr, base, first_global, q);
+        base += (uint32_t)it->second.size();
+      }
+    }
   }
-  wl.n = (int)work.size();
-  Pack::Filtered& fl = pk.filtered[key];
-  fl.n = wl.n; fl.coarse_bytes = wl.coarse_bytes;
-  if (fl.work.ensure(work.size() * 4 + 64) != LM_OK || fl.order.ensure(order.size() * 4 + 64) != LM_OK) return LM_E_CUDA;
-  if (wl.n) {  // first use of this filter only: synchronous copies
-    CU(cudaMemcpy(fl.work.p, work.data(), work.size() * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(fl.order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice));
-  }
-  wl.d_work = fl.work.as<uint32_t>(); wl.d_order = fl.order.as<uint32_t>();
-  (void)ln;
+  if (items.size() >= (1u << 28)) return fail(LM_E_INVALID, "too many templates in one request");
+  std::stable_sort(tiles.begin(), tiles.end(), [](const Tile& a, const Tile& b) { return a.cost > b.cost; });
+  std::vector<uint2> tl(tiles.size());
+  for (size_t i = 0; i < tiles.size(); ++i) tl[i] = tiles[i].t;
+  plan.n_items = (int)items.size();
+  plan.n_tiles = (int)tl.size();
+  plan.evals = (uint64_t)items.size();
+  Pack::Plan& dst = pk.plans[key];
+  dst = plan;
+  if (dst.items.ensure(items.size() * sizeof(WorkItem) + 64) != LM_OK || dst.tiles.ensure(tl.size() * sizeof(uint2) + 64) != LM_OK) return LM_E_CUDA;
+  if (!items.empty()) CU(cudaMemcpy(dst.items.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+  if (!tl.empty()) CU(cudaMemcpy(dst.tiles.p, tl.data(), tl.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+  *out = &dst;
   return LM_OK;
 }
 
-static const size_t kFirstChunkRecords = 2048;  // records fetched together with each header in one D2H copy
-static const int kMaxQueries = 8;               // (class list, threshold) queries answered from one front end
+static size_t result_bytes(const Lane& ln) { return sizeof(ResultHeader) + (size_t)ln.out_cap * sizeof(lm_raw_match); }
 
-static size_t region_stride(const Lane& ln) { return sizeof(ResultHeader) + (size_t)ln.out_cap * sizeof(lm_raw_match); }
-
-static int ensure_match_buffers(Lane& ln, uint32_t cand_cap, uint32_t out_cap, int n_q) {
+static int ensure_match_buffers(Lane& ln, uint32_t cand_cap, uint32_t out_cap) {
   if (cand_cap > ln.cand_cap) {
     if (ln.cand.ensure((size_t)cand_cap * sizeof(Cand)) != LM_OK) return LM_E_CUDA;
     ln.cand_cap = cand_cap;
   }
   if (out_cap > ln.out_cap) ln.out_cap = out_cap;
-  if (n_q > ln.n_regions) ln.n_regions = n_q;
-  const size_t total = (size_t)ln.n_regions * region_stride(ln);
-  if (ln.result.ensure(total) != LM_OK) return LM_E_CUDA;
-  if (ln.stage_out.ensure(total) != LM_OK) return LM_E_CUDA;
+  if (ln.result.ensure(result_bytes(ln)) != LM_OK) return LM_E_CUDA;
+  if (ln.stage_out.ensure(result_bytes(ln)) != LM_OK) return LM_E_CUDA;
   return LM_OK;
 }
 
-// Enqueues coarse similarity + refinement of one query on stream s, into result region `qi`.
-static int enqueue_match(lm_detector* d, Lane& ln, const WorkList& wl, float threshold, int qi, cudaStream_t s,
+// Enqueues the request's coarse similarity + refinement on stream s: one launch each, whatever the number of queries.
+static int enqueue_match(lm_detector* d, Lane& ln, const Pack::Plan& plan, const Query* qs, int n_q, cudaStream_t s,
                          cudaEvent_t ev_mid) {
   const HostModel& md = d->model;
   const int L = md.levels(), M = md.M();
   Pack& pk = d->pack;
   const LevelGeom& gc = ln.geom[L - 1];
-  uint8_t* region = ln.result.as<uint8_t>() + (size_t)qi * region_stride(ln);
-  ResultHeader* d_hdr = reinterpret_cast<ResultHeader*>(region);
-  lm_raw_match* d_out = reinterpret_cast<lm_raw_match*>(region + sizeof(ResultHeader));
+  ResultHeader* d_hdr = ln.result.as<ResultHeader>();
+  lm_raw_match* d_out = reinterpret_cast<lm_raw_match*>(ln.result.as<uint8_t>() + sizeof(ResultHeader));
   CU(cudaMemsetAsync(d_hdr, 0, sizeof(ResultHeader), s));
-  launch_similarity_coarse(ln.lmem[L - 1].as<uint8_t>(), pk.foff.as<uint32_t>(), pk.ctpl.as<CoarseTpl>(), wl.d_work, wl.n,
-                           pk.max_P, threshold, M, ln.cand.as<Cand>(), d_hdr, ln.cand_cap, nullptr, 0,
-                           d->coarse_variant, s);
-  if (wl.n > 0 && pk.max_P > 0) ++ln.launches;
-  if (ev_mid) CU(cudaEventRecord(ev_mid, s));
+  QueryThresholds qt;
   RefineParams rp;
   std::memset(&rp, 0, sizeof(rp));
-  rp.levels = L; rp.M = M; rp.coarse_T = gc.T; rp.coarse_W = gc.W; rp.threshold = threshold;
+  std::memset(&qt, 0, sizeof(qt));
+  for (int q = 0; q < n_q; ++q) { qt.v[q] = qs[q].threshold; rp.threshold[q] = qs[q].threshold; }
+  launch_similarity_coarse(ln.lmem[L - 1].as<uint8_t>(), pk.foff.as<uint32_t>(), pk.ctpl.as<CoarseTpl>(),
+                           plan.items.as<WorkItem>(), plan.tiles.as<uint2>(), plan.n_tiles, qt, M, ln.cand.as<Cand>(), d_hdr,
+                           ln.cand_cap, nullptr, 0, s);
+  if (plan.n_tiles > 0) ++ln.launches;
+  if (ev_mid) CU(cudaEventRecord(ev_mid, s));
+  rp.levels = L; rp.M = M; rp.coarse_T = gc.T; rp.coarse_W = gc.W;
   for (int l = 0; l < L - 1; ++l) {
     const LevelGeom& g = ln.geom[l];
     rp.level[l].lm = ln.lmem[l].as<uint8_t>();
@@ -705,7 +720,8 @@ static int enqueue_match(lm_detector* d, Lane& ln, const WorkList& wl, float thr
     rp.level[l].plane_stride = g.plane_stride;
     rp.level[l].rows = g.rows; rp.level[l].cols = g.cols; rp.level[l].T = g.T; rp.level[l].W = g.W;
   }
-  launch_refine(rp, pk.ctpl.as<CoarseTpl>(), wl.d_order, ln.cand.as<Cand>(), ln.cand_cap, d_hdr, d_out, ln.out_cap, s);
+  launch_refine(rp, pk.ctpl.as<CoarseTpl>(), plan.items.as<WorkItem>(), ln.cand.as<Cand>(), ln.cand_cap, d_hdr, d_out,
+                ln.out_cap, s);
   ++ln.launches;
   CU(cudaGetLastError());
   return LM_OK;
@@ -743,33 +759,25 @@ static void finalize_records(int levels, std::vector<lm_raw_match>& raw, std::ve
   out.erase(std::unique(out.begin(), out.end(), match_equal), out.end());
 }
 
-// One strided D2H copy brings every query's header + first records; long lists need a second copy.
-static int download_records(Lane& ln, cudaStream_t s, int n_q, std::vector<lm_raw_match>* raw, bool* overflow,
-                            uint32_t* n_cands) {
+// One D2H copy brings the header + the first records; long lists need a second copy.
+static int download_records(Lane& ln, cudaStream_t s, std::vector<lm_raw_match>& raw, bool* overflow, uint32_t* n_cands) {
   const size_t first = std::min<size_t>(kFirstChunkRecords, ln.out_cap);
-  const size_t first_bytes = sizeof(ResultHeader) + first * sizeof(lm_raw_match);
-  const size_t stride = region_stride(ln);
   uint8_t* host = ln.stage_out.as<uint8_t>();
-  CU(cudaMemcpy2DAsync(host, stride, ln.result.p, stride, first_bytes, n_q, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(host, ln.result.p, sizeof(ResultHeader) + first * sizeof(lm_raw_match), cudaMemcpyDeviceToHost, s));
   CU(cudaEventRecord(ln.ev[5], s));
   CU(cudaStreamSynchronize(s));
-  *overflow = false;
-  for (int q = 0; q < n_q; ++q) {
-    ResultHeader h = *reinterpret_cast<ResultHeader*>(host + q * stride);
-    n_cands[q] = h.n_cands;
-    if (h.overflow != 0 || h.count > ln.out_cap) *overflow = true;
-  }
+  ResultHeader h = *reinterpret_cast<ResultHeader*>(host);
+  *overflow = h.overflow != 0 || h.count > ln.out_cap;
+  *n_cands = h.n_cands;
   if (*overflow) return LM_OK;
-  for (int q = 0; q < n_q; ++q) {
-    ResultHeader h = *reinterpret_cast<ResultHeader*>(host + q * stride);
-    if (h.count > first) {
-      CU(cudaMemcpyAsync(host + q * stride + first_bytes, ln.result.as<uint8_t>() + q * stride + first_bytes,
-                         (h.count - first) * sizeof(lm_raw_match), cudaMemcpyDeviceToHost, s));
-      CU(cudaStreamSynchronize(s));
-    }
-    const lm_raw_match* recs = reinterpret_cast<const lm_raw_match*>(host + q * stride + sizeof(ResultHeader));
-    raw[q].assign(recs, recs + h.count);
+  if (h.count > first) {
+    CU(cudaMemcpyAsync(host + sizeof(ResultHeader) + first * sizeof(lm_raw_match),
+                       ln.result.as<uint8_t>() + sizeof(ResultHeader) + first * sizeof(lm_raw_match),
+                       (h.count - first) * sizeof(lm_raw_match), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
   }
+  const lm_raw_match* recs = reinterpret_cast<const lm_raw_match*>(host + sizeof(ResultHeader));
+  raw.assign(recs, recs + h.count);
   return LM_OK;
 }
 
@@ -781,53 +789,47 @@ static void collect_timings(Lane& ln) {
   }
 }
 
-struct Query {
-  float threshold;
-  const char* const* class_ids;
-  int n_ids;
-};
+// Splits the request's survivors by query tag (order_key >> 28) and finalises each query's list.
+static void finalize_queries(lm_detector* d, Lane& ln, std::vector<lm_raw_match>& raw, int n_q, std::vector<lm_match_rec>* out) {
+  std::vector<lm_raw_match> part;
+  for (int q = 0; q < n_q; ++q) {
+    part.clear();
+    for (const lm_raw_match& r : raw)
+      if ((int)(r.order_key >> 28) == q) part.push_back(r);
+    finalize_records(d->model.levels(), part, ln.presort, out[q]);
+  }
+}
 
-// Matching on an already-built front end: every query is a coarse + refinement pass over its class list; buffers grow
-// and the queries are re-run on overflow (exactness over speed there).
+// Matching on an already-built front end; buffers grow and the request is re-run on overflow (exactness over speed).
 static int match_front(lm_detector* d, Lane& ln, const Query* queries, int n_q, std::vector<lm_match_rec>* out) {
   if (n_q < 1 || n_q > kMaxQueries) return fail(LM_E_INVALID, "number of queries must be 1..%d", kMaxQueries);
   int rc = ensure_pack(d, ln);
   if (rc != LM_OK) return rc;
-  WorkList wl[kMaxQueries];
-  for (int q = 0; q < n_q; ++q) {
-    rc = build_worklist(d, ln, queries[q].class_ids, queries[q].n_ids, wl[q]);
-    if (rc != LM_OK) return rc;
-  }
+  Pack::Plan* plan = nullptr;
+  rc = get_plan(d, queries, n_q, &plan);
+  if (rc != LM_OK) return rc;
   uint32_t cand_cap = std::max<uint32_t>(ln.cand_cap, 1u << 16), out_cap = std::max<uint32_t>(ln.out_cap, 1u << 14);
-  std::vector<lm_raw_match> raw[kMaxQueries];
-  uint32_t n_cands[kMaxQueries];
+  std::vector<lm_raw_match> raw;
+  uint32_t n_cands = 0;
   for (int attempt = 0;; ++attempt) {
-    if (ensure_match_buffers(ln, cand_cap, out_cap, n_q) != LM_OK) return LM_E_CUDA;
+    if (ensure_match_buffers(ln, cand_cap, out_cap) != LM_OK) return LM_E_CUDA;
     if (attempt > 0) CU(cudaEventRecord(ln.ev[2], ln.stream));
-    for (int q = 0; q < n_q; ++q)
-      if (enqueue_match(d, ln, wl[q], queries[q].threshold, q, ln.stream, q == 0 ? ln.ev[3] : nullptr) != LM_OK) return LM_E_CUDA;
+    if (enqueue_match(d, ln, *plan, queries, n_q, ln.stream, ln.ev[3]) != LM_OK) return LM_E_CUDA;
     CU(cudaEventRecord(ln.ev[4], ln.stream));
     bool overflow = false;
-    if (download_records(ln, ln.stream, n_q, raw, &overflow, n_cands) != LM_OK) return LM_E_CUDA;
+    if (download_records(ln, ln.stream, raw, &overflow, &n_cands) != LM_OK) return LM_E_CUDA;
     if (!overflow) break;
     if (attempt >= 8) return fail(LM_E_CUDA, "match buffers overflowed repeatedly");
-    uint32_t worst = 0;
-    for (int q = 0; q < n_q; ++q) worst = std::max(worst, n_cands[q]);
-    if (worst > ln.cand_cap) cand_cap = std::max<uint32_t>(worst + worst / 4, cand_cap * 2);
-    out_cap = std::max<uint32_t>(out_cap * 4, std::min<uint32_t>(worst + 1024, 1u << 26));
+    if (n_cands > ln.cand_cap) cand_cap = std::max<uint32_t>(n_cands + n_cands / 4, cand_cap * 2);
+    out_cap = std::max<uint32_t>(out_cap * 4, std::min<uint32_t>(n_cands + 1024, 1u << 26));
   }
-  // work accounting: B_coarse from the pack; B_refine = candidates x refine features x 256 bytes
-  uint64_t rsum = 0;
-  for (uint32_t v : d->pack.refine_nf) rsum += v;
-  const double mean_rnf = d->pack.n ? (double)rsum / d->pack.n : 0.0;
-  for (int q = 0; q < n_q; ++q) {
-    ln.work_stats[1] += wl[q].coarse_bytes;
-    ln.work_stats[4] += n_cands[q];
-    ln.work_stats[5] += (uint64_t)wl[q].n * (uint64_t)(ln.geom.back().W * ln.geom.back().H);
-    ln.work_stats[2] += (uint64_t)((double)n_cands[q] * mean_rnf * 256.0);
-    ln.work_stats[3] += 20ull * raw[q].size();
-    finalize_records(d->model.levels(), raw[q], ln.presort, out[q]);
-  }
+  // work accounting: B_coarse from the plan; B_refine = candidates x mean refine features x 256 bytes
+  ln.work_stats[1] = plan->coarse_bytes;
+  ln.work_stats[4] = n_cands;
+  ln.work_stats[5] = (uint64_t)plan->n_items * (uint64_t)(ln.geom.back().W * ln.geom.back().H);
+  ln.work_stats[2] = plan->n_items ? (uint64_t)((double)n_cands * (plan->refine_nf_sum / plan->n_items) * 256.0) : 0;
+  ln.work_stats[3] = 20ull * raw.size();
+  finalize_queries(d, ln, raw, n_q, out);
   return LM_OK;
 }
 
@@ -1275,13 +1277,13 @@ int lm_match_batch(lm_detector* d, const lm_image* sources, int n_frames, int n_
   out_offsets[0] = 0;
   const Query query = {threshold, class_ids, n_ids};
   // Two lanes: while lane A's kernels run, lane B's frame is packed into pinned memory and copied.
-  struct Pending { bool busy = false; WorkList wl; } pend[2];
+  bool busy[2] = {false, false};
   auto finish = [&](int li, int frame) -> int {
     Lane& ln = d->lane[li];
     std::vector<lm_raw_match> raw;
     bool overflow = false;
     uint32_t n_cands = 0;
-    if (download_records(ln, ln.stream, 1, &raw, &overflow, &n_cands) != LM_OK) return LM_E_CUDA;
+    if (download_records(ln, ln.stream, raw, &overflow, &n_cands) != LM_OK) return LM_E_CUDA;
     std::vector<lm_match_rec> out;
     if (overflow) {  // rare: redo this frame alone with growing buffers
       int rc = match_front(d, ln, &query, 1, &out);
@@ -1294,20 +1296,21 @@ int lm_match_batch(lm_detector* d, const lm_image* sources, int n_frames, int n_
   for (int f = 0; f < n_frames; ++f) {
     const int li = f & 1;
     Lane& ln = d->lane[li];
-    if (pend[li].busy) { int rc = finish(li, f - 2); if (rc != LM_OK) return rc; pend[li].busy = false; }
+    if (busy[li]) { int rc = finish(li, f - 2); if (rc != LM_OK) return rc; busy[li] = false; }
     int rc = front_from_host(d, ln, sources + (size_t)f * n_sources, n_sources, nullptr, 0);
     if (rc != LM_OK) return rc;
     rc = ensure_pack(d, ln);
     if (rc != LM_OK) return rc;
-    rc = build_worklist(d, ln, class_ids, n_ids, pend[li].wl);
+    Pack::Plan* plan = nullptr;
+    rc = get_plan(d, &query, 1, &plan);
     if (rc != LM_OK) return rc;
-    if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14), 1) != LM_OK) return LM_E_CUDA;
-    if (enqueue_match(d, ln, pend[li].wl, threshold, 0, ln.stream, ln.ev[3]) != LM_OK) return LM_E_CUDA;
+    if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
+    if (enqueue_match(d, ln, *plan, &query, 1, ln.stream, ln.ev[3]) != LM_OK) return LM_E_CUDA;
     CU(cudaEventRecord(ln.ev[4], ln.stream));
-    pend[li].busy = true;
+    busy[li] = true;
   }
   for (int f = std::max(0, n_frames - 2); f < n_frames; ++f)
-    if (pend[f & 1].busy) { int rc = finish(f & 1, f); if (rc != LM_OK) return rc; pend[f & 1].busy = false; }
+    if (busy[f & 1]) { int rc = finish(f & 1, f); if (rc != LM_OK) return rc; busy[f & 1] = false; }
   size_t n = 0;
   return copy_out(all, out_matches, &n);
 }
@@ -1316,7 +1319,7 @@ void lm_free_matches(lm_match_rec* m) { std::free(m); }
 
 int lm_match_device_multi(lm_detector* d, const void* const* d_sources, int n_sources, int rows, int cols,
                           const lm_query* queries, int n_queries, void* stream, const void** d_records,
-                          size_t* region_stride_bytes) {
+                          size_t* record_bytes_capacity) {
   if (!d || !d_sources || !d_records) return fail(LM_E_INVALID, "NULL argument");
   if (n_sources != d->model.M()) return fail(LM_E_INVALID, "sources.size() (%d) != modalities.size() (%d)", n_sources, d->model.M());
   Query qs[kMaxQueries];
@@ -1334,16 +1337,13 @@ int lm_match_device_multi(lm_detector* d, const void* const* d_sources, int n_so
   if (run_front(d, ln, s) != LM_OK) return LM_E_CUDA;
   rc = ensure_pack(d, ln);
   if (rc != LM_OK) return rc;
-  WorkList wl[kMaxQueries];
-  for (int q = 0; q < n_queries; ++q) {
-    rc = build_worklist(d, ln, qs[q].class_ids, qs[q].n_ids, wl[q]);
-    if (rc != LM_OK) return rc;
-  }
-  if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 18), std::max<uint32_t>(ln.out_cap, 1u << 14), n_queries) != LM_OK) return LM_E_CUDA;
-  for (int q = 0; q < n_queries; ++q)
-    if (enqueue_match(d, ln, wl[q], qs[q].threshold, q, s, nullptr) != LM_OK) return LM_E_CUDA;
+  Pack::Plan* plan = nullptr;
+  rc = get_plan(d, qs, n_queries, &plan);
+  if (rc != LM_OK) return rc;
+  if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 18), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
+  if (enqueue_match(d, ln, *plan, qs, n_queries, s, nullptr) != LM_OK) return LM_E_CUDA;
   *d_records = ln.result.p;
-  if (region_stride_bytes) *region_stride_bytes = region_stride(ln);
+  if (record_bytes_capacity) *record_bytes_capacity = result_bytes(ln);
   return LM_OK;
 }
 
@@ -1418,17 +1418,23 @@ int lm_debug_coarse_map(lm_detector* d, const char* class_id, int template_id, u
   if (local < 0) return fail(LM_E_NOTFOUND, "class '%s' template %d is not on this shard", class_id, template_id);
   const LevelGeom& gc = ln.geom.back();
   const int WH = gc.W * gc.H;
-  if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14), 1) != LM_OK) return LM_E_CUDA;
-  if (ln.dump.ensure((size_t)WH * 2) != LM_OK || ln.work.ensure(64) != LM_OK) return LM_E_CUDA;
-  uint32_t w = (uint32_t)local;
+  if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
+  const int pass_pos = coarse_positions_per_pass();
+  const int P = pk.h_ctpl[local].P;
+  std::vector<uint2> tl;
+  for (int pass = 0; pass * pass_pos < P; ++pass) tl.push_back(make_uint2(0u, (uint32_t)pass));
+  if (ln.dump.ensure((size_t)WH * 2) != LM_OK || ln.work.ensure(64) != LM_OK || ln.work_order.ensure(tl.size() * sizeof(uint2) + 64) != LM_OK) return LM_E_CUDA;
+  WorkItem it = {(uint32_t)local, 0u};
   CU(cudaMemsetAsync(ln.dump.p, 0, (size_t)WH * 2, ln.stream));
-  CU(cudaMemcpyAsync(ln.work.p, &w, 4, cudaMemcpyHostToDevice, ln.stream));
+  CU(cudaMemcpyAsync(ln.work.p, &it, sizeof(it), cudaMemcpyHostToDevice, ln.stream));
+  if (!tl.empty()) CU(cudaMemcpyAsync(ln.work_order.p, tl.data(), tl.size() * sizeof(uint2), cudaMemcpyHostToDevice, ln.stream));
   CU(cudaMemsetAsync(ln.result.p, 0, sizeof(ResultHeader), ln.stream));
   // threshold 1e30 -> raw threshold saturates: nothing becomes a candidate, the kernel only dumps its accumulators
+  QueryThresholds qt;
+  for (int q = 0; q < LM_MAX_QUERIES; ++q) qt.v[q] = 1e30f;
   launch_similarity_coarse(ln.lmem[d->model.levels() - 1].as<uint8_t>(), pk.foff.as<uint32_t>(), pk.ctpl.as<CoarseTpl>(),
-                           ln.work.as<uint32_t>(), 1, pk.h_ctpl[local].P, 1e30f, d->model.M(),
-                           ln.cand.as<Cand>(), ln.result.as<ResultHeader>(), 0, ln.dump.as<uint16_t>(), WH,
-                           d->coarse_variant, ln.stream);
+                           ln.work.as<WorkItem>(), ln.work_order.as<uint2>(), (int)tl.size(), qt, d->model.M(),
+                           ln.cand.as<Cand>(), ln.result.as<ResultHeader>(), 0, ln.dump.as<uint16_t>(), WH, ln.stream);
   CU(cudaMemcpyAsync(dst, ln.dump.p, (size_t)WH * 2, cudaMemcpyDeviceToHost, ln.stream));
   CU(cudaStreamSynchronize(ln.stream));
   return LM_OK;

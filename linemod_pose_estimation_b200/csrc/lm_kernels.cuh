@@ -14,6 +14,8 @@
 
 #include "../../include/linemod_b200.h"
 
+#define LM_MAX_QUERIES 8
+
 namespace lmk {
 
 struct CoarseTpl {                        // one per template (canonical order), coarse (lowest) pyramid level
@@ -43,15 +45,26 @@ struct RefineLevel {
 struct RefineParams {
   RefineLevel level[LM_MAX_LEVELS];       // index = pyramid level (only 0 .. L-2 used)
   int levels, M, coarse_T, coarse_W;
-  float threshold;
+  float threshold[LM_MAX_QUERIES];        // per query of the request
+};
+
+struct QueryThresholds {
+  float v[LM_MAX_QUERIES];
+};
+
+struct WorkItem {                         // one template of one query of the request
+  uint32_t tglob;                         // index into the packed template records of this shard
+  uint32_t order;                         // emission order key: position in the query's iteration | query << 28
 };
 
 struct Cand {                             // coarse candidate: raw score above the template's raw threshold
-  uint32_t tglob, pos, raw, pad;
+  uint32_t tglob, pos, raw, item;
 };
 
-struct ResultHeader {  // zeroed before every query; `capacity` is filled in by the host when a block leaves the GPU
-  uint32_t count, capacity, overflow, n_cands;
+struct ResultHeader {                     // zeroed before every request
+  uint32_t count;                         // surviving matches written (may exceed the capacity: overflow)
+  uint32_t next_tile;                     // coarse kernel's tile dispenser
+  uint32_t overflow, n_cands;
 };
 
 // ------------------------------------------------------------------------------------------------ front end
@@ -110,13 +123,13 @@ int spread_all_blocks(int W, int H, int* blocks_x);
 bool launch_spread_all(const SpreadParams& p, int total_blocks, int max_T, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------ matching
-// dump (nullable): u16 totals, [work index][W*H], written for every scored position (parity tap).
-void launch_similarity_coarse(const uint8_t* lmc, const uint32_t* foff, const CoarseTpl* tpl, const uint32_t* work,
-                              int n_work, int max_P, float threshold, int M, Cand* cand,
-                              ResultHeader* hdr, uint32_t cand_cap, uint16_t* dump, int dump_stride, int variant,
-                              cudaStream_t s);
-// work_order[i]: canonical order key of work item i (Cand::pad carries i).
-void launch_refine(const RefineParams& p, const CoarseTpl* ctpl, const uint32_t* work_order, const Cand* cand,
+// tiles: (work item, pass) pairs with at least one position, heaviest first.  dump (nullable): u16 totals,
+// [work item][dump_stride], written for every scored position (parity tap).
+int coarse_positions_per_pass();
+void launch_similarity_coarse(const uint8_t* lmc, const uint32_t* foff, const CoarseTpl* tpl, const WorkItem* items,
+                              const uint2* tiles, int n_tiles, const QueryThresholds& thr, int M, Cand* cand,
+                              ResultHeader* hdr, uint32_t cand_cap, uint16_t* dump, int dump_stride, cudaStream_t s);
+void launch_refine(const RefineParams& p, const CoarseTpl* ctpl, const WorkItem* items, const Cand* cand,
                    uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* out, uint32_t out_cap, cudaStream_t s);
 
 }  // namespace lmk

@@ -63,97 +63,104 @@ __device__ __forceinline__ void add_group(const uint8_t* __restrict__ lmc, const
 }
 
 // Coarse similarity of every (template, position) at the lowest pyramid level, thresholded in registers.
-// A warp owns one (template, 512-position pass) tile; tiles are dealt round-robin to a persistent grid.  There are no
-// warp collectives in the hot loop: every lane fetches its own (unaligned) 16-byte window with two vector loads.
+// A warp owns one (work item, 512-position pass) tile at a time; the non-empty tiles of all queries of the request
+// are listed heaviest-first and handed out through an atomic counter, so the persistent grid stays balanced to the
+// last tile.  There are no warp collectives in the accumulation loop: every lane fetches its own (unaligned) 16-byte
+// window with two vector loads.
 __global__ void __launch_bounds__(256) k_similarity_coarse(const uint8_t* __restrict__ lmc,
                                                            const uint32_t* __restrict__ foff,
                                                            const CoarseTpl* __restrict__ tpl,
-                                                           const uint32_t* __restrict__ work, int n_work,
-                                                           int passes_per_tpl, float threshold,
-                                                           int M, Cand* __restrict__ cand, ResultHeader* hdr,
-                                                           uint32_t cand_cap, uint16_t* __restrict__ dump,
-                                                           int dump_stride) {
+                                                           const WorkItem* __restrict__ items,
+                                                           const uint2* __restrict__ tiles, int n_tiles,
+                                                           const QueryThresholds thr_q, int M, Cand* __restrict__ cand,
+                                                           ResultHeader* hdr, uint32_t cand_cap,
+                                                           uint16_t* __restrict__ dump, int dump_stride) {
   const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int n_warps = (gridDim.x * blockDim.x) >> 5;
-  const int n_tiles = n_work * passes_per_tpl;
-  for (int tile = warp; tile < n_tiles; tile += n_warps) {
-    const int wi = tile / passes_per_tpl;
-    const int pass = tile - wi * passes_per_tpl;
-    const uint32_t tg = work[wi];
-    const int t_P = tpl[tg].P;
-    const int j0 = pass * kWarpPos;
-    if (j0 >= t_P) continue;
-    const int rem = min(t_P - j0, kWarpPos);  // positions of this pass
-    const int first = lane * kLanePos;        // first position of this lane within the pass
-    if (first >= rem) continue;               // lane has no position to score
-    const uint32_t t_feat_begin = tpl[tg].feat_begin, t_nf = tpl[tg].nf;
-    const uint32_t lane_off = (uint32_t)(j0 + first);
-    uint32_t tot_lo[4] = {0, 0, 0, 0}, tot_hi[4] = {0, 0, 0, 0};  // u16 x 2 per word: bytes (0,2) and (1,3)
-    const uint32_t* fp = foff + t_feat_begin;
-    for (int m = 0; m < M; ++m) {
-      uint32_t acc[4] = {0, 0, 0, 0};
-      const uint32_t c4 = __ldg(reinterpret_cast<const uint32_t*>(tpl[tg].cnt) + m);  // 4 group sizes, one word
-      const int n0 = c4 & 255, n1 = (c4 >> 8) & 255, n2 = (c4 >> 16) & 255, n3 = c4 >> 24;
-      add_group<0>(lmc, fp, n0, lane_off, acc); fp += n0;
-      add_group<1>(lmc, fp, n1, lane_off, acc); fp += n1;
-      add_group<2>(lmc, fp, n2, lane_off, acc); fp += n2;
-      add_group<3>(lmc, fp, n3, lane_off, acc); fp += n3;
+  for (;;) {
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(&hdr->next_tile, 1u);
+    tile = __shfl_sync(kFull, tile, 0);
+    if (tile >= (uint32_t)n_tiles) break;
+    const uint2 tl = tiles[tile];
+    const uint32_t item = tl.x;
+    const int j0 = (int)tl.y * kWarpPos;
+    const WorkItem wi = items[item];
+    const uint32_t tg = wi.tglob;
+    const int rem = min(tpl[tg].P - j0, kWarpPos);  // positions of this pass (> 0 by construction of the tile list)
+    const int first = lane * kLanePos;               // first position of this lane within the pass
+    if (first < rem) {
+      const uint32_t t_feat_begin = tpl[tg].feat_begin, t_nf = tpl[tg].nf;
+      const uint32_t lane_off = (uint32_t)(j0 + first);
+      uint32_t tot_lo[4] = {0, 0, 0, 0}, tot_hi[4] = {0, 0, 0, 0};  // u16 x 2 per word: bytes (0,2) and (1,3)
+      const uint32_t* fp = foff + t_feat_begin;
+      for (int m = 0; m < M; ++m) {
+        uint32_t acc[4] = {0, 0, 0, 0};
+        const uint32_t c4 = __ldg(reinterpret_cast<const uint32_t*>(tpl[tg].cnt) + m);  // 4 group sizes, one word
+        const int n0 = c4 & 255, n1 = (c4 >> 8) & 255, n2 = (c4 >> 16) & 255, n3 = c4 >> 24;
+        add_group<0>(lmc, fp, n0, lane_off, acc); fp += n0;
+        add_group<1>(lmc, fp, n1, lane_off, acc); fp += n1;
+        add_group<2>(lmc, fp, n2, lane_off, acc); fp += n2;
+        add_group<3>(lmc, fp, n3, lane_off, acc); fp += n3;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {  // [OCV] addSimilarities: widen u8 -> u16 and add the modality
-        tot_lo[k] += acc[k] & 0x00ff00ffu;
-        tot_hi[k] += (acc[k] >> 8) & 0x00ff00ffu;
-      }
-    }
-    // [OCV] matchClass: raw_threshold = (int)(2*nf + (threshold / 100.f) * (2*nf) + 0.5f), same f32 roundings
-    const float two_nf = (float)(2 * (int)t_nf);
-    const int thr = __float2int_rz(__fadd_rn(__fadd_rn(two_nf, __fmul_rn(__fdiv_rn(threshold, 100.f), two_nf)), 0.5f));
-    bool hit = thr < 0;
-    if (!hit) {
-      const uint32_t thr2 = (uint32_t)min(thr, 0xffff) * 0x00010001u;
-      uint32_t any = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) any |= __vcmpgtu2(tot_lo[k], thr2) | __vcmpgtu2(tot_hi[k], thr2);
-      hit = any != 0;
-    }
-    if (dump != nullptr) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          int p = first + 4 * k + i;
-          uint32_t src = (i & 1) ? tot_hi[k] : tot_lo[k];
-          if (p < rem) dump[(size_t)wi * dump_stride + j0 + p] = (uint16_t)((i & 2) ? (src >> 16) : (src & 0xffffu));
+        for (int k = 0; k < 4; ++k) {  // [OCV] addSimilarities: widen u8 -> u16 and add the modality
+          tot_lo[k] += acc[k] & 0x00ff00ffu;
+          tot_hi[k] += (acc[k] >> 8) & 0x00ff00ffu;
         }
-    }
-    if (hit) {  // rare: [OCV] matchClass raster scan, "raw_score > raw_threshold"
+      }
+      // [OCV] matchClass: raw_threshold = (int)(2*nf + (threshold / 100.f) * (2*nf) + 0.5f), same f32 roundings
+      const float threshold = thr_q.v[wi.order >> 28];
+      const float two_nf = (float)(2 * (int)t_nf);
+      const int thr = __float2int_rz(__fadd_rn(__fadd_rn(two_nf, __fmul_rn(__fdiv_rn(threshold, 100.f), two_nf)), 0.5f));
+      bool hit = thr < 0;
+      if (!hit) {
+        const uint32_t thr2 = (uint32_t)min(thr, 0xffff) * 0x00010001u;
+        uint32_t any = 0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < 4; ++k) any |= __vcmpgtu2(tot_lo[k], thr2) | __vcmpgtu2(tot_hi[k], thr2);
+        hit = any != 0;
+      }
+      if (dump != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          int p = first + 4 * k + i;
-          uint32_t src = (i & 1) ? tot_hi[k] : tot_lo[k];
-          int raw = (int)((i & 2) ? (src >> 16) : (src & 0xffffu));
-          if (p < rem && raw > thr) {
-            uint32_t idx = atomicAdd(&hdr->n_cands, 1u);
-            if (idx < cand_cap) {
-              Cand c;
-              c.tglob = tg; c.pos = (uint32_t)(j0 + p); c.raw = (uint32_t)raw; c.pad = (uint32_t)wi;
-              cand[idx] = c;
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int p = first + 4 * k + i;
+            uint32_t src = (i & 1) ? tot_hi[k] : tot_lo[k];
+            if (p < rem) dump[(size_t)item * dump_stride + j0 + p] = (uint16_t)((i & 2) ? (src >> 16) : (src & 0xffffu));
+          }
+      }
+      if (hit) {  // rare: [OCV] matchClass raster scan, "raw_score > raw_threshold"
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int p = first + 4 * k + i;
+            uint32_t src = (i & 1) ? tot_hi[k] : tot_lo[k];
+            int raw = (int)((i & 2) ? (src >> 16) : (src & 0xffffu));
+            if (p < rem && raw > thr) {
+              uint32_t idx = atomicAdd(&hdr->n_cands, 1u);
+              if (idx < cand_cap) {
+                Cand c;
+                c.tglob = tg; c.pos = (uint32_t)(j0 + p); c.raw = (uint32_t)raw; c.item = item;
+                cand[idx] = c;
+              }
             }
           }
-        }
+      }
     }
+    __syncwarp();
   }
 }
 
 // Local refinement of every coarse candidate up the pyramid.  One 8-warp block per candidate: the 16 x 16 patch is
 // mapped lane -> (row = lane / 2, 8 columns = lane % 2) in every warp, the template's features are dealt round-robin
 // to the warps (each keeps its own u8 accumulators), and the per-warp u16 partial sums meet in shared memory.
+// Features that fall outside the image after the shift are redirected to a zero byte run instead of being skipped, so
+// that a warp's loads stay independent and overlap.
 constexpr int kRefineWarps = 8;
 
 __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams P, const CoarseTpl* __restrict__ ctpl,
-                                                             const uint32_t* __restrict__ work_order,
+                                                             const WorkItem* __restrict__ items,
                                                              const Cand* __restrict__ cand, uint32_t cand_cap,
                                                              ResultHeader* hdr, lm_raw_match* __restrict__ out,
                                                              uint32_t out_cap) {
@@ -165,6 +172,8 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams
   const int prow = lane >> 1, pcol0 = (lane & 1) * 8;
   for (uint32_t ci = blockIdx.x; ci < n_cands; ci += gridDim.x) {
     const Cand c = cand[ci];
+    const uint32_t order = items[c.item].order;
+    const float threshold = P.threshold[order >> 28];
     const int cT = P.coarse_T;
     const int coff = cT / 2 + (cT % 2 - 1);
     int x = (int)(c.pos % (uint32_t)P.coarse_W) * cT + coff;
@@ -182,6 +191,7 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams
       x = min(x, max_x); y = min(y, max_y);
       const int offset_x = (x / T - 8) * T, offset_y = (y / T - 8) * T;
       const size_t WH = (size_t)W * (L.rows / T);
+      const size_t zero_run = (size_t)L.plane_stride - 16;  // the tail of every plane is zero (App. D-2 padding)
       uint32_t tot[4] = {0, 0, 0, 0};  // 8 x u16: columns pcol0 .. pcol0+7 as (0,2),(1,3),(4,6),(5,7)
       const uint32_t* fp = L.feats + rtp->feat_begin;
       for (int m = 0; m < P.M; ++m) {
@@ -190,15 +200,16 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams
         const int n = rtp->cnt[m];
 #pragma unroll 4
         for (int f = warp; f < n; f += kRefineWarps) {
-          uint32_t pk = fp[f];
-          int fx = (int)(pk & 0x1fffu) - 4096 + offset_x, fy = (int)((pk >> 13) & 0x1fffu) - 4096 + offset_y;
-          if (fx < 0 || fy < 0 || fx >= L.cols || fy >= L.rows) continue;
-          int label = (int)(pk >> 26);
+          const uint32_t pk = fp[f];
+          const int fx = (int)(pk & 0x1fffu) - 4096 + offset_x, fy = (int)((pk >> 13) & 0x1fffu) - 4096 + offset_y;
+          const bool inside = fx >= 0 && fy >= 0 && fx < L.cols && fy < L.rows;
+          const int label = (int)(pk >> 26);
           size_t addr = (size_t)label * L.plane_stride + (size_t)((fy % T) * T + (fx % T)) * WH + (size_t)(fy / T) * W +
                         fx / T + (size_t)prow * W + pcol0;
+          if (!inside) addr = zero_run;  // "Discard feature if out of bounds": contributes zeros
           const uint8_t* p = lmm + (addr & ~(size_t)3);
           const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(addr & 3);
-          uint32_t w0 = ldg32(p), w1 = ldg32(p + 4), w2 = ldg32(p + 8);
+          const uint32_t w0 = ldg32(p), w1 = ldg32(p + 4), w2 = ldg32(p + 8);
           a0 += __byte_perm(w0, w1, sel);
           a1 += __byte_perm(w1, w2, sel);
         }
@@ -238,7 +249,7 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams
           float sim = __fdiv_rn(__fmul_rn((float)best_score, 100.f), (float)(4 * nfl));
           s_state[0] = (x / T - 8 + best_c) * T + off;
           s_state[1] = (y / T - 8 + best_r) * T + off;
-          s_state[2] = (sim < P.threshold) ? 0 : 1;  // [OCV] remove_if(MatchPredicate(threshold))
+          s_state[2] = (sim < threshold) ? 0 : 1;  // [OCV] remove_if(MatchPredicate(threshold))
           s_state[3] = best_score;
         }
       }
@@ -250,7 +261,7 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams
       uint32_t idx = atomicAdd(&hdr->count, 1u);
       if (idx < out_cap) {
         lm_raw_match r;
-        r.order_key = work_order[c.pad]; r.coarse_pos = c.pos; r.x = x; r.y = y; r.score = score; r.nf = nf;
+        r.order_key = order; r.coarse_pos = c.pos; r.x = x; r.y = y; r.score = score; r.nf = nf;
         r.template_id = ctpl[c.tglob].template_id; r.class_index = ctpl[c.tglob].class_index;
         out[idx] = r;
       } else hdr->overflow = 1;
@@ -260,24 +271,22 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams
 
 }  // namespace
 
-void launch_similarity_coarse(const uint8_t* lmc, const uint32_t* foff, const CoarseTpl* tpl, const uint32_t* work,
-                              int n_work, int max_P, float threshold, int M, Cand* cand,
-                              ResultHeader* hdr, uint32_t cand_cap, uint16_t* dump, int dump_stride, int variant,
-                              cudaStream_t s) {
-  (void)variant;
-  if (n_work <= 0 || max_P <= 0) return;
-  const int passes = (max_P + kWarpPos - 1) / kWarpPos;
-  const long long tiles = (long long)n_work * passes;
-  int blocks = (int)((tiles + 7) / 8);
-  const int persistent = 148 * 8;  // up to 8 resident CTAs (64 warps) per SM
+int coarse_positions_per_pass() { return kWarpPos; }
+
+void launch_similarity_coarse(const uint8_t* lmc, const uint32_t* foff, const CoarseTpl* tpl, const WorkItem* items,
+                              const uint2* tiles, int n_tiles, const QueryThresholds& thr, int M, Cand* cand,
+                              ResultHeader* hdr, uint32_t cand_cap, uint16_t* dump, int dump_stride, cudaStream_t s) {
+  if (n_tiles <= 0) return;
+  int blocks = (n_tiles + 7) / 8;
+  const int persistent = 148 * 4;  // 64 registers/thread: 4 resident 8-warp CTAs per SM
   if (blocks > persistent) blocks = persistent;
-  k_similarity_coarse<<<blocks, 256, 0, s>>>(lmc, foff, tpl, work, n_work, passes, threshold, M, cand, hdr,
-                                             cand_cap, dump, dump_stride);
+  k_similarity_coarse<<<blocks, 256, 0, s>>>(lmc, foff, tpl, items, tiles, n_tiles, thr, M, cand, hdr, cand_cap, dump,
+                                             dump_stride);
 }
 
-void launch_refine(const RefineParams& p, const CoarseTpl* ctpl, const uint32_t* work_order, const Cand* cand,
+void launch_refine(const RefineParams& p, const CoarseTpl* ctpl, const WorkItem* items, const Cand* cand,
                    uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* out, uint32_t out_cap, cudaStream_t s) {
-  k_refine<<<148 * 4, kRefineWarps * 32, 0, s>>>(p, ctpl, work_order, cand, cand_cap, hdr, out, out_cap);
+  k_refine<<<148 * 4, kRefineWarps * 32, 0, s>>>(p, ctpl, items, cand, cand_cap, hdr, out, out_cap);
 }
 
 }  // namespace lmk

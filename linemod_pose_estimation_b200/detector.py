@@ -205,14 +205,14 @@ class Detector:
         return [allm[offs[i]:offs[i + 1]] for i in range(len(queries))]
 
     def match_device_multi(self, d_ptrs, rows, cols, queries, stream=0):
-        """Device-resident sources, several queries, asynchronous on `stream`.
-        -> (device pointer of region 0, byte stride between the per-query regions)."""
+        """Device-resident sources, several queries, asynchronous on `stream`.  -> (device pointer of the record block,
+        capacity in bytes); a record's query index is order_key >> 28."""
         qarr, qkeep = _capi.query_array(queries)
         ptrs = (C.c_void_p * len(d_ptrs))(*d_ptrs)
-        rec, stride = C.c_void_p(), C.c_size_t()
+        rec, cap = C.c_void_p(), C.c_size_t()
         check(lib().lm_match_device_multi(self._h, ptrs, len(d_ptrs), rows, cols, qarr, len(queries),
-                                          C.c_void_p(stream), C.byref(rec), C.byref(stride)))
-        return rec.value, stride.value
+                                          C.c_void_p(stream), C.byref(rec), C.byref(cap)))
+        return rec.value, cap.value
 
     def match_batch(self, frames, threshold, class_ids=()):
         """frames: list of per-frame source lists.  -> list of match arrays (pipelined over two streams)."""

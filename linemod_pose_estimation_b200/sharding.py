@@ -61,9 +61,9 @@ def unpack_blocks(gathered, world, capacity):
 class ShardedMatcher:
     """Exchange + finalisation around a rank-local matcher.
 
-    local_match(frame_tensors, queries) must return one uint8 tensor per query holding the rank's survivor block with
-    room for at least `capacity` records (the CUDA library's blocks are used in place; the CPU tests build them with
-    pack_block)."""
+    local_match(frame_tensors, queries) must return a uint8 tensor holding the rank's survivor block for the whole
+    request (records tagged with their query index in order_key >> 28) with room for at least `capacity` records (the
+    CUDA library's block is used in place; the CPU tests build one with pack_block)."""
 
     def __init__(self, local_match, finalize, rank, world, group=None, capacity=4096):
         self.local_match, self.finalize = local_match, finalize
@@ -77,37 +77,28 @@ class ShardedMatcher:
                 dist.broadcast(t.view(torch.uint8), src=0, group=self.group)  # C1
         return tensors
 
-    def gather_async(self, blocks):
-        """C2, device side only: all-gather of the first `capacity` records of every query's survivor block.
-        blocks: list (one per query) of uint8 tensors.  Returns the gathered tensor [world][n_queries][block bytes];
-        nothing is synchronised, so this is what the device-timed path runs."""
+    def gather_async(self, block):
+        """C2, device side only: all-gather of the header + first `capacity` records of every rank's survivor block.
+        Nothing is synchronised, so this is what the device-timed path runs."""
         nbytes = RESULT_HEADER_BYTES + self.capacity * RECORD_BYTES
-        mine = torch.cat([b[:nbytes] for b in blocks]) if len(blocks) > 1 else blocks[0][:nbytes].contiguous()
+        mine = block[:nbytes]
         if self.world == 1:
             return mine
-        total = mine.numel() * self.world
+        total = nbytes * self.world
         if self._gather_buf is None or self._gather_buf.numel() != total or self._gather_buf.device != mine.device:
             self._gather_buf = torch.empty(total, dtype=torch.uint8, device=mine.device)
-        dist.all_gather_into_tensor(self._gather_buf, mine, group=self.group)
+        dist.all_gather_into_tensor(self._gather_buf, mine.contiguous(), group=self.group)
         return self._gather_buf
 
-    def gather(self, blocks):
-        """C2 + download: per query, the list of every rank's raw records.  Every rank sees every header, so all ranks
-        agree on whether a (rare) second round with a larger capacity is needed without an extra collective."""
-        if torch.is_tensor(blocks):
-            blocks = [blocks]
-        n_q = len(blocks)
+    def gather(self, block):
+        """C2 + download: every rank's raw records.  Every rank sees every header, so all ranks agree on whether a
+        (rare) second round with a larger capacity is needed without an extra collective."""
         while True:
-            nbytes = RESULT_HEADER_BYTES + self.capacity * RECORD_BYTES
-            host = self.gather_async(blocks).cpu().numpy().reshape(self.world, n_q, nbytes)
-            per_query, need = [], 0
-            for q in range(n_q):
-                raws, nd = unpack_blocks(np.ascontiguousarray(host[:, q, :]).reshape(-1), self.world, self.capacity)
-                per_query.append(raws)
-                need = max(need, nd)
+            host = self.gather_async(block).cpu().numpy()
+            raws, need = unpack_blocks(host, self.world, self.capacity)
             if need == 0:
-                return per_query
-            if need > (blocks[0].numel() - RESULT_HEADER_BYTES) // RECORD_BYTES:
+                return raws
+            if need > (block.numel() - RESULT_HEADER_BYTES) // RECORD_BYTES:
                 raise RuntimeError("survivor block too small for %d records" % need)
             self.capacity = int(need * 1.25) + 64
 
@@ -116,15 +107,13 @@ class ShardedMatcher:
         queries: [(threshold, [class ids])].  Returns the finalised match lists (one per query) on rank 0, None
         elsewhere."""
         self.broadcast_frame(frame_tensors)
-        blocks = self.local_match(frame_tensors, queries)
-        per_query = self.gather(blocks)
+        block = self.local_match(frame_tensors, queries)
+        raws = self.gather(block)
         if self.rank != 0:
             return None
-        out = []
-        for raws in per_query:
-            raw = np.concatenate(raws) if raws else np.zeros(0, RAW_DTYPE)
-            out.append(self.finalize(raw))
-        return out
+        raw = np.concatenate(raws) if raws else np.zeros(0, RAW_DTYPE)
+        tag = raw["order_key"] >> 28
+        return [self.finalize(raw[tag == q]) for q in range(len(queries))]
 
 
 class ShardedDetector(ShardedMatcher):
@@ -141,9 +130,8 @@ class ShardedDetector(ShardedMatcher):
     def _local(self, frame_tensors, queries):
         rows, cols = frame_tensors[0].shape[:2]
         ptrs = [t.data_ptr() for t in frame_tensors]
-        rec, stride = self.det.match_device_multi(ptrs, rows, cols, queries,
-                                                  stream=torch.cuda.current_stream().cuda_stream)
-        return [device_view(rec + q * stride, stride, self.device) for q in range(len(queries))]
+        rec, cap = self.det.match_device_multi(ptrs, rows, cols, queries, stream=torch.cuda.current_stream().cuda_stream)
+        return device_view(rec, cap, self.device)
 
     def frame_buffers(self, rows, cols, kinds):
         """Device buffers for one frame: uint8 [rows, cols, 3] for ColorGradient, int16-typed uint16 storage for depth."""

@@ -46,15 +46,17 @@ def _worker(rank, world, port, capacity, out_dir):
         def local_match(tensors, queries):
             b = tensors[0].numpy()
             d = tensors[1].numpy().view(np.uint16)
-            blocks = []
-            for thr, ids in queries:
+            parts = []
+            for q, (thr, ids) in enumerate(queries):
                 orc.match([b, d], thr, class_ids=ids, keep_candidates=True)
                 raw = orc.last_raw()
                 # this rank's template shard: canonical index % world == rank ("b" alone starts at its own offset 0,
                 # so recover the canonical index from class + template id)
                 canon = raw["template_id"] + np.where(raw["class_index"] == 1, orc.num_templates("a"), 0)
-                blocks.append(torch.from_numpy(pack_block(raw[canon % world == rank], 1 << 14)))
-            return blocks
+                mine = raw[canon % world == rank].copy()
+                mine["order_key"] |= np.uint32(q << 28)   # query tag, as the CUDA matcher emits it
+                parts.append(mine)
+            return torch.from_numpy(pack_block(np.concatenate(parts), 1 << 14))
 
         sm = ShardedMatcher(local_match, det.finalize_raw, rank, world, capacity=capacity)
         queries = [(70.0, []), (60.0, ["b"])]
