@@ -1,0 +1,356 @@
+// linemod_b200.hpp -- header-only C++ facade over the C ABI (linemod_b200.h) with the method set of
+// cv::linemod::Detector as the reference ROS package drives it:
+//
+//   cv::linemod::Detector(modalities, T_pyramid), ColorGradient(), DepthNormal()   /root/reference/src/renderer.cpp:179-185
+//   detector->match(sources, threshold, matches, class_ids, noArray())             src/rgbdDetector.cpp:31-34
+//   detector->addTemplate(sources, "obj", mask)                                    src/renderer.cpp:308
+//   readLinemod(filename): read(fs.root()) + readClass per "classes" entry         src/rgbdDetector.cpp:1668-1680
+//   writeLinemod(detector, filename): write(fs) + writeClass per class             src/renderer.cpp:56-70
+//   detector->getTemplates(class_id, template_id)                                  src/linemod_ensenso_detect_3_mult_detect_service.cpp:351,741-744
+//   detector->classIds(), numTemplates()                                           src/linemod_carmine_detect.cpp:319, src/renderer.cpp:61
+//
+// Types keep OpenCV's names and field order (Feature, Template, Match with the same operator< / operator==), images are
+// borrowed views (linemod_b200::Image) so no OpenCV headers are needed; define LINEMOD_B200_WITH_OPENCV before
+// including this file to get cv::Mat / cv::Rect overloads (see INTEGRATION.md for the three-line change in the
+// reference).  Failed preconditions that OpenCV reports with CV_Assert -> cv::Exception surface here as
+// linemod_b200::Exception carrying the LM_E_* code and the library's message.
+#ifndef LINEMOD_B200_HPP_
+#define LINEMOD_B200_HPP_
+
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "linemod_b200.h"
+
+#ifdef LINEMOD_B200_WITH_OPENCV
+#include <opencv2/core/core.hpp>
+#endif
+
+namespace linemod_b200 {
+
+class Exception : public std::runtime_error {
+ public:
+  Exception(int code_, const std::string& what) : std::runtime_error(what), code(code_) {}
+  int code;  // LM_E_*
+};
+
+namespace detail {
+inline int check(int rc) {
+  if (rc < 0) throw Exception(rc, lm_last_error());
+  return rc;
+}
+}  // namespace detail
+
+// cv::linemod::Feature
+struct Feature {
+  int x, y, label;
+  Feature() : x(0), y(0), label(0) {}
+  Feature(int x_, int y_, int label_) : x(x_), y(y_), label(label_) {}
+};
+
+// cv::linemod::Template
+struct Template {
+  int width, height, pyramid_level;
+  std::vector<Feature> features;
+  Template() : width(0), height(0), pyramid_level(0) {}
+};
+
+// cv::linemod::Match, including its ordering (similarity descending, then template_id ascending) and its equality
+// (x, y, similarity, class_id -- template_id is NOT compared).
+struct Match {
+  int x, y;
+  float similarity;
+  std::string class_id;
+  int template_id;
+  Match() : x(0), y(0), similarity(0), template_id(0) {}
+  Match(int x_, int y_, float s, const std::string& c, int t) : x(x_), y(y_), similarity(s), class_id(c), template_id(t) {}
+  bool operator<(const Match& rhs) const {
+    if (similarity != rhs.similarity) return similarity > rhs.similarity;
+    return template_id < rhs.template_id;
+  }
+  bool operator==(const Match& rhs) const {
+    return x == rhs.x && y == rhs.y && similarity == rhs.similarity && class_id == rhs.class_id;
+  }
+};
+
+struct Rect {
+  int x, y, width, height;
+  Rect() : x(0), y(0), width(0), height(0) {}
+};
+
+// Borrowed view of host pixels (the role cv::Mat plays in the reference's calls).  step = bytes between rows, so a
+// cropped ROI (mat_rgb(crop), ..._service.cpp:324-326) is passed without copying.
+struct Image {
+  const void* data;
+  int rows, cols, type;  // LM_8UC3 (BGR) / LM_16UC1 (depth, mm) / LM_8UC1 (mask)
+  size_t step;
+  Image() : data(nullptr), rows(0), cols(0), type(LM_8UC1), step(0) {}
+  Image(const void* d, int r, int c, int t, size_t s = 0) : data(d), rows(r), cols(c), type(t), step(s) {
+    if (step == 0) step = (size_t)cols * (type == LM_8UC3 ? 3 : type == LM_16UC1 ? 2 : 1);
+  }
+  bool empty() const { return data == nullptr; }
+#ifdef LINEMOD_B200_WITH_OPENCV
+  Image(const cv::Mat& m) : data(m.data), rows(m.rows), cols(m.cols), step(m.step[0]) {  // NOLINT: implicit on purpose
+    if (m.empty()) { data = nullptr; type = LM_8UC1; return; }
+    if (m.type() == CV_8UC3) type = LM_8UC3;
+    else if (m.type() == CV_16UC1) type = LM_16UC1;
+    else if (m.type() == CV_8UC1) type = LM_8UC1;
+    else throw Exception(LM_E_INVALID, "unsupported cv::Mat type (CV_8UC3, CV_16UC1 or CV_8UC1 expected)");
+  }
+#endif
+  lm_image c() const {
+    lm_image im;
+    im.data = data; im.rows = rows; im.cols = cols; im.type = type; im.step = step;
+    return im;
+  }
+};
+
+// cv::linemod::Modality and its two implementations: parameter carriers here, the processing is in the CUDA kernels.
+class Modality {
+ public:
+  virtual ~Modality() {}
+  virtual std::string name() const = 0;
+  virtual lm_modality_desc desc() const = 0;
+  static std::shared_ptr<Modality> create(const std::string& modality_type);
+};
+
+class ColorGradient : public Modality {
+ public:
+  ColorGradient() : weak_threshold(10.0f), num_features(63), strong_threshold(55.0f) {}
+  ColorGradient(float weak, size_t nf, float strong) : weak_threshold(weak), num_features(nf), strong_threshold(strong) {}
+  std::string name() const override { return "ColorGradient"; }
+  lm_modality_desc desc() const override {
+    lm_modality_desc d = {LM_COLOR_GRADIENT, weak_threshold, strong_threshold, 2000, 50, 2, (int32_t)num_features};
+    return d;
+  }
+  float weak_threshold;
+  size_t num_features;
+  float strong_threshold;
+};
+
+class DepthNormal : public Modality {
+ public:
+  DepthNormal() : distance_threshold(2000), difference_threshold(50), num_features(63), extract_threshold(2) {}
+  DepthNormal(int distance, int difference, size_t nf, int extract)
+      : distance_threshold(distance), difference_threshold(difference), num_features(nf), extract_threshold(extract) {}
+  std::string name() const override { return "DepthNormal"; }
+  lm_modality_desc desc() const override {
+    lm_modality_desc d = {LM_DEPTH_NORMAL, 10.0f, 55.0f, distance_threshold, difference_threshold, extract_threshold,
+                          (int32_t)num_features};
+    return d;
+  }
+  int distance_threshold, difference_threshold;
+  size_t num_features;
+  int extract_threshold;
+};
+
+inline std::shared_ptr<Modality> Modality::create(const std::string& modality_type) {
+  if (modality_type == "ColorGradient") return std::make_shared<ColorGradient>();
+  if (modality_type == "DepthNormal") return std::make_shared<DepthNormal>();
+  throw Exception(LM_E_INVALID, "unknown modality '" + modality_type + "'");
+}
+
+// cv::linemod::Detector
+class Detector {
+ public:
+  typedef std::vector<Template> TemplatePyramid;
+
+  // Empty detector, to be filled by read() exactly like `new cv::linemod::Detector` + read(fs.root()).
+  Detector() : h_(nullptr) {}
+  Detector(const std::vector<std::shared_ptr<Modality> >& modalities, const std::vector<int>& T_pyramid)
+      : h_(nullptr), modalities_(modalities) {
+    std::vector<lm_modality_desc> mods;
+    for (size_t i = 0; i < modalities.size(); ++i) mods.push_back(modalities[i]->desc());
+    std::vector<int32_t> T(T_pyramid.begin(), T_pyramid.end());
+    detail::check(lm_create(T.data(), (int)T.size(), mods.data(), (int)mods.size(), &h_));
+  }
+  ~Detector() { lm_destroy(h_); }
+  Detector(const Detector&) = delete;
+  Detector& operator=(const Detector&) = delete;
+
+  // Detector::match.  quantized_images (nullable) receives pyramidLevels()*modalities images, index l*M+m, each
+  // (rows>>l) x (cols>>l) bytes.  masks: empty or one LM_8UC1 image per modality.
+  void match(const std::vector<Image>& sources, float threshold, std::vector<Match>& matches,
+             const std::vector<std::string>& class_ids = std::vector<std::string>(),
+             std::vector<std::vector<uint8_t> >* quantized_images = nullptr,
+             const std::vector<Image>& masks = std::vector<Image>()) const {
+    need_handle();
+    std::vector<lm_image> src, msk;
+    for (size_t i = 0; i < sources.size(); ++i) src.push_back(sources[i].c());
+    for (size_t i = 0; i < masks.size(); ++i) msk.push_back(masks[i].c());
+    std::vector<const char*> ids;
+    for (size_t i = 0; i < class_ids.size(); ++i) ids.push_back(class_ids[i].c_str());
+    std::vector<lm_image_out> qout;
+    if (quantized_images && !sources.empty()) {
+      const int L = pyramidLevels(), M = lm_num_modalities(h_);
+      quantized_images->assign((size_t)L * M, std::vector<uint8_t>());
+      for (int l = 0; l < L; ++l)
+        for (int m = 0; m < M; ++m) {
+          std::vector<uint8_t>& q = (*quantized_images)[(size_t)l * M + m];
+          const int r = sources[0].rows >> l, c = sources[0].cols >> l;
+          q.assign((size_t)r * c, 0);
+          lm_image_out o;
+          o.data = q.data(); o.rows = r; o.cols = c; o.type = LM_8UC1; o.step = (size_t)c;
+          qout.push_back(o);
+        }
+    }
+    lm_match_rec* recs = nullptr;
+    size_t n = 0;
+    detail::check(lm_match(h_, src.data(), (int)src.size(), threshold, ids.empty() ? nullptr : ids.data(), (int)ids.size(),
+                           msk.empty() ? nullptr : msk.data(), (int)msk.size(), qout.empty() ? nullptr : qout.data(),
+                           &recs, &n));
+    matches.clear();
+    matches.reserve(n);
+    for (size_t i = 0; i < n; ++i)
+      matches.push_back(Match(recs[i].x, recs[i].y, recs[i].similarity, lm_class_id(h_, recs[i].class_index),
+                              recs[i].template_id));
+    lm_free_matches(recs);
+  }
+
+  // Detector::addTemplate: template_id, or -1 when some pyramid level lacks candidate features.
+  int addTemplate(const std::vector<Image>& sources, const std::string& class_id, const Image& object_mask,
+                  Rect* bounding_box = nullptr) {
+    need_handle();
+    std::vector<lm_image> src;
+    for (size_t i = 0; i < sources.size(); ++i) src.push_back(sources[i].c());
+    lm_image mask = object_mask.c();
+    lm_rect bb = {0, 0, 0, 0};
+    int id = lm_add_template(h_, src.data(), (int)src.size(), class_id.c_str(), object_mask.empty() ? nullptr : &mask, &bb);
+    if (id < -1) throw Exception(id + 100, lm_last_error());
+    if (bounding_box) { bounding_box->x = bb.x; bounding_box->y = bb.y; bounding_box->width = bb.width; bounding_box->height = bb.height; }
+    cache_.clear();
+    return id;
+  }
+
+  // Detector::addSyntheticTemplate
+  int addSyntheticTemplate(const std::vector<Template>& templates, const std::string& class_id) {
+    need_handle();
+    std::vector<lm_template_hdr> hdr(templates.size());
+    std::vector<int32_t> feats;
+    for (size_t i = 0; i < templates.size(); ++i) {
+      hdr[i].width = templates[i].width; hdr[i].height = templates[i].height;
+      hdr[i].pyramid_level = templates[i].pyramid_level; hdr[i].num_features = (int32_t)templates[i].features.size();
+      for (size_t j = 0; j < templates[i].features.size(); ++j) {
+        feats.push_back(templates[i].features[j].x); feats.push_back(templates[i].features[j].y);
+        feats.push_back(templates[i].features[j].label);
+      }
+    }
+    if (feats.empty()) feats.push_back(0);
+    cache_.clear();
+    return detail::check(lm_add_synthetic_template(h_, class_id.c_str(), (int)templates.size(), hdr.data(), feats.data()));
+  }
+
+  // Detector::getTemplates: the pyramid (index l*M+m) of one template; the reference stays valid until the next
+  // addTemplate / read on this detector.
+  const std::vector<Template>& getTemplates(const std::string& class_id, int template_id) const {
+    need_handle();
+    std::pair<std::string, int> key(class_id, template_id);
+    std::map<std::pair<std::string, int>, TemplatePyramid>::const_iterator it = cache_.find(key);
+    if (it != cache_.end()) return it->second;
+    const int n = pyramidLevels() * lm_num_modalities(h_);
+    std::vector<lm_template_hdr> hdr((size_t)n);
+    int total = detail::check(lm_get_templates(h_, class_id.c_str(), template_id, hdr.data(), nullptr));
+    std::vector<int32_t> feats((size_t)total * 3 + 3);
+    detail::check(lm_get_templates(h_, class_id.c_str(), template_id, hdr.data(), feats.data()));
+    TemplatePyramid tp((size_t)n);
+    size_t k = 0;
+    for (int i = 0; i < n; ++i) {
+      tp[i].width = hdr[i].width; tp[i].height = hdr[i].height; tp[i].pyramid_level = hdr[i].pyramid_level;
+      for (int j = 0; j < hdr[i].num_features; ++j, ++k)
+        tp[i].features.push_back(Feature(feats[3 * k], feats[3 * k + 1], feats[3 * k + 2]));
+    }
+    return cache_[key] = tp;
+  }
+
+  int numTemplates() const { return h_ ? lm_num_templates(h_, nullptr) : 0; }
+  int numTemplates(const std::string& class_id) const { return h_ ? lm_num_templates(h_, class_id.c_str()) : 0; }
+  int numClasses() const { return h_ ? lm_num_classes(h_) : 0; }
+  std::vector<std::string> classIds() const {
+    std::vector<std::string> ids;
+    for (int i = 0; i < numClasses(); ++i) ids.push_back(lm_class_id(h_, i));
+    return ids;
+  }
+  int pyramidLevels() const { return h_ ? lm_pyramid_levels(h_) : 0; }
+  int getT(int pyramid_level) const { need_handle(); return detail::check(lm_get_T(h_, pyramid_level)); }
+  const std::vector<std::shared_ptr<Modality> >& getModalities() const { return modalities_; }
+
+  // readLinemod(filename): Detector::read(fs.root()) followed by readClass for every entry of "classes".
+  void read(const std::string& filename) {
+    lm_detector* fresh = nullptr;
+    detail::check(lm_create_from_yaml(filename.c_str(), &fresh));
+    lm_destroy(h_);
+    h_ = fresh;
+    cache_.clear();
+    modalities_.clear();
+    for (int m = 0; m < lm_num_modalities(h_); ++m) {
+      lm_modality_desc d;
+      detail::check(lm_get_modality(h_, m, &d));
+      if (d.type == LM_COLOR_GRADIENT)
+        modalities_.push_back(std::make_shared<ColorGradient>(d.weak_threshold, (size_t)d.num_features, d.strong_threshold));
+      else
+        modalities_.push_back(std::make_shared<DepthNormal>(d.distance_threshold, d.difference_threshold,
+                                                            (size_t)d.num_features, d.extract_threshold));
+    }
+  }
+  // writeLinemod(detector, filename): Detector::write(fs) + "classes" [ { writeClass } ... ].
+  void write(const std::string& filename) const { need_handle(); detail::check(lm_write_yaml(h_, filename.c_str())); }
+  // Detector::readClasses / writeClasses (one FileStorage file per class, gzip when the name ends in .gz).
+  void readClasses(const std::vector<std::string>& class_ids, const std::string& format = "templates_%s.yml.gz") {
+    need_handle();
+    std::vector<const char*> ids;
+    for (size_t i = 0; i < class_ids.size(); ++i) ids.push_back(class_ids[i].c_str());
+    detail::check(lm_read_classes(h_, ids.data(), (int)ids.size(), format.c_str()));
+    cache_.clear();
+  }
+  void writeClasses(const std::string& format = "templates_%s.yml.gz") const {
+    need_handle();
+    detail::check(lm_write_classes(h_, format.c_str()));
+  }
+
+#ifdef LINEMOD_B200_WITH_OPENCV
+  // cv::Mat spellings of the two calls the reference makes with images.
+  void match(const std::vector<cv::Mat>& sources, float threshold, std::vector<Match>& matches,
+             const std::vector<std::string>& class_ids = std::vector<std::string>(),
+             std::vector<cv::Mat>* quantized_images = nullptr,
+             const std::vector<cv::Mat>& masks = std::vector<cv::Mat>()) const {
+    std::vector<Image> src(sources.begin(), sources.end()), msk(masks.begin(), masks.end());
+    std::vector<std::vector<uint8_t> > q;
+    match(src, threshold, matches, class_ids, quantized_images ? &q : nullptr, msk);
+    if (quantized_images) {
+      quantized_images->clear();
+      const int M = lm_num_modalities(h_);
+      for (size_t i = 0; i < q.size(); ++i) {
+        const int l = (int)i / M;
+        quantized_images->push_back(cv::Mat(sources[0].rows >> l, sources[0].cols >> l, CV_8UC1, q[i].data()).clone());
+      }
+    }
+  }
+  int addTemplate(const std::vector<cv::Mat>& sources, const std::string& class_id, const cv::Mat& object_mask,
+                  cv::Rect* bounding_box = nullptr) {
+    std::vector<Image> src(sources.begin(), sources.end());
+    Rect bb;
+    int id = addTemplate(src, class_id, Image(object_mask), &bb);
+    if (bounding_box) *bounding_box = cv::Rect(bb.x, bb.y, bb.width, bb.height);
+    return id;
+  }
+#endif
+
+  lm_detector* handle() const { return h_; }  // for the batch / multi-query / multi-GPU entry points of the C ABI
+
+ private:
+  void need_handle() const {
+    if (!h_) throw Exception(LM_E_STATE, "empty Detector: construct it with modalities or read() a templates.yml first");
+  }
+  lm_detector* h_;
+  std::vector<std::shared_ptr<Modality> > modalities_;
+  mutable std::map<std::pair<std::string, int>, TemplatePyramid> cache_;
+};
+
+}  // namespace linemod_b200
+
+#endif  // LINEMOD_B200_HPP_

@@ -1,0 +1,166 @@
+// facade_test.cpp -- exercises include/linemod_b200.hpp the way the reference drives cv::linemod::Detector
+// (/root/reference/src/renderer.cpp:179-185,308; src/rgbdDetector.cpp:31-34,1668-1680).
+//   facade_test host <tmpdir>   template bookkeeping + persistence, no CUDA device needed
+//   facade_test gpu  <tmpdir>   addTemplate + match on the GPU
+// Prints "ok <mode>" and exits 0 on success.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/linemod_b200.hpp"
+
+namespace lm = linemod_b200;
+
+#define REQUIRE(cond)                                                             \
+  do {                                                                            \
+    if (!(cond)) { std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); std::exit(1); } \
+  } while (0)
+
+static std::shared_ptr<lm::Detector> make_detector() {
+  std::vector<std::shared_ptr<lm::Modality> > modalities;
+  modalities.push_back(std::make_shared<lm::ColorGradient>());
+  modalities.push_back(std::make_shared<lm::DepthNormal>());
+  std::vector<int> T;
+  T.push_back(5);
+  T.push_back(8);
+  return std::make_shared<lm::Detector>(modalities, T);
+}
+
+static uint32_t rng_state = 12345u;
+static uint32_t rnd() { rng_state = rng_state * 1664525u + 1013904223u; return rng_state >> 8; }
+
+static std::vector<lm::Template> synthetic_pyramid(int w, int h) {
+  std::vector<lm::Template> tp(4);  // index l*M+m, L = 2, M = 2
+  for (int l = 0; l < 2; ++l)
+    for (int m = 0; m < 2; ++m) {
+      lm::Template& t = tp[l * 2 + m];
+      t.width = w >> l; t.height = h >> l; t.pyramid_level = l;
+      const int nf = l == 0 ? 63 : 31;
+      for (int i = 0; i < nf; ++i) t.features.push_back(lm::Feature((int)(rnd() % (w >> l)), (int)(rnd() % (h >> l)), (int)(rnd() % 8)));
+    }
+  return tp;
+}
+
+static int run_host(const std::string& dir) {
+  std::shared_ptr<lm::Detector> det = make_detector();
+  REQUIRE(det->pyramidLevels() == 2 && det->getT(0) == 5 && det->getT(1) == 8);
+  REQUIRE(det->getModalities().size() == 2 && det->getModalities()[0]->name() == "ColorGradient");
+  std::vector<lm::Template> a = synthetic_pyramid(120, 100), b = synthetic_pyramid(80, 90);
+  REQUIRE(det->addSyntheticTemplate(a, "obj") == 0);
+  REQUIRE(det->addSyntheticTemplate(b, "obj") == 1);
+  REQUIRE(det->addSyntheticTemplate(b, "another") == 0);
+  REQUIRE(det->numTemplates() == 3 && det->numTemplates("obj") == 2 && det->numClasses() == 2);
+  std::vector<std::string> ids = det->classIds();
+  REQUIRE(ids.size() == 2 && ids[0] == "another" && ids[1] == "obj");  // std::map order
+  const std::vector<lm::Template>& got = det->getTemplates("obj", 1);
+  REQUIRE(got.size() == 4 && got[0].width == 80 && got[3].features.size() == 31);
+  for (size_t i = 0; i < got.size(); ++i)
+    for (size_t j = 0; j < got[i].features.size(); ++j)
+      REQUIRE(got[i].features[j].x == b[i].features[j].x && got[i].features[j].y == b[i].features[j].y &&
+              got[i].features[j].label == b[i].features[j].label);
+  // writeLinemod / readLinemod round trip
+  const std::string path = dir + "/templates.yml";
+  det->write(path);
+  lm::Detector loaded;
+  REQUIRE(loaded.numTemplates() == 0);
+  loaded.read(path);
+  REQUIRE(loaded.numTemplates() == 3 && loaded.pyramidLevels() == 2 && loaded.getT(1) == 8);
+  REQUIRE(loaded.getModalities().size() == 2 && loaded.getModalities()[1]->name() == "DepthNormal");
+  const std::vector<lm::Template>& again = loaded.getTemplates("obj", 0);
+  REQUIRE(again.size() == 4 && again[0].features.size() == 63 && again[0].features[5].x == a[0].features[5].x);
+  // per-class files
+  det->writeClasses(dir + "/cls_%s.yml.gz");
+  std::shared_ptr<lm::Detector> fresh = make_detector();
+  fresh->readClasses(ids, dir + "/cls_%s.yml.gz");
+  REQUIRE(fresh->numTemplates("obj") == 2 && fresh->numTemplates("another") == 1);
+  // CV_Assert-style failures become exceptions
+  bool threw = false;
+  try { std::vector<lm::Template> bad(3); det->addSyntheticTemplate(bad, "obj"); } catch (const lm::Exception& e) { threw = e.code == LM_E_INVALID; }
+  REQUIRE(threw);
+  threw = false;
+  try { lm::Detector empty; std::vector<lm::Match> m; empty.match(std::vector<lm::Image>(), 90.f, m); } catch (const lm::Exception& e) { threw = e.code == LM_E_STATE; }
+  REQUIRE(threw);
+  threw = false;
+  try { lm::Detector missing; missing.read(dir + "/does_not_exist.yml"); } catch (const lm::Exception& e) { threw = e.code == LM_E_IO; }
+  REQUIRE(threw);
+  // Match ordering / equality as std::sort + std::unique see them
+  lm::Match m1(1, 2, 95.f, "obj", 7), m2(1, 2, 95.f, "obj", 3), m3(4, 2, 96.f, "obj", 9);
+  REQUIRE(m3 < m1 && m2 < m1 && m1 == m2 && !(m1 == m3));
+  std::printf("ok host\n");
+  return 0;
+}
+
+// A textured box on a tilted ground plane: enough gradient and normal structure for both modalities.
+static void scene(int rows, int cols, int ox, int oy, std::vector<uint8_t>& bgr, std::vector<uint16_t>& depth,
+                  std::vector<uint8_t>& mask, int bw, int bh) {
+  bgr.assign((size_t)rows * cols * 3, 0); depth.assign((size_t)rows * cols, 0); mask.assign((size_t)rows * cols, 0);
+  for (int y = 0; y < rows; ++y)
+    for (int x = 0; x < cols; ++x) {
+      uint8_t* p = &bgr[((size_t)y * cols + x) * 3];
+      p[0] = (uint8_t)(90 + (x * 40) / cols); p[1] = (uint8_t)(100 + (y * 30) / rows); p[2] = 110;
+      depth[(size_t)y * cols + x] = (uint16_t)(900 + y / 4);
+      const int u = x - ox, v = y - oy;
+      if (u >= 0 && u < bw && v >= 0 && v < bh) {
+        mask[(size_t)y * cols + x] = 255;
+        const int cell = ((u / 12) + (v / 12)) & 1, stripe = (u / 7) % 3;
+        p[0] = (uint8_t)(cell ? 30 : 10); p[1] = (uint8_t)(stripe == 0 ? 250 : 225); p[2] = (uint8_t)(cell ? 20 : 40);
+        depth[(size_t)y * cols + x] = (uint16_t)(600 + (u * 3) / 2 + ((v / 20) % 2 ? v : -v) / 2);
+      }
+    }
+}
+
+static int run_gpu(const std::string& dir) {
+  std::shared_ptr<lm::Detector> det = make_detector();
+  const int bw = 96, bh = 88;
+  std::vector<uint8_t> bgr, mask;
+  std::vector<uint16_t> depth;
+  scene(240, 240, 70, 60, bgr, depth, mask, bw, bh);
+  std::vector<lm::Image> sources;
+  sources.push_back(lm::Image(bgr.data(), 240, 240, LM_8UC3));
+  sources.push_back(lm::Image(depth.data(), 240, 240, LM_16UC1));
+  lm::Rect bb;
+  int id = det->addTemplate(sources, "obj", lm::Image(mask.data(), 240, 240, LM_8UC1), &bb);
+  REQUIRE(id == 0);
+  REQUIRE(bb.width > 40 && bb.height > 40 && bb.x >= 60 && bb.y >= 50);
+  // the same object elsewhere in a 640x480 frame
+  const int ox = 301, oy = 177;
+  scene(480, 640, ox, oy, bgr, depth, mask, bw, bh);
+  std::vector<lm::Image> frame;
+  frame.push_back(lm::Image(bgr.data(), 480, 640, LM_8UC3));
+  frame.push_back(lm::Image(depth.data(), 480, 640, LM_16UC1));
+  std::vector<lm::Match> matches;
+  std::vector<std::vector<uint8_t> > quantized;
+  det->match(frame, 80.f, matches, std::vector<std::string>(), &quantized);
+  REQUIRE(!matches.empty());
+  REQUIRE(quantized.size() == 4 && quantized[0].size() == 640u * 480u && quantized[2].size() == 320u * 240u);
+  for (size_t i = 1; i < matches.size(); ++i) REQUIRE(!(matches[i] < matches[i - 1]));  // sorted
+  const lm::Match& best = matches[0];
+  REQUIRE(best.class_id == "obj" && best.template_id == 0 && best.similarity >= 80.f);
+  // Match.x/y is where the template's (0,0) lands: the bounding-box corner shifted by the planted offset
+  REQUIRE(std::abs(best.x - (bb.x - 70 + ox)) <= 8 && std::abs(best.y - (bb.y - 60 + oy)) <= 8);
+  // class filter with an unknown id yields nothing; persistence keeps matching identical
+  std::vector<lm::Match> none;
+  det->match(frame, 80.f, none, std::vector<std::string>(1, "nope"));
+  REQUIRE(none.empty());
+  det->write(dir + "/gpu_templates.yml");
+  lm::Detector loaded;
+  loaded.read(dir + "/gpu_templates.yml");
+  std::vector<lm::Match> again;
+  loaded.match(frame, 80.f, again);
+  REQUIRE(again.size() == matches.size());
+  for (size_t i = 0; i < again.size(); ++i)
+    REQUIRE(again[i] == matches[i] && again[i].template_id == matches[i].template_id);
+  std::printf("ok gpu (%zu matches, best %.2f at %d,%d)\n", matches.size(), best.similarity, best.x, best.y);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 3) { std::fprintf(stderr, "usage: facade_test host|gpu <tmpdir>\n"); return 2; }
+  try {
+    return std::strcmp(argv[1], "gpu") == 0 ? run_gpu(argv[2]) : run_host(argv[2]);
+  } catch (const lm::Exception& e) {
+    std::fprintf(stderr, "linemod_b200::Exception %d: %s\n", e.code, e.what());
+    return 1;
+  }
+}
