@@ -212,6 +212,8 @@ int lm_get_normal_lut(const lm_detector* det, uint8_t lut[8000]);
 #define LM_STAGE_LINEAR 3    /* u8 [8][plane_stride]                             (linearize, flat + zero tail) */
 #define LM_STAGE_MAGNITUDE 4 /* f32 [rows][cols], ColorGradient only             (quantizedOrientations) */
 #define LM_STAGE_QUANT_RAW 5 /* u8 [rows][cols], before mask */
+#define LM_STAGE_LINEAR_PACKED 6 /* u8 [8][plane_stride / 2]: the coarsest level's LM_STAGE_LINEAR packed two positions
+                                    per byte (position p = nibble p), the layout k_similarity_coarse_nib reads */
 /* Copies a stage of the LAST lm_match / lm_build_front call to host memory. dst NULL = size query. Returns bytes. */
 long lm_debug_fetch(lm_detector* det, int stage, int level, int modality, void* dst);
 /* Front end only (quantise -> spread -> response -> linearize) without matching. */
@@ -228,9 +230,11 @@ long lm_debug_presort(lm_detector* det, lm_match_rec* dst /*nullable*/);
  * [0] H2D, [1] front end, [2] coarse similarity, [3] local refinement, [4] D2H; and kernel launches it made. */
 int lm_last_timings(const lm_detector* det, float ms[5], int* kernel_launches);
 /* Algorithmic bytes of the last match: [0] B_front [1] B_coarse [2] B_refine [3] B_out,
- * and [4] coarse candidates, [5] template*position evals. */
-int lm_last_work(const lm_detector* det, uint64_t out[6]);
-/* Selects the coarse-similarity kernel variant (0 = default).  For A/B measurements in bench.py only. */
+ * and [4] coarse candidates, [5] template*position evals, [6] the part of B_coarse the coarse kernel actually gathered
+ * (exact early termination skips features of tiles in which no position can reach the threshold any more), [7] 0. */
+int lm_last_work(const lm_detector* det, uint64_t out[8]);
+/* Tuning / A-B switches: "coarse_variant" (0 production, 1 byte planes, 2 nibble planes without tile records),
+ * "prune" (1 = exact early termination in the coarse kernel, default), "frontend_variant", "debug_taps". */
 int lm_set_option(lm_detector* det, const char* key, int value);
 
 #ifdef __cplusplus

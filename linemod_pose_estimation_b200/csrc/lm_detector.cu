@@ -103,14 +103,15 @@ struct Lane {
   DevBuf quantized[LM_MAX_LEVELS][LM_MAX_MODALITIES];
   DevBuf spread[LM_MAX_LEVELS][LM_MAX_MODALITIES], response[LM_MAX_LEVELS][LM_MAX_MODALITIES];  // parity taps only
   DevBuf lmem[LM_MAX_LEVELS];                          // [M][8][plane_stride] + slack
+  DevBuf lmn;                                          // coarsest level again, nibble-packed (two positions per byte)
   // matching
-  DevBuf cand, result, work, work_order, dump;
+  DevBuf cand, result, work, work_order, dump, dbg_recs;
   uint32_t cand_cap = 0, out_cap = 0;
   PinBuf stage_in, stage_out;
   // last-call bookkeeping
   float ms[5] = {0, 0, 0, 0, 0};
   int launches = 0;
-  uint64_t work_stats[6] = {0, 0, 0, 0, 0, 0};
+  uint64_t work_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::vector<lm_match_rec> presort;
 
   int init() {
@@ -127,7 +128,8 @@ struct Lane {
       }
     }
     for (int l = 0; l < LM_MAX_LEVELS; ++l) lmem[l].release();
-    cand.release(); result.release(); work.release(); work_order.release(); dump.release();
+    lmn.release();
+    cand.release(); result.release(); work.release(); work_order.release(); dump.release(); dbg_recs.release();
     stage_in.release(); stage_out.release();
     for (int i = 0; i < 6; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
     if (stream) cudaStreamDestroy(stream);
@@ -137,12 +139,13 @@ struct Lane {
 // Device-resident template records for one frame geometry.
 struct Pack {
   uint64_t version = 0;
-  int rows = 0, cols = 0, shard_rank = 0, shard_world = 1;
+  int rows = 0, cols = 0, shard_rank = 0, shard_world = 1, variant = -1;
   int n = 0;        // templates on this shard
   int max_P = 0;
   DevBuf ctpl, foff;
   DevBuf rtpl[LM_MAX_LEVELS], rfeats[LM_MAX_LEVELS];
   std::vector<CoarseTpl> h_ctpl;
+  std::vector<uint32_t> h_foff;         // host copy of the coarse feature offsets (tile records are built from it)
   std::vector<uint64_t> coarse_bytes;   // per template: in-bounds features x positions (B_coarse)
   uint64_t coarse_bytes_all = 0;
   uint64_t refine_bytes_per_cand = 0;   // approximate (first template); exact per candidate is computed at finalise
@@ -150,10 +153,10 @@ struct Pack {
   struct ClassRange { std::string id; int class_index; std::vector<uint32_t> local; std::vector<uint32_t> global_pos; };
   std::vector<ClassRange> classes;      // canonical order
   // Device-side description of one (multi-query) request: work items and coarse tiles.  Cached by the class lists.
-  struct Plan { DevBuf items, tiles; int n_items = 0, n_tiles = 0; uint64_t coarse_bytes = 0, evals = 0; double refine_nf_sum = 0; };
+  struct Plan { DevBuf items, tiles, recs; int n_items = 0, n_tiles = 0, rec_words = 0; uint64_t coarse_bytes = 0, evals = 0; double refine_nf_sum = 0; };
   std::map<std::string, Plan> plans;
   void clear_filtered() {
-    for (auto& kv : plans) { kv.second.items.release(); kv.second.tiles.release(); }
+    for (auto& kv : plans) { kv.second.items.release(); kv.second.tiles.release(); kv.second.recs.release(); }
     plans.clear();
   }
   void release() {
@@ -174,7 +177,7 @@ struct lm_detector {
   Lane lane[2];
   Pack pack;
   int shard_rank = 0, shard_world = 1;
-  int debug_taps = 0, coarse_variant = 0, timing = 1, frontend_variant = 0;
+  int debug_taps = 0, coarse_variant = 0, timing = 1, frontend_variant = 0, prune = 1;
   std::vector<std::string> class_id_cache;
 };
 
@@ -272,6 +275,11 @@ static int ensure_lm_ws(lm_detector* d, Lane& ln, int rows, int cols) {
     size_t bytes = (size_t)M * 8 * geom[l].plane_stride + kLmSlack;
     if (ln.lmem[l].ensure(bytes) != LM_OK) return LM_E_CUDA;
     CU(cudaMemsetAsync(ln.lmem[l].p, 0, ln.lmem[l].cap, ln.stream));  // zero tails (and slack) once per geometry
+  }
+  {
+    size_t bytes = ((size_t)M * 8 * geom[L - 1].plane_stride + kLmSlack) / 2;
+    if (ln.lmn.ensure(bytes) != LM_OK) return LM_E_CUDA;
+    CU(cudaMemsetAsync(ln.lmn.p, 0, ln.lmn.cap, ln.stream));
   }
   ln.geom.swap(geom);
   ln.lm_ready = true;
@@ -481,6 +489,11 @@ static int run_front(lm_detector* d, Lane& ln, cudaStream_t s) {
     if (!launch_spread_all(sp, total, max_T, s)) return fail(LM_E_INVALID, "T=%d needs too much shared memory", max_T);
     ++ln.launches;
   }
+  {  // nibble-packed copy of the coarsest level for k_similarity_coarse_nib
+    const LevelGeom& gc = ln.geom[L - 1];
+    launch_pack_nibbles(ln.lmem[L - 1].as<uint8_t>(), ln.lmn.as<uint8_t>(), (size_t)M * 8 * gc.plane_stride, s);
+    ++ln.launches;
+  }
   CU(cudaGetLastError());
   ln.front_valid = true;
   ln.debug_taps_written = taps;
@@ -492,7 +505,7 @@ static int ensure_pack(lm_detector* d, const Lane& ln) {
   Pack& pk = d->pack;
   const HostModel& md = d->model;
   if (pk.version == md.version && pk.rows == ln.rows && pk.cols == ln.cols && pk.shard_rank == d->shard_rank &&
-      pk.shard_world == d->shard_world)
+      pk.shard_world == d->shard_world && pk.variant == d->coarse_variant)
     return LM_OK;
   // all lanes must be idle before the shared records are replaced
   for (int i = 0; i < 2; ++i)
@@ -540,7 +553,10 @@ static int ensure_pack(lm_detector* d, const Lane& ln) {
           if (f.x < 0 || f.x >= gc.cols || f.y < 0 || f.y >= gc.rows) continue;  // "Discard feature if out of bounds"
           size_t a = (size_t)m * 8 * gc.plane_stride + (size_t)f.label * gc.plane_stride +
                      (size_t)((f.y % gc.T) * gc.T + (f.x % gc.T)) * ((size_t)gc.W * gc.H) + (size_t)(f.y / gc.T) * gc.W + f.x / gc.T;
-          grp[(a & 15) >> 2].push_back((uint32_t)a);
+          // window-alignment class of the feature (a compile-time constant in the kernels): byte planes -> word
+          // offset in the 16-byte chunk; nibble planes -> the same with a = nibble index
+          const int q = d->coarse_variant == 1 ? (int)((a & 15) >> 2) : (int)((a >> 3) & 3);
+          grp[q].push_back((uint32_t)a);
         }
         for (int q = 0; q < 4; ++q) {
           ct.cnt[m][q] = (uint8_t)grp[q].size();
@@ -589,8 +605,9 @@ static int ensure_pack(lm_detector* d, const Lane& ln) {
     if (up(pk.rfeats[l], rfeats[l].data(), rfeats[l].size() * 4) != LM_OK) return LM_E_CUDA;
   }
   pk.h_ctpl.swap(ctpl);
+  pk.h_foff.swap(foff);
   pk.version = md.version; pk.rows = ln.rows; pk.cols = ln.cols;
-  pk.shard_rank = d->shard_rank; pk.shard_world = d->shard_world;
+  pk.shard_rank = d->shard_rank; pk.shard_world = d->shard_world; pk.variant = d->coarse_variant;
   return LM_OK;
 }
 
@@ -603,6 +620,42 @@ struct Query {
 
 static const size_t kFirstChunkRecords = 1024;  // records fetched together with the header in one D2H copy
 static const int kMaxQueries = LM_MAX_QUERIES;  // (class list, threshold) queries answered from one front end
+
+// Self-contained tile records of the production coarse kernel (layout: lm_kernels.cuh).
+static int build_tile_records(const Pack& pk, const std::vector<WorkItem>& items, const std::vector<uint2>& tiles,
+                              int pass_pos, int M, std::vector<uint32_t>& recs, int* rec_words) {
+  const int hdr = coarse_record_header_words();
+  int max_feat = 0;
+  for (const WorkItem& it : items) {
+    const CoarseTpl& ct = pk.h_ctpl[it.tglob];
+    int n = 0;
+    for (int m = 0; m < M; ++m) for (int g = 0; g < 4; ++g) n += ct.cnt[m][g];
+    max_feat = std::max(max_feat, n);
+  }
+  const int words = (hdr + max_feat + 3) & ~3;
+  if (words > coarse_record_max_words()) return fail(LM_E_INVALID, "template with too many features for a tile record");
+  *rec_words = words;
+  recs.assign((size_t)words * tiles.size(), 0u);
+  for (size_t t = 0; t < tiles.size(); ++t) {
+    uint32_t* r = &recs[t * (size_t)words];
+    const WorkItem& it = items[tiles[t].x];
+    const CoarseTpl& ct = pk.h_ctpl[it.tglob];
+    const int j0 = (int)tiles[t].y * pass_pos;
+    int n = 0;
+    for (int m = 0; m < M; ++m) {
+      uint32_t c4 = 0;
+      for (int g = 0; g < 4; ++g) { c4 |= (uint32_t)ct.cnt[m][g] << (8 * g); n += ct.cnt[m][g]; }
+      r[8 + m] = c4;
+    }
+    r[0] = tiles[t].x; r[1] = it.tglob; r[2] = (ct.nf & 0x0fffffffu) | (it.order & 0xf0000000u); r[3] = (uint32_t)n;
+    r[4] = (uint32_t)j0; r[5] = (uint32_t)std::min(pass_pos, ct.P - j0);
+    for (int f = 0; f < n; ++f) {
+      const uint32_t a = pk.h_foff[ct.feat_begin + f] + (uint32_t)j0;  // nibble index of lane 0's window
+      r[hdr + f] = ((a >> 1) & ~15u) | (a & 7u);
+    }
+  }
+  return LM_OK;
+}
 
 // [OCV] Detector::match: "if (class_ids.empty()) match all templates else only the requested class IDs" (in the
 // order requested, unknown ids skipped) -- for every query of the request.  The plan lists the work items (template
@@ -625,7 +678,7 @@ static int get_plan(lm_detector* d, const Query* qs, int n_q, Pack::Plan** out) 
   struct Tile { uint2 t; uint64_t cost; };
   std::vector<Tile> tiles;
   Pack::Plan plan;
-  const int pass_pos = coarse_positions_per_pass();
+  const int pass_pos = coarse_positions_per_pass(d->coarse_variant);
   auto add_class = [&](const Pack::ClassRange& cr, uint32_t base, uint32_t first_global, int q) {
     for (size_t k = 0; k < cr.local.size(); ++k) {
       const uint32_t local = cr.local[k];
@@ -669,8 +722,16 @@ static int get_plan(lm_detector* d, const Query* qs, int n_q, Pack::Plan** out) 
   plan.n_items = (int)items.size();
   plan.n_tiles = (int)tl.size();
   plan.evals = (uint64_t)items.size();
+  std::vector<uint32_t> recs;
+  if (d->coarse_variant == 0) {
+    if (build_tile_records(pk, items, tl, pass_pos, d->model.M(), recs, &plan.rec_words) != LM_OK) return LM_E_INVALID;
+  }
   Pack::Plan& dst = pk.plans[key];
   dst = plan;
+  if (!recs.empty()) {
+    if (dst.recs.ensure(recs.size() * 4 + 64) != LM_OK) return LM_E_CUDA;
+    CU(cudaMemcpy(dst.recs.p, recs.data(), recs.size() * 4, cudaMemcpyHostToDevice));
+  }
   if (dst.items.ensure(items.size() * sizeof(WorkItem) + 64) != LM_OK || dst.tiles.ensure(tl.size() * sizeof(uint2) + 64) != LM_OK) return LM_E_CUDA;
   if (!items.empty()) CU(cudaMemcpy(dst.items.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
   if (!tl.empty()) CU(cudaMemcpy(dst.tiles.p, tl.data(), tl.size() * sizeof(uint2), cudaMemcpyHostToDevice));
@@ -678,7 +739,15 @@ static int get_plan(lm_detector* d, const Query* qs, int n_q, Pack::Plan** out) 
   return LM_OK;
 }
 
+// Device pointer of the plan's tile records (variant 0) or null.
+static const uint32_t* plan_recs(const Pack::Plan& plan) { return plan.recs.as<uint32_t>(); }
+
+// Result block in device memory: [16 B kernel statistics][ResultHeader][out_cap x lm_raw_match].  The statistics
+// (u64 (feature, position) pairs the coarse kernel gathered) sit in front so that one memset clears both and one D2H
+// copy brings both; the public block (lm_match_device) starts at the header.
+static const size_t kStatsBytes = 16;
 static size_t result_bytes(const Lane& ln) { return sizeof(ResultHeader) + (size_t)ln.out_cap * sizeof(lm_raw_match); }
+static uint8_t* block_ptr(const Lane& ln) { return ln.result.as<uint8_t>() + kStatsBytes; }
 
 static int ensure_match_buffers(Lane& ln, uint32_t cand_cap, uint32_t out_cap) {
   if (cand_cap > ln.cand_cap) {
@@ -686,8 +755,8 @@ static int ensure_match_buffers(Lane& ln, uint32_t cand_cap, uint32_t out_cap) {
     ln.cand_cap = cand_cap;
   }
   if (out_cap > ln.out_cap) ln.out_cap = out_cap;
-  if (ln.result.ensure(result_bytes(ln)) != LM_OK) return LM_E_CUDA;
-  if (ln.stage_out.ensure(result_bytes(ln)) != LM_OK) return LM_E_CUDA;
+  if (ln.result.ensure(kStatsBytes + result_bytes(ln)) != LM_OK) return LM_E_CUDA;
+  if (ln.stage_out.ensure(kStatsBytes + result_bytes(ln)) != LM_OK) return LM_E_CUDA;
   return LM_OK;
 }
 
@@ -698,16 +767,17 @@ static int enqueue_match(lm_detector* d, Lane& ln, const Pack::Plan& plan, const
   const int L = md.levels(), M = md.M();
   Pack& pk = d->pack;
   const LevelGeom& gc = ln.geom[L - 1];
-  ResultHeader* d_hdr = ln.result.as<ResultHeader>();
-  lm_raw_match* d_out = reinterpret_cast<lm_raw_match*>(ln.result.as<uint8_t>() + sizeof(ResultHeader));
-  CU(cudaMemsetAsync(d_hdr, 0, sizeof(ResultHeader), s));
+  ResultHeader* d_hdr = reinterpret_cast<ResultHeader*>(block_ptr(ln));
+  lm_raw_match* d_out = reinterpret_cast<lm_raw_match*>(block_ptr(ln) + sizeof(ResultHeader));
+  CU(cudaMemsetAsync(ln.result.p, 0, kStatsBytes + sizeof(ResultHeader), s));
   QueryThresholds qt;
   RefineParams rp;
   std::memset(&rp, 0, sizeof(rp));
   std::memset(&qt, 0, sizeof(qt));
   for (int q = 0; q < n_q; ++q) { qt.v[q] = qs[q].threshold; rp.threshold[q] = qs[q].threshold; }
-  launch_similarity_coarse(ln.lmem[L - 1].as<uint8_t>(), pk.foff.as<uint32_t>(), pk.ctpl.as<CoarseTpl>(),
-                           plan.items.as<WorkItem>(), plan.tiles.as<uint2>(), plan.n_tiles, qt, M, ln.cand.as<Cand>(), d_hdr,
+  launch_similarity_coarse(d->coarse_variant, ln.lmem[L - 1].as<uint8_t>(), ln.lmn.as<uint8_t>(), pk.foff.as<uint32_t>(),
+                           pk.ctpl.as<CoarseTpl>(), plan.items.as<WorkItem>(), plan.tiles.as<uint2>(), plan_recs(plan), plan.rec_words,
+                           plan.n_tiles, qt, M, d->prune, ln.cand.as<Cand>(), d_hdr, ln.result.as<unsigned long long>(),
                            ln.cand_cap, nullptr, 0, s);
   if (plan.n_tiles > 0) ++ln.launches;
   if (ev_mid) CU(cudaEventRecord(ev_mid, s));
@@ -763,16 +833,18 @@ static void finalize_records(int levels, std::vector<lm_raw_match>& raw, std::ve
 static int download_records(Lane& ln, cudaStream_t s, std::vector<lm_raw_match>& raw, bool* overflow, uint32_t* n_cands) {
   const size_t first = std::min<size_t>(kFirstChunkRecords, ln.out_cap);
   uint8_t* host = ln.stage_out.as<uint8_t>();
-  CU(cudaMemcpyAsync(host, ln.result.p, sizeof(ResultHeader) + first * sizeof(lm_raw_match), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(host, ln.result.p, kStatsBytes + sizeof(ResultHeader) + first * sizeof(lm_raw_match), cudaMemcpyDeviceToHost, s));
   CU(cudaEventRecord(ln.ev[5], s));
   CU(cudaStreamSynchronize(s));
+  ln.work_stats[6] = *reinterpret_cast<const unsigned long long*>(host);
+  host += kStatsBytes;
   ResultHeader h = *reinterpret_cast<ResultHeader*>(host);
   *overflow = h.overflow != 0 || h.count > ln.out_cap;
   *n_cands = h.n_cands;
   if (*overflow) return LM_OK;
   if (h.count > first) {
     CU(cudaMemcpyAsync(host + sizeof(ResultHeader) + first * sizeof(lm_raw_match),
-                       ln.result.as<uint8_t>() + sizeof(ResultHeader) + first * sizeof(lm_raw_match),
+                       block_ptr(ln) + sizeof(ResultHeader) + first * sizeof(lm_raw_match),
                        (h.count - first) * sizeof(lm_raw_match), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
   }
@@ -825,6 +897,7 @@ static int match_front(lm_detector* d, Lane& ln, const Query* queries, int n_q, 
   }
   // work accounting: B_coarse from the plan; B_refine = candidates x mean refine features x 256 bytes
   ln.work_stats[1] = plan->coarse_bytes;
+  if (d->coarse_variant != 0) ln.work_stats[6] = plan->coarse_bytes;  // the A/B kernels always gather everything
   ln.work_stats[4] = n_cands;
   ln.work_stats[5] = (uint64_t)plan->n_items * (uint64_t)(ln.geom.back().W * ln.geom.back().H);
   ln.work_stats[2] = plan->n_items ? (uint64_t)((double)n_cands * (plan->refine_nf_sum / plan->n_items) * 256.0) : 0;
@@ -1175,6 +1248,7 @@ int lm_set_option(lm_detector* d, const char* key, int value) {
   if (k == "debug_taps") d->debug_taps = value;
   else if (k == "coarse_variant") d->coarse_variant = value;
   else if (k == "timing") d->timing = value;
+  else if (k == "prune") d->prune = value;
   else if (k == "frontend_variant") { d->frontend_variant = value; for (int i = 0; i < 2; ++i) d->lane[i].front_valid = false; }
   else return fail(LM_E_INVALID, "unknown option '%s'", key);
   return LM_OK;
@@ -1342,7 +1416,7 @@ int lm_match_device_multi(lm_detector* d, const void* const* d_sources, int n_so
   if (rc != LM_OK) return rc;
   if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 18), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
   if (enqueue_match(d, ln, *plan, qs, n_queries, s, nullptr) != LM_OK) return LM_E_CUDA;
-  *d_records = ln.result.p;
+  *d_records = block_ptr(ln);
   if (record_bytes_capacity) *record_bytes_capacity = result_bytes(ln);
   return LM_OK;
 }
@@ -1394,6 +1468,9 @@ long lm_debug_fetch(lm_detector* d, int stage, int level, int modality, void* ds
       bytes = stage == LM_STAGE_SPREAD ? n : 8 * n; break;
     case LM_STAGE_LINEAR:
       src = ln.lmem[level].as<uint8_t>() + (size_t)modality * 8 * g.plane_stride; bytes = 8 * g.plane_stride; break;
+    case LM_STAGE_LINEAR_PACKED:
+      if (level != d->model.levels() - 1) return fail(LM_E_INVALID, "only the coarsest level has a packed copy");
+      src = ln.lmn.as<uint8_t>() + (size_t)modality * 4 * g.plane_stride; bytes = 4 * g.plane_stride; break;
     default: return fail(LM_E_INVALID, "unknown stage %d", stage);
   }
   if (dst) {
@@ -1419,7 +1496,7 @@ int lm_debug_coarse_map(lm_detector* d, const char* class_id, int template_id, u
   const LevelGeom& gc = ln.geom.back();
   const int WH = gc.W * gc.H;
   if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
-  const int pass_pos = coarse_positions_per_pass();
+  const int pass_pos = coarse_positions_per_pass(d->coarse_variant);
   const int P = pk.h_ctpl[local].P;
   std::vector<uint2> tl;
   for (int pass = 0; pass * pass_pos < P; ++pass) tl.push_back(make_uint2(0u, (uint32_t)pass));
@@ -1428,13 +1505,23 @@ int lm_debug_coarse_map(lm_detector* d, const char* class_id, int template_id, u
   CU(cudaMemsetAsync(ln.dump.p, 0, (size_t)WH * 2, ln.stream));
   CU(cudaMemcpyAsync(ln.work.p, &it, sizeof(it), cudaMemcpyHostToDevice, ln.stream));
   if (!tl.empty()) CU(cudaMemcpyAsync(ln.work_order.p, tl.data(), tl.size() * sizeof(uint2), cudaMemcpyHostToDevice, ln.stream));
-  CU(cudaMemsetAsync(ln.result.p, 0, sizeof(ResultHeader), ln.stream));
+  CU(cudaMemsetAsync(ln.result.p, 0, kStatsBytes + sizeof(ResultHeader), ln.stream));
+  std::vector<uint32_t> recs;
+  int rec_words = 0;
+  if (d->coarse_variant == 0) {
+    std::vector<WorkItem> one(1, it);
+    if (build_tile_records(pk, one, tl, pass_pos, d->model.M(), recs, &rec_words) != LM_OK) return LM_E_INVALID;
+    if (ln.dbg_recs.ensure(recs.size() * 4 + 64) != LM_OK) return LM_E_CUDA;
+    if (!recs.empty()) CU(cudaMemcpyAsync(ln.dbg_recs.p, recs.data(), recs.size() * 4, cudaMemcpyHostToDevice, ln.stream));
+  }
   // threshold 1e30 -> raw threshold saturates: nothing becomes a candidate, the kernel only dumps its accumulators
   QueryThresholds qt;
   for (int q = 0; q < LM_MAX_QUERIES; ++q) qt.v[q] = 1e30f;
-  launch_similarity_coarse(ln.lmem[d->model.levels() - 1].as<uint8_t>(), pk.foff.as<uint32_t>(), pk.ctpl.as<CoarseTpl>(),
-                           ln.work.as<WorkItem>(), ln.work_order.as<uint2>(), (int)tl.size(), qt, d->model.M(),
-                           ln.cand.as<Cand>(), ln.result.as<ResultHeader>(), 0, ln.dump.as<uint16_t>(), WH, ln.stream);
+  launch_similarity_coarse(d->coarse_variant, ln.lmem[d->model.levels() - 1].as<uint8_t>(), ln.lmn.as<uint8_t>(),
+                           pk.foff.as<uint32_t>(), pk.ctpl.as<CoarseTpl>(),
+                           ln.work.as<WorkItem>(), ln.work_order.as<uint2>(), ln.dbg_recs.as<uint32_t>(), rec_words,
+                           (int)tl.size(), qt, d->model.M(),
+                           0, ln.cand.as<Cand>(), reinterpret_cast<ResultHeader*>(block_ptr(ln)), nullptr, 0, ln.dump.as<uint16_t>(), WH, ln.stream);
   CU(cudaMemcpyAsync(dst, ln.dump.p, (size_t)WH * 2, cudaMemcpyDeviceToHost, ln.stream));
   CU(cudaStreamSynchronize(ln.stream));
   return LM_OK;
@@ -1452,8 +1539,8 @@ int lm_last_timings(const lm_detector* d, float ms[5], int* kernel_launches) {
   if (kernel_launches) *kernel_launches = ln.launches;
   return LM_OK;
 }
-int lm_last_work(const lm_detector* d, uint64_t out[6]) {
-  for (int i = 0; i < 6; ++i) out[i] = d->lane[0].work_stats[i];
+int lm_last_work(const lm_detector* d, uint64_t out[8]) {
+  for (int i = 0; i < 8; ++i) out[i] = d->lane[0].work_stats[i];
   return LM_OK;
 }
 

@@ -125,10 +125,26 @@ bool launch_spread_all(const SpreadParams& p, int total_blocks, int max_T, cudaS
 // ------------------------------------------------------------------------------------------------ matching
 // tiles: (work item, pass) pairs with at least one position, heaviest first.  dump (nullable): u16 totals,
 // [work item][dump_stride], written for every scored position (parity tap).
-int coarse_positions_per_pass();
-void launch_similarity_coarse(const uint8_t* lmc, const uint32_t* foff, const CoarseTpl* tpl, const WorkItem* items,
-                              const uint2* tiles, int n_tiles, const QueryThresholds& thr, int M, Cand* cand,
-                              ResultHeader* hdr, uint32_t cand_cap, uint16_t* dump, int dump_stride, cudaStream_t s);
+// variant: 0 = nibble-packed linear memories, self-contained tile records, exact early termination (production;
+// prune = 0 switches the early termination off, `touched` (nullable) accumulates the (feature, position) pairs gathered); 2 = nibble-packed, two overlapping vector loads per feature; 1 = byte linear memories.  2 and 1 are the
+// A/B references and read the (items, tiles, tpl, foff) arrays; 0 reads `recs`.
+// lmc: byte planes, lmn: nibble-packed planes of the coarsest level.
+//
+// Tile record of variant 0 (rec_words 32-bit words each, 16-byte aligned):
+//   [0] work item  [1] template index in the pack  [2] nf | query << 28  [3] number of feature words
+//   [4] j0 = first position of the pass  [5] positions in the pass  [6..7] 0  [8..11] per modality: 4 class sizes, u8 each
+//   [12..] feature words, modality-major, grouped by class Q = (a >> 3) & 3 where a = nibble index of the window of
+//   lane 0: ((a >> 1) & ~15) | (a & 7)  -- aligned chunk byte offset | nibble shift
+int coarse_positions_per_pass(int variant);
+int coarse_record_header_words();
+int coarse_record_max_words();
+void launch_similarity_coarse(int variant, const uint8_t* lmc, const uint8_t* lmn, const uint32_t* foff,
+                              const CoarseTpl* tpl, const WorkItem* items, const uint2* tiles, const uint32_t* recs,
+                              int rec_words, int n_tiles, const QueryThresholds& thr, int M, int prune, Cand* cand,
+                              ResultHeader* hdr, unsigned long long* touched, uint32_t cand_cap, uint16_t* dump,
+                              int dump_stride, cudaStream_t s);
+// n_bytes (multiple of 16) of byte planes -> n_bytes / 2 of nibble-packed planes
+void launch_pack_nibbles(const uint8_t* lm_bytes, uint8_t* lm_nibbles, size_t n_bytes, cudaStream_t s);
 void launch_refine(const RefineParams& p, const CoarseTpl* ctpl, const WorkItem* items, const Cand* cand,
                    uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* out, uint32_t out_cap, cudaStream_t s);
 

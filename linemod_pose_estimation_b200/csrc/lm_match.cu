@@ -152,6 +152,428 @@ __global__ void __launch_bounds__(256) k_similarity_coarse(const uint8_t* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------ nibble-packed coarse
+// Production coarse kernel.  Responses are <= 4, so the coarsest level's linear memories are also kept packed two
+// positions per byte (k_pack_nibbles): position p of the reference's flat byte plane is nibble p.  That halves the
+// bytes every window load moves through L1/L2.  Up to three features are summed in the nibble domain (3 x 4 = 12 < 16:
+// no carry between positions) before the even / odd nibbles are spread into the u8 accumulators the reference uses, so
+// the sums are bit-identical to _mm_add_epi8 over bytes.
+//
+// A lane owns 8*WORDS consecutive positions = one aligned (4*WORDS)-byte window per feature plus the Q+1 following
+// words; the window is realigned with one funnel shift per word (nibble granularity).  Q = word offset of the window
+// inside its aligned chunk is the packer's feature grouping, hence a compile-time constant.  The feature offsets of the
+// warp's template are staged in shared memory first, so the window loads of consecutive features do not wait on a
+// dependent global load and six features (twelve loads) are in flight per lane.
+template <int WORDS>
+struct Nib {
+  static constexpr int kLanePos = 8 * WORDS;
+  static constexpr int kWarpPos = 32 * kLanePos;
+};
+
+template <int WORDS, int Q>
+__device__ __forceinline__ void nib_window(const uint8_t* __restrict__ lmn, uint32_t a, uint32_t (&n)[WORDS]) {
+  const uint8_t* p = lmn + ((a >> 1) & ~(uint32_t)(4 * WORDS - 1));
+  const uint32_t sh = (a & 7u) * 4u;
+  uint32_t w[2 * WORDS];
+  if (WORDS == 4) {
+    const uint4 v = ldg128(p);
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    if (Q == 0) {
+      w[4] = ldg32(p + 16);
+    } else if (Q == 1) {
+      const uint2 e = ldg64(p + 16);
+      w[4] = e.x; w[5] = e.y;
+    } else {
+      const uint4 e = ldg128(p + 16);
+      w[4] = e.x; w[5] = e.y; w[6] = e.z; w[7] = e.w;
+    }
+  } else {
+    const uint2 v = ldg64(p);
+    w[0] = v.x; w[1] = v.y;
+    if (Q == 0) {
+      w[2] = ldg32(p + 8);
+    } else {
+      const uint2 e = ldg64(p + 8);
+      w[2] = e.x; w[3] = e.y;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < WORDS; ++k) n[k] = __funnelshift_r(w[Q + k], w[Q + k + 1], sh);
+}
+
+template <int WORDS>
+__device__ __forceinline__ void nib_flush(const uint32_t (&nib)[WORDS], uint32_t (&acc_e)[WORDS], uint32_t (&acc_o)[WORDS]) {
+#pragma unroll
+  for (int k = 0; k < WORDS; ++k) {
+    acc_e[k] += nib[k] & 0x0f0f0f0fu;
+    acc_o[k] += (nib[k] >> 4) & 0x0f0f0f0fu;
+  }
+}
+
+template <int WORDS, int Q>
+__device__ __forceinline__ void nib_group(const uint8_t* __restrict__ lmn, const uint32_t* so, int n, uint32_t lane_off,
+                                          uint32_t (&acc_e)[WORDS], uint32_t (&acc_o)[WORDS]) {
+  int f = 0;
+  for (; f + 6 <= n; f += 6) {
+    uint32_t a[6][WORDS];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) nib_window<WORDS, Q>(lmn, so[f + i] + lane_off, a[i]);
+    uint32_t s0[WORDS], s1[WORDS];
+#pragma unroll
+    for (int k = 0; k < WORDS; ++k) { s0[k] = a[0][k] + a[1][k] + a[2][k]; s1[k] = a[3][k] + a[4][k] + a[5][k]; }
+    nib_flush<WORDS>(s0, acc_e, acc_o);
+    nib_flush<WORDS>(s1, acc_e, acc_o);
+  }
+  if (f + 3 <= n) {
+    uint32_t a[3][WORDS];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) nib_window<WORDS, Q>(lmn, so[f + i] + lane_off, a[i]);
+    uint32_t s0[WORDS];
+#pragma unroll
+    for (int k = 0; k < WORDS; ++k) s0[k] = a[0][k] + a[1][k] + a[2][k];
+    nib_flush<WORDS>(s0, acc_e, acc_o);
+    f += 3;
+  }
+  if (f < n) {  // one or two left
+    uint32_t a0[WORDS], a1[WORDS];
+    nib_window<WORDS, Q>(lmn, so[f] + lane_off, a0);
+    if (f + 1 < n) {
+      nib_window<WORDS, Q>(lmn, so[f + 1] + lane_off, a1);
+#pragma unroll
+      for (int k = 0; k < WORDS; ++k) a0[k] += a1[k];
+    }
+    nib_flush<WORDS>(a0, acc_e, acc_o);
+  }
+}
+
+constexpr int kMaxTplFeatures = LM_MAX_MODALITIES * 64;
+
+template <int WORDS>
+__global__ void __launch_bounds__(256) k_similarity_coarse_nib(const uint8_t* __restrict__ lmn,
+                                                               const uint32_t* __restrict__ foff,
+                                                               const CoarseTpl* __restrict__ tpl,
+                                                               const WorkItem* __restrict__ items,
+                                                               const uint2* __restrict__ tiles, int n_tiles,
+                                                               const QueryThresholds thr_q, int M,
+                                                               Cand* __restrict__ cand, ResultHeader* hdr,
+                                                               uint32_t cand_cap, uint16_t* __restrict__ dump,
+                                                               int dump_stride) {
+  constexpr int kLanePos = Nib<WORDS>::kLanePos, kWarpPos = Nib<WORDS>::kWarpPos;
+  __shared__ uint32_t s_off[8][kMaxTplFeatures];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* so = s_off[warp];
+  for (;;) {
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(&hdr->next_tile, 1u);
+    tile = __shfl_sync(kFull, tile, 0);
+    if (tile >= (uint32_t)n_tiles) break;
+    const uint2 tl = tiles[tile];
+    const uint32_t item = tl.x;
+    const int j0 = (int)tl.y * kWarpPos;
+    const WorkItem wi = items[item];
+    const uint32_t tg = wi.tglob;
+    const CoarseTpl* __restrict__ ct = tpl + tg;
+    // stage this template's feature offsets (all modalities, grouped by Q) in shared memory
+    int n_feat = 0;
+    for (int m = 0; m < M; ++m) n_feat += __dp4a(__ldg(reinterpret_cast<const uint32_t*>(ct->cnt) + m), 0x01010101u, 0u);
+    const uint32_t feat_begin = ct->feat_begin;
+    __syncwarp();
+    for (int i = lane; i < n_feat; i += 32) so[i] = __ldg(foff + feat_begin + i);
+    __syncwarp();
+    const int rem = min(ct->P - j0, kWarpPos);  // positions of this pass (> 0 by construction of the tile list)
+    const int first = lane * kLanePos;           // first position of this lane within the pass
+    if (first < rem) {
+      const uint32_t lane_off = (uint32_t)(j0 + first);
+      uint32_t tot[WORDS][4];  // u16 x 2 per register: [k][r], r = (i & 1) * 2 + ((i >> 1) & 1) for position 8k + i
+#pragma unroll
+      for (int k = 0; k < WORDS; ++k) tot[k][0] = tot[k][1] = tot[k][2] = tot[k][3] = 0;
+      const uint32_t* fp = so;
+      for (int m = 0; m < M; ++m) {
+        uint32_t acc_e[WORDS], acc_o[WORDS];
+#pragma unroll
+        for (int k = 0; k < WORDS; ++k) acc_e[k] = acc_o[k] = 0;
+        const uint32_t c4 = __ldg(reinterpret_cast<const uint32_t*>(ct->cnt) + m);  // 4 group sizes, one word
+        const int n0 = c4 & 255, n1 = (c4 >> 8) & 255, n2 = (c4 >> 16) & 255, n3 = c4 >> 24;
+        nib_group<WORDS, 0>(lmn, fp, n0, lane_off, acc_e, acc_o); fp += n0;
+        nib_group<WORDS, 1>(lmn, fp, n1, lane_off, acc_e, acc_o); fp += n1;
+        if (WORDS == 4) {
+          nib_group<WORDS, (WORDS == 4 ? 2 : 0)>(lmn, fp, n2, lane_off, acc_e, acc_o); fp += n2;
+          nib_group<WORDS, (WORDS == 4 ? 3 : 1)>(lmn, fp, n3, lane_off, acc_e, acc_o); fp += n3;
+        }
+#pragma unroll
+        for (int k = 0; k < WORDS; ++k) {  // [OCV] addSimilarities: widen u8 -> u16 and add the modality
+          tot[k][0] += acc_e[k] & 0x00ff00ffu;
+          tot[k][1] += (acc_e[k] >> 8) & 0x00ff00ffu;
+          tot[k][2] += acc_o[k] & 0x00ff00ffu;
+          tot[k][3] += (acc_o[k] >> 8) & 0x00ff00ffu;
+        }
+      }
+      // [OCV] matchClass: raw_threshold = (int)(2*nf + (threshold / 100.f) * (2*nf) + 0.5f), same f32 roundings
+      const float threshold = thr_q.v[wi.order >> 28];
+      const float two_nf = (float)(2 * (int)ct->nf);
+      const int thr = __float2int_rz(__fadd_rn(__fadd_rn(two_nf, __fmul_rn(__fdiv_rn(threshold, 100.f), two_nf)), 0.5f));
+      bool hit = thr < 0;
+      if (!hit) {
+        const uint32_t thr2 = (uint32_t)min(thr, 0xffff) * 0x00010001u;
+        uint32_t any = 0;
+#pragma unroll
+        for (int k = 0; k < WORDS; ++k)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) any |= __vcmpgtu2(tot[k][r], thr2);
+        hit = any != 0;
+      }
+      if (dump != nullptr || hit) {  // rare: [OCV] matchClass raster scan, "raw_score > raw_threshold"
+#pragma unroll
+        for (int k = 0; k < WORDS; ++k)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int p = first + 8 * k + i;
+            const uint32_t src = tot[k][(i & 1) * 2 + ((i >> 1) & 1)];
+            const int raw = (int)((i & 4) ? (src >> 16) : (src & 0xffffu));
+            if (p < rem) {
+              if (dump != nullptr) dump[(size_t)item * dump_stride + j0 + p] = (uint16_t)raw;
+              if (raw > thr) {
+                uint32_t idx = atomicAdd(&hdr->n_cands, 1u);
+                if (idx < cand_cap) {
+                  Cand c;
+                  c.tglob = tg; c.pos = (uint32_t)(j0 + p); c.raw = (uint32_t)raw; c.item = item;
+                  cand[idx] = c;
+                }
+              }
+            }
+          }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ production coarse
+// k_similarity_coarse_rec: nibble-packed linear memories + self-contained tile records + exact early termination.
+//
+//  * The host plan stores one record per (template, 1024-position pass) tile: a 48-byte header followed by the feature
+//    words (aligned chunk byte offset of lane 0's window | nibble shift).  A warp prefetches the record of its next tile
+//    (and draws the one after from the dispenser) while it scores the current one, so the tile bookkeeping adds no
+//    dependent global-load latency between tiles.
+//  * Early termination ([OCV] matchClass keeps a position only if raw > raw_threshold): a response is at most 4, so
+//    after `done` of the tile's n features a position can still pass only if partial + 4 * (n - done) > raw_threshold.
+//    The warp stops as soon as none of its 1024 positions can.  Tiles that survive are summed to the end, so every
+//    reported raw score is the complete sum: the candidate list is bit-identical to the exhaustive scan.  At the
+//    reference's thresholds (92 / 94) nearly every tile stops after the first quarter of its features.
+//    Disabled (prune = 0) for the parity tap, which wants every position's full sum.
+constexpr int kRecHdrWords = 12;                      // TileRec header, see lm_kernels.cuh
+constexpr int kRecMaxWords = kRecHdrWords + 256;      // header + LM_MAX_MODALITIES * 64 feature words
+constexpr int kRecPre = (kRecMaxWords + 31) / 32;     // registers per lane holding a prefetched record
+constexpr int kRecWarpPos = 32 * 32;
+
+template <int Q>
+__device__ __forceinline__ void rec_window(const uint8_t* __restrict__ lmn, uint32_t v, uint32_t lane_byte,
+                                           uint32_t (&n)[4]) {
+  const uint8_t* p = lmn + (v & ~15u) + lane_byte;
+  const uint32_t sh = v << 2;  // funnel shifts use the low five bits: 4 * (v & 7)
+  uint32_t w[8];
+  const uint4 c = ldg128(p);
+  w[0] = c.x; w[1] = c.y; w[2] = c.z; w[3] = c.w;
+  if (Q == 0) {
+    w[4] = ldg32(p + 16);
+  } else if (Q == 1) {
+    const uint2 e = ldg64(p + 16);
+    w[4] = e.x; w[5] = e.y;
+  } else {
+    const uint4 e = ldg128(p + 16);
+    w[4] = e.x; w[5] = e.y; w[6] = e.z; w[7] = e.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) n[k] = __funnelshift_r(w[Q + k], w[Q + k + 1], sh);
+}
+
+template <int Q>
+__device__ __forceinline__ void rec_group(const uint8_t* __restrict__ lmn, const uint32_t* fw, int n, uint32_t lane_byte,
+                                          uint32_t (&acc_e)[4], uint32_t (&acc_o)[4]) {
+  int f = 0;
+  for (; f + 6 <= n; f += 6) {
+    uint32_t a[6][4];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) rec_window<Q>(lmn, fw[f + i], lane_byte, a[i]);
+    uint32_t s0[4], s1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s0[k] = a[0][k] + a[1][k] + a[2][k]; s1[k] = a[3][k] + a[4][k] + a[5][k]; }
+    nib_flush<4>(s0, acc_e, acc_o);
+    nib_flush<4>(s1, acc_e, acc_o);
+  }
+  if (f + 3 <= n) {
+    uint32_t a[3][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) rec_window<Q>(lmn, fw[f + i], lane_byte, a[i]);
+    uint32_t s0[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s0[k] = a[0][k] + a[1][k] + a[2][k];
+    nib_flush<4>(s0, acc_e, acc_o);
+    f += 3;
+  }
+  if (f < n) {  // one or two left
+    uint32_t a0[4], a1[4];
+    rec_window<Q>(lmn, fw[f], lane_byte, a0);
+    if (f + 1 < n) {
+      rec_window<Q>(lmn, fw[f + 1], lane_byte, a1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a0[k] += a1[k];
+    }
+    nib_flush<4>(a0, acc_e, acc_o);
+  }
+}
+
+// u8 sums of at most 63 features -> added to the u16 totals ([OCV] addSimilarities widening), accumulators cleared.
+__device__ __forceinline__ void rec_widen(uint32_t (&acc_e)[4], uint32_t (&acc_o)[4], uint32_t (&tot)[4][4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    tot[k][0] += acc_e[k] & 0x00ff00ffu;
+    tot[k][1] += (acc_e[k] >> 8) & 0x00ff00ffu;
+    tot[k][2] += acc_o[k] & 0x00ff00ffu;
+    tot[k][3] += (acc_o[k] >> 8) & 0x00ff00ffu;
+    acc_e[k] = 0; acc_o[k] = 0;
+  }
+}
+
+// Can any position of the warp's tile still exceed raw_threshold, `remaining` features (<= 4 each) to go?
+__device__ __forceinline__ bool rec_alive(const uint32_t (&tot)[4][4], int thr, int remaining, bool active) {
+  const int need = thr - 4 * remaining;  // a position passes only if partial > need
+  if (need < 0) return true;             // warp-uniform
+  uint32_t mx = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) mx = __vmaxu2(mx, tot[k][r]);
+  const int best = (int)max(mx & 0xffffu, mx >> 16);
+  return __any_sync(kFull, active && best > need);
+}
+
+__global__ void __launch_bounds__(256, 3) k_similarity_coarse_rec(const uint8_t* __restrict__ lmn,
+                                                               const uint32_t* __restrict__ recs, int rec_words,
+                                                               int n_tiles, const QueryThresholds thr_q, int M, int prune,
+                                                               Cand* __restrict__ cand, ResultHeader* hdr,
+                                                               unsigned long long* touched, uint32_t cand_cap,
+                                                               uint16_t* __restrict__ dump, int dump_stride) {
+  __shared__ uint32_t s_rec[8][kRecMaxWords];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* sr = s_rec[warp];
+  auto draw = [&]() -> uint32_t {
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(&hdr->next_tile, 1u);
+    return __shfl_sync(kFull, t, 0);
+  };
+  uint32_t cur = draw();
+  if (cur >= (uint32_t)n_tiles) return;
+  for (int i = lane; i < rec_words; i += 32) sr[i] = __ldg(recs + (size_t)cur * rec_words + i);
+  uint32_t nxt = draw();
+  const uint32_t lane_byte = (uint32_t)lane * 16u;
+  const int first = lane * 32;  // first position of this lane within the pass
+  unsigned long long bytes = 0;  // (feature, position) pairs actually gathered by this warp
+  for (;;) {
+    __syncwarp();
+    // prefetch the next tile's record into registers and draw the tile after it
+    const bool has_next = nxt < (uint32_t)n_tiles;
+    uint32_t pre[kRecPre];
+#pragma unroll
+    for (int i = 0; i < kRecPre; ++i) {
+      const int idx = lane + 32 * i;
+      pre[i] = (has_next && idx < rec_words) ? __ldg(recs + (size_t)nxt * rec_words + idx) : 0u;
+    }
+    const uint32_t nxt2 = has_next ? draw() : nxt;
+
+    const uint32_t item = sr[0], tg = sr[1], nfq = sr[2];
+    const int n_feat = (int)sr[3], j0 = (int)sr[4], rem = (int)sr[5];
+    const bool active = first < rem;
+    // [OCV] matchClass: raw_threshold = (int)(2*nf + (threshold / 100.f) * (2*nf) + 0.5f), same f32 roundings
+    const float threshold = thr_q.v[nfq >> 28];
+    const float two_nf = (float)(2 * (int)(nfq & 0x0fffffffu));
+    const int thr = __float2int_rz(__fadd_rn(__fadd_rn(two_nf, __fmul_rn(__fdiv_rn(threshold, 100.f), two_nf)), 0.5f));
+    uint32_t tot[4][4];  // u16 x 2 per register: [k][r], r = (i & 1) * 2 + ((i >> 1) & 1) for position 8k + i
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tot[k][0] = tot[k][1] = tot[k][2] = tot[k][3] = 0;
+    uint32_t acc_e[4] = {0, 0, 0, 0}, acc_o[4] = {0, 0, 0, 0};
+    const uint32_t* fw = sr + kRecHdrWords;
+    int done = 0;
+    bool alive = true;
+    for (int m = 0; m < M && alive; ++m) {
+      const uint32_t c4 = sr[8 + m];  // 4 class sizes, one word
+      const int n0 = c4 & 255, n1 = (c4 >> 8) & 255, n2 = (c4 >> 16) & 255, n3 = c4 >> 24;
+      if (active) {
+        rec_group<0>(lmn, fw, n0, lane_byte, acc_e, acc_o);
+        rec_group<1>(lmn, fw + n0, n1, lane_byte, acc_e, acc_o);
+      }
+      fw += n0 + n1; done += n0 + n1;
+      rec_widen(acc_e, acc_o, tot);
+      if (prune && !rec_alive(tot, thr, n_feat - done, active)) { alive = false; break; }
+      if (active) {
+        rec_group<2>(lmn, fw, n2, lane_byte, acc_e, acc_o);
+        rec_group<3>(lmn, fw + n2, n3, lane_byte, acc_e, acc_o);
+      }
+      fw += n2 + n3; done += n2 + n3;
+      rec_widen(acc_e, acc_o, tot);
+      if (prune && !rec_alive(tot, thr, n_feat - done, active)) alive = false;
+    }
+    bytes += (unsigned long long)done * (unsigned)rem;
+    if (alive && active) {
+      bool hit = thr < 0;
+      if (!hit) {
+        const uint32_t thr2 = (uint32_t)min(thr, 0xffff) * 0x00010001u;
+        uint32_t any = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) any |= __vcmpgtu2(tot[k][r], thr2);
+        hit = any != 0;
+      }
+      if (dump != nullptr || hit) {  // rare: [OCV] matchClass raster scan, "raw_score > raw_threshold"
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int p = first + 8 * k + i;
+            const uint32_t src = tot[k][(i & 1) * 2 + ((i >> 1) & 1)];
+            const int raw = (int)((i & 4) ? (src >> 16) : (src & 0xffffu));
+            if (p < rem) {
+              if (dump != nullptr) dump[(size_t)item * dump_stride + j0 + p] = (uint16_t)raw;
+              if (raw > thr) {
+                uint32_t idx = atomicAdd(&hdr->n_cands, 1u);
+                if (idx < cand_cap) {
+                  Cand c;
+                  c.tglob = tg; c.pos = (uint32_t)(j0 + p); c.raw = (uint32_t)raw; c.item = item;
+                  cand[idx] = c;
+                }
+              }
+            }
+          }
+      }
+    }
+    if (!has_next) break;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kRecPre; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < rec_words) sr[idx] = pre[i];
+    }
+    nxt = nxt2;
+  }
+  if (lane == 0 && touched != nullptr) atomicAdd(touched, bytes);
+}
+
+// Byte linear memories -> nibble-packed copy (two positions per byte), 16 bytes in / 8 bytes out per thread.
+__global__ void __launch_bounds__(256) k_pack_nibbles(const uint4* __restrict__ src, uint2* __restrict__ dst, size_t n16) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n16) return;
+  const uint4 v = src[i];
+  // bytes b0 b1 b2 b3 of a word -> nibbles b0 | b1<<4 | b2<<8 | b3<<12
+  auto squeeze = [](uint32_t w) -> uint32_t {
+    uint32_t t = (w | (w >> 4)) & 0x00ff00ffu;  // b0|b1<<4 in byte 0, b2|b3<<4 in byte 2
+    return (t | (t >> 8)) & 0xffffu;
+  };
+  uint2 o;
+  o.x = squeeze(v.x) | (squeeze(v.y) << 16);
+  o.y = squeeze(v.z) | (squeeze(v.w) << 16);
+  dst[i] = o;
+}
+
 // Local refinement of every coarse candidate up the pyramid.  One 8-warp block per candidate: the 16 x 16 patch is
 // mapped lane -> (row = lane / 2, 8 columns = lane % 2) in every warp, the template's features are dealt round-robin
 // to the warps (each keeps its own u8 accumulators), and the per-warp u16 partial sums meet in shared memory.
@@ -271,17 +693,52 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams
 
 }  // namespace
 
-int coarse_positions_per_pass() { return kWarpPos; }
+int coarse_positions_per_pass(int variant) {
+  return variant == 1 ? kWarpPos : (variant == 2 ? Nib<4>::kWarpPos : kRecWarpPos);
+}
+int coarse_record_header_words() { return kRecHdrWords; }
+int coarse_record_max_words() { return kRecMaxWords; }
 
-void launch_similarity_coarse(const uint8_t* lmc, const uint32_t* foff, const CoarseTpl* tpl, const WorkItem* items,
-                              const uint2* tiles, int n_tiles, const QueryThresholds& thr, int M, Cand* cand,
-                              ResultHeader* hdr, uint32_t cand_cap, uint16_t* dump, int dump_stride, cudaStream_t s) {
+template <class K>
+static int resident_ctas(K kernel) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 2;
+  }
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return per_sm * sms;
+}
+
+void launch_similarity_coarse(int variant, const uint8_t* lmc, const uint8_t* lmn, const uint32_t* foff,
+                              const CoarseTpl* tpl, const WorkItem* items, const uint2* tiles, const uint32_t* recs,
+                              int rec_words, int n_tiles, const QueryThresholds& thr, int M, int prune, Cand* cand,
+                              ResultHeader* hdr, unsigned long long* touched, uint32_t cand_cap, uint16_t* dump,
+                              int dump_stride, cudaStream_t s) {
   if (n_tiles <= 0) return;
   int blocks = (n_tiles + 7) / 8;
-  const int persistent = 148 * 4;  // 64 registers/thread: 4 resident 8-warp CTAs per SM
-  if (blocks > persistent) blocks = persistent;
-  k_similarity_coarse<<<blocks, 256, 0, s>>>(lmc, foff, tpl, items, tiles, n_tiles, thr, M, cand, hdr, cand_cap, dump,
-                                             dump_stride);
+  if (variant == 1) {  // byte linear memories (A/B reference of the nibble kernels)
+    static const int persistent = resident_ctas(k_similarity_coarse);
+    k_similarity_coarse<<<min(blocks, persistent), 256, 0, s>>>(lmc, foff, tpl, items, tiles, n_tiles, thr, M, cand,
+                                                                hdr, cand_cap, dump, dump_stride);
+  } else if (variant == 2) {  // nibble planes, two overlapping vector loads per feature (A/B reference)
+    static const int persistent = resident_ctas(k_similarity_coarse_nib<4>);
+    k_similarity_coarse_nib<4><<<min(blocks, persistent), 256, 0, s>>>(lmn, foff, tpl, items, tiles, n_tiles, thr, M,
+                                                                       cand, hdr, cand_cap, dump, dump_stride);
+  } else {
+    static const int persistent = resident_ctas(k_similarity_coarse_rec);
+    k_similarity_coarse_rec<<<min(blocks, persistent), 256, 0, s>>>(lmn, recs, rec_words, n_tiles, thr, M,
+                                                                    dump == nullptr ? prune : 0, cand, hdr, touched,
+                                                                    cand_cap, dump, dump_stride);
+  }
+}
+
+void launch_pack_nibbles(const uint8_t* lm_bytes, uint8_t* lm_nibbles, size_t n_bytes, cudaStream_t s) {
+  const size_t n16 = n_bytes / 16;
+  if (n16 == 0) return;
+  k_pack_nibbles<<<(unsigned)((n16 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(lm_bytes),
+                                                                reinterpret_cast<uint2*>(lm_nibbles), n16);
 }
 
 void launch_refine(const RefineParams& p, const CoarseTpl* ctpl, const WorkItem* items, const Cand* cand,

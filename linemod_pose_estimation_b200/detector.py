@@ -32,7 +32,7 @@ def DepthNormal(distance_threshold=2000, difference_threshold=50, num_features=6
 
 
 class Stage:
-    QUANTIZED, SPREAD, RESPONSE, LINEAR, MAGNITUDE, QUANT_RAW = range(6)
+    QUANTIZED, SPREAD, RESPONSE, LINEAR, MAGNITUDE, QUANT_RAW, LINEAR_PACKED = range(7)
 
 
 class Detector:
@@ -291,6 +291,8 @@ class Detector:
             return buf.reshape(8, g["rows"], g["cols"])
         if stage == Stage.LINEAR:
             return buf.reshape(8, g["plane_stride"])
+        if stage == Stage.LINEAR_PACKED:
+            return buf.reshape(8, g["plane_stride"] // 2)
         return buf.view(np.float32).reshape(g["rows"], g["cols"])
 
     def coarse_map(self, class_id, template_id):
@@ -312,6 +314,7 @@ class Detector:
         return dict(h2d=ms[0], front=ms[1], coarse=ms[2], refine=ms[3], d2h=ms[4], launches=k.value)
 
     def last_work(self):
-        w = (C.c_uint64 * 6)()
+        w = (C.c_uint64 * 8)()
         check(lib().lm_last_work(self._h, w))
-        return dict(B_front=w[0], B_coarse=w[1], B_refine=w[2], B_out=w[3], candidates=w[4], evals=w[5])
+        return dict(B_front=w[0], B_coarse=w[1], B_refine=w[2], B_out=w[3], candidates=w[4], evals=w[5],
+                    B_coarse_gathered=w[6])

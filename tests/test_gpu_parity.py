@@ -108,6 +108,32 @@ def test_coarse_similarity_maps_bit_exact():
         assert np.array_equal(a, b), "coarse map of template %d differs in %d cells" % (tid, np.count_nonzero(a != b))
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_coarse_kernel_variants(variant):
+    """0: nibble-packed linear memories, 128-bit windows (production); 2: nibble-packed, 64-bit windows; 1: byte linear
+    memories.  Every variant must give the oracle's coarse maps and match lists; the packed planes must be the byte
+    planes two positions per byte."""
+    orc, det, views = _pair(n_views=8, n_random=90, seed=21, classes=("a", "b"))
+    det.set_option("coarse_variant", variant)
+    bgr, depth, _ = synth.compose_scene(1003, views[:4])
+    orc.build_front([bgr, depth])
+    det.build_front([bgr, depth])
+    for m in range(2):
+        packed = det.fetch(Stage.LINEAR_PACKED, 1, m)
+        want = orc.fetch(Stage.LINEAR, 1, m)
+        assert np.array_equal(packed & 15, want[:, 0::2]) and np.array_equal(packed >> 4, want[:, 1::2])
+    for cid in ("a", "b"):
+        for tid in range(orc.num_templates(cid)):
+            a, b = det.coarse_map(cid, tid), orc.coarse_map(cid, tid)
+            assert np.array_equal(a, b), "variant %d: coarse map of %s/%d differs in %d cells" % (variant, cid, tid, np.count_nonzero(a != b))
+    for thr in (90.0, 65.0):
+        want = orc.match([bgr, depth], thr, keep_candidates=True)
+        got = det.match([bgr, depth], thr)
+        common.assert_matches_equal(got, want, "variant %d thr %g" % (variant, thr))
+        assert det.last_work()["candidates"] == len(orc.last_candidates())
+    assert len(want) > 0
+
+
 @pytest.mark.parametrize("threshold", [92.0, 80.0, 60.0])
 def test_match_lists_identical(threshold):
     orc, det, views = _pair(n_views=10, n_random=60, seed=13, classes=("cpu_binary", "memoryChip2"))
