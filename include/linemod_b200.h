@@ -166,6 +166,10 @@ int lm_match_multi(lm_detector* det, const lm_image* sources, int n_sources, con
  * into out_matches. */
 int lm_match_batch(lm_detector* det, const lm_image* sources, int n_frames, int n_sources, float threshold,
                    const char* const* class_ids, int n_ids, lm_match_rec** out_matches, size_t* out_offsets);
+/* Batch + multi-query: every frame answers every query from one front end (a video stream watched by the reference's
+ * two-object service).  out_offsets receives n_frames * n_queries + 1 prefix offsets, frame-major. */
+int lm_match_batch_multi(lm_detector* det, const lm_image* sources, int n_frames, int n_sources, const lm_query* queries,
+                         int n_queries, lm_match_rec** out_matches, size_t* out_offsets);
 void lm_free_matches(lm_match_rec* matches);
 
 /* Device-resident variant for multi-GPU sharding and for callers that already hold the frame in HBM:

@@ -1343,14 +1343,14 @@ int lm_match(lm_detector* d, const lm_image* sources, int n_sources, float thres
   return rc;
 }
 
-int lm_match_batch(lm_detector* d, const lm_image* sources, int n_frames, int n_sources, float threshold,
-                   const char* const* class_ids, int n_ids, lm_match_rec** out_matches, size_t* out_offsets) {
-  if (!d || !sources || !out_matches || !out_offsets || n_frames < 0) return fail(LM_E_INVALID, "NULL argument");
+// Frames pipelined over the two lanes: while lane A's kernels run, lane B's frame is packed / copied to the device.
+// out_offsets: n_frames * n_q + 1 prefix offsets, frame-major.
+static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frames, int n_sources, const Query* qs, int n_q,
+                            lm_match_rec** out_matches, size_t* out_offsets) {
   *out_matches = nullptr;
+  if (n_q < 1 || n_q > kMaxQueries) return fail(LM_E_INVALID, "number of queries must be 1..%d", kMaxQueries);
   std::vector<lm_match_rec> all;
   out_offsets[0] = 0;
-  const Query query = {threshold, class_ids, n_ids};
-  // Two lanes: while lane A's kernels run, lane B's frame is packed into pinned memory and copied.
   bool busy[2] = {false, false};
   auto finish = [&](int li, int frame) -> int {
     Lane& ln = d->lane[li];
@@ -1358,13 +1358,15 @@ int lm_match_batch(lm_detector* d, const lm_image* sources, int n_frames, int n_
     bool overflow = false;
     uint32_t n_cands = 0;
     if (download_records(ln, ln.stream, raw, &overflow, &n_cands) != LM_OK) return LM_E_CUDA;
-    std::vector<lm_match_rec> out;
+    std::vector<lm_match_rec> out[kMaxQueries];
     if (overflow) {  // rare: redo this frame alone with growing buffers
-      int rc = match_front(d, ln, &query, 1, &out);
+      int rc = match_front(d, ln, qs, n_q, out);
       if (rc != LM_OK) return rc;
-    } else finalize_records(d->model.levels(), raw, ln.presort, out);
-    all.insert(all.end(), out.begin(), out.end());
-    out_offsets[frame + 1] = all.size();
+    } else finalize_queries(d, ln, raw, n_q, out);
+    for (int q = 0; q < n_q; ++q) {
+      all.insert(all.end(), out[q].begin(), out[q].end());
+      out_offsets[(size_t)frame * n_q + q + 1] = all.size();
+    }
     return LM_OK;
   };
   for (int f = 0; f < n_frames; ++f) {
@@ -1376,10 +1378,10 @@ int lm_match_batch(lm_detector* d, const lm_image* sources, int n_frames, int n_
     rc = ensure_pack(d, ln);
     if (rc != LM_OK) return rc;
     Pack::Plan* plan = nullptr;
-    rc = get_plan(d, &query, 1, &plan);
+    rc = get_plan(d, qs, n_q, &plan);
     if (rc != LM_OK) return rc;
     if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
-    if (enqueue_match(d, ln, *plan, &query, 1, ln.stream, ln.ev[3]) != LM_OK) return LM_E_CUDA;
+    if (enqueue_match(d, ln, *plan, qs, n_q, ln.stream, ln.ev[3]) != LM_OK) return LM_E_CUDA;
     CU(cudaEventRecord(ln.ev[4], ln.stream));
     busy[li] = true;
   }
@@ -1387,6 +1389,22 @@ int lm_match_batch(lm_detector* d, const lm_image* sources, int n_frames, int n_
     if (busy[f & 1]) { int rc = finish(f & 1, f); if (rc != LM_OK) return rc; busy[f & 1] = false; }
   size_t n = 0;
   return copy_out(all, out_matches, &n);
+}
+
+int lm_match_batch(lm_detector* d, const lm_image* sources, int n_frames, int n_sources, float threshold,
+                   const char* const* class_ids, int n_ids, lm_match_rec** out_matches, size_t* out_offsets) {
+  if (!d || !sources || !out_matches || !out_offsets || n_frames < 0) return fail(LM_E_INVALID, "NULL argument");
+  const Query query = {threshold, class_ids, n_ids};
+  return match_batch_impl(d, sources, n_frames, n_sources, &query, 1, out_matches, out_offsets);
+}
+
+int lm_match_batch_multi(lm_detector* d, const lm_image* sources, int n_frames, int n_sources, const lm_query* queries,
+                         int n_queries, lm_match_rec** out_matches, size_t* out_offsets) {
+  if (!d || !sources || !out_matches || !out_offsets || n_frames < 0) return fail(LM_E_INVALID, "NULL argument");
+  Query qs[kMaxQueries];
+  int rc = to_queries(queries, n_queries, qs);
+  if (rc != LM_OK) return rc;
+  return match_batch_impl(d, sources, n_frames, n_sources, qs, n_queries, out_matches, out_offsets);
 }
 
 void lm_free_matches(lm_match_rec* m) { std::free(m); }

@@ -226,6 +226,20 @@ class Detector:
         allm = self._take(out, offs[len(frames)])
         return [allm[offs[i]:offs[i + 1]] for i in range(len(frames))]
 
+    def match_batch_multi(self, frames, queries):
+        """frames: list of per-frame source lists; queries: [(threshold, [class ids])].
+        -> list (per frame) of lists (per query) of match arrays; frames are pipelined over two streams."""
+        flat = [s for f in frames for s in f]
+        arr, keep = image_array(flat)
+        qarr, qkeep = _capi.query_array(queries)
+        out = C.c_void_p()
+        n_q = len(queries)
+        offs = (C.c_size_t * (len(frames) * n_q + 1))()
+        check(lib().lm_match_batch_multi(self._h, arr, len(frames), len(frames[0]) if frames else 0, qarr, n_q,
+                                         C.byref(out), offs))
+        allm = self._take(out, offs[len(frames) * n_q])
+        return [[allm[offs[f * n_q + q]:offs[f * n_q + q + 1]] for q in range(n_q)] for f in range(len(frames))]
+
     def match_device(self, d_ptrs, rows, cols, threshold, stream=0, class_ids=()):
         """Device-resident sources (tightly packed), asynchronous on `stream`.  -> (device pointer of the record
         block {count, capacity, overflow, n_cands} + raw records, capacity in bytes)."""

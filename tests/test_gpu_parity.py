@@ -386,3 +386,24 @@ def test_match_multi_equals_separate_matches():
             common.assert_matches_equal(g, orc.match([bgr, depth], thr, class_ids=ids), "query %s" % ((thr, ids),))
             common.assert_matches_equal(g, det.match([bgr, depth], thr, class_ids=ids), "separate call %s" % ((thr, ids),))
     assert sum(len(g) for g in got) > 0
+
+
+def test_batch_multi_equals_per_frame_multi():
+    """lm_match_batch_multi: a stream of frames, every frame answering every query == lm_match_multi per frame."""
+    orc, det, views = _pair(n_views=8, n_random=40, seed=79, classes=("cpu_binary", "memoryChip2"))
+    queries = [(90.0, ["memoryChip2"]), (70.0, ["cpu_binary"]), (62.0, [])]
+    frames = []
+    for seed in (3000, 3001, 3002, 3003, 3004):
+        bgr, depth, _ = synth.compose_scene(seed, views[:5])
+        frames.append([bgr, depth])
+    got = det.match_batch_multi(frames, queries)
+    assert len(got) == len(frames)
+    total = 0
+    for f, per_query in zip(frames, got):
+        single = det.match_multi(f, queries)
+        for q, (g, s) in enumerate(zip(per_query, single)):
+            common.assert_matches_equal(g, s, "frame/query %d" % q)
+            common.assert_matches_equal(g, orc.match(f, queries[q][0], class_ids=queries[q][1]), "oracle, query %d" % q)
+            total += len(g)
+    assert total > 0
+    assert det.match_batch_multi([], queries) == []
