@@ -89,6 +89,7 @@ struct Lane {
   bool lm_ready = false;      // LM buffers sized + zero-tailed for (rows, cols)
   bool front_valid = false;
   bool debug_taps_written = false;
+  bool coarse_bytes_valid = false;  // the coarsest level's byte planes were written by the last front end
   std::vector<LevelGeom> geom;
   // per modality
   DevBuf src[LM_MAX_MODALITIES];       // level-0 source (BGR / depth)
@@ -453,6 +454,7 @@ static int run_front(lm_detector* d, Lane& ln, cudaStream_t s) {
   if (run_quantize(d, ln, s) != LM_OK) return LM_E_CUDA;
   const bool taps = d->debug_taps != 0;
   if (taps && ensure_tap_ws(d, ln) != LM_OK) return LM_E_CUDA;
+  bool direct_nibbles = false, coarse_bytes = true;
   if (d->frontend_variant == 1) {
     for (int l = 0; l < L; ++l) {
       const LevelGeom& g = ln.geom[l];
@@ -468,6 +470,11 @@ static int run_front(lm_detector* d, Lane& ln, cudaStream_t s) {
     SpreadParams sp;
     std::memset(&sp, 0, sizeof(sp));
     sp.resp_all = d->d_resp_all.as<uint32_t>();
+    {
+      const LevelGeom& gc = ln.geom[L - 1];
+      direct_nibbles = (gc.W % 8) == 0 && ((size_t)gc.W * gc.H) % 8 == 0;  // word-aligned nibble rows
+      coarse_bytes = taps || d->coarse_variant == 1 || !direct_nibbles;
+    }
     int total = 0, max_T = 1;
     for (int l = 0; l < L; ++l) {
       const LevelGeom& g = ln.geom[l];
@@ -480,6 +487,11 @@ static int run_front(lm_detector* d, Lane& ln, cudaStream_t s) {
         e.spread = taps ? ln.spread[l][m].as<uint8_t>() : nullptr;
         e.response = taps ? ln.response[l][m].as<uint8_t>() : nullptr;
         e.lm = ln.lmem[l].as<uint8_t>() + (size_t)m * 8 * g.plane_stride;
+        e.lm_nib = nullptr;
+        if (l == L - 1) {  // the matcher reads the coarsest level nibble-packed; byte planes only when something wants them
+          if (direct_nibbles) e.lm_nib = ln.lmn.as<uint8_t>() + (size_t)m * 4 * g.plane_stride;
+          if (!coarse_bytes) e.lm = nullptr;
+        }
         e.plane_stride = g.plane_stride;
         e.rows = g.rows; e.cols = g.cols; e.T = g.T; e.W = g.W; e.H = g.H; e.level = l; e.mask_cols0 = ln.cols;
         e.block_begin = total;
@@ -489,11 +501,12 @@ static int run_front(lm_detector* d, Lane& ln, cudaStream_t s) {
     if (!launch_spread_all(sp, total, max_T, s)) return fail(LM_E_INVALID, "T=%d needs too much shared memory", max_T);
     ++ln.launches;
   }
-  {  // nibble-packed copy of the coarsest level for k_similarity_coarse_nib
+  if (!direct_nibbles) {  // nibble-packed copy of the coarsest level from its byte planes
     const LevelGeom& gc = ln.geom[L - 1];
     launch_pack_nibbles(ln.lmem[L - 1].as<uint8_t>(), ln.lmn.as<uint8_t>(), (size_t)M * 8 * gc.plane_stride, s);
     ++ln.launches;
   }
+  ln.coarse_bytes_valid = coarse_bytes;
   CU(cudaGetLastError());
   ln.front_valid = true;
   ln.debug_taps_written = taps;
@@ -1246,7 +1259,7 @@ int lm_set_option(lm_detector* d, const char* key, int value) {
   if (!d || !key) return fail(LM_E_INVALID, "NULL argument");
   std::string k(key);
   if (k == "debug_taps") d->debug_taps = value;
-  else if (k == "coarse_variant") d->coarse_variant = value;
+  else if (k == "coarse_variant") { d->coarse_variant = value; for (int i = 0; i < 2; ++i) d->lane[i].front_valid = false; }
   else if (k == "timing") d->timing = value;
   else if (k == "prune") d->prune = value;
   else if (k == "frontend_variant") { d->frontend_variant = value; for (int i = 0; i < 2; ++i) d->lane[i].front_valid = false; }
@@ -1485,7 +1498,19 @@ long lm_debug_fetch(lm_detector* d, int stage, int level, int modality, void* ds
       src = stage == LM_STAGE_SPREAD ? ln.spread[level][modality].p : ln.response[level][modality].p;
       bytes = stage == LM_STAGE_SPREAD ? n : 8 * n; break;
     case LM_STAGE_LINEAR:
-      src = ln.lmem[level].as<uint8_t>() + (size_t)modality * 8 * g.plane_stride; bytes = 8 * g.plane_stride; break;
+      bytes = 8 * g.plane_stride;
+      if (level == d->model.levels() - 1 && !ln.coarse_bytes_valid) {  // only the packed planes exist: unpack them
+        if (dst) {
+          std::vector<uint8_t> packed(bytes / 2);
+          if (cudaStreamSynchronize(ln.stream) != cudaSuccess ||
+              cudaMemcpy(packed.data(), ln.lmn.as<uint8_t>() + (size_t)modality * 4 * g.plane_stride, bytes / 2, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return fail(LM_E_CUDA, "debug fetch failed: %s", cudaGetErrorString(cudaGetLastError()));
+          uint8_t* o = static_cast<uint8_t*>(dst);
+          for (size_t i = 0; i < bytes / 2; ++i) { o[2 * i] = packed[i] & 15; o[2 * i + 1] = packed[i] >> 4; }
+        }
+        return (long)bytes;
+      }
+      src = ln.lmem[level].as<uint8_t>() + (size_t)modality * 8 * g.plane_stride; break;
     case LM_STAGE_LINEAR_PACKED:
       if (level != d->model.levels() - 1) return fail(LM_E_INVALID, "only the coarsest level has a packed copy");
       src = ln.lmn.as<uint8_t>() + (size_t)modality * 4 * g.plane_stride; bytes = 4 * g.plane_stride; break;

@@ -228,19 +228,33 @@ __global__ void __launch_bounds__(256) k_dn_fused(const DnParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------- spread -> LM
-constexpr int SP_CW = 16;  // grid cells per block along x
+// One CTA = one row of T-cells x SP_CW cells of one (level, modality).  Everything is done on 32-bit words (four
+// pixels): masked quantisation -> separable OR (T-1 funnel shifts along x, T-1 word ORs along y) -> one LUT word per
+// spread byte (8 response nibbles) -> 4x4 byte transposes (PRMT) so that every store is a full word of one
+// (orientation, T^2 phase) row of the linear memories.  The coarsest level is written nibble-packed directly (an 8x8
+// nibble transpose: one word = 8 consecutive cells) when its rows are word-aligned.
+constexpr int SP_CW = 32;  // grid cells per block along x
 
-__global__ void __launch_bounds__(256) k_spread_all(const SpreadParams P) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  int ei = 0;
-  while (ei + 1 < P.n && (int)blockIdx.x >= P.e[ei + 1].block_begin) ++ei;
-  const SpreadEntry& E = P.e[ei];
-  const int T = E.T, W = E.W, H = E.H, rows = E.rows, cols = E.cols;
-  const int TWp = SP_CW * T, IW = TWp + T - 1, IH = 2 * T - 1;
+__host__ __device__ inline int sp_nwo(int T) { return SP_CW * T / 4; }
+__host__ __device__ inline int sp_nwq(int T) { return (SP_CW * T + T - 1 + 3) / 4 + 1; }
+
+// 4x4 byte transpose: in[j] = bytes (k = 0..3) of item j  ->  out[k] = bytes (j = 0..3)
+__device__ __forceinline__ void transpose4x4(const uint32_t (&in)[4], uint32_t (&out)[4]) {
+  const uint32_t t0 = __byte_perm(in[0], in[1], 0x5140), t1 = __byte_perm(in[2], in[3], 0x5140);
+  const uint32_t t2 = __byte_perm(in[0], in[1], 0x7362), t3 = __byte_perm(in[2], in[3], 0x7362);
+  out[0] = __byte_perm(t0, t1, 0x5410); out[1] = __byte_perm(t0, t1, 0x7632);
+  out[2] = __byte_perm(t2, t3, 0x5410); out[3] = __byte_perm(t2, t3, 0x7632);
+}
+
+template <int TT>
+__device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadEntry& E, uint8_t* smem) {
+  const int T = TT ? TT : E.T;
+  const int W = E.W, H = E.H, rows = E.rows, cols = E.cols;
+  const int IH = 2 * T - 1, NWO = sp_nwo(T), NWQ = sp_nwq(T);
   uint32_t* s_resp = reinterpret_cast<uint32_t*>(smem);
-  uint8_t* sq = smem + 1024;
-  uint8_t* sh = sq + ((IH * IW + 15) & ~15);
-  uint8_t* sp = sh + ((IH * TWp + 15) & ~15);
+  uint32_t* sq = s_resp + 256;
+  uint32_t* sh = sq + IH * NWQ;
+  uint32_t* sp = sh + IH * NWO;
   const int b = blockIdx.x - E.block_begin;
   const int c0 = (b % E.blocks_x) * SP_CW, a = b / E.blocks_x;
   const int px0 = c0 * T, py0 = a * T;
@@ -248,72 +262,145 @@ __global__ void __launch_bounds__(256) k_spread_all(const SpreadParams P) {
   const uint8_t* __restrict__ qraw = E.qraw;
   const uint8_t* __restrict__ mask0 = E.mask0;
   s_resp[tid] = P.resp_all[tid];
-  for (int i = tid; i < IH * IW; i += 256) {
-    int r = i / IW, x = i - r * IW;
-    int gy = py0 + r, gx = px0 + x;
-    uint8_t v = 0;
-    if (gy < rows && gx < cols) {
-      v = qraw[(size_t)gy * cols + gx];
-      if (mask0 && !mask0[(size_t)(gy << E.level) * E.mask_cols0 + (gx << E.level)]) v = 0;
-      if (r < T && x < TWp) E.quantized[(size_t)gy * cols + gx] = v;
+  // ---- masked quantisation, four pixels per word; pixels outside the image are 0 ([OCV] spread stays in bounds)
+  const bool fast = mask0 == nullptr && (cols & 3) == 0;
+  for (int i = tid; i < IH * NWQ; i += 256) {
+    const int r = i / NWQ, wi = i - r * NWQ;
+    const int gy = py0 + r, gx = px0 + 4 * wi;
+    uint32_t v = 0;
+    const bool own = r < T && wi < NWO;  // inside the block's own T x (SP_CW*T) pixels: write Detector::match's quantized image
+    if (fast) {
+      if (gy < rows && gx < cols) {
+        v = __ldg(reinterpret_cast<const uint32_t*>(qraw + (size_t)gy * cols + gx));
+        if (own) *reinterpret_cast<uint32_t*>(E.quantized + (size_t)gy * cols + gx) = v;
+      }
+    } else if (gy < rows) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int x = gx + k;
+        if (x < cols) {
+          uint32_t q = qraw[(size_t)gy * cols + x];
+          if (mask0 && !mask0[(size_t)(gy << E.level) * E.mask_cols0 + (x << E.level)]) q = 0;
+          if (own) E.quantized[(size_t)gy * cols + x] = (uint8_t)q;
+          v |= q << (8 * k);
+        }
+      }
     }
     sq[i] = v;
   }
   __syncthreads();
-  for (int i = tid; i < IH * TWp; i += 256) {
-    int r = i / TWp, x = i - r * TWp;
-    const uint8_t* p = sq + r * IW + x;
-    uint8_t v = 0;
-    for (int c = 0; c < T; ++c) v |= p[c];
+  // ---- OR over T pixels along x: byte x of the result needs bytes x .. x+T-1
+  for (int i = tid; i < IH * NWO; i += 256) {
+    const int r = i / NWO, wi = i - r * NWO;
+    const uint32_t* q = sq + r * NWQ + wi;
+    uint32_t v = q[0];
+    if (TT) {
+      uint32_t w[(TT + 2) / 4 + 2];
+#pragma unroll
+      for (int k = 0; k < (TT + 2) / 4 + 2; ++k) w[k] = q[k];
+#pragma unroll
+      for (int c = 1; c < TT; ++c) v |= __funnelshift_r(w[c >> 2], w[(c >> 2) + 1], 8 * (c & 3));
+    } else {
+      for (int c = 1; c < T; ++c) v |= __funnelshift_r(q[c >> 2], q[(c >> 2) + 1], 8 * (c & 3));
+    }
     sh[i] = v;
   }
   __syncthreads();
-  for (int i = tid; i < T * TWp; i += 256) {
-    int r = i / TWp, x = i - r * TWp;
-    uint8_t v = 0;
-    for (int k = 0; k < T; ++k) v |= sh[(r + k) * TWp + x];
-    sp[i] = v;
-    int gy = py0 + r, gx = px0 + x;
-    if (E.spread && gy < rows && gx < cols) E.spread[(size_t)gy * cols + gx] = v;
-  }
-  __syncthreads();
-  const size_t WH = (size_t)W * H;
-  const int ncell = min(SP_CW, W - c0);
-  uint8_t* __restrict__ lm = E.lm;
-  if ((W & 3) == 0) {
-    const int items = T * T * (SP_CW / 4);
-    for (int it = tid; it < items; it += 256) {
-      int b4 = it % (SP_CW / 4), g = it / (SP_CW / 4);
-      if (b4 * 4 >= ncell) continue;
-      int rs = g / T, cs = g - rs * T;
-      const uint8_t* p = sp + rs * TWp + cs + T * (b4 * 4);
-      uint32_t r0 = s_resp[p[0]], r1 = s_resp[p[T]], r2 = s_resp[p[2 * T]], r3 = s_resp[p[3 * T]];
-      size_t o = (size_t)g * WH + (size_t)a * W + c0 + b4 * 4;
+  // ---- OR over T rows
+  for (int i = tid; i < T * NWO; i += 256) {
+    const int r = i / NWO, wi = i - r * NWO;
+    uint32_t v = 0;
+    if (TT) {
 #pragma unroll
-      for (int ori = 0; ori < 8; ++ori) {
-        uint32_t v = ((r0 >> (4 * ori)) & 15) | (((r1 >> (4 * ori)) & 15) << 8) | (((r2 >> (4 * ori)) & 15) << 16) |
-                     (((r3 >> (4 * ori)) & 15) << 24);
-        *reinterpret_cast<uint32_t*>(lm + ori * E.plane_stride + o) = v;
+      for (int k = 0; k < TT; ++k) v |= sh[(r + k) * NWO + wi];
+    } else {
+      for (int k = 0; k < T; ++k) v |= sh[(r + k) * NWO + wi];
+    }
+    sp[i] = v;
+    if (E.spread) {
+      const int gy = py0 + r;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int gx = px0 + 4 * wi + k;
+        if (gy < rows && gx < cols) E.spread[(size_t)gy * cols + gx] = (uint8_t)(v >> (8 * k));
       }
     }
-  } else {
-    const int items = T * T * SP_CW;
-    for (int it = tid; it < items; it += 256) {
-      int bb = it % SP_CW, g = it / SP_CW;
-      if (bb >= ncell) continue;
-      int rs = g / T, cs = g - rs * T;
-      uint32_t r0 = s_resp[sp[rs * TWp + cs + T * bb]];
-      size_t o = (size_t)g * WH + (size_t)a * W + c0 + bb;
+  }
+  __syncthreads();
+  // ---- responses -> linear memories
+  const uint8_t* spb = reinterpret_cast<const uint8_t*>(sp);
+  const int row_bytes = NWO * 4;
+  const size_t WH = (size_t)W * H;
+  const int ncell = min(SP_CW, W - c0);
+  if (E.lm_nib != nullptr) {  // coarsest level, nibble-packed: one word = 8 consecutive cells of one (orientation, phase) row
+    const size_t nib_stride = (size_t)E.plane_stride / 2;
+    for (int it = tid; it < T * T * (SP_CW / 8); it += 256) {
+      const int b8 = it & (SP_CW / 8 - 1), g = it / (SP_CW / 8);
+      if (b8 * 8 >= ncell) continue;
+      const int rs = g / T, cs = g - rs * T;
+      const uint8_t* p = spb + rs * row_bytes + cs + T * (b8 * 8);
+      uint32_t ev[4], od[4];  // pixel pair (2p, 2p+1): even / odd orientations, one byte per orientation pair
 #pragma unroll
-      for (int ori = 0; ori < 8; ++ori) lm[ori * E.plane_stride + o] = (uint8_t)((r0 >> (4 * ori)) & 15);
+      for (int pr = 0; pr < 4; ++pr) {
+        const uint32_t r0 = s_resp[p[T * (2 * pr)]], r1 = s_resp[p[T * (2 * pr + 1)]];
+        ev[pr] = (r0 & 0x0f0f0f0fu) | ((r1 & 0x0f0f0f0fu) << 4);
+        od[pr] = ((r0 >> 4) & 0x0f0f0f0fu) | (r1 & 0xf0f0f0f0u);
+      }
+      uint32_t oe[4], oo[4];
+      transpose4x4(ev, oe);  // oe[k]: orientation 2k, nibbles = cells 0..7
+      transpose4x4(od, oo);  // oo[k]: orientation 2k+1
+      const size_t n0 = (size_t)g * WH + (size_t)a * W + c0 + b8 * 8;  // nibble index inside the plane (multiple of 8)
+      uint8_t* dst = E.lm_nib + n0 / 2;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        *reinterpret_cast<uint32_t*>(dst + (size_t)(2 * k) * nib_stride) = oe[k];
+        *reinterpret_cast<uint32_t*>(dst + (size_t)(2 * k + 1) * nib_stride) = oo[k];
+      }
+    }
+  }
+  uint8_t* __restrict__ lm = E.lm;
+  if (lm != nullptr) {
+    if ((W & 3) == 0) {
+      for (int it = tid; it < T * T * (SP_CW / 4); it += 256) {
+        const int b4 = it & (SP_CW / 4 - 1), g = it / (SP_CW / 4);
+        if (b4 * 4 >= ncell) continue;
+        const int rs = g / T, cs = g - rs * T;
+        const uint8_t* p = spb + rs * row_bytes + cs + T * (b4 * 4);
+        uint32_t ev[4], od[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t r = s_resp[p[T * j]];
+          ev[j] = r & 0x0f0f0f0fu;
+          od[j] = (r >> 4) & 0x0f0f0f0fu;
+        }
+        uint32_t oe[4], oo[4];
+        transpose4x4(ev, oe);
+        transpose4x4(od, oo);
+        uint8_t* dst = lm + (size_t)g * WH + (size_t)a * W + c0 + b4 * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          *reinterpret_cast<uint32_t*>(dst + (size_t)(2 * k) * E.plane_stride) = oe[k];
+          *reinterpret_cast<uint32_t*>(dst + (size_t)(2 * k + 1) * E.plane_stride) = oo[k];
+        }
+      }
+    } else {
+      for (int it = tid; it < T * T * SP_CW; it += 256) {
+        const int bb = it & (SP_CW - 1), g = it / SP_CW;
+        if (bb >= ncell) continue;
+        const int rs = g / T, cs = g - rs * T;
+        const uint32_t r0 = s_resp[spb[rs * row_bytes + cs + T * bb]];
+        const size_t o = (size_t)g * WH + (size_t)a * W + c0 + bb;
+#pragma unroll
+        for (int ori = 0; ori < 8; ++ori) lm[ori * E.plane_stride + o] = (uint8_t)((r0 >> (4 * ori)) & 15);
+      }
     }
   }
   if (E.response) {
-    for (int i = tid; i < T * TWp; i += 256) {
-      int r = i / TWp, x = i - r * TWp;
-      int gy = py0 + r, gx = px0 + x;
+    for (int i = tid; i < T * NWO * 4; i += 256) {
+      const int r = i / (NWO * 4), x = i - r * (NWO * 4);
+      const int gy = py0 + r, gx = px0 + x;
       if (gy < rows && gx < cols) {
-        uint32_t r0 = s_resp[sp[i]];
+        const uint32_t r0 = s_resp[spb[r * row_bytes + x]];
 #pragma unroll
         for (int ori = 0; ori < 8; ++ori)
           E.response[(size_t)ori * rows * cols + (size_t)gy * cols + gx] = (uint8_t)((r0 >> (4 * ori)) & 15);
@@ -322,9 +409,19 @@ __global__ void __launch_bounds__(256) k_spread_all(const SpreadParams P) {
   }
 }
 
+__global__ void __launch_bounds__(256) k_spread_all(const SpreadParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  int ei = 0;
+  while (ei + 1 < P.n && (int)blockIdx.x >= P.e[ei + 1].block_begin) ++ei;
+  const SpreadEntry& E = P.e[ei];
+  if (E.T == 5) spread_tile<5>(P, E, smem);        // the reference trainer's T pyramid {5, 8}
+  else if (E.T == 8) spread_tile<8>(P, E, smem);
+  else spread_tile<0>(P, E, smem);
+}
+
 size_t spread_all_smem(int T) {
-  int TWp = SP_CW * T, IW = TWp + T - 1, IH = 2 * T - 1;
-  return 1024 + ((IH * IW + 15) & ~15) + ((IH * TWp + 15) & ~15) + (size_t)T * TWp;
+  const int IH = 2 * T - 1;
+  return 1024 + (size_t)4 * (IH * sp_nwq(T) + IH * sp_nwo(T) + T * sp_nwo(T));
 }
 
 }  // namespace
@@ -347,7 +444,7 @@ int spread_all_blocks(int W, int H, int* blocks_x) {
 }
 bool launch_spread_all(const SpreadParams& p, int total_blocks, int max_T, cudaStream_t s) {
   size_t smem = spread_all_smem(max_T);
-  if (smem > 48 * 1024) return false;  // T > 32 is rejected earlier; 16 cells x T=32 needs 47.6 KB
+  if (smem > 48 * 1024) return false;  // T <= 16 (checked by the host) needs 41 KB
   k_spread_all<<<total_blocks, 256, smem, s>>>(p);
   return true;
 }

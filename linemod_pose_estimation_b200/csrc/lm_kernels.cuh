@@ -107,7 +107,8 @@ struct SpreadEntry {
   uint8_t* quantized;    // masked quantisation (Detector::match's quantized_images)
   uint8_t* spread;       // parity tap or null
   uint8_t* response;     // parity tap or null
-  uint8_t* lm;           // this modality's 8 orientation planes
+  uint8_t* lm;           // this modality's 8 orientation byte planes, or null (coarsest level when only lm_nib is needed)
+  uint8_t* lm_nib;       // coarsest level: this modality's 8 nibble-packed planes (plane_stride / 2 bytes each), or null
   unsigned long long plane_stride;
   int rows, cols, T, W, H, level, mask_cols0, block_begin, blocks_x;
 };
