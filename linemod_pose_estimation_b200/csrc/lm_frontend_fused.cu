@@ -42,14 +42,31 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 // ---------------------------------------------------------------------------------------------- ColorGradient
-constexpr int C_TW = 64, C_TH = 8;
+// One CTA (320 threads) = a 64 x 16 pixel tile of one pyramid level, halo 5 (blur 3 + Sobel 1 + vote 1).  All stages
+// work on packed data:
+//   A  source tile -> smem as 32-bit words (replicate-extended at the image border)
+//   B  vertical 7-tap blur on byte pairs (u16x2 lanes: 255 * 256 fits), sliding window down a word column
+//   C  horizontal 7-tap blur on the u16 sums, (sum + 2^15) >> 16, written planar (one byte plane per channel)
+//   C' BORDER_REPLICATE of the *smoothed* image for Sobel: out-of-image entries take the value at the clamped coordinate
+//   D  Sobel 3x3 for four pixels at a time on u16x2 lanes, max-magnitude channel, fastAtan2, 16-bin rounding;
+//      every pixel leaves a one-hot vote nibble 1 << 4q
+//   E  3x3 vote = sum of nine nibble words; at most one bin can reach 5 of 9 votes, found with one add + mask + ffs
+constexpr int C_TW = 64, C_TH = 16, C_THREADS = 320;
+constexpr int C_SRC_ROWS = C_TH + 10, C_SRC_WORDS = 57;   // 57 words = 228 bytes >= 1 + 74 * 3
+constexpr int C_V_ROWS = C_TH + 4, C_V_COLS = C_SRC_WORDS * 4;
+constexpr int C_SM_W = 72;                                // smoothed plane row: 68 pixels + pad, 18 words
+constexpr int C_OH_ROWS = C_TH + 2, C_OH_W = 68;
 
-__global__ void __launch_bounds__(256) k_cg_fused(const CgParams P) {
-  __shared__ uint8_t s_in[C_TH + 10][(C_TW + 10) * 3];   // source, halo 5, replicate-extended
-  __shared__ uint16_t s_h[C_TH + 10][(C_TW + 4) * 3];    // horizontal blur pass
-  __shared__ uint8_t s_sm[C_TH + 4][(C_TW + 4) * 3];     // smoothed, halo 2
-  __shared__ uint8_t s_q[C_TH + 2][C_TW + 2];            // unfiltered quantisation, halo 1
-  __shared__ float s_mag[C_TH][C_TW];
+__global__ void __launch_bounds__(C_THREADS) k_cg_fused(const CgParams P) {
+  __shared__ __align__(16) uint32_t s_src[C_SRC_ROWS][C_SRC_WORDS];   // source bytes; pixel x0-5+i, channel c at byte 1+3i+c
+  __shared__ __align__(16) uint16_t s_v[C_V_ROWS][C_V_COLS];         // vertical blur sums, same byte indexing
+  __shared__ __align__(16) uint8_t s_sm[3][C_V_ROWS][C_SM_W];         // smoothed, planar; entry ix <-> x0-2+ix
+  // s_oh / s_mag live in the space of s_src / s_v, which are dead once stage C is done
+  uint32_t (*s_oh)[C_OH_W] = reinterpret_cast<uint32_t (*)[C_OH_W]>(&s_v[0][0]);       // [18][68] vote nibbles, jx <-> x0-1+jx
+  float (*s_mag)[C_TW] = reinterpret_cast<float (*)[C_TW]>(&s_src[0][0]);              // [16][64]
+  static_assert(sizeof(uint32_t) * C_OH_ROWS * C_OH_W <= sizeof(s_v), "s_oh must fit in s_v");
+  static_assert(sizeof(float) * C_TH * C_TW <= sizeof(s_src), "s_mag must fit in s_src");
+
   int lvl = 0;
   while (lvl + 1 < P.n_levels && (int)blockIdx.x >= P.lv[lvl + 1].block_begin) ++lvl;
   const uint8_t* __restrict__ src = P.lv[lvl].src;
@@ -58,84 +75,180 @@ __global__ void __launch_bounds__(256) k_cg_fused(const CgParams P) {
   const int x0 = (b % P.lv[lvl].blocks_x) * C_TW, y0 = (b / P.lv[lvl].blocks_x) * C_TH;
   const int tid = threadIdx.x;
 
-  constexpr int IN_W = (C_TW + 10) * 3;
-  for (int i = tid; i < (C_TH + 10) * IN_W; i += 256) {
-    int r = i / IN_W, rem = i - r * IN_W;
-    int cx = rem / 3, c = rem - cx * 3;
-    int gy = clampi(y0 - 5 + r, 0, rows - 1), gx = clampi(x0 - 5 + cx, 0, cols - 1);
-    s_in[r][rem] = src[((size_t)gy * cols + gx) * 3 + c];
+  // ---- A: source tile
+  if ((cols & 3) == 0 && x0 >= C_TW && x0 + 71 <= cols) {
+    const uint8_t* base = src + (size_t)3 * x0 - 16;  // 4-byte aligned: cols % 4 == 0 and x0 % 64 == 0
+    for (int i = tid; i < C_SRC_ROWS * C_SRC_WORDS; i += C_THREADS) {
+      const int r = i / C_SRC_WORDS, w = i - r * C_SRC_WORDS;
+      const int gy = clampi(y0 - 5 + r, 0, rows - 1);
+      s_src[r][w] = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)gy * cols * 3) + w);
+    }
+  } else {
+    uint8_t* sb = reinterpret_cast<uint8_t*>(&s_src[0][0]);
+    for (int i = tid; i < C_SRC_ROWS * (C_TW + 10); i += C_THREADS) {
+      const int r = i / (C_TW + 10), px = i - r * (C_TW + 10);
+      const int gy = clampi(y0 - 5 + r, 0, rows - 1), gx = clampi(x0 - 5 + px, 0, cols - 1);
+      const uint8_t* g = src + ((size_t)gy * cols + gx) * 3;
+      uint8_t* d = sb + r * (C_SRC_WORDS * 4) + 1 + 3 * px;
+      d[0] = g[0]; d[1] = g[1]; d[2] = g[2];
+    }
   }
   __syncthreads();
-  constexpr int H_W = (C_TW + 4) * 3;
-  for (int i = tid; i < (C_TH + 10) * H_W; i += 256) {
-    int r = i / H_W, e = i - r * H_W;
-    const uint8_t* p = &s_in[r][e];
-    s_h[r][e] = (uint16_t)(8 * (p[0] + p[18]) + 28 * (p[3] + p[15]) + 56 * (p[6] + p[12]) + 72 * p[9]);
-  }
-  __syncthreads();
-  for (int i = tid; i < (C_TH + 4) * H_W; i += 256) {
-    int r = i / H_W, e = i - r * H_W;
-    int s = 8 * ((int)s_h[r][e] + s_h[r + 6][e]) + 28 * ((int)s_h[r + 1][e] + s_h[r + 5][e]) +
-            56 * ((int)s_h[r + 2][e] + s_h[r + 4][e]) + 72 * (int)s_h[r + 3][e];
-    s_sm[r][e] = (uint8_t)((s + 32768) >> 16);
-  }
-  __syncthreads();
-  // Sobel on the smoothed image with BORDER_REPLICATE: out-of-image neighbours read the smoothed value at the clamped
-  // coordinate (which is inside this tile whenever the tile touches the border).
-  for (int i = tid; i < (C_TH + 2) * (C_TW + 2); i += 256) {
-    int r = i / (C_TW + 2), x = i - r * (C_TW + 2);
-    int gy = y0 - 1 + r, gx = x0 - 1 + x;
-    uint8_t q8 = 0;
-    if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) {
-      const int ra = clampi(gy - 1, 0, rows - 1) - (y0 - 2), rb = gy - (y0 - 2), rd = clampi(gy + 1, 0, rows - 1) - (y0 - 2);
-      const int ca = (clampi(gx - 1, 0, cols - 1) - (x0 - 2)) * 3, cb = (gx - (x0 - 2)) * 3,
-                cd = (clampi(gx + 1, 0, cols - 1) - (x0 - 2)) * 3;
-      int m[3], dxs[3], dys[3];
+
+  // ---- B: vertical blur, thread = (word column, group of 5 output rows); output row o uses source rows o .. o+6
+  if (tid < C_SRC_WORDS * 4) {
+    const int w = tid % C_SRC_WORDS, g = tid / C_SRC_WORDS;
+    uint32_t e[11], o[11];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        int aa = s_sm[ra][ca + c], ab = s_sm[ra][cb + c], ad = s_sm[ra][cd + c];
-        int ba = s_sm[rb][ca + c], bd = s_sm[rb][cd + c];
-        int da = s_sm[rd][ca + c], db = s_sm[rd][cb + c], dd = s_sm[rd][cd + c];
-        int dx = (ad + 2 * bd + dd) - (aa + 2 * ba + da);
-        int dy = (da + 2 * db + dd) - (aa + 2 * ab + ad);
-        dxs[c] = dx; dys[c] = dy; m[c] = dx * dx + dy * dy;
-      }
+    for (int k = 0; k < 11; ++k) {
+      const uint32_t v = s_src[5 * g + k][w];
+      e[k] = v & 0x00ff00ffu;
+      o[k] = (v >> 8) & 0x00ff00ffu;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const uint32_t E = 8u * (e[k] + e[k + 6]) + 28u * (e[k + 1] + e[k + 5]) + 56u * (e[k + 2] + e[k + 4]) + 72u * e[k + 3];
+      const uint32_t O = 8u * (o[k] + o[k + 6]) + 28u * (o[k + 1] + o[k + 5]) + 56u * (o[k + 2] + o[k + 4]) + 72u * o[k + 3];
+      uint2 st;
+      st.x = __byte_perm(E, O, 0x5410);  // bytes 4w, 4w+1
+      st.y = __byte_perm(E, O, 0x7632);  // bytes 4w+2, 4w+3
+      *reinterpret_cast<uint2*>(&s_v[5 * g + k][4 * w]) = st;
+    }
+  }
+  __syncthreads();
+
+  // ---- C: horizontal blur, item = (row, channel, run of 4 pixels); smoothed ix uses source pixels ix .. ix+6
+  for (int it = tid; it < C_V_ROWS * 3 * 17; it += C_THREADS) {
+    const int run = it % 17, rc = it / 17;
+    const int c = rc % 3, r = rc / 3;
+    const uint16_t* v = &s_v[r][1 + 12 * run + c];
+    uint32_t t[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) t[k] = v[3 * k];
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t sum = 8u * (t[k] + t[k + 6]) + 28u * (t[k + 1] + t[k + 5]) + 56u * (t[k + 2] + t[k + 4]) + 72u * t[k + 3];
+      out |= ((sum + 32768u) >> 16) << (8 * k);
+    }
+    *reinterpret_cast<uint32_t*>(&s_sm[c][r][4 * run]) = out;
+  }
+  __syncthreads();
+
+  // ---- C': Sobel's BORDER_REPLICATE acts on the smoothed image (only tiles that touch the image border)
+  if (y0 < 2 || y0 + C_TH + 2 > rows || x0 < 2 || x0 + C_TW + 2 > cols) {
+    for (int i = tid; i < 3 * C_V_ROWS * 68; i += C_THREADS) {
+      const int ix = i % 68, rc = i / 68;
+      const int r = rc % C_V_ROWS, c = rc / C_V_ROWS;
+      const int gy = y0 - 2 + r, gx = x0 - 2 + ix;
+      const int cy = clampi(gy, 0, rows - 1), cx = clampi(gx, 0, cols - 1);
+      if (cy != gy || cx != gx) s_sm[c][r][ix] = s_sm[c][cy - (y0 - 2)][cx - (x0 - 2)];  // source entry is in-image: never rewritten
+    }
+    __syncthreads();
+  }
+
+  // ---- D: Sobel + orientation, item = (row jr <-> y0-1+jr, quad q <-> pixels jx = 4q .. 4q+3 <-> x0-1+jx)
+  float mag_keep[4];
+  int keep_r = -1, keep_q = 0;
+  if (tid < C_OH_ROWS * 17) {
+    const int q = tid % 17, jr = tid / 17;
+    int dxs[3][4], dys[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const uint32_t* ra = reinterpret_cast<const uint32_t*>(&s_sm[c][jr][0]) + q;
+      const uint32_t* rb = reinterpret_cast<const uint32_t*>(&s_sm[c][jr + 1][0]) + q;
+      const uint32_t* rc = reinterpret_cast<const uint32_t*>(&s_sm[c][jr + 2][0]) + q;
+      const uint32_t a0 = ra[0], a1 = ra[1], b0 = rb[0], b1 = rb[1], c0 = rc[0], c1 = rc[1];
+      const uint32_t M = 0x00ff00ffu;
+      const uint32_t ae0 = a0 & M, ao0 = (a0 >> 8) & M, ae1 = a1 & M, ao1 = (a1 >> 8) & M;
+      const uint32_t be0 = b0 & M, bo0 = (b0 >> 8) & M, be1 = b1 & M, bo1 = (b1 >> 8) & M;
+      const uint32_t ce0 = c0 & M, co0 = (c0 >> 8) & M, ce1 = c1 & M, co1 = (c1 >> 8) & M;
+      // vertical (1,2,1): s[j] for byte columns 0..5 as u16x2: (s0,s2) (s1,s3) (s4,-) (s5,-)
+      const uint32_t se0 = ae0 + 2u * be0 + ce0, so0 = ao0 + 2u * bo0 + co0;
+      const uint32_t se1 = ae1 + 2u * be1 + ce1, so1 = ao1 + 2u * bo1 + co1;
+      dxs[c][0] = (int)(se0 >> 16) - (int)(se0 & 0xffffu);
+      dxs[c][1] = (int)(so0 >> 16) - (int)(so0 & 0xffffu);
+      dxs[c][2] = (int)(se1 & 0xffffu) - (int)(se0 >> 16);
+      dxs[c][3] = (int)(so1 & 0xffffu) - (int)(so0 >> 16);
+      // horizontal (1,2,1) of the rows above and below: h[j] = r[j] + 2 r[j+1] + r[j+2]
+      const uint32_t ha_e = ae0 + 2u * ao0 + __byte_perm(ae0, ae1, 0x5432);  // (h0, h2)
+      const uint32_t ha_o = ao0 + 2u * __byte_perm(ae0, ae1, 0x5432) + __byte_perm(ao0, ao1, 0x5432);  // (h1, h3)
+      const uint32_t hc_e = ce0 + 2u * co0 + __byte_perm(ce0, ce1, 0x5432);
+      const uint32_t hc_o = co0 + 2u * __byte_perm(ce0, ce1, 0x5432) + __byte_perm(co0, co1, 0x5432);
+      dys[c][0] = (int)(hc_e & 0xffffu) - (int)(ha_e & 0xffffu);
+      dys[c][1] = (int)(hc_o & 0xffffu) - (int)(ha_o & 0xffffu);
+      dys[c][2] = (int)(hc_e >> 16) - (int)(ha_e >> 16);
+      dys[c][3] = (int)(hc_o >> 16) - (int)(ha_o >> 16);
+    }
+    const int gy = y0 - 1 + jr;
+    uint32_t oh[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int gx = x0 - 1 + 4 * q + k;
+      const int m0 = dxs[0][k] * dxs[0][k] + dys[0][k] * dys[0][k];
+      const int m1 = dxs[1][k] * dxs[1][k] + dys[1][k] * dys[1][k];
+      const int m2 = dxs[2][k] * dxs[2][k] + dys[2][k] * dys[2][k];
       int bm, bdx, bdy;
-      if (m[0] >= m[1] && m[0] >= m[2]) { bm = m[0]; bdx = dxs[0]; bdy = dys[0]; }
-      else if (m[1] >= m[0] && m[1] >= m[2]) { bm = m[1]; bdx = dxs[1]; bdy = dys[1]; }
-      else { bm = m[2]; bdx = dxs[2]; bdy = dys[2]; }
-      float angle = fast_atan2_deg((float)bdy, (float)bdx);
-      int q = clampi(__float2int_rn(__fmul_rn(angle, (float)(16.0 / 360.0))), 0, 255);
-      const bool border = gy == 0 || gy == rows - 1 || gx == 0 || gx == cols - 1;
-      q8 = border ? 0 : (uint8_t)(q & 7);
-      if (r >= 1 && r <= C_TH && x >= 1 && x <= C_TW) {
-        s_mag[r - 1][x - 1] = (float)bm;
-        P.lv[lvl].mag[(size_t)gy * cols + gx] = (float)bm;
+      if (m0 >= m1 && m0 >= m2) { bm = m0; bdx = dxs[0][k]; bdy = dys[0][k]; }
+      else if (m1 >= m0 && m1 >= m2) { bm = m1; bdx = dxs[1][k]; bdy = dys[1][k]; }
+      else { bm = m2; bdx = dxs[2][k]; bdy = dys[2][k]; }
+      const float angle = fast_atan2_deg((float)bdy, (float)bdx);
+      const int qq = clampi(__float2int_rn(__fmul_rn(angle, (float)(16.0 / 360.0))), 0, 255) & 7;
+      const bool border = gy <= 0 || gy >= rows - 1 || gx <= 0 || gx >= cols - 1;  // [OCV] first / last row and column are zeroed
+      oh[k] = border ? 1u : (1u << (4 * qq));
+      mag_keep[k] = (float)bm;
+    }
+    *reinterpret_cast<uint4*>(&s_oh[jr][4 * q]) = make_uint4(oh[0], oh[1], oh[2], oh[3]);  // s_v is dead: every thread passed stage C
+    keep_r = jr; keep_q = q;
+  }
+  // magnitudes of the tile's own pixels: to global memory (addTemplate reads them) and to s_mag (aliases s_src, dead)
+  if (keep_r >= 1 && keep_r <= C_TH) {
+    const int gy = y0 + keep_r - 1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int jx = 4 * keep_q + k;
+      const int gx = x0 - 1 + jx;
+      if (jx >= 1 && jx <= C_TW) {
+        s_mag[keep_r - 1][jx - 1] = mag_keep[k];
+        if (gy < rows && gx < cols) P.lv[lvl].mag[(size_t)gy * cols + gx] = mag_keep[k];
       }
     }
-    s_q[r][x] = q8;
   }
   __syncthreads();
-  for (int i = tid; i < C_TH * C_TW; i += 256) {
-    int r = i / C_TW, x = i - r * C_TW;
-    int gy = y0 + r, gx = x0 + x;
-    if (gy >= rows || gx >= cols) continue;
-    uint8_t out = 0;
-    if (gy >= 1 && gy < rows - 1 && gx >= 1 && gx < cols - 1 && s_mag[r][x] > P.thr_sq) {
-      unsigned hist = 0;
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) hist += 1u << (4 * s_q[r + j][x + k]);
-      int max_votes = 0, index = -1;
-#pragma unroll
-      for (int bb = 0; bb < 8; ++bb) {
-        int v = (hist >> (4 * bb)) & 15;
-        if (max_votes < v) { index = bb; max_votes = v; }
-      }
-      if (max_votes >= 5) out = (uint8_t)(1 << index);
+
+  // ---- E: hysteresis vote, thread = four consecutive pixels of a row
+  if (tid < C_TH * (C_TW / 4)) {
+    const int eq = tid % (C_TW / 4), er = tid / (C_TW / 4);
+    const int gy = y0 + er, gx0 = x0 + 4 * eq;
+    uint32_t cs[6];
+    {
+      const uint4 r0 = *reinterpret_cast<const uint4*>(&s_oh[er][4 * eq]);
+      const uint4 r1 = *reinterpret_cast<const uint4*>(&s_oh[er + 1][4 * eq]);
+      const uint4 r2 = *reinterpret_cast<const uint4*>(&s_oh[er + 2][4 * eq]);
+      const uint2 t0 = *reinterpret_cast<const uint2*>(&s_oh[er][4 * eq + 4]);
+      const uint2 t1 = *reinterpret_cast<const uint2*>(&s_oh[er + 1][4 * eq + 4]);
+      const uint2 t2 = *reinterpret_cast<const uint2*>(&s_oh[er + 2][4 * eq + 4]);
+      cs[0] = r0.x + r1.x + r2.x; cs[1] = r0.y + r1.y + r2.y; cs[2] = r0.z + r1.z + r2.z; cs[3] = r0.w + r1.w + r2.w;
+      cs[4] = t0.x + t1.x + t2.x; cs[5] = t0.y + t1.y + t2.y;
     }
-    P.lv[lvl].quant[(size_t)gy * cols + gx] = out;
+    const float4 mg = *reinterpret_cast<const float4*>(&s_mag[er][4 * eq]);
+    const float mags[4] = {mg.x, mg.y, mg.z, mg.w};
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int gx = gx0 + k;
+      const uint32_t hist = cs[k] + cs[k + 1] + cs[k + 2];             // nine 4-bit vote counters
+      const uint32_t five = (hist + 0x33333333u) & 0x88888888u;        // counters >= 5: at most one (9 votes in all)
+      const bool inner = gy >= 1 && gy < rows - 1 && gx >= 1 && gx < cols - 1;
+      if (inner && mags[k] > P.thr_sq && five != 0) packed |= (1u << ((__ffs((int)five) - 1) >> 2)) << (8 * k);
+    }
+    uint8_t* qrow = P.lv[lvl].quant + (size_t)gy * cols;
+    if (gy < rows) {
+      if ((cols & 3) == 0 && gx0 + 3 < cols) *reinterpret_cast<uint32_t*>(qrow + gx0) = packed;
+      else
+        for (int k = 0; k < 4; ++k)
+          if (gx0 + k < cols) qrow[gx0 + k] = (uint8_t)(packed >> (8 * k));
+    }
   }
 }
 
@@ -432,7 +545,7 @@ int cg_fused_blocks(int rows, int cols, int* blocks_x) {
   return *blocks_x * ((rows + C_TH - 1) / C_TH);
 }
 void launch_cg_fused(const CgParams& p, int total_blocks, cudaStream_t s) {
-  k_cg_fused<<<total_blocks, 256, 0, s>>>(p);
+  k_cg_fused<<<total_blocks, C_THREADS, 0, s>>>(p);
 }
 void launch_dn_fused(const DnParams& p, cudaStream_t s) {
   dim3 grid((p.cols + D_TW - 1) / D_TW, (p.rows + D_TH - 1) / D_TH);
