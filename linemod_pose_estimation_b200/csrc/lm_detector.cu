@@ -85,6 +85,9 @@ static const size_t kLmSlack = 8192;  // tail slack: vector loads of partially f
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // modalities quantise concurrently: modality m > 0 runs on side[m-1], forked from / joined into the frame's stream
+  cudaStream_t side[LM_MAX_MODALITIES - 1] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[LM_MAX_MODALITIES - 1] = {nullptr, nullptr, nullptr};
   int rows = 0, cols = 0;     // geometry of the quantisation workspace
   bool lm_ready = false;      // LM buffers sized + zero-tailed for (rows, cols)
   bool front_valid = false;
@@ -118,6 +121,11 @@ struct Lane {
   int init() {
     CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (int i = 0; i < 6; ++i) CU(cudaEventCreate(&ev[i]));
+    CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < LM_MAX_MODALITIES - 1; ++i) {
+      CU(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
+    }
     return LM_OK;
   }
   void destroy() {
@@ -133,6 +141,11 @@ struct Lane {
     cand.release(); result.release(); work.release(); work_order.release(); dump.release(); dbg_recs.release();
     stage_in.release(); stage_out.release();
     for (int i = 0; i < 6; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    for (int i = 0; i < LM_MAX_MODALITIES - 1; ++i) {
+      if (ev_join[i]) cudaEventDestroy(ev_join[i]);
+      if (side[i]) cudaStreamDestroy(side[i]);
+    }
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -405,11 +418,14 @@ static int run_quantize_staged(lm_detector* d, Lane& ln, cudaStream_t s) {
 
 // Production path (lm_frontend_fused.cu): per ColorGradient modality the pyrDown chain plus ONE launch covering every
 // level, per DepthNormal modality ONE launch.
-static int run_quantize(lm_detector* d, Lane& ln, cudaStream_t s) {
-  if (d->frontend_variant == 1) return run_quantize_staged(d, ln, s);
+static int run_quantize(lm_detector* d, Lane& ln, cudaStream_t main_stream) {
+  if (d->frontend_variant == 1) return run_quantize_staged(d, ln, main_stream);
   const int L = d->model.levels(), M = d->model.M();
+  if (M > 1) CU(cudaEventRecord(ln.ev_fork, main_stream));
   for (int m = 0; m < M; ++m) {
     const lm_modality_desc& md = d->model.mods[m];
+    cudaStream_t s = m == 0 ? main_stream : ln.side[m - 1];
+    if (m > 0) CU(cudaStreamWaitEvent(s, ln.ev_fork, 0));
     if (md.type == LM_COLOR_GRADIENT) {
       CgParams cp;
       std::memset(&cp, 0, sizeof(cp));
@@ -420,7 +436,7 @@ static int run_quantize(lm_detector* d, Lane& ln, cudaStream_t s) {
         const int rows = ln.rows >> l, cols = ln.cols >> l;
         if (l > 0) {
           const uint8_t* prev = l == 1 ? (const uint8_t*)ln.src_ptr[m] : ln.bgr[l - 1][m].as<uint8_t>();
-          launch_pyrdown_u8c3(prev, ln.rows >> (l - 1), ln.cols >> (l - 1), ln.bgr[l][m].as<uint8_t>(), s);
+          launch_pyrdown_fast(prev, ln.rows >> (l - 1), ln.cols >> (l - 1), ln.bgr[l][m].as<uint8_t>(), s);
           ++ln.launches;
         }
         CgLevel& lv = cp.lv[l];
@@ -442,6 +458,10 @@ static int run_quantize(lm_detector* d, Lane& ln, cudaStream_t s) {
       for (int l = 0; l < L; ++l) dp.quant[l] = ln.quant_raw[l][m].as<uint8_t>();
       launch_dn_fused(dp, s);
       ++ln.launches;
+    }
+    if (m > 0) {
+      CU(cudaEventRecord(ln.ev_join[m - 1], s));
+      CU(cudaStreamWaitEvent(main_stream, ln.ev_join[m - 1], 0));
     }
   }
   CU(cudaGetLastError());

@@ -12,6 +12,8 @@
 // Arithmetic is identical to the stage-by-stage kernels in lm_frontend.cu (kept as the A/B reference).
 #include <float.h>
 
+#include <type_traits>
+
 #include "lm_kernels.cuh"
 #include "lm_median_net.h"
 
@@ -252,43 +254,135 @@ __global__ void __launch_bounds__(C_THREADS) k_cg_fused(const CgParams P) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------- pyrDown (BGR)
+// [OCV] ColorGradientPyramid::pyrDown -> cv::pyrDown: 5x5 (1 4 6 4 1)^2, reflect-101, even samples, (sum + 128) >> 8.
+// 64 x 8 output pixels per CTA: source region to smem as words (reflected at the image border), vertical taps on
+// byte pairs (u16x2 lanes, 16 * 255 fits), horizontal taps on the u16 sums.
+constexpr int Y_TW = 64, Y_TH = 8;
+constexpr int Y_SRC_ROWS = 2 * Y_TH + 3, Y_SRC_WORDS = 99;  // 99 words = 396 bytes >= 2 + 131 * 3
+
+__device__ __forceinline__ int reflect101_f(int p, int len) {
+  if (len == 1) return 0;
+  while (p < 0 || p >= len) p = (p < 0) ? -p : 2 * len - 2 - p;
+  return p;
+}
+
+__global__ void __launch_bounds__(256) k_pyrdown_fast(const uint8_t* __restrict__ src, int rows, int cols,
+                                                      uint8_t* __restrict__ dst) {
+  __shared__ __align__(16) uint32_t s_src[Y_SRC_ROWS][Y_SRC_WORDS];   // region pixel i <-> source x 2*x0-2+i, channel c at byte 2+3i+c
+  __shared__ __align__(16) uint16_t s_v[Y_TH][Y_SRC_WORDS * 4];
+  const int orows = rows / 2, ocols = cols / 2;
+  const int x0 = blockIdx.x * Y_TW, y0 = blockIdx.y * Y_TH;
+  const int tid = threadIdx.x;
+  if ((cols & 3) == 0 && x0 >= Y_TW && 2 * x0 + 130 <= cols) {
+    const uint8_t* base = src + (size_t)6 * x0 - 8;  // 4-byte aligned
+    for (int i = tid; i < Y_SRC_ROWS * Y_SRC_WORDS; i += 256) {
+      const int r = i / Y_SRC_WORDS, w = i - r * Y_SRC_WORDS;
+      const int gy = reflect101_f(2 * y0 - 2 + r, rows);
+      s_src[r][w] = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)gy * cols * 3) + w);
+    }
+  } else {
+    uint8_t* sb = reinterpret_cast<uint8_t*>(&s_src[0][0]);
+    for (int i = tid; i < Y_SRC_ROWS * 131; i += 256) {
+      const int r = i / 131, px = i - r * 131;
+      const int gy = reflect101_f(2 * y0 - 2 + r, rows), gx = reflect101_f(2 * x0 - 2 + px, cols);
+      const uint8_t* g = src + ((size_t)gy * cols + gx) * 3;
+      uint8_t* d = sb + r * (Y_SRC_WORDS * 4) + 2 + 3 * px;
+      d[0] = g[0]; d[1] = g[1]; d[2] = g[2];
+    }
+  }
+  __syncthreads();
+  // vertical taps: output row oy uses region rows 2*oy .. 2*oy+4; thread = (word column, group of 4 output rows)
+  if (tid < Y_SRC_WORDS * 2) {
+    const int w = tid % Y_SRC_WORDS, g = tid / Y_SRC_WORDS;
+    uint32_t e[11], o[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      const uint32_t v = s_src[8 * g + k][w];
+      e[k] = v & 0x00ff00ffu;
+      o[k] = (v >> 8) & 0x00ff00ffu;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t E = (e[2 * k] + e[2 * k + 4]) + 4u * (e[2 * k + 1] + e[2 * k + 3]) + 6u * e[2 * k + 2];
+      const uint32_t O = (o[2 * k] + o[2 * k + 4]) + 4u * (o[2 * k + 1] + o[2 * k + 3]) + 6u * o[2 * k + 2];
+      uint2 st;
+      st.x = __byte_perm(E, O, 0x5410);
+      st.y = __byte_perm(E, O, 0x7632);
+      *reinterpret_cast<uint2*>(&s_v[4 * g + k][4 * w]) = st;
+    }
+  }
+  __syncthreads();
+  // horizontal taps: output ox uses region pixels 2*ox .. 2*ox+4; item = (row, channel, run of 4 output pixels)
+  for (int it = tid; it < Y_TH * 3 * 16; it += 256) {
+    const int run = it & 15, rc = it >> 4;
+    const int c = rc % 3, oy = rc / 3;
+    const int gy = y0 + oy;
+    if (gy >= orows) continue;
+    const uint16_t* v = &s_v[oy][2 + 24 * run + c];
+    uint32_t t[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) t[k] = v[3 * k];
+    uint8_t* out = dst + ((size_t)gy * ocols + x0 + 4 * run) * 3 + c;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t sum = (t[2 * k] + t[2 * k + 4]) + 4u * (t[2 * k + 1] + t[2 * k + 3]) + 6u * t[2 * k + 2];
+      if (x0 + 4 * run + k < ocols) out[3 * k] = (uint8_t)((sum + 128u) >> 8);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- DepthNormal
+// [OCV] quantizedNormals accumulates the 2x2 normal equations in `long`.  With difference_threshold <= 200 (default
+// 50) every intermediate fits 32 bits -- |b| <= 30 * 199, A <= 150, |1150 * ddx| <= 1150 * 250 * 5970 < 2^31,
+// det * d <= 22500 * 65535 < 2^31 -- so FAST evaluates the same integers in int32 (identical values, identical
+// int -> float conversions); larger thresholds take the 64-bit path.
+template <bool FAST>
 __device__ __forceinline__ uint8_t dn_normal_at(const uint16_t* __restrict__ depth, int rows, int cols, int y, int x,
                                                 int distance_threshold, int difference_threshold,
                                                 const uint8_t* __restrict__ lut) {
+  typedef typename std::conditional<FAST, int, long long>::type acc_t;
   const int r = 5;
   if (!(y >= r && y < rows - r - 1 && x >= r && x < cols - r - 1)) return 0;
-  long long d = depth[(size_t)y * cols + x];
+  const uint16_t* pc = depth + (size_t)y * cols + x;
+  const int d = pc[0];
   if (!(d < distance_threshold)) return 0;
-  long long A0 = 0, A1 = 0, A3 = 0, b0 = 0, b1 = 0;
+  acc_t A0 = 0, A1 = 0, A3 = 0, b0 = 0, b1 = 0;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int kk = k < 4 ? k : k + 1;
     const int i = (kk % 3 - 1) * r, j = (kk / 3 - 1) * r;
-    long long delta = (long long)depth[(size_t)(y + j) * cols + (x + i)] - d;
-    long long f = (delta < 0 ? -delta : delta) < difference_threshold ? 1 : 0;
-    long long fi = f * i, fj = f * j;
-    A0 += fi * i; A1 += fi * j; A3 += fj * j;
-    b0 += fi * delta; b1 += fj * delta;
+    const int delta = (int)pc[j * cols + i] - d;
+    if (abs(delta) < difference_threshold) {
+      A0 += i * i; A1 += i * j; A3 += j * j;
+      b0 += (acc_t)(i * delta); b1 += (acc_t)(j * delta);
+    }
   }
-  long long det = A0 * A3 - A1 * A1;
-  long long ddx = A3 * b0 - A1 * b1;
-  long long ddy = -A1 * b0 + A0 * b1;
-  float nx = __ll2float_rn(1150 * ddx);
-  float ny = __ll2float_rn(1150 * ddy);
-  float nz = __ll2float_rn(-det * d);
-  float s = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz)));
+  const acc_t det = A0 * A3 - A1 * A1;
+  const acc_t ddx = A3 * b0 - A1 * b1;
+  const acc_t ddy = -A1 * b0 + A0 * b1;
+  float nx, ny, nz;
+  if (FAST) {
+    nx = __int2float_rn((int)(1150 * ddx));
+    ny = __int2float_rn((int)(1150 * ddy));
+    nz = __int2float_rn((int)(-det * d));
+  } else {
+    nx = __ll2float_rn((long long)(1150 * ddx));
+    ny = __ll2float_rn((long long)(1150 * ddy));
+    nz = __ll2float_rn((long long)(-det * d));
+  }
+  const float s = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz)));
   if (!(s > 0)) return 0;
-  float inv = __fdiv_rn(1.0f, s);
+  const float inv = __fdiv_rn(1.0f, s);
   nx = __fmul_rn(nx, inv); ny = __fmul_rn(ny, inv); nz = __fmul_rn(nz, inv);
-  int v1 = __float2int_rz(__fadd_rn(__fmul_rn(nx, 10.0f), 10.0f));
-  int v2 = __float2int_rz(__fadd_rn(__fmul_rn(ny, 10.0f), 10.0f));
-  int v3 = __float2int_rz(__fadd_rn(__fmul_rn(nz, 20.0f), 20.0f));
-  int flat = (v3 * 20 + v2) * 20 + v1;
+  const int v1 = __float2int_rz(__fadd_rn(__fmul_rn(nx, 10.0f), 10.0f));
+  const int v2 = __float2int_rz(__fadd_rn(__fmul_rn(ny, 10.0f), 10.0f));
+  const int v3 = __float2int_rz(__fadd_rn(__fmul_rn(nz, 20.0f), 20.0f));
+  const int flat = (v3 * 20 + v2) * 20 + v1;
   return (flat >= 0 && flat < 8000) ? lut[flat] : (uint8_t)0;
 }
 
-constexpr int D_TW = 64, D_TH = 8;
+constexpr int D_TW = 64, D_TH = 16;
 
 __device__ __forceinline__ void cswap_u16x2(uint32_t& a, uint32_t& b) {
   uint32_t lo, hi;
@@ -297,47 +391,62 @@ __device__ __forceinline__ void cswap_u16x2(uint32_t& a, uint32_t& b) {
   a = lo; b = hi;
 }
 
-__global__ void __launch_bounds__(256) k_dn_fused(const DnParams P) {
-  __shared__ uint8_t s_raw[D_TH + 4][D_TW + 4 + 4];
+template <bool FAST>
+__device__ __forceinline__ void dn_tile(const DnParams& P, int bx, int by) {
+  __shared__ __align__(4) uint8_t s_raw[D_TH + 4][D_TW + 8];
   const int rows = P.rows, cols = P.cols;
-  const int x0 = blockIdx.x * D_TW, y0 = blockIdx.y * D_TH;
+  const int x0 = bx * D_TW, y0 = by * D_TH;
   const int tid = threadIdx.x;
   // raw quantised normals for the tile + halo 2; medianBlur's BORDER_REPLICATE = value at the clamped coordinate
   for (int i = tid; i < (D_TH + 4) * (D_TW + 4); i += 256) {
-    int r = i / (D_TW + 4), c = i - r * (D_TW + 4);
-    int gy = clampi(y0 - 2 + r, 0, rows - 1), gx = clampi(x0 - 2 + c, 0, cols - 1);
-    s_raw[r][c] = dn_normal_at(P.depth, rows, cols, gy, gx, P.distance_threshold, P.difference_threshold, P.lut);
+    const int r = i / (D_TW + 4), c = i - r * (D_TW + 4);
+    const int gy = clampi(y0 - 2 + r, 0, rows - 1), gx = clampi(x0 - 2 + c, 0, cols - 1);
+    s_raw[r][c] = dn_normal_at<FAST>(P.depth, rows, cols, gy, gx, P.distance_threshold, P.difference_threshold, P.lut);
   }
   __syncthreads();
   // median of 25 for two horizontally adjacent pixels at once (one per 16-bit lane)
-  const int r = tid >> 5, c = (tid & 31) * 2;
-  uint32_t p[25];
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    const int r = (tid >> 5) + 8 * half, c = (tid & 31) * 2;
+    uint32_t p[25];
 #pragma unroll
-  for (int dy = 0; dy < 5; ++dy) {
-    uint32_t b[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) b[k] = s_raw[r + dy][c + k];
-#pragma unroll
-    for (int dx = 0; dx < 5; ++dx) p[dy * 5 + dx] = b[dx] | (b[dx + 1] << 16);
-  }
+    for (int dy = 0; dy < 5; ++dy) {
+      // six consecutive bytes starting at an even column: three aligned 16-bit loads
+      const uint16_t* row = reinterpret_cast<const uint16_t*>(&s_raw[r + dy][c]);
+      const uint32_t h0 = row[0], h1 = row[1], h2 = row[2];
+      const uint32_t b0 = h0 & 255u, b1 = h0 >> 8, b2 = h1 & 255u, b3 = h1 >> 8, b4 = h2 & 255u, b5 = h2 >> 8;
+      p[dy * 5 + 0] = b0 | (b1 << 16);
+      p[dy * 5 + 1] = b1 | (b2 << 16);
+      p[dy * 5 + 2] = b2 | (b3 << 16);
+      p[dy * 5 + 3] = b3 | (b4 << 16);
+      p[dy * 5 + 4] = b4 | (b5 << 16);
+    }
 #define LM_CSWAP(a, b) cswap_u16x2(p[a], p[b]);
-  LM_MEDIAN25_NET(LM_CSWAP)
+    LM_MEDIAN25_NET(LM_CSWAP)
 #undef LM_CSWAP
-  const uint32_t med = p[12];
+    const uint32_t med = p[12];
+    const int gy = y0 + r;
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int gy = y0 + r, gx = x0 + c + k;
-    if (gy >= rows || gx >= cols) continue;
-    const uint8_t v = (uint8_t)(k ? (med >> 16) : (med & 0xffffu));
-    P.quant[0][(size_t)gy * cols + gx] = v;
-    // [OCV] DepthNormalPyramid::pyrDown: level l is the NN decimation src(2^l y, 2^l x) of the level-0 map
-    for (int l = 1; l < P.n_levels; ++l) {
-      const int mask = (1 << l) - 1;
-      if ((gy & mask) || (gx & mask)) break;
-      const int lr = rows >> l, lc = cols >> l;
-      if ((gy >> l) < lr && (gx >> l) < lc) P.quant[l][(size_t)(gy >> l) * lc + (gx >> l)] = v;
+    for (int k = 0; k < 2; ++k) {
+      const int gx = x0 + c + k;
+      if (gy >= rows || gx >= cols) continue;
+      const uint8_t v = (uint8_t)(k ? (med >> 16) : (med & 0xffffu));
+      P.quant[0][(size_t)gy * cols + gx] = v;
+      // [OCV] DepthNormalPyramid::pyrDown: level l is the NN decimation src(2^l y, 2^l x) of the level-0 map
+#pragma unroll
+      for (int l = 1; l < LM_MAX_LEVELS; ++l) {
+        const int mask = (1 << l) - 1;
+        if (l >= P.n_levels || (gy & mask) || (gx & mask)) break;
+        const int lr = rows >> l, lc = cols >> l;
+        if ((gy >> l) < lr && (gx >> l) < lc) P.quant[l][(size_t)(gy >> l) * lc + (gx >> l)] = v;
+      }
     }
   }
+}
+
+__global__ void __launch_bounds__(256) k_dn_fused(const DnParams P) {
+  if (P.difference_threshold <= 200) dn_tile<true>(P, blockIdx.x, blockIdx.y);
+  else dn_tile<false>(P, blockIdx.x, blockIdx.y);
 }
 
 // ---------------------------------------------------------------------------------------------- spread -> LM
@@ -550,6 +659,10 @@ void launch_cg_fused(const CgParams& p, int total_blocks, cudaStream_t s) {
 void launch_dn_fused(const DnParams& p, cudaStream_t s) {
   dim3 grid((p.cols + D_TW - 1) / D_TW, (p.rows + D_TH - 1) / D_TH);
   k_dn_fused<<<grid, 256, 0, s>>>(p);
+}
+void launch_pyrdown_fast(const uint8_t* src, int rows, int cols, uint8_t* dst, cudaStream_t s) {
+  dim3 grid((cols / 2 + Y_TW - 1) / Y_TW, (rows / 2 + Y_TH - 1) / Y_TH);
+  k_pyrdown_fast<<<grid, 256, 0, s>>>(src, rows, cols, dst);
 }
 int spread_all_blocks(int W, int H, int* blocks_x) {
   *blocks_x = (W + SP_CW - 1) / SP_CW;

@@ -117,6 +117,7 @@ struct SpreadParams {
   const uint32_t* resp_all;
   int n;
 };
+void launch_pyrdown_fast(const uint8_t* src, int rows, int cols, uint8_t* dst, cudaStream_t s);
 int cg_fused_blocks(int rows, int cols, int* blocks_x);
 void launch_cg_fused(const CgParams& p, int total_blocks, cudaStream_t s);
 void launch_dn_fused(const DnParams& p, cudaStream_t s);
