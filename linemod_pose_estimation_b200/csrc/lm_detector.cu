@@ -681,7 +681,7 @@ static int build_tile_records(const Pack& pk, const std::vector<WorkItem>& items
       r[8 + m] = c4;
     }
     r[0] = tiles[t].x; r[1] = it.tglob; r[2] = (ct.nf & 0x0fffffffu) | (it.order & 0xf0000000u); r[3] = (uint32_t)n;
-    r[4] = (uint32_t)j0; r[5] = (uint32_t)std::min(pass_pos, ct.P - j0);
+    r[4] = (uint32_t)j0; r[5] = (uint32_t)std::min(pass_pos, ct.P - j0); r[6] = it.order;
     for (int f = 0; f < n; ++f) {
       const uint32_t a = pk.h_foff[ct.feat_begin + f] + (uint32_t)j0;  // nibble index of lane 0's window
       r[hdr + f] = ((a >> 1) & ~15u) | (a & 7u);

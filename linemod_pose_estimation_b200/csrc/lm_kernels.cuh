@@ -58,7 +58,9 @@ struct WorkItem {                         // one template of one query of the re
 };
 
 struct Cand {                             // coarse candidate: raw score above the template's raw threshold
-  uint32_t tglob, pos, raw, item;
+  uint32_t tglob, pos;                    // template index in the pack, raster position at the coarsest level
+  uint32_t raw_nf;                        // raw score (u16) | number of features behind it << 16
+  uint32_t order;                         // the work item's emission order key (query << 28 | position in the iteration)
 };
 
 struct ResultHeader {                     // zeroed before every request
@@ -134,7 +136,7 @@ bool launch_spread_all(const SpreadParams& p, int total_blocks, int max_T, cudaS
 //
 // Tile record of variant 0 (rec_words 32-bit words each, 16-byte aligned):
 //   [0] work item  [1] template index in the pack  [2] nf | query << 28  [3] number of feature words
-//   [4] j0 = first position of the pass  [5] positions in the pass  [6..7] 0  [8..11] per modality: 4 class sizes, u8 each
+//   [4] j0 = first position of the pass  [5] positions in the pass  [6] the item's order key  [7] 0  [8..11] per modality: 4 class sizes, u8 each
 //   [12..] feature words, modality-major, grouped by class Q = (a >> 3) & 3 where a = nibble index of the window of
 //   lane 0: ((a >> 1) & ~15) | (a & 7)  -- aligned chunk byte offset | nibble shift
 int coarse_positions_per_pass(int variant);

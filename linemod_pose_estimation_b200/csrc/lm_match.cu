@@ -10,6 +10,8 @@
 // 128-bit loads.  Responses are <= 4 and a template has <= 63 features per modality, so four byte lanes packed in
 // a 32-bit register never carry into each other: plain integer adds are bit-identical to the reference's
 // _mm_add_epi8 (and to __vaddus4) at a quarter of the instruction count.
+#include <string.h>
+
 #include "lm_kernels.cuh"
 
 namespace lmk {
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(256) k_similarity_coarse(const uint8_t* __rest
               uint32_t idx = atomicAdd(&hdr->n_cands, 1u);
               if (idx < cand_cap) {
                 Cand c;
-                c.tglob = tg; c.pos = (uint32_t)(j0 + p); c.raw = (uint32_t)raw; c.item = item;
+                c.tglob = tg; c.pos = (uint32_t)(j0 + p); c.raw_nf = (uint32_t)raw | (t_nf << 16); c.order = wi.order;
                 cand[idx] = c;
               }
             }
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(256) k_similarity_coarse_nib(const uint8_t* __
                 uint32_t idx = atomicAdd(&hdr->n_cands, 1u);
                 if (idx < cand_cap) {
                   Cand c;
-                  c.tglob = tg; c.pos = (uint32_t)(j0 + p); c.raw = (uint32_t)raw; c.item = item;
+                  c.tglob = tg; c.pos = (uint32_t)(j0 + p); c.raw_nf = (uint32_t)raw | (ct->nf << 16); c.order = wi.order;
                   cand[idx] = c;
                 }
               }
@@ -456,6 +458,8 @@ __global__ void __launch_bounds__(256, 3) k_similarity_coarse_rec(const uint8_t*
   __shared__ uint32_t s_rec[8][kRecMaxWords];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* sr = s_rec[warp];
+  cudaGridDependencySynchronize();            // linear memories (previous kernel in the stream) are complete
+  cudaTriggerProgrammaticLaunchCompletion();  // let k_refine's blocks be scheduled as this grid drains
   auto draw = [&]() -> uint32_t {
     uint32_t t = 0;
     if (lane == 0) t = atomicAdd(&hdr->next_tile, 1u);
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(256, 3) k_similarity_coarse_rec(const uint8_t*
     }
     const uint32_t nxt2 = has_next ? draw() : nxt;
 
-    const uint32_t item = sr[0], tg = sr[1], nfq = sr[2];
+    const uint32_t item = sr[0], tg = sr[1], nfq = sr[2], order = sr[6];
     const int n_feat = (int)sr[3], j0 = (int)sr[4], rem = (int)sr[5];
     const bool active = first < rem;
     // [OCV] matchClass: raw_threshold = (int)(2*nf + (threshold / 100.f) * (2*nf) + 0.5f), same f32 roundings
@@ -538,7 +542,7 @@ __global__ void __launch_bounds__(256, 3) k_similarity_coarse_rec(const uint8_t*
                 uint32_t idx = atomicAdd(&hdr->n_cands, 1u);
                 if (idx < cand_cap) {
                   Cand c;
-                  c.tglob = tg; c.pos = (uint32_t)(j0 + p); c.raw = (uint32_t)raw; c.item = item;
+                  c.tglob = tg; c.pos = (uint32_t)(j0 + p); c.raw_nf = (uint32_t)raw | ((nfq & 0xffffu) << 16); c.order = order;
                   cand[idx] = c;
                 }
               }
@@ -575,11 +579,14 @@ __global__ void __launch_bounds__(256) k_pack_nibbles(const uint4* __restrict__ 
 }
 
 // Local refinement of every coarse candidate up the pyramid.  One 8-warp block per candidate: the 16 x 16 patch is
-// mapped lane -> (row = lane / 2, 8 columns = lane % 2) in every warp, the template's features are dealt round-robin
-// to the warps (each keeps its own u8 accumulators), and the per-warp u16 partial sums meet in shared memory.
-// Features that fall outside the image after the shift are redirected to a zero byte run instead of being skipped, so
-// that a warp's loads stay independent and overlap.
+// mapped lane -> (row = lane / 2, 8 columns = lane % 2) in every warp and the template's features are dealt round-robin
+// to the warps.  Per level the block first turns the template's features into linear-memory byte offsets in shared
+// memory (one thread per feature: shift by the patch origin, bounds test, phase/cell split); then every warp issues the
+// window loads of all its features of a modality back to back (<= 8 features, 24 loads in flight per lane) before it
+// adds them up, so a candidate costs two load latencies per modality instead of a dependent chain per feature.
+// Features that fall outside the image after the shift are redirected to a zero byte run instead of being skipped.
 constexpr int kRefineWarps = 8;
+constexpr int kRefineMaxFeat = LM_MAX_MODALITIES * 64;
 
 __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams P, const CoarseTpl* __restrict__ ctpl,
                                                              const WorkItem* __restrict__ items,
@@ -587,20 +594,22 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams
                                                              ResultHeader* hdr, lm_raw_match* __restrict__ out,
                                                              uint32_t out_cap) {
   __shared__ uint32_t s_part[kRefineWarps][32][4];
-  __shared__ int s_state[4];  // x, y, alive, best_score
+  __shared__ uint32_t s_addr[kRefineMaxFeat];  // byte offset of the feature's patch origin inside its modality's planes
+  __shared__ int s_state[4];                   // x, y, alive, best_score
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  cudaGridDependencySynchronize();  // programmatic dependent launch: the coarse kernel's candidates are complete from here on
   const uint32_t n_cands = min(hdr->n_cands, cand_cap);
   if (blockIdx.x == 0 && threadIdx.x == 0 && hdr->n_cands > cand_cap) hdr->overflow = 1;  // candidate list truncated
   const int prow = lane >> 1, pcol0 = (lane & 1) * 8;
   for (uint32_t ci = blockIdx.x; ci < n_cands; ci += gridDim.x) {
     const Cand c = cand[ci];
-    const uint32_t order = items[c.item].order;
+    const uint32_t order = c.order;
     const float threshold = P.threshold[order >> 28];
     const int cT = P.coarse_T;
     const int coff = cT / 2 + (cT % 2 - 1);
     int x = (int)(c.pos % (uint32_t)P.coarse_W) * cT + coff;
     int y = (int)(c.pos / (uint32_t)P.coarse_W) * cT + coff;
-    uint32_t score = c.raw, nf = ctpl[c.tglob].nf;
+    uint32_t score = c.raw_nf & 0xffffu, nf = c.raw_nf >> 16;
     bool alive = true;
     for (int l = P.levels - 2; l >= 0 && alive; --l) {
       const RefineLevel& L = P.level[l];
@@ -612,30 +621,45 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams
       x = max(x, border); y = max(y, border);
       x = min(x, max_x); y = min(y, max_y);
       const int offset_x = (x / T - 8) * T, offset_y = (y / T - 8) * T;
-      const size_t WH = (size_t)W * (L.rows / T);
-      const size_t zero_run = (size_t)L.plane_stride - 16;  // the tail of every plane is zero (App. D-2 padding)
-      uint32_t tot[4] = {0, 0, 0, 0};  // 8 x u16: columns pcol0 .. pcol0+7 as (0,2),(1,3),(4,6),(5,7)
+      const uint32_t WH = (uint32_t)W * (uint32_t)(L.rows / T);
+      const uint32_t zero_run = (uint32_t)L.plane_stride - 16u;  // the tail of every plane is zero (App. D-2 padding)
+      // ---- features -> byte offsets (one thread each)
+      int n_all = 0;
+      for (int m = 0; m < P.M; ++m) n_all += rtp->cnt[m];
       const uint32_t* fp = L.feats + rtp->feat_begin;
+      for (int i = threadIdx.x; i < n_all; i += kRefineWarps * 32) {
+        const uint32_t pk = fp[i];
+        const int fx = (int)(pk & 0x1fffu) - 4096 + offset_x, fy = (int)((pk >> 13) & 0x1fffu) - 4096 + offset_y;
+        const bool inside = fx >= 0 && fy >= 0 && fx < L.cols && fy < L.rows;  // "Discard feature if out of bounds"
+        const uint32_t label = pk >> 26;
+        uint32_t addr = label * (uint32_t)L.plane_stride + (uint32_t)((fy % T) * T + (fx % T)) * WH +
+                        (uint32_t)(fy / T) * (uint32_t)W + (uint32_t)(fx / T);
+        s_addr[i] = inside ? addr : zero_run;
+      }
+      __syncthreads();
+      const uint32_t lane_off = (uint32_t)(prow * W + pcol0);
+      uint32_t tot[4] = {0, 0, 0, 0};  // 8 x u16: columns pcol0 .. pcol0+7 as (0,2),(1,3),(4,6),(5,7)
+      int begin = 0;
       for (int m = 0; m < P.M; ++m) {
-        uint32_t a0 = 0, a1 = 0;
         const uint8_t* lmm = L.lm + (size_t)m * 8 * L.plane_stride;
-        const int n = rtp->cnt[m];
-#pragma unroll 4
-        for (int f = warp; f < n; f += kRefineWarps) {
-          const uint32_t pk = fp[f];
-          const int fx = (int)(pk & 0x1fffu) - 4096 + offset_x, fy = (int)((pk >> 13) & 0x1fffu) - 4096 + offset_y;
-          const bool inside = fx >= 0 && fy >= 0 && fx < L.cols && fy < L.rows;
-          const int label = (int)(pk >> 26);
-          size_t addr = (size_t)label * L.plane_stride + (size_t)((fy % T) * T + (fx % T)) * WH + (size_t)(fy / T) * W +
-                        fx / T + (size_t)prow * W + pcol0;
-          if (!inside) addr = zero_run;  // "Discard feature if out of bounds": contributes zeros
-          const uint8_t* p = lmm + (addr & ~(size_t)3);
-          const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(addr & 3);
-          const uint32_t w0 = ldg32(p), w1 = ldg32(p + 4), w2 = ldg32(p + 8);
-          a0 += __byte_perm(w0, w1, sel);
-          a1 += __byte_perm(w1, w2, sel);
+        const int n = rtp->cnt[m];  // <= 63: at most 8 features per warp, u8 lanes cannot overflow (8 * 4)
+        uint32_t w[8][3], sel[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int f = warp + kRefineWarps * k;
+          const uint32_t base = f < n ? s_addr[begin + f] : zero_run;
+          const uint32_t addr = base + (base == zero_run ? 0u : lane_off);
+          const uint8_t* p = lmm + (addr & ~3u);
+          sel[k] = 0x3210u + 0x1111u * (addr & 3u);
+          w[k][0] = ldg32(p); w[k][1] = ldg32(p + 4); w[k][2] = ldg32(p + 8);
         }
-        fp += n;
+        uint32_t a0 = 0, a1 = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          a0 += __byte_perm(w[k][0], w[k][1], sel[k]);
+          a1 += __byte_perm(w[k][1], w[k][2], sel[k]);
+        }
+        begin += n;
         tot[0] += a0 & 0x00ff00ffu; tot[1] += (a0 >> 8) & 0x00ff00ffu;
         tot[2] += a1 & 0x00ff00ffu; tot[3] += (a1 >> 8) & 0x00ff00ffu;
       }
@@ -647,7 +671,7 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams
         for (int k = 0; k < 4; ++k) {
           uint32_t s = 0;
 #pragma unroll
-          for (int w = 0; w < kRefineWarps; ++w) s += s_part[w][lane][k];
+          for (int w2 = 0; w2 < kRefineWarps; ++w2) s += s_part[w2][lane][k];
           tot[k] = s;
         }
         // first maximum in raster order: key = score << 8 | (255 - raster index)
@@ -677,7 +701,7 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams
       }
       __syncthreads();
       x = s_state[0]; y = s_state[1]; alive = s_state[2] != 0; score = (uint32_t)s_state[3]; nf = rtp->nf;
-      __syncthreads();  // s_state / s_part are rewritten by the next level
+      __syncthreads();  // s_state / s_part / s_addr are rewritten by the next level
     }
     if (alive && threadIdx.x == 0) {
       uint32_t idx = atomicAdd(&hdr->count, 1u);
@@ -698,6 +722,22 @@ int coarse_positions_per_pass(int variant) {
 }
 int coarse_record_header_words() { return kRecHdrWords; }
 int coarse_record_max_words() { return kRecMaxWords; }
+
+// Launch configuration with programmatic stream serialization: the grid may be scheduled while its predecessor in the
+// stream drains; the kernel itself waits (cudaGridDependencySynchronize) before it reads the predecessor's results.
+static cudaLaunchAttribute g_pdl_attr;
+static cudaLaunchConfig_t pdl_config(int blocks, int threads, cudaStream_t s) {
+  g_pdl_attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  g_pdl_attr.val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks, 1, 1);
+  cfg.blockDim = dim3((unsigned)threads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cfg.attrs = &g_pdl_attr;
+  cfg.numAttrs = 1;
+  return cfg;
+}
 
 template <class K>
 static int resident_ctas(K kernel) {
@@ -728,9 +768,9 @@ void launch_similarity_coarse(int variant, const uint8_t* lmc, const uint8_t* lm
                                                                        cand, hdr, cand_cap, dump, dump_stride);
   } else {
     static const int persistent = resident_ctas(k_similarity_coarse_rec);
-    k_similarity_coarse_rec<<<min(blocks, persistent), 256, 0, s>>>(lmn, recs, rec_words, n_tiles, thr, M,
-                                                                    dump == nullptr ? prune : 0, cand, hdr, touched,
-                                                                    cand_cap, dump, dump_stride);
+    cudaLaunchConfig_t cfg = pdl_config(min(blocks, persistent), 256, s);
+    cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec, lmn, recs, rec_words, n_tiles, thr, M,
+                       dump == nullptr ? prune : 0, cand, hdr, touched, cand_cap, dump, dump_stride);
   }
 }
 
@@ -743,7 +783,8 @@ void launch_pack_nibbles(const uint8_t* lm_bytes, uint8_t* lm_nibbles, size_t n_
 
 void launch_refine(const RefineParams& p, const CoarseTpl* ctpl, const WorkItem* items, const Cand* cand,
                    uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* out, uint32_t out_cap, cudaStream_t s) {
-  k_refine<<<148 * 4, kRefineWarps * 32, 0, s>>>(p, ctpl, items, cand, cand_cap, hdr, out, out_cap);
+  cudaLaunchConfig_t cfg = pdl_config(148 * 4, kRefineWarps * 32, s);
+  cudaLaunchKernelEx(&cfg, k_refine, p, ctpl, items, cand, cand_cap, hdr, out, out_cap);
 }
 
 }  // namespace lmk
