@@ -230,6 +230,23 @@ def test_edge_templates():
         common.assert_matches_equal(det.last_presort(), orc.last_presort(), "pre-sort thr %g" % thr)
 
 
+def test_config3_1280x960_refinement_heavy():
+    """BASELINE config 3: Ensenso-resolution frames (1280x960 with T = {5, 8}; 1280x1024 violates rows % T, see
+    test_geometry_asserts_like_the_reference), both modalities, a threshold loose enough for > 1000 coarse candidates per
+    frame so that similarityLocal dominates.  Every stage tap and the match list against the oracle."""
+    orc, det, views = _pair(n_views=8, n_random=40, seed=83)
+    det.set_option("debug_taps", 1)
+    bgr, depth, _ = synth.compose_scene(4001, views[:6], rows=960, cols=1280)
+    want = orc.match([bgr, depth], 55.0, keep_candidates=True)
+    got = det.match([bgr, depth], 55.0)
+    assert len(orc.last_candidates()) > 1000
+    assert det.last_work()["candidates"] == len(orc.last_candidates())
+    common.assert_matches_equal(det.last_presort(), orc.last_presort(), "pre-sort list")
+    common.assert_matches_equal(got, want)
+    _check_stages(orc, det, 2, 2, ("cg", "dn"))
+    assert len(want) > 0
+
+
 def test_no_templates_and_empty_results():
     det = Detector()
     bgr = np.zeros((480, 640, 3), np.uint8)
