@@ -195,6 +195,11 @@ int lm_match_device(lm_detector* det, const void* const* d_sources, int n_source
 int lm_match_device_multi(lm_detector* det, const void* const* d_sources, int n_sources, int rows, int cols,
                           const lm_query* queries, int n_queries, void* stream, const void** d_records,
                           size_t* record_bytes_capacity);
+/* The same with an explicit workspace lane (0 or 1): a handle owns two independent workspaces + result blocks, so two
+ * frames can be in flight on two streams of the caller (the kernels of a 640x480 frame do not fill a B200). */
+int lm_match_device_multi_lane(lm_detector* det, int lane, const void* const* d_sources, int n_sources, int rows, int cols,
+                               const lm_query* queries, int n_queries, void* stream, const void** d_records,
+                               size_t* record_bytes_capacity);
 int lm_finalize_raw(const lm_detector* det, const lm_raw_match* raw, size_t n_raw, lm_match_rec** out_matches,
                     size_t* out_n);
 /* Template sharding (north-star multi-GPU layout): keep only templates whose canonical order index i satisfies

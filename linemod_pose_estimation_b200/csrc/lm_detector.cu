@@ -1442,16 +1442,17 @@ int lm_match_batch_multi(lm_detector* d, const lm_image* sources, int n_frames, 
 
 void lm_free_matches(lm_match_rec* m) { std::free(m); }
 
-int lm_match_device_multi(lm_detector* d, const void* const* d_sources, int n_sources, int rows, int cols,
-                          const lm_query* queries, int n_queries, void* stream, const void** d_records,
-                          size_t* record_bytes_capacity) {
+int lm_match_device_multi_lane(lm_detector* d, int lane_index, const void* const* d_sources, int n_sources, int rows,
+                               int cols, const lm_query* queries, int n_queries, void* stream, const void** d_records,
+                               size_t* record_bytes_capacity) {
   if (!d || !d_sources || !d_records) return fail(LM_E_INVALID, "NULL argument");
+  if (lane_index < 0 || lane_index > 1) return fail(LM_E_INVALID, "lane must be 0 or 1");
   if (n_sources != d->model.M()) return fail(LM_E_INVALID, "sources.size() (%d) != modalities.size() (%d)", n_sources, d->model.M());
   Query qs[kMaxQueries];
   int rc = to_queries(queries, n_queries, qs);
   if (rc != LM_OK) return rc;
   if (set_device(d) != LM_OK || upload_luts(d) != LM_OK) return LM_E_CUDA;
-  Lane& ln = d->lane[0];
+  Lane& ln = d->lane[lane_index];
   cudaStream_t s = (cudaStream_t)stream;
   const bool fresh_ws = !(ln.lm_ready && ln.rows == rows && ln.cols == cols);
   rc = ensure_lm_ws(d, ln, rows, cols);
@@ -1470,6 +1471,13 @@ int lm_match_device_multi(lm_detector* d, const void* const* d_sources, int n_so
   *d_records = block_ptr(ln);
   if (record_bytes_capacity) *record_bytes_capacity = result_bytes(ln);
   return LM_OK;
+}
+
+int lm_match_device_multi(lm_detector* d, const void* const* d_sources, int n_sources, int rows, int cols,
+                          const lm_query* queries, int n_queries, void* stream, const void** d_records,
+                          size_t* record_bytes_capacity) {
+  return lm_match_device_multi_lane(d, 0, d_sources, n_sources, rows, cols, queries, n_queries, stream, d_records,
+                                    record_bytes_capacity);
 }
 
 int lm_match_device(lm_detector* d, const void* const* d_sources, int n_sources, int rows, int cols, float threshold,

@@ -70,6 +70,7 @@ class ShardedMatcher:
         self.rank, self.world, self.group = rank, world, group
         self.capacity = capacity
         self._gather_buf = None
+        self._send_buf = self._recv_buf = None
 
     def broadcast_frame(self, tensors):
         if self.world > 1:
@@ -77,18 +78,45 @@ class ShardedMatcher:
                 dist.broadcast(t.view(torch.uint8), src=0, group=self.group)  # C1
         return tensors
 
-    def gather_async(self, block):
+    def gather_async(self, block, slot=0):
         """C2, device side only: all-gather of the header + first `capacity` records of every rank's survivor block.
-        Nothing is synchronised, so this is what the device-timed path runs."""
+        Nothing is synchronised, so this is what the device-timed path runs.  `slot` selects the receive buffer (one per
+        frame in flight)."""
         nbytes = RESULT_HEADER_BYTES + self.capacity * RECORD_BYTES
         mine = block[:nbytes]
         if self.world == 1:
             return mine
         total = nbytes * self.world
-        if self._gather_buf is None or self._gather_buf.numel() != total or self._gather_buf.device != mine.device:
-            self._gather_buf = torch.empty(total, dtype=torch.uint8, device=mine.device)
-        dist.all_gather_into_tensor(self._gather_buf, mine.contiguous(), group=self.group)
-        return self._gather_buf
+        if self._gather_buf is None:
+            self._gather_buf = {}
+        buf = self._gather_buf.get(slot)
+        if buf is None or buf.numel() != total or buf.device != mine.device:
+            buf = self._gather_buf[slot] = torch.empty(total, dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(buf, mine.contiguous(), group=self.group)
+        return buf
+
+    def stage_block(self, block, slot, n_slots):
+        """Streamed exchange, step 1 (device side, asynchronous): park a frame's survivor block in slot `slot` of this
+        rank's send buffer.  One collective then moves `n_slots` frames at once (gather_staged): the per-frame payload
+        is a few hundred bytes, so the exchange is launch-latency bound and is batched over frames, not over links."""
+        nbytes = RESULT_HEADER_BYTES + self.capacity * RECORD_BYTES
+        if self._send_buf is None or self._send_buf.shape != (n_slots, nbytes) or self._send_buf.device != block.device:
+            self._send_buf = torch.empty((n_slots, nbytes), dtype=torch.uint8, device=block.device)
+            self._recv_buf = torch.empty((self.world, n_slots, nbytes), dtype=torch.uint8, device=block.device)
+            self._send_slots = [self._send_buf[i] for i in range(n_slots)]
+            self._heads = {}
+        head = self._heads.get(block.data_ptr())   # the library's blocks are few and stable: keep their sliced views
+        if head is None:
+            head = self._heads[block.data_ptr()] = block[:nbytes]
+        self._send_slots[slot].copy_(head, non_blocking=True)
+
+    def gather_staged(self):
+        """Streamed exchange, step 2: all-gather of every rank's staged blocks -> tensor [world][n_slots][block bytes]
+        (device, asynchronous).  unpack_blocks() on recv[:, slot].reshape(-1) yields frame `slot`'s raw records."""
+        if self.world == 1:
+            return self._send_buf.unsqueeze(0)
+        dist.all_gather_into_tensor(self._recv_buf.view(-1), self._send_buf.view(-1), group=self.group)
+        return self._recv_buf
 
     def gather(self, block):
         """C2 + download: every rank's raw records.  Every rank sees every header, so all ranks agree on whether a

@@ -70,6 +70,19 @@ def _worker(rank, world, port, capacity, out_dir):
         else:
             assert got is None
             assert np.array_equal(frame[0].numpy(), synth.compose_scene(1001, views[:4], rows=240, cols=320)[0])  # broadcast arrived
+        # streamed exchange: the survivor blocks of several frames travel in one all-gather
+        if capacity >= 64:
+            from linemod_pose_estimation_b200.sharding import unpack_blocks
+            thresholds = (75.0, 68.0, 62.0)
+            for slot, thr in enumerate(thresholds):
+                sm.stage_block(local_match(frame, [(thr, [])]), slot, len(thresholds))
+            recv = sm.gather_staged().numpy()
+            assert recv.shape[:2] == (world, len(thresholds))
+            for slot, thr in enumerate(thresholds):
+                raws, need = unpack_blocks(np.ascontiguousarray(recv[:, slot]).reshape(-1), world, sm.capacity)
+                assert need == 0
+                common.assert_matches_equal(det.finalize_raw(np.concatenate(raws)),
+                                            orc.match([frame[0].numpy(), frame[1].numpy().view(np.uint16)], thr), "slot %d" % slot)
     finally:
         dist.destroy_process_group()
 
