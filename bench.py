@@ -44,7 +44,8 @@ TEMPLATES_PER_CLASS = 2652
 EXTRACTED_PER_CLASS = 24
 FRAME_POOL = 128            # 128 x 1.536 MB = 197 MB of distinct input frames > 126 MB L2
 METRIC = "template_pixel_evals_per_sec_640x480"
-GATHER_EVERY = 8            # N > 1, device-timed path: frames per survivor all-gather
+N_INFLIGHT = int(os.environ.get("LM_BENCH_INFLIGHT", "4"))   # frames in flight on the device-timed path (workspace lanes)
+GATHER_EVERY = int(os.environ.get("LM_BENCH_GATHER", "16"))           # N > 1, device-timed path: frames per survivor all-gather
 REFERENCE_BUDGET_S = 60.0  # wall-clock bound of the CPU arm's timed region
 
 
@@ -316,10 +317,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- value: frames resident in HBM on every rank, device-timed; survivors end in rank 0's HBM (all-gather).
-    # Two frames are in flight on two streams (the handle's two workspace lanes): the kernels of one 640x480 frame do
-    # not fill a B200, so consecutive frames of the stream overlap.
-    streams = [stream, torch.cuda.Stream(device=dev)]
-    recs = [(C.c_void_p(), C.c_size_t()), (C.c_void_p(), C.c_size_t())]
+    # N_INFLIGHT frames are in flight on as many streams (the handle's workspace lanes): the kernels of one 640x480
+    # frame do not fill a B200, so consecutive frames of the stream overlap.
+    streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(N_INFLIGHT - 1)]
+    recs = [(C.c_void_p(), C.c_size_t()) for _ in range(N_INFLIGHT)]
     views_cache = {}
 
     def block_view(k):   # torch view of lane k's survivor block (the pointer is stable; building a view costs ~30 us)
@@ -330,7 +331,7 @@ def run_ours(args):
         return v
 
     def device_step(i):
-        k = i & 1
+        k = i % N_INFLIGHT
         _capi.check(lib.lm_match_device_multi_lane(det._h, k, dev_ptrs[i % FRAME_POOL], 2, ROWS, COLS, qarr, n_q,
                                                    C.c_void_p(streams[k].cuda_stream), C.byref(recs[k][0]),
                                                    C.byref(recs[k][1])))
@@ -338,22 +339,25 @@ def run_ours(args):
             with torch.cuda.stream(streams[k]):
                 sharded.stage_block(block_view(k), i % GATHER_EVERY, GATHER_EVERY)
             if i % GATHER_EVERY == GATHER_EVERY - 1:
-                streams[0].wait_stream(streams[1])
+                for st in streams[1:]:
+                    streams[0].wait_stream(st)
                 with torch.cuda.stream(streams[0]):
                     sharded.gather_staged()
-                streams[1].wait_stream(streams[0])
+                for st in streams[1:]:
+                    st.wait_stream(streams[0])
 
     for i in range(args.warmup):
         device_step(i)
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    streams[1].wait_stream(streams[0])
     e0.record(streams[0])
-    streams[1].wait_stream(streams[0])   # both lanes start after e0
+    for st in streams[1:]:
+        st.wait_stream(streams[0])       # every lane starts after e0
     for i in range(args.steps):
         device_step(args.warmup + i)
-    streams[0].wait_stream(streams[1])   # e1 after the last frame of either lane
+    for st in streams[1:]:
+        streams[0].wait_stream(st)       # e1 after the last frame of every lane
     e1.record(streams[0])
     barrier()
     ms = e0.elapsed_time(e1)
@@ -521,6 +525,8 @@ def main():
         run_reference(args)
     else:
         args.warmup = max(args.warmup, 3)
+        if args.gpus > 1:   # the first collectives (communicator set-up) and graph captures of every lane stay outside the timing
+            args.warmup = max(args.warmup, 2 * GATHER_EVERY)
         run_ours(args)
 
 

@@ -81,6 +81,10 @@ static size_t plane_stride_of(int T, int W, int H) {
 }
 static const size_t kLmSlack = 8192;  // tail slack: vector loads of partially filled passes may over-read
 
+// Frames in flight per handle: lm_match_batch* pipelines this many frames (H2D copy, kernels, D2H copy of different
+// frames overlap), lm_match_device_multi_lane exposes them to callers that manage their own streams.
+static const int LM_LANES = 4;
+
 // One in-flight frame: stream, events, device workspace, pinned staging.
 struct Lane {
   cudaStream_t stream = nullptr;
@@ -108,6 +112,17 @@ struct Lane {
   DevBuf spread[LM_MAX_LEVELS][LM_MAX_MODALITIES], response[LM_MAX_LEVELS][LM_MAX_MODALITIES];  // parity taps only
   DevBuf lmem[LM_MAX_LEVELS];                          // [M][8][plane_stride] + slack
   DevBuf lmn;                                          // coarsest level again, nibble-packed (two positions per byte)
+  // The GPU work of one frame (front end, header memset, coarse, refine) as an instantiated CUDA graph: the batch and
+  // device-resident paths replay it instead of ~20 runtime calls per frame.  Valid while `gkey` matches.
+  struct GraphKey {
+    const void* plan; const void* plan_recs; const void* cand; const void* result; const void* src[LM_MAX_MODALITIES];
+    uint64_t model_version; int rows, cols, n_q, n_tiles, variant, prune, frontend, shard_rank, shard_world; uint32_t cand_cap, out_cap;
+    float thr[LM_MAX_QUERIES];
+  };
+  cudaGraphExec_t gexec = nullptr;
+  GraphKey gkey;
+  int graph_launches = 0;
+  bool graph_broken = false;  // capture failed once on this lane: stay on the eager path
   // matching
   DevBuf cand, result, work, work_order, dump, dbg_recs;
   uint32_t cand_cap = 0, out_cap = 0;
@@ -140,6 +155,7 @@ struct Lane {
     lmn.release();
     cand.release(); result.release(); work.release(); work_order.release(); dump.release(); dbg_recs.release();
     stage_in.release(); stage_out.release();
+    if (gexec) cudaGraphExecDestroy(gexec);
     for (int i = 0; i < 6; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
     if (ev_fork) cudaEventDestroy(ev_fork);
     for (int i = 0; i < LM_MAX_MODALITIES - 1; ++i) {
@@ -188,10 +204,10 @@ struct lm_detector {
   uint8_t normal_lut[8000];
   DevBuf d_resp_all, d_normal_lut;
   bool luts_dirty = true;
-  Lane lane[2];
+  Lane lane[LM_LANES];
   Pack pack;
   int shard_rank = 0, shard_world = 1;
-  int debug_taps = 0, coarse_variant = 0, timing = 1, frontend_variant = 0, prune = 1;
+  int debug_taps = 0, coarse_variant = 0, timing = 1, frontend_variant = 0, prune = 1, graphs = 1;
   std::vector<std::string> class_id_cache;
 };
 
@@ -235,7 +251,7 @@ static int upload_luts(lm_detector* d) {
   CU(cudaMemcpy(d->d_resp_all.p, resp_all, sizeof(resp_all), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(d->d_normal_lut.p, d->normal_lut, 8000, cudaMemcpyHostToDevice));
   d->luts_dirty = false;
-  for (int i = 0; i < 2; ++i) d->lane[i].front_valid = false;
+  for (int i = 0; i < LM_LANES; ++i) d->lane[i].front_valid = false;
   return LM_OK;
 }
 
@@ -541,7 +557,7 @@ static int ensure_pack(lm_detector* d, const Lane& ln) {
       pk.shard_world == d->shard_world && pk.variant == d->coarse_variant)
     return LM_OK;
   // all lanes must be idle before the shared records are replaced
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < LM_LANES; ++i)
     if (d->lane[i].stream) CU(cudaStreamSynchronize(d->lane[i].stream));
   const int L = md.levels(), M = md.M();
   const LevelGeom& gc = ln.geom[L - 1];
@@ -830,6 +846,57 @@ static int enqueue_match(lm_detector* d, Lane& ln, const Pack::Plan& plan, const
   return LM_OK;
 }
 
+// Front end + matching of one frame whose sources are already in device memory (ln.src_ptr), enqueued on s.  Replays
+// the lane's CUDA graph when one matching this request exists, records a new one otherwise; falls back to plain
+// launches when graphs are switched off, the parity taps are on, or a capture ever failed on this lane.
+static int enqueue_frame(lm_detector* d, Lane& ln, const Pack::Plan& plan, const Query* qs, int n_q, cudaStream_t s) {
+  bool masks = false;
+  for (int m = 0; m < d->model.M(); ++m) masks = masks || ln.has_mask[m];
+  if (!d->graphs || ln.graph_broken || d->debug_taps || masks) {
+    if (run_front(d, ln, s) != LM_OK) return LM_E_CUDA;
+    return enqueue_match(d, ln, plan, qs, n_q, s, nullptr);
+  }
+  Lane::GraphKey key;
+  std::memset(&key, 0, sizeof(key));
+  key.plan = &plan; key.plan_recs = plan.recs.p; key.n_tiles = plan.n_tiles; key.cand = ln.cand.p; key.result = ln.result.p;
+  key.shard_rank = d->shard_rank; key.shard_world = d->shard_world;
+  for (int m = 0; m < d->model.M(); ++m) key.src[m] = ln.src_ptr[m];
+  key.model_version = d->model.version; key.rows = ln.rows; key.cols = ln.cols; key.n_q = n_q;
+  key.variant = d->coarse_variant; key.prune = d->prune; key.frontend = d->frontend_variant;
+  key.cand_cap = ln.cand_cap; key.out_cap = ln.out_cap;
+  for (int q = 0; q < n_q; ++q) key.thr[q] = qs[q].threshold;
+  if (ln.gexec == nullptr || std::memcmp(&key, &ln.gkey, sizeof(key)) != 0) {
+    if (ln.gexec) { cudaGraphExecDestroy(ln.gexec); ln.gexec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    set_programmatic_launch(false);
+    cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed);
+    int rc = LM_OK;
+    if (e == cudaSuccess) {
+      ln.launches = 0;
+      rc = run_front(d, ln, s);
+      if (rc == LM_OK) rc = enqueue_match(d, ln, plan, qs, n_q, s, nullptr);
+      e = cudaStreamEndCapture(s, &graph);
+    }
+    set_programmatic_launch(true);
+    if (e == cudaSuccess && rc == LM_OK && graph != nullptr) e = cudaGraphInstantiate(&ln.gexec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess || rc != LM_OK || ln.gexec == nullptr) {  // not fatal: this lane keeps to plain launches
+      cudaGetLastError();
+      ln.gexec = nullptr;
+      ln.graph_broken = true;
+      if (run_front(d, ln, s) != LM_OK) return LM_E_CUDA;
+      return enqueue_match(d, ln, plan, qs, n_q, s, nullptr);
+    }
+    ln.gkey = key;
+    ln.graph_launches = ln.launches;
+  }
+  CU(cudaGraphLaunch(ln.gexec, s));
+  ln.launches = ln.graph_launches;
+  ln.front_valid = true;
+  ln.debug_taps_written = false;
+  return LM_OK;
+}
+
 // [OCV] Match::operator< and operator==
 static inline bool match_less(const lm_match_rec& a, const lm_match_rec& b) {
   if (a.similarity != b.similarity) return a.similarity > b.similarity;
@@ -973,7 +1040,7 @@ static int set_device(lm_detector* d) {
       return fail(LM_E_CUDA, "no CUDA device available (%s); this library has no CPU path", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     }
     CU(cudaGetDevice(&d->device));
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < LM_LANES; ++i)
       if (d->lane[i].init() != LM_OK) return LM_E_CUDA;
     d->cuda_ready = true;
   }
@@ -1079,7 +1146,7 @@ void lm_destroy(lm_detector* d) {
   if (!d) return;
   if (d->cuda_ready) {
     cudaSetDevice(d->device);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < LM_LANES; ++i) {
       if (d->lane[i].stream) cudaStreamSynchronize(d->lane[i].stream);
       d->lane[i].destroy();
     }
@@ -1279,16 +1346,18 @@ int lm_set_option(lm_detector* d, const char* key, int value) {
   if (!d || !key) return fail(LM_E_INVALID, "NULL argument");
   std::string k(key);
   if (k == "debug_taps") d->debug_taps = value;
-  else if (k == "coarse_variant") { d->coarse_variant = value; for (int i = 0; i < 2; ++i) d->lane[i].front_valid = false; }
+  else if (k == "coarse_variant") { d->coarse_variant = value; for (int i = 0; i < LM_LANES; ++i) d->lane[i].front_valid = false; }
   else if (k == "timing") d->timing = value;
   else if (k == "prune") d->prune = value;
-  else if (k == "frontend_variant") { d->frontend_variant = value; for (int i = 0; i < 2; ++i) d->lane[i].front_valid = false; }
+  else if (k == "graphs") d->graphs = value;
+  else if (k == "frontend_variant") { d->frontend_variant = value; for (int i = 0; i < LM_LANES; ++i) d->lane[i].front_valid = false; }
   else return fail(LM_E_INVALID, "unknown option '%s'", key);
   return LM_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- match
-static int front_from_host(lm_detector* d, Lane& ln, const lm_image* sources, int n_sources, const lm_image* masks, int n_masks) {
+static int front_from_host(lm_detector* d, Lane& ln, const lm_image* sources, int n_sources, const lm_image* masks, int n_masks,
+                           bool run = true) {
   int rc = check_sources(d, sources, n_sources, masks, n_masks);
   if (rc != LM_OK) return rc;
   if (set_device(d) != LM_OK || upload_luts(d) != LM_OK) return LM_E_CUDA;
@@ -1300,8 +1369,10 @@ static int front_from_host(lm_detector* d, Lane& ln, const lm_image* sources, in
   CU(cudaEventRecord(ln.ev[0], ln.stream));
   if (upload_frame(d, ln, sources, masks, n_masks) != LM_OK) return LM_E_CUDA;
   CU(cudaEventRecord(ln.ev[1], ln.stream));
-  if (run_front(d, ln, ln.stream) != LM_OK) return LM_E_CUDA;
-  CU(cudaEventRecord(ln.ev[2], ln.stream));
+  if (run) {
+    if (run_front(d, ln, ln.stream) != LM_OK) return LM_E_CUDA;
+    CU(cudaEventRecord(ln.ev[2], ln.stream));
+  }
   // B_front: sources read once + linear memories written once
   uint64_t bf = 0;
   for (int m = 0; m < n_sources; ++m) bf += src_row_bytes(sources[m].type, cols) * rows;
@@ -1384,7 +1455,7 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
   if (n_q < 1 || n_q > kMaxQueries) return fail(LM_E_INVALID, "number of queries must be 1..%d", kMaxQueries);
   std::vector<lm_match_rec> all;
   out_offsets[0] = 0;
-  bool busy[2] = {false, false};
+  bool busy[LM_LANES] = {};
   auto finish = [&](int li, int frame) -> int {
     Lane& ln = d->lane[li];
     std::vector<lm_raw_match> raw;
@@ -1403,10 +1474,10 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
     return LM_OK;
   };
   for (int f = 0; f < n_frames; ++f) {
-    const int li = f & 1;
+    const int li = f % LM_LANES;
     Lane& ln = d->lane[li];
-    if (busy[li]) { int rc = finish(li, f - 2); if (rc != LM_OK) return rc; busy[li] = false; }
-    int rc = front_from_host(d, ln, sources + (size_t)f * n_sources, n_sources, nullptr, 0);
+    if (busy[li]) { int rc = finish(li, f - LM_LANES); if (rc != LM_OK) return rc; busy[li] = false; }
+    int rc = front_from_host(d, ln, sources + (size_t)f * n_sources, n_sources, nullptr, 0, false);  // upload only
     if (rc != LM_OK) return rc;
     rc = ensure_pack(d, ln);
     if (rc != LM_OK) return rc;
@@ -1414,12 +1485,12 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
     rc = get_plan(d, qs, n_q, &plan);
     if (rc != LM_OK) return rc;
     if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
-    if (enqueue_match(d, ln, *plan, qs, n_q, ln.stream, ln.ev[3]) != LM_OK) return LM_E_CUDA;
+    if (enqueue_frame(d, ln, *plan, qs, n_q, ln.stream) != LM_OK) return LM_E_CUDA;
     CU(cudaEventRecord(ln.ev[4], ln.stream));
     busy[li] = true;
   }
-  for (int f = std::max(0, n_frames - 2); f < n_frames; ++f)
-    if (busy[f & 1]) { int rc = finish(f & 1, f); if (rc != LM_OK) return rc; busy[f & 1] = false; }
+  for (int f = std::max(0, n_frames - LM_LANES); f < n_frames; ++f)
+    if (busy[f % LM_LANES]) { int rc = finish(f % LM_LANES, f); if (rc != LM_OK) return rc; busy[f % LM_LANES] = false; }
   size_t n = 0;
   return copy_out(all, out_matches, &n);
 }
@@ -1446,7 +1517,7 @@ int lm_match_device_multi_lane(lm_detector* d, int lane_index, const void* const
                                int cols, const lm_query* queries, int n_queries, void* stream, const void** d_records,
                                size_t* record_bytes_capacity) {
   if (!d || !d_sources || !d_records) return fail(LM_E_INVALID, "NULL argument");
-  if (lane_index < 0 || lane_index > 1) return fail(LM_E_INVALID, "lane must be 0 or 1");
+  if (lane_index < 0 || lane_index >= LM_LANES) return fail(LM_E_INVALID, "lane must be 0..%d", LM_LANES - 1);
   if (n_sources != d->model.M()) return fail(LM_E_INVALID, "sources.size() (%d) != modalities.size() (%d)", n_sources, d->model.M());
   Query qs[kMaxQueries];
   int rc = to_queries(queries, n_queries, qs);
@@ -1458,16 +1529,23 @@ int lm_match_device_multi_lane(lm_detector* d, int lane_index, const void* const
   rc = ensure_lm_ws(d, ln, rows, cols);
   if (rc != LM_OK) return rc;
   if (fresh_ws) CU(cudaStreamSynchronize(ln.stream));  // workspace memsets were enqueued on the lane's own stream
-  for (int m = 0; m < n_sources; ++m) { ln.src_ptr[m] = d_sources[m]; ln.has_mask[m] = false; }
+  const bool replay = d->graphs && !ln.graph_broken && !d->debug_taps;
+  for (int m = 0; m < n_sources; ++m) {
+    ln.has_mask[m] = false;
+    if (replay) {  // the recorded graph reads the lane's own source buffers: one device-to-device copy per source
+      const size_t bytes = src_row_bytes(expected_src_type(d->model.mods[m]), cols) * rows;
+      CU(cudaMemcpyAsync(ln.src[m].p, d_sources[m], bytes, cudaMemcpyDeviceToDevice, s));
+      ln.src_ptr[m] = ln.src[m].p;
+    } else ln.src_ptr[m] = d_sources[m];
+  }
   ln.launches = 0;
-  if (run_front(d, ln, s) != LM_OK) return LM_E_CUDA;
   rc = ensure_pack(d, ln);
   if (rc != LM_OK) return rc;
   Pack::Plan* plan = nullptr;
   rc = get_plan(d, qs, n_queries, &plan);
   if (rc != LM_OK) return rc;
   if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 18), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
-  if (enqueue_match(d, ln, *plan, qs, n_queries, s, nullptr) != LM_OK) return LM_E_CUDA;
+  if (enqueue_frame(d, ln, *plan, qs, n_queries, s) != LM_OK) return LM_E_CUDA;
   *d_records = block_ptr(ln);
   if (record_bytes_capacity) *record_bytes_capacity = result_bytes(ln);
   return LM_OK;

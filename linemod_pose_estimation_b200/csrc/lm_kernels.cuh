@@ -139,6 +139,7 @@ bool launch_spread_all(const SpreadParams& p, int total_blocks, int max_T, cudaS
 //   [4] j0 = first position of the pass  [5] positions in the pass  [6] the item's order key  [7] 0  [8..11] per modality: 4 class sizes, u8 each
 //   [12..] feature words, modality-major, grouped by class Q = (a >> 3) & 3 where a = nibble index of the window of
 //   lane 0: ((a >> 1) & ~15) | (a & 7)  -- aligned chunk byte offset | nibble shift
+void set_programmatic_launch(bool enabled);  // per thread; disabled while launches are recorded into a CUDA graph
 int coarse_positions_per_pass(int variant);
 int coarse_record_header_words();
 int coarse_record_max_words();

@@ -726,6 +726,7 @@ int coarse_record_max_words() { return kRecMaxWords; }
 // Launch configuration with programmatic stream serialization: the grid may be scheduled while its predecessor in the
 // stream drains; the kernel itself waits (cudaGridDependencySynchronize) before it reads the predecessor's results.
 static cudaLaunchAttribute g_pdl_attr;
+static thread_local bool g_pdl_enabled = true;  // off while a stream capture records the launches (graph edges instead)
 static cudaLaunchConfig_t pdl_config(int blocks, int threads, cudaStream_t s) {
   g_pdl_attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
   g_pdl_attr.val.programmaticStreamSerializationAllowed = 1;
@@ -735,9 +736,11 @@ static cudaLaunchConfig_t pdl_config(int blocks, int threads, cudaStream_t s) {
   cfg.dynamicSmemBytes = 0;
   cfg.stream = s;
   cfg.attrs = &g_pdl_attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl_enabled ? 1 : 0;
   return cfg;
 }
+
+void set_programmatic_launch(bool enabled) { g_pdl_enabled = enabled; }
 
 template <class K>
 static int resident_ctas(K kernel) {
