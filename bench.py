@@ -320,42 +320,45 @@ def run_ours(args):
     # N_INFLIGHT frames are in flight on as many streams (the handle's workspace lanes): the kernels of one 640x480
     # frame do not fill a B200, so consecutive frames of the stream overlap.
     streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(N_INFLIGHT - 1)]
-    recs = [(C.c_void_p(), C.c_size_t()) for _ in range(N_INFLIGHT)]
-    views_cache = {}
+    stream_ptrs = (C.c_void_p * N_INFLIGHT)(*[st.cuda_stream for st in streams])
+    # runs of GATHER_EVERY consecutive frames of the pool: one lm_match_device_stream call each (frame f of a run on lane
+    # f % N_INFLIGHT), and for N > 1 one all-gather of the run's survivor blocks (launch-latency bound exchange)
+    assert FRAME_POOL % GATHER_EVERY == 0
+    run_ptrs = []
+    for r0 in range(0, FRAME_POOL, GATHER_EVERY):
+        flat = [p for (fb, fd) in dev_frames[r0:r0 + GATHER_EVERY] for p in (fb.data_ptr(), fd.data_ptr())]
+        run_ptrs.append((C.c_void_p * len(flat))(*flat))
 
-    def block_view(k):   # torch view of lane k's survivor block (the pointer is stable; building a view costs ~30 us)
-        key = (recs[k][0].value, recs[k][1].value)
-        v = views_cache.get(key)
-        if v is None:
-            v = views_cache[key] = device_view(key[0], key[1], dev)
-        return v
+    def device_run(r, n):
+        stage_ptr, stage_bytes = None, 0
+        if world > 1:
+            stage_bytes = sharded._ensure_send(GATHER_EVERY, dev)
+            stage_ptr = sharded._send_ptrs[0]
+        _capi.check(lib.lm_match_device_stream(det._h, run_ptrs[r % len(run_ptrs)], n, 2, ROWS, COLS, qarr, n_q, stream_ptrs,
+                                               N_INFLIGHT, stage_ptr, stage_bytes))
+        if world > 1:
+            for st in streams[1:]:
+                streams[0].wait_stream(st)
+            with torch.cuda.stream(streams[0]):
+                sharded.gather_staged()
+            for st in streams[1:]:
+                st.wait_stream(streams[0])
 
-    def device_step(i):
-        k = i % N_INFLIGHT
-        _capi.check(lib.lm_match_device_multi_lane(det._h, k, dev_ptrs[i % FRAME_POOL], 2, ROWS, COLS, qarr, n_q,
-                                                   C.c_void_p(streams[k].cuda_stream), C.byref(recs[k][0]),
-                                                   C.byref(recs[k][1])))
-        if world > 1:   # survivors of GATHER_EVERY frames travel in one all-gather (launch-latency bound exchange)
-            with torch.cuda.stream(streams[k]):
-                sharded.stage_block(block_view(k), i % GATHER_EVERY, GATHER_EVERY)
-            if i % GATHER_EVERY == GATHER_EVERY - 1:
-                for st in streams[1:]:
-                    streams[0].wait_stream(st)
-                with torch.cuda.stream(streams[0]):
-                    sharded.gather_staged()
-                for st in streams[1:]:
-                    st.wait_stream(streams[0])
+    def device_steps(first, count):
+        done = 0
+        while done < count:
+            n = min(GATHER_EVERY, count - done)
+            device_run((first + done) // GATHER_EVERY, n)
+            done += n
 
-    for i in range(args.warmup):
-        device_step(i)
+    device_steps(0, max(args.warmup, GATHER_EVERY))
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(streams[0])
     for st in streams[1:]:
         st.wait_stream(streams[0])       # every lane starts after e0
-    for i in range(args.steps):
-        device_step(args.warmup + i)
+    device_steps(GATHER_EVERY * 2, args.steps)
     for st in streams[1:]:
         streams[0].wait_stream(st)       # e1 after the last frame of every lane
     e1.record(streams[0])
@@ -447,14 +450,30 @@ def run_ours(args):
                       "what": "one blocking lm_match_multi call per frame (no overlap between frames)"}
         n_matches = matches_streamed
     else:
-        for i in range(args.warmup):
-            e2e_step(i, False)
+        # streamed: ShardedDetector.match_stream -- per chunk of frames one upload + broadcast from rank 0 and one
+        # all-gather of the survivor blocks, frames of a chunk in flight on the handle's lanes, upload of chunk c+1
+        # overlapping the matching of chunk c; rank 0 ends with the finalised host match lists of every frame
+        host_lists = [[pb, pd] for (pb, pd) in host]
+        check = sharded.match_stream(host_lists[:E2E_CHUNK], QUERIES, chunk=E2E_CHUNK)
+        if rank == 0:   # same lists as the per-frame path (outside the timed region)
+            bufs[0].copy_(torch.from_numpy(host[3][0])); bufs[1].copy_(torch.from_numpy(host[3][1].view(np.int16)))
+        ref3 = sharded.match(bufs, QUERIES)
+        if rank == 0:
+            for a, b_ in zip(check[3], ref3):
+                assert np.array_equal(a, b_), "streamed sharded path disagrees with the per-frame path"
         barrier()
+        n_matches = 0
         t0 = time.perf_counter()
-        for i in range(args.steps):
-            e2e_step(args.warmup + i, True)
+        done = 0
+        while done < args.steps:
+            n = min(FRAME_POOL, args.steps - done)
+            res = sharded.match_stream(host_lists[:n], QUERIES, chunk=E2E_CHUNK)
+            if rank == 0:
+                n_matches += sum(len(q) for fr in res for q in fr)
+            done += n
         barrier()
         dt = time.perf_counter() - t0
+        launches = det.last_timings()["launches"] * args.steps
         launches_single = 0
         t = torch.tensor([dt], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -502,8 +521,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": 16 + (1024 if world == 1 else sharded.capacity * world) * 32,
                     "matches_per_step": n_matches / max(1, args.steps),
                     "what": ("lm_match_batch_multi over chunks of %d pinned host frames (copies of frame f+1 overlap the kernels of "
-                             "frame f)" % E2E_CHUNK) if world == 1 else "per frame: H2D on rank 0, NCCL broadcast, local match, "
-                            "NCCL all-gather, D2H + finalise on rank 0"},
+                             "frame f)" % E2E_CHUNK) if world == 1 else "ShardedDetector.match_stream: per chunk of %d frames "
+                            "H2D on rank 0 + one NCCL broadcast per modality, local matching on 4 lanes, one NCCL all-gather of the "
+                            "survivor blocks, D2H + finalise on rank 0; chunk c+1's upload overlaps chunk c's matching" % E2E_CHUNK},
             "e2e_single_call": e2e_single,
             "gpu_launches": launches_device + launches + launches_single, "clocks": clock_info,
             "stage_ms_per_frame": {k: float(np.mean(v)) for k, v in stage_ms.items() if v},

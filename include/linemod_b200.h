@@ -200,6 +200,22 @@ int lm_match_device_multi(lm_detector* det, const void* const* d_sources, int n_
 int lm_match_device_multi_lane(lm_detector* det, int lane, const void* const* d_sources, int n_sources, int rows, int cols,
                                const lm_query* queries, int n_queries, void* stream, const void** d_records,
                                size_t* record_bytes_capacity);
+/* The lanes' record blocks are one contiguous device allocation: block of lane i = *base + i * *lane_stride (each a
+ * header + records as above; the bytes between blocks are padding).  A sharded caller exchanges the survivors of all
+ * frames in flight with one collective over [*base, *base + n_lanes * lane_stride) and no staging copies.  The region
+ * moves only when a host-path call has to grow the record capacity ("device_out_cap" option: records per block on the
+ * device-resident path, default 2048). */
+int lm_device_result_region(lm_detector* det, const void** base, size_t* lane_stride, int* n_lanes);
+/* Enqueues on `stream` a device-to-device copy of the first `bytes` of lane's record block (header + leading records)
+ * to d_dst: how a sharded caller parks the survivors of a frame in its send buffer without leaving the stream. */
+int lm_copy_result_block(lm_detector* det, int lane, void* d_dst, size_t bytes, void* stream);
+/* A run of device-resident frames in one call: frame f (sources d_sources[f * n_sources + m]) is enqueued on lane
+ * f % n_streams and stream streams[f % n_streams]; when d_stage is given, the head of its record block (stage_slot_bytes:
+ * header + leading records) is copied to d_stage + f * stage_slot_bytes on the same stream -- the send buffer of the
+ * sharded exchange (one collective per run of frames).  Nothing is synchronised. */
+int lm_match_device_stream(lm_detector* det, const void* const* d_sources, int n_frames, int n_sources, int rows, int cols,
+                           const lm_query* queries, int n_queries, void* const* streams, int n_streams, void* d_stage,
+                           size_t stage_slot_bytes);
 int lm_finalize_raw(const lm_detector* det, const lm_raw_match* raw, size_t n_raw, lm_match_rec** out_matches,
                     size_t* out_n);
 /* Template sharding (north-star multi-GPU layout): keep only templates whose canonical order index i satisfies

@@ -51,7 +51,7 @@ EXPORTS = [
     "lm_last_error", "lm_alloc_pinned", "lm_free_pinned", "lm_device", "lm_pyramid_levels", "lm_get_T",
     "lm_num_modalities", "lm_get_modality", "lm_num_classes", "lm_num_templates", "lm_class_id", "lm_get_templates",
     "lm_add_template", "lm_add_template_from_quantized", "lm_add_synthetic_template", "lm_match", "lm_match_multi", "lm_match_batch", "lm_match_batch_multi", "lm_free_matches",
-    "lm_match_device", "lm_match_device_multi", "lm_match_device_multi_lane", "lm_finalize_raw", "lm_set_shard", "lm_set_similarity_lut", "lm_get_similarity_lut",
+    "lm_match_device", "lm_match_device_multi", "lm_match_device_multi_lane", "lm_device_result_region", "lm_copy_result_block", "lm_match_device_stream", "lm_finalize_raw", "lm_set_shard", "lm_set_similarity_lut", "lm_get_similarity_lut",
     "lm_set_normal_lut", "lm_get_normal_lut", "lm_debug_fetch", "lm_build_front", "lm_level_geometry",
     "lm_debug_coarse_map", "lm_debug_presort", "lm_last_timings", "lm_last_work", "lm_set_option",
 ]
@@ -107,6 +107,10 @@ def lib():
                                         C.POINTER(C.c_size_t)]
     L.lm_match_device_multi_lane.argtypes = [vp, ci, C.POINTER(vp), ci, ci, ci, C.POINTER(LmQuery), ci, vp, C.POINTER(vp),
                                              C.POINTER(C.c_size_t)]
+    L.lm_device_result_region.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(ci)]
+    L.lm_copy_result_block.argtypes = [vp, ci, vp, C.c_size_t, vp]
+    L.lm_match_device_stream.argtypes = [vp, C.POINTER(vp), ci, ci, ci, ci, C.POINTER(LmQuery), ci, C.POINTER(vp), ci, vp,
+                                         C.c_size_t]
     L.lm_match_batch.argtypes = [vp, C.POINTER(LmImage), ci, ci, C.c_float, C.POINTER(cp), ci, C.POINTER(vp),
                                  C.POINTER(C.c_size_t)]
     L.lm_match_batch_multi.argtypes = [vp, C.POINTER(LmImage), ci, ci, C.POINTER(LmQuery), ci, C.POINTER(vp),

@@ -124,7 +124,11 @@ struct Lane {
   int graph_launches = 0;
   bool graph_broken = false;  // capture failed once on this lane: stay on the eager path
   // matching
-  DevBuf cand, result, work, work_order, dump, dbg_recs;
+  DevBuf cand, work, work_order, dump, dbg_recs;
+  struct Ref {  // this lane's result block inside the detector-wide allocation (lm_detector::results_all)
+    void* p = nullptr;
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+  } result;
   uint32_t cand_cap = 0, out_cap = 0;
   PinBuf stage_in, stage_out;
   // last-call bookkeeping
@@ -153,7 +157,7 @@ struct Lane {
     }
     for (int l = 0; l < LM_MAX_LEVELS; ++l) lmem[l].release();
     lmn.release();
-    cand.release(); result.release(); work.release(); work_order.release(); dump.release(); dbg_recs.release();
+    cand.release(); work.release(); work_order.release(); dump.release(); dbg_recs.release();
     stage_in.release(); stage_out.release();
     if (gexec) cudaGraphExecDestroy(gexec);
     for (int i = 0; i < 6; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
@@ -203,6 +207,11 @@ struct lm_detector {
   uint8_t sim_lut[256];
   uint8_t normal_lut[8000];
   DevBuf d_resp_all, d_normal_lut;
+  // result blocks of all lanes, contiguous (lane stride result_stride): a sharded caller exchanges the survivors of
+  // LM_LANES frames in flight with ONE collective over this region and no staging copies
+  DevBuf results_all;
+  size_t result_stride = 0;
+  uint32_t out_cap = 0, device_out_cap = 2048;
   bool luts_dirty = true;
   Lane lane[LM_LANES];
   Pack pack;
@@ -798,13 +807,30 @@ static const size_t kStatsBytes = 16;
 static size_t result_bytes(const Lane& ln) { return sizeof(ResultHeader) + (size_t)ln.out_cap * sizeof(lm_raw_match); }
 static uint8_t* block_ptr(const Lane& ln) { return ln.result.as<uint8_t>() + kStatsBytes; }
 
-static int ensure_match_buffers(Lane& ln, uint32_t cand_cap, uint32_t out_cap) {
+static int ensure_match_buffers(lm_detector* d, Lane& ln, uint32_t cand_cap, uint32_t out_cap) {
   if (cand_cap > ln.cand_cap) {
     if (ln.cand.ensure((size_t)cand_cap * sizeof(Cand)) != LM_OK) return LM_E_CUDA;
     ln.cand_cap = cand_cap;
   }
-  if (out_cap > ln.out_cap) ln.out_cap = out_cap;
-  if (ln.result.ensure(kStatsBytes + result_bytes(ln)) != LM_OK) return LM_E_CUDA;
+  if (out_cap > d->out_cap || d->results_all.p == nullptr) {
+    // every lane's block moves: nothing may be in flight (callers' streams included); blocks whose results have not
+    // been downloaded yet (other lanes of a batch) keep their contents
+    CU(cudaDeviceSynchronize());
+    const size_t old_stride = d->result_stride;
+    DevBuf old = d->results_all;
+    d->results_all = DevBuf();
+    d->out_cap = std::max(out_cap, d->out_cap);
+    d->result_stride = (kStatsBytes + sizeof(ResultHeader) + (size_t)d->out_cap * sizeof(lm_raw_match) + 255) & ~(size_t)255;
+    if (d->results_all.ensure(d->result_stride * LM_LANES) != LM_OK) { d->results_all = old; return LM_E_CUDA; }
+    CU(cudaMemset(d->results_all.p, 0, d->results_all.cap));
+    for (int i = 0; i < LM_LANES; ++i) {
+      uint8_t* fresh = d->results_all.as<uint8_t>() + (size_t)i * d->result_stride;
+      if (old.p) CU(cudaMemcpy(fresh, old.as<uint8_t>() + (size_t)i * old_stride, std::min(old_stride, d->result_stride), cudaMemcpyDeviceToDevice));
+      d->lane[i].result.p = fresh;
+      d->lane[i].out_cap = d->out_cap;
+    }
+    old.release();
+  }
   if (ln.stage_out.ensure(kStatsBytes + result_bytes(ln)) != LM_OK) return LM_E_CUDA;
   return LM_OK;
 }
@@ -984,7 +1010,7 @@ static int match_front(lm_detector* d, Lane& ln, const Query* queries, int n_q, 
   std::vector<lm_raw_match> raw;
   uint32_t n_cands = 0;
   for (int attempt = 0;; ++attempt) {
-    if (ensure_match_buffers(ln, cand_cap, out_cap) != LM_OK) return LM_E_CUDA;
+    if (ensure_match_buffers(d, ln, cand_cap, out_cap) != LM_OK) return LM_E_CUDA;
     if (attempt > 0) CU(cudaEventRecord(ln.ev[2], ln.stream));
     if (enqueue_match(d, ln, *plan, queries, n_q, ln.stream, ln.ev[3]) != LM_OK) return LM_E_CUDA;
     CU(cudaEventRecord(ln.ev[4], ln.stream));
@@ -1151,6 +1177,7 @@ void lm_destroy(lm_detector* d) {
       d->lane[i].destroy();
     }
     d->pack.release();
+    d->results_all.release();
     d->d_resp_all.release(); d->d_normal_lut.release();
   }
   delete d;
@@ -1350,6 +1377,7 @@ int lm_set_option(lm_detector* d, const char* key, int value) {
   else if (k == "timing") d->timing = value;
   else if (k == "prune") d->prune = value;
   else if (k == "graphs") d->graphs = value;
+  else if (k == "device_out_cap") d->device_out_cap = (uint32_t)std::max(16, value);
   else if (k == "frontend_variant") { d->frontend_variant = value; for (int i = 0; i < LM_LANES; ++i) d->lane[i].front_valid = false; }
   else return fail(LM_E_INVALID, "unknown option '%s'", key);
   return LM_OK;
@@ -1484,7 +1512,7 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
     Pack::Plan* plan = nullptr;
     rc = get_plan(d, qs, n_q, &plan);
     if (rc != LM_OK) return rc;
-    if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
+    if (ensure_match_buffers(d, ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
     if (enqueue_frame(d, ln, *plan, qs, n_q, ln.stream) != LM_OK) return LM_E_CUDA;
     CU(cudaEventRecord(ln.ev[4], ln.stream));
     busy[li] = true;
@@ -1544,7 +1572,7 @@ int lm_match_device_multi_lane(lm_detector* d, int lane_index, const void* const
   Pack::Plan* plan = nullptr;
   rc = get_plan(d, qs, n_queries, &plan);
   if (rc != LM_OK) return rc;
-  if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 18), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
+  if (ensure_match_buffers(d, ln, std::max<uint32_t>(ln.cand_cap, 1u << 18), std::max<uint32_t>(ln.out_cap, d->device_out_cap)) != LM_OK) return LM_E_CUDA;
   if (enqueue_frame(d, ln, *plan, qs, n_queries, s) != LM_OK) return LM_E_CUDA;
   *d_records = block_ptr(ln);
   if (record_bytes_capacity) *record_bytes_capacity = result_bytes(ln);
@@ -1556,6 +1584,46 @@ int lm_match_device_multi(lm_detector* d, const void* const* d_sources, int n_so
                           size_t* record_bytes_capacity) {
   return lm_match_device_multi_lane(d, 0, d_sources, n_sources, rows, cols, queries, n_queries, stream, d_records,
                                     record_bytes_capacity);
+}
+
+int lm_device_result_region(lm_detector* d, const void** base, size_t* lane_stride, int* n_lanes) {
+  if (!d || !base || !lane_stride || !n_lanes) return fail(LM_E_INVALID, "NULL argument");
+  if (set_device(d) != LM_OK) return LM_E_CUDA;
+  if (d->results_all.p == nullptr &&
+      ensure_match_buffers(d, d->lane[0], std::max<uint32_t>(d->lane[0].cand_cap, 1u << 18), d->device_out_cap) != LM_OK)
+    return LM_E_CUDA;
+  *base = d->results_all.as<uint8_t>() + kStatsBytes;
+  *lane_stride = d->result_stride;
+  *n_lanes = LM_LANES;
+  return LM_OK;
+}
+
+int lm_copy_result_block(lm_detector* d, int lane_index, void* d_dst, size_t bytes, void* stream) {
+  if (!d || !d_dst) return fail(LM_E_INVALID, "NULL argument");
+  if (lane_index < 0 || lane_index >= LM_LANES || d->lane[lane_index].result.p == nullptr) return fail(LM_E_STATE, "lane %d has no result block yet", lane_index);
+  const Lane& ln = d->lane[lane_index];
+  if (bytes > result_bytes(ln)) return fail(LM_E_INVALID, "block is only %zu bytes", result_bytes(ln));
+  CU(cudaMemcpyAsync(d_dst, block_ptr(ln), bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return LM_OK;
+}
+
+int lm_match_device_stream(lm_detector* d, const void* const* d_sources, int n_frames, int n_sources, int rows, int cols,
+                           const lm_query* queries, int n_queries, void* const* streams, int n_streams, void* d_stage,
+                           size_t stage_slot_bytes) {
+  if (!d || !d_sources || !streams || n_frames < 0) return fail(LM_E_INVALID, "NULL argument");
+  if (n_streams < 1 || n_streams > LM_LANES) return fail(LM_E_INVALID, "number of streams must be 1..%d", LM_LANES);
+  for (int f = 0; f < n_frames; ++f) {
+    const int lane = f % n_streams;
+    const void* rec = nullptr;
+    int rc = lm_match_device_multi_lane(d, lane, d_sources + (size_t)f * n_sources, n_sources, rows, cols, queries, n_queries,
+                                        streams[lane], &rec, nullptr);
+    if (rc != LM_OK) return rc;
+    if (d_stage) {
+      rc = lm_copy_result_block(d, lane, static_cast<uint8_t*>(d_stage) + (size_t)f * stage_slot_bytes, stage_slot_bytes, streams[lane]);
+      if (rc != LM_OK) return rc;
+    }
+  }
+  return LM_OK;
 }
 
 int lm_match_device(lm_detector* d, const void* const* d_sources, int n_sources, int rows, int cols, float threshold,
@@ -1644,7 +1712,7 @@ int lm_debug_coarse_map(lm_detector* d, const char* class_id, int template_id, u
   if (local < 0) return fail(LM_E_NOTFOUND, "class '%s' template %d is not on this shard", class_id, template_id);
   const LevelGeom& gc = ln.geom.back();
   const int WH = gc.W * gc.H;
-  if (ensure_match_buffers(ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
+  if (ensure_match_buffers(d, ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
   const int pass_pos = coarse_positions_per_pass(d->coarse_variant);
   const int P = pk.h_ctpl[local].P;
   std::vector<uint2> tl;

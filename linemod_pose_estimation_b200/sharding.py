@@ -49,9 +49,9 @@ def unpack_blocks(gathered, world, capacity):
         blk = gathered[r * stride:(r + 1) * stride]
         hdr = blk[:RESULT_HEADER_BYTES].view(np.uint32)
         count = int(hdr[0])
-        if hdr[2] != 0:
-            raise RuntimeError("rank %d overflowed its device-side match buffer" % r)
-        if count > capacity:
+        if hdr[2] != 0 and count <= capacity:   # not the record block: the candidate list was truncated
+            raise RuntimeError("rank %d overflowed its device-side candidate list" % r)
+        if count > capacity:                    # (also when the device block itself overflowed: count keeps counting)
             need = max(need, count)
             continue
         raws.append(blk[RESULT_HEADER_BYTES:RESULT_HEADER_BYTES + count * RECORD_BYTES].view(RAW_DTYPE).copy())
@@ -95,16 +95,21 @@ class ShardedMatcher:
         dist.all_gather_into_tensor(buf, mine.contiguous(), group=self.group)
         return buf
 
+    def _ensure_send(self, n_slots, device):
+        nbytes = RESULT_HEADER_BYTES + self.capacity * RECORD_BYTES
+        if self._send_buf is None or self._send_buf.shape != (n_slots, nbytes) or self._send_buf.device != device:
+            self._send_buf = torch.empty((n_slots, nbytes), dtype=torch.uint8, device=device)
+            self._recv_buf = torch.empty((self.world, n_slots, nbytes), dtype=torch.uint8, device=device)
+            self._send_slots = [self._send_buf[i] for i in range(n_slots)]
+            self._send_ptrs = [self._send_buf[i].data_ptr() for i in range(n_slots)]
+            self._heads = {}
+        return nbytes
+
     def stage_block(self, block, slot, n_slots):
         """Streamed exchange, step 1 (device side, asynchronous): park a frame's survivor block in slot `slot` of this
         rank's send buffer.  One collective then moves `n_slots` frames at once (gather_staged): the per-frame payload
         is a few hundred bytes, so the exchange is launch-latency bound and is batched over frames, not over links."""
-        nbytes = RESULT_HEADER_BYTES + self.capacity * RECORD_BYTES
-        if self._send_buf is None or self._send_buf.shape != (n_slots, nbytes) or self._send_buf.device != block.device:
-            self._send_buf = torch.empty((n_slots, nbytes), dtype=torch.uint8, device=block.device)
-            self._recv_buf = torch.empty((self.world, n_slots, nbytes), dtype=torch.uint8, device=block.device)
-            self._send_slots = [self._send_buf[i] for i in range(n_slots)]
-            self._heads = {}
+        nbytes = self._ensure_send(n_slots, block.device)
         head = self._heads.get(block.data_ptr())   # the library's blocks are few and stable: keep their sliced views
         if head is None:
             head = self._heads[block.data_ptr()] = block[:nbytes]
@@ -125,18 +130,26 @@ class ShardedMatcher:
             host = self.gather_async(block).cpu().numpy()
             raws, need = unpack_blocks(host, self.world, self.capacity)
             if need == 0:
-                return raws
+                return raws, 0
             if need > (block.numel() - RESULT_HEADER_BYTES) // RECORD_BYTES:
-                raise RuntimeError("survivor block too small for %d records" % need)
+                return None, need          # the rank-local block itself is too small: the local match must be redone
             self.capacity = int(need * 1.25) + 64
+
+    def grow_local(self, need):
+        """Called on every rank when some rank's local survivor block overflowed (`need` records)."""
+        raise RuntimeError("survivor block too small for %d records" % need)
 
     def match(self, frame_tensors, queries):
         """frame_tensors: per-modality tensors, valid on rank 0 (other ranks pass same-shaped buffers).
         queries: [(threshold, [class ids])].  Returns the finalised match lists (one per query) on rank 0, None
         elsewhere."""
         self.broadcast_frame(frame_tensors)
-        block = self.local_match(frame_tensors, queries)
-        raws = self.gather(block)
+        while True:
+            block = self.local_match(frame_tensors, queries)
+            raws, need = self.gather(block)
+            if need == 0:
+                break
+            self.grow_local(need)
         if self.rank != 0:
             return None
         raw = np.concatenate(raws) if raws else np.zeros(0, RAW_DTYPE)
@@ -161,7 +174,133 @@ class ShardedDetector(ShardedMatcher):
         rec, cap = self.det.match_device_multi(ptrs, rows, cols, queries, stream=torch.cuda.current_stream().cuda_stream)
         return device_view(rec, cap, self.device)
 
+    def grow_local(self, need):
+        self.det.set_option("device_out_cap", int(need * 1.25) + 64)   # the library re-allocates its record blocks
+
     def frame_buffers(self, rows, cols, kinds):
         """Device buffers for one frame: uint8 [rows, cols, 3] for ColorGradient, int16-typed uint16 storage for depth."""
         return [torch.empty((rows, cols, 3), dtype=torch.uint8, device=self.device) if k == "cg"
                 else torch.empty((rows, cols), dtype=torch.int16, device=self.device) for k in kinds]
+
+    def stage_lane(self, lane, slot, n_slots, stream):
+        """stage_block for the CUDA matcher without torch ops: the library copies lane's survivor block into the send
+        slot on `stream` (lm_copy_result_block)."""
+        from . import _capi
+        nbytes = self._ensure_send(n_slots, self.device)
+        _capi.check(_capi.lib().lm_copy_result_block(self.det._h, lane, self._send_ptrs[slot], nbytes, stream))
+
+    # ------------------------------------------------------------------ streamed frames
+    def match_stream(self, host_frames, queries, kinds=("cg", "dn"), chunk=16, lanes=4):
+        """A stream of frames through the sharded matcher, pipelined: per chunk of `chunk` frames ONE broadcast per
+        modality (rank 0 uploads its pinned host frames into a device chunk buffer first) and ONE all-gather of the
+        survivor blocks; within a chunk `lanes` frames are in flight on as many streams; the upload + broadcast of chunk
+        c+1 overlaps the matching of chunk c (two chunk buffers).
+
+        host_frames: list of per-frame lists of numpy arrays (pinned for full copy speed); their contents matter on
+        rank 0 only, every rank must pass the same number of frames of the same shape.
+        Returns on rank 0 a list (per frame) of lists (per query) of finalised match arrays; None elsewhere."""
+        import ctypes as C
+
+        from . import _capi
+        n = len(host_frames)
+        if n == 0:
+            return [] if self.rank == 0 else None
+        rows, cols = host_frames[0][0].shape[:2]
+        if getattr(self, "_stream_state", None) is None or self._stream_state["key"] != (rows, cols, kinds, chunk, lanes):
+            bufs = [[torch.empty((chunk, rows, cols, 3), dtype=torch.uint8, device=self.device) if k == "cg"
+                     else torch.empty((chunk, rows, cols), dtype=torch.int16, device=self.device) for k in kinds]
+                    for _ in range(2)]
+            self._stream_state = {
+                "key": (rows, cols, kinds, chunk, lanes), "bufs": bufs,
+                "copy": torch.cuda.Stream(device=self.device),
+                "lanes": [torch.cuda.Stream(device=self.device) for _ in range(lanes)],
+                "ready": [torch.cuda.Event() for _ in range(2)], "free": [None, None],
+            }
+            st0 = self._stream_state
+            st0["stream_ptrs"] = (C.c_void_p * lanes)(*[s.cuda_stream for s in st0["lanes"]])
+            st0["ptrs"] = [(C.c_void_p * (chunk * len(kinds)))(*[bufs[b][m][j].data_ptr() for j in range(chunk)
+                                                                 for m in range(len(kinds))]) for b in range(2)]
+        st = self._stream_state
+        qarr, _qkeep = _capi.query_array(queries)
+        lib = _capi.lib()
+        n_q = len(queries)
+        n_chunks = (n + chunk - 1) // chunk
+
+        def stage(c):   # upload (rank 0) + broadcast of chunk c into buffer c & 1, on the copy stream
+            b, lo = c & 1, c * chunk
+            g = min(chunk, n - lo)
+            with torch.cuda.stream(st["copy"]):
+                if st["free"][b] is not None:
+                    st["copy"].wait_event(st["free"][b])      # the matching of chunk c-2 has finished reading this buffer
+                for m, k in enumerate(kinds):
+                    if self.rank == 0:
+                        for j in range(g):
+                            a = host_frames[lo + j][m]
+                            src = torch.from_numpy(a if k == "cg" else a.view(np.int16))
+                            st["bufs"][b][m][j].copy_(src, non_blocking=True)
+                    if self.world > 1:
+                        dist.broadcast(st["bufs"][b][m][:g].view(torch.uint8), src=0, group=self.group)
+                st["ready"][b].record(st["copy"])
+
+        def run(c):     # matching of chunk c on the lane streams, survivors staged, one all-gather -> device tensor
+            b, lo = c & 1, c * chunk
+            g = min(chunk, n - lo)
+            for s in st["lanes"]:
+                s.wait_event(st["ready"][b])
+            nbytes = self._ensure_send(chunk, self.device)
+            ptrs = st["ptrs"][b]
+            _capi.check(lib.lm_match_device_stream(self.det._h, ptrs, g, len(kinds), rows, cols, qarr, n_q, st["stream_ptrs"],
+                                                   lanes, self._send_ptrs[0], nbytes))
+            main = st["lanes"][0]
+            for s in st["lanes"][1:]:
+                main.wait_stream(s)
+            with torch.cuda.stream(main):
+                recv = self.gather_staged()
+                host = torch.empty(recv.shape, dtype=torch.uint8, pin_memory=True)
+                host.copy_(recv, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(main)
+            for s in st["lanes"][1:]:
+                s.wait_stream(main)                           # the send buffer is reused by the next chunk
+            st["free"][b] = done
+            return host, done, g, lo
+
+        def finish(host, done, g, lo):
+            done.synchronize()
+            arr = host.numpy()
+            out = []
+            for j in range(g):
+                # every rank sees every header, so all ranks agree on which frames outgrew the staged capacity
+                raws, need = unpack_blocks(np.ascontiguousarray(arr[:, j]).reshape(-1), arr.shape[0], self.capacity)
+                if need:   # rare: this frame again through the per-frame path, which grows its exchange (not ours)
+                    keep = self.capacity
+                    if not hasattr(self, "_redo_bufs") or self._redo_bufs[0].shape[:2] != (rows, cols):
+                        self._redo_bufs = self.frame_buffers(rows, cols, kinds)
+                    if self.rank == 0:
+                        for m, k in enumerate(kinds):
+                            a = host_frames[lo + j][m]
+                            self._redo_bufs[m].copy_(torch.from_numpy(a if k == "cg" else a.view(np.int16)))
+                    res = self.match(self._redo_bufs, queries)
+                    self.capacity = keep
+                    out.append(res)
+                    continue
+                if self.rank != 0:
+                    out.append(None)
+                    continue
+                raw = np.concatenate(raws) if raws else np.zeros(0, RAW_DTYPE)
+                tag = raw["order_key"] >> 28
+                out.append([self.finalize(raw[tag == q]) for q in range(n_q)])
+            return out
+
+        results = []
+        stage(0)
+        pending = None
+        for c in range(n_chunks):
+            if c + 1 < n_chunks:
+                stage(c + 1)
+            cur = run(c)
+            if pending is not None:
+                results.extend(finish(*pending))
+            pending = cur
+        results.extend(finish(*pending))
+        return results if self.rank == 0 else None

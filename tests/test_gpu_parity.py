@@ -424,3 +424,55 @@ def test_batch_multi_equals_per_frame_multi():
             total += len(g)
     assert total > 0
     assert det.match_batch_multi([], queries) == []
+
+
+def test_sharded_stream_single_rank():
+    """ShardedDetector.match_stream (chunked upload, lanes, staged survivor exchange) at world size 1 == lm_match_multi per
+    frame; the collectives themselves are exercised at world size 2 on CPU (tests/test_sharding_gloo.py) and by bench.py."""
+    from linemod_pose_estimation_b200.sharding import ShardedDetector
+    orc, det, views = _pair(n_views=8, n_random=40, seed=89, classes=("cpu_binary", "memoryChip2"))
+    queries = [(88.0, ["memoryChip2"]), (66.0, [])]
+    frames = [list(synth.compose_scene(5000 + i, views[:5])[:2]) for i in range(11)]
+    sd = ShardedDetector(det, capacity=256)   # 66 % over all classes outgrows 256 records: those frames take the fallback
+    got = sd.match_stream(frames, queries, chunk=4, lanes=3)
+    assert len(got) == len(frames)
+    total = 0
+    for f, per_query in zip(frames, got):
+        for g, s in zip(per_query, det.match_multi(f, queries)):
+            common.assert_matches_equal(g, s, "streamed vs single")
+            total += len(g)
+    assert total > 0
+
+
+def test_lane_result_blocks_are_one_region():
+    """lm_device_result_region: the record blocks of all lanes are contiguous, lane stride apart, and are the blocks
+    lm_match_device_multi_lane reports; lm_copy_result_block copies a block's head."""
+    import ctypes as C
+
+    import torch
+    from linemod_pose_estimation_b200 import _capi
+    from linemod_pose_estimation_b200.sharding import device_view
+    orc, det, views = _pair(n_views=6, n_random=20, seed=97)
+    bgr, depth, _ = synth.compose_scene(6001, views[:4])
+    dev = torch.device("cuda", 0)
+    d_bgr, d_depth = torch.from_numpy(bgr).to(dev), torch.from_numpy(depth.view(np.int16)).to(dev)
+    lib = _capi.lib()
+    base, stride, n_lanes = C.c_void_p(), C.c_size_t(), C.c_int()
+    _capi.check(lib.lm_device_result_region(det._h, C.byref(base), C.byref(stride), C.byref(n_lanes)))
+    assert n_lanes.value >= 2 and stride.value % 256 == 0
+    qarr, _keep = _capi.query_array([(88.0, [])])
+    ptrs = (C.c_void_p * 2)(d_bgr.data_ptr(), d_depth.data_ptr())
+    s = torch.cuda.current_stream().cuda_stream
+    want = orc.match([bgr, depth], 88.0)   # 364 survivors before sort/unique: inside the 512 records copied below
+    for lane in range(n_lanes.value):
+        rec, cap = C.c_void_p(), C.c_size_t()
+        _capi.check(lib.lm_match_device_multi_lane(det._h, lane, ptrs, 2, 480, 640, qarr, 1, C.c_void_p(s), C.byref(rec), C.byref(cap)))
+        assert rec.value == base.value + lane * stride.value
+        dst = torch.zeros(16 + 512 * 32, dtype=torch.uint8, device=dev)
+        _capi.check(lib.lm_copy_result_block(det._h, lane, dst.data_ptr(), dst.numel(), s))
+        block = dst.cpu().numpy()
+        hdr = block[:16].view(np.uint32)
+        assert hdr[2] == 0 and 0 < hdr[0] <= 512
+        from linemod_pose_estimation_b200 import RAW_DTYPE
+        raw = block[16:16 + int(hdr[0]) * 32].view(RAW_DTYPE).copy()
+        common.assert_matches_equal(det.finalize_raw(raw), want, "lane %d" % lane)
