@@ -97,6 +97,12 @@ int lm_create(const int32_t* T, int levels, const lm_modality_desc* mods, int M,
 int lm_create_from_yaml(const char* path, lm_detector** out);
 /* writeLinemod(): Detector::write + writeClass per class into one file       src/renderer.cpp:56-70 */
 int lm_write_yaml(const lm_detector* det, const char* path);
+/* Binary template cache: the detector of a templates.yml as flat, checksummed arrays.  The reference's service calls
+ * readLinemod() -- a YAML parse of thousands of templates -- on every request
+ * (src/linemod_ensenso_detect_3_mult_detect_service.cpp:1784,1851); a cache written once with lm_write_cache loads
+ * without parsing.  Same model either way (templates, classes, modalities, T): matching results are identical. */
+int lm_create_from_cache(const char* path, lm_detector** out);
+int lm_write_cache(const lm_detector* det, const char* path);
 /* Detector::readClasses(class_ids, format) / writeClasses(format), format default "templates_%s.yml.gz" */
 int lm_read_classes(lm_detector* det, const char* const* class_ids, int n_ids, const char* format);
 int lm_write_classes(const lm_detector* det, const char* format);

@@ -47,7 +47,7 @@ RESULT_HEADER_BYTES = 16
 
 # every symbol include/linemod_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTS = [
-    "lm_create", "lm_create_from_yaml", "lm_write_yaml", "lm_read_classes", "lm_write_classes", "lm_destroy",
+    "lm_create", "lm_create_from_yaml", "lm_write_yaml", "lm_create_from_cache", "lm_write_cache", "lm_read_classes", "lm_write_classes", "lm_destroy",
     "lm_last_error", "lm_alloc_pinned", "lm_free_pinned", "lm_device", "lm_pyramid_levels", "lm_get_T",
     "lm_num_modalities", "lm_get_modality", "lm_num_classes", "lm_num_templates", "lm_class_id", "lm_get_templates",
     "lm_add_template", "lm_add_template_from_quantized", "lm_add_synthetic_template", "lm_match", "lm_match_multi", "lm_match_batch", "lm_match_batch_multi", "lm_free_matches",
@@ -78,6 +78,8 @@ def lib():
     L.lm_create.argtypes = [C.POINTER(C.c_int32), ci, C.POINTER(LmModalityDesc), ci, C.POINTER(vp)]
     L.lm_create_from_yaml.argtypes = [cp, C.POINTER(vp)]
     L.lm_write_yaml.argtypes = [vp, cp]
+    L.lm_create_from_cache.argtypes = [cp, C.POINTER(vp)]
+    L.lm_write_cache.argtypes = [vp, cp]
     L.lm_read_classes.argtypes = [vp, C.POINTER(cp), ci, cp]
     L.lm_write_classes.argtypes = [vp, cp]
     L.lm_destroy.argtypes = [vp]

@@ -1134,6 +1134,26 @@ int lm_create_from_yaml(const char* path, lm_detector** out) {
   return LM_OK;
 }
 
+int lm_create_from_cache(const char* path, lm_detector** out) {
+  if (!out || !path) return fail(LM_E_INVALID, "NULL argument");
+  *out = nullptr;
+  lm_detector* d = new lm_detector();
+  std::string err;
+  if (!load_model_cache(path, d->model, err)) { delete d; return fail(LM_E_IO, "%s", err.c_str()); }
+  int rc = create_common(d);
+  if (rc != LM_OK) { delete d; return rc; }
+  refresh_class_cache(d);
+  *out = d;
+  return LM_OK;
+}
+
+int lm_write_cache(const lm_detector* d, const char* path) {
+  if (!d || !path) return fail(LM_E_INVALID, "NULL argument");
+  std::string err;
+  if (!save_model_cache(d->model, path, err)) return fail(LM_E_IO, "%s", err.c_str());
+  return LM_OK;
+}
+
 int lm_write_yaml(const lm_detector* d, const char* path) {
   if (!d || !path) return fail(LM_E_INVALID, "NULL argument");
   std::string err;

@@ -402,4 +402,114 @@ bool save_class_file(const HostModel& model, const std::string& class_id, const 
   return w.save(path, err);
 }
 
+// ------------------------------------------------------------------------------------------------ binary cache
+// the reference's service re-parses templates.yml on every request
+// (/root/reference/src/linemod_ensenso_detect_3_mult_detect_service.cpp:1784,1851 -> readLinemod).  The cache holds the
+// same model as flat little-endian arrays: a detector loads from it with a few large reads instead of a YAML parse.
+//   header  : "LMB2CACH", u32 version (1), u32 levels, u32 modalities, u32 classes, u64 payload bytes, u64 FNV-1a of payload
+//   payload : i32 T[levels]; lm_modality_desc mods[modalities];
+//             per class: u32 name length, name bytes, u32 templates; per template pyramid, per (level, modality):
+//             i32 width, height, pyramid_level, n_features, then n_features x (i16 x, i16 y, u8 label) packed in 5 bytes
+namespace {
+const char kCacheMagic[8] = {'L', 'M', 'B', '2', 'C', 'A', 'C', 'H'};
+uint64_t fnv1a(const uint8_t* p, size_t n) {
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+template <class T> void put(std::vector<uint8_t>& b, const T& v) {
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(&v);
+  b.insert(b.end(), p, p + sizeof(T));
+}
+struct Cursor {
+  const uint8_t* p; const uint8_t* end; bool ok = true;
+  template <class T> T get() {
+    T v = T();
+    if ((size_t)(end - p) < sizeof(T)) { ok = false; return v; }
+    std::memcpy(&v, p, sizeof(T)); p += sizeof(T);
+    return v;
+  }
+};
+}  // namespace
+
+bool save_model_cache(const HostModel& model, const std::string& path, std::string& err) {
+  std::vector<uint8_t> pay;
+  for (int t : model.T) put<int32_t>(pay, t);
+  for (const lm_modality_desc& m : model.mods) put(pay, m);
+  for (const auto& kv : model.classes) {
+    put<uint32_t>(pay, (uint32_t)kv.first.size());
+    pay.insert(pay.end(), kv.first.begin(), kv.first.end());
+    put<uint32_t>(pay, (uint32_t)kv.second.size());
+    for (const TemplatePyramid& tp : kv.second) {
+      if ((int)tp.size() != model.levels() * model.M()) { err = "class '" + kv.first + "' holds a template pyramid of the wrong size"; return false; }
+      for (const Template& t : tp) {
+        put<int32_t>(pay, t.width); put<int32_t>(pay, t.height); put<int32_t>(pay, t.pyramid_level);
+        put<int32_t>(pay, (int32_t)t.features.size());
+        for (const Feature& f : t.features) {
+          if (f.x < -32768 || f.x > 32767 || f.y < -32768 || f.y > 32767 || f.label < 0 || f.label > 255) { err = "feature outside the cache's value range"; return false; }
+          put<int16_t>(pay, (int16_t)f.x); put<int16_t>(pay, (int16_t)f.y); put<uint8_t>(pay, (uint8_t)f.label);
+        }
+      }
+    }
+  }
+  std::vector<uint8_t> hdr;
+  hdr.insert(hdr.end(), kCacheMagic, kCacheMagic + 8);
+  put<uint32_t>(hdr, 1u); put<uint32_t>(hdr, (uint32_t)model.levels()); put<uint32_t>(hdr, (uint32_t)model.M());
+  put<uint32_t>(hdr, (uint32_t)model.classes.size());
+  put<uint64_t>(hdr, (uint64_t)pay.size()); put<uint64_t>(hdr, fnv1a(pay.data(), pay.size()));
+  FILE* f = std::fopen(path.c_str(), "wb");
+  if (!f) { err = "cannot open '" + path + "' for writing"; return false; }
+  bool ok = std::fwrite(hdr.data(), 1, hdr.size(), f) == hdr.size() && std::fwrite(pay.data(), 1, pay.size(), f) == pay.size();
+  ok = (std::fclose(f) == 0) && ok;
+  if (!ok) err = "short write to '" + path + "'";
+  return ok;
+}
+
+bool load_model_cache(const std::string& path, HostModel& model, std::string& err) {
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) { err = "cannot open '" + path + "'"; return false; }
+  uint8_t hdr[40];
+  if (std::fread(hdr, 1, sizeof(hdr), f) != sizeof(hdr) || std::memcmp(hdr, kCacheMagic, 8) != 0) {
+    std::fclose(f); err = path + ": not a linemod_b200 template cache"; return false;
+  }
+  uint32_t version, levels, M, n_classes; uint64_t bytes, sum;
+  std::memcpy(&version, hdr + 8, 4); std::memcpy(&levels, hdr + 12, 4); std::memcpy(&M, hdr + 16, 4);
+  std::memcpy(&n_classes, hdr + 20, 4); std::memcpy(&bytes, hdr + 24, 8); std::memcpy(&sum, hdr + 32, 8);
+  if (version != 1 || levels < 1 || levels > LM_MAX_LEVELS || M < 1 || M > LM_MAX_MODALITIES || bytes > (1ull << 34)) {
+    std::fclose(f); err = path + ": unsupported cache header"; return false;
+  }
+  std::vector<uint8_t> pay((size_t)bytes);
+  const bool read_ok = std::fread(pay.data(), 1, pay.size(), f) == pay.size();
+  std::fclose(f);
+  if (!read_ok || fnv1a(pay.data(), pay.size()) != sum) { err = path + ": truncated or corrupted cache (checksum mismatch)"; return false; }
+  Cursor c{pay.data(), pay.data() + pay.size()};
+  HostModel fresh;
+  for (uint32_t l = 0; l < levels; ++l) fresh.T.push_back(c.get<int32_t>());
+  for (uint32_t m = 0; m < M; ++m) fresh.mods.push_back(c.get<lm_modality_desc>());
+  for (uint32_t k = 0; k < n_classes && c.ok; ++k) {
+    const uint32_t len = c.get<uint32_t>();
+    if (!c.ok || (size_t)(c.end - c.p) < len) { c.ok = false; break; }
+    std::string id(reinterpret_cast<const char*>(c.p), len);
+    c.p += len;
+    const uint32_t n_templates = c.get<uint32_t>();
+    std::vector<TemplatePyramid>& tps = fresh.classes[id];
+    tps.resize(n_templates);
+    for (uint32_t t = 0; t < n_templates && c.ok; ++t) {
+      TemplatePyramid& tp = tps[t];
+      tp.resize((size_t)levels * M);
+      for (Template& tm : tp) {
+        tm.width = c.get<int32_t>(); tm.height = c.get<int32_t>(); tm.pyramid_level = c.get<int32_t>();
+        const int32_t nf = c.get<int32_t>();
+        if (!c.ok || nf < 0 || nf > LM_MAX_FEATURES || (size_t)(c.end - c.p) < (size_t)nf * 5) { c.ok = false; break; }
+        tm.features.resize((size_t)nf);
+        for (Feature& ft : tm.features) { ft.x = c.get<int16_t>(); ft.y = c.get<int16_t>(); ft.label = c.get<uint8_t>(); }
+      }
+    }
+  }
+  if (!c.ok || c.p != c.end) { err = path + ": malformed cache payload"; return false; }
+  fresh.version = model.version + 1;
+  model = fresh;
+  return true;
+}
+
 }  // namespace lm

@@ -53,4 +53,8 @@ bool save_detector_yaml(const HostModel& model, const std::string& path, std::st
 bool load_class_file(const std::string& path, HostModel& model, std::string& err);           // readClasses(): one file
 bool save_class_file(const HostModel& model, const std::string& class_id, const std::string& path, std::string& err);
 
+// Binary template cache: the same model as flat arrays, checksummed; loads without a YAML parse.
+bool save_model_cache(const HostModel& model, const std::string& path, std::string& err);
+bool load_model_cache(const std::string& path, HostModel& model, std::string& err);
+
 }  // namespace lm

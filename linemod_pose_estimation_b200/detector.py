@@ -72,6 +72,16 @@ class Detector:
         """writeLinemod(): Detector::write + writeClass per class, single file."""
         check(lib().lm_write_yaml(self._h, str(path).encode()))
 
+    @classmethod
+    def read_cache(cls, path):
+        """Binary template cache written by write_cache(): the same detector without a YAML parse."""
+        h = C.c_void_p()
+        check(lib().lm_create_from_cache(str(path).encode(), C.byref(h)))
+        return cls(_handle=h)
+
+    def write_cache(self, path):
+        check(lib().lm_write_cache(self._h, str(path).encode()))
+
     def readClasses(self, class_ids, fmt="templates_%s.yml.gz"):
         ids = [c.encode() for c in class_ids]
         arr = (C.c_char_p * max(1, len(ids)))(*ids)

@@ -242,3 +242,41 @@ def test_finalize_raw_equals_reference_sort_unique():
     common.assert_matches_equal(got, want)
     assert len(got) < n  # duplicates were merged
     assert np.all(np.diff(got["similarity"]) <= 0)
+
+
+def test_binary_template_cache_roundtrip_and_speed(tmp_path):
+    """lm_write_cache / lm_create_from_cache hold exactly the model of the templates.yml, reject corrupted
+    files, and load far faster than the YAML parse the reference's service repeats on every request."""
+    import time
+    rng = np.random.default_rng(17)
+    det = Detector()
+    for cid, n in (("memoryChip2", 700), ("cpu_binary", 300)):
+        for _ in range(n):
+            det.addSyntheticTemplate(synth.random_pyramid(rng), cid)
+    yml, cache = str(tmp_path / "templates.yml"), str(tmp_path / "templates.lmb2")
+    det.write(yml)
+    det.write_cache(cache)
+    t0 = time.perf_counter(); from_yaml = Detector.read(yml); t_yaml = time.perf_counter() - t0
+    t0 = time.perf_counter(); from_cache = Detector.read_cache(cache); t_cache = time.perf_counter() - t0
+    assert from_cache.classIds() == from_yaml.classIds() == det.classIds()
+    assert from_cache.pyramidLevels() == 2 and [from_cache.getT(l) for l in range(2)] == [5, 8]
+    for a, b in zip(from_cache.getModalities(), det.getModalities()):
+        assert bytes(a) == bytes(b)
+    for cid in det.classIds():
+        assert from_cache.numTemplates(cid) == det.numTemplates(cid)
+        for tid in range(0, det.numTemplates(cid), 37):
+            for x, y, z in zip(from_cache.getTemplates(cid, tid), det.getTemplates(cid, tid), from_yaml.getTemplates(cid, tid)):
+                assert x[:3] == y[:3] == z[:3] and np.array_equal(x[3], y[3]) and np.array_equal(x[3], z[3])
+    assert t_cache * 5 < t_yaml, (t_cache, t_yaml)
+    # the cache of a cache-loaded detector is byte-identical; corruption and truncation are detected
+    from_cache.write_cache(str(tmp_path / "again.lmb2"))
+    blob = open(cache, "rb").read()
+    assert open(str(tmp_path / "again.lmb2"), "rb").read() == blob
+    bad = bytearray(blob); bad[len(bad) // 2] ^= 0x40
+    open(str(tmp_path / "bad.lmb2"), "wb").write(bytes(bad))
+    open(str(tmp_path / "short.lmb2"), "wb").write(blob[:len(blob) - 100])
+    open(str(tmp_path / "notcache.lmb2"), "wb").write(b"%YAML:1.0\n" + b" " * 64)
+    for name in ("bad.lmb2", "short.lmb2", "notcache.lmb2", "missing.lmb2"):
+        with pytest.raises(LinemodError) as e:
+            Detector.read_cache(str(tmp_path / name))
+        assert e.value.code == -3
