@@ -290,7 +290,9 @@ def run_ours(args):
     fill_templates(lambda cid, b, d, m: det.addTemplate([b, d], cid, m)[0],
                    lambda cid, pyr: det.addSyntheticTemplate(pyr, cid), views, TEMPLATES_PER_CLASS * world)
     n_t = det.numTemplates()
-    sharded = ShardedDetector(det, capacity=1024)
+    if os.environ.get("LM_BENCH_COARSE_GRID"):
+        det.set_option("coarse_grid_limit", int(os.environ["LM_BENCH_COARSE_GRID"]))
+    sharded = ShardedDetector(det, capacity=256)   # records per frame and rank in the survivor exchange (grows / falls back)
     frames = make_frames(views, FRAME_POOL)
     evals_per_step = n_t * COARSE_POSITIONS
     n_q = len(QUERIES)
@@ -353,6 +355,10 @@ def run_ours(args):
 
     device_steps(0, max(args.warmup, GATHER_EVERY))
     barrier()
+    t_warm = time.perf_counter()     # untimed: keep the device busy for ~0.3 s so that clocks and caches are in steady state
+    while time.perf_counter() - t_warm < 0.3:
+        device_steps(0, 4 * GATHER_EVERY)
+        barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(streams[0])

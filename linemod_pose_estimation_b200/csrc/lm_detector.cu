@@ -1397,6 +1397,11 @@ int lm_set_option(lm_detector* d, const char* key, int value) {
   else if (k == "timing") d->timing = value;
   else if (k == "prune") d->prune = value;
   else if (k == "graphs") d->graphs = value;
+  else if (k == "coarse_grid_limit") {  // process-wide; recorded graphs hold the old grid
+    set_coarse_grid_limit(value);
+    for (int i = 0; i < LM_LANES; ++i)
+      if (d->lane[i].gexec) { cudaGraphExecDestroy(d->lane[i].gexec); d->lane[i].gexec = nullptr; }
+  }
   else if (k == "device_out_cap") d->device_out_cap = (uint32_t)std::max(16, value);
   else if (k == "frontend_variant") { d->frontend_variant = value; for (int i = 0; i < LM_LANES; ++i) d->lane[i].front_valid = false; }
   else return fail(LM_E_INVALID, "unknown option '%s'", key);

@@ -140,6 +140,7 @@ bool launch_spread_all(const SpreadParams& p, int total_blocks, int max_T, cudaS
 //   [12..] feature words, modality-major, grouped by class Q = (a >> 3) & 3 where a = nibble index of the window of
 //   lane 0: ((a >> 1) & ~15) | (a & 7)  -- aligned chunk byte offset | nibble shift
 void set_programmatic_launch(bool enabled);  // per thread; disabled while launches are recorded into a CUDA graph
+void set_coarse_grid_limit(int blocks);     // process-wide; 0 = no limit
 int coarse_positions_per_pass(int variant);
 int coarse_record_header_words();
 int coarse_record_max_words();

@@ -742,6 +742,11 @@ static cudaLaunchConfig_t pdl_config(int blocks, int threads, cudaStream_t s) {
 
 void set_programmatic_launch(bool enabled) { g_pdl_enabled = enabled; }
 
+// Upper bound on the production coarse kernel's persistent grid (0 = every resident CTA slot).  With several frames in
+// flight a smaller grid per frame lets the coarse kernels of consecutive frames share the SMs instead of queueing.
+static int g_coarse_grid_limit = 0;
+void set_coarse_grid_limit(int blocks) { g_coarse_grid_limit = blocks; }
+
 template <class K>
 static int resident_ctas(K kernel) {
   int per_sm = 0;
@@ -771,7 +776,9 @@ void launch_similarity_coarse(int variant, const uint8_t* lmc, const uint8_t* lm
                                                                        cand, hdr, cand_cap, dump, dump_stride);
   } else {
     static const int persistent = resident_ctas(k_similarity_coarse_rec);
-    cudaLaunchConfig_t cfg = pdl_config(min(blocks, persistent), 256, s);
+    int grid = min(blocks, persistent);
+    if (g_coarse_grid_limit > 0) grid = min(grid, g_coarse_grid_limit);
+    cudaLaunchConfig_t cfg = pdl_config(grid, 256, s);
     cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec, lmn, recs, rec_words, n_tiles, thr, M,
                        dump == nullptr ? prune : 0, cand, hdr, touched, cand_cap, dump, dump_stride);
   }

@@ -267,13 +267,15 @@ class ShardedDetector(ShardedMatcher):
 
         def finish(host, done, g, lo):
             done.synchronize()
-            arr = host.numpy()
+            arr = host.numpy()                                   # [world][chunk][block bytes]
+            world = arr.shape[0]
+            hdr = np.ascontiguousarray(arr[:, :g, :RESULT_HEADER_BYTES]).view(np.uint32).reshape(world, g, 4)
+            counts, overflow = hdr[:, :, 0].astype(np.int64), hdr[:, :, 2]
             out = []
             for j in range(g):
                 # every rank sees every header, so all ranks agree on which frames outgrew the staged capacity
-                raws, need = unpack_blocks(np.ascontiguousarray(arr[:, j]).reshape(-1), arr.shape[0], self.capacity)
-                if need:   # rare: this frame again through the per-frame path, which grows its exchange (not ours)
-                    keep = self.capacity
+                if (counts[:, j] > self.capacity).any():   # rare: this frame again through the per-frame path, which
+                    keep = self.capacity                     # grows its own exchange (and the device block if need be)
                     if not hasattr(self, "_redo_bufs") or self._redo_bufs[0].shape[:2] != (rows, cols):
                         self._redo_bufs = self.frame_buffers(rows, cols, kinds)
                     if self.rank == 0:
@@ -284,12 +286,19 @@ class ShardedDetector(ShardedMatcher):
                     self.capacity = keep
                     out.append(res)
                     continue
+                if overflow[:, j].any():
+                    raise RuntimeError("a rank overflowed its device-side candidate list")
                 if self.rank != 0:
                     out.append(None)
                     continue
-                raw = np.concatenate(raws) if raws else np.zeros(0, RAW_DTYPE)
-                tag = raw["order_key"] >> 28
-                out.append([self.finalize(raw[tag == q]) for q in range(n_q)])
+                parts = [arr[r, j, RESULT_HEADER_BYTES:RESULT_HEADER_BYTES + int(counts[r, j]) * RECORD_BYTES]
+                         for r in range(world) if counts[r, j]]
+                raw = np.concatenate(parts).view(RAW_DTYPE) if parts else np.zeros(0, RAW_DTYPE)
+                if n_q == 1:
+                    out.append([self.finalize(raw)])
+                else:
+                    tag = raw["order_key"] >> 28
+                    out.append([self.finalize(raw[tag == q]) for q in range(n_q)])
             return out
 
         results = []
