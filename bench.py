@@ -355,10 +355,10 @@ def run_ours(args):
 
     device_steps(0, max(args.warmup, GATHER_EVERY))
     barrier()
-    t_warm = time.perf_counter()     # untimed: keep the device busy for ~0.3 s so that clocks and caches are in steady state
-    while time.perf_counter() - t_warm < 0.3:
-        device_steps(0, 4 * GATHER_EVERY)
-        barrier()
+    # untimed: ~0.2 s of the same work so that clocks and caches are in steady state (a fixed frame count: every rank
+    # must issue the same number of collectives)
+    device_steps(0, 4096)
+    barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(streams[0])
