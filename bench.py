@@ -357,9 +357,9 @@ def run_ours(args):
     barrier()
     # untimed: ~0.2 s of the same work so that clocks and caches are in steady state (a fixed frame count: every rank
     # must issue the same number of collectives)
+    clocks = ClockSampler(local) if rank == 0 else None   # samples from here (same load as the timed regions) to the end of e2e
     device_steps(0, 4096)
     barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(streams[0])
     for st in streams[1:]:
