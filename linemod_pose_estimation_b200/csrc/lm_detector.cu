@@ -75,6 +75,9 @@ struct LevelGeom {
   int rows = 0, cols = 0, T = 0, W = 0, H = 0;
   size_t plane_stride = 0;
 };
+// Nibble-packed rows of a level start on 32-bit words when W and W*H are multiples of 8 (one word = 8 positions).
+static bool level_nibble_aligned(const LevelGeom& g) { return (g.W % 8) == 0 && ((size_t)g.W * g.H) % 8 == 0; }
+
 static size_t plane_stride_of(int T, int W, int H) {
   size_t wh = (size_t)W * H;
   return ((size_t)T * T * wh + wh + 16 * (size_t)W + 16 + 15) & ~(size_t)15;  // same rule as the oracle (App. D-2)
@@ -96,7 +99,8 @@ struct Lane {
   bool lm_ready = false;      // LM buffers sized + zero-tailed for (rows, cols)
   bool front_valid = false;
   bool debug_taps_written = false;
-  bool coarse_bytes_valid = false;  // the coarsest level's byte planes were written by the last front end
+  bool bytes_valid[LM_MAX_LEVELS] = {false, false, false, false};    // byte planes written by the last front end
+  bool nibbles_valid[LM_MAX_LEVELS] = {false, false, false, false};  // nibble planes written by the last front end
   std::vector<LevelGeom> geom;
   // per modality
   DevBuf src[LM_MAX_MODALITIES];       // level-0 source (BGR / depth)
@@ -111,7 +115,8 @@ struct Lane {
   DevBuf quantized[LM_MAX_LEVELS][LM_MAX_MODALITIES];
   DevBuf spread[LM_MAX_LEVELS][LM_MAX_MODALITIES], response[LM_MAX_LEVELS][LM_MAX_MODALITIES];  // parity taps only
   DevBuf lmem[LM_MAX_LEVELS];                          // [M][8][plane_stride] + slack
-  DevBuf lmn;                                          // coarsest level again, nibble-packed (two positions per byte)
+  DevBuf lmn[LM_MAX_LEVELS];                           // the same planes nibble-packed (two positions per byte): what the
+                                                       // matching kernels read when the level's rows are word-aligned
   // The GPU work of one frame (front end, header memset, coarse, refine) as an instantiated CUDA graph: the batch and
   // device-resident paths replay it instead of ~20 runtime calls per frame.  Valid while `gkey` matches.
   struct GraphKey {
@@ -156,7 +161,7 @@ struct Lane {
       }
     }
     for (int l = 0; l < LM_MAX_LEVELS; ++l) lmem[l].release();
-    lmn.release();
+    for (int l = 0; l < LM_MAX_LEVELS; ++l) lmn[l].release();
     cand.release(); work.release(); work_order.release(); dump.release(); dbg_recs.release();
     stage_in.release(); stage_out.release();
     if (gexec) cudaGraphExecDestroy(gexec);
@@ -216,7 +221,7 @@ struct lm_detector {
   Lane lane[LM_LANES];
   Pack pack;
   int shard_rank = 0, shard_world = 1;
-  int debug_taps = 0, coarse_variant = 0, timing = 1, frontend_variant = 0, prune = 1, graphs = 1;
+  int debug_taps = 0, coarse_variant = 0, refine_variant = 0, timing = 1, frontend_variant = 0, prune = 1, graphs = 1;
   std::vector<std::string> class_id_cache;
 };
 
@@ -315,10 +320,10 @@ static int ensure_lm_ws(lm_detector* d, Lane& ln, int rows, int cols) {
     if (ln.lmem[l].ensure(bytes) != LM_OK) return LM_E_CUDA;
     CU(cudaMemsetAsync(ln.lmem[l].p, 0, ln.lmem[l].cap, ln.stream));  // zero tails (and slack) once per geometry
   }
-  {
-    size_t bytes = ((size_t)M * 8 * geom[L - 1].plane_stride + kLmSlack) / 2;
-    if (ln.lmn.ensure(bytes) != LM_OK) return LM_E_CUDA;
-    CU(cudaMemsetAsync(ln.lmn.p, 0, ln.lmn.cap, ln.stream));
+  for (int l = 0; l < L; ++l) {
+    size_t bytes = ((size_t)M * 8 * geom[l].plane_stride + kLmSlack) / 2;
+    if (ln.lmn[l].ensure(bytes) != LM_OK) return LM_E_CUDA;
+    CU(cudaMemsetAsync(ln.lmn[l].p, 0, ln.lmn[l].cap, ln.stream));
   }
   ln.geom.swap(geom);
   ln.lm_ready = true;
@@ -493,13 +498,23 @@ static int run_quantize(lm_detector* d, Lane& ln, cudaStream_t main_stream) {
   return LM_OK;
 }
 
+// The refinement kernel reads nibble planes when every refinement level has word-aligned rows (refine_variant 0), byte
+// planes otherwise.
+static bool refine_nibbles(const lm_detector* d, const Lane& ln) {
+  if (d->refine_variant != 0) return false;
+  for (size_t l = 0; l + 1 < ln.geom.size(); ++l)
+    if (!level_nibble_aligned(ln.geom[l])) return false;
+  return true;
+}
+
 // [OCV] Detector::match front half: quantize (mask) -> spread -> computeResponseMaps -> linearize per level/modality.
 static int run_front(lm_detector* d, Lane& ln, cudaStream_t s) {
   const int L = d->model.levels(), M = d->model.M();
   if (run_quantize(d, ln, s) != LM_OK) return LM_E_CUDA;
   const bool taps = d->debug_taps != 0;
   if (taps && ensure_tap_ws(d, ln) != LM_OK) return LM_E_CUDA;
-  bool direct_nibbles = false, coarse_bytes = true;
+  // which planes this front end produces per level (staged A/B path: byte planes everywhere, nibbles packed from them)
+  bool nib[LM_MAX_LEVELS] = {false, false, false, false}, byt[LM_MAX_LEVELS] = {true, true, true, true};
   if (d->frontend_variant == 1) {
     for (int l = 0; l < L; ++l) {
       const LevelGeom& g = ln.geom[l];
@@ -515,15 +530,14 @@ static int run_front(lm_detector* d, Lane& ln, cudaStream_t s) {
     SpreadParams sp;
     std::memset(&sp, 0, sizeof(sp));
     sp.resp_all = d->d_resp_all.as<uint32_t>();
-    {
-      const LevelGeom& gc = ln.geom[L - 1];
-      direct_nibbles = (gc.W % 8) == 0 && ((size_t)gc.W * gc.H) % 8 == 0;  // word-aligned nibble rows
-      coarse_bytes = taps || d->coarse_variant == 1 || !direct_nibbles;
-    }
     int total = 0, max_T = 1;
     for (int l = 0; l < L; ++l) {
       const LevelGeom& g = ln.geom[l];
       max_T = std::max(max_T, g.T);
+      // nibble planes are written directly when every (orientation, phase) row starts on a word; the byte planes only
+      // when something reads them: parity taps, the byte A/B kernels, or a level whose rows are not word-aligned
+      nib[l] = l == L - 1 ? level_nibble_aligned(g) : refine_nibbles(d, ln);
+      byt[l] = taps || !nib[l] || (l == L - 1 && d->coarse_variant == 1);
       for (int m = 0; m < M; ++m) {
         SpreadEntry& e = sp.e[sp.n++];
         e.qraw = ln.quant_raw[l][m].as<uint8_t>();
@@ -531,12 +545,8 @@ static int run_front(lm_detector* d, Lane& ln, cudaStream_t s) {
         e.quantized = ln.quantized[l][m].as<uint8_t>();
         e.spread = taps ? ln.spread[l][m].as<uint8_t>() : nullptr;
         e.response = taps ? ln.response[l][m].as<uint8_t>() : nullptr;
-        e.lm = ln.lmem[l].as<uint8_t>() + (size_t)m * 8 * g.plane_stride;
-        e.lm_nib = nullptr;
-        if (l == L - 1) {  // the matcher reads the coarsest level nibble-packed; byte planes only when something wants them
-          if (direct_nibbles) e.lm_nib = ln.lmn.as<uint8_t>() + (size_t)m * 4 * g.plane_stride;
-          if (!coarse_bytes) e.lm = nullptr;
-        }
+        e.lm = byt[l] ? ln.lmem[l].as<uint8_t>() + (size_t)m * 8 * g.plane_stride : nullptr;
+        e.lm_nib = nib[l] ? ln.lmn[l].as<uint8_t>() + (size_t)m * 4 * g.plane_stride : nullptr;
         e.plane_stride = g.plane_stride;
         e.rows = g.rows; e.cols = g.cols; e.T = g.T; e.W = g.W; e.H = g.H; e.level = l; e.mask_cols0 = ln.cols;
         e.block_begin = total;
@@ -546,12 +556,17 @@ static int run_front(lm_detector* d, Lane& ln, cudaStream_t s) {
     if (!launch_spread_all(sp, total, max_T, s)) return fail(LM_E_INVALID, "T=%d needs too much shared memory", max_T);
     ++ln.launches;
   }
-  if (!direct_nibbles) {  // nibble-packed copy of the coarsest level from its byte planes
-    const LevelGeom& gc = ln.geom[L - 1];
-    launch_pack_nibbles(ln.lmem[L - 1].as<uint8_t>(), ln.lmn.as<uint8_t>(), (size_t)M * 8 * gc.plane_stride, s);
-    ++ln.launches;
+  for (int l = 0; l < L; ++l) {
+    // nibble planes the matching kernels will read but the spread kernel could not write directly: pack the byte planes
+    const bool wanted = l == L - 1 ? d->coarse_variant != 1 : refine_nibbles(d, ln);
+    if (wanted && !nib[l]) {
+      launch_pack_nibbles(ln.lmem[l].as<uint8_t>(), ln.lmn[l].as<uint8_t>(), (size_t)M * 8 * ln.geom[l].plane_stride, s);
+      ++ln.launches;
+      nib[l] = true;
+    }
+    ln.bytes_valid[l] = byt[l];
+    ln.nibbles_valid[l] = nib[l];
   }
-  ln.coarse_bytes_valid = coarse_bytes;
   CU(cudaGetLastError());
   ln.front_valid = true;
   ln.debug_taps_written = taps;
@@ -850,7 +865,7 @@ static int enqueue_match(lm_detector* d, Lane& ln, const Pack::Plan& plan, const
   std::memset(&rp, 0, sizeof(rp));
   std::memset(&qt, 0, sizeof(qt));
   for (int q = 0; q < n_q; ++q) { qt.v[q] = qs[q].threshold; rp.threshold[q] = qs[q].threshold; }
-  launch_similarity_coarse(d->coarse_variant, ln.lmem[L - 1].as<uint8_t>(), ln.lmn.as<uint8_t>(), pk.foff.as<uint32_t>(),
+  launch_similarity_coarse(d->coarse_variant, ln.lmem[L - 1].as<uint8_t>(), ln.lmn[d->model.levels() - 1].as<uint8_t>(), pk.foff.as<uint32_t>(),
                            pk.ctpl.as<CoarseTpl>(), plan.items.as<WorkItem>(), plan.tiles.as<uint2>(), plan_recs(plan), plan.rec_words,
                            plan.n_tiles, qt, M, d->prune, ln.cand.as<Cand>(), d_hdr, ln.result.as<unsigned long long>(),
                            ln.cand_cap, nullptr, 0, s);
@@ -860,13 +875,14 @@ static int enqueue_match(lm_detector* d, Lane& ln, const Pack::Plan& plan, const
   for (int l = 0; l < L - 1; ++l) {
     const LevelGeom& g = ln.geom[l];
     rp.level[l].lm = ln.lmem[l].as<uint8_t>();
+    rp.level[l].lmn = ln.lmn[l].as<uint8_t>();
     rp.level[l].tpl = pk.rtpl[l].as<RefineTpl>();
     rp.level[l].feats = pk.rfeats[l].as<uint32_t>();
     rp.level[l].plane_stride = g.plane_stride;
     rp.level[l].rows = g.rows; rp.level[l].cols = g.cols; rp.level[l].T = g.T; rp.level[l].W = g.W;
   }
-  launch_refine(rp, pk.ctpl.as<CoarseTpl>(), plan.items.as<WorkItem>(), ln.cand.as<Cand>(), ln.cand_cap, d_hdr, d_out,
-                ln.out_cap, s);
+  launch_refine(refine_nibbles(d, ln), rp, pk.ctpl.as<CoarseTpl>(), plan.items.as<WorkItem>(), ln.cand.as<Cand>(), ln.cand_cap,
+                d_hdr, d_out, ln.out_cap, s);
   ++ln.launches;
   CU(cudaGetLastError());
   return LM_OK;
@@ -888,7 +904,7 @@ static int enqueue_frame(lm_detector* d, Lane& ln, const Pack::Plan& plan, const
   key.shard_rank = d->shard_rank; key.shard_world = d->shard_world;
   for (int m = 0; m < d->model.M(); ++m) key.src[m] = ln.src_ptr[m];
   key.model_version = d->model.version; key.rows = ln.rows; key.cols = ln.cols; key.n_q = n_q;
-  key.variant = d->coarse_variant; key.prune = d->prune; key.frontend = d->frontend_variant;
+  key.variant = d->coarse_variant + 16 * d->refine_variant; key.prune = d->prune; key.frontend = d->frontend_variant;
   key.cand_cap = ln.cand_cap; key.out_cap = ln.out_cap;
   for (int q = 0; q < n_q; ++q) key.thr[q] = qs[q].threshold;
   if (ln.gexec == nullptr || std::memcmp(&key, &ln.gkey, sizeof(key)) != 0) {
@@ -1396,6 +1412,7 @@ int lm_set_option(lm_detector* d, const char* key, int value) {
   else if (k == "coarse_variant") { d->coarse_variant = value; for (int i = 0; i < LM_LANES; ++i) d->lane[i].front_valid = false; }
   else if (k == "timing") d->timing = value;
   else if (k == "prune") d->prune = value;
+  else if (k == "refine_variant") { d->refine_variant = value; for (int i = 0; i < LM_LANES; ++i) d->lane[i].front_valid = false; }
   else if (k == "graphs") d->graphs = value;
   else if (k == "coarse_grid_limit") {  // process-wide; recorded graphs hold the old grid
     set_coarse_grid_limit(value);
@@ -1698,11 +1715,11 @@ long lm_debug_fetch(lm_detector* d, int stage, int level, int modality, void* ds
       bytes = stage == LM_STAGE_SPREAD ? n : 8 * n; break;
     case LM_STAGE_LINEAR:
       bytes = 8 * g.plane_stride;
-      if (level == d->model.levels() - 1 && !ln.coarse_bytes_valid) {  // only the packed planes exist: unpack them
+      if (!ln.bytes_valid[level]) {  // only the packed planes exist: unpack them
         if (dst) {
           std::vector<uint8_t> packed(bytes / 2);
           if (cudaStreamSynchronize(ln.stream) != cudaSuccess ||
-              cudaMemcpy(packed.data(), ln.lmn.as<uint8_t>() + (size_t)modality * 4 * g.plane_stride, bytes / 2, cudaMemcpyDeviceToHost) != cudaSuccess)
+              cudaMemcpy(packed.data(), ln.lmn[level].as<uint8_t>() + (size_t)modality * 4 * g.plane_stride, bytes / 2, cudaMemcpyDeviceToHost) != cudaSuccess)
             return fail(LM_E_CUDA, "debug fetch failed: %s", cudaGetErrorString(cudaGetLastError()));
           uint8_t* o = static_cast<uint8_t*>(dst);
           for (size_t i = 0; i < bytes / 2; ++i) { o[2 * i] = packed[i] & 15; o[2 * i + 1] = packed[i] >> 4; }
@@ -1711,8 +1728,8 @@ long lm_debug_fetch(lm_detector* d, int stage, int level, int modality, void* ds
       }
       src = ln.lmem[level].as<uint8_t>() + (size_t)modality * 8 * g.plane_stride; break;
     case LM_STAGE_LINEAR_PACKED:
-      if (level != d->model.levels() - 1) return fail(LM_E_INVALID, "only the coarsest level has a packed copy");
-      src = ln.lmn.as<uint8_t>() + (size_t)modality * 4 * g.plane_stride; bytes = 4 * g.plane_stride; break;
+      if (!ln.nibbles_valid[level]) return fail(LM_E_STATE, "level %d has no packed planes (rows not word-aligned, or a byte kernel variant is selected)", level);
+      src = ln.lmn[level].as<uint8_t>() + (size_t)modality * 4 * g.plane_stride; bytes = 4 * g.plane_stride; break;
     default: return fail(LM_E_INVALID, "unknown stage %d", stage);
   }
   if (dst) {
@@ -1759,7 +1776,7 @@ int lm_debug_coarse_map(lm_detector* d, const char* class_id, int template_id, u
   // threshold 1e30 -> raw threshold saturates: nothing becomes a candidate, the kernel only dumps its accumulators
   QueryThresholds qt;
   for (int q = 0; q < LM_MAX_QUERIES; ++q) qt.v[q] = 1e30f;
-  launch_similarity_coarse(d->coarse_variant, ln.lmem[d->model.levels() - 1].as<uint8_t>(), ln.lmn.as<uint8_t>(),
+  launch_similarity_coarse(d->coarse_variant, ln.lmem[d->model.levels() - 1].as<uint8_t>(), ln.lmn[d->model.levels() - 1].as<uint8_t>(),
                            pk.foff.as<uint32_t>(), pk.ctpl.as<CoarseTpl>(),
                            ln.work.as<WorkItem>(), ln.work_order.as<uint2>(), ln.dbg_recs.as<uint32_t>(), rec_words,
                            (int)tl.size(), qt, d->model.M(),

@@ -35,7 +35,8 @@ struct RefineTpl {                        // one per (level < L-1, template)
 };
 
 struct RefineLevel {
-  const uint8_t* lm;                      // [M][8][plane_stride]
+  const uint8_t* lm;                      // [M][8][plane_stride] byte planes (valid when the byte kernel is used)
+  const uint8_t* lmn;                     // [M][8][plane_stride / 2] nibble-packed planes (valid when the nibble kernel is used)
   const RefineTpl* tpl;
   const uint32_t* feats;                  // (x + 4096) | (y + 4096) << 13 | label << 26
   unsigned long long plane_stride;
@@ -151,7 +152,7 @@ void launch_similarity_coarse(int variant, const uint8_t* lmc, const uint8_t* lm
                               int dump_stride, cudaStream_t s);
 // n_bytes (multiple of 16) of byte planes -> n_bytes / 2 of nibble-packed planes
 void launch_pack_nibbles(const uint8_t* lm_bytes, uint8_t* lm_nibbles, size_t n_bytes, cudaStream_t s);
-void launch_refine(const RefineParams& p, const CoarseTpl* ctpl, const WorkItem* items, const Cand* cand,
+void launch_refine(bool nibble_planes, const RefineParams& p, const CoarseTpl* ctpl, const WorkItem* items, const Cand* cand,
                    uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* out, uint32_t out_cap, cudaStream_t s);
 
 }  // namespace lmk

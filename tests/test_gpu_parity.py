@@ -134,6 +134,28 @@ def test_coarse_kernel_variants(variant):
     assert len(want) > 0
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+def test_refine_kernel_variants(variant):
+    """0: refinement on nibble-packed planes (production when every refinement level has word-aligned rows), 1: on byte
+    planes.  Loose thresholds so that thousands of candidates are refined; both must give the oracle's lists, and the
+    packed planes of the refinement level must be its byte planes two positions per byte."""
+    orc, det, views = _pair(n_views=8, n_random=60, seed=23, classes=("a", "b"))
+    det.set_option("refine_variant", variant)
+    for seed, thr in ((1005, 86.0), (1006, 58.0)):
+        bgr, depth, _ = synth.compose_scene(seed, views[:5])
+        want = orc.match([bgr, depth], thr, keep_candidates=True)
+        got = det.match([bgr, depth], thr)
+        common.assert_matches_equal(det.last_presort(), orc.last_presort(), "variant %d thr %g pre-sort" % (variant, thr))
+        common.assert_matches_equal(got, want, "variant %d thr %g" % (variant, thr))
+    assert len(orc.last_candidates()) > 500
+    for m in range(2):
+        want = orc.fetch(Stage.LINEAR, 0, m)
+        assert np.array_equal(det.fetch(Stage.LINEAR, 0, m), want)   # unpacked from the nibble planes when variant == 0
+        if variant == 0:
+            packed = det.fetch(Stage.LINEAR_PACKED, 0, m)
+            assert np.array_equal(packed & 15, want[:, 0::2]) and np.array_equal(packed >> 4, want[:, 1::2])
+
+
 @pytest.mark.parametrize("threshold", [92.0, 80.0, 60.0])
 def test_match_lists_identical(threshold):
     orc, det, views = _pair(n_views=10, n_random=60, seed=13, classes=("cpu_binary", "memoryChip2"))
