@@ -715,23 +715,19 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams
   }
 }
 
-// Refinement on nibble-packed planes (every refinement level has word-aligned rows).  A patch row is 16 positions =
+// Refinement on nibble-packed planes, ONE BLOCK PER CANDIDATE (few candidates: lowest latency).  A patch row is 16 positions =
 // 8 bytes at an arbitrary nibble offset: lane r (< 16) and lane r + 16 load the two aligned 8-byte chunks the row spans
 // -- one LDG.64 per feature and lane, 16 cache lines per warp instruction instead of the 48 the byte kernel touches --
 // lane r takes the second chunk from its partner with two shuffles, realigns with two funnel shifts and sums up to
 // three features in the nibble domain before spreading even / odd nibbles into byte accumulators.  Same block / warp
 // decomposition, argmax and bookkeeping as k_refine.
-__global__ void __launch_bounds__(kRefineWarps * 32) k_refine_nib(const RefineParams P, const CoarseTpl* __restrict__ ctpl,
-                                                                 const Cand* __restrict__ cand, uint32_t cand_cap,
-                                                                 ResultHeader* hdr, lm_raw_match* __restrict__ out,
-                                                                 uint32_t out_cap) {
-  __shared__ uint32_t s_part[kRefineWarps][16][4];
-  __shared__ uint32_t s_addr[kRefineMaxFeat];  // nibble index of the feature's patch origin inside its modality's planes
-  __shared__ int s_state[4];                   // x, y, alive, best_score
+__device__ __forceinline__ void refine_nib_block(const RefineParams& P, const CoarseTpl* __restrict__ ctpl,
+                                                 const Cand* __restrict__ cand, uint32_t n_cands, ResultHeader* hdr,
+                                                 lm_raw_match* __restrict__ out, uint32_t out_cap, uint32_t* smem) {
+  uint32_t (*s_part)[16][4] = reinterpret_cast<uint32_t (*)[16][4]>(smem);                       // [kRefineWarps][16][4]
+  uint32_t* s_addr = smem + kRefineWarps * 16 * 4;  // [kRefineMaxFeat] nibble index of each feature's patch origin
+  int* s_state = reinterpret_cast<int*>(s_addr + kRefineMaxFeat);  // x, y, alive, best_score
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  cudaGridDependencySynchronize();
-  const uint32_t n_cands = min(hdr->n_cands, cand_cap);
-  if (blockIdx.x == 0 && threadIdx.x == 0 && hdr->n_cands > cand_cap) hdr->overflow = 1;  // candidate list truncated
   const int prow = lane & 15, half = lane >> 4;
   for (uint32_t ci = blockIdx.x; ci < n_cands; ci += gridDim.x) {
     const Cand c = cand[ci];
@@ -866,6 +862,155 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine_nib(const RefinePa
   }
 }
 
+// Refinement on nibble-packed planes (every refinement level has word-aligned rows), ONE WARP PER CANDIDATE: no block
+// barriers, candidates of a frame are refined by up to 148 x 64 warps at once.  A patch row is 16 positions = 8 bytes
+// at an arbitrary nibble offset: lane r (< 16) and lane r + 16 load the two aligned 8-byte chunks the row spans -- one
+// LDG.64 per feature and lane, 16 cache lines per warp instruction instead of the 48 the byte kernel touches -- lane r
+// takes the second chunk from its partner with two shuffles, realigns with two funnel shifts and sums up to three
+// features in the nibble domain before spreading even / odd nibbles into byte accumulators (widened to u16 after each
+// modality: <= 63 features x 4).  The warp first turns the template's features into plane offsets in its slice of shared
+// memory (one lane per feature), then issues eight window loads back to back per step.
+__device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const CoarseTpl* __restrict__ ctpl,
+                                                const Cand* __restrict__ cand, uint32_t n_cands, ResultHeader* hdr,
+                                                lm_raw_match* __restrict__ out, uint32_t out_cap, uint32_t* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* s_addr = smem + warp * kRefineMaxFeat;  // nibble index of each feature's patch origin (this warp's slice)
+  const int prow = lane & 15, half = lane >> 4;
+  // consecutive candidates go to different CTAs (SMs): a handful of candidates must not queue on one SM's L1
+  for (uint32_t ci = (uint32_t)warp * gridDim.x + blockIdx.x; ci < n_cands; ci += gridDim.x * kRefineWarps) {
+    const Cand c = cand[ci];
+    const uint32_t order = c.order;
+    const float threshold = P.threshold[order >> 28];
+    const int cT = P.coarse_T;
+    const int coff = cT / 2 + (cT % 2 - 1);
+    int x = (int)(c.pos % (uint32_t)P.coarse_W) * cT + coff;
+    int y = (int)(c.pos / (uint32_t)P.coarse_W) * cT + coff;
+    uint32_t score = c.raw_nf & 0xffffu, nf = c.raw_nf >> 16;
+    bool alive = true;
+    for (int l = P.levels - 2; l >= 0 && alive; --l) {
+      const RefineLevel& L = P.level[l];
+      const RefineTpl* rtp = L.tpl + c.tglob;
+      const int T = L.T, W = L.W;
+      const int border = 8 * T, off = T / 2 + (T % 2 - 1);
+      const int max_x = L.cols - rtp->width - border, max_y = L.rows - rtp->height - border;
+      x = x * 2 + 1; y = y * 2 + 1;
+      x = max(x, border); y = max(y, border);
+      x = min(x, max_x); y = min(y, max_y);
+      const int offset_x = (x / T - 8) * T, offset_y = (y / T - 8) * T;
+      const uint32_t WH = (uint32_t)W * (uint32_t)(L.rows / T);
+      const uint32_t zero_run = (uint32_t)L.plane_stride - 32u;  // the tail of every plane is zero (App. D-2 padding)
+      int n_all = 0;
+      for (int m = 0; m < P.M; ++m) n_all += rtp->cnt[m];
+      const uint32_t* fp = L.feats + rtp->feat_begin;
+      __syncwarp();
+      for (int i = lane; i < n_all; i += 32) {
+        const uint32_t pk = fp[i];
+        const int fx = (int)(pk & 0x1fffu) - 4096 + offset_x, fy = (int)((pk >> 13) & 0x1fffu) - 4096 + offset_y;
+        const bool inside = fx >= 0 && fy >= 0 && fx < L.cols && fy < L.rows;  // "Discard feature if out of bounds"
+        const uint32_t label = pk >> 26;
+        const uint32_t addr = label * (uint32_t)L.plane_stride + (uint32_t)((fy % T) * T + (fx % T)) * WH +
+                              (uint32_t)(fy / T) * (uint32_t)W + (uint32_t)(fx / T);
+        s_addr[i] = inside ? addr : zero_run;
+      }
+      __syncwarp();
+      const uint32_t row_off = (uint32_t)(prow * W);
+      // u16 totals of row prow: [j][h], word j: 0 even columns 0..7, 1 odd 0..7, 2 even 8..15, 3 odd 8..15; h: bytes (0,2) / (1,3)
+      uint32_t tot[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tot[j][0] = tot[j][1] = 0;
+      int begin = 0;
+      for (int m = 0; m < P.M; ++m) {
+        const uint8_t* lmm = L.lmn + (size_t)m * 4 * L.plane_stride;
+        const int n = rtp->cnt[m];  // <= 63 features: the u8 sums below cannot overflow
+        uint32_t acc[4] = {0, 0, 0, 0};
+        for (int f0 = 0; f0 < n; f0 += 8) {
+          uint2 w[8];
+          uint32_t sh[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t base = f0 + k < n ? s_addr[begin + f0 + k] : zero_run;
+            const uint32_t nidx = base + (base == zero_run ? 0u : row_off);   // nibble index of this row's first position
+            sh[k] = nidx & 15u;
+            w[k] = ldg64(lmm + (size_t)((nidx >> 4) + (uint32_t)half) * 8u);
+          }
+          uint32_t nib0 = 0, nib1 = 0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t w2 = __shfl_down_sync(kFull, w[k].x, 16), w3 = __shfl_down_sync(kFull, w[k].y, 16);
+            const bool hi = sh[k] >= 8u;                 // window starts in the second word of the first chunk
+            const uint32_t a = hi ? w[k].y : w[k].x, b = hi ? w2 : w[k].y, cc = hi ? w3 : w2;
+            const uint32_t bits = (sh[k] & 7u) * 4u;
+            nib0 += __funnelshift_r(a, b, bits);
+            nib1 += __funnelshift_r(b, cc, bits);
+            if (k == 2 || k == 5 || k == 7) {            // <= 3 features per nibble sum (3 * 4 < 16)
+              acc[0] += nib0 & 0x0f0f0f0fu; acc[1] += (nib0 >> 4) & 0x0f0f0f0fu;
+              acc[2] += nib1 & 0x0f0f0f0fu; acc[3] += (nib1 >> 4) & 0x0f0f0f0fu;
+              nib0 = nib1 = 0;
+            }
+          }
+        }
+        begin += n;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // [OCV] similarityLocal totals are u16: widen this modality's u8 sums
+          tot[j][0] += acc[j] & 0x00ff00ffu;
+          tot[j][1] += (acc[j] >> 8) & 0x00ff00ffu;
+        }
+      }
+      // first maximum in raster order: key = score << 8 | (255 - raster index); byte b of word j is column
+      // 8 * (j / 2) + 2 * b + (j & 1)
+      uint32_t best_key = 0;
+      if (half == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const uint32_t src = tot[j][b & 1];
+            const uint32_t sc = (b & 2) ? (src >> 16) : (src & 0xffffu);
+            const int col = 8 * (j >> 1) + 2 * b + (j & 1);
+            best_key = max(best_key, (sc << 8) | (uint32_t)(255 - (prow * 16 + col)));
+          }
+      }
+      best_key = __reduce_max_sync(kFull, best_key);
+      const int best_score = (int)(best_key >> 8);
+      int best_r = -1, best_c = -1;
+      if (best_score > 0) {
+        const int idx = 255 - (int)(best_key & 0xffu);
+        best_r = idx >> 4; best_c = idx & 15;
+      }
+      const int nfl = (int)rtp->nf;
+      const float sim = __fdiv_rn(__fmul_rn((float)best_score, 100.f), (float)(4 * nfl));
+      x = (x / T - 8 + best_c) * T + off;
+      y = (y / T - 8 + best_r) * T + off;
+      alive = !(sim < threshold);  // [OCV] remove_if(MatchPredicate(threshold))
+      score = (uint32_t)best_score; nf = rtp->nf;
+    }
+    if (alive && lane == 0) {
+      uint32_t idx = atomicAdd(&hdr->count, 1u);
+      if (idx < out_cap) {
+        lm_raw_match r;
+        r.order_key = order; r.coarse_pos = c.pos; r.x = x; r.y = y; r.score = score; r.nf = nf;
+        r.template_id = ctpl[c.tglob].template_id; r.class_index = ctpl[c.tglob].class_index;
+        out[idx] = r;
+      } else hdr->overflow = 1;
+    }
+  }
+}
+
+// Few candidates (the usual case at the reference's thresholds): a block per candidate finishes each one soonest.  Many
+// candidates (loose thresholds, BASELINE config 3): a warp per candidate keeps every SM's L1 busy without block barriers.
+__global__ void __launch_bounds__(kRefineWarps * 32) k_refine_nib(const RefineParams P, const CoarseTpl* __restrict__ ctpl,
+                                                                 const Cand* __restrict__ cand, uint32_t cand_cap,
+                                                                 ResultHeader* hdr, lm_raw_match* __restrict__ out,
+                                                                 uint32_t out_cap) {
+  __shared__ uint32_t smem[kRefineWarps * kRefineMaxFeat];
+  static_assert(kRefineWarps * kRefineMaxFeat >= kRefineWarps * 16 * 4 + kRefineMaxFeat + 4, "block path fits the warp path's smem");
+  cudaGridDependencySynchronize();  // programmatic dependent launch: the coarse kernel's candidates are complete from here on
+  const uint32_t n_cands = min(hdr->n_cands, cand_cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && hdr->n_cands > cand_cap) hdr->overflow = 1;  // candidate list truncated
+  if (n_cands <= 2u * gridDim.x) refine_nib_block(P, ctpl, cand, n_cands, hdr, out, out_cap, smem);
+  else refine_nib_warp(P, ctpl, cand, n_cands, hdr, out, out_cap, smem);
+}
+
 }  // namespace
 
 int coarse_positions_per_pass(int variant) {
@@ -944,9 +1089,13 @@ void launch_pack_nibbles(const uint8_t* lm_bytes, uint8_t* lm_nibbles, size_t n_
 
 void launch_refine(bool nibble_planes, const RefineParams& p, const CoarseTpl* ctpl, const WorkItem* items, const Cand* cand,
                    uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* out, uint32_t out_cap, cudaStream_t s) {
-  cudaLaunchConfig_t cfg = pdl_config(148 * 4, kRefineWarps * 32, s);
-  if (nibble_planes) cudaLaunchKernelEx(&cfg, k_refine_nib, p, ctpl, cand, cand_cap, hdr, out, out_cap);
-  else cudaLaunchKernelEx(&cfg, k_refine, p, ctpl, items, cand, cand_cap, hdr, out, out_cap);
+  if (nibble_planes) {  // one warp per candidate, 3 resident CTAs per SM
+    cudaLaunchConfig_t cfg = pdl_config(148 * 3, kRefineWarps * 32, s);
+    cudaLaunchKernelEx(&cfg, k_refine_nib, p, ctpl, cand, cand_cap, hdr, out, out_cap);
+  } else {
+    cudaLaunchConfig_t cfg = pdl_config(148 * 4, kRefineWarps * 32, s);
+    cudaLaunchKernelEx(&cfg, k_refine, p, ctpl, items, cand, cand_cap, hdr, out, out_cap);
+  }
 }
 
 }  // namespace lmk
