@@ -2,12 +2,19 @@
 //
 // Kernel <-> reference function map ([OCV] = OpenCV 2.4.x modules/objdetect/src/linemod.cpp, the code behind
 // cv::linemod::Detector::match called at /root/reference/src/rgbdDetector.cpp:33):
-//   k_gauss7_u8c3, k_cg_grad, k_cg_hysteresis   [OCV] quantizedOrientations + hysteresisGradient   (SURVEY 8a a1,a2)
-//   k_pyrdown_u8c3                              [OCV] ColorGradientPyramid::pyrDown -> cv::pyrDown  (a3)
-//   k_dn_normals, k_median5_u8, k_nn_half_u8    [OCV] quantizedNormals, medianBlur(5), DepthNormalPyramid::pyrDown (a4,a5)
-//   k_spread_lm                                 [OCV] spread + computeResponseMaps + linearize      (a6,a7,a8)
-//   k_similarity_coarse                         [OCV] similarity + addSimilarities + matchClass coarse scan (a9-a12)
-//   k_refine                                    [OCV] similarityLocal + matchClass refinement loop  (a13)
+//   production path
+//   k_pyrdown_fast                              [OCV] ColorGradientPyramid::pyrDown -> cv::pyrDown            
+//   k_cg_fused                                  [OCV] quantizedOrientations + hysteresisGradient, all levels (a1, a2)
+//   k_dn_fused                                  [OCV] quantizedNormals + medianBlur(5) + DepthNormalPyramid::pyrDown (a4, a5)
+//   k_spread_all                                [OCV] quantize(mask) + spread + computeResponseMaps + linearize (a6-a8)
+//   k_similarity_coarse_rec                     [OCV] similarity + addSimilarities + matchClass coarse scan  (a9-a12)
+//   k_refine_nib                                [OCV] similarityLocal + matchClass refinement loop          (a13)
+//   A/B references and fallbacks (same results, selected with lm_set_option)
+//   k_gauss7_u8c3, k_cg_grad, k_cg_hysteresis, k_pyrdown_u8c3, k_dn_normals, k_median5_u8, k_nn_half_u8, k_spread_lm
+//                                               the front end stage by stage            (frontend_variant = 1)
+//   k_similarity_coarse, k_similarity_coarse_nib<4>   coarse scan on byte / nibble planes without tile records (coarse_variant = 1 / 2)
+//   k_refine                                    refinement on byte planes (refine_variant = 1, or rows not word-aligned)
+//   k_pack_nibbles                              byte planes -> nibble planes when the spread kernel could not write them
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
