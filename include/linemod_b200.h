@@ -228,6 +228,37 @@ int lm_finalize_raw(const lm_detector* det, const lm_raw_match* raw, size_t n_ra
  * i % world == rank on this handle; template_id / class_index / order_key stay global. */
 int lm_set_shard(lm_detector* det, int rank, int world);
 
+/* ------------------------------------------------------------------------------------------------ match clustering */
+/* The stage right behind Detector::match in the reference's nodes:
+ *   rgbdDetector::rcd_voting            src/rgbdDetector.cpp:36-70    bin matches by (y / step, x / step, depth bin of the template)
+ *   rgbdDetector::cluster_filter        src/rgbdDetector.cpp:72-84    drop bins with <= cluster_threshold matches
+ *   rgbdDetector::similarity_score_calc src/rgbdDetector.cpp:133-145  cluster score = mean similarity
+ *   rgbdDetector::nonMaximaSuppressionUsingIOU + computeIoU   src/rgbdDetector.cpp:462-574   mean rectangle per cluster,
+ *                                       std::sort by score (descending), greedy suppression at IoU > iou_threshold
+ * as driven at src/linemod_ensenso_detect_3_mult_detect.cpp:352-424 (thresh = 2, IoU 0.4).  Host code: a frame yields a few
+ * dozen matches.  (cluster_filter erases from the std::map while iterating over it -- undefined behaviour upstream; the
+ * evident intent, "erase every bin with size <= thresh", is what is implemented.) */
+typedef struct {
+  int32_t vote_row_col_step;     /* clustering_step_: bin size in pixels (rows and columns) */
+  double renderer_radius_min;    /* depth of bin 0 (m) */
+  double renderer_radius_step;   /* depth bin size (m); converted to float like the reference does */
+  int32_t cluster_threshold;     /* bins with <= this many matches are dropped (reference: 2) */
+  double iou_threshold;          /* reference: 0.4 */
+} lm_cluster_params;
+typedef struct {
+  int32_t index[3];              /* (row bin, column bin, depth bin) */
+  double score;                  /* mean similarity of the cluster's matches */
+  lm_rect rect;                  /* mean x, y of the matches; mean width, height of their templates' rectangles */
+  uint32_t first, count;         /* the cluster's matches: match_index[first .. first + count) */
+} lm_cluster;
+/* obj_origin_dists / rects are indexed by template_id (the reference's renderer_params.yml tables).  Outputs are
+ * library-allocated (release both with lm_free_clusters): the surviving clusters in the reference's order and, grouped
+ * per cluster, indices into `matches` in the order the reference's std::vector<Match> holds them. */
+int lm_cluster_matches(const lm_match_rec* matches, size_t n_matches, const double* obj_origin_dists, const lm_rect* rects,
+                       size_t n_templates, const lm_cluster_params* params, lm_cluster** out_clusters, size_t* out_n,
+                       uint32_t** out_match_index);
+void lm_free_clusters(lm_cluster* clusters, uint32_t* match_index);
+
 /* ------------------------------------------------------------------------------------------------ data tables */
 /* SIMILARITY_LUT[256] ([OCV] linemod.cpp) and NORMAL_LUT[20][20][20] ([OCV] normal_lut.i) are data, not code: both
  * are recalled / regenerated here (DESIGN.md "LUTs"), so both are injectable.  Similarity entries must be <= 4. */

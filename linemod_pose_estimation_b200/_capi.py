@@ -53,7 +53,7 @@ EXPORTS = [
     "lm_add_template", "lm_add_template_from_quantized", "lm_add_synthetic_template", "lm_match", "lm_match_multi", "lm_match_batch", "lm_match_batch_multi", "lm_free_matches",
     "lm_match_device", "lm_match_device_multi", "lm_match_device_multi_lane", "lm_device_result_region", "lm_copy_result_block", "lm_match_device_stream", "lm_finalize_raw", "lm_set_shard", "lm_set_similarity_lut", "lm_get_similarity_lut",
     "lm_set_normal_lut", "lm_get_normal_lut", "lm_debug_fetch", "lm_build_front", "lm_level_geometry",
-    "lm_debug_coarse_map", "lm_debug_presort", "lm_last_timings", "lm_last_work", "lm_set_option",
+    "lm_cluster_matches", "lm_free_clusters", "lm_debug_coarse_map", "lm_debug_presort", "lm_last_timings", "lm_last_work", "lm_set_option",
 ]
 
 _lib = None
@@ -125,6 +125,9 @@ def lib():
     L.lm_set_shard.argtypes = [vp, ci, ci]
     for n in ("lm_set_similarity_lut", "lm_get_similarity_lut", "lm_set_normal_lut", "lm_get_normal_lut"):
         getattr(L, n).argtypes = [vp, vp]
+    L.lm_cluster_matches.argtypes = [vp, C.c_size_t, vp, vp, C.c_size_t, vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp)]
+    L.lm_free_clusters.argtypes = [vp, vp]
+    L.lm_free_clusters.restype = None
     L.lm_debug_fetch.argtypes = [vp, ci, ci, ci, vp]
     L.lm_debug_fetch.restype = C.c_long
     L.lm_build_front.argtypes = [vp, C.POINTER(LmImage), ci, C.POINTER(LmImage), ci]

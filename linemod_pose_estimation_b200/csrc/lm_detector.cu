@@ -1683,6 +1683,97 @@ int lm_finalize_raw(const lm_detector* d, const lm_raw_match* raw, size_t n_raw,
   return copy_out(out, out_matches, out_n);
 }
 
+// ---------------------------------------------------------------------------------------------- match clustering
+// Restates rgbdDetector::{rcd_voting, cluster_filter, similarity_score_calc, nonMaximaSuppressionUsingIOU, computeIoU}
+// (/root/reference/src/rgbdDetector.cpp:36-84, 133-145, 462-574) on the match records this library returns.
+namespace {
+struct ClusterTmp {
+  std::vector<int> index;
+  std::vector<uint32_t> members;  // indices into the match list, in arrival order
+  double score = 0;
+  lm_rect rect = {0, 0, 0, 0};
+  bool checked = false;
+};
+float compute_iou(const lm_rect& r1, const lm_rect& r2) {
+  const int r1_minX = r1.x, r1_maxX = r1.x + r1.width - 1, r1_minY = r1.y, r1_maxY = r1.y + r1.height - 1;
+  const int r2_minX = r2.x, r2_maxX = r2.x + r2.width - 1, r2_minY = r2.y, r2_maxY = r2.y + r2.height - 1;
+  const int minX = std::max(r1_minX, r2_minX), maxX = std::min(r1_maxX, r2_maxX);
+  const int minY = std::max(r1_minY, r2_minY), maxY = std::min(r1_maxY, r2_maxY);
+  const bool x_inter = (minX >= r1_minX && minX <= r1_maxX) || (minX >= r2_minX && minX <= r2_maxX);
+  const bool y_inter = (minY >= r1_minY && minY <= r1_maxY) || (minY >= r2_minY && minY <= r2_maxY);
+  float inter_area = 0.0f;
+  if (x_inter && y_inter) inter_area = (float)((maxX - minX + 1) * (maxY - minY + 1));
+  const float union_area = (float)(r1.width * r1.height + r2.width * r2.height) - inter_area;
+  return inter_area / union_area;
+}
+}  // namespace
+
+int lm_cluster_matches(const lm_match_rec* matches, size_t n_matches, const double* obj_origin_dists, const lm_rect* rects,
+                       size_t n_templates, const lm_cluster_params* p, lm_cluster** out_clusters, size_t* out_n,
+                       uint32_t** out_match_index) {
+  if ((!matches && n_matches) || !obj_origin_dists || !rects || !p || !out_clusters || !out_n || !out_match_index)
+    return fail(LM_E_INVALID, "NULL argument");
+  if (p->vote_row_col_step <= 0 || !(p->renderer_radius_step > 0)) return fail(LM_E_INVALID, "voting steps must be positive");
+  *out_clusters = nullptr; *out_match_index = nullptr; *out_n = 0;
+  // rcd_voting: std::map<std::vector<int>, std::vector<Match>> keyed by (row bin, column bin, depth bin)
+  std::map<std::vector<int>, ClusterTmp> bins;
+  const float depth_step = (float)p->renderer_radius_step;
+  for (size_t i = 0; i < n_matches; ++i) {
+    const lm_match_rec& m = matches[i];
+    if (m.template_id < 0 || (size_t)m.template_id >= n_templates) return fail(LM_E_INVALID, "match %zu: template_id %d outside the pose tables", i, m.template_id);
+    const float depth = (float)obj_origin_dists[m.template_id];
+    std::vector<int> index(3);
+    index[0] = m.y / p->vote_row_col_step;
+    index[1] = m.x / p->vote_row_col_step;
+    index[2] = (int)((depth - p->renderer_radius_min) / depth_step);
+    ClusterTmp& c = bins[index];
+    c.index = index;
+    c.members.push_back((uint32_t)i);
+  }
+  // cluster_filter (intent: erase bins with size <= thresh) + cluster_scoring (mean similarity) in map order
+  std::vector<ClusterTmp> clusters;
+  for (auto& kv : bins) {
+    ClusterTmp& c = kv.second;
+    if ((int)c.members.size() <= p->cluster_threshold) continue;
+    double sum = 0.0;
+    int num = 0;
+    for (uint32_t i : c.members) { sum += matches[i].similarity; ++num; }
+    c.score = sum / num;
+    // nonMaximaSuppressionUsingIOU: mean position of the matches, mean size of their templates (integer division)
+    int X = 0, Y = 0, Wd = 0, Ht = 0;
+    for (uint32_t i : c.members) {
+      X += matches[i].x; Y += matches[i].y;
+      Wd += rects[matches[i].template_id].width; Ht += rects[matches[i].template_id].height;
+    }
+    const int n = (int)c.members.size();
+    c.rect.x = X / n; c.rect.y = Y / n; c.rect.width = Wd / n; c.rect.height = Ht / n;
+    clusters.push_back(c);
+  }
+  std::sort(clusters.begin(), clusters.end(), [](const ClusterTmp& a, const ClusterTmp& b) { return a.score > b.score; });
+  for (size_t i = 0; i < clusters.size(); ++i) {
+    if (clusters[i].checked) continue;
+    for (size_t j = i + 1; j < clusters.size(); ++j)
+      if (!clusters[j].checked && (double)compute_iou(clusters[i].rect, clusters[j].rect) > p->iou_threshold) clusters[j].checked = true;
+  }
+  size_t n_out = 0, n_idx = 0;
+  for (const ClusterTmp& c : clusters) if (!c.checked) { ++n_out; n_idx += c.members.size(); }
+  lm_cluster* oc = (lm_cluster*)std::malloc(std::max<size_t>(1, n_out) * sizeof(lm_cluster));
+  uint32_t* oi = (uint32_t*)std::malloc(std::max<size_t>(1, n_idx) * sizeof(uint32_t));
+  if (!oc || !oi) { std::free(oc); std::free(oi); return fail(LM_E_INVALID, "out of host memory"); }
+  size_t k = 0, pos = 0;
+  for (const ClusterTmp& c : clusters) {
+    if (c.checked) continue;
+    lm_cluster& o = oc[k++];
+    o.index[0] = c.index[0]; o.index[1] = c.index[1]; o.index[2] = c.index[2];
+    o.score = c.score; o.rect = c.rect; o.first = (uint32_t)pos; o.count = (uint32_t)c.members.size();
+    for (uint32_t i : c.members) oi[pos++] = i;
+  }
+  *out_clusters = oc; *out_match_index = oi; *out_n = n_out;
+  return LM_OK;
+}
+
+void lm_free_clusters(lm_cluster* clusters, uint32_t* match_index) { std::free(clusters); std::free(match_index); }
+
 // ---------------------------------------------------------------------------------------------- parity taps
 int lm_level_geometry(lm_detector* d, int level, int32_t out[5], size_t* plane_stride) {
   Lane& ln = d->lane[0];

@@ -266,6 +266,39 @@ class Detector:
         check(lib().lm_finalize_raw(self._h, raw.ctypes.data, len(raw), C.byref(out), C.byref(n)))
         return self._take(out, n.value)
 
+    @staticmethod
+    def cluster_matches(matches, obj_origin_dists, rects, vote_step, radius_min, radius_step, cluster_threshold=2,
+                        iou_threshold=0.4):
+        """rcd_voting -> cluster_filter -> mean-similarity score -> IoU non-maximum suppression (lm_cluster_matches), the
+        stage the reference runs right behind Detector::match.  rects: int32 [n_templates, 4] (x, y, width, height).
+        -> list of dicts {index, score, rect, matches (indices into `matches`)} in the reference's order."""
+        m = np.ascontiguousarray(matches, dtype=MATCH_DTYPE)
+        dists = np.ascontiguousarray(obj_origin_dists, dtype=np.float64)
+        r = np.ascontiguousarray(rects, dtype=np.int32).reshape(-1, 4)
+        assert len(dists) == len(r)
+
+        class Params(C.Structure):
+            _fields_ = [("vote_row_col_step", C.c_int32), ("renderer_radius_min", C.c_double),
+                        ("renderer_radius_step", C.c_double), ("cluster_threshold", C.c_int32),
+                        ("iou_threshold", C.c_double)]
+        CL = np.dtype([("index", "<i4", (3,)), ("score", "<f8"), ("rect", "<i4", (4,)), ("first", "<u4"), ("count", "<u4")],
+                      align=True)
+        p = Params(vote_step, radius_min, radius_step, cluster_threshold, iou_threshold)
+        oc, oi, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        check(lib().lm_cluster_matches(m.ctypes.data, len(m), dists.ctypes.data, r.ctypes.data, len(r), C.byref(p),
+                                       C.byref(oc), C.byref(n), C.byref(oi)))
+        out = []
+        if n.value:
+            cl = np.frombuffer((C.c_char * (n.value * CL.itemsize)).from_address(oc.value), dtype=CL).copy()
+            total = int(cl["first"][-1] + cl["count"][-1])
+            idx = np.frombuffer((C.c_char * (total * 4)).from_address(oi.value), dtype=np.uint32).copy()
+            for c in cl:
+                out.append(dict(index=tuple(int(v) for v in c["index"]), score=float(c["score"]),
+                                rect=tuple(int(v) for v in c["rect"]),
+                                matches=[int(v) for v in idx[c["first"]:c["first"] + c["count"]]]))
+        lib().lm_free_clusters(oc, oi)
+        return out
+
     def set_shard(self, rank, world):
         check(lib().lm_set_shard(self._h, rank, world))
 

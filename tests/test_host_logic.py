@@ -280,3 +280,35 @@ def test_binary_template_cache_roundtrip_and_speed(tmp_path):
         with pytest.raises(LinemodError) as e:
             Detector.read_cache(str(tmp_path / name))
         assert e.value.code == -3
+
+
+def test_match_clustering_equals_reference_restatement():
+    """lm_cluster_matches against the pure-Python restatement of rcd_voting / cluster_filter /
+    similarity_score_calc / nonMaximaSuppressionUsingIOU / computeIoU (oracle/cluster_oracle.py)."""
+    from oracle import cluster_oracle as CO
+    rng = np.random.default_rng(5)
+    n_templates = 400
+    dists = 0.6 + 0.1 * rng.integers(0, 6, n_templates) + rng.uniform(-1e-3, 1e-3, n_templates)   # radii like the trainer's
+    rects = np.stack([np.zeros(n_templates), np.zeros(n_templates), rng.integers(55, 194, n_templates),
+                      rng.integers(55, 194, n_templates)], 1).astype(np.int32)
+    for trial in range(6):
+        n = int(rng.integers(0, 400))
+        m = np.zeros(n, MATCH_DTYPE)
+        centres = rng.integers(40, 440, (8, 2))
+        pick = rng.integers(0, 8, n)
+        m["x"] = centres[pick, 0] + rng.integers(-14, 15, n)
+        m["y"] = centres[pick, 1] + rng.integers(-14, 15, n)
+        m["template_id"] = rng.integers(0, n_templates, n)
+        m["similarity"] = (rng.integers(8400, 10000, n) / 100.0 + rng.uniform(0, 0.004, n)).astype(np.float32)
+        for step, thr in ((8, 2), (16, 1), (25, 0)):
+            got = Detector.cluster_matches(m, dists, rects, step, 0.6, 0.1, cluster_threshold=thr, iou_threshold=0.4)
+            want = CO.cluster_matches(m, dists, rects, step, 0.6, 0.1, cluster_threshold=thr, iou_threshold=0.4)
+            assert len(got) == len(want), (trial, step, len(got), len(want))
+            for g, w in zip(got, want):
+                assert g["index"] == tuple(w[0]) and g["rect"] == tuple(w[2]) and g["matches"] == list(w[3])
+                assert g["score"] == w[1]
+        if n > 50:
+            assert len(got) > 0
+    with pytest.raises(LinemodError):
+        bad = np.zeros(1, MATCH_DTYPE); bad["template_id"] = n_templates + 3
+        Detector.cluster_matches(bad, dists, rects, 8, 0.6, 0.1)
