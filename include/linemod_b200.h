@@ -144,6 +144,66 @@ int lm_add_template_from_quantized(lm_detector* det, const lm_image* quantized, 
 int lm_add_synthetic_template(lm_detector* det, const char* class_id, int n_templates, const lm_template_hdr* hdr,
                               const int32_t* feats);
 
+/* ------------------------------------------------------------------------------------------------ template generation */
+/* Training at scale: the loop of /root/reference/src/renderer.cpp:239-329 --
+ *     for every view of RendererIterator: render(image, depth, mask, rect); detector->addTemplate(sources, "obj", mask)
+ * -- with the renders produced by a CUDA z-buffer rasteriser and addTemplate's feature extraction done on the GPU for a
+ * batch of views at a time.  The reference renders with `object_recognition_renderer` (OpenGL + assimp), which is not part
+ * of its tree; this library's rasteriser is specified in oracle/render_oracle.cpp (pinhole camera looking at the object
+ * origin, principal point at the image centre as K at renderer.cpp:273, depth in u16 millimetres, mask 255). */
+typedef struct lm_mesh lm_mesh;
+/* triangles: n_triangles x 3 vertices x (x, y, z) f32, object frame, metres (Renderer3d(stl_file), renderer.cpp:239) */
+int lm_mesh_create(const float* triangles, int n_triangles, lm_mesh** out);
+int lm_mesh_load_stl(const char* path, lm_mesh** out); /* ASCII or binary STL */
+int lm_mesh_num_triangles(const lm_mesh* mesh);
+int lm_mesh_get_triangles(const lm_mesh* mesh, float* dst /* n*9 */);
+void lm_mesh_destroy(lm_mesh* mesh);
+
+/* Renderer3d::set_parameters(width, height, focal_length_x, focal_length_y, near, far)        renderer.cpp:240-241 */
+typedef struct {
+  int32_t width, height;
+  double fx, fy, near_, far_;
+} lm_camera;
+/* RendererIterator(renderer, n_points) + angle_step_ / radius_{min,max,step}_               renderer.cpp:242-246.
+ * ORK defaults: angle_min -80, angle_max 80. */
+typedef struct {
+  int32_t n_points, angle_min, angle_max, angle_step;
+  float radius_min, radius_max, radius_step;
+} lm_view_sphere;
+/* RendererIterator::n_templates(), by enumeration (angle innermost, then radius, then sphere point) */
+int lm_view_count(const lm_view_sphere* sphere);
+/* RendererIterator::view_params for the index-th view: camera position T (object frame) and up vector; optionally the
+ * view's radius (D_obj), sphere point and in-plane angle. */
+int lm_view_params(const lm_view_sphere* sphere, int index, double T[3], double up[3], float* radius /*nullable*/,
+                   int32_t* point_index /*nullable*/, int32_t* angle_deg /*nullable*/);
+/* Pose of the object in the camera frame for a view: Pc = R * Po + t (row-major R, OpenCV camera convention) -- what
+ * the trainer stores per template (Rs_, Ts_ at renderer.cpp:313-318) in this library's convention. */
+int lm_view_pose(const double T[3], const double up[3], double R[9], double t[3]);
+/* Renders n_views views (T, up: n_views x 3 each) on the detector's GPU.  Outputs are host buffers, one tightly packed
+ * image per view (bgr: rows*cols*3, depth: rows*cols u16, mask: rows*cols u8), each nullable; rects = bounding box of
+ * each mask (all zero when the object is not visible). */
+int lm_render_views(lm_detector* det, const lm_mesh* mesh, const lm_camera* cam, const double* T, const double* up,
+                    int n_views, uint8_t* bgr, uint16_t* depth, uint8_t* mask, lm_rect* rects);
+/* Detector::addTemplate for a batch of views (sources[v * n_sources + m], masks[v]; a mask is required): quantisation,
+ * candidate extraction, the stable sort and the scattered feature selection all run on the GPU, many views in flight.
+ * template_ids[v] receives the new template_id or -1 (some level lacks candidates), bounding_boxes (nullable) the
+ * cropTemplates boxes.  Result identical to n_views lm_add_template calls in order. */
+int lm_add_templates_batch(lm_detector* det, const lm_image* sources, const lm_image* masks, int n_views, int n_sources,
+                           const char* class_id, int32_t* template_ids, lm_rect* bounding_boxes /*nullable*/);
+/* Render + addTemplate for n_views views without leaving the device: the trainer's loop.  mask_rects (nullable) receives
+ * the render rectangles (`rects` at renderer.cpp:318). */
+int lm_train_views(lm_detector* det, const lm_mesh* mesh, const lm_camera* cam, const double* T, const double* up,
+                   int n_views, const char* class_id, int32_t* template_ids, lm_rect* bounding_boxes /*nullable*/,
+                   lm_rect* mask_rects /*nullable*/);
+
+/* ------------------------------------------------------------------------------------------------ hypothesis checks */
+/* rgbdDetector::depth_diff as driven by depth_normal_diff_calc (src/rgbdDetector.cpp:147-283): for each
+ * hypothesis i the template view (T, up) is rendered depth-only, cropped to its mask's bounding box, laid over the scene
+ * depth at (x[i], y[i]) and the mean |template - scene| (metres) over pixels valid in both is returned in out[i]
+ * (NaN when no pixel is valid, like the reference's 0/0).  LM_E_INVALID when a crop leaves the scene image. */
+int lm_depth_diff_batch(lm_detector* det, const lm_image* scene_depth, const lm_mesh* mesh, const lm_camera* cam,
+                        const double* T, const double* up, const int32_t* x, const int32_t* y, int n, double* out);
+
 /* ------------------------------------------------------------------------------------------------ matching */
 /* Detector::match(sources, threshold, matches, class_ids, quantized_images, masks)   src/rgbdDetector.cpp:33
  *   class_ids/n_ids   : empty = all classes in std::map order

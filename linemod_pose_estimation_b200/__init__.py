@@ -6,3 +6,4 @@ kernels for the path cv::linemod::Detector::match, which the reference enters at
 """
 from .detector import ColorGradient, DepthNormal, Detector, Stage  # noqa: F401
 from ._capi import LinemodError, MATCH_DTYPE, RAW_DTYPE  # noqa: F401
+from .training import Mesh, ViewSphere, camera  # noqa: F401

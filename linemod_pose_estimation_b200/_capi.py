@@ -38,6 +38,16 @@ class LmRect(C.Structure):
     _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("width", C.c_int32), ("height", C.c_int32)]
 
 
+class LmCamera(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_double), ("fy", C.c_double),
+                ("near_", C.c_double), ("far_", C.c_double)]
+
+
+class LmViewSphere(C.Structure):
+    _fields_ = [("n_points", C.c_int32), ("angle_min", C.c_int32), ("angle_max", C.c_int32), ("angle_step", C.c_int32),
+                ("radius_min", C.c_float), ("radius_max", C.c_float), ("radius_step", C.c_float)]
+
+
 MATCH_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("template_id", "<i4"), ("class_index", "<i4"),
                         ("similarity", "<f4")])
 RAW_DTYPE = np.dtype([("order_key", "<u4"), ("coarse_pos", "<u4"), ("x", "<i4"), ("y", "<i4"), ("score", "<u4"),
@@ -53,6 +63,8 @@ EXPORTS = [
     "lm_add_template", "lm_add_template_from_quantized", "lm_add_synthetic_template", "lm_match", "lm_match_multi", "lm_match_batch", "lm_match_batch_multi", "lm_free_matches",
     "lm_match_device", "lm_match_device_multi", "lm_match_device_multi_lane", "lm_device_result_region", "lm_copy_result_block", "lm_match_device_stream", "lm_finalize_raw", "lm_set_shard", "lm_set_similarity_lut", "lm_get_similarity_lut",
     "lm_set_normal_lut", "lm_get_normal_lut", "lm_debug_fetch", "lm_build_front", "lm_level_geometry",
+    "lm_mesh_create", "lm_mesh_load_stl", "lm_mesh_num_triangles", "lm_mesh_get_triangles", "lm_mesh_destroy", "lm_view_count", "lm_view_params",
+    "lm_view_pose", "lm_render_views", "lm_add_templates_batch", "lm_train_views", "lm_depth_diff_batch",
     "lm_cluster_matches", "lm_free_clusters", "lm_debug_coarse_map", "lm_debug_presort", "lm_last_timings", "lm_last_work", "lm_set_option",
 ]
 
@@ -125,6 +137,20 @@ def lib():
     L.lm_set_shard.argtypes = [vp, ci, ci]
     for n in ("lm_set_similarity_lut", "lm_get_similarity_lut", "lm_set_normal_lut", "lm_get_normal_lut"):
         getattr(L, n).argtypes = [vp, vp]
+    L.lm_mesh_create.argtypes = [vp, ci, C.POINTER(vp)]
+    L.lm_mesh_load_stl.argtypes = [cp, C.POINTER(vp)]
+    L.lm_mesh_num_triangles.argtypes = [vp]
+    L.lm_mesh_get_triangles.argtypes = [vp, vp]
+    L.lm_mesh_destroy.argtypes = [vp]
+    L.lm_mesh_destroy.restype = None
+    L.lm_view_count.argtypes = [C.POINTER(LmViewSphere)]
+    L.lm_view_params.argtypes = [C.POINTER(LmViewSphere), ci, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_int32)]
+    L.lm_view_pose.argtypes = [vp, vp, vp, vp]
+    L.lm_render_views.argtypes = [vp, vp, C.POINTER(LmCamera), vp, vp, ci, vp, vp, vp, vp]
+    L.lm_add_templates_batch.argtypes = [vp, C.POINTER(LmImage), C.POINTER(LmImage), ci, ci, cp, vp, vp]
+    L.lm_train_views.argtypes = [vp, vp, C.POINTER(LmCamera), vp, vp, ci, cp, vp, vp, vp]
+    L.lm_depth_diff_batch.argtypes = [vp, C.POINTER(LmImage), vp, C.POINTER(LmCamera), vp, vp, vp, vp, ci, vp]
     L.lm_cluster_matches.argtypes = [vp, C.c_size_t, vp, vp, C.c_size_t, vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp)]
     L.lm_free_clusters.argtypes = [vp, vp]
     L.lm_free_clusters.restype = None

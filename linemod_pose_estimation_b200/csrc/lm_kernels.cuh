@@ -162,4 +162,49 @@ void launch_pack_nibbles(const uint8_t* lm_bytes, uint8_t* lm_nibbles, size_t n_
 void launch_refine(bool nibble_planes, const RefineParams& p, const CoarseTpl* ctpl, const WorkItem* items, const Cand* cand,
                    uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* out, uint32_t out_cap, cudaStream_t s);
 
+// ------------------------------------------------------------------------------------------------ rendering (lm_render.cu)
+struct RenderView {                       // Pc = R * Po + t, OpenCV camera convention (x right, y down, z forward)
+  float R[9], t[3];
+};
+struct RenderCamera {
+  int width, height;
+  float fx, fy, cx, cy, z_near, z_max;    // z_max = 0.99 * far: fragments beyond it are dropped
+};
+struct RenderTargets {                    // per view v: base + v * stride (elements); null pointers are skipped
+  uint8_t* bgr; uint16_t* depth; uint8_t* mask;
+  size_t bgr_stride, depth_stride, mask_stride;
+  int* rect;                              // [n_views][4] = x_min, y_min, x_max, y_max of the mask (x_max < 0: empty)
+};
+void launch_raster(const float* tris, int n_tri, const RenderView* views, int n_views, const RenderCamera& cam,
+                   unsigned long long* zbuf, float* nz_abs, const RenderTargets& out, cudaStream_t s);
+void launch_mask_rect(const uint8_t* mask, int W, int H, int* rect, cudaStream_t s);
+void launch_depth_diff(const uint16_t* scene, int scene_cols, const uint16_t* templ, const uint8_t* tmask, int templ_cols,
+                       int x, int y, int tx, int ty, int w, int h, unsigned long long* out, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------ batched extraction (lm_train.cu)
+struct TrainSeg {                         // one (view, level, modality) of a training batch
+  uint32_t off, cap;                      // key pool region (cap: power of two >= any possible candidate count)
+  uint32_t count, area;                   // device: candidates appended, pixels of the twice-eroded mask (DepthNormal)
+  uint32_t per_label[8];                  // device: DepthNormal candidates per bin
+  int32_t cols, nf, type, n_sel;          // level width, features wanted, LM_COLOR_GRADIENT / LM_DEPTH_NORMAL; device:
+                                          // features selected, -1 = too few candidates, -2 = pool overflow
+};
+struct TrainLevel {
+  const uint8_t* quant;                   // unmasked quantisation of this level
+  const float* mag;                       // ColorGradient only
+  int rows, cols, seg, block_begin;
+};
+struct TrainViewParams {
+  TrainLevel lv[LM_MAX_LEVELS];
+  uint8_t* pb[LM_MAX_LEVELS];             // DepthNormal scratch: normal bin where the eroded mask is set, else 0
+  const uint8_t* mask0;                   // level-0 object mask
+  int extract_threshold[LM_MAX_LEVELS];
+  int n_levels, cols0;
+  float thr_sq;                           // strong_threshold^2
+};
+int train_blocks(int rows, int cols);
+void launch_train_cg(const TrainViewParams& p, int total_blocks, TrainSeg* segs, unsigned long long* pool, cudaStream_t s);
+void launch_train_dn(const TrainViewParams& p, int total_blocks, TrainSeg* segs, unsigned long long* pool, cudaStream_t s);
+void launch_train_finish(TrainSeg* segs, int n_segs, unsigned long long* pool, uint32_t* out_feats, cudaStream_t s);
+
 }  // namespace lmk

@@ -142,6 +142,16 @@ class Detector:
             raise LinemodError(r + 100, _capi.last_error())
         return r, (bb.x, bb.y, bb.width, bb.height)
 
+    def addTemplates(self, views, class_id):
+        """Batched addTemplate on the GPU: views = [(sources, object_mask)] -> (template_ids, bounding_boxes)."""
+        from . import training
+        return training.add_templates_batch(self, views, class_id)
+
+    def trainViews(self, mesh, cam, T, up, class_id):
+        """Render + addTemplate for many views (renderer.cpp:239-329) -> (template_ids, bounding_boxes, mask_rects)."""
+        from . import training
+        return training.train_views(self, mesh, cam, T, up, class_id)
+
     def addTemplateFromQuantized(self, quantized, magnitudes, class_id, object_mask=None):
         """Host half of addTemplate: quantized[l*M+m] u8 maps, magnitudes[l*M+m] f32 maps (None for DepthNormal)."""
         arr, keep = image_array(quantized)

@@ -164,3 +164,68 @@ def view_params(n_views, seed=0, scales=(0.6, 0.7, 0.8, 0.9, 1.0, 1.1)):
                 out.append((seed * 100003 + v, float(s), rot, tilt))
         v += 1
     return out
+
+
+# ------------------------------------------------------------------------------------------------ meshes
+def _quad(a, b, c, d):
+    return [[a, b, c], [a, c, d]]
+
+
+def box_mesh(sx=0.093, sy=0.133, sz=0.08, centre=(0.0, 0.0, 0.0)):
+    """Axis-aligned box (12 triangles), metres; the default is the extent of the reference's config/stl/boxNew.stl."""
+    hx, hy, hz = sx / 2.0, sy / 2.0, sz / 2.0
+    cx, cy, cz = centre
+    v = np.array([[cx + dx * hx, cy + dy * hy, cz + dz * hz] for dz in (-1, 1) for dy in (-1, 1) for dx in (-1, 1)], np.float32)
+    faces = [(0, 2, 3, 1), (4, 5, 7, 6), (0, 1, 5, 4), (2, 6, 7, 3), (0, 4, 6, 2), (1, 3, 7, 5)]
+    tris = []
+    for f in faces:
+        tris += _quad(*[v[i] for i in f])
+    return np.array(tris, np.float32)
+
+
+def bracket_mesh(length=0.12, width=0.06, height=0.08, thickness=0.02):
+    """L-shaped bracket: two boxes sharing an edge (24 triangles, interior faces included -- the z-buffer hides them)."""
+    base = box_mesh(length, width, thickness, (0.0, 0.0, -height / 2.0 + thickness / 2.0))
+    wall = box_mesh(thickness, width, height, (-length / 2.0 + thickness / 2.0, 0.0, 0.0))
+    return np.concatenate([base, wall])
+
+
+def gear_mesh(teeth=9, r_in=0.035, r_out=0.05, height=0.02):
+    """Extruded star polygon: a non-convex silhouette with many short edges (4 * 2 * teeth triangles)."""
+    n = 2 * teeth
+    ang = np.arange(n) * (2.0 * np.pi / n)
+    rad = np.where(np.arange(n) % 2 == 0, r_out, r_in)
+    ring = np.stack([rad * np.cos(ang), rad * np.sin(ang)], 1)
+    top = np.concatenate([ring, np.full((n, 1), height / 2.0)], 1)
+    bot = np.concatenate([ring, np.full((n, 1), -height / 2.0)], 1)
+    ct, cb = np.array([0.0, 0.0, height / 2.0]), np.array([0.0, 0.0, -height / 2.0])
+    tris = []
+    for i in range(n):
+        j = (i + 1) % n
+        tris.append([ct, top[i], top[j]])
+        tris.append([cb, bot[j], bot[i]])
+        tris += _quad(bot[i], bot[j], top[j], top[i])
+    return np.array(tris, np.float32)
+
+
+def write_stl(path, triangles, binary=True, name="synth"):
+    """Writes a mesh as binary or ASCII STL (facet normals recomputed, zero for degenerate facets)."""
+    tri = np.asarray(triangles, np.float32).reshape(-1, 3, 3)
+    nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    ln = np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm = np.where(ln > 0, nrm / np.maximum(ln, 1e-30), 0).astype(np.float32)
+    if binary:
+        with open(path, "wb") as f:
+            f.write(name.encode().ljust(80, b" "))
+            f.write(np.uint32(len(tri)).tobytes())
+            for t, n in zip(tri, nrm):
+                f.write(n.tobytes() + t.tobytes() + b"\0\0")
+    else:
+        with open(path, "w") as f:
+            f.write("solid %s\n" % name)
+            for t, n in zip(tri, nrm):
+                f.write("   facet normal %.6e %.6e %.6e\n      outer loop\n" % tuple(n))
+                for v in t:
+                    f.write("         vertex %.9e %.9e %.9e\n" % tuple(v))
+                f.write("      endloop\n   endfacet\n")
+            f.write("endsolid %s\n" % name)

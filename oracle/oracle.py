@@ -36,10 +36,20 @@ RAW_DTYPE = np.dtype([("order_key", "<u4"), ("coarse_pos", "<u4"), ("x", "<i4"),
 CAND_DTYPE = np.dtype([("class_index", "<i4"), ("template_id", "<i4"), ("pos", "<i4"), ("raw", "<i4")])
 
 
+class OrcViewSphere(C.Structure):
+    _fields_ = [("n_points", C.c_int32), ("angle_min", C.c_int32), ("angle_max", C.c_int32), ("angle_step", C.c_int32),
+                ("radius_min", C.c_float), ("radius_max", C.c_float), ("radius_step", C.c_float)]
+
+
+class OrcCamera(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_double), ("fy", C.c_double),
+                ("near_", C.c_double), ("far_", C.c_double)]
+
+
 def build(force=False):
     """Compile the oracle with oracle/Makefile (g++ only; no GPU, no reference sources needed)."""
-    src = os.path.join(_HERE, "linemod_oracle.cpp")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("linemod_oracle.cpp", "render_oracle.cpp")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB_PATH
 
@@ -91,6 +101,15 @@ def lib():
         L.orc_level_geometry.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_size_t)]
         L.orc_sort_unique.restype = C.c_long
         L.orc_sort_unique.argtypes = [C.c_void_p, C.c_long]
+        L.orc_view_count.argtypes = [C.POINTER(OrcViewSphere)]
+        L.orc_view_params.argtypes = [C.POINTER(OrcViewSphere), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_float)]
+        L.orc_view_list.argtypes = [C.POINTER(OrcViewSphere), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_look_at.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_render.argtypes = [C.c_void_p, C.c_int, C.POINTER(OrcCamera), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]
+        L.orc_depth_diff.restype = C.c_double
+        L.orc_depth_diff.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_int] * 6
         L.orc_prim_phase_deg.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.orc_prim_cg_quantize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
@@ -410,3 +429,64 @@ def prim_spread(src, T):
     dst = np.empty_like(src)
     lib().orc_prim_spread(_p(src), src.shape[0], src.shape[1], T, _p(dst))
     return dst
+
+
+# ---------------------------------------------------------------------------------------------- render_oracle.cpp
+def view_sphere(n_points=150, angle_step=10, radius_min=0.5, radius_max=1.0, radius_step=0.1, angle_min=-80, angle_max=80):
+    return OrcViewSphere(n_points, angle_min, angle_max, angle_step, radius_min, radius_max, radius_step)
+
+
+def view_count(vs):
+    return lib().orc_view_count(C.byref(vs))
+
+
+def view_params(vs, index):
+    """-> (T[3], up[3], radius, sphere point, angle)"""
+    T, up = np.zeros(3), np.zeros(3)
+    st, r = (C.c_int32 * 2)(), C.c_float()
+    if lib().orc_view_params(C.byref(vs), index, T.ctypes.data, up.ctypes.data, st, C.byref(r)) != 0:
+        raise IndexError(index)
+    return T, up, r.value, st[0], st[1]
+
+
+def view_list(vs):
+    """Every view in iteration order -> list of (T[3], up[3], radius, sphere point, angle)"""
+    n = view_count(vs)
+    T, up = np.zeros((n, 3)), np.zeros((n, 3))
+    st, r = np.zeros((n, 2), np.int32), np.zeros(n, np.float32)
+    assert lib().orc_view_list(C.byref(vs), T.ctypes.data, up.ctypes.data, st.ctypes.data, r.ctypes.data) == n
+    return [(T[i], up[i], float(r[i]), int(st[i, 0]), int(st[i, 1])) for i in range(n)]
+
+
+def look_at(T, up):
+    T, up = np.ascontiguousarray(T, np.float64), np.ascontiguousarray(up, np.float64)
+    R, t = np.zeros((3, 3), np.float32), np.zeros(3, np.float32)
+    if lib().orc_look_at(T.ctypes.data, up.ctypes.data, R.ctypes.data, t.ctypes.data) != 0:
+        raise ValueError("degenerate view")
+    return R, t
+
+
+def camera(width=640, height=480, fx=535.566011, fy=537.168115, near=0.1, far=1000.0):
+    return OrcCamera(width, height, fx, fy, near, far)
+
+
+def render(triangles, cam, T, up):
+    """-> (bgr, depth, mask, (x, y, w, h)) of one view, see the specification in render_oracle.cpp"""
+    tri = np.ascontiguousarray(triangles, np.float32).reshape(-1, 9)
+    T, up = np.ascontiguousarray(T, np.float64), np.ascontiguousarray(up, np.float64)
+    bgr = np.zeros((cam.height, cam.width, 3), np.uint8)
+    depth = np.zeros((cam.height, cam.width), np.uint16)
+    mask = np.zeros((cam.height, cam.width), np.uint8)
+    rect = (C.c_int32 * 4)()
+    if lib().orc_render(tri.ctypes.data, len(tri), C.byref(cam), T.ctypes.data, up.ctypes.data, bgr.ctypes.data,
+                        depth.ctypes.data, mask.ctypes.data, rect) != 0:
+        raise ValueError("degenerate view")
+    return bgr, depth, mask, tuple(rect)
+
+
+def depth_diff(scene, templ, templ_mask, x, y, tx, ty, w, h):
+    """rgbdDetector::depth_diff on a scene ROI at (x, y) and a template crop at (tx, ty), both w x h."""
+    scene, templ = np.ascontiguousarray(scene, np.uint16), np.ascontiguousarray(templ, np.uint16)
+    templ_mask = np.ascontiguousarray(templ_mask, np.uint8)
+    return lib().orc_depth_diff(scene.ctypes.data, scene.shape[1], templ.ctypes.data, templ_mask.ctypes.data, templ.shape[1],
+                                x, y, tx, ty, w, h)
