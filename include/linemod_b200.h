@@ -191,10 +191,34 @@ int lm_render_views(lm_detector* det, const lm_mesh* mesh, const lm_camera* cam,
 int lm_add_templates_batch(lm_detector* det, const lm_image* sources, const lm_image* masks, int n_views, int n_sources,
                            const char* class_id, int32_t* template_ids, lm_rect* bounding_boxes /*nullable*/);
 /* Render + addTemplate for n_views views without leaving the device: the trainer's loop.  mask_rects (nullable) receives
- * the render rectangles (`rects` at renderer.cpp:318). */
+ * the render rectangles (`rects` at renderer.cpp:318), centre_depth_mm (nullable) the rendered depth at the image centre
+ * (what `distance` is computed from at renderer.cpp:271). */
 int lm_train_views(lm_detector* det, const lm_mesh* mesh, const lm_camera* cam, const double* T, const double* up,
                    int n_views, const char* class_id, int32_t* template_ids, lm_rect* bounding_boxes /*nullable*/,
-                   lm_rect* mask_rects /*nullable*/);
+                   lm_rect* mask_rects /*nullable*/, uint16_t* centre_depth_mm /*nullable*/);
+
+/* The pose table the trainer writes next to templates.yml and the detection nodes read back:
+ *   writeLinemodTemplateParams   src/renderer.cpp:72-123      "Template i": {ID, R, T, K, D, Ori_dist, Rect} + renderer_* keys
+ *   readLinemodTemplateParams    src/rgbdDetector.cpp:1681-1749
+ * Same cv::FileStorage YAML 1.0 layout (the shipped config/data/..._renderer_params.yml parses; files written here load
+ * with cv::FileStorage).  Host only. */
+typedef struct {
+  double R[9];      /* Rs_: row-major, == lm_view_pose's R */
+  double T[3];      /* Ts_: minus the camera position in the object frame (renderer_iterator.T()) */
+  float K[9];       /* Ks_: [fx 0 cols/2; 0 fy rows/2; 0 0 1] (renderer.cpp:273) */
+  double D;         /* distances_: D_obj - depth(image centre) / 1000 */
+  double ori_dist;  /* Origin_dists_: D_obj, the view's radius */
+  lm_rect rect;     /* rects */
+} lm_template_pose;
+typedef struct {
+  int32_t n_points, angle_step;
+  double radius_min, radius_max, radius_step;
+  int32_t width, height;
+  double fx, fy, near_, far_;
+} lm_renderer_params;
+int lm_write_renderer_params(const char* path, const lm_template_pose* poses, size_t n, const lm_renderer_params* params);
+int lm_read_renderer_params(const char* path, lm_template_pose** out_poses, size_t* out_n, lm_renderer_params* params);
+void lm_free_poses(lm_template_pose* poses);
 
 /* ------------------------------------------------------------------------------------------------ hypothesis checks */
 /* rgbdDetector::depth_diff as driven by depth_normal_diff_calc (src/rgbdDetector.cpp:147-283): for each

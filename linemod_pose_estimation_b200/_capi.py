@@ -43,6 +43,16 @@ class LmCamera(C.Structure):
                 ("near_", C.c_double), ("far_", C.c_double)]
 
 
+class LmRendererParams(C.Structure):
+    _fields_ = [("n_points", C.c_int32), ("angle_step", C.c_int32), ("radius_min", C.c_double), ("radius_max", C.c_double),
+                ("radius_step", C.c_double), ("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_double),
+                ("fy", C.c_double), ("near_", C.c_double), ("far_", C.c_double)]
+
+
+POSE_DTYPE = np.dtype([("R", "<f8", (3, 3)), ("T", "<f8", (3,)), ("K", "<f4", (3, 3)), ("pad", "<u4"), ("D", "<f8"),
+                       ("ori_dist", "<f8"), ("rect", [("x", "<i4"), ("y", "<i4"), ("width", "<i4"), ("height", "<i4")])])
+
+
 class LmViewSphere(C.Structure):
     _fields_ = [("n_points", C.c_int32), ("angle_min", C.c_int32), ("angle_max", C.c_int32), ("angle_step", C.c_int32),
                 ("radius_min", C.c_float), ("radius_max", C.c_float), ("radius_step", C.c_float)]
@@ -65,6 +75,7 @@ EXPORTS = [
     "lm_set_normal_lut", "lm_get_normal_lut", "lm_debug_fetch", "lm_build_front", "lm_level_geometry",
     "lm_mesh_create", "lm_mesh_load_stl", "lm_mesh_num_triangles", "lm_mesh_get_triangles", "lm_mesh_destroy", "lm_view_count", "lm_view_params",
     "lm_view_pose", "lm_render_views", "lm_add_templates_batch", "lm_train_views", "lm_depth_diff_batch",
+    "lm_write_renderer_params", "lm_read_renderer_params", "lm_free_poses",
     "lm_cluster_matches", "lm_free_clusters", "lm_debug_coarse_map", "lm_debug_presort", "lm_last_timings", "lm_last_work", "lm_set_option",
 ]
 
@@ -149,8 +160,12 @@ def lib():
     L.lm_view_pose.argtypes = [vp, vp, vp, vp]
     L.lm_render_views.argtypes = [vp, vp, C.POINTER(LmCamera), vp, vp, ci, vp, vp, vp, vp]
     L.lm_add_templates_batch.argtypes = [vp, C.POINTER(LmImage), C.POINTER(LmImage), ci, ci, cp, vp, vp]
-    L.lm_train_views.argtypes = [vp, vp, C.POINTER(LmCamera), vp, vp, ci, cp, vp, vp, vp]
+    L.lm_train_views.argtypes = [vp, vp, C.POINTER(LmCamera), vp, vp, ci, cp, vp, vp, vp, vp]
     L.lm_depth_diff_batch.argtypes = [vp, C.POINTER(LmImage), vp, C.POINTER(LmCamera), vp, vp, vp, vp, ci, vp]
+    L.lm_write_renderer_params.argtypes = [cp, vp, C.c_size_t, C.POINTER(LmRendererParams)]
+    L.lm_read_renderer_params.argtypes = [cp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(LmRendererParams)]
+    L.lm_free_poses.argtypes = [vp]
+    L.lm_free_poses.restype = None
     L.lm_cluster_matches.argtypes = [vp, C.c_size_t, vp, vp, C.c_size_t, vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp)]
     L.lm_free_clusters.argtypes = [vp, vp]
     L.lm_free_clusters.restype = None

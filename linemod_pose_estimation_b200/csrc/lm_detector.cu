@@ -2337,7 +2337,8 @@ int lm_render_views(lm_detector* d, const lm_mesh* mesh, const lm_camera* cam, c
 }
 
 int lm_train_views(lm_detector* d, const lm_mesh* mesh, const lm_camera* cam, const double* T, const double* up,
-                   int n_views, const char* class_id, int32_t* template_ids, lm_rect* bounding_boxes, lm_rect* mask_rects) {
+                   int n_views, const char* class_id, int32_t* template_ids, lm_rect* bounding_boxes, lm_rect* mask_rects,
+                   uint16_t* centre_depth_mm) {
   if (!d || !mesh || !T || !up || !class_id || !template_ids || n_views < 0) return fail(LM_E_INVALID, "NULL argument");
   if (check_camera(cam) != LM_OK) return LM_E_INVALID;
   const int M = d->model.M();
@@ -2356,13 +2357,18 @@ int lm_train_views(lm_detector* d, const lm_mesh* mesh, const lm_camera* cam, co
     const int n = std::min(kTrainBatch, n_views - v0);
     // one rendered image pool per source type; modalities of the same type share it
     if (ws.src[0].ensure(px * 3 * n) != LM_OK || ws.src[1].ensure(px * 2 * n) != LM_OK || ws.mask.ensure(px * n) != LM_OK ||
-        ws.h_rects.ensure(16 * (size_t)n) != LM_OK)
+        ws.h_rects.ensure(16 * (size_t)n + 2 * (size_t)n) != LM_OK)
       return LM_E_CUDA;
     int rc = render_batch(d, d_tris, mesh->n, *cam, T + 3 * (size_t)v0, up + 3 * (size_t)v0, n, ws.src[0].as<uint8_t>(),
                           ws.src[1].as<uint16_t>(), ws.mask.as<uint8_t>(), s);
     if (rc != LM_OK) return rc;
     CU(cudaMemcpyAsync(ws.h_rects.p, ws.rects.p, 16 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    uint16_t* h_centre = reinterpret_cast<uint16_t*>(ws.h_rects.as<uint8_t>() + 16 * (size_t)n);
+    if (centre_depth_mm)  // one strided copy: the centre pixel of every view's depth image
+      CU(cudaMemcpy2DAsync(h_centre, 2, ws.src[1].as<uint16_t>() + (size_t)(rows / 2) * cols + cols / 2, px * 2, 2, n,
+                           cudaMemcpyDeviceToHost, s));
     if (cudaStreamSynchronize(s) != cudaSuccess) return fail(LM_E_CUDA, "rasteriser failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (centre_depth_mm) std::memcpy(centre_depth_mm + v0, h_centre, 2 * (size_t)n);
     std::vector<int> rects(ws.h_rects.as<int>(), ws.h_rects.as<int>() + 4 * n);
     std::vector<const void*> srcs((size_t)n * M);
     std::vector<const uint8_t*> masks((size_t)n);
@@ -2487,5 +2493,117 @@ int lm_depth_diff_batch(lm_detector* d, const lm_image* scene, const lm_mesh* me
   }
   return LM_OK;
 }
+
+}  // extern "C"
+
+// ================================================================================================ pose table
+// writeLinemodTemplateParams (/root/reference/src/renderer.cpp:72-123) / readLinemodTemplateParams
+// (src/rgbdDetector.cpp:1681-1749): cv::FileStorage YAML, one "Template i" map per template + the renderer_* scalars.
+#include "lm_yaml.hpp"
+
+namespace {
+
+void write_matrix(lmyaml::Writer& w, const char* key, int rows, int cols, const double* d, const float* f) {
+  w.key(key);
+  w.begin_map_tagged("!!opencv-matrix");
+  w.key("rows"); w.write_int(rows);
+  w.key("cols"); w.write_int(cols);
+  w.key("dt"); w.write_string(d ? "d" : "f");
+  w.key("data");
+  w.begin_seq(true);
+  for (int i = 0; i < rows * cols; ++i) {
+    if (d) w.write_double(d[i]);
+    else w.write_float(f[i]);
+  }
+  w.end_seq();
+  w.end_map();
+}
+
+bool read_matrix(const lmyaml::Node& n, int count, double* d, float* f) {
+  const lmyaml::Node& data = n["data"];
+  if (data.kind != lmyaml::Node::SEQ || (int)data.size() != count) return false;
+  for (int i = 0; i < count; ++i) {
+    if (d) d[i] = data.num(i);
+    else f[i] = (float)data.num(i);
+  }
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lm_write_renderer_params(const char* path, const lm_template_pose* poses, size_t n, const lm_renderer_params* p) {
+  if (!path || (n && !poses) || !p) return fail(LM_E_INVALID, "NULL argument");
+  lmyaml::Writer w;
+  for (size_t i = 0; i < n; ++i) {
+    const lm_template_pose& t = poses[i];
+    w.key("Template " + std::to_string(i));
+    w.begin_map();
+    w.key("ID"); w.write_int((int)i);
+    write_matrix(w, "R", 3, 3, t.R, nullptr);
+    write_matrix(w, "T", 3, 1, t.T, nullptr);
+    write_matrix(w, "K", 3, 3, nullptr, t.K);
+    w.key("D"); w.write_double(t.D);
+    w.key("Ori_dist"); w.write_double(t.ori_dist);
+    w.key("Rect");
+    w.begin_seq(true);
+    w.write_int(t.rect.x); w.write_int(t.rect.y); w.write_int(t.rect.width); w.write_int(t.rect.height);
+    w.end_seq();
+    w.end_map();
+  }
+  w.key("renderer_n_points"); w.write_int(p->n_points);
+  w.key("renderer_angle_step"); w.write_int(p->angle_step);
+  w.key("renderer_radius_min"); w.write_double(p->radius_min);
+  w.key("renderer_radius_max"); w.write_double(p->radius_max);
+  w.key("renderer_radius_step"); w.write_double(p->radius_step);
+  w.key("renderer_width"); w.write_int(p->width);
+  w.key("renderer_height"); w.write_int(p->height);
+  w.key("renderer_focal_length_x"); w.write_double(p->fx);
+  w.key("renderer_focal_length_y"); w.write_double(p->fy);
+  w.key("renderer_near"); w.write_double(p->near_);
+  w.key("renderer_far"); w.write_double(p->far_);
+  std::string err;
+  if (!w.save(path, err)) return fail(LM_E_IO, "%s", err.c_str());
+  return LM_OK;
+}
+
+int lm_read_renderer_params(const char* path, lm_template_pose** out_poses, size_t* out_n, lm_renderer_params* p) {
+  if (!path || !out_poses || !out_n || !p) return fail(LM_E_INVALID, "NULL argument");
+  lmyaml::Node root;
+  std::string err;
+  if (!lmyaml::parse_file(path, root, err)) return fail(LM_E_IO, "%s: %s", path, err.c_str());
+  std::vector<lm_template_pose> poses;
+  for (size_t i = 0;; ++i) {  // the reference reads "Template 0", "Template 1", ... until the first missing key
+    const lmyaml::Node& t = root["Template " + std::to_string(i)];
+    if (t.empty()) break;
+    lm_template_pose ps;
+    std::memset(&ps, 0, sizeof(ps));
+    const lmyaml::Node& rc = t["Rect"];
+    if (!read_matrix(t["R"], 9, ps.R, nullptr) || !read_matrix(t["T"], 3, ps.T, nullptr) || !read_matrix(t["K"], 9, nullptr, ps.K) ||
+        !t["D"].as_double(ps.D) || !t["Ori_dist"].as_double(ps.ori_dist) || rc.kind != lmyaml::Node::SEQ || rc.size() != 4)
+      return fail(LM_E_IO, "%s: malformed entry \"Template %zu\"", path, i);
+    ps.rect.x = (int)rc.num(0); ps.rect.y = (int)rc.num(1); ps.rect.width = (int)rc.num(2); ps.rect.height = (int)rc.num(3);
+    poses.push_back(ps);
+  }
+  std::memset(p, 0, sizeof(*p));
+  bool ok = root["renderer_n_points"].as_int(p->n_points) && root["renderer_angle_step"].as_int(p->angle_step) &&
+            root["renderer_radius_min"].as_double(p->radius_min) && root["renderer_radius_max"].as_double(p->radius_max) &&
+            root["renderer_radius_step"].as_double(p->radius_step) && root["renderer_width"].as_int(p->width) &&
+            root["renderer_height"].as_int(p->height) && root["renderer_focal_length_x"].as_double(p->fx) &&
+            root["renderer_focal_length_y"].as_double(p->fy) && root["renderer_near"].as_double(p->near_) &&
+            root["renderer_far"].as_double(p->far_);
+  if (!ok) return fail(LM_E_IO, "%s: renderer_* parameters missing", path);
+  *out_n = poses.size();
+  *out_poses = nullptr;
+  if (!poses.empty()) {
+    *out_poses = (lm_template_pose*)std::malloc(poses.size() * sizeof(lm_template_pose));
+    if (!*out_poses) return fail(LM_E_INVALID, "out of memory");
+    std::memcpy(*out_poses, poses.data(), poses.size() * sizeof(lm_template_pose));
+  }
+  return LM_OK;
+}
+
+void lm_free_poses(lm_template_pose* poses) { std::free(poses); }
 
 }  // extern "C"

@@ -363,6 +363,7 @@ void Writer::start_collection(bool is_seq, bool flow) {
     newline_indent(p.indent);
     if (p.is_seq) out_ += "-";
     else { out_ += pending_key_; out_ += ":"; }
+    if (!pending_tag_.empty()) { out_ += " "; out_ += pending_tag_; pending_tag_.clear(); }
     if (f.flow) { out_ += is_seq ? " [" : " {"; f.indent = p.indent + 4; }
     else f.indent = p.indent + 3;
   }
@@ -371,6 +372,7 @@ void Writer::start_collection(bool is_seq, bool flow) {
   stack_.push_back(f);
 }
 void Writer::begin_map() { start_collection(false, false); }
+void Writer::begin_map_tagged(const std::string& tag) { pending_tag_ = tag; start_collection(false, false); }
 void Writer::begin_seq(bool flow) { start_collection(true, flow); }
 void Writer::end_map() {
   Frame f = stack_.back();

@@ -42,6 +42,7 @@ class Writer {
   Writer();
   void key(const std::string& k);  // next value / collection is a map member named k
   void begin_map();                // "{"   (block mapping)
+  void begin_map_tagged(const std::string& tag);  // "{:tag" e.g. "!!opencv-matrix" (block mapping only)
   void end_map();                  // "}"
   void begin_seq(bool flow);       // "[" (block) or "[:" (flow)
   void end_seq();                  // "]"
@@ -55,7 +56,7 @@ class Writer {
  private:
   struct Frame { bool is_seq; bool flow; bool first; int indent; };
   std::vector<Frame> stack_;
-  std::string out_, pending_key_;
+  std::string out_, pending_key_, pending_tag_;
   bool has_key_ = false;
   size_t line_start_ = 0;
   void emit_scalar(const std::string& text);

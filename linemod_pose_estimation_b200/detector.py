@@ -147,10 +147,11 @@ class Detector:
         from . import training
         return training.add_templates_batch(self, views, class_id)
 
-    def trainViews(self, mesh, cam, T, up, class_id):
-        """Render + addTemplate for many views (renderer.cpp:239-329) -> (template_ids, bounding_boxes, mask_rects)."""
+    def trainViews(self, mesh, cam, T, up, class_id, centre_depth=False):
+        """Render + addTemplate for many views (renderer.cpp:239-329) -> (template_ids, bounding_boxes, mask_rects
+        [, centre depth])."""
         from . import training
-        return training.train_views(self, mesh, cam, T, up, class_id)
+        return training.train_views(self, mesh, cam, T, up, class_id, centre_depth)
 
     def addTemplateFromQuantized(self, quantized, magnitudes, class_id, object_mask=None):
         """Host half of addTemplate: quantized[l*M+m] u8 maps, magnitudes[l*M+m] f32 maps (None for DepthNormal)."""

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import _capi
-from ._capi import LmCamera, LmViewSphere, check, image, image_array, lib
+from ._capi import LmCamera, LmRendererParams, LmViewSphere, POSE_DTYPE, check, image, image_array, lib
 
 RECT_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("width", "<i4"), ("height", "<i4")])
 
@@ -111,15 +111,17 @@ def render_views(det, mesh, cam, T, up, want=("bgr", "depth", "mask")):
     return out
 
 
-def train_views(det, mesh, cam, T, up, class_id):
-    """lm_train_views: render + addTemplate per view on the GPU -> (template_ids[n], bounding_boxes[n], mask_rects[n])."""
+def train_views(det, mesh, cam, T, up, class_id, centre_depth=False):
+    """lm_train_views: render + addTemplate per view on the GPU -> (template_ids[n], bounding_boxes[n], mask_rects[n]
+    [, centre depth in mm [n]])."""
     T, up = _views(T, up)
     n = len(T)
     tids = np.full(n, -1, np.int32)
     bbs, rects = np.zeros(n, RECT_DTYPE), np.zeros(n, RECT_DTYPE)
+    centre = np.zeros(n, np.uint16)
     check(lib().lm_train_views(det._h, mesh._h, C.byref(cam), T.ctypes.data, up.ctypes.data, n, class_id.encode(),
-                               tids.ctypes.data, bbs.ctypes.data, rects.ctypes.data))
-    return tids, bbs, rects
+                               tids.ctypes.data, bbs.ctypes.data, rects.ctypes.data, centre.ctypes.data if centre_depth else None))
+    return (tids, bbs, rects, centre) if centre_depth else (tids, bbs, rects)
 
 
 def add_templates_batch(det, views, class_id):
@@ -148,4 +150,36 @@ def depth_diff(det, scene_depth, mesh, cam, T, up, xs, ys):
     out = np.zeros(len(T), np.float64)
     check(lib().lm_depth_diff_batch(det._h, C.byref(simg), mesh._h, C.byref(cam), T.ctypes.data, up.ctypes.data,
                                     xs.ctypes.data, ys.ctypes.data, len(T), out.ctypes.data))
+    return out
+
+
+def write_renderer_params(path, poses, params):
+    """writeLinemodTemplateParams (renderer.cpp:72-123): poses = POSE_DTYPE array, params = LmRendererParams."""
+    poses = np.ascontiguousarray(poses, POSE_DTYPE)
+    check(lib().lm_write_renderer_params(str(path).encode(), poses.ctypes.data, len(poses), C.byref(params)))
+
+
+def read_renderer_params(path):
+    """readLinemodTemplateParams (rgbdDetector.cpp:1681-1749) -> (POSE_DTYPE array, LmRendererParams)."""
+    p, n, params = C.c_void_p(), C.c_size_t(), LmRendererParams()
+    check(lib().lm_read_renderer_params(str(path).encode(), C.byref(p), C.byref(n), C.byref(params)))
+    out = np.zeros(n.value, POSE_DTYPE)
+    if n.value:
+        C.memmove(out.ctypes.data, p.value, n.value * POSE_DTYPE.itemsize)
+        lib().lm_free_poses(p)
+    return out, params
+
+
+def poses_for_views(T, up, cam, radii, rects, centre_depth_mm):
+    """The trainer's per-template records (renderer.cpp:262-318) for views (T, up): R = lm_view_pose's rotation, T = minus
+    the camera position, K from the camera, D = radius - centre depth, Ori_dist = radius, Rect = the render rectangle."""
+    T, up = _views(T, up)
+    out = np.zeros(len(T), POSE_DTYPE)
+    for i in range(len(T)):
+        out["R"][i] = view_pose(T[i], up[i])[0]
+        out["T"][i] = -T[i]
+        out["K"][i] = np.array([[cam.fx, 0, cam.width / 2.0], [0, cam.fy, cam.height / 2.0], [0, 0, 1]], np.float32)
+        out["ori_dist"][i] = radii[i]
+        out["D"][i] = float(radii[i]) - float(np.float32(centre_depth_mm[i]) / np.float32(1000.0))
+        out["rect"][i] = tuple(rects[i])
     return out

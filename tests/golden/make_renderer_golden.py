@@ -11,6 +11,7 @@ iterator and the rasteriser's geometry on the GPU box, where /root/reference doe
 
     python tests/golden/make_renderer_golden.py
 """
+import hashlib
 import os
 import re
 import struct
@@ -22,7 +23,9 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "renderer_params_
 
 
 def main():
-    s = open(os.path.join(REF, "config/data/boxNew_longDistance_linemod_xtion_renderer_params.yml")).read()
+    yml = os.path.join(REF, "config/data/boxNew_longDistance_linemod_xtion_renderer_params.yml")
+    s = open(yml).read()
+    sha = hashlib.sha256(open(yml, "rb").read()).hexdigest()
 
     def mats(key):
         out = re.findall(key + r": !!opencv-matrix\s+rows: \d\s+cols: \d\s+dt: \w\s+data: \[([^\]]+)\]", s)
@@ -42,6 +45,7 @@ def main():
     for i in range(n):
         tri[i] = np.frombuffer(raw[84 + 50 * i + 12:84 + 50 * i + 48], np.float32)
     np.savez_compressed(OUT, R=R, T=T, D=D, ori_dist=ori, rect=rect, triangles=tri.reshape(n, 3, 3),
+                        yml_sha256=np.array(sha), yml_bytes=np.array(os.path.getsize(yml)),
                         param_names=np.array(sorted(params)), param_values=np.array([params[k] for k in sorted(params)]))
     print(OUT, os.path.getsize(OUT), "bytes;", len(R), "templates,", n, "triangles;", params)
 

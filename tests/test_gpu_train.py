@@ -207,3 +207,41 @@ def test_depth_diff_equals_reference_restatement():
         assert got[v] == want, (v, got[v], want)
     with pytest.raises(LinemodError):   # crop leaves the scene
         training.depth_diff(det, scene, mesh, cam, T[:1], up[:1], [630], [470])
+
+
+def test_trainer_tool_writes_the_reference_file_pair(tmp_path):
+    """tools/train.py == renderer_node (renderer.cpp:170-354): templates.yml + renderer_params.yml for an STL file; and on
+    the reference's own run (boxNew.stl, the 2 652 recorded views) the pose table it derives agrees with the recorded one:
+    R, T to 1e-15, D within 2 mm, Rect within the rasteriser tolerance."""
+    import json
+    import os
+    import subprocess
+    import sys
+    stl = tmp_path / "gear.stl"
+    synth.write_stl(stl, MESHES["gear"] * 2.0, binary=True)
+    out_t, out_p = tmp_path / "gear_templates.yml", tmp_path / "gear_renderer_params.yml"
+    r = subprocess.run([sys.executable, os.path.join(common.ROOT, "tools", "train.py"), "--stl", str(stl), "--templates", str(out_t),
+                        "--params", str(out_p), "--n-points", "16", "--angle-step", "40", "--radius-min", "0.4", "--radius-max", "0.6",
+                        "--radius-step", "0.1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["views"] == 16 * 5 * 3 and info["templates"] > 100
+    det = Detector.read(out_t)
+    poses, params = training.read_renderer_params(out_p)
+    assert det.numTemplates("obj") == len(poses) == info["templates"] and params.n_points == 16
+    assert np.allclose(np.linalg.norm(poses["T"], axis=1), poses["ori_dist"], atol=1e-6)
+    # the reference's run
+    G = golden.G
+    views, idx = golden._oracle_views()
+    cam = golden._golden_camera(training)
+    T = np.array([views[i][0] for i in idx])
+    up = np.array([views[i][1] for i in idx])
+    d2 = Detector()
+    tids, bbs, rects, centre = d2.trainViews(Mesh(G["triangles"]), cam, T, up, "obj", centre_depth=True)
+    assert (tids >= 0).all() and len(tids) == 2652   # the reference kept exactly these 2 652 views
+    rr = np.array([(q["x"] - 1, cam.height - (q["y"] + q["height"]) - 1, q["width"] + 2, q["height"] + 2) for q in rects])
+    mine = training.poses_for_views(T, up, cam, [views[i][2] for i in idx], rr, centre)
+    assert np.abs(mine["R"] - G["R"]).max() < 1e-12 and np.abs(mine["T"] - G["T"]).max() < 1e-12
+    assert np.array_equal(mine["ori_dist"], G["ori_dist"]) and np.abs(mine["D"] - G["D"]).max() <= 2.001e-3
+    d = np.abs(rr - G["rect"])
+    assert d.max() <= 1 and (d.max(axis=1) == 0).mean() >= 0.85

@@ -177,3 +177,37 @@ def test_depth_diff_restatement():
     sub = np.where(t > roi, t - roi, 0).astype(np.uint16).view(np.int16)          # u16 saturating subtract read as short
     want = np.abs(sub.astype(np.int64))[m > 0].sum() / ((m > 0).sum() * 1000.0)
     assert O.depth_diff(scene, templ, tmask, x, y, tx, ty, w, h) == want
+
+
+def test_pose_table_writer_reproduces_the_shipped_file_byte_for_byte(tmp_path):
+    """writeLinemodTemplateParams (renderer.cpp:72-123): the 2 652 recorded poses written by lm_write_renderer_params give
+    the reference's own 2 MB renderer_params.yml back exactly (sha256 recorded by make_renderer_golden.py), the reader
+    returns what was written, and OpenCV's FileStorage loads the file."""
+    import hashlib
+
+    from linemod_pose_estimation_b200._capi import LmRendererParams, POSE_DTYPE
+    n = len(G["R"])
+    poses = np.zeros(n, POSE_DTYPE)
+    poses["R"], poses["T"], poses["D"], poses["ori_dist"] = G["R"], G["T"], G["D"], G["ori_dist"]
+    K = np.array([[PARAMS["renderer_focal_length_x"], 0, PARAMS["renderer_width"] / 2.0],
+                  [0, PARAMS["renderer_focal_length_y"], PARAMS["renderer_height"] / 2.0], [0, 0, 1]], np.float32)
+    poses["K"] = K
+    for i, name in enumerate(("x", "y", "width", "height")):
+        poses["rect"][name] = G["rect"][:, i]
+    params = LmRendererParams(int(PARAMS["renderer_n_points"]), int(PARAMS["renderer_angle_step"]), PARAMS["renderer_radius_min"],
+                              PARAMS["renderer_radius_max"], PARAMS["renderer_radius_step"], int(PARAMS["renderer_width"]),
+                              int(PARAMS["renderer_height"]), PARAMS["renderer_focal_length_x"],
+                              PARAMS["renderer_focal_length_y"], PARAMS["renderer_near"], PARAMS["renderer_far"])
+    p = tmp_path / "renderer_params.yml"
+    training.write_renderer_params(p, poses, params)
+    raw = open(p, "rb").read()
+    assert len(raw) == int(G["yml_bytes"]) and hashlib.sha256(raw).hexdigest() == str(G["yml_sha256"])
+    back, bp = training.read_renderer_params(p)
+    assert back.tobytes() == poses.tobytes()
+    assert (bp.n_points, bp.angle_step, bp.width, bp.height, bp.fx, bp.far_) == (150, 10, 640, 480, 535.566011, 1000.0)
+    cv2 = pytest.importorskip("cv2")
+    fs = cv2.FileStorage(str(p), cv2.FILE_STORAGE_READ)
+    assert np.array_equal(fs.getNode("Template 2651").getNode("R").mat(), G["R"][2651])
+    assert fs.getNode("Template 2652").empty() and fs.getNode("renderer_radius_step").real() == 0.1
+    with pytest.raises(LinemodError):
+        training.read_renderer_params(tmp_path / "missing.yml")
