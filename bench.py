@@ -44,7 +44,7 @@ TEMPLATES_PER_CLASS = 2652
 EXTRACTED_PER_CLASS = 24
 FRAME_POOL = 128            # 128 x 1.536 MB = 197 MB of distinct input frames > 126 MB L2
 METRIC = "template_pixel_evals_per_sec_640x480"
-N_INFLIGHT = int(os.environ.get("LM_BENCH_INFLIGHT", "4"))   # frames in flight on the device-timed path (workspace lanes)
+N_INFLIGHT = int(os.environ.get("LM_BENCH_INFLIGHT", "8"))   # frames in flight on the device-timed path (workspace lanes)
 GATHER_EVERY = int(os.environ.get("LM_BENCH_GATHER", "16"))           # N > 1, device-timed path: frames per survivor all-gather
 REFERENCE_BUDGET_S = 60.0  # wall-clock bound of the CPU arm's timed region
 
@@ -407,7 +407,8 @@ def run_ours(args):
             if record:
                 launches += det.last_timings()["launches"]
 
-    E2E_CHUNK = 32
+    # frames per streamed call: lm_match_batch_multi at N = 1 (configs[4]'s 64-frame batches), match_stream chunks at N > 1
+    E2E_CHUNK = int(os.environ.get("LM_BENCH_E2E_CHUNK", "64" if world == 1 else "32"))
     e2e_single = None
     if world == 1:
         # streamed: lm_match_batch_multi over chunks of frames (two internal lanes: the H2D copy of frame f+1 overlaps the
@@ -516,6 +517,22 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_baseline_leg(views, frames, n_t)
 
+    # what bounds e2e: the host -> device copy of the frame.  Pinned H2D rate of this box, measured on a 64 MB block.
+    h2d_gbs = None
+    if rank == 0:
+        hbuf = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+        dbuf = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            dbuf.copy_(hbuf, non_blocking=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(8):
+            dbuf.copy_(hbuf, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = 8 * (64 << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        del hbuf, dbuf
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -526,9 +543,11 @@ def run_ours(args):
                     "h2d_bytes_per_step": ROWS * COLS * 3 + ROWS * COLS * 2,
                     "d2h_bytes_per_step": 16 + (1024 if world == 1 else sharded.capacity * world) * 32,
                     "matches_per_step": n_matches / max(1, args.steps),
+                    "h2d_gbs_measured": h2d_gbs,
+                    "h2d_floor_ms_per_step": (ROWS * COLS * 5) / (h2d_gbs * 1e9) * 1e3 if h2d_gbs else None,
                     "what": ("lm_match_batch_multi over chunks of %d pinned host frames (copies of frame f+1 overlap the kernels of "
                              "frame f)" % E2E_CHUNK) if world == 1 else "ShardedDetector.match_stream: per chunk of %d frames "
-                            "H2D on rank 0 + one NCCL broadcast per modality, local matching on 4 lanes, one NCCL all-gather of the "
+                            "H2D on rank 0 + one NCCL broadcast per modality, local matching on the handle's lanes, one NCCL all-gather of the "
                             "survivor blocks, D2H + finalise on rank 0; chunk c+1's upload overlaps chunk c's matching" % E2E_CHUNK},
             "e2e_single_call": e2e_single,
             "gpu_launches": launches_device + launches + launches_single, "clocks": clock_info,

@@ -251,7 +251,7 @@ typedef struct {
 int lm_match_multi(lm_detector* det, const lm_image* sources, int n_sources, const lm_query* queries, int n_queries,
                    const lm_image* masks, int n_masks, lm_image_out* quantized_out, lm_match_rec** out_matches,
                    size_t* out_offsets);
-/* The same over a batch of frames (sources[f*n_sources + m]); frames are pipelined over four internal lanes so that
+/* The same over a batch of frames (sources[f*n_sources + m]); frames are pipelined over eight internal lanes so that
  * the host->device copy, the kernels and the result download of consecutive frames overlap.  out_offsets receives n_frames+1 prefix offsets
  * into out_matches. */
 int lm_match_batch(lm_detector* det, const lm_image* sources, int n_frames, int n_sources, float threshold,
@@ -285,7 +285,7 @@ int lm_match_device(lm_detector* det, const void* const* d_sources, int n_source
 int lm_match_device_multi(lm_detector* det, const void* const* d_sources, int n_sources, int rows, int cols,
                           const lm_query* queries, int n_queries, void* stream, const void** d_records,
                           size_t* record_bytes_capacity);
-/* The same with an explicit workspace lane (0..3): a handle owns four independent workspaces + result blocks, so several
+/* The same with an explicit workspace lane (0..7): a handle owns eight independent workspaces + result blocks, so several
  * frames can be in flight on streams of the caller (the kernels of one 640x480 frame do not fill a B200). */
 int lm_match_device_multi_lane(lm_detector* det, int lane, const void* const* d_sources, int n_sources, int rows, int cols,
                                const lm_query* queries, int n_queries, void* stream, const void** d_records,

@@ -6,6 +6,7 @@
 // (persistence).  Everything that touches pixels runs in the CUDA kernels of lm_frontend.cu / lm_match.cu; the host
 // only stages buffers, packs template records and orders the (few) surviving matches.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -86,7 +87,7 @@ static const size_t kLmSlack = 8192;  // tail slack: vector loads of partially f
 
 // Frames in flight per handle: lm_match_batch* pipelines this many frames (H2D copy, kernels, D2H copy of different
 // frames overlap), lm_match_device_multi_lane exposes them to callers that manage their own streams.
-static const int LM_LANES = 4;
+static const int LM_LANES = 8;
 
 // One in-flight frame: stream, events, device workspace, pinned staging.
 struct Lane {
@@ -213,7 +214,7 @@ struct TrainWs {
   DevBuf pb[LM_LANES][LM_MAX_LEVELS];            // DepthNormal scratch per lane and level
   DevBuf scene, diff;                            // lm_depth_diff_batch: scene depth, [n][2] sums / counts
   PinBuf h_rects, h_segs, h_feats, h_stage;
-  cudaEvent_t ev[LM_LANES] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[LM_LANES] = {};
   void release() {
     zbuf.release(); nz_abs.release(); views.release(); rects.release(); mask.release();
     for (int m = 0; m < LM_MAX_MODALITIES; ++m) src[m].release();
@@ -375,7 +376,8 @@ static int upload_image(Lane& ln, const lm_image& im, void* dst, size_t* stage_o
   const size_t rb = src_row_bytes(im.type, im.cols);
   const size_t total = rb * im.rows;
   if (is_pinned(im.data)) {
-    CU(cudaMemcpy2DAsync(dst, rb, im.data, im.step, rb, im.rows, cudaMemcpyHostToDevice, ln.stream));
+    if (im.step == rb) CU(cudaMemcpyAsync(dst, im.data, total, cudaMemcpyHostToDevice, ln.stream));  // one linear DMA
+    else CU(cudaMemcpy2DAsync(dst, rb, im.data, im.step, rb, im.rows, cudaMemcpyHostToDevice, ln.stream));
     return LM_OK;
   }
   uint8_t* st = ln.stage_in.as<uint8_t>() + *stage_off;
@@ -993,12 +995,21 @@ static void finalize_records(int levels, std::vector<lm_raw_match>& raw, std::ve
 }
 
 // One D2H copy brings the header + the first records; long lists need a second copy.
-static int download_records(Lane& ln, cudaStream_t s, std::vector<lm_raw_match>& raw, bool* overflow, uint32_t* n_cands) {
+// Result download, part 1: header + leading records into the lane's pinned staging block.  The pipelined paths enqueue it
+// right behind the frame's kernels, so that by the time the host comes back to this lane the records are already there.
+static int enqueue_download(Lane& ln, cudaStream_t s) {
+  const size_t first = std::min<size_t>(kFirstChunkRecords, ln.out_cap);
+  CU(cudaMemcpyAsync(ln.stage_out.p, ln.result.p, kStatsBytes + sizeof(ResultHeader) + first * sizeof(lm_raw_match), cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(ln.ev[5], s));
+  return LM_OK;
+}
+
+static int download_records(Lane& ln, cudaStream_t s, std::vector<lm_raw_match>& raw, bool* overflow, uint32_t* n_cands,
+                            bool pre_enqueued = false) {
   const size_t first = std::min<size_t>(kFirstChunkRecords, ln.out_cap);
   uint8_t* host = ln.stage_out.as<uint8_t>();
-  CU(cudaMemcpyAsync(host, ln.result.p, kStatsBytes + sizeof(ResultHeader) + first * sizeof(lm_raw_match), cudaMemcpyDeviceToHost, s));
-  CU(cudaEventRecord(ln.ev[5], s));
-  CU(cudaStreamSynchronize(s));
+  if (!pre_enqueued && enqueue_download(ln, s) != LM_OK) return LM_E_CUDA;
+  CU(cudaEventSynchronize(ln.ev[5]));
   ln.work_stats[6] = *reinterpret_cast<const unsigned long long*>(host);
   host += kStatsBytes;
   ResultHeader h = *reinterpret_cast<ResultHeader*>(host);
@@ -1553,7 +1564,7 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
     std::vector<lm_raw_match> raw;
     bool overflow = false;
     uint32_t n_cands = 0;
-    if (download_records(ln, ln.stream, raw, &overflow, &n_cands) != LM_OK) return LM_E_CUDA;
+    if (download_records(ln, ln.stream, raw, &overflow, &n_cands, true) != LM_OK) return LM_E_CUDA;
     std::vector<lm_match_rec> out[kMaxQueries];
     if (overflow) {  // rare: redo this frame alone with growing buffers
       int rc = match_front(d, ln, qs, n_q, out);
@@ -1565,22 +1576,34 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
     }
     return LM_OK;
   };
+  const bool prof = getenv("LM_HOST_PROFILE") != nullptr;
+  double t_fin = 0, t_up = 0, t_plan = 0, t_enq = 0;
+  auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   for (int f = 0; f < n_frames; ++f) {
     const int li = f % LM_LANES;
     Lane& ln = d->lane[li];
+    double t0 = prof ? now() : 0;
     if (busy[li]) { int rc = finish(li, f - LM_LANES); if (rc != LM_OK) return rc; busy[li] = false; }
+    double t1 = prof ? now() : 0;
     int rc = front_from_host(d, ln, sources + (size_t)f * n_sources, n_sources, nullptr, 0, false);  // upload only
     if (rc != LM_OK) return rc;
+    double t2 = prof ? now() : 0;
     rc = ensure_pack(d, ln);
     if (rc != LM_OK) return rc;
     Pack::Plan* plan = nullptr;
     rc = get_plan(d, qs, n_q, &plan);
     if (rc != LM_OK) return rc;
     if (ensure_match_buffers(d, ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
+    double t3 = prof ? now() : 0;
     if (enqueue_frame(d, ln, *plan, qs, n_q, ln.stream) != LM_OK) return LM_E_CUDA;
     CU(cudaEventRecord(ln.ev[4], ln.stream));
+    if (enqueue_download(ln, ln.stream) != LM_OK) return LM_E_CUDA;
     busy[li] = true;
+    if (prof) { double t4 = now(); t_fin += t1 - t0; t_up += t2 - t1; t_plan += t3 - t2; t_enq += t4 - t3; }
   }
+  if (prof && n_frames)
+    fprintf(stderr, "[lm host profile] per frame us: finish %.1f upload %.1f pack/plan %.1f enqueue %.1f\n", t_fin / n_frames,
+            t_up / n_frames, t_plan / n_frames, t_enq / n_frames);
   for (int f = std::max(0, n_frames - LM_LANES); f < n_frames; ++f)
     if (busy[f % LM_LANES]) { int rc = finish(f % LM_LANES, f); if (rc != LM_OK) return rc; busy[f % LM_LANES] = false; }
   size_t n = 0;

@@ -9,6 +9,11 @@
 //   k_spread_all                                [OCV] quantize(mask) + spread + computeResponseMaps + linearize (a6-a8)
 //   k_similarity_coarse_rec                     [OCV] similarity + addSimilarities + matchClass coarse scan  (a9-a12)
 //   k_refine_nib                                [OCV] similarityLocal + matchClass refinement loop          (a13)
+//   template generation (/root/reference/src/renderer.cpp:239-329, src/rgbdDetector.cpp:147-283)
+//   k_raster_tris, k_raster_resolve             RendererIterator::render / renderDepthOnly (ORK) per oracle/render_oracle.cpp
+//   k_train_cg, k_train_dn_pb/dist/keys         [OCV] ColorGradientPyramid / DepthNormalPyramid::extractTemplate candidates
+//   k_train_sort, k_train_select                [OCV] std::stable_sort + QuantizedPyramid::selectScatteredFeatures
+//   k_depth_diff, k_mask_rect                   rgbdDetector::depth_diff; mask bounding boxes
 //   A/B references and fallbacks (same results, selected with lm_set_option)
 //   k_gauss7_u8c3, k_cg_grad, k_cg_hysteresis, k_pyrdown_u8c3, k_dn_normals, k_median5_u8, k_nn_half_u8, k_spread_lm
 //                                               the front end stage by stage            (frontend_variant = 1)

@@ -498,3 +498,23 @@ def test_lane_result_blocks_are_one_region():
         from linemod_pose_estimation_b200 import RAW_DTYPE
         raw = block[16:16 + int(hdr[0]) * 32].view(RAW_DTYPE).copy()
         common.assert_matches_equal(det.finalize_raw(raw), want, "lane %d" % lane)
+
+
+def test_config5_64_frame_batch_15_classes():
+    """BASELINE configs[4] at test scale: a 64-frame synthetic 640x480 video against 15 object classes, end to end
+    (quantise -> spread -> response -> match) through lm_match_batch; every frame's match list equals the oracle's."""
+    classes = tuple("obj%02d" % i for i in range(15))
+    orc, det, views = _pair(n_views=2, n_random=6, seed=131, classes=classes, canvas=(200, 200))
+    assert det.numClasses() == 15
+    frames = [list(synth.compose_scene(7000 + i, views[(i % 5):(i % 5) + 4])[:2]) for i in range(64)]
+    got = det.match_batch(frames, 80.0)
+    assert len(got) == 64
+    total = 0
+    for f, g in zip(frames, got):
+        common.assert_matches_equal(g, orc.match(f, 80.0))
+        total += len(g)
+    assert total > 64
+    # a class subset in caller order, same stream
+    sub = [classes[11], classes[3]]
+    for f, g in zip(frames[:8], det.match_batch(frames[:8], 80.0, class_ids=sub)):
+        common.assert_matches_equal(g, orc.match(f, 80.0, class_ids=sub))
