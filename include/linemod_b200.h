@@ -308,6 +308,15 @@ int lm_match_device_stream(lm_detector* det, const void* const* d_sources, int n
                            size_t stage_slot_bytes);
 int lm_finalize_raw(const lm_detector* det, const lm_raw_match* raw, size_t n_raw, lm_match_rec** out_matches,
                     size_t* out_n);
+/* The same for a whole exchange buffer of a streamed run: blocks + r * rank_stride + f * block_bytes is rank r's staged
+ * block of frame f (header + leading records, as lm_match_device_stream parks them and an all-gather concatenates them).
+ * For every frame and query the union of the ranks' records is finalised like lm_finalize_raw; out_offsets receives
+ * n_frames * n_queries + 1 prefix offsets (frame-major).  frame_status[f]: 0 = finalised, 1 = some rank has more than
+ * capacity_records survivors for this frame (its slices are empty: redo the frame with a larger exchange), 2 = a rank's
+ * candidate list overflowed on the device. */
+int lm_finalize_gathered(const lm_detector* det, const void* blocks, int world, int n_frames, size_t block_bytes,
+                         size_t rank_stride, uint32_t capacity_records, int n_queries, lm_match_rec** out_matches,
+                         size_t* out_offsets, uint8_t* frame_status);
 /* Template sharding (north-star multi-GPU layout): keep only templates whose canonical order index i satisfies
  * i % world == rank on this handle; template_id / class_index / order_key stay global. */
 int lm_set_shard(lm_detector* det, int rank, int world);

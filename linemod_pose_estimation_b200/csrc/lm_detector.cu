@@ -1728,6 +1728,51 @@ int lm_finalize_raw(const lm_detector* d, const lm_raw_match* raw, size_t n_raw,
   return copy_out(out, out_matches, out_n);
 }
 
+int lm_finalize_gathered(const lm_detector* d, const void* blocks, int world, int n_frames, size_t block_bytes,
+                         size_t rank_stride, uint32_t capacity_records, int n_queries, lm_match_rec** out_matches,
+                         size_t* out_offsets, uint8_t* frame_status) {
+  if (!d || !blocks || !out_matches || !out_offsets || !frame_status || world < 1 || n_frames < 0 || n_queries < 1 ||
+      n_queries > kMaxQueries || block_bytes < sizeof(ResultHeader))
+    return fail(LM_E_INVALID, "bad argument");
+  const uint8_t* base = static_cast<const uint8_t*>(blocks);
+  const int levels = d->model.levels();
+  std::vector<lm_match_rec> all, presort, out;
+  std::vector<lm_raw_match> raw, part;
+  out_offsets[0] = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    raw.clear();
+    bool over = false, dev_overflow = false;
+    for (int r = 0; r < world; ++r) {  // every rank's header first: a frame is finalised only when all blocks are whole
+      ResultHeader h;
+      std::memcpy(&h, base + (size_t)r * rank_stride + (size_t)f * block_bytes, sizeof(h));
+      over = over || h.count > capacity_records;
+      dev_overflow = dev_overflow || h.overflow != 0;
+    }
+    const uint8_t status = over ? 1 : (dev_overflow ? 2 : 0);
+    for (int r = 0; r < world && status == 0; ++r) {
+      const uint8_t* blk = base + (size_t)r * rank_stride + (size_t)f * block_bytes;
+      ResultHeader h;
+      std::memcpy(&h, blk, sizeof(h));
+      const size_t at = raw.size();
+      raw.resize(at + h.count);
+      if (h.count) std::memcpy(&raw[at], blk + sizeof(ResultHeader), (size_t)h.count * sizeof(lm_raw_match));
+    }
+    frame_status[f] = status;
+    for (int q = 0; q < n_queries; ++q) {
+      if (status == 0) {
+        part.clear();
+        for (const lm_raw_match& m : raw)
+          if ((int)(m.order_key >> 28) == q) part.push_back(m);
+        finalize_records(levels, part, presort, out);
+        all.insert(all.end(), out.begin(), out.end());
+      }
+      out_offsets[(size_t)f * n_queries + q + 1] = all.size();
+    }
+  }
+  size_t n = 0;
+  return copy_out(all, out_matches, &n);
+}
+
 // ---------------------------------------------------------------------------------------------- match clustering
 // Restates rgbdDetector::{rcd_voting, cluster_filter, similarity_score_calc, nonMaximaSuppressionUsingIOU, computeIoU}
 // (/root/reference/src/rgbdDetector.cpp:36-84, 133-145, 462-574) on the match records this library returns.

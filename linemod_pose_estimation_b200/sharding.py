@@ -190,7 +190,7 @@ class ShardedDetector(ShardedMatcher):
         _capi.check(_capi.lib().lm_copy_result_block(self.det._h, lane, self._send_ptrs[slot], nbytes, stream))
 
     # ------------------------------------------------------------------ streamed frames
-    def match_stream(self, host_frames, queries, kinds=("cg", "dn"), chunk=16, lanes=4):
+    def match_stream(self, host_frames, queries, kinds=("cg", "dn"), chunk=16, lanes=8):
         """A stream of frames through the sharded matcher, pipelined: per chunk of `chunk` frames ONE broadcast per
         modality (rank 0 uploads its pinned host frames into a device chunk buffer first) and ONE all-gather of the
         survivor blocks; within a chunk `lanes` frames are in flight on as many streams; the upload + broadcast of chunk
@@ -265,40 +265,41 @@ class ShardedDetector(ShardedMatcher):
             st["free"][b] = done
             return host, done, g, lo
 
+        def redo(j, lo):   # rare: this frame again through the per-frame path, which grows its own exchange
+            keep = self.capacity
+            if not hasattr(self, "_redo_bufs") or self._redo_bufs[0].shape[:2] != (rows, cols):
+                self._redo_bufs = self.frame_buffers(rows, cols, kinds)
+            if self.rank == 0:
+                for m, k in enumerate(kinds):
+                    a = host_frames[lo + j][m]
+                    self._redo_bufs[m].copy_(torch.from_numpy(a if k == "cg" else a.view(np.int16)))
+            res = self.match(self._redo_bufs, queries)
+            self.capacity = keep
+            return res
+
         def finish(host, done, g, lo):
             done.synchronize()
             arr = host.numpy()                                   # [world][chunk][block bytes]
-            world = arr.shape[0]
+            world, slots, block_bytes = arr.shape
             hdr = np.ascontiguousarray(arr[:, :g, :RESULT_HEADER_BYTES]).view(np.uint32).reshape(world, g, 4)
-            counts, overflow = hdr[:, :, 0].astype(np.int64), hdr[:, :, 2]
+            # every rank sees every header, so all ranks agree on which frames outgrew the staged capacity
+            over = (hdr[:, :, 0] > self.capacity).any(axis=0)
+            if ((hdr[:, :, 2] != 0).any(axis=0) & ~over).any():
+                raise RuntimeError("a rank overflowed its device-side candidate list")
+            if self.rank != 0:
+                return [redo(j, lo) if over[j] else None for j in range(g)]
+            # rank 0: the whole chunk is ordered / de-duplicated in one library call (lm_finalize_gathered)
+            outp = C.c_void_p()
+            offs = (C.c_size_t * (g * n_q + 1))()
+            status = np.zeros(g, np.uint8)
+            _capi.check(lib.lm_finalize_gathered(self.det._h, arr.ctypes.data, world, g, block_bytes, slots * block_bytes,
+                                                 self.capacity, n_q, C.byref(outp), offs, status.ctypes.data))
+            allm = self.det._take(outp, offs[g * n_q])
             out = []
             for j in range(g):
-                # every rank sees every header, so all ranks agree on which frames outgrew the staged capacity
-                if (counts[:, j] > self.capacity).any():   # rare: this frame again through the per-frame path, which
-                    keep = self.capacity                     # grows its own exchange (and the device block if need be)
-                    if not hasattr(self, "_redo_bufs") or self._redo_bufs[0].shape[:2] != (rows, cols):
-                        self._redo_bufs = self.frame_buffers(rows, cols, kinds)
-                    if self.rank == 0:
-                        for m, k in enumerate(kinds):
-                            a = host_frames[lo + j][m]
-                            self._redo_bufs[m].copy_(torch.from_numpy(a if k == "cg" else a.view(np.int16)))
-                    res = self.match(self._redo_bufs, queries)
-                    self.capacity = keep
-                    out.append(res)
-                    continue
-                if overflow[:, j].any():
+                if status[j] == 2:
                     raise RuntimeError("a rank overflowed its device-side candidate list")
-                if self.rank != 0:
-                    out.append(None)
-                    continue
-                parts = [arr[r, j, RESULT_HEADER_BYTES:RESULT_HEADER_BYTES + int(counts[r, j]) * RECORD_BYTES]
-                         for r in range(world) if counts[r, j]]
-                raw = np.concatenate(parts).view(RAW_DTYPE) if parts else np.zeros(0, RAW_DTYPE)
-                if n_q == 1:
-                    out.append([self.finalize(raw)])
-                else:
-                    tag = raw["order_key"] >> 28
-                    out.append([self.finalize(raw[tag == q]) for q in range(n_q)])
+                out.append(redo(j, lo) if status[j] == 1 else [allm[offs[j * n_q + q]:offs[j * n_q + q + 1]] for q in range(n_q)])
             return out
 
         results = []

@@ -244,6 +244,49 @@ def test_finalize_raw_equals_reference_sort_unique():
     assert np.all(np.diff(got["similarity"]) <= 0)
 
 
+def test_finalize_gathered_equals_per_frame_finalize():
+    """lm_finalize_gathered (one call per exchanged chunk of the sharded stream) == lm_finalize_raw on every frame's and
+    query's union of the ranks' records; frames whose staged slot is too small are flagged, not silently truncated."""
+    import ctypes as C
+
+    from linemod_pose_estimation_b200 import _capi
+    from linemod_pose_estimation_b200.sharding import pack_block
+    det = _random_detector(8)
+    rng = np.random.default_rng(8)
+    world, frames, slots, cap, n_q = 3, 5, 6, 64, 2
+    block_bytes = 16 + cap * RAW_DTYPE.itemsize
+    buf = np.zeros((world, slots, block_bytes), np.uint8)
+    raws = {}
+    for f in range(frames):
+        for r in range(world):
+            n = int(rng.integers(0, 50)) if f != 3 else (cap + 9 if r == 1 else 5)   # frame 3: rank 1 outgrows its slot
+            raw = np.zeros(n, RAW_DTYPE)
+            pos = rng.permutation(20 * 1200)[:n]
+            q = rng.integers(0, n_q, n)
+            raw["order_key"] = (pos // 1200 * world + r) | (q << 28)
+            raw["coarse_pos"] = pos % 1200
+            raw["x"], raw["y"] = rng.integers(0, 9, n) * 5 + 2, rng.integers(0, 5, n) * 5 + 2
+            raw["score"], raw["nf"] = rng.integers(230, 253, n), 63
+            raw["template_id"], raw["class_index"] = raw["order_key"] & 0xfffffff, q
+            raws[(f, r)] = raw
+            buf[r, f] = pack_block(raw, cap)
+    out, offs = C.c_void_p(), (C.c_size_t * (frames * n_q + 1))()
+    status = np.zeros(frames, np.uint8)
+    _capi.check(_capi.lib().lm_finalize_gathered(det._h, buf.ctypes.data, world, frames, block_bytes, slots * block_bytes, cap, n_q,
+                                                 C.byref(out), offs, status.ctypes.data))
+    allm = det._take(out, offs[frames * n_q])
+    assert list(status) == [0, 0, 0, 1, 0]
+    for f in range(frames):
+        union = np.concatenate([raws[(f, r)] for r in range(world)])
+        for q in range(n_q):
+            got = allm[offs[f * n_q + q]:offs[f * n_q + q + 1]]
+            if f == 3:
+                assert len(got) == 0
+            else:
+                common.assert_matches_equal(got, det.finalize_raw(union[(union["order_key"] >> 28) == q]), "frame %d query %d" % (f, q))
+    assert offs[frames * n_q] > 100
+
+
 def test_binary_template_cache_roundtrip_and_speed(tmp_path):
     """lm_write_cache / lm_create_from_cache hold exactly the model of the templates.yml, reject corrupted
     files, and load far faster than the YAML parse the reference's service repeats on every request."""
