@@ -131,6 +131,7 @@ struct Lane {
   bool graph_broken = false;  // capture failed once on this lane: stay on the eager path
   // matching
   DevBuf cand, work, work_order, dump, dbg_recs;
+  DevBuf mod_bits;  // per modality: orientation bits set in the coarsest level's spread image (front end -> coarse kernel hint)
   struct Ref {  // this lane's result block inside the detector-wide allocation (lm_detector::results_all)
     void* p = nullptr;
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
@@ -147,6 +148,7 @@ struct Lane {
     CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (int i = 0; i < 6; ++i) CU(cudaEventCreate(&ev[i]));
     CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    if (mod_bits.ensure(sizeof(unsigned int) * LM_MAX_MODALITIES) != LM_OK) return LM_E_CUDA;
     for (int i = 0; i < LM_MAX_MODALITIES - 1; ++i) {
       CU(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
       CU(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
@@ -163,7 +165,7 @@ struct Lane {
     }
     for (int l = 0; l < LM_MAX_LEVELS; ++l) lmem[l].release();
     for (int l = 0; l < LM_MAX_LEVELS; ++l) lmn[l].release();
-    cand.release(); work.release(); work_order.release(); dump.release(); dbg_recs.release();
+    cand.release(); work.release(); work_order.release(); dump.release(); dbg_recs.release(); mod_bits.release();
     stage_in.release(); stage_out.release();
     if (gexec) cudaGraphExecDestroy(gexec);
     for (int i = 0; i < 6; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
@@ -244,6 +246,7 @@ struct lm_detector {
   Pack pack;
   int shard_rank = 0, shard_world = 1;
   int debug_taps = 0, coarse_variant = 0, refine_variant = 0, timing = 1, frontend_variant = 0, prune = 1, graphs = 1;
+  int mod_order = 2;  // coarse kernel: 0 = modalities in template order, 1 = reversed, 2 = chosen per frame (default)
   std::vector<std::string> class_id_cache;
 };
 
@@ -533,6 +536,7 @@ static bool refine_nibbles(const lm_detector* d, const Lane& ln) {
 // [OCV] Detector::match front half: quantize (mask) -> spread -> computeResponseMaps -> linearize per level/modality.
 static int run_front(lm_detector* d, Lane& ln, cudaStream_t s) {
   const int L = d->model.levels(), M = d->model.M();
+  CU(cudaMemsetAsync(ln.mod_bits.p, 0, sizeof(unsigned int) * LM_MAX_MODALITIES, s));
   if (run_quantize(d, ln, s) != LM_OK) return LM_E_CUDA;
   const bool taps = d->debug_taps != 0;
   if (taps && ensure_tap_ws(d, ln) != LM_OK) return LM_E_CUDA;
@@ -570,6 +574,7 @@ static int run_front(lm_detector* d, Lane& ln, cudaStream_t s) {
         e.response = taps ? ln.response[l][m].as<uint8_t>() : nullptr;
         e.lm = byt[l] ? ln.lmem[l].as<uint8_t>() + (size_t)m * 8 * g.plane_stride : nullptr;
         e.lm_nib = nib[l] ? ln.lmn[l].as<uint8_t>() + (size_t)m * 4 * g.plane_stride : nullptr;
+        e.bits = l == L - 1 ? ln.mod_bits.as<unsigned int>() + m : nullptr;
         e.plane_stride = g.plane_stride;
         e.rows = g.rows; e.cols = g.cols; e.T = g.T; e.W = g.W; e.H = g.H; e.level = l; e.mask_cols0 = ln.cols;
         e.block_begin = total;
@@ -890,8 +895,9 @@ static int enqueue_match(lm_detector* d, Lane& ln, const Pack::Plan& plan, const
   for (int q = 0; q < n_q; ++q) { qt.v[q] = qs[q].threshold; rp.threshold[q] = qs[q].threshold; }
   launch_similarity_coarse(d->coarse_variant, ln.lmem[L - 1].as<uint8_t>(), ln.lmn[d->model.levels() - 1].as<uint8_t>(), pk.foff.as<uint32_t>(),
                            pk.ctpl.as<CoarseTpl>(), plan.items.as<WorkItem>(), plan.tiles.as<uint2>(), plan_recs(plan), plan.rec_words,
-                           plan.n_tiles, qt, M, d->prune, ln.cand.as<Cand>(), d_hdr, ln.result.as<unsigned long long>(),
-                           ln.cand_cap, nullptr, 0, s);
+                           plan.n_tiles, qt, M, (d->prune & 1) | (d->mod_order << 8), ln.cand.as<Cand>(), d_hdr,
+                           ln.result.as<unsigned long long>(), ln.cand_cap, nullptr, 0, s,
+                           d->frontend_variant == 0 ? ln.mod_bits.as<unsigned int>() : nullptr);
   if (plan.n_tiles > 0) ++ln.launches;
   if (ev_mid) CU(cudaEventRecord(ev_mid, s));
   rp.levels = L; rp.M = M; rp.coarse_T = gc.T; rp.coarse_W = gc.W;
@@ -927,7 +933,7 @@ static int enqueue_frame(lm_detector* d, Lane& ln, const Pack::Plan& plan, const
   key.shard_rank = d->shard_rank; key.shard_world = d->shard_world;
   for (int m = 0; m < d->model.M(); ++m) key.src[m] = ln.src_ptr[m];
   key.model_version = d->model.version; key.rows = ln.rows; key.cols = ln.cols; key.n_q = n_q;
-  key.variant = d->coarse_variant + 16 * d->refine_variant; key.prune = d->prune; key.frontend = d->frontend_variant;
+  key.variant = d->coarse_variant + 16 * d->refine_variant; key.prune = d->prune | (d->mod_order << 8); key.frontend = d->frontend_variant;
   key.cand_cap = ln.cand_cap; key.out_cap = ln.out_cap;
   for (int q = 0; q < n_q; ++q) key.thr[q] = qs[q].threshold;
   if (ln.gexec == nullptr || std::memcmp(&key, &ln.gkey, sizeof(key)) != 0) {
@@ -1445,6 +1451,7 @@ int lm_set_option(lm_detector* d, const char* key, int value) {
   else if (k == "coarse_variant") { d->coarse_variant = value; for (int i = 0; i < LM_LANES; ++i) d->lane[i].front_valid = false; }
   else if (k == "timing") d->timing = value;
   else if (k == "prune") d->prune = value;
+  else if (k == "mod_order") d->mod_order = value & 3;
   else if (k == "refine_variant") { d->refine_variant = value; for (int i = 0; i < LM_LANES; ++i) d->lane[i].front_valid = false; }
   else if (k == "graphs") d->graphs = value;
   else if (k == "coarse_grid_limit") {  // process-wide; recorded graphs hold the old grid

@@ -529,6 +529,7 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
   }
   __syncthreads();
   // ---- OR over T rows
+  unsigned int n_bits = 0;
   for (int i = tid; i < T * NWO; i += 256) {
     const int r = i / NWO, wi = i - r * NWO;
     uint32_t v = 0;
@@ -539,6 +540,7 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
       for (int k = 0; k < T; ++k) v |= sh[(r + k) * NWO + wi];
     }
     sp[i] = v;
+    n_bits += __popc(v);
     if (E.spread) {
       const int gy = py0 + r;
 #pragma unroll
@@ -547,6 +549,10 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
         if (gy < rows && gx < cols) E.spread[(size_t)gy * cols + gx] = (uint8_t)(v >> (8 * k));
       }
     }
+  }
+  if (E.bits != nullptr) {  // a performance hint for the coarse kernel, not a result: see SpreadEntry::bits
+    n_bits = __reduce_add_sync(0xffffffffu, n_bits);
+    if ((tid & 31) == 0 && n_bits) atomicAdd(E.bits, n_bits);
   }
   __syncthreads();
   // ---- responses -> linear memories

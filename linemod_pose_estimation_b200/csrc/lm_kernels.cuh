@@ -124,6 +124,8 @@ struct SpreadEntry {
   uint8_t* response;     // parity tap or null
   uint8_t* lm;           // this modality's 8 orientation byte planes, or null (coarsest level when only lm_nib is needed)
   uint8_t* lm_nib;       // coarsest level: this modality's 8 nibble-packed planes (plane_stride / 2 bytes each), or null
+  unsigned int* bits;    // coarsest level: += orientation bits set in this modality's spread image (null: not counted);
+                         // the coarse kernel starts with the modality that has fewer (lower responses, earlier pruning)
   unsigned long long plane_stride;
   int rows, cols, T, W, H, level, mask_cols0, block_begin, blocks_x;
 };
@@ -161,7 +163,10 @@ void launch_similarity_coarse(int variant, const uint8_t* lmc, const uint8_t* lm
                               const CoarseTpl* tpl, const WorkItem* items, const uint2* tiles, const uint32_t* recs,
                               int rec_words, int n_tiles, const QueryThresholds& thr, int M, int prune, Cand* cand,
                               ResultHeader* hdr, unsigned long long* touched, uint32_t cand_cap, uint16_t* dump,
-                              int dump_stride, cudaStream_t s);
+                              int dump_stride, cudaStream_t s, const unsigned int* mod_bits = nullptr);
+// `prune` bits for variant 0: bit 0 = exact early termination; bit 8 = sum the modalities in reverse order; bit 9 = pick
+// the order per frame: reversed when mod_bits[M-1] < mod_bits[0] (mod_bits[m] = orientation bits set in modality m's
+// spread image at the coarsest level, counted by the front end: fewer bits = lower responses = earlier termination).
 // n_bytes (multiple of 16) of byte planes -> n_bytes / 2 of nibble-packed planes
 void launch_pack_nibbles(const uint8_t* lm_bytes, uint8_t* lm_nibbles, size_t n_bytes, cudaStream_t s);
 void launch_refine(bool nibble_planes, const RefineParams& p, const CoarseTpl* ctpl, const WorkItem* items, const Cand* cand,

@@ -454,23 +454,35 @@ __global__ void __launch_bounds__(256, 3) k_similarity_coarse_rec(const uint8_t*
                                                                int n_tiles, const QueryThresholds thr_q, int M, int prune,
                                                                Cand* __restrict__ cand, ResultHeader* hdr,
                                                                unsigned long long* touched, uint32_t cand_cap,
-                                                               uint16_t* __restrict__ dump, int dump_stride) {
+                                                               uint16_t* __restrict__ dump, int dump_stride,
+                                                               const unsigned int* __restrict__ mod_bits) {
   __shared__ uint32_t s_rec[8][kRecMaxWords];
+  __shared__ unsigned long long s_bytes;
+  __shared__ uint32_t s_done, s_expected;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* sr = s_rec[warp];
   cudaGridDependencySynchronize();            // linear memories (previous kernel in the stream) are complete
   cudaTriggerProgrammaticLaunchCompletion();  // let k_refine's blocks be scheduled as this grid drains
-  auto draw = [&]() -> uint32_t {
-    uint32_t t = 0;
-    if (lane == 0) t = atomicAdd(&hdr->next_tile, 1u);
-    return __shfl_sync(kFull, t, 0);
-  };
-  uint32_t cur = draw();
+  // Tile hand-out: the first two tiles of every warp are static (tile = global warp index, then + number of warps) --
+  // thousands of warps drawing from one counter at kernel start serialise on that address -- and only the rest comes from
+  // the atomic dispenser (tiles are sorted heaviest first, so the dynamic part balances the light tail).
+  const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+  const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
+  uint32_t cur = gwarp;
+  if (threadIdx.x == 0) {
+    s_bytes = 0; s_done = 0;
+    const uint32_t first_warp = blockIdx.x * (blockDim.x >> 5);  // warps of this CTA that have a first tile
+    s_expected = (uint32_t)n_tiles > first_warp ? min((uint32_t)n_tiles - first_warp, blockDim.x >> 5) : 0u;
+  }
+  __syncthreads();
   if (cur >= (uint32_t)n_tiles) return;
   for (int i = lane; i < rec_words; i += 32) sr[i] = __ldg(recs + (size_t)cur * rec_words + i);
-  uint32_t nxt = draw();
+  uint32_t nxt = gwarp + n_warps;
   const uint32_t lane_byte = (uint32_t)lane * 16u;
   const int first = lane * 32;  // first position of this lane within the pass
+  const bool do_prune = (prune & 1) != 0;
+  // bit 8 of `prune`: sum the modalities in reverse order; bit 9: decide per frame from the front end's counters
+  const bool mod_reversed = (prune & 0x200) ? (mod_bits != nullptr && mod_bits[M - 1] < mod_bits[0]) : (prune & 0x100) != 0;
   unsigned long long bytes = 0;  // (feature, position) pairs actually gathered by this warp
   for (;;) {
     __syncwarp();
@@ -482,7 +494,10 @@ __global__ void __launch_bounds__(256, 3) k_similarity_coarse_rec(const uint8_t*
       const int idx = lane + 32 * i;
       pre[i] = (has_next && idx < rec_words) ? __ldg(recs + (size_t)nxt * rec_words + idx) : 0u;
     }
-    const uint32_t nxt2 = has_next ? draw() : nxt;
+    // the ticket of the tile after next: issued now, read at the end of this tile (the atomic's round trip -- long when
+    // thousands of warps draw at once -- overlaps the scoring instead of stalling it)
+    uint32_t ticket = 0;
+    if (has_next && lane == 0) ticket = atomicAdd(&hdr->next_tile, 1u);
 
     const uint32_t item = sr[0], tg = sr[1], nfq = sr[2], order = sr[6];
     const int n_feat = (int)sr[3], j0 = (int)sr[4], rem = (int)sr[5];
@@ -495,10 +510,14 @@ __global__ void __launch_bounds__(256, 3) k_similarity_coarse_rec(const uint8_t*
 #pragma unroll
     for (int k = 0; k < 4; ++k) tot[k][0] = tot[k][1] = tot[k][2] = tot[k][3] = 0;
     uint32_t acc_e[4] = {0, 0, 0, 0}, acc_o[4] = {0, 0, 0, 0};
-    const uint32_t* fw = sr + kRecHdrWords;
     int done = 0;
     bool alive = true;
-    for (int m = 0; m < M && alive; ++m) {
+    for (int mi = 0; mi < M && alive; ++mi) {
+      // The order in which the modalities are summed is free (the pruning bound is exact for any order and survivors are
+      // summed completely): start with the modality the front end found more discriminative on this frame.
+      const int m = mod_reversed ? M - 1 - mi : mi;
+      const uint32_t* fw = sr + kRecHdrWords;
+      for (int k = 0; k < m; ++k) fw += __dp4a(sr[8 + k], 0x01010101u, 0u);  // features of the modalities before m
       const uint32_t c4 = sr[8 + m];  // 4 class sizes, one word
       const int n0 = c4 & 255, n1 = (c4 >> 8) & 255, n2 = (c4 >> 16) & 255, n3 = c4 >> 24;
       if (active) {
@@ -507,14 +526,14 @@ __global__ void __launch_bounds__(256, 3) k_similarity_coarse_rec(const uint8_t*
       }
       fw += n0 + n1; done += n0 + n1;
       rec_widen(acc_e, acc_o, tot);
-      if (prune && !rec_alive(tot, thr, n_feat - done, active)) { alive = false; break; }
+      if (do_prune && !rec_alive(tot, thr, n_feat - done, active)) { alive = false; break; }
       if (active) {
         rec_group<2>(lmn, fw, n2, lane_byte, acc_e, acc_o);
         rec_group<3>(lmn, fw + n2, n3, lane_byte, acc_e, acc_o);
       }
-      fw += n2 + n3; done += n2 + n3;
+      done += n2 + n3;
       rec_widen(acc_e, acc_o, tot);
-      if (prune && !rec_alive(tot, thr, n_feat - done, active)) alive = false;
+      if (do_prune && !rec_alive(tot, thr, n_feat - done, active)) alive = false;
     }
     bytes += (unsigned long long)done * (unsigned)rem;
     if (alive && active) {
@@ -557,9 +576,15 @@ __global__ void __launch_bounds__(256, 3) k_similarity_coarse_rec(const uint8_t*
       const int idx = lane + 32 * i;
       if (idx < rec_words) sr[idx] = pre[i];
     }
-    nxt = nxt2;
+    nxt = __shfl_sync(kFull, ticket, 0) + 2u * n_warps;
   }
-  if (lane == 0 && touched != nullptr) atomicAdd(touched, bytes);
+  // gathered-bytes statistic: summed per CTA in shared memory, one global atomic per CTA by the warp that finishes last
+  // (one atomic per warp on a single address costs microseconds at the end of a launch of thousands of warps)
+  if (lane == 0 && touched != nullptr) {
+    atomicAdd(&s_bytes, bytes);
+    __threadfence_block();
+    if (atomicAdd(&s_done, 1u) + 1u == s_expected) atomicAdd(touched, s_bytes);
+  }
 }
 
 // Byte linear memories -> nibble-packed copy (two positions per byte), 16 bytes in / 8 bytes out per thread.
@@ -1059,7 +1084,7 @@ void launch_similarity_coarse(int variant, const uint8_t* lmc, const uint8_t* lm
                               const CoarseTpl* tpl, const WorkItem* items, const uint2* tiles, const uint32_t* recs,
                               int rec_words, int n_tiles, const QueryThresholds& thr, int M, int prune, Cand* cand,
                               ResultHeader* hdr, unsigned long long* touched, uint32_t cand_cap, uint16_t* dump,
-                              int dump_stride, cudaStream_t s) {
+                              int dump_stride, cudaStream_t s, const unsigned int* mod_bits) {
   if (n_tiles <= 0) return;
   int blocks = (n_tiles + 7) / 8;
   if (variant == 1) {  // byte linear memories (A/B reference of the nibble kernels)
@@ -1076,7 +1101,7 @@ void launch_similarity_coarse(int variant, const uint8_t* lmc, const uint8_t* lm
     if (g_coarse_grid_limit > 0) grid = min(grid, g_coarse_grid_limit);
     cudaLaunchConfig_t cfg = pdl_config(grid, 256, s);
     cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec, lmn, recs, rec_words, n_tiles, thr, M,
-                       dump == nullptr ? prune : 0, cand, hdr, touched, cand_cap, dump, dump_stride);
+                       dump == nullptr ? prune : 0, cand, hdr, touched, cand_cap, dump, dump_stride, mod_bits);
   }
 }
 
