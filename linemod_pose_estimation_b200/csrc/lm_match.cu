@@ -388,14 +388,43 @@ __device__ __forceinline__ void rec_window(const uint8_t* __restrict__ lmn, uint
   for (int k = 0; k < 4; ++k) n[k] = __funnelshift_r(w[Q + k], w[Q + k + 1], sh);
 }
 
+// The five words w[Q .. Q+4] a window of class Q needs (the rest of the second vector load is dropped at once).
+template <int Q>
+__device__ __forceinline__ void rec_load(const uint8_t* __restrict__ lmn, uint32_t v, uint32_t lane_byte, uint32_t (&x)[5]) {
+  const uint8_t* p = lmn + (v & ~15u) + lane_byte;
+  const uint4 c = ldg128(p);
+  if (Q == 0) {
+    x[0] = c.x; x[1] = c.y; x[2] = c.z; x[3] = c.w; x[4] = ldg32(p + 16);
+  } else if (Q == 1) {
+    const uint2 e = ldg64(p + 16);
+    x[0] = c.y; x[1] = c.z; x[2] = c.w; x[3] = e.x; x[4] = e.y;
+  } else {
+    const uint4 e = ldg128(p + 16);
+    if (Q == 2) { x[0] = c.z; x[1] = c.w; x[2] = e.x; x[3] = e.y; x[4] = e.z; }
+    else { x[0] = c.w; x[1] = e.x; x[2] = e.y; x[3] = e.z; x[4] = e.w; }
+  }
+}
+
+// `zero` is a run-time zero the compiler cannot see through.  OR-ing (last loaded word & zero) into the first word makes
+// every shift of the group depend on the LAST load, so all twelve loads of a group are in flight before the first result
+// is consumed; left alone, ptxas recycles the destination registers of the first loads for the later ones and turns one
+// round trip to L2 per group into two or three -- on the kernel's critical path, the tiles that survive every check.
+// (Measured alternatives that lost: rounds of nine features with predicated loads, an L1 prefetch of the next class.)
 template <int Q>
 __device__ __forceinline__ void rec_group(const uint8_t* __restrict__ lmn, const uint32_t* fw, int n, uint32_t lane_byte,
-                                          uint32_t (&acc_e)[4], uint32_t (&acc_o)[4]) {
+                                          uint32_t (&acc_e)[4], uint32_t (&acc_o)[4], uint32_t zero) {
   int f = 0;
   for (; f + 6 <= n; f += 6) {
-    uint32_t a[6][4];
+    uint32_t x[6][5], a[6][4];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) rec_window<Q>(lmn, fw[f + i], lane_byte, a[i]);
+    for (int i = 0; i < 6; ++i) rec_load<Q>(lmn, fw[f + i], lane_byte, x[i]);
+    x[0][0] |= x[5][4] & zero;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const uint32_t sh = fw[f + i] << 2;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a[i][k] = __funnelshift_r(x[i][k], x[i][k + 1], sh);
+    }
     uint32_t s0[4], s1[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { s0[k] = a[0][k] + a[1][k] + a[2][k]; s1[k] = a[3][k] + a[4][k] + a[5][k]; }
@@ -449,7 +478,7 @@ __device__ __forceinline__ bool rec_alive(const uint32_t (&tot)[4][4], int thr, 
   return __any_sync(kFull, active && best > need);
 }
 
-__global__ void __launch_bounds__(256, 3) k_similarity_coarse_rec(const uint8_t* __restrict__ lmn,
+__global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const uint8_t* __restrict__ lmn,
                                                                const uint32_t* __restrict__ recs, int rec_words,
                                                                int n_tiles, const QueryThresholds thr_q, int M, int prune,
                                                                Cand* __restrict__ cand, ResultHeader* hdr,
@@ -481,6 +510,7 @@ __global__ void __launch_bounds__(256, 3) k_similarity_coarse_rec(const uint8_t*
   const uint32_t lane_byte = (uint32_t)lane * 16u;
   const int first = lane * 32;  // first position of this lane within the pass
   const bool do_prune = (prune & 1) != 0;
+  const uint32_t zero = (uint32_t)n_tiles >> 31;  // n_tiles > 0: zero, but only at run time (see rec_group)
   // bit 8 of `prune`: sum the modalities in reverse order; bit 9: decide per frame from the front end's counters
   const bool mod_reversed = (prune & 0x200) ? (mod_bits != nullptr && mod_bits[M - 1] < mod_bits[0]) : (prune & 0x100) != 0;
   unsigned long long bytes = 0;  // (feature, position) pairs actually gathered by this warp
@@ -521,15 +551,15 @@ __global__ void __launch_bounds__(256, 3) k_similarity_coarse_rec(const uint8_t*
       const uint32_t c4 = sr[8 + m];  // 4 class sizes, one word
       const int n0 = c4 & 255, n1 = (c4 >> 8) & 255, n2 = (c4 >> 16) & 255, n3 = c4 >> 24;
       if (active) {
-        rec_group<0>(lmn, fw, n0, lane_byte, acc_e, acc_o);
-        rec_group<1>(lmn, fw + n0, n1, lane_byte, acc_e, acc_o);
+        rec_group<0>(lmn, fw, n0, lane_byte, acc_e, acc_o, zero);
+        rec_group<1>(lmn, fw + n0, n1, lane_byte, acc_e, acc_o, zero);
       }
       fw += n0 + n1; done += n0 + n1;
       rec_widen(acc_e, acc_o, tot);
       if (do_prune && !rec_alive(tot, thr, n_feat - done, active)) { alive = false; break; }
       if (active) {
-        rec_group<2>(lmn, fw, n2, lane_byte, acc_e, acc_o);
-        rec_group<3>(lmn, fw + n2, n3, lane_byte, acc_e, acc_o);
+        rec_group<2>(lmn, fw, n2, lane_byte, acc_e, acc_o, zero);
+        rec_group<3>(lmn, fw + n2, n3, lane_byte, acc_e, acc_o, zero);
       }
       done += n2 + n3;
       rec_widen(acc_e, acc_o, tot);
