@@ -389,7 +389,10 @@ int lm_last_timings(const lm_detector* det, float ms[5], int* kernel_launches);
  * (exact early termination skips features of tiles in which no position can reach the threshold any more), [7] 0. */
 int lm_last_work(const lm_detector* det, uint64_t out[8]);
 /* Tuning / A-B switches: "coarse_variant" (0 production, 1 byte planes, 2 nibble planes without tile records),
- * "prune" (1 = exact early termination in the coarse kernel, default), "frontend_variant", "debug_taps". */
+ * "prune" (1 = exact early termination in the coarse kernel, default), "mod_order" (order in which the coarse kernel sums
+ * the modalities: 0 = template order, 1 = reversed, 2 = chosen per frame from the front end's spread-bit counters,
+ * default; results do not depend on it), "refine_variant", "frontend_variant", "graphs", "timing", "debug_taps",
+ * "coarse_grid_limit", "device_out_cap". */
 int lm_set_option(lm_detector* det, const char* key, int value);
 
 #ifdef __cplusplus

@@ -134,6 +134,26 @@ def test_coarse_kernel_variants(variant):
     assert len(want) > 0
 
 
+@pytest.mark.parametrize("order", [0, 1, 2])
+@pytest.mark.parametrize("kinds", [("cg", "dn"), ("dn", "cg"), ("cg", "dn", "cg")])
+def test_modality_order_of_the_coarse_sum_does_not_change_results(order, kinds):
+    """The coarse kernel may sum the modalities in template order (0), reversed (1) or in the order the front end's
+    spread-bit counters suggest for the frame (2, default): the early-termination bound is exact for any order, so the
+    candidate counts and the match lists are the oracle's in every case, while the bytes gathered differ."""
+    orc, det, views = _pair(kinds=kinds, n_views=6, n_random=60, seed=33)
+    det.set_option("mod_order", order)
+    bgr, depth, _ = synth.compose_scene(1007, views[:4])
+    src = common.sources_for(kinds, bgr, depth)
+    for thr in (92.0, 70.0):
+        want = orc.match(src, thr, keep_candidates=True)
+        got = det.match(src, thr)
+        common.assert_matches_equal(got, want, "order %d thr %g" % (order, thr))
+        assert det.last_work()["candidates"] == len(orc.last_candidates())
+        w = det.last_work()
+        assert 0 < w["B_coarse_gathered"] <= w["B_coarse"]
+    assert len(want) > 0
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 def test_refine_kernel_variants(variant):
     """0: refinement on nibble-packed planes (production when every refinement level has word-aligned rows), 1: on byte
