@@ -81,6 +81,7 @@ struct Match {
 struct Rect {
   int x, y, width, height;
   Rect() : x(0), y(0), width(0), height(0) {}
+  Rect(int x_, int y_, int w_, int h_) : x(x_), y(y_), width(w_), height(h_) {}
 };
 
 // Borrowed view of host pixels (the role cv::Mat plays in the reference's calls).  step = bytes between rows, so a
@@ -340,6 +341,12 @@ class Detector {
   }
 #endif
 
+  // The trainer's loop (src/renderer.cpp:239-329): render every view (T, up: camera position and up vector per view,
+  // see ViewSphere) of `mesh` and addTemplate it, all on the GPU.  Returns the template ids (-1 where a view failed).
+  std::vector<int> trainViews(const class Mesh& mesh, const lm_camera& camera, const std::vector<double>& T,
+                              const std::vector<double>& up, const std::string& class_id,
+                              std::vector<Rect>* mask_rects = nullptr, std::vector<uint16_t>* centre_depth_mm = nullptr);
+
   lm_detector* handle() const { return h_; }  // for the batch / multi-query / multi-GPU entry points of the C ABI
 
  private:
@@ -350,6 +357,82 @@ class Detector {
   std::vector<std::shared_ptr<Modality> > modalities_;
   mutable std::map<std::pair<std::string, int>, TemplatePyramid> cache_;
 };
+
+// ------------------------------------------------------------------------------------------------ training helpers
+// Renderer3d(stl_file) of the reference's trainer (src/renderer.cpp:239): a triangle mesh in the object frame, metres.
+class Mesh {
+ public:
+  explicit Mesh(const std::string& stl_file) : m_(nullptr) { detail::check(lm_mesh_load_stl(stl_file.c_str(), &m_)); }
+  Mesh(const float* triangles, int n_triangles) : m_(nullptr) { detail::check(lm_mesh_create(triangles, n_triangles, &m_)); }
+  ~Mesh() { lm_mesh_destroy(m_); }
+  int numTriangles() const { return lm_mesh_num_triangles(m_); }
+  lm_mesh* handle() const { return m_; }
+
+ private:
+  Mesh(const Mesh&);
+  Mesh& operator=(const Mesh&);
+  lm_mesh* m_;
+};
+
+// RendererIterator (src/renderer.cpp:242-246): n_points on a sphere x in-plane angles x radii, in the reference's order.
+class ViewSphere {
+ public:
+  ViewSphere(int n_points, int angle_step, float radius_min, float radius_max, float radius_step, int angle_min = -80,
+             int angle_max = 80) {
+    vs_.n_points = n_points; vs_.angle_min = angle_min; vs_.angle_max = angle_max; vs_.angle_step = angle_step;
+    vs_.radius_min = radius_min; vs_.radius_max = radius_max; vs_.radius_step = radius_step;
+  }
+  int size() const { return detail::check(lm_view_count(&vs_)); }  // n_templates()
+  // camera position T and up vector of view `index`; D_obj = radius
+  void view(int index, double T[3], double up[3], float* radius = nullptr) const {
+    detail::check(lm_view_params(&vs_, index, T, up, radius, nullptr, nullptr));
+  }
+  // all views, flattened (3 doubles per view)
+  void views(std::vector<double>& T, std::vector<double>& up, std::vector<float>* radii = nullptr) const {
+    const int n = size();
+    T.assign((size_t)n * 3, 0.0); up.assign((size_t)n * 3, 0.0);
+    if (radii) radii->assign((size_t)n, 0.f);
+    for (int i = 0; i < n; ++i) view(i, &T[3 * (size_t)i], &up[3 * (size_t)i], radii ? &(*radii)[(size_t)i] : nullptr);
+  }
+  const lm_view_sphere& c() const { return vs_; }
+
+ private:
+  lm_view_sphere vs_;
+};
+
+inline std::vector<int> Detector::trainViews(const Mesh& mesh, const lm_camera& camera, const std::vector<double>& T,
+                                             const std::vector<double>& up, const std::string& class_id,
+                                             std::vector<Rect>* mask_rects, std::vector<uint16_t>* centre_depth_mm) {
+  need_handle();
+  if (T.size() != up.size() || T.size() % 3 != 0) throw Exception(LM_E_INVALID, "T and up must hold 3 doubles per view");
+  const int n = (int)(T.size() / 3);
+  std::vector<int32_t> ids((size_t)n, -1);
+  std::vector<lm_rect> rects((size_t)n);
+  std::vector<uint16_t> centre((size_t)n);
+  const double zero3[3] = {0, 0, 0};
+  detail::check(lm_train_views(h_, mesh.handle(), &camera, n ? T.data() : zero3, n ? up.data() : zero3, n, class_id.c_str(),
+                               ids.data(), nullptr, rects.data(), centre.data()));
+  cache_.clear();
+  if (mask_rects) {
+    mask_rects->clear();
+    for (int i = 0; i < n; ++i) mask_rects->push_back(Rect(rects[i].x, rects[i].y, rects[i].width, rects[i].height));
+  }
+  if (centre_depth_mm) *centre_depth_mm = centre;
+  return std::vector<int>(ids.begin(), ids.end());
+}
+
+// writeLinemodTemplateParams (src/renderer.cpp:72-123) / readLinemodTemplateParams (src/rgbdDetector.cpp:1681-1749)
+inline void writeRendererParams(const std::string& filename, const std::vector<lm_template_pose>& poses,
+                                const lm_renderer_params& params) {
+  detail::check(lm_write_renderer_params(filename.c_str(), poses.empty() ? nullptr : poses.data(), poses.size(), &params));
+}
+inline void readRendererParams(const std::string& filename, std::vector<lm_template_pose>& poses, lm_renderer_params& params) {
+  lm_template_pose* p = nullptr;
+  size_t n = 0;
+  detail::check(lm_read_renderer_params(filename.c_str(), &p, &n, &params));
+  poses.assign(p, p + n);
+  lm_free_poses(p);
+}
 
 }  // namespace linemod_b200
 

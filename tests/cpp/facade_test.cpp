@@ -3,6 +3,7 @@
 //   facade_test host <tmpdir>   template bookkeeping + persistence, no CUDA device needed
 //   facade_test gpu  <tmpdir>   addTemplate + match on the GPU
 // Prints "ok <mode>" and exits 0 on success.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -87,6 +88,30 @@ static int run_host(const std::string& dir) {
   // Match ordering / equality as std::sort + std::unique see them
   lm::Match m1(1, 2, 95.f, "obj", 7), m2(1, 2, 95.f, "obj", 3), m3(4, 2, 96.f, "obj", 9);
   REQUIRE(m3 < m1 && m2 < m1 && m1 == m2 && !(m1 == m3));
+  // the trainer's view sphere and pose table (src/renderer.cpp:242-246, 72-123): host-only
+  lm::ViewSphere sphere(150, 10, 0.5f, 1.0f, 0.1f);
+  REQUIRE(sphere.size() == 150 * 17 * 6);
+  double T[3], up[3];
+  float radius = 0;
+  sphere.view(3672, T, up, &radius);   // first template of the reference's shipped renderer_params.yml (T = -camera position)
+  REQUIRE(std::fabs(T[0] - 2.0922734402120113e-03) < 1e-12 && std::fabs(T[1] + 2.5666666030883789e-01) < 1e-12 &&
+          std::fabs(T[2] + 4.2908957600593567e-01) < 1e-12 && radius == 0.5f);
+  std::vector<lm_template_pose> poses(2);
+  std::memset(poses.data(), 0, sizeof(lm_template_pose) * 2);
+  for (int k = 0; k < 2; ++k) {
+    REQUIRE(lm_view_pose(T, up, poses[k].R, poses[k].T) == LM_OK);
+    for (int j = 0; j < 3; ++j) poses[k].T[j] = -T[j];
+    poses[k].K[0] = 535.566011f; poses[k].K[2] = 320.f; poses[k].K[4] = 537.168115f; poses[k].K[5] = 240.f; poses[k].K[8] = 1.f;
+    poses[k].D = 0.047 + k; poses[k].ori_dist = radius; poses[k].rect.x = 253; poses[k].rect.width = 134 + k;
+  }
+  REQUIRE(std::fabs(poses[0].R[6] + 4.1845467435124026e-03) < 1e-12 && std::fabs(poses[0].R[0] - 9.7591209808210677e-01) < 1e-12);
+  lm_renderer_params rp = {150, 10, 0.5, 1.0, 0.1, 640, 480, 535.566011, 537.168115, 0.1, 1000.0};
+  lm::writeRendererParams(dir + "/renderer_params.yml", poses, rp);
+  std::vector<lm_template_pose> back;
+  lm_renderer_params rp2;
+  lm::readRendererParams(dir + "/renderer_params.yml", back, rp2);
+  REQUIRE(back.size() == 2 && std::memcmp(back.data(), poses.data(), sizeof(lm_template_pose) * 2) == 0);
+  REQUIRE(rp2.n_points == 150 && rp2.width == 640 && rp2.far_ == 1000.0);
   std::printf("ok host\n");
   return 0;
 }
@@ -151,6 +176,45 @@ static int run_gpu(const std::string& dir) {
   REQUIRE(again.size() == matches.size());
   for (size_t i = 0; i < again.size(); ++i)
     REQUIRE(again[i] == matches[i] && again[i].template_id == matches[i].template_id);
+  // the trainer's loop on a box mesh: every view rendered and added on the GPU, then one rendered view is found again
+  const float hx = 0.06f, hy = 0.04f, hz = 0.03f;
+  const float v[8][3] = {{-hx, -hy, -hz}, {hx, -hy, -hz}, {-hx, hy, -hz}, {hx, hy, -hz}, {-hx, -hy, hz}, {hx, -hy, hz}, {-hx, hy, hz}, {hx, hy, hz}};
+  const int faces[6][4] = {{0, 2, 3, 1}, {4, 5, 7, 6}, {0, 1, 5, 4}, {2, 6, 7, 3}, {0, 4, 6, 2}, {1, 3, 7, 5}};
+  std::vector<float> tris;
+  for (int f = 0; f < 6; ++f) {
+    const int order[6] = {0, 1, 2, 0, 2, 3};
+    for (int k = 0; k < 6; ++k)
+      for (int c = 0; c < 3; ++c) tris.push_back(v[faces[f][order[k]]][c]);
+  }
+  lm::Mesh mesh(tris.data(), 12);
+  REQUIRE(mesh.numTriangles() == 12);
+  lm_camera cam = {640, 480, 535.566011, 537.168115, 0.1, 1000.0};
+  lm::ViewSphere sphere(20, 40, 0.4f, 0.5f, 0.1f);
+  std::vector<double> T, up;
+  sphere.views(T, up);
+  std::shared_ptr<lm::Detector> trained = make_detector();
+  std::vector<lm::Rect> rects;
+  std::vector<uint16_t> centre;
+  std::vector<int> ids = trained->trainViews(mesh, cam, T, up, "box", &rects, &centre);
+  REQUIRE((int)ids.size() == sphere.size() && trained->numTemplates("box") > 100);
+  int pick = -1;
+  for (size_t i = 37; i < ids.size() && pick < 0; ++i)
+    if (ids[i] >= 0) pick = (int)i;
+  REQUIRE(pick >= 0 && rects[pick].width > 40 && centre[pick] > 300 && centre[pick] < 500);
+  std::vector<uint8_t> rb(640 * 480 * 3), rm(640 * 480);
+  std::vector<uint16_t> rd(640 * 480);
+  lm_rect rr;
+  REQUIRE(lm_render_views(trained->handle(), mesh.handle(), &cam, &T[3 * pick], &up[3 * pick], 1, rb.data(), rd.data(), rm.data(), &rr) == LM_OK);
+  REQUIRE(rr.x == rects[pick].x && rr.width == rects[pick].width);
+  std::vector<lm::Image> rframe;
+  rframe.push_back(lm::Image(rb.data(), 480, 640, LM_8UC3));
+  rframe.push_back(lm::Image(rd.data(), 480, 640, LM_16UC1));
+  std::vector<lm::Match> found;
+  trained->match(rframe, 90.f, found);
+  REQUIRE(!found.empty() && found[0].similarity >= 99.f);
+  bool self = false;
+  for (size_t i = 0; i < found.size() && found[i].similarity == found[0].similarity; ++i) self = self || found[i].template_id == ids[pick];
+  REQUIRE(self);
   std::printf("ok gpu (%zu matches, best %.2f at %d,%d)\n", matches.size(), best.similarity, best.x, best.y);
   return 0;
 }
