@@ -214,6 +214,7 @@ struct TrainWs {
   DevBuf src[LM_MAX_MODALITIES], mask;           // per-view source images and masks of a batch, tightly packed
   DevBuf segs, pool, feats;                      // TrainSeg table, candidate key pool, selected features [seg][64]
   DevBuf pb[LM_LANES][LM_MAX_LEVELS];            // DepthNormal scratch per lane and level
+  DevBuf runs[LM_LANES][LM_MAX_LEVELS];          // DepthNormal run tables per lane and level (u16)
   DevBuf scene, diff;                            // lm_depth_diff_batch: scene depth, [n][2] sums / counts
   PinBuf h_rects, h_segs, h_feats, h_stage;
   cudaEvent_t ev[LM_LANES] = {};
@@ -222,7 +223,7 @@ struct TrainWs {
     for (int m = 0; m < LM_MAX_MODALITIES; ++m) src[m].release();
     segs.release(); pool.release(); feats.release(); scene.release(); diff.release();
     for (int i = 0; i < LM_LANES; ++i)
-      for (int l = 0; l < LM_MAX_LEVELS; ++l) pb[i][l].release();
+      for (int l = 0; l < LM_MAX_LEVELS; ++l) { pb[i][l].release(); runs[i][l].release(); }
     h_rects.release(); h_segs.release(); h_feats.release(); h_stage.release();
     for (int i = 0; i < LM_LANES; ++i) if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = nullptr; }
   }
@@ -1590,10 +1591,14 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
     const int li = f % LM_LANES;
     Lane& ln = d->lane[li];
     double t0 = prof ? now() : 0;
-    if (busy[li]) { int rc = finish(li, f - LM_LANES); if (rc != LM_OK) return rc; busy[li] = false; }
-    double t1 = prof ? now() : 0;
+    // The upload of frame f is queued on the lane's stream BEFORE the host waits for the lane's previous frame: stream order
+    // keeps it behind that frame's kernels and download, and the copy engine always has the next frame waiting instead of
+    // idling until the host comes back (the frame's H2D copy is what bounds the end-to-end rate).  The previous frame's
+    // linear memories and result block are untouched until the kernels of frame f are enqueued below.
     int rc = front_from_host(d, ln, sources + (size_t)f * n_sources, n_sources, nullptr, 0, false);  // upload only
     if (rc != LM_OK) return rc;
+    double t1 = prof ? now() : 0;
+    if (busy[li]) { rc = finish(li, f - LM_LANES); if (rc != LM_OK) return rc; busy[li] = false; }
     double t2 = prof ? now() : 0;
     rc = ensure_pack(d, ln);
     if (rc != LM_OK) return rc;
@@ -1606,7 +1611,7 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
     CU(cudaEventRecord(ln.ev[4], ln.stream));
     if (enqueue_download(ln, ln.stream) != LM_OK) return LM_E_CUDA;
     busy[li] = true;
-    if (prof) { double t4 = now(); t_fin += t1 - t0; t_up += t2 - t1; t_plan += t3 - t2; t_enq += t4 - t3; }
+    if (prof) { double t4 = now(); t_up += t1 - t0; t_fin += t2 - t1; t_plan += t3 - t2; t_enq += t4 - t3; }
   }
   if (prof && n_frames)
     fprintf(stderr, "[lm host profile] per frame us: finish %.1f upload %.1f pack/plan %.1f enqueue %.1f\n", t_fin / n_frames,
@@ -2191,7 +2196,9 @@ int train_device_batch(lm_detector* d, int rows, int cols, int n, const void* co
     if (ensure_quant_ws(d, ln, rows, cols) != LM_OK) return LM_E_CUDA;
     ln.lm_ready = false; ln.front_valid = false;
     for (int l = 0; l < L; ++l)
-      if (ws.pb[i][l].ensure((size_t)(rows >> l) * (cols >> l)) != LM_OK) return LM_E_CUDA;
+      if (ws.pb[i][l].ensure((size_t)(rows >> l) * (cols >> l)) != LM_OK ||
+          ws.runs[i][l].ensure((size_t)(rows >> l) * (cols >> l) * 2) != LM_OK)
+        return LM_E_CUDA;
     if (!ws.ev[i]) CU(cudaEventCreateWithFlags(&ws.ev[i], cudaEventDisableTiming));
   }
   // segment table: (view, level, modality); the candidates of a level lie inside the decimated bounding box of the mask
@@ -2252,6 +2259,7 @@ int train_device_batch(lm_detector* d, int rows, int cols, int n, const void* co
         lv.block_begin = blocks;
         blocks += train_blocks(lv.rows, lv.cols);
         tp.pb[l] = ws.pb[li][l].as<uint8_t>();
+        tp.runs[l] = ws.runs[li][l].as<uint16_t>();
       }
       if (md.type == LM_COLOR_GRADIENT) launch_train_cg(tp, blocks, ws.segs.as<TrainSeg>(), ws.pool.as<unsigned long long>(), ln.stream);
       else launch_train_dn(tp, blocks, ws.segs.as<TrainSeg>(), ws.pool.as<unsigned long long>(), ln.stream);

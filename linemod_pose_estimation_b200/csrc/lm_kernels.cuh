@@ -198,6 +198,8 @@ struct TrainSeg {                         // one (view, level, modality) of a tr
   uint32_t per_label[8];                  // device: DepthNormal candidates per bin
   int32_t cols, nf, type, n_sel;          // level width, features wanted, LM_COLOR_GRADIENT / LM_DEPTH_NORMAL; device:
                                           // features selected, -1 = too few candidates, -2 = pool overflow
+  uint32_t flags;                         // device: bit 0 = the eroded normal map holds a value that is not one-hot
+                                          // (injected LUTs only): distances by ring search instead of run tables
 };
 struct TrainLevel {
   const uint8_t* quant;                   // unmasked quantisation of this level
@@ -207,6 +209,7 @@ struct TrainLevel {
 struct TrainViewParams {
   TrainLevel lv[LM_MAX_LEVELS];
   uint8_t* pb[LM_MAX_LEVELS];             // DepthNormal scratch: normal bin where the eroded mask is set, else 0
+  uint16_t* runs[LM_MAX_LEVELS];          // DepthNormal scratch: horizontal distance to the nearest pixel with another value
   const uint8_t* mask0;                   // level-0 object mask
   int extract_threshold[LM_MAX_LEVELS];
   int n_levels, cols0;

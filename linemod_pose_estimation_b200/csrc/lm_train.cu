@@ -14,9 +14,12 @@
 //   k_train_cg       thread per pixel, every level in one grid: ring test (3x3 minimum of the decimated mask, replicated
 //                    border), candidate key = ~f32 bits(magnitude) << 32 | raster << 3 | label, appended with one atomic
 //   k_train_dn_pb    pb = (5x5 minimum of the decimated mask != 0) ? normal : 0, and the eroded area
-//   k_train_dn_dist  chessboard distance of a candidate pixel to the nearest pixel outside its bin's plane by an expanding
-//                    ring search (exact L-infinity distance = what cv::distanceTransform(DIST_C, 3) computes; frames
-//                    without any such pixel take the reference's "far border" value), per-bin candidate counts
+//   k_train_dn_runs  per pixel the horizontal distance to the nearest pixel of its row with another pb value
+//   k_train_dn_dist  chessboard distance of a candidate pixel to the nearest pixel outside its bin's plane (exact
+//                    L-infinity distance = what cv::distanceTransform(DIST_C, 3) computes; frames without any such pixel
+//                    take the reference's "far border" value): min over rows of max(row offset, run-table distance) when
+//                    the map is one-hot (always, with the stock NORMAL_LUT), an expanding ring search otherwise;
+//                    per-bin candidate counts
 //   k_train_dn_keys  score = distance / bin count -> sort key                                  (once per batch)
 //   k_train_sort     block per segment: bitonic sort of the 64-bit keys (shared memory up to 4096 keys, global above).
 //                    The raster index in the low word makes every key unique, so "stable sort by score" is a plain sort
@@ -80,10 +83,39 @@ __global__ void __launch_bounds__(256) k_train_dn_pb(const TrainViewParams P, Tr
 #pragma unroll
       for (int dx = -2; dx <= 2; ++dx) er = min(er, mask_at(P, l, lv.rows, lv.cols, y + dy, x + dx));
     inner = er != 0;
-    P.pb[l][i] = inner ? lv.quant[i] : (uint8_t)0;
+    const uint8_t q = inner ? lv.quant[i] : (uint8_t)0;
+    P.pb[l][i] = q;
+    if (q & (q - 1)) atomicOr(&segs[lv.seg].flags, 1u);  // more than one bit: only with an injected NORMAL_LUT
   }
   const unsigned n = __popc(__ballot_sync(kFull, inner));
   if ((threadIdx.x & 31) == 0 && n) atomicAdd(&segs[lv.seg].area, n);
+}
+
+constexpr int kRunInf = 0xffff;
+
+// Horizontal distance (in pixels, >= 1) from every non-zero pb pixel to the nearest pixel of its row holding another
+// value; a side on which the run of equal values reaches the frame edge has no such pixel (the frame border is not a
+// zero of the plane), kRunInf when that holds on both sides.
+__global__ void __launch_bounds__(256) k_train_dn_runs(const TrainViewParams P) {
+  const int l = level_of_block(P, blockIdx.x);
+  const TrainLevel lv = P.lv[l];
+  const int i = (blockIdx.x - lv.block_begin) * 256 + threadIdx.x;
+  if (i >= lv.rows * lv.cols) return;
+  const uint8_t* __restrict__ pb = P.pb[l];
+  const uint8_t q = pb[i];
+  int h = 0;
+  if (q) {
+    const int cols = lv.cols;
+    const int y = i / cols, x = i - y * cols;
+    const uint8_t* row = pb + (size_t)y * cols;
+    int left = kRunInf, right = kRunInf;
+    for (int c = 1; c <= x; ++c)
+      if (row[x - c] != q) { left = c; break; }
+    for (int c = 1; x + c < cols && c < left; ++c)
+      if (row[x + c] != q) { right = c; break; }
+    h = min(left, right);
+  }
+  P.runs[l][i] = (uint16_t)h;
 }
 
 __global__ void __launch_bounds__(256) k_train_dn_dist(const TrainViewParams P, TrainSeg* __restrict__ segs,
@@ -100,7 +132,26 @@ __global__ void __launch_bounds__(256) k_train_dn_dist(const TrainViewParams P, 
   // exact chessboard distance to the nearest in-frame pixel whose plane value is zero
   const int k_out = max(max(x, y), max(cols - 1 - x, rows - 1 - y));  // beyond this the ring is outside the frame
   int d = 0;
-  for (int k = 1; k <= k_out && !d; ++k) {
+  const bool one_hot_map = (segs[lv.seg].flags & 1u) == 0;
+  if (one_hot_map) {
+    // Every value of the map is zero or one-hot, so "outside bin q's plane" == "another value" and the distance separates:
+    // d = min over rows y' of max(|y' - y|, horizontal distance in row y' from column x to another value), the latter
+    // read from the run table (0 when (y', x) itself holds another value).  O(d) reads instead of the ring search's O(d^2).
+    const uint16_t* __restrict__ runs = P.runs[l];
+    int best = runs[i];
+    for (int k = 1; k < best && (y - k >= 0 || y + k < rows); ++k) {
+      if (y - k >= 0) {
+        const size_t j = (size_t)(y - k) * cols + x;
+        best = min(best, max(k, pb[j] == q ? (int)runs[j] : 0));
+      }
+      if (y + k < rows) {
+        const size_t j = (size_t)(y + k) * cols + x;
+        best = min(best, max(k, pb[j] == q ? (int)runs[j] : 0));
+      }
+    }
+    d = best >= kRunInf ? 0 : best;  // 0: no pixel of another value anywhere -> the "far border" value below
+  }
+  for (int k = 1; k <= k_out && !d && !one_hot_map; ++k) {
     bool zero = false;
     const int y0 = y - k, y1 = y + k, x0 = x - k, x1 = x + k;
     const int xa = max(x0, 0), xb = min(x1, cols - 1);
@@ -264,6 +315,7 @@ void launch_train_cg(const TrainViewParams& p, int total_blocks, TrainSeg* segs,
 }
 void launch_train_dn(const TrainViewParams& p, int total_blocks, TrainSeg* segs, unsigned long long* pool, cudaStream_t s) {
   k_train_dn_pb<<<total_blocks, 256, 0, s>>>(p, segs);
+  k_train_dn_runs<<<total_blocks, 256, 0, s>>>(p);
   k_train_dn_dist<<<total_blocks, 256, 0, s>>>(p, segs, pool);
 }
 void launch_train_finish(TrainSeg* segs, int n_segs, unsigned long long* pool, uint32_t* out_feats, cudaStream_t s) {

@@ -140,6 +140,21 @@ def test_batch_add_template_large_object_and_full_mask():
     _same_templates(det, orc, "obj", "DepthNormal only, full mask")
 
 
+def test_batch_add_template_with_multi_bit_normal_lut():
+    """An injected NORMAL_LUT whose entries are not one-hot (the stock table is): the DepthNormal distance falls back from
+    the run-table separation to the ring search; templates still equal the oracle's."""
+    views = common.rendered_views(16, 181, (240, 240))
+    orc, det = O.OracleDetector(), Detector()
+    lut = orc.normal_lut().copy()
+    lut[lut == 4] = 12     # bins 2 and 3 merged into a two-bit value: such pixels are in two planes and never candidates
+    orc.set_normal_lut(lut)
+    det.set_normal_lut(lut)
+    want = [orc.add_template([b, d], "obj", m)[0] for b, d, m in views]
+    tids, _ = det.addTemplates([([b, d], m) for b, d, m in views], "obj")
+    assert list(tids) == want and max(want) >= 3 and -1 in want
+    _same_templates(det, orc, "obj", "multi-bit LUT")
+
+
 def test_add_templates_batch_argument_errors():
     det = Detector()
     bgr, depth, mask = common.rendered_views(1, 5)[0]

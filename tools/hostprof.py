@@ -1,6 +1,6 @@
 # host-side cost per device-path frame (no GPU wait): time 2000 enqueue calls, sync at the end only
 import sys,time,ctypes as C
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import numpy as np, torch, bench
 from linemod_pose_estimation_b200 import Detector,_capi
 dev=torch.device('cuda',0); torch.cuda.set_device(0)
