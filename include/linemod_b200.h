@@ -306,6 +306,10 @@ int lm_copy_result_block(lm_detector* det, int lane, void* d_dst, size_t bytes, 
 int lm_match_device_stream(lm_detector* det, const void* const* d_sources, int n_frames, int n_sources, int rows, int cols,
                            const lm_query* queries, int n_queries, void* const* streams, int n_streams, void* d_stage,
                            size_t stage_slot_bytes);
+/* Host -> device copies of n images into caller-owned device buffers (tightly packed rows), enqueued on `stream`: how a
+ * sharded caller fills the chunk buffer it broadcasts without one binding call per image.  Page-locked sources are copied
+ * asynchronously (they must stay valid until the stream reaches the copy); pageable ones synchronously. */
+int lm_upload_images(lm_detector* det, const lm_image* images, int n, void* const* d_dst, void* stream);
 int lm_finalize_raw(const lm_detector* det, const lm_raw_match* raw, size_t n_raw, lm_match_rec** out_matches,
                     size_t* out_n);
 /* The same for a whole exchange buffer of a streamed run: blocks + r * rank_stride + f * block_bytes is rank r's staged

@@ -71,7 +71,7 @@ EXPORTS = [
     "lm_last_error", "lm_alloc_pinned", "lm_free_pinned", "lm_device", "lm_pyramid_levels", "lm_get_T",
     "lm_num_modalities", "lm_get_modality", "lm_num_classes", "lm_num_templates", "lm_class_id", "lm_get_templates",
     "lm_add_template", "lm_add_template_from_quantized", "lm_add_synthetic_template", "lm_match", "lm_match_multi", "lm_match_batch", "lm_match_batch_multi", "lm_free_matches",
-    "lm_match_device", "lm_match_device_multi", "lm_match_device_multi_lane", "lm_device_result_region", "lm_copy_result_block", "lm_match_device_stream", "lm_finalize_raw", "lm_finalize_gathered", "lm_set_shard", "lm_set_similarity_lut", "lm_get_similarity_lut",
+    "lm_match_device", "lm_match_device_multi", "lm_match_device_multi_lane", "lm_device_result_region", "lm_copy_result_block", "lm_match_device_stream", "lm_finalize_raw", "lm_finalize_gathered", "lm_upload_images", "lm_set_shard", "lm_set_similarity_lut", "lm_get_similarity_lut",
     "lm_set_normal_lut", "lm_get_normal_lut", "lm_debug_fetch", "lm_build_front", "lm_level_geometry",
     "lm_mesh_create", "lm_mesh_load_stl", "lm_mesh_num_triangles", "lm_mesh_get_triangles", "lm_mesh_destroy", "lm_view_count", "lm_view_params",
     "lm_view_pose", "lm_render_views", "lm_add_templates_batch", "lm_train_views", "lm_depth_diff_batch",
@@ -147,6 +147,7 @@ def lib():
     L.lm_finalize_raw.argtypes = [vp, vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.lm_finalize_gathered.argtypes = [vp, vp, ci, ci, C.c_size_t, C.c_size_t, C.c_uint32, ci, C.POINTER(vp),
                                        C.POINTER(C.c_size_t), vp]
+    L.lm_upload_images.argtypes = [vp, C.POINTER(LmImage), ci, C.POINTER(vp), vp]
     L.lm_set_shard.argtypes = [vp, ci, ci]
     for n in ("lm_set_similarity_lut", "lm_get_similarity_lut", "lm_set_normal_lut", "lm_get_normal_lut"):
         getattr(L, n).argtypes = [vp, vp]

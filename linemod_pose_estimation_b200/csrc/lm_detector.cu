@@ -1732,6 +1732,25 @@ int lm_match_device(lm_detector* d, const void* const* d_sources, int n_sources,
   return lm_match_device_multi(d, d_sources, n_sources, rows, cols, &q, 1, stream, d_records, record_bytes_capacity);
 }
 
+int lm_upload_images(lm_detector* d, const lm_image* images, int n, void* const* d_dst, void* stream) {
+  if (!d || n < 0 || (n > 0 && (!images || !d_dst))) return fail(LM_E_INVALID, "NULL argument");
+  if (set_device(d) != LM_OK) return LM_E_CUDA;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int i = 0; i < n; ++i) {
+    const lm_image& im = images[i];
+    if (!im.data || !d_dst[i]) return fail(LM_E_INVALID, "image %d: NULL data / destination", i);
+    const size_t rb = src_row_bytes(im.type, im.cols);
+    if (is_pinned(im.data)) {
+      if (im.step == rb) CU(cudaMemcpyAsync(d_dst[i], im.data, rb * im.rows, cudaMemcpyHostToDevice, s));
+      else CU(cudaMemcpy2DAsync(d_dst[i], rb, im.data, im.step, rb, im.rows, cudaMemcpyHostToDevice, s));
+    } else {  // pageable: the copy returns once the source has been read
+      CU(cudaStreamSynchronize(s));
+      CU(cudaMemcpy2D(d_dst[i], rb, im.data, im.step, rb, im.rows, cudaMemcpyHostToDevice));
+    }
+  }
+  return LM_OK;
+}
+
 int lm_finalize_raw(const lm_detector* d, const lm_raw_match* raw, size_t n_raw, lm_match_rec** out_matches, size_t* out_n) {
   if (!d || (!raw && n_raw) || !out_matches || !out_n) return fail(LM_E_INVALID, "NULL argument");
   std::vector<lm_raw_match> r(raw, raw + n_raw);

@@ -214,7 +214,7 @@ class ShardedDetector(ShardedMatcher):
                 "key": (rows, cols, kinds, chunk, lanes), "bufs": bufs,
                 "copy": torch.cuda.Stream(device=self.device),
                 "lanes": [torch.cuda.Stream(device=self.device) for _ in range(lanes)],
-                "ready": [torch.cuda.Event() for _ in range(2)], "free": [None, None],
+                "ready": [torch.cuda.Event() for _ in range(2)], "free": [None, None], "keep": [None, None],
             }
             st0 = self._stream_state
             st0["stream_ptrs"] = (C.c_void_p * lanes)(*[s.cuda_stream for s in st0["lanes"]])
@@ -232,13 +232,13 @@ class ShardedDetector(ShardedMatcher):
             with torch.cuda.stream(st["copy"]):
                 if st["free"][b] is not None:
                     st["copy"].wait_event(st["free"][b])      # the matching of chunk c-2 has finished reading this buffer
-                for m, k in enumerate(kinds):
-                    if self.rank == 0:
-                        for j in range(g):
-                            a = host_frames[lo + j][m]
-                            src = torch.from_numpy(a if k == "cg" else a.view(np.int16))
-                            st["bufs"][b][m][j].copy_(src, non_blocking=True)
-                    if self.world > 1:
+                if self.rank == 0:   # the whole chunk's host -> device copies in one library call (lm_upload_images)
+                    imgs, keep = _capi.image_array([host_frames[lo + j][m] for j in range(g) for m in range(len(kinds))])
+                    _capi.check(lib.lm_upload_images(self.det._h, imgs, g * len(kinds), st["ptrs"][b],
+                                                     C.c_void_p(st["copy"].cuda_stream)))
+                    st["keep"][b] = keep   # borrowed host images stay referenced until the buffer is reused
+                if self.world > 1:
+                    for m in range(len(kinds)):
                         dist.broadcast(st["bufs"][b][m][:g].view(torch.uint8), src=0, group=self.group)
                 st["ready"][b].record(st["copy"])
 
