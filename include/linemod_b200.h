@@ -152,7 +152,9 @@ int lm_add_synthetic_template(lm_detector* det, const char* class_id, int n_temp
  * of its tree; this library's rasteriser is specified in oracle/render_oracle.cpp (pinhole camera looking at the object
  * origin, principal point at the image centre as K at renderer.cpp:273, depth in u16 millimetres, mask 255). */
 typedef struct lm_mesh lm_mesh;
-/* triangles: n_triangles x 3 vertices x (x, y, z) f32, object frame, metres (Renderer3d(stl_file), renderer.cpp:239) */
+/* A mesh keeps a device copy of its triangles on the GPU of the detector that used it last: share one lm_mesh between
+ * detectors on the same device freely, but give concurrent callers on different devices their own.
+ * triangles: n_triangles x 3 vertices x (x, y, z) f32, object frame, metres (Renderer3d(stl_file), renderer.cpp:239) */
 int lm_mesh_create(const float* triangles, int n_triangles, lm_mesh** out);
 int lm_mesh_load_stl(const char* path, lm_mesh** out); /* ASCII or binary STL */
 int lm_mesh_num_triangles(const lm_mesh* mesh);
