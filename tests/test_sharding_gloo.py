@@ -83,6 +83,26 @@ def _worker(rank, world, port, capacity, out_dir):
                 assert need == 0
                 common.assert_matches_equal(det.finalize_raw(np.concatenate(raws)),
                                             orc.match([frame[0].numpy(), frame[1].numpy().view(np.uint16)], thr), "slot %d" % slot)
+            # ... and rank 0 finalises the whole gathered chunk in one library call (what match_stream does)
+            import ctypes as C
+
+            from linemod_pose_estimation_b200 import _capi
+            two = [(70.0, []), (60.0, ["b"])]
+            for slot in range(len(thresholds)):
+                sm.stage_block(local_match(frame, two), slot, len(thresholds))
+            recv = np.ascontiguousarray(sm.gather_staged().numpy())
+            n_slots, block_bytes = recv.shape[1], recv.shape[2]
+            outp, offs = C.c_void_p(), (C.c_size_t * (n_slots * 2 + 1))()
+            status = np.zeros(n_slots, np.uint8)
+            _capi.check(_capi.lib().lm_finalize_gathered(det._h, recv.ctypes.data, world, n_slots, block_bytes, n_slots * block_bytes,
+                                                         sm.capacity, 2, C.byref(outp), offs, status.ctypes.data))
+            allm = det._take(outp, offs[n_slots * 2])
+            assert not status.any()
+            for slot in range(n_slots):
+                for q, (thr, ids) in enumerate(two):
+                    common.assert_matches_equal(allm[offs[slot * 2 + q]:offs[slot * 2 + q + 1]],
+                                                orc.match([frame[0].numpy(), frame[1].numpy().view(np.uint16)], thr, class_ids=ids),
+                                                "gathered chunk, slot %d query %d" % (slot, q))
     finally:
         dist.destroy_process_group()
 
