@@ -85,3 +85,23 @@ def test_argument_validation_matches_reference_asserts():
         det.set_similarity_lut(bad)
     with pytest.raises(LinemodError):
         Detector(T=(5, 8, 8, 8, 8))
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="a GPU is present")
+def test_template_generation_fails_loudly_without_gpu():
+    """Rendering / batched addTemplate / depth check need the GPU and say so; the view sphere is host code."""
+    from linemod_pose_estimation_b200 import Mesh, ViewSphere, camera, training
+    from common import synth
+    det = Detector()
+    bgr = np.zeros((480, 640, 3), np.uint8)
+    depth = np.zeros((480, 640), np.uint16)
+    T, up = ViewSphere(4, 80, 0.5, 0.5, 0.1).views()
+    assert len(T) == 4 * 3   # angles -80, 0, 80
+    mesh = Mesh(synth.box_mesh())
+    for call in (lambda: training.render_views(det, mesh, camera(), T, up),
+                 lambda: det.trainViews(mesh, camera(), T, up, "obj"),
+                 lambda: det.addTemplates([([bgr, depth], np.full((480, 640), 255, np.uint8))], "obj"),
+                 lambda: training.depth_diff(det, depth, mesh, camera(), T[:1], up[:1], [0], [0])):
+        with pytest.raises(LinemodError) as e:
+            call()
+        assert e.value.code == _capi.LM_E_CUDA, str(e.value)
