@@ -8,7 +8,6 @@ import ctypes as C
 
 import numpy as np
 
-from . import _capi
 from ._capi import LmCamera, LmRendererParams, LmViewSphere, POSE_DTYPE, check, image, image_array, lib
 
 RECT_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("width", "<i4"), ("height", "<i4")])

@@ -2,7 +2,6 @@
 import os, sys, time
 os.environ["LM_HOST_PROFILE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import bench
 from linemod_pose_estimation_b200 import Detector, _capi
 views = bench.rendered_views(); det = Detector()
