@@ -260,3 +260,26 @@ def test_trainer_tool_writes_the_reference_file_pair(tmp_path):
     assert np.array_equal(mine["ori_dist"], G["ori_dist"]) and np.abs(mine["D"] - G["D"]).max() <= 2.001e-3
     d = np.abs(rr - G["rect"])
     assert d.max() <= 1 and (d.max(axis=1) == 0).mean() >= 0.85
+
+
+def test_train_views_reproduces_the_frozen_fixture():
+    """lm_train_views against tests/golden/train_gear.npz (oracle render + addTemplate, frozen): rectangles, centre depths,
+    template ids and every feature."""
+    import os
+    with np.load(os.path.join(common.GOLDEN, "train_gear.npz")) as z:
+        F = {k: z[k] for k in z.files}
+    det, mesh = Detector(), Mesh(F["triangles"])
+    cam = camera(320, 240, 420.0, 415.0)
+    tids, bbs, rects, centre = det.trainViews(mesh, cam, F["T"], F["up"], "gear", centre_depth=True)
+    assert np.array_equal(tids, F["tid"])
+    assert np.array_equal(np.array([tuple(r) for r in rects], np.int32), F["rect"])
+    assert np.array_equal(centre.astype(np.int32), F["centre_mm"])
+    k = f0 = 0
+    for tid in range(int(F["tid"].max()) + 1):
+        for (w, h, lvl, feats) in det.getTemplates("gear", tid):
+            t, fw, fh, fl, n = F["hdr"][k]
+            assert (t, fw, fh, fl, n) == (tid, w, h, lvl, len(feats)), (tid, k)
+            assert np.array_equal(feats, F["feats"][f0:f0 + n]), (tid, k)
+            k += 1
+            f0 += n
+    assert k == len(F["hdr"]) and f0 == len(F["feats"])

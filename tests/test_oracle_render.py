@@ -211,3 +211,18 @@ def test_pose_table_writer_reproduces_the_shipped_file_byte_for_byte(tmp_path):
     assert fs.getNode("Template 2652").empty() and fs.getNode("renderer_radius_step").real() == 0.1
     with pytest.raises(LinemodError):
         training.read_renderer_params(tmp_path / "missing.yml")
+
+
+def test_training_fixture_is_reproduced_by_the_oracle():
+    """tests/golden/train_gear.npz (made by tests/golden/make_train_golden.py): oracle render + addTemplate of 12 views of a
+    gear mesh, frozen.  Guards the oracle against drift; tests/test_gpu_train.py holds lm_train_views to the same file."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_train_golden", os.path.join(common.GOLDEN, "make_train_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    now = mod.build()
+    with np.load(os.path.join(common.GOLDEN, "train_gear.npz")) as z:
+        assert sorted(z.files) == sorted(now)
+        for k in z.files:
+            assert np.array_equal(z[k], now[k]), k
+        assert (z["tid"] >= 0).sum() >= 10 and len(z["hdr"]) == 4 * (z["tid"] >= 0).sum()
