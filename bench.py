@@ -89,7 +89,9 @@ def workload_config(world, n_templates):
                         "T={5,8}, synthetic 640x480 RGB-D stream; step = 1 frame = 1 front end + 1 matching pass per class",
             "templates_total": n_templates, "templates_per_gpu": n_templates // world, "classes": 2,
             "evals_per_step": n_templates * COARSE_POSITIONS,
-            "frame": "640x480 BGR u8 + depth u16", "parallelism": "templates sharded x%d, frame replicated, survivor blocks all-gathered every %d frames (value) / every frame (e2e)" % (world, GATHER_EVERY),
+            "frame": "640x480 BGR u8 + depth u16", "parallelism": ("single GPU, %d frames in flight on the handle's workspace lanes" % N_INFLIGHT) if world == 1 else
+                           ("templates sharded x%d by canonical index, frame replicated (broadcast from rank 0 on the e2e path), survivor "
+                            "blocks all-gathered every %d frames (value) / once per chunk of frames (e2e)" % (world, GATHER_EVERY)),
             "l2": "pool of %d distinct frames (%.0f MB > 126 MB L2) cycled; linear memories are produced and consumed inside each step" % (FRAME_POOL, FRAME_POOL * 1.536)}
 
 
