@@ -148,8 +148,9 @@ int check_camera(const lm_camera* cam) {
   return LM_OK;
 }
 
-// Enqueues the rasteriser for views [v0, v0 + n) on stream s: images land in d->train.{src of the modality types, mask},
-// rectangles in d->train.rects (x_min, y_min, x_max, y_max per view).  want_* select the targets.
+// Enqueues the rasteriser for n views (T, up: 3 doubles each) on stream s.  The images land in the device buffers given
+// (one tightly packed image per view; a null buffer skips that output), the mask rectangles in d->train.rects as
+// (x_min, y_min, x_max, y_max) per view.
 int render_batch(lm_detector* d, const float* d_tris, int n_tri, const lm_camera& cam, const double* T, const double* up, int n,
                  uint8_t* d_bgr, uint16_t* d_depth, uint8_t* d_mask, cudaStream_t s) {
   TrainWs& ws = d->train;
