@@ -15,8 +15,8 @@
  * calling thread is lm_last_error().  (The reference's OpenCV raises cv::Exception from CV_Assert at the same
  * conditions; the C++ facade include/linemod_b200.hpp rethrows.)
  *
- * Threading: one CUDA stream + workspace per lm_detector.  Calls on one handle must be serialised by the caller;
- * distinct handles are independent.
+ * Threading: CUDA streams + workspaces belong to the lm_detector.  Calls on one handle must be serialised by the caller;
+ * distinct handles are independent (lm_group below drives one handle per GPU from its own threads).
  */
 #ifndef LINEMOD_B200_H_
 #define LINEMOD_B200_H_
@@ -253,9 +253,10 @@ typedef struct {
 int lm_match_multi(lm_detector* det, const lm_image* sources, int n_sources, const lm_query* queries, int n_queries,
                    const lm_image* masks, int n_masks, lm_image_out* quantized_out, lm_match_rec** out_matches,
                    size_t* out_offsets);
-/* The same over a batch of frames (sources[f*n_sources + m]); frames are pipelined over eight internal lanes so that
- * the host->device copy, the kernels and the result download of consecutive frames overlap.  out_offsets receives n_frames+1 prefix offsets
- * into out_matches. */
+/* The same over a batch of frames (sources[f*n_sources + m]).  Frames are processed in chunks of "batch_frames" (option,
+ * default 8): every kernel launch of the path covers a whole chunk, and chunks are pipelined over "batch_lanes" workspace
+ * lanes so that the host->device copies, the kernels and the result download of consecutive chunks overlap.
+ * out_offsets receives n_frames+1 prefix offsets into out_matches. */
 int lm_match_batch(lm_detector* det, const lm_image* sources, int n_frames, int n_sources, float threshold,
                    const char* const* class_ids, int n_ids, lm_match_rec** out_matches, size_t* out_offsets);
 /* Batch + multi-query: every frame answers every query from one front end (a video stream watched by the reference's
@@ -288,23 +289,25 @@ int lm_match_device_multi(lm_detector* det, const void* const* d_sources, int n_
                           const lm_query* queries, int n_queries, void* stream, const void** d_records,
                           size_t* record_bytes_capacity);
 /* The same with an explicit workspace lane (0..7): a handle owns eight independent workspaces + result blocks, so several
- * frames can be in flight on streams of the caller (the kernels of one 640x480 frame do not fill a B200). */
+ * requests can be in flight on streams of the caller. */
 int lm_match_device_multi_lane(lm_detector* det, int lane, const void* const* d_sources, int n_sources, int rows, int cols,
                                const lm_query* queries, int n_queries, void* stream, const void** d_records,
                                size_t* record_bytes_capacity);
-/* The lanes' record blocks are one contiguous device allocation: block of lane i = *base + i * *lane_stride (each a
- * header + records as above; the bytes between blocks are padding).  A sharded caller exchanges the survivors of all
- * frames in flight with one collective over [*base, *base + n_lanes * lane_stride) and no staging copies.  The region
- * moves only when a host-path call has to grow the record capacity ("device_out_cap" option: records per block on the
- * device-resident path, default 2048). */
-int lm_device_result_region(lm_detector* det, const void** base, size_t* lane_stride, int* n_lanes);
-/* Enqueues on `stream` a device-to-device copy of the first `bytes` of lane's record block (header + leading records)
- * to d_dst: how a sharded caller parks the survivors of a frame in its send buffer without leaving the stream. */
+/* The record blocks of a lane's chunk are one device allocation: block of frame f = *base + f * *frame_stride (each a
+ * header + records as above; the bytes between blocks are padding and 16 bytes of kernel statistics).  A sharded caller
+ * can exchange the survivors of a whole chunk with one collective over the region and no staging copies.  The region
+ * moves only when the record capacity has to grow ("device_out_cap" option: records per block on the device-resident
+ * path, default 2048) or a larger chunk is requested. */
+int lm_device_result_region(lm_detector* det, int lane, const void** base, size_t* frame_stride, int* n_frames);
+/* Enqueues on `stream` a device-to-device copy of the first `bytes` of the lane's first record block (header + leading
+ * records) to d_dst: how a sharded caller parks the survivors of a frame in its send buffer without leaving the stream. */
 int lm_copy_result_block(lm_detector* det, int lane, void* d_dst, size_t bytes, void* stream);
-/* A run of device-resident frames in one call: frame f (sources d_sources[f * n_sources + m]) is enqueued on lane
- * f % n_streams and stream streams[f % n_streams]; when d_stage is given, the head of its record block (stage_slot_bytes:
- * header + leading records) is copied to d_stage + f * stage_slot_bytes on the same stream -- the send buffer of the
- * sharded exchange (one collective per run of frames).  Nothing is synchronised. */
+/* A run of device-resident frames in one call (sources d_sources[f * n_sources + m]): the frames are cut into chunks of
+ * "batch_frames"; chunk c -- ONE launch set for all its frames -- is enqueued on lane c % n_streams and stream
+ * streams[c % n_streams]; when d_stage is given, the head of frame f's record block (stage_slot_bytes: header + leading
+ * records) is copied to d_stage + f * stage_slot_bytes on the same stream -- the send buffer of the sharded exchange (one
+ * collective per run of frames).  Nothing is synchronised, nothing is copied: the kernels read the caller's buffers
+ * through a device-resident frame table. */
 int lm_match_device_stream(lm_detector* det, const void* const* d_sources, int n_frames, int n_sources, int rows, int cols,
                            const lm_query* queries, int n_queries, void* const* streams, int n_streams, void* d_stage,
                            size_t stage_slot_bytes);
@@ -387,18 +390,22 @@ int lm_debug_coarse_map(lm_detector* det, const char* class_id, int template_id,
 long lm_debug_presort(lm_detector* det, lm_match_rec* dst /*nullable*/);
 
 /* ------------------------------------------------------------------------------------------------ measurement */
-/* Device time (ms, CUDA events on the detector's stream) of the stages of the LAST lm_match call:
- * [0] H2D, [1] front end, [2] coarse similarity, [3] local refinement, [4] D2H; and kernel launches it made. */
+/* Device time (ms, CUDA events on the detector's stream) of the stages of the LAST lm_match / lm_match_multi call made with
+ * the "timing" option on (plain launches with events between the stages instead of the lane's CUDA graph):
+ * [0] H2D, [1] front end, [2] coarse similarity, [3] local refinement, [4] D2H; and the kernel launches of the last call. */
 int lm_last_timings(const lm_detector* det, float ms[5], int* kernel_launches);
 /* Algorithmic bytes of the last match: [0] B_front [1] B_coarse [2] B_refine [3] B_out,
  * and [4] coarse candidates, [5] template*position evals, [6] the part of B_coarse the coarse kernel actually gathered
  * (exact early termination skips features of tiles in which no position can reach the threshold any more), [7] 0. */
 int lm_last_work(const lm_detector* det, uint64_t out[8]);
-/* Tuning / A-B switches: "coarse_variant" (0 production, 1 byte planes, 2 nibble planes without tile records),
- * "prune" (1 = exact early termination in the coarse kernel, default), "mod_order" (order in which the coarse kernel sums
- * the modalities: 0 = template order, 1 = reversed, 2 = chosen per frame from the front end's spread-bit counters,
- * default; results do not depend on it), "refine_variant", "frontend_variant", "graphs", "timing", "debug_taps",
- * "coarse_grid_limit", "device_out_cap". */
+/* Tuning switches: "batch_frames" (frames per chunk = per launch set on the batched paths, 1..32, default 8),
+ * "batch_lanes" (chunks in flight in lm_match_batch*, default 4), "prune" (1 = exact early termination in the coarse
+ * kernel, default), "mod_order" (order in which the coarse kernel sums the modalities: 0 = template order, 1 = reversed,
+ * 2 = chosen per frame from the front end's spread-bit counters, default; results do not depend on it), "graphs" (replay
+ * a recorded CUDA graph per chunk, default 1), "timing" (per-stage events for lm_last_timings, default 0), "debug_taps",
+ * "coarse_grid_limit", "device_out_cap" (records per frame block on the device-resident paths, default 2048),
+ * "cand_per_frame" (coarse candidates a chunk may produce per frame on the device-resident paths, default 65536; the
+ * host paths grow both by themselves). */
 int lm_set_option(lm_detector* det, const char* key, int value);
 
 #ifdef __cplusplus

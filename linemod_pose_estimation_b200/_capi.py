@@ -132,7 +132,7 @@ def lib():
                                         C.POINTER(C.c_size_t)]
     L.lm_match_device_multi_lane.argtypes = [vp, ci, C.POINTER(vp), ci, ci, ci, C.POINTER(LmQuery), ci, vp, C.POINTER(vp),
                                              C.POINTER(C.c_size_t)]
-    L.lm_device_result_region.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(ci)]
+    L.lm_device_result_region.argtypes = [vp, ci, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(ci)]
     L.lm_copy_result_block.argtypes = [vp, ci, vp, C.c_size_t, vp]
     L.lm_match_device_stream.argtypes = [vp, C.POINTER(vp), ci, ci, ci, ci, C.POINTER(LmQuery), ci, C.POINTER(vp), ci, vp,
                                          C.c_size_t]

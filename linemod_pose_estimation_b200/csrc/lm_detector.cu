@@ -68,33 +68,45 @@ int upload_luts(lm_detector* d) {
 size_t src_row_bytes(int type, int cols) { return type == LM_8UC3 ? (size_t)cols * 3 : (type == LM_16UC1 ? (size_t)cols * 2 : (size_t)cols); }
 int expected_src_type(const lm_modality_desc& m) { return m.type == LM_COLOR_GRADIENT ? LM_8UC3 : LM_16UC1; }
 
-// Buffers needed by quantisation at (rows, cols); no divisibility requirements (addTemplate uses this alone).
-int ensure_quant_ws(lm_detector* d, Lane& ln, int rows, int cols) {
+// Buffers needed by quantisation at (rows, cols) for `frames` frame slots; no divisibility requirements (addTemplate
+// uses this alone).
+int ensure_quant_ws(lm_detector* d, Lane& ln, int rows, int cols, int frames) {
   const int L = d->model.levels(), M = d->model.M();
-  if (ln.rows != rows || ln.cols != cols) { ln.lm_ready = false; ln.front_valid = false; }
-  ln.rows = rows; ln.cols = cols;
+  if (frames < 1 || frames > LM_MAX_BATCH) return lm_fail(LM_E_INVALID, "a chunk holds 1..%d frames", LM_MAX_BATCH);
+  if (ln.rows != rows || ln.cols != cols || ln.frames < frames) { ln.lm_ready = false; ln.front_valid = false; }
+  frames = std::max(frames, ln.rows == rows && ln.cols == cols ? ln.frames : 0);
+  bool grew = false, g = false;
   for (int m = 0; m < M; ++m) {
     const bool cg = d->model.mods[m].type == LM_COLOR_GRADIENT;
-    size_t n0 = (size_t)rows * cols;
-    if (ln.src[m].ensure(src_row_bytes(expected_src_type(d->model.mods[m]), cols) * rows) != LM_OK) return LM_E_CUDA;
-    if (cg) {
-      if (ln.smoothed[m].ensure(n0 * 3) != LM_OK || ln.qunf[m].ensure(n0) != LM_OK) return LM_E_CUDA;
-    } else if (ln.dn_raw[m].ensure(n0) != LM_OK) return LM_E_CUDA;
+    if (ln.src[m].ensure(src_row_bytes(expected_src_type(d->model.mods[m]), cols) * rows, frames, &g) != LM_OK) return LM_E_CUDA;
+    grew = grew || g;
     for (int l = 0; l < L; ++l) {
       size_t n = (size_t)(rows >> l) * (cols >> l);
       if (n == 0) return lm_fail(LM_E_INVALID, "image too small for %d pyramid levels", L);
-      if (cg && l > 0 && ln.bgr[l][m].ensure(n * 3) != LM_OK) return LM_E_CUDA;
-      if (cg && ln.mag[l][m].ensure(n * sizeof(float)) != LM_OK) return LM_E_CUDA;
-      if (ln.quant_raw[l][m].ensure(n) != LM_OK || ln.quantized[l][m].ensure(n) != LM_OK) return LM_E_CUDA;
+      if (cg && l > 0) { if (ln.bgr[l][m].ensure(n * 3, frames, &g) != LM_OK) return LM_E_CUDA; grew = grew || g; }
+      if (cg) { if (ln.mag[l][m].ensure(n * sizeof(float), frames, &g) != LM_OK) return LM_E_CUDA; grew = grew || g; }
+      if (ln.quant_raw[l][m].ensure(n, frames, &g) != LM_OK) return LM_E_CUDA;
+      grew = grew || g;
+      if (ln.quantized[l][m].ensure(n, frames, &g) != LM_OK) return LM_E_CUDA;
+      grew = grew || g;
     }
   }
+  if (grew) ln.drop_graphs();  // recorded launches hold the old addresses
+  ln.rows = rows; ln.cols = cols; ln.frames = frames;
   return LM_OK;
 }
 
+// Does this request need the reference's byte planes of a level (besides the nibble-packed ones the kernels read)?
+static bool level_needs_bytes(const lm_detector* d, const LevelGeom& g) { return d->debug_taps != 0 || !level_nibble_aligned(g); }
+
 // Linear-memory buffers for matching at (rows, cols): enforces the reference's CV_Asserts on the geometry.
-static int ensure_lm_ws(lm_detector* d, Lane& ln, int rows, int cols) {
+static int ensure_lm_ws(lm_detector* d, Lane& ln, int rows, int cols, int frames) {
   const int L = d->model.levels(), M = d->model.M();
-  if (ln.lm_ready && ln.rows == rows && ln.cols == cols && (int)ln.geom.size() == L) return LM_OK;
+  bool bytes_ok = true;
+  if (ln.lm_ready && ln.rows == rows && ln.cols == cols && (int)ln.geom.size() == L)
+    for (int l = 0; l < L; ++l)
+      if (level_needs_bytes(d, ln.geom[l]) && ln.lmem[l].frames < (level_nibble_aligned(ln.geom[l]) ? 1 : ln.frames)) bytes_ok = false;
+  if (ln.lm_ready && ln.rows == rows && ln.cols == cols && (int)ln.geom.size() == L && ln.frames >= frames && bytes_ok) return LM_OK;
   std::vector<LevelGeom> geom(L);
   for (int l = 0; l < L; ++l) {
     LevelGeom& g = geom[l];
@@ -109,17 +121,22 @@ static int ensure_lm_ws(lm_detector* d, Lane& ln, int rows, int cols) {
     g.W = g.cols / g.T; g.H = g.rows / g.T;
     g.plane_stride = plane_stride_of(g.T, g.W, g.H);
   }
-  if (ensure_quant_ws(d, ln, rows, cols) != LM_OK) return LM_E_CUDA;
+  if (ensure_quant_ws(d, ln, rows, cols, frames) != LM_OK) return LM_E_CUDA;
+  frames = ln.frames;
+  // everything that reads or wrote the old planes must be done (callers' streams included) before they move
+  CU(cudaDeviceSynchronize());
+  ln.drop_graphs();
   for (int l = 0; l < L; ++l) {
-    size_t bytes = (size_t)M * 8 * geom[l].plane_stride + kLmSlack;
-    if (ln.lmem[l].ensure(bytes) != LM_OK) return LM_E_CUDA;
-    CU(cudaMemsetAsync(ln.lmem[l].p, 0, ln.lmem[l].cap, ln.stream));  // zero tails (and slack) once per geometry
+    const size_t bytes = (size_t)M * 8 * geom[l].plane_stride + kLmSlack;
+    if (level_needs_bytes(d, geom[l])) {
+      // parity taps look at frame 0 only; unaligned levels are packed from byte planes for every frame
+      if (ln.lmem[l].ensure(bytes, level_nibble_aligned(geom[l]) ? 1 : frames) != LM_OK) return LM_E_CUDA;
+      CU(cudaMemsetAsync(ln.lmem[l].buf.p, 0, ln.lmem[l].bytes(), ln.stream));  // zero tails (and slack) once per geometry
+    }
+    if (ln.lmn[l].ensure(bytes / 2, frames) != LM_OK) return LM_E_CUDA;
+    CU(cudaMemsetAsync(ln.lmn[l].buf.p, 0, ln.lmn[l].bytes(), ln.stream));
   }
-  for (int l = 0; l < L; ++l) {
-    size_t bytes = ((size_t)M * 8 * geom[l].plane_stride + kLmSlack) / 2;
-    if (ln.lmn[l].ensure(bytes) != LM_OK) return LM_E_CUDA;
-    CU(cudaMemsetAsync(ln.lmn[l].p, 0, ln.lmn[l].cap, ln.stream));
-  }
+  CU(cudaStreamSynchronize(ln.stream));
   ln.geom.swap(geom);
   ln.lm_ready = true;
   ln.front_valid = false;
@@ -144,7 +161,8 @@ bool is_pinned(const void* p) {
 }
 
 // Host image -> tightly packed device buffer.  Pinned sources go straight to the copy engine; pageable ones are
-// packed into the lane's pinned staging area first (offset *stage_off, advanced).
+// packed into the lane's pinned staging area first (offset *stage_off, advanced).  The staging area belongs to the lane's
+// current chunk: callers wait for the lane's previous chunk before they upload the next one.
 int upload_image(Lane& ln, const lm_image& im, void* dst, size_t* stage_off) {
   const size_t rb = src_row_bytes(im.type, im.cols);
   const size_t total = rb * im.rows;
@@ -182,71 +200,55 @@ static int check_sources(lm_detector* d, const lm_image* sources, int n_sources,
   return LM_OK;
 }
 
-static int upload_frame(lm_detector* d, Lane& ln, const lm_image* sources, const lm_image* masks, int n_masks) {
+// Host frames (sources[f * M + m]) -> the lane's source slots 0 .. n_frames-1; masks for single-frame requests only.
+static int upload_frames(lm_detector* d, Lane& ln, const lm_image* sources, int n_frames, const lm_image* masks, int n_masks) {
   const int M = d->model.M();
   size_t need = 0;
-  for (int m = 0; m < M; ++m) {
-    need += ((src_row_bytes(sources[m].type, sources[m].cols) * sources[m].rows) + 255) & ~(size_t)255;
-    if (n_masks && masks[m].data) need += (((size_t)masks[m].rows * masks[m].cols) + 255) & ~(size_t)255;
-  }
-  if (ln.stage_in.ensure(need) != LM_OK) return LM_E_CUDA;
+  for (int f = 0; f < n_frames; ++f)
+    for (int m = 0; m < M; ++m) {
+      const lm_image& im = sources[(size_t)f * M + m];
+      if (!is_pinned(im.data)) need += ((src_row_bytes(im.type, im.cols) * im.rows) + 255) & ~(size_t)255;
+    }
+  for (int m = 0; m < M && n_masks; ++m)
+    if (masks[m].data) need += (((size_t)masks[m].rows * masks[m].cols) + 255) & ~(size_t)255;
+  if (need && ln.stage_in.ensure(need) != LM_OK) return LM_E_CUDA;
   size_t off = 0;
+  for (int f = 0; f < n_frames; ++f)
+    for (int m = 0; m < M; ++m) {
+      if (upload_image(ln, sources[(size_t)f * M + m], ln.src[m].as<uint8_t>(f), &off) != LM_OK) return LM_E_CUDA;
+      ln.src_ptr[f][m] = ln.src[m].as<uint8_t>(f);
+    }
   for (int m = 0; m < M; ++m) {
-    if (upload_image(ln, sources[m], ln.src[m].p, &off) != LM_OK) return LM_E_CUDA;
-    ln.src_ptr[m] = ln.src[m].p;
     ln.has_mask[m] = n_masks && masks[m].data;
     if (ln.has_mask[m]) {
       if (ln.mask0[m].ensure((size_t)masks[m].rows * masks[m].cols) != LM_OK) return LM_E_CUDA;
       if (upload_image(ln, masks[m], ln.mask0[m].p, &off) != LM_OK) return LM_E_CUDA;
     }
   }
+  ln.n_frames = n_frames;
   return LM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ front end
-// [OCV] Modality::process + QuantizedPyramid::pyrDown for every level: fills quant_raw[l][m] (and mag[l][m]).
-// Stage-by-stage kernels (lm_frontend.cu): the A/B reference of the fused path, selected by option frontend_variant=1.
-static int run_quantize_staged(lm_detector* d, Lane& ln, cudaStream_t s) {
-  const int L = d->model.levels(), M = d->model.M();
-  for (int m = 0; m < M; ++m) {
-    const lm_modality_desc& md = d->model.mods[m];
-    for (int l = 0; l < L; ++l) {
-      const int rows = ln.rows >> l, cols = ln.cols >> l;
-      if (md.type == LM_COLOR_GRADIENT) {
-        const uint8_t* src = l == 0 ? (const uint8_t*)ln.src_ptr[m] : ln.bgr[l][m].as<uint8_t>();
-        if (l > 0) {
-          const uint8_t* prev = l == 1 ? (const uint8_t*)ln.src_ptr[m] : ln.bgr[l - 1][m].as<uint8_t>();
-          launch_pyrdown_u8c3(prev, ln.rows >> (l - 1), ln.cols >> (l - 1), ln.bgr[l][m].as<uint8_t>(), s);
-          ++ln.launches;
-        }
-        launch_gauss7_u8c3(src, rows, cols, ln.smoothed[m].as<uint8_t>(), s);
-        launch_cg_grad(ln.smoothed[m].as<uint8_t>(), rows, cols, ln.mag[l][m].as<float>(), ln.qunf[m].as<uint8_t>(), s);
-        launch_cg_hysteresis(ln.qunf[m].as<uint8_t>(), ln.mag[l][m].as<float>(), rows, cols,
-                             md.weak_threshold * md.weak_threshold, ln.quant_raw[l][m].as<uint8_t>(), s);
-        ln.launches += 3;
-      } else {
-        if (l == 0) {
-          launch_dn_normals((const uint16_t*)ln.src_ptr[m], rows, cols, md.distance_threshold, md.difference_threshold,
-                            d->d_normal_lut.as<uint8_t>(), ln.dn_raw[m].as<uint8_t>(), s);
-          launch_median5_u8(ln.dn_raw[m].as<uint8_t>(), rows, cols, ln.quant_raw[0][m].as<uint8_t>(), s);
-          ln.launches += 2;
-        } else {
-          launch_nn_half_u8(ln.quant_raw[l - 1][m].as<uint8_t>(), ln.rows >> (l - 1), ln.cols >> (l - 1),
-                            ln.quant_raw[l][m].as<uint8_t>(), s);
-          ++ln.launches;
-        }
-      }
-    }
-  }
+int begin_chunk(lm_detector* d, Lane& ln, int n_frames, int result_blocks, cudaStream_t s) {
+  FrameTable ft;
+  std::memset(&ft, 0, sizeof(ft));
+  ft.n_frames = n_frames;
+  for (int f = 0; f < n_frames; ++f)
+    for (int m = 0; m < d->model.M(); ++m) ft.src[f][m] = ln.src_ptr[f][m];
+  launch_begin_chunk(ft, ln.ctl.as<BatchCtl>(), ln.result.as<uint8_t>(), ln.result.stride, ln.result.buf.p ? result_blocks : 0, s);
+  ln.n_frames = n_frames;
+  ++ln.launches;
   CU(cudaGetLastError());
   return LM_OK;
 }
 
-// Production path (lm_frontend_fused.cu): per ColorGradient modality the pyrDown chain plus ONE launch covering every
-// level, per DepthNormal modality ONE launch.
-int run_quantize(lm_detector* d, Lane& ln, cudaStream_t main_stream) {
-  if (d->frontend_variant == 1) return run_quantize_staged(d, ln, main_stream);
+// [OCV] Modality::process + QuantizedPyramid::pyrDown for every level: fills quant_raw[l][m] (and mag[l][m]) of every
+// frame of the chunk.  Per ColorGradient modality the pyrDown chain plus ONE launch covering every level, per DepthNormal
+// modality ONE launch; the modalities run concurrently on forked streams.
+int run_quantize(lm_detector* d, Lane& ln, int grid_frames, cudaStream_t main_stream) {
   const int L = d->model.levels(), M = d->model.M();
+  const BatchCtl* ctl = ln.ctl.as<BatchCtl>();
   if (M > 1) CU(cudaEventRecord(ln.ev_fork, main_stream));
   for (int m = 0; m < M; ++m) {
     const lm_modality_desc& md = d->model.mods[m];
@@ -255,34 +257,35 @@ int run_quantize(lm_detector* d, Lane& ln, cudaStream_t main_stream) {
     if (md.type == LM_COLOR_GRADIENT) {
       CgParams cp;
       std::memset(&cp, 0, sizeof(cp));
-      cp.n_levels = L;
+      cp.ctl = ctl; cp.n_levels = L; cp.modality = m;
       cp.thr_sq = md.weak_threshold * md.weak_threshold;
       int total = 0;
       for (int l = 0; l < L; ++l) {
         const int rows = ln.rows >> l, cols = ln.cols >> l;
         if (l > 0) {
-          const uint8_t* prev = l == 1 ? (const uint8_t*)ln.src_ptr[m] : ln.bgr[l - 1][m].as<uint8_t>();
-          launch_pyrdown_fast(prev, ln.rows >> (l - 1), ln.cols >> (l - 1), ln.bgr[l][m].as<uint8_t>(), s);
+          launch_pyrdown_fast(ctl, m, l == 1 ? nullptr : ln.bgr[l - 1][m].as<uint8_t>(), l == 1 ? 0 : ln.bgr[l - 1][m].stride,
+                              ln.rows >> (l - 1), ln.cols >> (l - 1), ln.bgr[l][m].as<uint8_t>(), ln.bgr[l][m].stride, grid_frames, s);
           ++ln.launches;
         }
         CgLevel& lv = cp.lv[l];
-        lv.src = l == 0 ? (const uint8_t*)ln.src_ptr[m] : ln.bgr[l][m].as<uint8_t>();
-        lv.mag = ln.mag[l][m].as<float>();
-        lv.quant = ln.quant_raw[l][m].as<uint8_t>();
+        lv.src = l == 0 ? nullptr : ln.bgr[l][m].as<uint8_t>();
+        lv.src_stride = l == 0 ? 0 : ln.bgr[l][m].stride;
+        lv.mag = ln.mag[l][m].as<float>(); lv.mag_stride = ln.mag[l][m].stride_in<float>();
+        lv.quant = ln.quant_raw[l][m].as<uint8_t>(); lv.quant_stride = ln.quant_raw[l][m].stride;
         lv.rows = rows; lv.cols = cols; lv.block_begin = total;
         total += cg_fused_blocks(rows, cols, &lv.blocks_x);
       }
-      launch_cg_fused(cp, total, s);
+      launch_cg_fused(cp, total, grid_frames, s);
       ++ln.launches;
     } else {
       DnParams dp;
       std::memset(&dp, 0, sizeof(dp));
-      dp.depth = (const uint16_t*)ln.src_ptr[m];
+      dp.ctl = ctl; dp.modality = m;
       dp.lut = d->d_normal_lut.as<uint8_t>();
       dp.rows = ln.rows; dp.cols = ln.cols; dp.n_levels = L;
       dp.distance_threshold = md.distance_threshold; dp.difference_threshold = md.difference_threshold;
-      for (int l = 0; l < L; ++l) dp.quant[l] = ln.quant_raw[l][m].as<uint8_t>();
-      launch_dn_fused(dp, s);
+      for (int l = 0; l < L; ++l) { dp.quant[l] = ln.quant_raw[l][m].as<uint8_t>(); dp.quant_stride[l] = ln.quant_raw[l][m].stride; }
+      launch_dn_fused(dp, grid_frames, s);
       ++ln.launches;
     }
     if (m > 0) {
@@ -294,76 +297,58 @@ int run_quantize(lm_detector* d, Lane& ln, cudaStream_t main_stream) {
   return LM_OK;
 }
 
-// The refinement kernel reads nibble planes when every refinement level has word-aligned rows (refine_variant 0), byte
-// planes otherwise.
-static bool refine_nibbles(const lm_detector* d, const Lane& ln) {
-  if (d->refine_variant != 0) return false;
-  for (size_t l = 0; l + 1 < ln.geom.size(); ++l)
-    if (!level_nibble_aligned(ln.geom[l])) return false;
-  return true;
-}
-
-// [OCV] Detector::match front half: quantize (mask) -> spread -> computeResponseMaps -> linearize per level/modality.
-static int run_front(lm_detector* d, Lane& ln, cudaStream_t s) {
+// [OCV] Detector::match front half: quantize (mask) -> spread -> computeResponseMaps -> linearize per level/modality,
+// for grid_frames frame slots of the lane (the frame table's count decides which of them do anything).
+static int run_front(lm_detector* d, Lane& ln, int grid_frames, cudaStream_t s) {
   const int L = d->model.levels(), M = d->model.M();
-  CU(cudaMemsetAsync(ln.mod_bits.p, 0, sizeof(unsigned int) * LM_MAX_MODALITIES, s));
-  if (run_quantize(d, ln, s) != LM_OK) return LM_E_CUDA;
+  if (run_quantize(d, ln, grid_frames, s) != LM_OK) return LM_E_CUDA;
   const bool taps = d->debug_taps != 0;
   if (taps && ensure_tap_ws(d, ln) != LM_OK) return LM_E_CUDA;
-  // which planes this front end produces per level (staged A/B path: byte planes everywhere, nibbles packed from them)
-  bool nib[LM_MAX_LEVELS] = {false, false, false, false}, byt[LM_MAX_LEVELS] = {true, true, true, true};
-  if (d->frontend_variant == 1) {
-    for (int l = 0; l < L; ++l) {
-      const LevelGeom& g = ln.geom[l];
-      for (int m = 0; m < M; ++m) {
-        launch_spread_lm(ln.quant_raw[l][m].as<uint8_t>(), ln.has_mask[m] ? ln.mask0[m].as<uint8_t>() : nullptr, ln.cols, l,
-                         g.rows, g.cols, g.T, d->d_resp_all.as<uint32_t>(), ln.quantized[l][m].as<uint8_t>(),
-                         taps ? ln.spread[l][m].as<uint8_t>() : nullptr, taps ? ln.response[l][m].as<uint8_t>() : nullptr,
-                         ln.lmem[l].as<uint8_t>() + (size_t)m * 8 * g.plane_stride, g.plane_stride, s);
-        ++ln.launches;
-      }
-    }
-  } else {
-    SpreadParams sp;
-    std::memset(&sp, 0, sizeof(sp));
-    sp.resp_all = d->d_resp_all.as<uint32_t>();
-    int total = 0, max_T = 1;
-    for (int l = 0; l < L; ++l) {
-      const LevelGeom& g = ln.geom[l];
-      max_T = std::max(max_T, g.T);
-      // nibble planes are written directly when every (orientation, phase) row starts on a word; the byte planes only
-      // when something reads them: parity taps, the byte A/B kernels, or a level whose rows are not word-aligned
-      nib[l] = l == L - 1 ? level_nibble_aligned(g) : refine_nibbles(d, ln);
-      byt[l] = taps || !nib[l] || (l == L - 1 && d->coarse_variant == 1);
-      for (int m = 0; m < M; ++m) {
-        SpreadEntry& e = sp.e[sp.n++];
-        e.qraw = ln.quant_raw[l][m].as<uint8_t>();
-        e.mask0 = ln.has_mask[m] ? ln.mask0[m].as<uint8_t>() : nullptr;
-        e.quantized = ln.quantized[l][m].as<uint8_t>();
-        e.spread = taps ? ln.spread[l][m].as<uint8_t>() : nullptr;
-        e.response = taps ? ln.response[l][m].as<uint8_t>() : nullptr;
-        e.lm = byt[l] ? ln.lmem[l].as<uint8_t>() + (size_t)m * 8 * g.plane_stride : nullptr;
-        e.lm_nib = nib[l] ? ln.lmn[l].as<uint8_t>() + (size_t)m * 4 * g.plane_stride : nullptr;
-        e.bits = l == L - 1 ? ln.mod_bits.as<unsigned int>() + m : nullptr;
-        e.plane_stride = g.plane_stride;
-        e.rows = g.rows; e.cols = g.cols; e.T = g.T; e.W = g.W; e.H = g.H; e.level = l; e.mask_cols0 = ln.cols;
-        e.block_begin = total;
-        total += spread_all_blocks(g.W, g.H, &e.blocks_x);
-      }
-    }
-    if (!launch_spread_all(sp, total, max_T, s)) return lm_fail(LM_E_INVALID, "T=%d needs too much shared memory", max_T);
-    ++ln.launches;
-  }
+  SpreadParams sp;
+  std::memset(&sp, 0, sizeof(sp));
+  sp.resp_all = d->d_resp_all.as<uint32_t>();
+  sp.ctl = ln.ctl.as<BatchCtl>();
+  int total = 0, max_T = 1;
+  bool direct[LM_MAX_LEVELS] = {false, false, false, false}, byt[LM_MAX_LEVELS] = {false, false, false, false};
   for (int l = 0; l < L; ++l) {
-    // nibble planes the matching kernels will read but the spread kernel could not write directly: pack the byte planes
-    const bool wanted = l == L - 1 ? d->coarse_variant != 1 : refine_nibbles(d, ln);
-    if (wanted && !nib[l]) {
-      launch_pack_nibbles(ln.lmem[l].as<uint8_t>(), ln.lmn[l].as<uint8_t>(), (size_t)M * 8 * ln.geom[l].plane_stride, s);
+    const LevelGeom& g = ln.geom[l];
+    max_T = std::max(max_T, g.T);
+    // nibble planes are written directly when every (orientation, phase) row starts on a word; otherwise the byte planes
+    // are written and packed.  The byte planes are also written for the parity taps (frame 0 of the chunk only then).
+    direct[l] = level_nibble_aligned(g);
+    byt[l] = taps || !direct[l];
+    for (int m = 0; m < M; ++m) {
+      SpreadEntry& e = sp.e[sp.n++];
+      e.qraw = ln.quant_raw[l][m].as<uint8_t>(); e.qraw_stride = ln.quant_raw[l][m].stride;
+      e.mask0 = ln.has_mask[m] ? ln.mask0[m].as<uint8_t>() : nullptr;
+      e.quantized = ln.quantized[l][m].as<uint8_t>(); e.quantized_stride = ln.quantized[l][m].stride;
+      e.spread = taps ? ln.spread[l][m].as<uint8_t>() : nullptr;
+      e.response = taps ? ln.response[l][m].as<uint8_t>() : nullptr;
+      e.lm = byt[l] ? ln.lmem[l].as<uint8_t>() + (size_t)m * 8 * g.plane_stride : nullptr;
+      e.lm_stride = ln.lmem[l].frames > 1 ? ln.lmem[l].stride : 0;
+      e.lm_nib = direct[l] ? ln.lmn[l].as<uint8_t>() + (size_t)m * 4 * g.plane_stride : nullptr;
+      e.lm_nib_stride = ln.lmn[l].stride;
+      e.count_bits = l == L - 1;
+      e.plane_stride = g.plane_stride;
+      e.rows = g.rows; e.cols = g.cols; e.T = g.T; e.W = g.W; e.H = g.H; e.level = l; e.modality = m; e.mask_cols0 = ln.cols;
+      e.block_begin = total;
+      total += spread_all_blocks(g.W, g.H, &e.blocks_x);
+    }
+  }
+  // byte planes that hold one frame only (taps on an aligned level) can be written by a single-frame launch only
+  for (int l = 0; l < L; ++l)
+    if (byt[l] && ln.lmem[l].frames < grid_frames && grid_frames > 1)
+      return lm_fail(LM_E_STATE, "parity taps are available for single-frame requests only");
+  if (!launch_spread_all(sp, total, max_T, grid_frames, s)) return lm_fail(LM_E_INVALID, "T=%d needs too much shared memory", max_T);
+  ++ln.launches;
+  for (int l = 0; l < L; ++l) {
+    if (!direct[l]) {
+      launch_pack_nibbles(ln.lmem[l].as<uint8_t>(), ln.lmem[l].stride, ln.lmn[l].as<uint8_t>(), ln.lmn[l].stride,
+                          (size_t)M * 8 * ln.geom[l].plane_stride, ln.ctl.as<BatchCtl>(), grid_frames, s);
       ++ln.launches;
-      nib[l] = true;
     }
     ln.bytes_valid[l] = byt[l];
-    ln.nibbles_valid[l] = nib[l];
+    ln.nibbles_valid[l] = true;
   }
   CU(cudaGetLastError());
   ln.front_valid = true;
@@ -376,7 +361,7 @@ static int ensure_pack(lm_detector* d, const Lane& ln) {
   Pack& pk = d->pack;
   const HostModel& md = d->model;
   if (pk.version == md.version && pk.rows == ln.rows && pk.cols == ln.cols && pk.shard_rank == d->shard_rank &&
-      pk.shard_world == d->shard_world && pk.variant == d->coarse_variant)
+      pk.shard_world == d->shard_world)
     return LM_OK;
   // all lanes must be idle before the shared records are replaced
   for (int i = 0; i < LM_LANES; ++i)
@@ -424,9 +409,9 @@ static int ensure_pack(lm_detector* d, const Lane& ln) {
           if (f.x < 0 || f.x >= gc.cols || f.y < 0 || f.y >= gc.rows) continue;  // "Discard feature if out of bounds"
           size_t a = (size_t)m * 8 * gc.plane_stride + (size_t)f.label * gc.plane_stride +
                      (size_t)((f.y % gc.T) * gc.T + (f.x % gc.T)) * ((size_t)gc.W * gc.H) + (size_t)(f.y / gc.T) * gc.W + f.x / gc.T;
-          // window-alignment class of the feature (a compile-time constant in the kernels): byte planes -> word
-          // offset in the 16-byte chunk; nibble planes -> the same with a = nibble index
-          const int q = d->coarse_variant == 1 ? (int)((a & 15) >> 2) : (int)((a >> 3) & 3);
+          // window-alignment class of the feature (a compile-time constant in the kernel): word offset of the window in
+          // its 16-byte chunk of the nibble-packed plane, a = nibble index
+          const int q = (int)((a >> 3) & 3);
           grp[q].push_back((uint32_t)a);
         }
         for (int q = 0; q < 4; ++q) {
@@ -468,9 +453,7 @@ static int ensure_pack(lm_detector* d, const Lane& ln) {
     if (bytes) CU(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
     return LM_OK;
   };
-  foff.resize(foff.size() + 8, 0);  // the 4-way unrolled loop never reads past the template, padding is for safety
   if (up(pk.ctpl, ctpl.data(), ctpl.size() * sizeof(CoarseTpl)) != LM_OK) return LM_E_CUDA;
-  if (up(pk.foff, foff.data(), foff.size() * 4) != LM_OK) return LM_E_CUDA;
   for (int l = 0; l < L - 1; ++l) {
     if (up(pk.rtpl[l], rtpl[l].data(), rtpl[l].size() * sizeof(RefineTpl)) != LM_OK) return LM_E_CUDA;
     if (up(pk.rfeats[l], rfeats[l].data(), rfeats[l].size() * 4) != LM_OK) return LM_E_CUDA;
@@ -478,7 +461,7 @@ static int ensure_pack(lm_detector* d, const Lane& ln) {
   pk.h_ctpl.swap(ctpl);
   pk.h_foff.swap(foff);
   pk.version = md.version; pk.rows = ln.rows; pk.cols = ln.cols;
-  pk.shard_rank = d->shard_rank; pk.shard_world = d->shard_world; pk.variant = d->coarse_variant;
+  pk.shard_rank = d->shard_rank; pk.shard_world = d->shard_world;
   return LM_OK;
 }
 
@@ -489,7 +472,6 @@ struct Query {
   int n_ids;
 };
 
-static const size_t kFirstChunkRecords = 1024;  // records fetched together with the header in one D2H copy
 static const int kMaxQueries = LM_MAX_QUERIES;  // (class list, threshold) queries answered from one front end
 
 // Self-contained tile records of the production coarse kernel (layout: lm_kernels.cuh).
@@ -549,7 +531,7 @@ static int get_plan(lm_detector* d, const Query* qs, int n_q, Pack::Plan** out) 
   struct Tile { uint2 t; uint64_t cost; };
   std::vector<Tile> tiles;
   Pack::Plan plan;
-  const int pass_pos = coarse_positions_per_pass(d->coarse_variant);
+  const int pass_pos = coarse_positions_per_pass();
   auto add_class = [&](const Pack::ClassRange& cr, uint32_t base, uint32_t first_global, int q) {
     for (size_t k = 0; k < cr.local.size(); ++k) {
       const uint32_t local = cr.local[k];
@@ -594,147 +576,155 @@ static int get_plan(lm_detector* d, const Query* qs, int n_q, Pack::Plan** out) 
   plan.n_tiles = (int)tl.size();
   plan.evals = (uint64_t)items.size();
   std::vector<uint32_t> recs;
-  if (d->coarse_variant == 0) {
-    if (build_tile_records(pk, items, tl, pass_pos, d->model.M(), recs, &plan.rec_words) != LM_OK) return LM_E_INVALID;
-  }
+  if (build_tile_records(pk, items, tl, pass_pos, d->model.M(), recs, &plan.rec_words) != LM_OK) return LM_E_INVALID;
   Pack::Plan& dst = pk.plans[key];
   dst = plan;
-  if (!recs.empty()) {
-    if (dst.recs.ensure(recs.size() * 4 + 64) != LM_OK) return LM_E_CUDA;
-    CU(cudaMemcpy(dst.recs.p, recs.data(), recs.size() * 4, cudaMemcpyHostToDevice));
-  }
-  if (dst.items.ensure(items.size() * sizeof(WorkItem) + 64) != LM_OK || dst.tiles.ensure(tl.size() * sizeof(uint2) + 64) != LM_OK) return LM_E_CUDA;
-  if (!items.empty()) CU(cudaMemcpy(dst.items.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
-  if (!tl.empty()) CU(cudaMemcpy(dst.tiles.p, tl.data(), tl.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+  if (dst.recs.ensure(recs.size() * 4 + 64) != LM_OK) return LM_E_CUDA;
+  if (!recs.empty()) CU(cudaMemcpy(dst.recs.p, recs.data(), recs.size() * 4, cudaMemcpyHostToDevice));
   *out = &dst;
   return LM_OK;
 }
 
-// Device pointer of the plan's tile records (variant 0) or null.
-static const uint32_t* plan_recs(const Pack::Plan& plan) { return plan.recs.as<uint32_t>(); }
-
-// Result block in device memory: [16 B kernel statistics][ResultHeader][out_cap x lm_raw_match].  The statistics
-// (u64 (feature, position) pairs the coarse kernel gathered) sit in front so that one memset clears both and one D2H
-// copy brings both; the public block (lm_match_device) starts at the header.
+// Result block of a frame in device memory: [16 B kernel statistics][ResultHeader][out_cap x lm_raw_match].  The
+// statistics (u64 (feature, position) pairs the coarse kernel gathered for the whole chunk, in frame 0's block) sit in
+// front so that k_begin_chunk clears both and one D2H copy brings both; the public block (lm_match_device) starts at the
+// header.  The blocks of a lane's frames are ln.result.stride apart.
 static const size_t kStatsBytes = 16;
 static size_t result_bytes(const Lane& ln) { return sizeof(ResultHeader) + (size_t)ln.out_cap * sizeof(lm_raw_match); }
-static uint8_t* block_ptr(const Lane& ln) { return ln.result.as<uint8_t>() + kStatsBytes; }
+static uint8_t* block_ptr(const Lane& ln, int frame = 0) { return ln.result.as<uint8_t>(frame) + kStatsBytes; }
+static const size_t kFirstChunkRecords = 256;  // records fetched together with the header in one D2H copy
+static size_t head_bytes(const Lane& ln) {
+  return (kStatsBytes + sizeof(ResultHeader) + std::min<size_t>(kFirstChunkRecords, ln.out_cap) * sizeof(lm_raw_match) + 255) & ~(size_t)255;
+}
 
-static int ensure_match_buffers(lm_detector* d, Lane& ln, uint32_t cand_cap, uint32_t out_cap) {
+static int ensure_match_buffers(lm_detector* d, Lane& ln, uint32_t cand_cap, uint32_t out_cap, int frames) {
   if (cand_cap > ln.cand_cap) {
+    CU(cudaDeviceSynchronize());  // a previous chunk (possibly on a caller's stream) may still read the list
     if (ln.cand.ensure((size_t)cand_cap * sizeof(Cand)) != LM_OK) return LM_E_CUDA;
     ln.cand_cap = cand_cap;
+    ln.drop_graphs();
   }
-  if (out_cap > d->out_cap || d->results_all.p == nullptr) {
-    // every lane's block moves: nothing may be in flight (callers' streams included); blocks whose results have not
-    // been downloaded yet (other lanes of a batch) keep their contents
+  out_cap = std::max(out_cap, ln.out_cap);
+  if (out_cap > ln.out_cap || ln.result.frames < frames) {
     CU(cudaDeviceSynchronize());
-    const size_t old_stride = d->result_stride;
-    DevBuf old = d->results_all;
-    d->results_all = DevBuf();
-    d->out_cap = std::max(out_cap, d->out_cap);
-    d->result_stride = (kStatsBytes + sizeof(ResultHeader) + (size_t)d->out_cap * sizeof(lm_raw_match) + 255) & ~(size_t)255;
-    if (d->results_all.ensure(d->result_stride * LM_LANES) != LM_OK) { d->results_all = old; return LM_E_CUDA; }
-    CU(cudaMemset(d->results_all.p, 0, d->results_all.cap));
-    for (int i = 0; i < LM_LANES; ++i) {
-      uint8_t* fresh = d->results_all.as<uint8_t>() + (size_t)i * d->result_stride;
-      if (old.p) CU(cudaMemcpy(fresh, old.as<uint8_t>() + (size_t)i * old_stride, std::min(old_stride, d->result_stride), cudaMemcpyDeviceToDevice));
-      d->lane[i].result.p = fresh;
-      d->lane[i].out_cap = d->out_cap;
-    }
-    old.release();
+    bool grew = false;
+    if (ln.result.ensure(kStatsBytes + sizeof(ResultHeader) + (size_t)out_cap * sizeof(lm_raw_match), frames, &grew) != LM_OK) return LM_E_CUDA;
+    ln.out_cap = out_cap;
+    CU(cudaMemset(ln.result.buf.p, 0, ln.result.bytes()));
+    ln.drop_graphs();
   }
-  if (ln.stage_out.ensure(kStatsBytes + result_bytes(ln)) != LM_OK) return LM_E_CUDA;
+  if (ln.stage_out.ensure(std::max(head_bytes(ln) * (size_t)ln.result.frames, kStatsBytes + result_bytes(ln))) != LM_OK) return LM_E_CUDA;
   return LM_OK;
 }
 
-// Enqueues the request's coarse similarity + refinement on stream s: one launch each, whatever the number of queries.
-static int enqueue_match(lm_detector* d, Lane& ln, const Pack::Plan& plan, const Query* qs, int n_q, cudaStream_t s,
-                         cudaEvent_t ev_mid) {
+// Enqueues the chunk's coarse similarity + refinement on stream s: one launch each, whatever the number of frames and
+// queries.
+static int enqueue_match(lm_detector* d, Lane& ln, const Pack::Plan& plan, const Query* qs, int n_q, int grid_frames,
+                         cudaStream_t s, cudaEvent_t ev_mid) {
   const HostModel& md = d->model;
   const int L = md.levels(), M = md.M();
   Pack& pk = d->pack;
   const LevelGeom& gc = ln.geom[L - 1];
-  ResultHeader* d_hdr = reinterpret_cast<ResultHeader*>(block_ptr(ln));
-  lm_raw_match* d_out = reinterpret_cast<lm_raw_match*>(block_ptr(ln) + sizeof(ResultHeader));
-  CU(cudaMemsetAsync(ln.result.p, 0, kStatsBytes + sizeof(ResultHeader), s));
-  QueryThresholds qt;
+  CoarseParams cp;
   RefineParams rp;
   std::memset(&rp, 0, sizeof(rp));
-  std::memset(&qt, 0, sizeof(qt));
-  for (int q = 0; q < n_q; ++q) { qt.v[q] = qs[q].threshold; rp.threshold[q] = qs[q].threshold; }
-  launch_similarity_coarse(d->coarse_variant, ln.lmem[L - 1].as<uint8_t>(), ln.lmn[d->model.levels() - 1].as<uint8_t>(), pk.foff.as<uint32_t>(),
-                           pk.ctpl.as<CoarseTpl>(), plan.items.as<WorkItem>(), plan.tiles.as<uint2>(), plan_recs(plan), plan.rec_words,
-                           plan.n_tiles, qt, M, (d->prune & 1) | (d->mod_order << 8), ln.cand.as<Cand>(), d_hdr,
-                           ln.result.as<unsigned long long>(), ln.cand_cap, nullptr, 0, s,
-                           d->frontend_variant == 0 ? ln.mod_bits.as<unsigned int>() : nullptr);
+  std::memset(&cp, 0, sizeof(cp));
+  for (int q = 0; q < n_q; ++q) { cp.thr.v[q] = qs[q].threshold; rp.threshold[q] = qs[q].threshold; }
+  cp.lmn = ln.lmn[L - 1].as<uint8_t>(); cp.lmn_stride = ln.lmn[L - 1].stride;
+  cp.recs = plan.recs.as<uint32_t>(); cp.rec_words = plan.rec_words; cp.n_tiles = plan.n_tiles;
+  cp.ctl = ln.ctl.as<BatchCtl>();
+  cp.cand = ln.cand.as<Cand>(); cp.cand_cap = ln.cand_cap;
+  cp.touched = ln.result.as<unsigned long long>();
+  cp.M = M; cp.prune = (d->prune & 1) | (d->mod_order << 8);
+  launch_similarity_coarse(cp, grid_frames, s);
   if (plan.n_tiles > 0) ++ln.launches;
   if (ev_mid) CU(cudaEventRecord(ev_mid, s));
   rp.levels = L; rp.M = M; rp.coarse_T = gc.T; rp.coarse_W = gc.W;
   for (int l = 0; l < L - 1; ++l) {
     const LevelGeom& g = ln.geom[l];
-    rp.level[l].lm = ln.lmem[l].as<uint8_t>();
     rp.level[l].lmn = ln.lmn[l].as<uint8_t>();
+    rp.level[l].frame_stride = ln.lmn[l].stride;
     rp.level[l].tpl = pk.rtpl[l].as<RefineTpl>();
     rp.level[l].feats = pk.rfeats[l].as<uint32_t>();
     rp.level[l].plane_stride = g.plane_stride;
     rp.level[l].rows = g.rows; rp.level[l].cols = g.cols; rp.level[l].T = g.T; rp.level[l].W = g.W;
   }
-  launch_refine(refine_nibbles(d, ln), rp, pk.ctpl.as<CoarseTpl>(), plan.items.as<WorkItem>(), ln.cand.as<Cand>(), ln.cand_cap,
-                d_hdr, d_out, ln.out_cap, s);
+  launch_refine(rp, pk.ctpl.as<CoarseTpl>(), ln.cand.as<Cand>(), ln.cand_cap, ln.ctl.as<BatchCtl>(), ln.result.as<uint8_t>(),
+                ln.result.stride, ln.out_cap, s);
   ++ln.launches;
   CU(cudaGetLastError());
   return LM_OK;
 }
 
-// Front end + matching of one frame whose sources are already in device memory (ln.src_ptr), enqueued on s.  Replays
-// the lane's CUDA graph when one matching this request exists, records a new one otherwise; falls back to plain
-// launches when graphs are switched off, the parity taps are on, or a capture ever failed on this lane.
-static int enqueue_frame(lm_detector* d, Lane& ln, const Pack::Plan& plan, const Query* qs, int n_q, cudaStream_t s) {
+static int graph_slot_of(int n_frames, int* grid_frames) {
+  int slot = 0, g = 1;
+  while (g < n_frames) { g <<= 1; ++slot; }
+  *grid_frames = g;
+  return slot;
+}
+
+// Front end + matching of the lane's current chunk (ln.src_ptr[0 .. n_frames), already in device memory), enqueued on s:
+// k_begin_chunk, then the lane's CUDA graph for this launch geometry (recorded on first use), or plain launches when
+// graphs are switched off, the parity taps or per-stage timing are on, masks are used, or a capture ever failed here.
+static int enqueue_chunk(lm_detector* d, Lane& ln, const Pack::Plan& plan, const Query* qs, int n_q, int n_frames, cudaStream_t s,
+                         bool stage_events = false) {
   bool masks = false;
   for (int m = 0; m < d->model.M(); ++m) masks = masks || ln.has_mask[m];
-  if (!d->graphs || ln.graph_broken || d->debug_taps || masks) {
-    if (run_front(d, ln, s) != LM_OK) return LM_E_CUDA;
-    return enqueue_match(d, ln, plan, qs, n_q, s, nullptr);
+  int grid_frames = 1;
+  const int slot = graph_slot_of(n_frames, &grid_frames);
+  grid_frames = std::min(grid_frames, ln.frames);
+  ln.launches = 0;
+  if (begin_chunk(d, ln, n_frames, n_frames, s) != LM_OK) return LM_E_CUDA;
+  if (!d->graphs || ln.graph_broken || d->debug_taps || masks || stage_events || slot >= LM_GRAPH_SLOTS) {
+    if (stage_events) CU(cudaEventRecord(ln.ev[1], s));
+    if (run_front(d, ln, n_frames, s) != LM_OK) return LM_E_CUDA;
+    if (stage_events) CU(cudaEventRecord(ln.ev[2], s));
+    if (enqueue_match(d, ln, plan, qs, n_q, n_frames, s, stage_events ? ln.ev[3] : nullptr) != LM_OK) return LM_E_CUDA;
+    if (stage_events) CU(cudaEventRecord(ln.ev[4], s));
+    return LM_OK;
   }
+  Lane::GraphSlot& gs = ln.graph[slot];
   Lane::GraphKey key;
   std::memset(&key, 0, sizeof(key));
-  key.plan = &plan; key.plan_recs = plan.recs.p; key.n_tiles = plan.n_tiles; key.cand = ln.cand.p; key.result = ln.result.p;
+  key.plan = &plan; key.plan_recs = plan.recs.p; key.n_tiles = plan.n_tiles; key.cand = ln.cand.p; key.result = ln.result.buf.p;
+  key.lmn0 = ln.lmn[0].buf.p; key.ctl = ln.ctl.p; key.ws_frames = ln.frames;
   key.shard_rank = d->shard_rank; key.shard_world = d->shard_world;
-  for (int m = 0; m < d->model.M(); ++m) key.src[m] = ln.src_ptr[m];
   key.model_version = d->model.version; key.rows = ln.rows; key.cols = ln.cols; key.n_q = n_q;
-  key.variant = d->coarse_variant + 16 * d->refine_variant; key.prune = d->prune | (d->mod_order << 8); key.frontend = d->frontend_variant;
+  key.prune = d->prune | (d->mod_order << 8);
   key.cand_cap = ln.cand_cap; key.out_cap = ln.out_cap;
   for (int q = 0; q < n_q; ++q) key.thr[q] = qs[q].threshold;
-  if (ln.gexec == nullptr || std::memcmp(&key, &ln.gkey, sizeof(key)) != 0) {
-    if (ln.gexec) { cudaGraphExecDestroy(ln.gexec); ln.gexec = nullptr; }
+  if (gs.exec == nullptr || std::memcmp(&key, &gs.key, sizeof(key)) != 0) {
+    if (gs.exec) { cudaGraphExecDestroy(gs.exec); gs.exec = nullptr; }
     cudaGraph_t graph = nullptr;
     set_programmatic_launch(false);
+    const int launches_before = ln.launches;
     cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed);
     int rc = LM_OK;
     if (e == cudaSuccess) {
-      ln.launches = 0;
-      rc = run_front(d, ln, s);
-      if (rc == LM_OK) rc = enqueue_match(d, ln, plan, qs, n_q, s, nullptr);
+      rc = run_front(d, ln, grid_frames, s);
+      if (rc == LM_OK) rc = enqueue_match(d, ln, plan, qs, n_q, grid_frames, s, nullptr);
       e = cudaStreamEndCapture(s, &graph);
     }
     set_programmatic_launch(true);
-    if (e == cudaSuccess && rc == LM_OK && graph != nullptr) e = cudaGraphInstantiate(&ln.gexec, graph, 0);
+    if (e == cudaSuccess && rc == LM_OK && graph != nullptr) e = cudaGraphInstantiate(&gs.exec, graph, 0);
     if (graph) cudaGraphDestroy(graph);
-    if (e != cudaSuccess || rc != LM_OK || ln.gexec == nullptr) {  // not fatal: this lane keeps to plain launches
+    if (e != cudaSuccess || rc != LM_OK || gs.exec == nullptr) {  // not fatal: this lane keeps to plain launches
       cudaGetLastError();
-      ln.gexec = nullptr;
+      gs.exec = nullptr;
       ln.graph_broken = true;
-      if (run_front(d, ln, s) != LM_OK) return LM_E_CUDA;
-      return enqueue_match(d, ln, plan, qs, n_q, s, nullptr);
+      ln.launches = launches_before;
+      if (run_front(d, ln, n_frames, s) != LM_OK) return LM_E_CUDA;
+      return enqueue_match(d, ln, plan, qs, n_q, n_frames, s, nullptr);
     }
-    ln.gkey = key;
-    ln.graph_launches = ln.launches;
+    gs.key = key;
+    gs.launches = ln.launches - launches_before;
+    ln.launches = launches_before;
   }
-  CU(cudaGraphLaunch(ln.gexec, s));
-  ln.launches = ln.graph_launches;
+  CU(cudaGraphLaunch(gs.exec, s));
+  ln.launches += gs.launches;
   ln.front_valid = true;
   ln.debug_taps_written = false;
+  for (size_t l = 0; l < ln.geom.size(); ++l) { ln.nibbles_valid[l] = true; ln.bytes_valid[l] = !level_nibble_aligned(ln.geom[l]); }
   return LM_OK;
 }
 
@@ -770,36 +760,37 @@ static void finalize_records(int levels, std::vector<lm_raw_match>& raw, std::ve
   out.erase(std::unique(out.begin(), out.end(), match_equal), out.end());
 }
 
-// One D2H copy brings the header + the first records; long lists need a second copy.
-// Result download, part 1: header + leading records into the lane's pinned staging block.  The pipelined paths enqueue it
-// right behind the frame's kernels, so that by the time the host comes back to this lane the records are already there.
-static int enqueue_download(Lane& ln, cudaStream_t s) {
-  const size_t first = std::min<size_t>(kFirstChunkRecords, ln.out_cap);
-  CU(cudaMemcpyAsync(ln.stage_out.p, ln.result.p, kStatsBytes + sizeof(ResultHeader) + first * sizeof(lm_raw_match), cudaMemcpyDeviceToHost, s));
+// Result download, part 1: (statistics + header + leading records) of every frame of the chunk into the lane's pinned
+// staging block, one strided copy.  The pipelined paths enqueue it right behind the chunk's kernels, so that by the time
+// the host comes back to this lane the records are already there.
+static int enqueue_download(Lane& ln, int n_frames, cudaStream_t s) {
+  const size_t hb = head_bytes(ln);
+  if (n_frames == 1) CU(cudaMemcpyAsync(ln.stage_out.p, ln.result.buf.p, hb, cudaMemcpyDeviceToHost, s));
+  else CU(cudaMemcpy2DAsync(ln.stage_out.p, hb, ln.result.buf.p, ln.result.stride, hb, (size_t)n_frames, cudaMemcpyDeviceToHost, s));
   CU(cudaEventRecord(ln.ev[5], s));
   return LM_OK;
 }
 
-static int download_records(Lane& ln, cudaStream_t s, std::vector<lm_raw_match>& raw, bool* overflow, uint32_t* n_cands,
-                            bool pre_enqueued = false) {
+// Result download, part 2 (after ln.ev[5]): frame f's records out of the staging block; long lists need a second copy.
+static int collect_records(Lane& ln, int f, cudaStream_t s, std::vector<lm_raw_match>& raw, bool* overflow, uint32_t* n_cands) {
   const size_t first = std::min<size_t>(kFirstChunkRecords, ln.out_cap);
-  uint8_t* host = ln.stage_out.as<uint8_t>();
-  if (!pre_enqueued && enqueue_download(ln, s) != LM_OK) return LM_E_CUDA;
-  CU(cudaEventSynchronize(ln.ev[5]));
-  ln.work_stats[6] = *reinterpret_cast<const unsigned long long*>(host);
+  const uint8_t* host = ln.stage_out.as<uint8_t>() + (size_t)f * head_bytes(ln);
+  if (f == 0) ln.work_stats[6] = *reinterpret_cast<const unsigned long long*>(host);
   host += kStatsBytes;
-  ResultHeader h = *reinterpret_cast<ResultHeader*>(host);
+  ResultHeader h;
+  std::memcpy(&h, host, sizeof(h));
   *overflow = h.overflow != 0 || h.count > ln.out_cap;
   *n_cands = h.n_cands;
+  raw.clear();
   if (*overflow) return LM_OK;
+  const lm_raw_match* recs = reinterpret_cast<const lm_raw_match*>(host + sizeof(ResultHeader));
+  raw.assign(recs, recs + std::min<size_t>(h.count, first));
   if (h.count > first) {
-    CU(cudaMemcpyAsync(host + sizeof(ResultHeader) + first * sizeof(lm_raw_match),
-                       block_ptr(ln) + sizeof(ResultHeader) + first * sizeof(lm_raw_match),
+    raw.resize(h.count);
+    CU(cudaMemcpyAsync(raw.data() + first, block_ptr(ln, f) + sizeof(ResultHeader) + first * sizeof(lm_raw_match),
                        (h.count - first) * sizeof(lm_raw_match), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
   }
-  const lm_raw_match* recs = reinterpret_cast<const lm_raw_match*>(host + sizeof(ResultHeader));
-  raw.assign(recs, recs + h.count);
   return LM_OK;
 }
 
@@ -822,32 +813,42 @@ static void finalize_queries(lm_detector* d, Lane& ln, std::vector<lm_raw_match>
   }
 }
 
-// Matching on an already-built front end; buffers grow and the request is re-run on overflow (exactness over speed).
-static int match_front(lm_detector* d, Lane& ln, const Query* queries, int n_q, std::vector<lm_match_rec>* out) {
+static const uint32_t kCandPerFrame = 1u << 16, kOutPerFrame = 1u << 12;
+
+// One frame (slot `frame` of the lane's uploaded / referenced sources), blocking; buffers grow and the request is re-run
+// on overflow (exactness over speed).  The single-frame calls land here, and the batched paths for the rare frame
+// whose survivors did not fit.
+static int match_one(lm_detector* d, Lane& ln, int frame, const Query* queries, int n_q, std::vector<lm_match_rec>* out,
+                     bool stage_events) {
   if (n_q < 1 || n_q > kMaxQueries) return lm_fail(LM_E_INVALID, "number of queries must be 1..%d", kMaxQueries);
   int rc = ensure_pack(d, ln);
   if (rc != LM_OK) return rc;
   Pack::Plan* plan = nullptr;
   rc = get_plan(d, queries, n_q, &plan);
   if (rc != LM_OK) return rc;
-  uint32_t cand_cap = std::max<uint32_t>(ln.cand_cap, 1u << 16), out_cap = std::max<uint32_t>(ln.out_cap, 1u << 14);
+  if (frame != 0)
+    for (int m = 0; m < d->model.M(); ++m) ln.src_ptr[0][m] = ln.src_ptr[frame][m];
+  uint32_t cand_cap = std::max<uint32_t>(ln.cand_cap, kCandPerFrame), out_cap = std::max<uint32_t>(ln.out_cap, kOutPerFrame);
   std::vector<lm_raw_match> raw;
   uint32_t n_cands = 0;
   for (int attempt = 0;; ++attempt) {
-    if (ensure_match_buffers(d, ln, cand_cap, out_cap) != LM_OK) return LM_E_CUDA;
-    if (attempt > 0) CU(cudaEventRecord(ln.ev[2], ln.stream));
-    if (enqueue_match(d, ln, *plan, queries, n_q, ln.stream, ln.ev[3]) != LM_OK) return LM_E_CUDA;
-    CU(cudaEventRecord(ln.ev[4], ln.stream));
+    if (ensure_match_buffers(d, ln, cand_cap, out_cap, 1) != LM_OK) return LM_E_CUDA;
+    if (enqueue_chunk(d, ln, *plan, queries, n_q, 1, ln.stream, stage_events) != LM_OK) return LM_E_CUDA;
+    if (enqueue_download(ln, 1, ln.stream) != LM_OK) return LM_E_CUDA;
+    CU(cudaEventSynchronize(ln.ev[5]));
     bool overflow = false;
-    if (download_records(ln, ln.stream, raw, &overflow, &n_cands) != LM_OK) return LM_E_CUDA;
+    if (collect_records(ln, 0, ln.stream, raw, &overflow, &n_cands) != LM_OK) return LM_E_CUDA;
     if (!overflow) break;
     if (attempt >= 8) return lm_fail(LM_E_CUDA, "match buffers overflowed repeatedly");
+    // the candidate count of a truncated list is the chunk-wide counter: read it back
+    BatchCtl ctl_head;
+    CU(cudaMemcpy(&ctl_head.next_tile, &ln.ctl.as<BatchCtl>()->next_tile, 16, cudaMemcpyDeviceToHost));
+    n_cands = std::max(n_cands, ctl_head.n_cands);
     if (n_cands > ln.cand_cap) cand_cap = std::max<uint32_t>(n_cands + n_cands / 4, cand_cap * 2);
     out_cap = std::max<uint32_t>(out_cap * 4, std::min<uint32_t>(n_cands + 1024, 1u << 26));
   }
   // work accounting: B_coarse from the plan; B_refine = candidates x mean refine features x 256 bytes
   ln.work_stats[1] = plan->coarse_bytes;
-  if (d->coarse_variant != 0) ln.work_stats[6] = plan->coarse_bytes;  // the A/B kernels always gather everything
   ln.work_stats[4] = n_cands;
   ln.work_stats[5] = (uint64_t)plan->n_items * (uint64_t)(ln.geom.back().W * ln.geom.back().H);
   ln.work_stats[2] = plan->n_items ? (uint64_t)((double)n_cands * (plan->refine_nf_sum / plan->n_items) * 256.0) : 0;
@@ -1022,7 +1023,6 @@ void lm_destroy(lm_detector* d) {
     }
     d->pack.release();
     d->train.release();
-    d->results_all.release();
     d->d_resp_all.release(); d->d_normal_lut.release();
   }
   delete d;
@@ -1109,9 +1109,10 @@ int lm_add_template(lm_detector* d, const lm_image* sources, int n_sources, cons
   if (upload_luts(d) != LM_OK) return LM_E_CUDA - 100;
   if (ensure_quant_ws(d, ln, rows, cols) != LM_OK) return LM_E_CUDA - 100;
   ln.lm_ready = false; ln.front_valid = false;
-  if (upload_frame(d, ln, sources, nullptr, 0) != LM_OK) return LM_E_CUDA - 100;
+  if (upload_frames(d, ln, sources, 1, nullptr, 0) != LM_OK) return LM_E_CUDA - 100;
   ln.launches = 0;
-  if (run_quantize(d, ln, ln.stream) != LM_OK) return LM_E_CUDA - 100;
+  if (begin_chunk(d, ln, 1, 0, ln.stream) != LM_OK) return LM_E_CUDA - 100;
+  if (run_quantize(d, ln, 1, ln.stream) != LM_OK) return LM_E_CUDA - 100;
   // download quantised maps (+ CG magnitudes) of every level
   size_t total = 0;
   std::vector<size_t> qoff((size_t)L * M), moff((size_t)L * M, 0);
@@ -1126,9 +1127,9 @@ int lm_add_template(lm_detector* d, const lm_image* sources, int n_sources, cons
   for (int l = 0; l < L; ++l)
     for (int m = 0; m < M; ++m) {
       size_t n = (size_t)(rows >> l) * (cols >> l);
-      if (cudaMemcpyAsync(host + qoff[l * M + m], ln.quant_raw[l][m].p, n, cudaMemcpyDeviceToHost, ln.stream) != cudaSuccess) return lm_fail(LM_E_CUDA, "D2H failed") - 100;
+      if (cudaMemcpyAsync(host + qoff[l * M + m], ln.quant_raw[l][m].buf.p, n, cudaMemcpyDeviceToHost, ln.stream) != cudaSuccess) return lm_fail(LM_E_CUDA, "D2H failed") - 100;
       if (d->model.mods[m].type == LM_COLOR_GRADIENT &&
-          cudaMemcpyAsync(host + moff[l * M + m], ln.mag[l][m].p, n * 4, cudaMemcpyDeviceToHost, ln.stream) != cudaSuccess)
+          cudaMemcpyAsync(host + moff[l * M + m], ln.mag[l][m].buf.p, n * 4, cudaMemcpyDeviceToHost, ln.stream) != cudaSuccess)
         return lm_fail(LM_E_CUDA, "D2H failed") - 100;
     }
   if (cudaStreamSynchronize(ln.stream) != cudaSuccess) return lm_fail(LM_E_CUDA, "quantisation kernels failed: %s", cudaGetErrorString(cudaGetLastError())) - 100;
@@ -1218,41 +1219,45 @@ int lm_set_option(lm_detector* d, const char* key, int value) {
   if (!d || !key) return lm_fail(LM_E_INVALID, "NULL argument");
   std::string k(key);
   if (k == "debug_taps") d->debug_taps = value;
-  else if (k == "coarse_variant") { d->coarse_variant = value; for (int i = 0; i < LM_LANES; ++i) d->lane[i].front_valid = false; }
   else if (k == "timing") d->timing = value;
   else if (k == "prune") d->prune = value;
   else if (k == "mod_order") d->mod_order = value & 3;
-  else if (k == "refine_variant") { d->refine_variant = value; for (int i = 0; i < LM_LANES; ++i) d->lane[i].front_valid = false; }
   else if (k == "graphs") d->graphs = value;
+  else if (k == "batch_frames") {
+    if (value < 1 || value > LM_MAX_BATCH) return lm_fail(LM_E_INVALID, "batch_frames must be 1..%d", LM_MAX_BATCH);
+    d->batch_frames = value;
+  }
+  else if (k == "batch_lanes") {
+    if (value < 1 || value > LM_LANES) return lm_fail(LM_E_INVALID, "batch_lanes must be 1..%d", LM_LANES);
+    d->batch_lanes = value;
+  }
   else if (k == "coarse_grid_limit") {  // process-wide; recorded graphs hold the old grid
     set_coarse_grid_limit(value);
-    for (int i = 0; i < LM_LANES; ++i)
-      if (d->lane[i].gexec) { cudaGraphExecDestroy(d->lane[i].gexec); d->lane[i].gexec = nullptr; }
+    for (int i = 0; i < LM_LANES; ++i) d->lane[i].drop_graphs();
   }
   else if (k == "device_out_cap") d->device_out_cap = (uint32_t)std::max(16, value);
-  else if (k == "frontend_variant") { d->frontend_variant = value; for (int i = 0; i < LM_LANES; ++i) d->lane[i].front_valid = false; }
+  else if (k == "cand_per_frame") d->cand_per_frame = (uint32_t)std::max(1024, value);
   else return lm_fail(LM_E_INVALID, "unknown option '%s'", key);
   return LM_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- match
-static int front_from_host(lm_detector* d, Lane& ln, const lm_image* sources, int n_sources, const lm_image* masks, int n_masks,
-                           bool run = true) {
-  int rc = check_sources(d, sources, n_sources, masks, n_masks);
-  if (rc != LM_OK) return rc;
+// Validates and uploads n_frames host frames (sources[f * M + m]) into the lane's source slots; nothing else is enqueued.
+static int frames_from_host(lm_detector* d, Lane& ln, const lm_image* sources, int n_frames, int n_sources, const lm_image* masks,
+                            int n_masks) {
+  for (int f = 0; f < n_frames; ++f) {
+    int rc = check_sources(d, sources + (size_t)f * n_sources, n_sources, f == 0 ? masks : nullptr, f == 0 ? n_masks : 0);
+    if (rc != LM_OK) return rc;
+    if (sources[(size_t)f * n_sources].rows != sources[0].rows || sources[(size_t)f * n_sources].cols != sources[0].cols)
+      return lm_fail(LM_E_INVALID, "frames of a batch differ in size");
+  }
   if (set_device(d) != LM_OK || upload_luts(d) != LM_OK) return LM_E_CUDA;
   const int rows = sources[0].rows, cols = sources[0].cols;
-  rc = ensure_lm_ws(d, ln, rows, cols);
+  int rc = ensure_lm_ws(d, ln, rows, cols, n_frames);
   if (rc != LM_OK) return rc;
-  ln.launches = 0;
   std::memset(ln.work_stats, 0, sizeof(ln.work_stats));
-  CU(cudaEventRecord(ln.ev[0], ln.stream));
-  if (upload_frame(d, ln, sources, masks, n_masks) != LM_OK) return LM_E_CUDA;
-  CU(cudaEventRecord(ln.ev[1], ln.stream));
-  if (run) {
-    if (run_front(d, ln, ln.stream) != LM_OK) return LM_E_CUDA;
-    CU(cudaEventRecord(ln.ev[2], ln.stream));
-  }
+  if (d->timing) CU(cudaEventRecord(ln.ev[0], ln.stream));
+  if (upload_frames(d, ln, sources, n_frames, masks, n_masks) != LM_OK) return LM_E_CUDA;
   // B_front: sources read once + linear memories written once
   uint64_t bf = 0;
   for (int m = 0; m < n_sources; ++m) bf += src_row_bytes(sources[m].type, cols) * rows;
@@ -1264,8 +1269,11 @@ static int front_from_host(lm_detector* d, Lane& ln, const lm_image* sources, in
 int lm_build_front(lm_detector* d, const lm_image* sources, int n_sources, const lm_image* masks, int n_masks) {
   if (!d || !sources) return lm_fail(LM_E_INVALID, "NULL argument");
   Lane& ln = d->lane[0];
-  int rc = front_from_host(d, ln, sources, n_sources, masks, n_masks);
+  int rc = frames_from_host(d, ln, sources, 1, n_sources, masks, n_masks);
   if (rc != LM_OK) return rc;
+  ln.launches = 0;
+  if (begin_chunk(d, ln, 1, 0, ln.stream) != LM_OK) return LM_E_CUDA;
+  if (run_front(d, ln, 1, ln.stream) != LM_OK) return LM_E_CUDA;
   CU(cudaStreamSynchronize(ln.stream));
   return LM_OK;
 }
@@ -1288,12 +1296,12 @@ int lm_match_multi(lm_detector* d, const lm_image* sources, int n_sources, const
   int rc = to_queries(queries, n_queries, qs);
   if (rc != LM_OK) return rc;
   Lane& ln = d->lane[0];
-  rc = front_from_host(d, ln, sources, n_sources, masks, n_masks);
+  rc = frames_from_host(d, ln, sources, 1, n_sources, masks, n_masks);
   if (rc != LM_OK) return rc;
   std::vector<lm_match_rec> out[kMaxQueries];
-  rc = match_front(d, ln, qs, n_queries, out);
+  rc = match_one(d, ln, 0, qs, n_queries, out, d->timing != 0);
   if (rc != LM_OK) return rc;
-  collect_timings(ln);
+  if (d->timing) collect_timings(ln);
   if (quantized_out) {
     const int L = d->model.levels(), M = d->model.M();
     for (int l = 0; l < L; ++l)
@@ -1302,7 +1310,7 @@ int lm_match_multi(lm_detector* d, const lm_image* sources, int n_sources, const
         const LevelGeom& g = ln.geom[l];
         if (!q.data || q.rows != g.rows || q.cols != g.cols || q.type != LM_8UC1 || q.step < (size_t)g.cols)
           return lm_fail(LM_E_INVALID, "quantized_out[%d] must be a %dx%d CV_8UC1 image", l * M + m, g.cols, g.rows);
-        CU(cudaMemcpy2D(q.data, q.step, ln.quantized[l][m].p, g.cols, g.cols, g.rows, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy2D(q.data, q.step, ln.quantized[l][m].as<uint8_t>(), g.cols, g.cols, g.rows, cudaMemcpyDeviceToHost));
       }
   }
   std::vector<lm_match_rec> all;
@@ -1327,66 +1335,92 @@ int lm_match(lm_detector* d, const lm_image* sources, int n_sources, float thres
   return rc;
 }
 
-// Frames pipelined over the two lanes: while lane A's kernels run, lane B's frame is packed / copied to the device.
-// out_offsets: n_frames * n_q + 1 prefix offsets, frame-major.
+// Pre-sizes a lane for chunks of `frames` frames of this geometry: workspace, template pack, plan, result blocks.
+static int prepare_lane(lm_detector* d, Lane& ln, int rows, int cols, int frames, const Query* qs, int n_q, uint32_t out_cap,
+                        Pack::Plan** plan) {
+  int rc = ensure_lm_ws(d, ln, rows, cols, frames);
+  if (rc != LM_OK) return rc;
+  rc = ensure_pack(d, ln);
+  if (rc != LM_OK) return rc;
+  rc = get_plan(d, qs, n_q, plan);
+  if (rc != LM_OK) return rc;
+  const uint32_t cand_cap = std::max<uint32_t>(ln.cand_cap, d->cand_per_frame * (uint32_t)std::max(frames, ln.frames));
+  return ensure_match_buffers(d, ln, cand_cap, std::max<uint32_t>(ln.out_cap, out_cap), std::max(frames, ln.frames));
+}
+
+// Frames in chunks of `batch_frames`, chunks pipelined over `batch_lanes` workspace lanes: while one chunk's kernels run,
+// the next chunk's frames are copied to the device and the previous chunk's survivors are ordered on the host.  Every
+// kernel launch covers a whole chunk.  out_offsets: n_frames * n_q + 1 prefix offsets, frame-major.
 static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frames, int n_sources, const Query* qs, int n_q,
                             lm_match_rec** out_matches, size_t* out_offsets) {
   *out_matches = nullptr;
   if (n_q < 1 || n_q > kMaxQueries) return lm_fail(LM_E_INVALID, "number of queries must be 1..%d", kMaxQueries);
-  std::vector<lm_match_rec> all;
   out_offsets[0] = 0;
-  bool busy[LM_LANES] = {};
-  auto finish = [&](int li, int frame) -> int {
+  if (n_frames == 0) { size_t n = 0; return copy_out(std::vector<lm_match_rec>(), out_matches, &n); }
+  if (set_device(d) != LM_OK) return LM_E_CUDA;
+  const int F = std::max(1, std::min(d->batch_frames, LM_MAX_BATCH));
+  const int NL = std::max(1, std::min(d->batch_lanes, LM_LANES));
+  const int n_chunks = (n_frames + F - 1) / F;
+  // per (frame, query) result lists, concatenated at the end (chunks finish in order, but a frame may be redone)
+  std::vector<std::vector<lm_match_rec> > lists((size_t)n_frames * n_q);
+  struct Pending { int first = -1, n = 0; } pending[LM_LANES];
+  std::vector<lm_raw_match> raw;
+  auto finish = [&](int li) -> int {
     Lane& ln = d->lane[li];
-    std::vector<lm_raw_match> raw;
-    bool overflow = false;
-    uint32_t n_cands = 0;
-    if (download_records(ln, ln.stream, raw, &overflow, &n_cands, true) != LM_OK) return LM_E_CUDA;
-    std::vector<lm_match_rec> out[kMaxQueries];
-    if (overflow) {  // rare: redo this frame alone with growing buffers
-      int rc = match_front(d, ln, qs, n_q, out);
+    const Pending pd = pending[li];
+    pending[li].first = -1;
+    CU(cudaEventSynchronize(ln.ev[5]));
+    std::vector<int> redo;
+    for (int f = 0; f < pd.n; ++f) {
+      bool overflow = false;
+      uint32_t n_cands = 0;
+      if (collect_records(ln, f, ln.stream, raw, &overflow, &n_cands) != LM_OK) return LM_E_CUDA;
+      if (overflow) { redo.push_back(f); continue; }
+      finalize_queries(d, ln, raw, n_q, &lists[(size_t)(pd.first + f) * n_q]);
+    }
+    for (int f : redo) {  // rare: this frame alone with growing buffers (its sources are still in the lane's slot f)
+      int rc = match_one(d, ln, f, qs, n_q, &lists[(size_t)(pd.first + f) * n_q], false);
       if (rc != LM_OK) return rc;
-    } else finalize_queries(d, ln, raw, n_q, out);
-    for (int q = 0; q < n_q; ++q) {
-      all.insert(all.end(), out[q].begin(), out[q].end());
-      out_offsets[(size_t)frame * n_q + q + 1] = all.size();
     }
     return LM_OK;
   };
   const bool prof = getenv("LM_HOST_PROFILE") != nullptr;
-  double t_fin = 0, t_up = 0, t_plan = 0, t_enq = 0;
+  double t_fin = 0, t_up = 0, t_enq = 0;
   auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  for (int f = 0; f < n_frames; ++f) {
-    const int li = f % LM_LANES;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int li = c % NL;
     Lane& ln = d->lane[li];
+    const int first = c * F, n = std::min(F, n_frames - first);
     double t0 = prof ? now() : 0;
-    // The upload of frame f is queued on the lane's stream BEFORE the host waits for the lane's previous frame: stream order
-    // keeps it behind that frame's kernels and download, and the copy engine always has the next frame waiting instead of
-    // idling until the host comes back (the frame's H2D copy is what bounds the end-to-end rate).  The previous frame's
-    // linear memories and result block are untouched until the kernels of frame f are enqueued below.
-    int rc = front_from_host(d, ln, sources + (size_t)f * n_sources, n_sources, nullptr, 0, false);  // upload only
-    if (rc != LM_OK) return rc;
+    // the lane's previous chunk must be done before its source slots and pinned staging are overwritten
+    if (pending[li].first >= 0) { int rc = finish(li); if (rc != LM_OK) return rc; }
     double t1 = prof ? now() : 0;
-    if (busy[li]) { rc = finish(li, f - LM_LANES); if (rc != LM_OK) return rc; busy[li] = false; }
-    double t2 = prof ? now() : 0;
-    rc = ensure_pack(d, ln);
+    const lm_image* fs = sources + (size_t)first * n_sources;
+    int rc = check_sources(d, fs, n_sources, nullptr, 0);
     if (rc != LM_OK) return rc;
     Pack::Plan* plan = nullptr;
-    rc = get_plan(d, qs, n_q, &plan);
+    rc = prepare_lane(d, ln, fs[0].rows, fs[0].cols, std::min(F, n_frames), qs, n_q, kOutPerFrame, &plan);
     if (rc != LM_OK) return rc;
-    if (ensure_match_buffers(d, ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
-    double t3 = prof ? now() : 0;
-    if (enqueue_frame(d, ln, *plan, qs, n_q, ln.stream) != LM_OK) return LM_E_CUDA;
-    CU(cudaEventRecord(ln.ev[4], ln.stream));
-    if (enqueue_download(ln, ln.stream) != LM_OK) return LM_E_CUDA;
-    busy[li] = true;
-    if (prof) { double t4 = now(); t_up += t1 - t0; t_fin += t2 - t1; t_plan += t3 - t2; t_enq += t4 - t3; }
+    rc = frames_from_host(d, ln, fs, n, n_sources, nullptr, 0);
+    if (rc != LM_OK) return rc;
+    double t2 = prof ? now() : 0;
+    if (enqueue_chunk(d, ln, *plan, qs, n_q, n, ln.stream) != LM_OK) return LM_E_CUDA;
+    if (enqueue_download(ln, n, ln.stream) != LM_OK) return LM_E_CUDA;
+    pending[li].first = first; pending[li].n = n;
+    if (prof) { double t3 = now(); t_fin += t1 - t0; t_up += t2 - t1; t_enq += t3 - t2; }
   }
-  if (prof && n_frames)
-    fprintf(stderr, "[lm host profile] per frame us: finish %.1f upload %.1f pack/plan %.1f enqueue %.1f\n", t_fin / n_frames,
-            t_up / n_frames, t_plan / n_frames, t_enq / n_frames);
-  for (int f = std::max(0, n_frames - LM_LANES); f < n_frames; ++f)
-    if (busy[f % LM_LANES]) { int rc = finish(f % LM_LANES, f); if (rc != LM_OK) return rc; busy[f % LM_LANES] = false; }
+  for (int k = 0; k < NL; ++k) {  // drain in submission order
+    const int li = (n_chunks + k) % NL;
+    if (pending[li].first >= 0) { int rc = finish(li); if (rc != LM_OK) return rc; }
+  }
+  if (prof)
+    fprintf(stderr, "[lm host profile] per frame us: finish %.1f upload %.1f enqueue %.1f\n", t_fin / n_frames, t_up / n_frames,
+            t_enq / n_frames);
+  std::vector<lm_match_rec> all;
+  for (size_t i = 0; i < lists.size(); ++i) {
+    all.insert(all.end(), lists[i].begin(), lists[i].end());
+    out_offsets[i + 1] = all.size();
+  }
   size_t n = 0;
   return copy_out(all, out_matches, &n);
 }
@@ -1409,39 +1443,36 @@ int lm_match_batch_multi(lm_detector* d, const lm_image* sources, int n_frames, 
 
 void lm_free_matches(lm_match_rec* m) { std::free(m); }
 
+// A chunk of device-resident frames on one lane and the caller's stream: nothing is uploaded, copied or synchronised.
+static int device_chunk(lm_detector* d, int lane_index, const void* const* d_sources, int n_frames, int n_sources, int rows,
+                        int cols, const Query* qs, int n_q, int ws_frames, cudaStream_t s) {
+  if (lane_index < 0 || lane_index >= LM_LANES) return lm_fail(LM_E_INVALID, "lane must be 0..%d", LM_LANES - 1);
+  if (n_sources != d->model.M()) return lm_fail(LM_E_INVALID, "sources.size() (%d) != modalities.size() (%d)", n_sources, d->model.M());
+  if (n_frames < 1 || n_frames > LM_MAX_BATCH) return lm_fail(LM_E_INVALID, "a chunk holds 1..%d frames", LM_MAX_BATCH);
+  if (set_device(d) != LM_OK || upload_luts(d) != LM_OK) return LM_E_CUDA;
+  Lane& ln = d->lane[lane_index];
+  Pack::Plan* plan = nullptr;
+  int rc = prepare_lane(d, ln, rows, cols, std::max(ws_frames, n_frames), qs, n_q, d->device_out_cap, &plan);
+  if (rc != LM_OK) return rc;
+  for (int f = 0; f < n_frames; ++f)
+    for (int m = 0; m < n_sources; ++m) {
+      if (!d_sources[(size_t)f * n_sources + m]) return lm_fail(LM_E_INVALID, "frame %d: source %d is NULL", f, m);
+      ln.src_ptr[f][m] = d_sources[(size_t)f * n_sources + m];
+    }
+  for (int m = 0; m < n_sources; ++m) ln.has_mask[m] = false;
+  return enqueue_chunk(d, ln, *plan, qs, n_q, n_frames, s);
+}
+
 int lm_match_device_multi_lane(lm_detector* d, int lane_index, const void* const* d_sources, int n_sources, int rows,
                                int cols, const lm_query* queries, int n_queries, void* stream, const void** d_records,
                                size_t* record_bytes_capacity) {
   if (!d || !d_sources || !d_records) return lm_fail(LM_E_INVALID, "NULL argument");
-  if (lane_index < 0 || lane_index >= LM_LANES) return lm_fail(LM_E_INVALID, "lane must be 0..%d", LM_LANES - 1);
-  if (n_sources != d->model.M()) return lm_fail(LM_E_INVALID, "sources.size() (%d) != modalities.size() (%d)", n_sources, d->model.M());
   Query qs[kMaxQueries];
   int rc = to_queries(queries, n_queries, qs);
   if (rc != LM_OK) return rc;
-  if (set_device(d) != LM_OK || upload_luts(d) != LM_OK) return LM_E_CUDA;
+  rc = device_chunk(d, lane_index, d_sources, 1, n_sources, rows, cols, qs, n_queries, 1, (cudaStream_t)stream);
+  if (rc != LM_OK) return rc;
   Lane& ln = d->lane[lane_index];
-  cudaStream_t s = (cudaStream_t)stream;
-  const bool fresh_ws = !(ln.lm_ready && ln.rows == rows && ln.cols == cols);
-  rc = ensure_lm_ws(d, ln, rows, cols);
-  if (rc != LM_OK) return rc;
-  if (fresh_ws) CU(cudaStreamSynchronize(ln.stream));  // workspace memsets were enqueued on the lane's own stream
-  const bool replay = d->graphs && !ln.graph_broken && !d->debug_taps;
-  for (int m = 0; m < n_sources; ++m) {
-    ln.has_mask[m] = false;
-    if (replay) {  // the recorded graph reads the lane's own source buffers: one device-to-device copy per source
-      const size_t bytes = src_row_bytes(expected_src_type(d->model.mods[m]), cols) * rows;
-      CU(cudaMemcpyAsync(ln.src[m].p, d_sources[m], bytes, cudaMemcpyDeviceToDevice, s));
-      ln.src_ptr[m] = ln.src[m].p;
-    } else ln.src_ptr[m] = d_sources[m];
-  }
-  ln.launches = 0;
-  rc = ensure_pack(d, ln);
-  if (rc != LM_OK) return rc;
-  Pack::Plan* plan = nullptr;
-  rc = get_plan(d, qs, n_queries, &plan);
-  if (rc != LM_OK) return rc;
-  if (ensure_match_buffers(d, ln, std::max<uint32_t>(ln.cand_cap, 1u << 18), std::max<uint32_t>(ln.out_cap, d->device_out_cap)) != LM_OK) return LM_E_CUDA;
-  if (enqueue_frame(d, ln, *plan, qs, n_queries, s) != LM_OK) return LM_E_CUDA;
   *d_records = block_ptr(ln);
   if (record_bytes_capacity) *record_bytes_capacity = result_bytes(ln);
   return LM_OK;
@@ -1454,21 +1485,20 @@ int lm_match_device_multi(lm_detector* d, const void* const* d_sources, int n_so
                                     record_bytes_capacity);
 }
 
-int lm_device_result_region(lm_detector* d, const void** base, size_t* lane_stride, int* n_lanes) {
-  if (!d || !base || !lane_stride || !n_lanes) return lm_fail(LM_E_INVALID, "NULL argument");
-  if (set_device(d) != LM_OK) return LM_E_CUDA;
-  if (d->results_all.p == nullptr &&
-      ensure_match_buffers(d, d->lane[0], std::max<uint32_t>(d->lane[0].cand_cap, 1u << 18), d->device_out_cap) != LM_OK)
-    return LM_E_CUDA;
-  *base = d->results_all.as<uint8_t>() + kStatsBytes;
-  *lane_stride = d->result_stride;
-  *n_lanes = LM_LANES;
+int lm_device_result_region(lm_detector* d, int lane_index, const void** base, size_t* frame_stride, int* n_frames) {
+  if (!d || !base || !frame_stride || !n_frames) return lm_fail(LM_E_INVALID, "NULL argument");
+  if (lane_index < 0 || lane_index >= LM_LANES) return lm_fail(LM_E_INVALID, "lane must be 0..%d", LM_LANES - 1);
+  const Lane& ln = d->lane[lane_index];
+  if (ln.result.buf.p == nullptr) return lm_fail(LM_E_STATE, "lane %d has no result blocks yet", lane_index);
+  *base = block_ptr(ln);
+  *frame_stride = ln.result.stride;
+  *n_frames = ln.result.frames;
   return LM_OK;
 }
 
 int lm_copy_result_block(lm_detector* d, int lane_index, void* d_dst, size_t bytes, void* stream) {
   if (!d || !d_dst) return lm_fail(LM_E_INVALID, "NULL argument");
-  if (lane_index < 0 || lane_index >= LM_LANES || d->lane[lane_index].result.p == nullptr) return lm_fail(LM_E_STATE, "lane %d has no result block yet", lane_index);
+  if (lane_index < 0 || lane_index >= LM_LANES || d->lane[lane_index].result.buf.p == nullptr) return lm_fail(LM_E_STATE, "lane %d has no result block yet", lane_index);
   const Lane& ln = d->lane[lane_index];
   if (bytes > result_bytes(ln)) return lm_fail(LM_E_INVALID, "block is only %zu bytes", result_bytes(ln));
   CU(cudaMemcpyAsync(d_dst, block_ptr(ln), bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -1480,15 +1510,20 @@ int lm_match_device_stream(lm_detector* d, const void* const* d_sources, int n_f
                            size_t stage_slot_bytes) {
   if (!d || !d_sources || !streams || n_frames < 0) return lm_fail(LM_E_INVALID, "NULL argument");
   if (n_streams < 1 || n_streams > LM_LANES) return lm_fail(LM_E_INVALID, "number of streams must be 1..%d", LM_LANES);
-  for (int f = 0; f < n_frames; ++f) {
-    const int lane = f % n_streams;
-    const void* rec = nullptr;
-    int rc = lm_match_device_multi_lane(d, lane, d_sources + (size_t)f * n_sources, n_sources, rows, cols, queries, n_queries,
-                                        streams[lane], &rec, nullptr);
+  Query qs[kMaxQueries];
+  int rc = to_queries(queries, n_queries, qs);
+  if (rc != LM_OK) return rc;
+  const int F = std::max(1, std::min(d->batch_frames, LM_MAX_BATCH));
+  for (int first = 0, c = 0; first < n_frames; first += F, ++c) {
+    const int lane = c % n_streams, n = std::min(F, n_frames - first);
+    cudaStream_t s = (cudaStream_t)streams[lane];
+    rc = device_chunk(d, lane, d_sources + (size_t)first * n_sources, n, n_sources, rows, cols, qs, n_queries, std::min(F, n_frames), s);
     if (rc != LM_OK) return rc;
-    if (d_stage) {
-      rc = lm_copy_result_block(d, lane, static_cast<uint8_t*>(d_stage) + (size_t)f * stage_slot_bytes, stage_slot_bytes, streams[lane]);
-      if (rc != LM_OK) return rc;
+    if (d_stage) {  // heads of the chunk's record blocks -> consecutive slots of the caller's exchange buffer, one strided copy
+      const Lane& ln = d->lane[lane];
+      if (stage_slot_bytes > result_bytes(ln)) return lm_fail(LM_E_INVALID, "block is only %zu bytes", result_bytes(ln));
+      CU(cudaMemcpy2DAsync(static_cast<uint8_t*>(d_stage) + (size_t)first * stage_slot_bytes, stage_slot_bytes, block_ptr(ln),
+                           ln.result.stride, stage_slot_bytes, (size_t)n, cudaMemcpyDeviceToDevice, s));
     }
   }
   return LM_OK;
@@ -1684,11 +1719,11 @@ long lm_debug_fetch(lm_detector* d, int stage, int level, int modality, void* ds
   const void* src = nullptr;
   size_t bytes = 0;
   switch (stage) {
-    case LM_STAGE_QUANTIZED: src = ln.quantized[level][modality].p; bytes = n; break;
-    case LM_STAGE_QUANT_RAW: src = ln.quant_raw[level][modality].p; bytes = n; break;
+    case LM_STAGE_QUANTIZED: src = ln.quantized[level][modality].buf.p; bytes = n; break;
+    case LM_STAGE_QUANT_RAW: src = ln.quant_raw[level][modality].buf.p; bytes = n; break;
     case LM_STAGE_MAGNITUDE:
       if (d->model.mods[modality].type != LM_COLOR_GRADIENT) return lm_fail(LM_E_INVALID, "magnitude exists for ColorGradient only");
-      src = ln.mag[level][modality].p; bytes = n * 4; break;
+      src = ln.mag[level][modality].buf.p; bytes = n * 4; break;
     case LM_STAGE_SPREAD:
     case LM_STAGE_RESPONSE:
       if (!ln.debug_taps_written) return lm_fail(LM_E_STATE, "enable lm_set_option(det, \"debug_taps\", 1) before matching");
@@ -1709,7 +1744,7 @@ long lm_debug_fetch(lm_detector* d, int stage, int level, int modality, void* ds
       }
       src = ln.lmem[level].as<uint8_t>() + (size_t)modality * 8 * g.plane_stride; break;
     case LM_STAGE_LINEAR_PACKED:
-      if (!ln.nibbles_valid[level]) return lm_fail(LM_E_STATE, "level %d has no packed planes (rows not word-aligned, or a byte kernel variant is selected)", level);
+      if (!ln.nibbles_valid[level]) return lm_fail(LM_E_STATE, "level %d has no packed planes", level);
       src = ln.lmn[level].as<uint8_t>() + (size_t)modality * 4 * g.plane_stride; bytes = 4 * g.plane_stride; break;
     default: return lm_fail(LM_E_INVALID, "unknown stage %d", stage);
   }
@@ -1735,33 +1770,30 @@ int lm_debug_coarse_map(lm_detector* d, const char* class_id, int template_id, u
   if (local < 0) return lm_fail(LM_E_NOTFOUND, "class '%s' template %d is not on this shard", class_id, template_id);
   const LevelGeom& gc = ln.geom.back();
   const int WH = gc.W * gc.H;
-  if (ensure_match_buffers(d, ln, std::max<uint32_t>(ln.cand_cap, 1u << 16), std::max<uint32_t>(ln.out_cap, 1u << 14)) != LM_OK) return LM_E_CUDA;
-  const int pass_pos = coarse_positions_per_pass(d->coarse_variant);
+  if (ensure_match_buffers(d, ln, std::max<uint32_t>(ln.cand_cap, kCandPerFrame), std::max<uint32_t>(ln.out_cap, kOutPerFrame), 1) != LM_OK) return LM_E_CUDA;
+  const int pass_pos = coarse_positions_per_pass();
   const int P = pk.h_ctpl[local].P;
   std::vector<uint2> tl;
   for (int pass = 0; pass * pass_pos < P; ++pass) tl.push_back(make_uint2(0u, (uint32_t)pass));
-  if (ln.dump.ensure((size_t)WH * 2) != LM_OK || ln.work.ensure(64) != LM_OK || ln.work_order.ensure(tl.size() * sizeof(uint2) + 64) != LM_OK) return LM_E_CUDA;
+  if (ln.dump.ensure((size_t)WH * 2) != LM_OK) return LM_E_CUDA;
   WorkItem it = {(uint32_t)local, 0u};
   CU(cudaMemsetAsync(ln.dump.p, 0, (size_t)WH * 2, ln.stream));
-  CU(cudaMemcpyAsync(ln.work.p, &it, sizeof(it), cudaMemcpyHostToDevice, ln.stream));
-  if (!tl.empty()) CU(cudaMemcpyAsync(ln.work_order.p, tl.data(), tl.size() * sizeof(uint2), cudaMemcpyHostToDevice, ln.stream));
-  CU(cudaMemsetAsync(ln.result.p, 0, kStatsBytes + sizeof(ResultHeader), ln.stream));
+  if (begin_chunk(d, ln, 1, 1, ln.stream) != LM_OK) return LM_E_CUDA;  // frame 0 = the front end built last
   std::vector<uint32_t> recs;
   int rec_words = 0;
-  if (d->coarse_variant == 0) {
-    std::vector<WorkItem> one(1, it);
-    if (build_tile_records(pk, one, tl, pass_pos, d->model.M(), recs, &rec_words) != LM_OK) return LM_E_INVALID;
-    if (ln.dbg_recs.ensure(recs.size() * 4 + 64) != LM_OK) return LM_E_CUDA;
-    if (!recs.empty()) CU(cudaMemcpyAsync(ln.dbg_recs.p, recs.data(), recs.size() * 4, cudaMemcpyHostToDevice, ln.stream));
-  }
+  std::vector<WorkItem> one(1, it);
+  if (build_tile_records(pk, one, tl, pass_pos, d->model.M(), recs, &rec_words) != LM_OK) return LM_E_INVALID;
+  if (ln.dbg_recs.ensure(recs.size() * 4 + 64) != LM_OK) return LM_E_CUDA;
+  if (!recs.empty()) CU(cudaMemcpyAsync(ln.dbg_recs.p, recs.data(), recs.size() * 4, cudaMemcpyHostToDevice, ln.stream));
   // threshold 1e30 -> raw threshold saturates: nothing becomes a candidate, the kernel only dumps its accumulators
-  QueryThresholds qt;
-  for (int q = 0; q < LM_MAX_QUERIES; ++q) qt.v[q] = 1e30f;
-  launch_similarity_coarse(d->coarse_variant, ln.lmem[d->model.levels() - 1].as<uint8_t>(), ln.lmn[d->model.levels() - 1].as<uint8_t>(),
-                           pk.foff.as<uint32_t>(), pk.ctpl.as<CoarseTpl>(),
-                           ln.work.as<WorkItem>(), ln.work_order.as<uint2>(), ln.dbg_recs.as<uint32_t>(), rec_words,
-                           (int)tl.size(), qt, d->model.M(),
-                           0, ln.cand.as<Cand>(), reinterpret_cast<ResultHeader*>(block_ptr(ln)), nullptr, 0, ln.dump.as<uint16_t>(), WH, ln.stream);
+  CoarseParams cp;
+  std::memset(&cp, 0, sizeof(cp));
+  for (int q = 0; q < LM_MAX_QUERIES; ++q) cp.thr.v[q] = 1e30f;
+  cp.lmn = ln.lmn[d->model.levels() - 1].as<uint8_t>(); cp.lmn_stride = ln.lmn[d->model.levels() - 1].stride;
+  cp.recs = ln.dbg_recs.as<uint32_t>(); cp.rec_words = rec_words; cp.n_tiles = (int)tl.size();
+  cp.ctl = ln.ctl.as<BatchCtl>(); cp.cand = ln.cand.as<Cand>(); cp.cand_cap = 0; cp.M = d->model.M();
+  cp.dump = ln.dump.as<uint16_t>(); cp.dump_stride = WH;
+  launch_similarity_coarse(cp, 1, ln.stream);
   CU(cudaMemcpyAsync(dst, ln.dump.p, (size_t)WH * 2, cudaMemcpyDeviceToHost, ln.stream));
   CU(cudaStreamSynchronize(ln.stream));
   return LM_OK;

@@ -60,6 +60,31 @@ struct PinBuf {  // grow-only page-locked host allocation
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Grow-only device allocation holding `frames` equally sized per-frame regions, `stride` bytes apart (multiple of 256):
+// the kernels of the matching path address frame f of a chunk as base + f * stride.
+struct FrameBuf {
+  DevBuf buf;
+  size_t stride = 0;
+  int frames = 0;
+  int ensure(size_t bytes_per_frame, int n_frames, bool* grew = nullptr) {
+    if (grew) *grew = false;
+    size_t st = (bytes_per_frame + 255) & ~(size_t)255;
+    if (buf.p && st <= stride && n_frames <= frames) return LM_OK;
+    st = std::max(st, stride);
+    n_frames = std::max(n_frames, frames);
+    buf.release();
+    stride = 0; frames = 0;
+    if (buf.ensure(st * (size_t)n_frames) != LM_OK) return LM_E_CUDA;
+    stride = st; frames = n_frames;
+    if (grew) *grew = true;
+    return LM_OK;
+  }
+  void release() { buf.release(); stride = 0; frames = 0; }
+  template <class T> T* as(int f = 0) const { return reinterpret_cast<T*>(static_cast<uint8_t*>(buf.p) + (size_t)f * stride); }
+  template <class T> size_t stride_in() const { return stride / sizeof(T); }
+  size_t bytes() const { return buf.cap; }
+};
+
 struct LevelGeom {
   int rows = 0, cols = 0, T = 0, W = 0, H = 0;
   size_t plane_stride = 0;
@@ -73,70 +98,79 @@ static inline size_t plane_stride_of(int T, int W, int H) {
 }
 static const size_t kLmSlack = 8192;  // tail slack: vector loads of partially filled passes may over-read
 
-// Frames in flight per handle: lm_match_batch* pipelines this many frames (H2D copy, kernels, D2H copy of different
-// frames overlap), lm_match_device_multi_lane exposes them to callers that manage their own streams.
+// Workspace lanes per handle.  A lane processes one CHUNK of frames at a time (one launch set: front end, coarse
+// similarity and refinement kernels each cover every frame of the chunk); lm_match_batch* pipelines chunks over
+// `batch_lanes` of them so that the host->device copies, the kernels and the result download of consecutive chunks
+// overlap, and lm_match_device_multi_lane / lm_match_device_stream expose them to callers that manage their own streams.
 static const int LM_LANES = 8;
+static const int LM_GRAPH_SLOTS = 6;  // recorded launch geometries per lane: 1, 2, 4, 8, 16, 32 frames
 
-// One in-flight frame: stream, events, device workspace, pinned staging.
+// One in-flight chunk: stream, events, device workspace, pinned staging.
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  // modalities quantise concurrently: modality m > 0 runs on side[m-1], forked from / joined into the frame's stream
+  // modalities quantise concurrently: modality m > 0 runs on side[m-1], forked from / joined into the chunk's stream
   cudaStream_t side[LM_MAX_MODALITIES - 1] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[LM_MAX_MODALITIES - 1] = {nullptr, nullptr, nullptr};
   int rows = 0, cols = 0;     // geometry of the quantisation workspace
-  bool lm_ready = false;      // LM buffers sized + zero-tailed for (rows, cols)
+  int frames = 0;             // frame slots the workspace holds
+  bool lm_ready = false;      // LM buffers sized + zero-tailed for (rows, cols, frames)
   bool front_valid = false;
   bool debug_taps_written = false;
   bool bytes_valid[LM_MAX_LEVELS] = {false, false, false, false};    // byte planes written by the last front end
   bool nibbles_valid[LM_MAX_LEVELS] = {false, false, false, false};  // nibble planes written by the last front end
   std::vector<LevelGeom> geom;
   // per modality
-  DevBuf src[LM_MAX_MODALITIES];       // level-0 source (BGR / depth)
-  const void* src_ptr[LM_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr};  // own buffer or caller's device ptr
-  DevBuf mask0[LM_MAX_MODALITIES];
+  FrameBuf src[LM_MAX_MODALITIES];     // level-0 sources uploaded from the host (BGR / depth)
+  const void* src_ptr[LM_MAX_BATCH][LM_MAX_MODALITIES] = {};  // sources of the current chunk: own slots or the caller's device pointers
+  int n_frames = 0;                    // frames of the current / last chunk
+  DevBuf mask0[LM_MAX_MODALITIES];     // single-frame requests only
   bool has_mask[LM_MAX_MODALITIES] = {false, false, false, false};
   // per (level, modality)
-  DevBuf bgr[LM_MAX_LEVELS][LM_MAX_MODALITIES];       // CG pyramid sources for level >= 1
-  DevBuf smoothed[LM_MAX_MODALITIES], qunf[LM_MAX_MODALITIES], dn_raw[LM_MAX_MODALITIES];  // scratch, reused per level
-  DevBuf mag[LM_MAX_LEVELS][LM_MAX_MODALITIES];
-  DevBuf quant_raw[LM_MAX_LEVELS][LM_MAX_MODALITIES];
-  DevBuf quantized[LM_MAX_LEVELS][LM_MAX_MODALITIES];
-  DevBuf spread[LM_MAX_LEVELS][LM_MAX_MODALITIES], response[LM_MAX_LEVELS][LM_MAX_MODALITIES];  // parity taps only
-  DevBuf lmem[LM_MAX_LEVELS];                          // [M][8][plane_stride] + slack
-  DevBuf lmn[LM_MAX_LEVELS];                           // the same planes nibble-packed (two positions per byte): what the
-                                                       // matching kernels read when the level's rows are word-aligned
-  // The GPU work of one frame (front end, header memset, coarse, refine) as an instantiated CUDA graph: the batch and
-  // device-resident paths replay it instead of ~20 runtime calls per frame.  Valid while `gkey` matches.
+  FrameBuf bgr[LM_MAX_LEVELS][LM_MAX_MODALITIES];       // CG pyramid sources for level >= 1
+  FrameBuf mag[LM_MAX_LEVELS][LM_MAX_MODALITIES];
+  FrameBuf quant_raw[LM_MAX_LEVELS][LM_MAX_MODALITIES];
+  FrameBuf quantized[LM_MAX_LEVELS][LM_MAX_MODALITIES];
+  DevBuf spread[LM_MAX_LEVELS][LM_MAX_MODALITIES], response[LM_MAX_LEVELS][LM_MAX_MODALITIES];  // parity taps only (frame 0)
+  FrameBuf lmem[LM_MAX_LEVELS];                        // [M][8][plane_stride] byte planes + slack: only for the parity taps and
+                                                       // for levels whose nibble rows are not word-aligned (packed from here)
+  FrameBuf lmn[LM_MAX_LEVELS];                         // [M][8][plane_stride / 2] nibble-packed planes + slack: what the
+                                                       // matching kernels read
+  DevBuf ctl;                                          // BatchCtl: frame table, dispenser / counters (k_begin_chunk)
+  // The GPU work of one chunk (front end, coarse, refine) as an instantiated CUDA graph per launch geometry (frames in
+  // the grid, rounded up to a power of two): replayed instead of ~20 runtime calls per chunk.  Valid while `key` matches.
   struct GraphKey {
-    const void* plan; const void* plan_recs; const void* cand; const void* result; const void* src[LM_MAX_MODALITIES];
-    uint64_t model_version; int rows, cols, n_q, n_tiles, variant, prune, frontend, shard_rank, shard_world; uint32_t cand_cap, out_cap;
+    const void* plan; const void* plan_recs; const void* cand; const void* result; const void* lmn0; const void* ctl;
+    uint64_t model_version; int rows, cols, n_q, n_tiles, prune, shard_rank, shard_world, ws_frames; uint32_t cand_cap, out_cap;
     float thr[LM_MAX_QUERIES];
   };
-  cudaGraphExec_t gexec = nullptr;
-  GraphKey gkey;
-  int graph_launches = 0;
+  struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    GraphKey key;
+    int launches = 0;
+  } graph[LM_GRAPH_SLOTS];
   bool graph_broken = false;  // capture failed once on this lane: stay on the eager path
   // matching
   DevBuf cand, work, work_order, dump, dbg_recs;
-  DevBuf mod_bits;  // per modality: orientation bits set in the coarsest level's spread image (front end -> coarse kernel hint)
-  struct Ref {  // this lane's result block inside the detector-wide allocation (lm_detector::results_all)
-    void* p = nullptr;
-    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-  } result;
+  FrameBuf result;            // per frame: [16 B statistics][ResultHeader][out_cap x lm_raw_match]
   uint32_t cand_cap = 0, out_cap = 0;
   PinBuf stage_in, stage_out;
-  // last-call bookkeeping
+  // last-call bookkeeping (frame 0 of the last chunk)
   float ms[5] = {0, 0, 0, 0, 0};
   int launches = 0;
   uint64_t work_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::vector<lm_match_rec> presort;
 
+  void drop_graphs() {
+    for (int i = 0; i < LM_GRAPH_SLOTS; ++i)
+      if (graph[i].exec) { cudaGraphExecDestroy(graph[i].exec); graph[i].exec = nullptr; }
+  }
   int init() {
     CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     for (int i = 0; i < 6; ++i) CU(cudaEventCreate(&ev[i]));
     CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    if (mod_bits.ensure(sizeof(unsigned int) * LM_MAX_MODALITIES) != LM_OK) return LM_E_CUDA;
+    if (ctl.ensure(sizeof(BatchCtl)) != LM_OK) return LM_E_CUDA;
+    CU(cudaMemset(ctl.p, 0, sizeof(BatchCtl)));
     for (int i = 0; i < LM_MAX_MODALITIES - 1; ++i) {
       CU(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
       CU(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
@@ -145,7 +179,7 @@ struct Lane {
   }
   void destroy() {
     for (int m = 0; m < LM_MAX_MODALITIES; ++m) {
-      src[m].release(); mask0[m].release(); smoothed[m].release(); qunf[m].release(); dn_raw[m].release();
+      src[m].release(); mask0[m].release();
       for (int l = 0; l < LM_MAX_LEVELS; ++l) {
         bgr[l][m].release(); mag[l][m].release(); quant_raw[l][m].release(); quantized[l][m].release();
         spread[l][m].release(); response[l][m].release();
@@ -153,9 +187,10 @@ struct Lane {
     }
     for (int l = 0; l < LM_MAX_LEVELS; ++l) lmem[l].release();
     for (int l = 0; l < LM_MAX_LEVELS; ++l) lmn[l].release();
-    cand.release(); work.release(); work_order.release(); dump.release(); dbg_recs.release(); mod_bits.release();
+    cand.release(); work.release(); work_order.release(); dump.release(); dbg_recs.release(); ctl.release();
+    result.release();
     stage_in.release(); stage_out.release();
-    if (gexec) cudaGraphExecDestroy(gexec);
+    drop_graphs();
     for (int i = 0; i < 6; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
     if (ev_fork) cudaEventDestroy(ev_fork);
     for (int i = 0; i < LM_MAX_MODALITIES - 1; ++i) {
@@ -169,7 +204,7 @@ struct Lane {
 // Device-resident template records for one frame geometry.
 struct Pack {
   uint64_t version = 0;
-  int rows = 0, cols = 0, shard_rank = 0, shard_world = 1, variant = -1;
+  int rows = 0, cols = 0, shard_rank = 0, shard_world = 1;
   int n = 0;        // templates on this shard
   int max_P = 0;
   DevBuf ctpl, foff;
@@ -183,10 +218,10 @@ struct Pack {
   struct ClassRange { std::string id; int class_index; std::vector<uint32_t> local; std::vector<uint32_t> global_pos; };
   std::vector<ClassRange> classes;      // canonical order
   // Device-side description of one (multi-query) request: work items and coarse tiles.  Cached by the class lists.
-  struct Plan { DevBuf items, tiles, recs; int n_items = 0, n_tiles = 0, rec_words = 0; uint64_t coarse_bytes = 0, evals = 0; double refine_nf_sum = 0; };
+  struct Plan { DevBuf items, recs; int n_items = 0, n_tiles = 0, rec_words = 0; uint64_t coarse_bytes = 0, evals = 0; double refine_nf_sum = 0; };
   std::map<std::string, Plan> plans;
   void clear_filtered() {
-    for (auto& kv : plans) { kv.second.items.release(); kv.second.tiles.release(); kv.second.recs.release(); }
+    for (auto& kv : plans) { kv.second.items.release(); kv.second.recs.release(); }
     plans.clear();
   }
   void release() {
@@ -225,16 +260,15 @@ struct lm_detector {
   uint8_t sim_lut[256];
   uint8_t normal_lut[8000];
   DevBuf d_resp_all, d_normal_lut;
-  // result blocks of all lanes, contiguous (lane stride result_stride): a sharded caller exchanges the survivors of
-  // LM_LANES frames in flight with ONE collective over this region and no staging copies
-  DevBuf results_all;
-  size_t result_stride = 0;
-  uint32_t out_cap = 0, device_out_cap = 2048;
+  uint32_t device_out_cap = 2048;  // records per frame block on the device-resident paths
+  uint32_t cand_per_frame = 1u << 16;  // coarse candidates a chunk may produce, per frame of the chunk
   bool luts_dirty = true;
   Lane lane[LM_LANES];
   Pack pack;
   int shard_rank = 0, shard_world = 1;
-  int debug_taps = 0, coarse_variant = 0, refine_variant = 0, timing = 1, frontend_variant = 0, prune = 1, graphs = 1;
+  int debug_taps = 0, timing = 0, prune = 1, graphs = 1;
+  int batch_frames = 8;  // frames per chunk on the batched paths (lm_match_batch*, lm_match_device_stream)
+  int batch_lanes = 4;   // chunks in flight on the batched host path
   int mod_order = 2;  // coarse kernel: 0 = modalities in template order, 1 = reversed, 2 = chosen per frame (default)
   std::vector<std::string> class_id_cache;
 };
@@ -243,8 +277,12 @@ struct lm_detector {
 // (defined in lm_detector.cu)
 int set_device(lm_detector* d);                                         // binds the handle to its CUDA device; no CPU path
 int upload_luts(lm_detector* d);
-int ensure_quant_ws(lm_detector* d, Lane& ln, int rows, int cols);
-int run_quantize(lm_detector* d, Lane& ln, cudaStream_t main_stream);  // [OCV] Modality::process + pyrDown, every level
+int ensure_quant_ws(lm_detector* d, Lane& ln, int rows, int cols, int frames = 1);
+// Installs the frame table of the lane's current chunk (ln.src_ptr[0 .. n_frames)) and zeroes the chunk's counters and the
+// first `result_blocks` result headers: must precede the chunk's kernels on `s`.
+int begin_chunk(lm_detector* d, Lane& ln, int n_frames, int result_blocks, cudaStream_t s);
+// [OCV] Modality::process + pyrDown, every level, for grid_frames frame slots (frames beyond the table's count idle)
+int run_quantize(lm_detector* d, Lane& ln, int grid_frames, cudaStream_t main_stream);
 int upload_image(Lane& ln, const lm_image& im, void* dst, size_t* stage_off);
 bool is_pinned(const void* p);
 size_t src_row_bytes(int type, int cols);

@@ -1,4 +1,4 @@
-// lm_frontend_fused.cu -- the production front end: three launches per frame instead of fourteen.
+// lm_frontend_fused.cu -- the front end: four launches per CHUNK of frames (pyrDown, ColorGradient, DepthNormal, spread).
 //
 //   k_cg_fused    [OCV] quantizedOrientations + hysteresisGradient for every pyramid level in one grid:
 //                 GaussianBlur 7x7 -> Sobel 3x3 -> max-magnitude channel -> fastAtan2 -> 16-bin rounding -> 3x3 vote,
@@ -7,9 +7,11 @@
 //                 99-exchange median-of-25 network on packed u16x2 (VIMNMX.U16x2), NN decimation to all levels.
 //   k_spread_all  [OCV] quantize(mask) + spread + computeResponseMaps + linearize for every (level, modality).
 //
-// The front end is O(pixels) and tiny next to a B200 (7.7 MB of algorithmic traffic per 640x480 frame), so it is bound
-// by launch count and dependent-phase latency, not by bandwidth: fusing removes the global round trips between stages.
-// Arithmetic is identical to the stage-by-stage kernels in lm_frontend.cu (kept as the A/B reference).
+// The front end is O(pixels) and tiny next to a B200 (7.7 MB of algorithmic traffic per 640x480 frame): one frame's
+// grids (150 - 900 CTAs) are less than one wave, so a launch costs the latency of its dependent shared-memory phases
+// whatever its size.  Hence (i) the stages are fused (no global round trips between them) and (ii) every kernel takes a
+// chunk of frames -- blockIdx.y / .z is the frame, buffers at base + frame * stride, level-0 sources from the device
+// frame table -- so that a launch fills the machine for several waves.
 #include <float.h>
 
 #include <type_traits>
@@ -69,16 +71,21 @@ __global__ void __launch_bounds__(C_THREADS) k_cg_fused(const CgParams P) {
   static_assert(sizeof(uint32_t) * C_OH_ROWS * C_OH_W <= sizeof(s_v), "s_oh must fit in s_v");
   static_assert(sizeof(float) * C_TH * C_TW <= sizeof(s_src), "s_mag must fit in s_src");
 
+  const int frame = blockIdx.y;
+  if (frame >= P.ctl->ft.n_frames) return;
   int lvl = 0;
   while (lvl + 1 < P.n_levels && (int)blockIdx.x >= P.lv[lvl + 1].block_begin) ++lvl;
-  const uint8_t* __restrict__ src = P.lv[lvl].src;
+  const uint8_t* __restrict__ src = lvl == 0 ? static_cast<const uint8_t*>(P.ctl->ft.src[frame][P.modality])
+                                             : P.lv[lvl].src + (size_t)frame * P.lv[lvl].src_stride;
+  float* __restrict__ mag_out = P.lv[lvl].mag + (size_t)frame * P.lv[lvl].mag_stride;
+  uint8_t* __restrict__ quant_out = P.lv[lvl].quant + (size_t)frame * P.lv[lvl].quant_stride;
   const int rows = P.lv[lvl].rows, cols = P.lv[lvl].cols;
   const int b = blockIdx.x - P.lv[lvl].block_begin;
   const int x0 = (b % P.lv[lvl].blocks_x) * C_TW, y0 = (b / P.lv[lvl].blocks_x) * C_TH;
   const int tid = threadIdx.x;
 
   // ---- A: source tile
-  if ((cols & 3) == 0 && x0 >= C_TW && x0 + 71 <= cols) {
+  if ((cols & 3) == 0 && x0 >= C_TW && x0 + 71 <= cols && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
     const uint8_t* base = src + (size_t)3 * x0 - 16;  // 4-byte aligned: cols % 4 == 0 and x0 % 64 == 0
     for (int i = tid; i < C_SRC_ROWS * C_SRC_WORDS; i += C_THREADS) {
       const int r = i / C_SRC_WORDS, w = i - r * C_SRC_WORDS;
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(C_THREADS) k_cg_fused(const CgParams P) {
       const int gx = x0 - 1 + jx;
       if (jx >= 1 && jx <= C_TW) {
         s_mag[keep_r - 1][jx - 1] = mag_keep[k];
-        if (gy < rows && gx < cols) P.lv[lvl].mag[(size_t)gy * cols + gx] = mag_keep[k];
+        if (gy < rows && gx < cols) mag_out[(size_t)gy * cols + gx] = mag_keep[k];
       }
     }
   }
@@ -244,9 +251,9 @@ __global__ void __launch_bounds__(C_THREADS) k_cg_fused(const CgParams P) {
       const bool inner = gy >= 1 && gy < rows - 1 && gx >= 1 && gx < cols - 1;
       if (inner && mags[k] > P.thr_sq && five != 0) packed |= (1u << ((__ffs((int)five) - 1) >> 2)) << (8 * k);
     }
-    uint8_t* qrow = P.lv[lvl].quant + (size_t)gy * cols;
+    uint8_t* qrow = quant_out + (size_t)gy * cols;
     if (gy < rows) {
-      if ((cols & 3) == 0 && gx0 + 3 < cols) *reinterpret_cast<uint32_t*>(qrow + gx0) = packed;
+      if ((cols & 3) == 0 && gx0 + 3 < cols) *reinterpret_cast<uint32_t*>(qrow + gx0) = packed;  // quant strides are multiples of 4
       else
         for (int k = 0; k < 4; ++k)
           if (gx0 + k < cols) qrow[gx0 + k] = (uint8_t)(packed >> (8 * k));
@@ -267,14 +274,19 @@ __device__ __forceinline__ int reflect101_f(int p, int len) {
   return p;
 }
 
-__global__ void __launch_bounds__(256) k_pyrdown_fast(const uint8_t* __restrict__ src, int rows, int cols,
-                                                      uint8_t* __restrict__ dst) {
+__global__ void __launch_bounds__(256) k_pyrdown_fast(const BatchCtl* __restrict__ ctl, int modality,
+                                                      const uint8_t* __restrict__ src0, size_t src_stride, int rows, int cols,
+                                                      uint8_t* __restrict__ dst0, size_t dst_stride) {
   __shared__ __align__(16) uint32_t s_src[Y_SRC_ROWS][Y_SRC_WORDS];   // region pixel i <-> source x 2*x0-2+i, channel c at byte 2+3i+c
   __shared__ __align__(16) uint16_t s_v[Y_TH][Y_SRC_WORDS * 4];
+  const int frame = blockIdx.z;
+  if (frame >= ctl->ft.n_frames) return;
+  const uint8_t* __restrict__ src = src0 ? src0 + (size_t)frame * src_stride : static_cast<const uint8_t*>(ctl->ft.src[frame][modality]);
+  uint8_t* __restrict__ dst = dst0 + (size_t)frame * dst_stride;
   const int orows = rows / 2, ocols = cols / 2;
   const int x0 = blockIdx.x * Y_TW, y0 = blockIdx.y * Y_TH;
   const int tid = threadIdx.x;
-  if ((cols & 3) == 0 && x0 >= Y_TW && 2 * x0 + 130 <= cols) {
+  if ((cols & 3) == 0 && x0 >= Y_TW && 2 * x0 + 130 <= cols && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
     const uint8_t* base = src + (size_t)6 * x0 - 8;  // 4-byte aligned
     for (int i = tid; i < Y_SRC_ROWS * Y_SRC_WORDS; i += 256) {
       const int r = i / Y_SRC_WORDS, w = i - r * Y_SRC_WORDS;
@@ -392,16 +404,17 @@ __device__ __forceinline__ void cswap_u16x2(uint32_t& a, uint32_t& b) {
 }
 
 template <bool FAST>
-__device__ __forceinline__ void dn_tile(const DnParams& P, int bx, int by) {
+__device__ __forceinline__ void dn_tile(const DnParams& P, int bx, int by, int frame) {
   __shared__ __align__(4) uint8_t s_raw[D_TH + 4][D_TW + 8];
   const int rows = P.rows, cols = P.cols;
+  const uint16_t* __restrict__ depth = static_cast<const uint16_t*>(P.ctl->ft.src[frame][P.modality]);
   const int x0 = bx * D_TW, y0 = by * D_TH;
   const int tid = threadIdx.x;
   // raw quantised normals for the tile + halo 2; medianBlur's BORDER_REPLICATE = value at the clamped coordinate
   for (int i = tid; i < (D_TH + 4) * (D_TW + 4); i += 256) {
     const int r = i / (D_TW + 4), c = i - r * (D_TW + 4);
     const int gy = clampi(y0 - 2 + r, 0, rows - 1), gx = clampi(x0 - 2 + c, 0, cols - 1);
-    s_raw[r][c] = dn_normal_at<FAST>(P.depth, rows, cols, gy, gx, P.distance_threshold, P.difference_threshold, P.lut);
+    s_raw[r][c] = dn_normal_at<FAST>(depth, rows, cols, gy, gx, P.distance_threshold, P.difference_threshold, P.lut);
   }
   __syncthreads();
   // median of 25 for two horizontally adjacent pixels at once (one per 16-bit lane)
@@ -431,22 +444,24 @@ __device__ __forceinline__ void dn_tile(const DnParams& P, int bx, int by) {
       const int gx = x0 + c + k;
       if (gy >= rows || gx >= cols) continue;
       const uint8_t v = (uint8_t)(k ? (med >> 16) : (med & 0xffffu));
-      P.quant[0][(size_t)gy * cols + gx] = v;
+      P.quant[0][(size_t)frame * P.quant_stride[0] + (size_t)gy * cols + gx] = v;
       // [OCV] DepthNormalPyramid::pyrDown: level l is the NN decimation src(2^l y, 2^l x) of the level-0 map
 #pragma unroll
       for (int l = 1; l < LM_MAX_LEVELS; ++l) {
         const int mask = (1 << l) - 1;
         if (l >= P.n_levels || (gy & mask) || (gx & mask)) break;
         const int lr = rows >> l, lc = cols >> l;
-        if ((gy >> l) < lr && (gx >> l) < lc) P.quant[l][(size_t)(gy >> l) * lc + (gx >> l)] = v;
+        if ((gy >> l) < lr && (gx >> l) < lc) P.quant[l][(size_t)frame * P.quant_stride[l] + (size_t)(gy >> l) * lc + (gx >> l)] = v;
       }
     }
   }
 }
 
 __global__ void __launch_bounds__(256) k_dn_fused(const DnParams P) {
-  if (P.difference_threshold <= 200) dn_tile<true>(P, blockIdx.x, blockIdx.y);
-  else dn_tile<false>(P, blockIdx.x, blockIdx.y);
+  const int frame = blockIdx.z;
+  if (frame >= P.ctl->ft.n_frames) return;
+  if (P.difference_threshold <= 200) dn_tile<true>(P, blockIdx.x, blockIdx.y, frame);
+  else dn_tile<false>(P, blockIdx.x, blockIdx.y, frame);
 }
 
 // ---------------------------------------------------------------------------------------------- spread -> LM
@@ -469,7 +484,7 @@ __device__ __forceinline__ void transpose4x4(const uint32_t (&in)[4], uint32_t (
 }
 
 template <int TT>
-__device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadEntry& E, uint8_t* smem) {
+__device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadEntry& E, uint8_t* smem, int frame) {
   const int T = TT ? TT : E.T;
   const int W = E.W, H = E.H, rows = E.rows, cols = E.cols;
   const int IH = 2 * T - 1, NWO = sp_nwo(T), NWQ = sp_nwq(T);
@@ -481,8 +496,11 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
   const int c0 = (b % E.blocks_x) * SP_CW, a = b / E.blocks_x;
   const int px0 = c0 * T, py0 = a * T;
   const int tid = threadIdx.x;
-  const uint8_t* __restrict__ qraw = E.qraw;
+  const uint8_t* __restrict__ qraw = E.qraw + (size_t)frame * E.qraw_stride;
+  uint8_t* __restrict__ quantized = E.quantized + (size_t)frame * E.quantized_stride;
   const uint8_t* __restrict__ mask0 = E.mask0;
+  uint8_t* tap_spread = frame == 0 ? E.spread : nullptr;
+  uint8_t* tap_response = frame == 0 ? E.response : nullptr;
   s_resp[tid] = P.resp_all[tid];
   // ---- masked quantisation, four pixels per word; pixels outside the image are 0 ([OCV] spread stays in bounds)
   const bool fast = mask0 == nullptr && (cols & 3) == 0;
@@ -494,7 +512,7 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
     if (fast) {
       if (gy < rows && gx < cols) {
         v = __ldg(reinterpret_cast<const uint32_t*>(qraw + (size_t)gy * cols + gx));
-        if (own) *reinterpret_cast<uint32_t*>(E.quantized + (size_t)gy * cols + gx) = v;
+        if (own) *reinterpret_cast<uint32_t*>(quantized + (size_t)gy * cols + gx) = v;
       }
     } else if (gy < rows) {
 #pragma unroll
@@ -503,7 +521,7 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
         if (x < cols) {
           uint32_t q = qraw[(size_t)gy * cols + x];
           if (mask0 && !mask0[(size_t)(gy << E.level) * E.mask_cols0 + (x << E.level)]) q = 0;
-          if (own) E.quantized[(size_t)gy * cols + x] = (uint8_t)q;
+          if (own) quantized[(size_t)gy * cols + x] = (uint8_t)q;
           v |= q << (8 * k);
         }
       }
@@ -541,18 +559,18 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
     }
     sp[i] = v;
     n_bits += __popc(v);
-    if (E.spread) {
+    if (tap_spread) {
       const int gy = py0 + r;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int gx = px0 + 4 * wi + k;
-        if (gy < rows && gx < cols) E.spread[(size_t)gy * cols + gx] = (uint8_t)(v >> (8 * k));
+        if (gy < rows && gx < cols) tap_spread[(size_t)gy * cols + gx] = (uint8_t)(v >> (8 * k));
       }
     }
   }
-  if (E.bits != nullptr) {  // a performance hint for the coarse kernel, not a result: see SpreadEntry::bits
+  if (E.count_bits) {  // a performance hint for the coarse kernel, not a result: see SpreadEntry::count_bits
     n_bits = __reduce_add_sync(0xffffffffu, n_bits);
-    if ((tid & 31) == 0 && n_bits) atomicAdd(E.bits, n_bits);
+    if ((tid & 31) == 0 && n_bits) atomicAdd(&P.ctl->mod_bits[frame][E.modality], n_bits);
   }
   __syncthreads();
   // ---- responses -> linear memories
@@ -578,7 +596,7 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
       transpose4x4(ev, oe);  // oe[k]: orientation 2k, nibbles = cells 0..7
       transpose4x4(od, oo);  // oo[k]: orientation 2k+1
       const size_t n0 = (size_t)g * WH + (size_t)a * W + c0 + b8 * 8;  // nibble index inside the plane (multiple of 8)
-      uint8_t* dst = E.lm_nib + n0 / 2;
+      uint8_t* dst = E.lm_nib + (size_t)frame * E.lm_nib_stride + n0 / 2;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         *reinterpret_cast<uint32_t*>(dst + (size_t)(2 * k) * nib_stride) = oe[k];
@@ -586,7 +604,7 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
       }
     }
   }
-  uint8_t* __restrict__ lm = E.lm;
+  uint8_t* __restrict__ lm = E.lm ? E.lm + (size_t)frame * E.lm_stride : nullptr;
   if (lm != nullptr) {
     if ((W & 3) == 0) {
       for (int it = tid; it < T * T * (SP_CW / 4); it += 256) {
@@ -623,7 +641,7 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
       }
     }
   }
-  if (E.response) {
+  if (tap_response) {
     for (int i = tid; i < T * NWO * 4; i += 256) {
       const int r = i / (NWO * 4), x = i - r * (NWO * 4);
       const int gy = py0 + r, gx = px0 + x;
@@ -631,7 +649,7 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
         const uint32_t r0 = s_resp[spb[r * row_bytes + x]];
 #pragma unroll
         for (int ori = 0; ori < 8; ++ori)
-          E.response[(size_t)ori * rows * cols + (size_t)gy * cols + gx] = (uint8_t)((r0 >> (4 * ori)) & 15);
+          tap_response[(size_t)ori * rows * cols + (size_t)gy * cols + gx] = (uint8_t)((r0 >> (4 * ori)) & 15);
       }
     }
   }
@@ -639,12 +657,14 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
 
 __global__ void __launch_bounds__(256) k_spread_all(const SpreadParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
+  const int frame = blockIdx.y;
+  if (frame >= P.ctl->ft.n_frames) return;
   int ei = 0;
   while (ei + 1 < P.n && (int)blockIdx.x >= P.e[ei + 1].block_begin) ++ei;
   const SpreadEntry& E = P.e[ei];
-  if (E.T == 5) spread_tile<5>(P, E, smem);        // the reference trainer's T pyramid {5, 8}
-  else if (E.T == 8) spread_tile<8>(P, E, smem);
-  else spread_tile<0>(P, E, smem);
+  if (E.T == 5) spread_tile<5>(P, E, smem, frame);        // the reference trainer's T pyramid {5, 8}
+  else if (E.T == 8) spread_tile<8>(P, E, smem, frame);
+  else spread_tile<0>(P, E, smem, frame);
 }
 
 size_t spread_all_smem(int T) {
@@ -659,25 +679,26 @@ int cg_fused_blocks(int rows, int cols, int* blocks_x) {
   *blocks_x = (cols + C_TW - 1) / C_TW;
   return *blocks_x * ((rows + C_TH - 1) / C_TH);
 }
-void launch_cg_fused(const CgParams& p, int total_blocks, cudaStream_t s) {
-  k_cg_fused<<<total_blocks, C_THREADS, 0, s>>>(p);
+void launch_cg_fused(const CgParams& p, int total_blocks, int n_frames, cudaStream_t s) {
+  k_cg_fused<<<dim3(total_blocks, n_frames), C_THREADS, 0, s>>>(p);
 }
-void launch_dn_fused(const DnParams& p, cudaStream_t s) {
-  dim3 grid((p.cols + D_TW - 1) / D_TW, (p.rows + D_TH - 1) / D_TH);
+void launch_dn_fused(const DnParams& p, int n_frames, cudaStream_t s) {
+  dim3 grid((p.cols + D_TW - 1) / D_TW, (p.rows + D_TH - 1) / D_TH, n_frames);
   k_dn_fused<<<grid, 256, 0, s>>>(p);
 }
-void launch_pyrdown_fast(const uint8_t* src, int rows, int cols, uint8_t* dst, cudaStream_t s) {
-  dim3 grid((cols / 2 + Y_TW - 1) / Y_TW, (rows / 2 + Y_TH - 1) / Y_TH);
-  k_pyrdown_fast<<<grid, 256, 0, s>>>(src, rows, cols, dst);
+void launch_pyrdown_fast(const BatchCtl* ctl, int modality, const uint8_t* src, size_t src_stride, int rows, int cols,
+                         uint8_t* dst, size_t dst_stride, int n_frames, cudaStream_t s) {
+  dim3 grid((cols / 2 + Y_TW - 1) / Y_TW, (rows / 2 + Y_TH - 1) / Y_TH, n_frames);
+  k_pyrdown_fast<<<grid, 256, 0, s>>>(ctl, modality, src, src_stride, rows, cols, dst, dst_stride);
 }
 int spread_all_blocks(int W, int H, int* blocks_x) {
   *blocks_x = (W + SP_CW - 1) / SP_CW;
   return *blocks_x * H;
 }
-bool launch_spread_all(const SpreadParams& p, int total_blocks, int max_T, cudaStream_t s) {
+bool launch_spread_all(const SpreadParams& p, int total_blocks, int max_T, int n_frames, cudaStream_t s) {
   size_t smem = spread_all_smem(max_T);
   if (smem > 48 * 1024) return false;  // T <= 16 (checked by the host) needs 41 KB
-  k_spread_all<<<total_blocks, 256, smem, s>>>(p);
+  k_spread_all<<<dim3(total_blocks, n_frames), 256, smem, s>>>(p);
   return true;
 }
 

@@ -14,12 +14,14 @@
 //   k_train_cg, k_train_dn_pb/dist/keys         [OCV] ColorGradientPyramid / DepthNormalPyramid::extractTemplate candidates
 //   k_train_sort, k_train_select                [OCV] std::stable_sort + QuantizedPyramid::selectScatteredFeatures
 //   k_depth_diff, k_mask_rect                   rgbdDetector::depth_diff; mask bounding boxes
-//   A/B references and fallbacks (same results, selected with lm_set_option)
-//   k_gauss7_u8c3, k_cg_grad, k_cg_hysteresis, k_pyrdown_u8c3, k_dn_normals, k_median5_u8, k_nn_half_u8, k_spread_lm
-//                                               the front end stage by stage            (frontend_variant = 1)
-//   k_similarity_coarse, k_similarity_coarse_nib<4>   coarse scan on byte / nibble planes without tile records (coarse_variant = 1 / 2)
-//   k_refine                                    refinement on byte planes (refine_variant = 1, or rows not word-aligned)
-//   k_pack_nibbles                              byte planes -> nibble planes when the spread kernel could not write them
+//   k_begin_chunk                               per launch set: frame table (source pointers of the chunk's frames), zeroed
+//                                               result headers / counters -- everything that changes between replays of a
+//                                               lane's CUDA graph
+//   k_pack_nibbles                              byte planes -> nibble planes for levels whose rows are not word-aligned
+//
+// Every kernel of the matching path takes a CHUNK of frames: blockIdx.y / .z (front end), the virtual tile index (coarse)
+// or the candidate's frame tag (refinement) select the frame, whose buffers lie at base + frame * stride; the level-0
+// sources come from the device-resident FrameTable.  A single-frame call is a chunk of one.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -47,8 +49,8 @@ struct RefineTpl {                        // one per (level < L-1, template)
 };
 
 struct RefineLevel {
-  const uint8_t* lm;                      // [M][8][plane_stride] byte planes (valid when the byte kernel is used)
-  const uint8_t* lmn;                     // [M][8][plane_stride / 2] nibble-packed planes (valid when the nibble kernel is used)
+  const uint8_t* lmn;                     // [M][8][plane_stride / 2] nibble-packed planes of frame 0
+  unsigned long long frame_stride;        // bytes between the planes of consecutive frames of the chunk
   const RefineTpl* tpl;
   const uint32_t* feats;                  // (x + 4096) | (y + 4096) << 13 | label << 26
   unsigned long long plane_stride;
@@ -71,106 +73,128 @@ struct WorkItem {                         // one template of one query of the re
 };
 
 struct Cand {                             // coarse candidate: raw score above the template's raw threshold
-  uint32_t tglob, pos;                    // template index in the pack, raster position at the coarsest level
+  uint32_t tglob, pos;                    // template index in the pack; raster position at the coarsest level (bits 0-23,
+                                          // <= 4095^2) | frame of the chunk << 24
   uint32_t raw_nf;                        // raw score (u16) | number of features behind it << 16
   uint32_t order;                         // the work item's emission order key (query << 28 | position in the iteration)
 };
 
-struct ResultHeader {                     // zeroed before every request
+struct ResultHeader {                     // one per frame, zeroed before every request (k_begin_chunk)
   uint32_t count;                         // surviving matches written (may exceed the capacity: overflow)
-  uint32_t next_tile;                     // coarse kernel's tile dispenser
-  uint32_t overflow, n_cands;
+  uint32_t reserved;
+  uint32_t overflow, n_cands;             // n_cands: coarse candidates of this frame (counted by the refinement kernel)
+};
+
+#define LM_MAX_BATCH 32                   // frames per launch set (chunk)
+
+struct FrameTable {                       // the frames of one launch set
+  int32_t n_frames, pad[3];
+  const void* src[LM_MAX_BATCH][LM_MAX_MODALITIES];  // level-0 sources, tightly packed rows, device memory
+};
+
+struct BatchCtl {                         // device-resident, one per workspace lane; rewritten by k_begin_chunk
+  FrameTable ft;
+  uint32_t next_tile, n_cands, overflow, pad;        // coarse kernel: tile dispenser, chunk-wide candidate count
+  unsigned int mod_bits[LM_MAX_BATCH][LM_MAX_MODALITIES];  // per frame and modality: orientation bits set in the coarsest
+                                                           // level's spread image (front end -> coarse kernel hint)
 };
 
 // ------------------------------------------------------------------------------------------------ front end
-void launch_gauss7_u8c3(const uint8_t* src, int rows, int cols, uint8_t* dst, cudaStream_t s);
-void launch_cg_grad(const uint8_t* smoothed, int rows, int cols, float* mag, uint8_t* qunf, cudaStream_t s);
-void launch_cg_hysteresis(const uint8_t* qunf, const float* mag, int rows, int cols, float threshold_sq, uint8_t* quant,
-                          cudaStream_t s);
-void launch_pyrdown_u8c3(const uint8_t* src, int rows, int cols, uint8_t* dst, cudaStream_t s);
-void launch_dn_normals(const uint16_t* depth, int rows, int cols, int distance_threshold, int difference_threshold,
-                       const uint8_t* normal_lut, uint8_t* out, cudaStream_t s);
-void launch_median5_u8(const uint8_t* src, int rows, int cols, uint8_t* dst, cudaStream_t s);
-void launch_nn_half_u8(const uint8_t* src, int rows, int cols, uint8_t* dst, cudaStream_t s);
-// mask0: level-0 mask (nullable) sampled at (y << level, x << level); resp_all: 256 x u32, 8 response nibbles per
-// spread value.  quantized_out always written; spread_out / response_out only when non-null (parity taps).
-void launch_spread_lm(const uint8_t* quant_raw, const uint8_t* mask0, int mask_cols0, int level, int rows, int cols,
-                      int T, const uint32_t* resp_all, uint8_t* quantized_out, uint8_t* spread_out,
-                      uint8_t* response_out, uint8_t* lm, size_t plane_stride, cudaStream_t s);
-
-// ------------------------------------------------------------------------------------------------ fused front end
+// Buffers of frame f of a chunk lie at base + f * stride (strides in ELEMENTS of the pointer's type); the level-0 source
+// of modality `modality` is ctl->ft.src[f][modality].  Blocks of frames >= ctl->ft.n_frames exit at once, so one recorded
+// launch geometry (a lane's CUDA graph) serves every chunk size up to the grid's frame count.
 struct CgLevel {
-  const uint8_t* src;  // BGR source of this level (level >= 1: output of k_pyrdown_u8c3)
+  const uint8_t* src;  // BGR source of this level for levels >= 1 (output of k_pyrdown_fast); level 0 comes from the table
   float* mag;          // [rows][cols] squared gradient magnitude (exact integer in f32)
   uint8_t* quant;      // [rows][cols] one-hot quantised orientation (unmasked)
+  unsigned long long src_stride, mag_stride, quant_stride;
   int rows, cols, block_begin, blocks_x;
 };
 struct CgParams {
   CgLevel lv[LM_MAX_LEVELS];
-  int n_levels;
+  const BatchCtl* ctl;
+  int n_levels, modality;
   float thr_sq;  // weak_threshold^2
 };
 struct DnParams {
-  const uint16_t* depth;
+  const BatchCtl* ctl;
   const uint8_t* lut;  // NORMAL_LUT, 8000 bytes
   uint8_t* quant[LM_MAX_LEVELS];
-  int rows, cols, n_levels, distance_threshold, difference_threshold;
+  unsigned long long quant_stride[LM_MAX_LEVELS];
+  int rows, cols, n_levels, modality, distance_threshold, difference_threshold;
 };
 struct SpreadEntry {
   const uint8_t* qraw;   // unmasked quantisation of this (level, modality)
-  const uint8_t* mask0;  // level-0 mask or null
+  const uint8_t* mask0;  // level-0 mask or null (single-frame requests only)
   uint8_t* quantized;    // masked quantisation (Detector::match's quantized_images)
-  uint8_t* spread;       // parity tap or null
-  uint8_t* response;     // parity tap or null
-  uint8_t* lm;           // this modality's 8 orientation byte planes, or null (coarsest level when only lm_nib is needed)
-  uint8_t* lm_nib;       // coarsest level: this modality's 8 nibble-packed planes (plane_stride / 2 bytes each), or null
-  unsigned int* bits;    // coarsest level: += orientation bits set in this modality's spread image (null: not counted);
+  uint8_t* spread;       // parity tap or null (frame 0 only)
+  uint8_t* response;     // parity tap or null (frame 0 only)
+  uint8_t* lm;           // this modality's 8 orientation byte planes, or null when only lm_nib is needed
+  uint8_t* lm_nib;       // this modality's 8 nibble-packed planes (plane_stride / 2 bytes each), or null
+  int count_bits;        // coarsest level: ctl->mod_bits[frame][modality] += orientation bits set in the spread image;
                          // the coarse kernel starts with the modality that has fewer (lower responses, earlier pruning)
   unsigned long long plane_stride;
-  int rows, cols, T, W, H, level, mask_cols0, block_begin, blocks_x;
+  unsigned long long qraw_stride, quantized_stride, lm_stride, lm_nib_stride;  // per frame, bytes
+  int rows, cols, T, W, H, level, modality, mask_cols0, block_begin, blocks_x;
 };
 struct SpreadParams {
   SpreadEntry e[LM_MAX_LEVELS * LM_MAX_MODALITIES];
   const uint32_t* resp_all;
+  BatchCtl* ctl;
   int n;
 };
-void launch_pyrdown_fast(const uint8_t* src, int rows, int cols, uint8_t* dst, cudaStream_t s);
+// Per launch set, outside the lane's CUDA graph: installs the frame table, zeroes the coarse kernel's dispenser and
+// counters and the (statistics + header) prefix of the first n_blocks result blocks (results + i * result_stride).
+void launch_begin_chunk(const FrameTable& ft, BatchCtl* ctl, uint8_t* results, size_t result_stride, int n_blocks,
+                        cudaStream_t s);
+// src: level-0 source of modality `modality` when null (frame table), else the previous pyramid level at src + f * src_stride
+void launch_pyrdown_fast(const BatchCtl* ctl, int modality, const uint8_t* src, size_t src_stride, int rows, int cols,
+                         uint8_t* dst, size_t dst_stride, int n_frames, cudaStream_t s);
 int cg_fused_blocks(int rows, int cols, int* blocks_x);
-void launch_cg_fused(const CgParams& p, int total_blocks, cudaStream_t s);
-void launch_dn_fused(const DnParams& p, cudaStream_t s);
+void launch_cg_fused(const CgParams& p, int total_blocks, int n_frames, cudaStream_t s);
+void launch_dn_fused(const DnParams& p, int n_frames, cudaStream_t s);
 int spread_all_blocks(int W, int H, int* blocks_x);
-bool launch_spread_all(const SpreadParams& p, int total_blocks, int max_T, cudaStream_t s);
+bool launch_spread_all(const SpreadParams& p, int total_blocks, int max_T, int n_frames, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------ matching
-// tiles: (work item, pass) pairs with at least one position, heaviest first.  dump (nullable): u16 totals,
-// [work item][dump_stride], written for every scored position (parity tap).
-// variant: 0 = nibble-packed linear memories, self-contained tile records, exact early termination (production;
-// prune = 0 switches the early termination off, `touched` (nullable) accumulates the (feature, position) pairs gathered); 2 = nibble-packed, two overlapping vector loads per feature; 1 = byte linear memories.  2 and 1 are the
-// A/B references and read the (items, tiles, tpl, foff) arrays; 0 reads `recs`.
-// lmc: byte planes, lmn: nibble-packed planes of the coarsest level.
+// Coarse similarity of a chunk of frames against the request's tile records, one launch.  Virtual tile v = frame *
+// n_tiles + tile (frame-major: at any time nearly every SM reads the same frame's linear memories, and the tail of one
+// frame -- the dependent-load chain of the tiles that survive every pruning test -- overlaps the head of the next).
 //
-// Tile record of variant 0 (rec_words 32-bit words each, 16-byte aligned):
+// Tile record (rec_words 32-bit words each, 16-byte aligned), one per (work item, 1 024-position pass), heaviest first:
 //   [0] work item  [1] template index in the pack  [2] nf | query << 28  [3] number of feature words
 //   [4] j0 = first position of the pass  [5] positions in the pass  [6] the item's order key  [7] 0  [8..11] per modality: 4 class sizes, u8 each
 //   [12..] feature words, modality-major, grouped by class Q = (a >> 3) & 3 where a = nibble index of the window of
 //   lane 0: ((a >> 1) & ~15) | (a & 7)  -- aligned chunk byte offset | nibble shift
+//
+// `prune` bits: bit 0 = exact early termination; bit 8 = sum the modalities in reverse order; bit 9 = pick the order per
+// frame: reversed when mod_bits[f][M-1] < mod_bits[f][0] (fewer orientation bits = lower responses = earlier termination).
+// dump (nullable, single frame): u16 totals [work item][dump_stride] of every scored position (parity tap; disables pruning).
+struct CoarseParams {
+  const uint8_t* lmn;                     // coarsest level's nibble planes of frame 0
+  unsigned long long lmn_stride;          // bytes between frames
+  const uint32_t* recs;
+  BatchCtl* ctl;
+  Cand* cand;                             // chunk-wide candidate list
+  unsigned long long* touched;            // (feature, position) pairs gathered by the launch (statistics), nullable
+  uint16_t* dump;
+  QueryThresholds thr;
+  uint32_t cand_cap;
+  int rec_words, n_tiles, M, prune, dump_stride;
+};
 void set_programmatic_launch(bool enabled);  // per thread; disabled while launches are recorded into a CUDA graph
 void set_coarse_grid_limit(int blocks);     // process-wide; 0 = no limit
-int coarse_positions_per_pass(int variant);
+int coarse_positions_per_pass();
 int coarse_record_header_words();
 int coarse_record_max_words();
-void launch_similarity_coarse(int variant, const uint8_t* lmc, const uint8_t* lmn, const uint32_t* foff,
-                              const CoarseTpl* tpl, const WorkItem* items, const uint2* tiles, const uint32_t* recs,
-                              int rec_words, int n_tiles, const QueryThresholds& thr, int M, int prune, Cand* cand,
-                              ResultHeader* hdr, unsigned long long* touched, uint32_t cand_cap, uint16_t* dump,
-                              int dump_stride, cudaStream_t s, const unsigned int* mod_bits = nullptr);
-// `prune` bits for variant 0: bit 0 = exact early termination; bit 8 = sum the modalities in reverse order; bit 9 = pick
-// the order per frame: reversed when mod_bits[M-1] < mod_bits[0] (mod_bits[m] = orientation bits set in modality m's
-// spread image at the coarsest level, counted by the front end: fewer bits = lower responses = earlier termination).
-// n_bytes (multiple of 16) of byte planes -> n_bytes / 2 of nibble-packed planes
-void launch_pack_nibbles(const uint8_t* lm_bytes, uint8_t* lm_nibbles, size_t n_bytes, cudaStream_t s);
-void launch_refine(bool nibble_planes, const RefineParams& p, const CoarseTpl* ctpl, const WorkItem* items, const Cand* cand,
-                   uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* out, uint32_t out_cap, cudaStream_t s);
+void launch_similarity_coarse(const CoarseParams& p, int max_frames, cudaStream_t s);
+// n_bytes (multiple of 16) of byte planes -> n_bytes / 2 of nibble-packed planes, for n_frames frames
+void launch_pack_nibbles(const uint8_t* lm_bytes, size_t bytes_stride, uint8_t* lm_nibbles, size_t nib_stride, size_t n_bytes,
+                         const BatchCtl* ctl, int n_frames, cudaStream_t s);
+// Refinement of every candidate of the chunk; survivors of frame f go to the result block results + f * result_stride
+// ([16 B statistics][ResultHeader][out_cap x lm_raw_match]).
+void launch_refine(const RefineParams& p, const CoarseTpl* ctpl, const Cand* cand, uint32_t cand_cap, BatchCtl* ctl,
+                   uint8_t* results, size_t result_stride, uint32_t out_cap, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------ rendering (lm_render.cu)
 struct RenderView {                       // Pc = R * Po + t, OpenCV camera convention (x right, y down, z forward)

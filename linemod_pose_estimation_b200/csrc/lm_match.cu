@@ -12,340 +12,30 @@
 // _mm_add_epi8 (and to __vaddus4) at a quarter of the instruction count.
 #include <string.h>
 
+#include <algorithm>
+
 #include "lm_kernels.cuh"
 
 namespace lmk {
 
 namespace {
 
-constexpr int kLanePos = 16;             // positions per lane and pass (one 128-bit window)
-constexpr int kWarpPos = 32 * kLanePos;  // positions per warp pass
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ uint4 ldg128(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ uint2 ldg64(const uint8_t* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
 __device__ __forceinline__ uint32_t ldg32(const uint8_t* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
 
-// One feature's contribution to this lane's 16 positions.  `a` is the flat byte address of the lane's first position;
-// Q = (a & 15) >> 2 is a compile-time constant because the packer groups a template's features by it.  The lane loads
-// the aligned 16 bytes at or below its window plus the Q+1 following words, and realigns with byte permutes.
-template <int Q>
-__device__ __forceinline__ void add_feature(const uint8_t* __restrict__ lmc, uint32_t a, uint32_t (&acc)[4]) {
-  const uint8_t* p = lmc + (a & ~15u);
-  const uint32_t sel = 0x3210u + 0x1111u * (a & 3u);
-  uint32_t w[8];
-  const uint4 v = ldg128(p);
-  w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-  if (Q == 0) {
-    w[4] = ldg32(p + 16);
-  } else if (Q == 1) {
-    const uint2 n = ldg64(p + 16);
-    w[4] = n.x; w[5] = n.y;
-  } else {
-    const uint4 n = ldg128(p + 16);
-    w[4] = n.x; w[5] = n.y; w[6] = n.z; w[7] = n.w;
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) acc[k] += __byte_perm(w[Q + k], w[Q + k + 1], sel);
-}
-
-template <int Q>
-__device__ __forceinline__ void add_group(const uint8_t* __restrict__ lmc, const uint32_t* __restrict__ foff, int n,
-                                          uint32_t lane_off, uint32_t (&acc)[4]) {
-  int f = 0;
-  for (; f + 4 <= n; f += 4) {  // four independent window loads in flight per lane
-    const uint32_t a0 = foff[f] + lane_off, a1 = foff[f + 1] + lane_off, a2 = foff[f + 2] + lane_off,
-                   a3 = foff[f + 3] + lane_off;
-    add_feature<Q>(lmc, a0, acc);
-    add_feature<Q>(lmc, a1, acc);
-    add_feature<Q>(lmc, a2, acc);
-    add_feature<Q>(lmc, a3, acc);
-  }
-  for (; f < n; ++f) add_feature<Q>(lmc, foff[f] + lane_off, acc);
-}
-
-// Coarse similarity of every (template, position) at the lowest pyramid level, thresholded in registers.
-// A warp owns one (work item, 512-position pass) tile at a time; the non-empty tiles of all queries of the request
-// are listed heaviest-first and handed out through an atomic counter, so the persistent grid stays balanced to the
-// last tile.  There are no warp collectives in the accumulation loop: every lane fetches its own (unaligned) 16-byte
-// window with two vector loads.
-__global__ void __launch_bounds__(256) k_similarity_coarse(const uint8_t* __restrict__ lmc,
-                                                           const uint32_t* __restrict__ foff,
-                                                           const CoarseTpl* __restrict__ tpl,
-                                                           const WorkItem* __restrict__ items,
-                                                           const uint2* __restrict__ tiles, int n_tiles,
-                                                           const QueryThresholds thr_q, int M, Cand* __restrict__ cand,
-                                                           ResultHeader* hdr, uint32_t cand_cap,
-                                                           uint16_t* __restrict__ dump, int dump_stride) {
-  const int lane = threadIdx.x & 31;
-  for (;;) {
-    uint32_t tile = 0;
-    if (lane == 0) tile = atomicAdd(&hdr->next_tile, 1u);
-    tile = __shfl_sync(kFull, tile, 0);
-    if (tile >= (uint32_t)n_tiles) break;
-    const uint2 tl = tiles[tile];
-    const uint32_t item = tl.x;
-    const int j0 = (int)tl.y * kWarpPos;
-    const WorkItem wi = items[item];
-    const uint32_t tg = wi.tglob;
-    const int rem = min(tpl[tg].P - j0, kWarpPos);  // positions of this pass (> 0 by construction of the tile list)
-    const int first = lane * kLanePos;               // first position of this lane within the pass
-    if (first < rem) {
-      const uint32_t t_feat_begin = tpl[tg].feat_begin, t_nf = tpl[tg].nf;
-      const uint32_t lane_off = (uint32_t)(j0 + first);
-      uint32_t tot_lo[4] = {0, 0, 0, 0}, tot_hi[4] = {0, 0, 0, 0};  // u16 x 2 per word: bytes (0,2) and (1,3)
-      const uint32_t* fp = foff + t_feat_begin;
-      for (int m = 0; m < M; ++m) {
-        uint32_t acc[4] = {0, 0, 0, 0};
-        const uint32_t c4 = __ldg(reinterpret_cast<const uint32_t*>(tpl[tg].cnt) + m);  // 4 group sizes, one word
-        const int n0 = c4 & 255, n1 = (c4 >> 8) & 255, n2 = (c4 >> 16) & 255, n3 = c4 >> 24;
-        add_group<0>(lmc, fp, n0, lane_off, acc); fp += n0;
-        add_group<1>(lmc, fp, n1, lane_off, acc); fp += n1;
-        add_group<2>(lmc, fp, n2, lane_off, acc); fp += n2;
-        add_group<3>(lmc, fp, n3, lane_off, acc); fp += n3;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {  // [OCV] addSimilarities: widen u8 -> u16 and add the modality
-          tot_lo[k] += acc[k] & 0x00ff00ffu;
-          tot_hi[k] += (acc[k] >> 8) & 0x00ff00ffu;
-        }
-      }
-      // [OCV] matchClass: raw_threshold = (int)(2*nf + (threshold / 100.f) * (2*nf) + 0.5f), same f32 roundings
-      const float threshold = thr_q.v[wi.order >> 28];
-      const float two_nf = (float)(2 * (int)t_nf);
-      const int thr = __float2int_rz(__fadd_rn(__fadd_rn(two_nf, __fmul_rn(__fdiv_rn(threshold, 100.f), two_nf)), 0.5f));
-      bool hit = thr < 0;
-      if (!hit) {
-        const uint32_t thr2 = (uint32_t)min(thr, 0xffff) * 0x00010001u;
-        uint32_t any = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) any |= __vcmpgtu2(tot_lo[k], thr2) | __vcmpgtu2(tot_hi[k], thr2);
-        hit = any != 0;
-      }
-      if (dump != nullptr) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            int p = first + 4 * k + i;
-            uint32_t src = (i & 1) ? tot_hi[k] : tot_lo[k];
-            if (p < rem) dump[(size_t)item * dump_stride + j0 + p] = (uint16_t)((i & 2) ? (src >> 16) : (src & 0xffffu));
-          }
-      }
-      if (hit) {  // rare: [OCV] matchClass raster scan, "raw_score > raw_threshold"
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            int p = first + 4 * k + i;
-            uint32_t src = (i & 1) ? tot_hi[k] : tot_lo[k];
-            int raw = (int)((i & 2) ? (src >> 16) : (src & 0xffffu));
-            if (p < rem && raw > thr) {
-              uint32_t idx = atomicAdd(&hdr->n_cands, 1u);
-              if (idx < cand_cap) {
-                Cand c;
-                c.tglob = tg; c.pos = (uint32_t)(j0 + p); c.raw_nf = (uint32_t)raw | (t_nf << 16); c.order = wi.order;
-                cand[idx] = c;
-              }
-            }
-          }
-      }
-    }
-    __syncwarp();
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ nibble-packed coarse
-// Production coarse kernel.  Responses are <= 4, so the coarsest level's linear memories are also kept packed two
-// positions per byte (k_pack_nibbles): position p of the reference's flat byte plane is nibble p.  That halves the
-// bytes every window load moves through L1/L2.  Up to three features are summed in the nibble domain (3 x 4 = 12 < 16:
-// no carry between positions) before the even / odd nibbles are spread into the u8 accumulators the reference uses, so
-// the sums are bit-identical to _mm_add_epi8 over bytes.
-//
-// A lane owns 8*WORDS consecutive positions = one aligned (4*WORDS)-byte window per feature plus the Q+1 following
-// words; the window is realigned with one funnel shift per word (nibble granularity).  Q = word offset of the window
-// inside its aligned chunk is the packer's feature grouping, hence a compile-time constant.  The feature offsets of the
-// warp's template are staged in shared memory first, so the window loads of consecutive features do not wait on a
-// dependent global load and six features (twelve loads) are in flight per lane.
-template <int WORDS>
-struct Nib {
-  static constexpr int kLanePos = 8 * WORDS;
-  static constexpr int kWarpPos = 32 * kLanePos;
-};
-
-template <int WORDS, int Q>
-__device__ __forceinline__ void nib_window(const uint8_t* __restrict__ lmn, uint32_t a, uint32_t (&n)[WORDS]) {
-  const uint8_t* p = lmn + ((a >> 1) & ~(uint32_t)(4 * WORDS - 1));
-  const uint32_t sh = (a & 7u) * 4u;
-  uint32_t w[2 * WORDS];
-  if (WORDS == 4) {
-    const uint4 v = ldg128(p);
-    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-    if (Q == 0) {
-      w[4] = ldg32(p + 16);
-    } else if (Q == 1) {
-      const uint2 e = ldg64(p + 16);
-      w[4] = e.x; w[5] = e.y;
-    } else {
-      const uint4 e = ldg128(p + 16);
-      w[4] = e.x; w[5] = e.y; w[6] = e.z; w[7] = e.w;
-    }
-  } else {
-    const uint2 v = ldg64(p);
-    w[0] = v.x; w[1] = v.y;
-    if (Q == 0) {
-      w[2] = ldg32(p + 8);
-    } else {
-      const uint2 e = ldg64(p + 8);
-      w[2] = e.x; w[3] = e.y;
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < WORDS; ++k) n[k] = __funnelshift_r(w[Q + k], w[Q + k + 1], sh);
-}
-
+// Responses are <= 4, so the linear memories are kept packed two positions per byte: position p of the reference's flat
+// byte plane is nibble p.  That halves the bytes every window load moves through L1/L2.  Up to three features are summed
+// in the nibble domain (3 x 4 = 12 < 16: no carry between positions) before the even / odd nibbles are spread into the
+// u8 accumulators the reference uses, so the sums are bit-identical to _mm_add_epi8 over bytes.
 template <int WORDS>
 __device__ __forceinline__ void nib_flush(const uint32_t (&nib)[WORDS], uint32_t (&acc_e)[WORDS], uint32_t (&acc_o)[WORDS]) {
 #pragma unroll
   for (int k = 0; k < WORDS; ++k) {
     acc_e[k] += nib[k] & 0x0f0f0f0fu;
     acc_o[k] += (nib[k] >> 4) & 0x0f0f0f0fu;
-  }
-}
-
-template <int WORDS, int Q>
-__device__ __forceinline__ void nib_group(const uint8_t* __restrict__ lmn, const uint32_t* so, int n, uint32_t lane_off,
-                                          uint32_t (&acc_e)[WORDS], uint32_t (&acc_o)[WORDS]) {
-  int f = 0;
-  for (; f + 6 <= n; f += 6) {
-    uint32_t a[6][WORDS];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) nib_window<WORDS, Q>(lmn, so[f + i] + lane_off, a[i]);
-    uint32_t s0[WORDS], s1[WORDS];
-#pragma unroll
-    for (int k = 0; k < WORDS; ++k) { s0[k] = a[0][k] + a[1][k] + a[2][k]; s1[k] = a[3][k] + a[4][k] + a[5][k]; }
-    nib_flush<WORDS>(s0, acc_e, acc_o);
-    nib_flush<WORDS>(s1, acc_e, acc_o);
-  }
-  if (f + 3 <= n) {
-    uint32_t a[3][WORDS];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) nib_window<WORDS, Q>(lmn, so[f + i] + lane_off, a[i]);
-    uint32_t s0[WORDS];
-#pragma unroll
-    for (int k = 0; k < WORDS; ++k) s0[k] = a[0][k] + a[1][k] + a[2][k];
-    nib_flush<WORDS>(s0, acc_e, acc_o);
-    f += 3;
-  }
-  if (f < n) {  // one or two left
-    uint32_t a0[WORDS], a1[WORDS];
-    nib_window<WORDS, Q>(lmn, so[f] + lane_off, a0);
-    if (f + 1 < n) {
-      nib_window<WORDS, Q>(lmn, so[f + 1] + lane_off, a1);
-#pragma unroll
-      for (int k = 0; k < WORDS; ++k) a0[k] += a1[k];
-    }
-    nib_flush<WORDS>(a0, acc_e, acc_o);
-  }
-}
-
-constexpr int kMaxTplFeatures = LM_MAX_MODALITIES * 64;
-
-template <int WORDS>
-__global__ void __launch_bounds__(256) k_similarity_coarse_nib(const uint8_t* __restrict__ lmn,
-                                                               const uint32_t* __restrict__ foff,
-                                                               const CoarseTpl* __restrict__ tpl,
-                                                               const WorkItem* __restrict__ items,
-                                                               const uint2* __restrict__ tiles, int n_tiles,
-                                                               const QueryThresholds thr_q, int M,
-                                                               Cand* __restrict__ cand, ResultHeader* hdr,
-                                                               uint32_t cand_cap, uint16_t* __restrict__ dump,
-                                                               int dump_stride) {
-  constexpr int kLanePos = Nib<WORDS>::kLanePos, kWarpPos = Nib<WORDS>::kWarpPos;
-  __shared__ uint32_t s_off[8][kMaxTplFeatures];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t* so = s_off[warp];
-  for (;;) {
-    uint32_t tile = 0;
-    if (lane == 0) tile = atomicAdd(&hdr->next_tile, 1u);
-    tile = __shfl_sync(kFull, tile, 0);
-    if (tile >= (uint32_t)n_tiles) break;
-    const uint2 tl = tiles[tile];
-    const uint32_t item = tl.x;
-    const int j0 = (int)tl.y * kWarpPos;
-    const WorkItem wi = items[item];
-    const uint32_t tg = wi.tglob;
-    const CoarseTpl* __restrict__ ct = tpl + tg;
-    // stage this template's feature offsets (all modalities, grouped by Q) in shared memory
-    int n_feat = 0;
-    for (int m = 0; m < M; ++m) n_feat += __dp4a(__ldg(reinterpret_cast<const uint32_t*>(ct->cnt) + m), 0x01010101u, 0u);
-    const uint32_t feat_begin = ct->feat_begin;
-    __syncwarp();
-    for (int i = lane; i < n_feat; i += 32) so[i] = __ldg(foff + feat_begin + i);
-    __syncwarp();
-    const int rem = min(ct->P - j0, kWarpPos);  // positions of this pass (> 0 by construction of the tile list)
-    const int first = lane * kLanePos;           // first position of this lane within the pass
-    if (first < rem) {
-      const uint32_t lane_off = (uint32_t)(j0 + first);
-      uint32_t tot[WORDS][4];  // u16 x 2 per register: [k][r], r = (i & 1) * 2 + ((i >> 1) & 1) for position 8k + i
-#pragma unroll
-      for (int k = 0; k < WORDS; ++k) tot[k][0] = tot[k][1] = tot[k][2] = tot[k][3] = 0;
-      const uint32_t* fp = so;
-      for (int m = 0; m < M; ++m) {
-        uint32_t acc_e[WORDS], acc_o[WORDS];
-#pragma unroll
-        for (int k = 0; k < WORDS; ++k) acc_e[k] = acc_o[k] = 0;
-        const uint32_t c4 = __ldg(reinterpret_cast<const uint32_t*>(ct->cnt) + m);  // 4 group sizes, one word
-        const int n0 = c4 & 255, n1 = (c4 >> 8) & 255, n2 = (c4 >> 16) & 255, n3 = c4 >> 24;
-        nib_group<WORDS, 0>(lmn, fp, n0, lane_off, acc_e, acc_o); fp += n0;
-        nib_group<WORDS, 1>(lmn, fp, n1, lane_off, acc_e, acc_o); fp += n1;
-        if (WORDS == 4) {
-          nib_group<WORDS, (WORDS == 4 ? 2 : 0)>(lmn, fp, n2, lane_off, acc_e, acc_o); fp += n2;
-          nib_group<WORDS, (WORDS == 4 ? 3 : 1)>(lmn, fp, n3, lane_off, acc_e, acc_o); fp += n3;
-        }
-#pragma unroll
-        for (int k = 0; k < WORDS; ++k) {  // [OCV] addSimilarities: widen u8 -> u16 and add the modality
-          tot[k][0] += acc_e[k] & 0x00ff00ffu;
-          tot[k][1] += (acc_e[k] >> 8) & 0x00ff00ffu;
-          tot[k][2] += acc_o[k] & 0x00ff00ffu;
-          tot[k][3] += (acc_o[k] >> 8) & 0x00ff00ffu;
-        }
-      }
-      // [OCV] matchClass: raw_threshold = (int)(2*nf + (threshold / 100.f) * (2*nf) + 0.5f), same f32 roundings
-      const float threshold = thr_q.v[wi.order >> 28];
-      const float two_nf = (float)(2 * (int)ct->nf);
-      const int thr = __float2int_rz(__fadd_rn(__fadd_rn(two_nf, __fmul_rn(__fdiv_rn(threshold, 100.f), two_nf)), 0.5f));
-      bool hit = thr < 0;
-      if (!hit) {
-        const uint32_t thr2 = (uint32_t)min(thr, 0xffff) * 0x00010001u;
-        uint32_t any = 0;
-#pragma unroll
-        for (int k = 0; k < WORDS; ++k)
-#pragma unroll
-          for (int r = 0; r < 4; ++r) any |= __vcmpgtu2(tot[k][r], thr2);
-        hit = any != 0;
-      }
-      if (dump != nullptr || hit) {  // rare: [OCV] matchClass raster scan, "raw_score > raw_threshold"
-#pragma unroll
-        for (int k = 0; k < WORDS; ++k)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int p = first + 8 * k + i;
-            const uint32_t src = tot[k][(i & 1) * 2 + ((i >> 1) & 1)];
-            const int raw = (int)((i & 4) ? (src >> 16) : (src & 0xffffu));
-            if (p < rem) {
-              if (dump != nullptr) dump[(size_t)item * dump_stride + j0 + p] = (uint16_t)raw;
-              if (raw > thr) {
-                uint32_t idx = atomicAdd(&hdr->n_cands, 1u);
-                if (idx < cand_cap) {
-                  Cand c;
-                  c.tglob = tg; c.pos = (uint32_t)(j0 + p); c.raw_nf = (uint32_t)raw | (ct->nf << 16); c.order = wi.order;
-                  cand[idx] = c;
-                }
-              }
-            }
-          }
-      }
-    }
   }
 }
 
@@ -478,13 +168,7 @@ __device__ __forceinline__ bool rec_alive(const uint32_t (&tot)[4][4], int thr, 
   return __any_sync(kFull, active && best > need);
 }
 
-__global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const uint8_t* __restrict__ lmn,
-                                                               const uint32_t* __restrict__ recs, int rec_words,
-                                                               int n_tiles, const QueryThresholds thr_q, int M, int prune,
-                                                               Cand* __restrict__ cand, ResultHeader* hdr,
-                                                               unsigned long long* touched, uint32_t cand_cap,
-                                                               uint16_t* __restrict__ dump, int dump_stride,
-                                                               const unsigned int* __restrict__ mod_bits) {
+__global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarseParams P) {
   __shared__ uint32_t s_rec[8][kRecMaxWords];
   __shared__ unsigned long long s_bytes;
   __shared__ uint32_t s_done, s_expected;
@@ -492,6 +176,12 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const uint8_t*
   uint32_t* sr = s_rec[warp];
   cudaGridDependencySynchronize();            // linear memories (previous kernel in the stream) are complete
   cudaTriggerProgrammaticLaunchCompletion();  // let k_refine's blocks be scheduled as this grid drains
+  BatchCtl* ctl = P.ctl;
+  const uint32_t* __restrict__ recs = P.recs;
+  const int rec_words = P.rec_words, M = P.M, prune = P.prune;
+  const uint32_t n_tiles = (uint32_t)P.n_tiles;
+  // virtual tiles of the chunk, frame-major: v = frame * n_tiles + tile
+  const uint32_t n_virtual = n_tiles * (uint32_t)ctl->ft.n_frames;
   // Tile hand-out: the first two tiles of every warp are static (tile = global warp index, then + number of warps) --
   // thousands of warps drawing from one counter at kernel start serialise on that address -- and only the rest comes from
   // the atomic dispenser (tiles are sorted heaviest first, so the dynamic part balances the light tail).
@@ -501,39 +191,43 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const uint8_t*
   if (threadIdx.x == 0) {
     s_bytes = 0; s_done = 0;
     const uint32_t first_warp = blockIdx.x * (blockDim.x >> 5);  // warps of this CTA that have a first tile
-    s_expected = (uint32_t)n_tiles > first_warp ? min((uint32_t)n_tiles - first_warp, blockDim.x >> 5) : 0u;
+    s_expected = n_virtual > first_warp ? min(n_virtual - first_warp, blockDim.x >> 5) : 0u;
   }
   __syncthreads();
-  if (cur >= (uint32_t)n_tiles) return;
-  for (int i = lane; i < rec_words; i += 32) sr[i] = __ldg(recs + (size_t)cur * rec_words + i);
+  if (cur >= n_virtual) return;
+  uint32_t cur_frame = cur / n_tiles;
+  for (int i = lane; i < rec_words; i += 32) sr[i] = __ldg(recs + (size_t)(cur - cur_frame * n_tiles) * rec_words + i);
   uint32_t nxt = gwarp + n_warps;
   const uint32_t lane_byte = (uint32_t)lane * 16u;
   const int first = lane * 32;  // first position of this lane within the pass
   const bool do_prune = (prune & 1) != 0;
-  const uint32_t zero = (uint32_t)n_tiles >> 31;  // n_tiles > 0: zero, but only at run time (see rec_group)
-  // bit 8 of `prune`: sum the modalities in reverse order; bit 9: decide per frame from the front end's counters
-  const bool mod_reversed = (prune & 0x200) ? (mod_bits != nullptr && mod_bits[M - 1] < mod_bits[0]) : (prune & 0x100) != 0;
+  const uint32_t zero = n_tiles >> 31;  // n_tiles > 0: zero, but only at run time (see rec_group)
   unsigned long long bytes = 0;  // (feature, position) pairs actually gathered by this warp
   for (;;) {
     __syncwarp();
     // prefetch the next tile's record into registers and draw the tile after it
-    const bool has_next = nxt < (uint32_t)n_tiles;
+    const bool has_next = nxt < n_virtual;
+    const uint32_t nxt_frame = has_next ? nxt / n_tiles : 0u;
+    const uint32_t nxt_tile = nxt - nxt_frame * n_tiles;
     uint32_t pre[kRecPre];
 #pragma unroll
     for (int i = 0; i < kRecPre; ++i) {
       const int idx = lane + 32 * i;
-      pre[i] = (has_next && idx < rec_words) ? __ldg(recs + (size_t)nxt * rec_words + idx) : 0u;
+      pre[i] = (has_next && idx < rec_words) ? __ldg(recs + (size_t)nxt_tile * rec_words + idx) : 0u;
     }
     // the ticket of the tile after next: issued now, read at the end of this tile (the atomic's round trip -- long when
     // thousands of warps draw at once -- overlaps the scoring instead of stalling it)
     uint32_t ticket = 0;
-    if (has_next && lane == 0) ticket = atomicAdd(&hdr->next_tile, 1u);
+    if (has_next && lane == 0) ticket = atomicAdd(&ctl->next_tile, 1u);
 
+    const uint8_t* __restrict__ lmn = P.lmn + (size_t)cur_frame * P.lmn_stride;
+    // bit 8 of `prune`: sum the modalities in reverse order; bit 9: decide per frame from the front end's counters
+    const bool mod_reversed = (prune & 0x200) ? (ctl->mod_bits[cur_frame][M - 1] < ctl->mod_bits[cur_frame][0]) : (prune & 0x100) != 0;
     const uint32_t item = sr[0], tg = sr[1], nfq = sr[2], order = sr[6];
     const int n_feat = (int)sr[3], j0 = (int)sr[4], rem = (int)sr[5];
     const bool active = first < rem;
     // [OCV] matchClass: raw_threshold = (int)(2*nf + (threshold / 100.f) * (2*nf) + 0.5f), same f32 roundings
-    const float threshold = thr_q.v[nfq >> 28];
+    const float threshold = P.thr.v[nfq >> 28];
     const float two_nf = (float)(2 * (int)(nfq & 0x0fffffffu));
     const int thr = __float2int_rz(__fadd_rn(__fadd_rn(two_nf, __fmul_rn(__fdiv_rn(threshold, 100.f), two_nf)), 0.5f));
     uint32_t tot[4][4];  // u16 x 2 per register: [k][r], r = (i & 1) * 2 + ((i >> 1) & 1) for position 8k + i
@@ -577,7 +271,7 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const uint8_t*
           for (int r = 0; r < 4; ++r) any |= __vcmpgtu2(tot[k][r], thr2);
         hit = any != 0;
       }
-      if (dump != nullptr || hit) {  // rare: [OCV] matchClass raster scan, "raw_score > raw_threshold"
+      if (P.dump != nullptr || hit) {  // rare: [OCV] matchClass raster scan, "raw_score > raw_threshold"
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -586,13 +280,14 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const uint8_t*
             const uint32_t src = tot[k][(i & 1) * 2 + ((i >> 1) & 1)];
             const int raw = (int)((i & 4) ? (src >> 16) : (src & 0xffffu));
             if (p < rem) {
-              if (dump != nullptr) dump[(size_t)item * dump_stride + j0 + p] = (uint16_t)raw;
+              if (P.dump != nullptr) P.dump[(size_t)item * P.dump_stride + j0 + p] = (uint16_t)raw;
               if (raw > thr) {
-                uint32_t idx = atomicAdd(&hdr->n_cands, 1u);
-                if (idx < cand_cap) {
+                uint32_t idx = atomicAdd(&ctl->n_cands, 1u);
+                if (idx < P.cand_cap) {
                   Cand c;
-                  c.tglob = tg; c.pos = (uint32_t)(j0 + p); c.raw_nf = (uint32_t)raw | ((nfq & 0xffffu) << 16); c.order = order;
-                  cand[idx] = c;
+                  c.tglob = tg; c.pos = (uint32_t)(j0 + p) | (cur_frame << 24);
+                  c.raw_nf = (uint32_t)raw | ((nfq & 0xffffu) << 16); c.order = order;
+                  P.cand[idx] = c;
                 }
               }
             }
@@ -606,22 +301,27 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const uint8_t*
       const int idx = lane + 32 * i;
       if (idx < rec_words) sr[idx] = pre[i];
     }
+    cur_frame = nxt_frame;
     nxt = __shfl_sync(kFull, ticket, 0) + 2u * n_warps;
   }
   // gathered-bytes statistic: summed per CTA in shared memory, one global atomic per CTA by the warp that finishes last
   // (one atomic per warp on a single address costs microseconds at the end of a launch of thousands of warps)
-  if (lane == 0 && touched != nullptr) {
+  if (lane == 0 && P.touched != nullptr) {
     atomicAdd(&s_bytes, bytes);
     __threadfence_block();
-    if (atomicAdd(&s_done, 1u) + 1u == s_expected) atomicAdd(touched, s_bytes);
+    if (atomicAdd(&s_done, 1u) + 1u == s_expected) atomicAdd(P.touched, s_bytes);
   }
 }
 
-// Byte linear memories -> nibble-packed copy (two positions per byte), 16 bytes in / 8 bytes out per thread.
-__global__ void __launch_bounds__(256) k_pack_nibbles(const uint4* __restrict__ src, uint2* __restrict__ dst, size_t n16) {
+// Byte linear memories -> nibble-packed copy (two positions per byte), 16 bytes in / 8 bytes out per thread; blockIdx.y = frame.
+__global__ void __launch_bounds__(256) k_pack_nibbles(const uint8_t* __restrict__ src0, size_t src_stride,
+                                                      uint8_t* __restrict__ dst0, size_t dst_stride, size_t n16,
+                                                      const BatchCtl* __restrict__ ctl) {
+  const int frame = blockIdx.y;
+  if (frame >= ctl->ft.n_frames) return;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n16) return;
-  const uint4 v = src[i];
+  const uint4 v = reinterpret_cast<const uint4*>(src0 + (size_t)frame * src_stride)[i];
   // bytes b0 b1 b2 b3 of a word -> nibbles b0 | b1<<4 | b2<<8 | b3<<12
   auto squeeze = [](uint32_t w) -> uint32_t {
     uint32_t t = (w | (w >> 4)) & 0x00ff00ffu;  // b0|b1<<4 in byte 0, b2|b3<<4 in byte 2
@@ -630,145 +330,26 @@ __global__ void __launch_bounds__(256) k_pack_nibbles(const uint4* __restrict__ 
   uint2 o;
   o.x = squeeze(v.x) | (squeeze(v.y) << 16);
   o.y = squeeze(v.z) | (squeeze(v.w) << 16);
-  dst[i] = o;
+  reinterpret_cast<uint2*>(dst0 + (size_t)frame * dst_stride)[i] = o;
 }
 
-// Local refinement of every coarse candidate up the pyramid.  One 8-warp block per candidate: the 16 x 16 patch is
-// mapped lane -> (row = lane / 2, 8 columns = lane % 2) in every warp and the template's features are dealt round-robin
-// to the warps.  Per level the block first turns the template's features into linear-memory byte offsets in shared
-// memory (one thread per feature: shift by the patch origin, bounds test, phase/cell split); then every warp issues the
-// window loads of all its features of a modality back to back (<= 8 features, 24 loads in flight per lane) before it
-// adds them up, so a candidate costs two load latencies per modality instead of a dependent chain per feature.
-// Features that fall outside the image after the shift are redirected to a zero byte run instead of being skipped.
+// Everything that differs between two replays of a lane's CUDA graph, installed by one tiny launch in front of it: the
+// frame table arrives as a kernel parameter (copied at launch time: no host buffer to keep alive), the coarse kernel's
+// dispenser / counters and the (statistics + header) prefix of the lane's result blocks are zeroed.
+__global__ void __launch_bounds__(256) k_begin_chunk(const FrameTable ft, BatchCtl* ctl, uint8_t* results, size_t result_stride,
+                                                     int n_blocks) {
+  const int tid = threadIdx.x;
+  constexpr int kWords = (int)(sizeof(BatchCtl) / 4), kFtWords = (int)(sizeof(FrameTable) / 4);
+  const uint32_t* in = reinterpret_cast<const uint32_t*>(&ft);
+  uint32_t* out = reinterpret_cast<uint32_t*>(ctl);
+  for (int i = tid; i < kWords; i += 256) out[i] = i < kFtWords ? in[i] : 0u;
+  for (int i = tid; i < n_blocks * 8; i += 256)   // 16 B statistics + ResultHeader = 8 words per block
+    reinterpret_cast<uint32_t*>(results + (size_t)(i >> 3) * result_stride)[i & 7] = 0u;
+}
+
 constexpr int kRefineWarps = 8;
 constexpr int kRefineMaxFeat = LM_MAX_MODALITIES * 64;
-
-__global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams P, const CoarseTpl* __restrict__ ctpl,
-                                                             const WorkItem* __restrict__ items,
-                                                             const Cand* __restrict__ cand, uint32_t cand_cap,
-                                                             ResultHeader* hdr, lm_raw_match* __restrict__ out,
-                                                             uint32_t out_cap) {
-  __shared__ uint32_t s_part[kRefineWarps][32][4];
-  __shared__ uint32_t s_addr[kRefineMaxFeat];  // byte offset of the feature's patch origin inside its modality's planes
-  __shared__ int s_state[4];                   // x, y, alive, best_score
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  cudaGridDependencySynchronize();  // programmatic dependent launch: the coarse kernel's candidates are complete from here on
-  const uint32_t n_cands = min(hdr->n_cands, cand_cap);
-  if (blockIdx.x == 0 && threadIdx.x == 0 && hdr->n_cands > cand_cap) hdr->overflow = 1;  // candidate list truncated
-  const int prow = lane >> 1, pcol0 = (lane & 1) * 8;
-  for (uint32_t ci = blockIdx.x; ci < n_cands; ci += gridDim.x) {
-    const Cand c = cand[ci];
-    const uint32_t order = c.order;
-    const float threshold = P.threshold[order >> 28];
-    const int cT = P.coarse_T;
-    const int coff = cT / 2 + (cT % 2 - 1);
-    int x = (int)(c.pos % (uint32_t)P.coarse_W) * cT + coff;
-    int y = (int)(c.pos / (uint32_t)P.coarse_W) * cT + coff;
-    uint32_t score = c.raw_nf & 0xffffu, nf = c.raw_nf >> 16;
-    bool alive = true;
-    for (int l = P.levels - 2; l >= 0 && alive; --l) {
-      const RefineLevel& L = P.level[l];
-      const RefineTpl* rtp = L.tpl + c.tglob;
-      const int T = L.T, W = L.W;
-      const int border = 8 * T, off = T / 2 + (T % 2 - 1);
-      const int max_x = L.cols - rtp->width - border, max_y = L.rows - rtp->height - border;
-      x = x * 2 + 1; y = y * 2 + 1;
-      x = max(x, border); y = max(y, border);
-      x = min(x, max_x); y = min(y, max_y);
-      const int offset_x = (x / T - 8) * T, offset_y = (y / T - 8) * T;
-      const uint32_t WH = (uint32_t)W * (uint32_t)(L.rows / T);
-      const uint32_t zero_run = (uint32_t)L.plane_stride - 16u;  // the tail of every plane is zero (App. D-2 padding)
-      // ---- features -> byte offsets (one thread each)
-      int n_all = 0;
-      for (int m = 0; m < P.M; ++m) n_all += rtp->cnt[m];
-      const uint32_t* fp = L.feats + rtp->feat_begin;
-      for (int i = threadIdx.x; i < n_all; i += kRefineWarps * 32) {
-        const uint32_t pk = fp[i];
-        const int fx = (int)(pk & 0x1fffu) - 4096 + offset_x, fy = (int)((pk >> 13) & 0x1fffu) - 4096 + offset_y;
-        const bool inside = fx >= 0 && fy >= 0 && fx < L.cols && fy < L.rows;  // "Discard feature if out of bounds"
-        const uint32_t label = pk >> 26;
-        uint32_t addr = label * (uint32_t)L.plane_stride + (uint32_t)((fy % T) * T + (fx % T)) * WH +
-                        (uint32_t)(fy / T) * (uint32_t)W + (uint32_t)(fx / T);
-        s_addr[i] = inside ? addr : zero_run;
-      }
-      __syncthreads();
-      const uint32_t lane_off = (uint32_t)(prow * W + pcol0);
-      uint32_t tot[4] = {0, 0, 0, 0};  // 8 x u16: columns pcol0 .. pcol0+7 as (0,2),(1,3),(4,6),(5,7)
-      int begin = 0;
-      for (int m = 0; m < P.M; ++m) {
-        const uint8_t* lmm = L.lm + (size_t)m * 8 * L.plane_stride;
-        const int n = rtp->cnt[m];  // <= 63: at most 8 features per warp, u8 lanes cannot overflow (8 * 4)
-        uint32_t w[8][3], sel[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int f = warp + kRefineWarps * k;
-          const uint32_t base = f < n ? s_addr[begin + f] : zero_run;
-          const uint32_t addr = base + (base == zero_run ? 0u : lane_off);
-          const uint8_t* p = lmm + (addr & ~3u);
-          sel[k] = 0x3210u + 0x1111u * (addr & 3u);
-          w[k][0] = ldg32(p); w[k][1] = ldg32(p + 4); w[k][2] = ldg32(p + 8);
-        }
-        uint32_t a0 = 0, a1 = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          a0 += __byte_perm(w[k][0], w[k][1], sel[k]);
-          a1 += __byte_perm(w[k][1], w[k][2], sel[k]);
-        }
-        begin += n;
-        tot[0] += a0 & 0x00ff00ffu; tot[1] += (a0 >> 8) & 0x00ff00ffu;
-        tot[2] += a1 & 0x00ff00ffu; tot[3] += (a1 >> 8) & 0x00ff00ffu;
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) s_part[warp][lane][k] = tot[k];
-      __syncthreads();
-      if (warp == 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint32_t s = 0;
-#pragma unroll
-          for (int w2 = 0; w2 < kRefineWarps; ++w2) s += s_part[w2][lane][k];
-          tot[k] = s;
-        }
-        // first maximum in raster order: key = score << 8 | (255 - raster index)
-        uint32_t best_key = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint32_t src = tot[(i >> 2) * 2 + (i & 1)];
-          uint32_t sc = (i & 2) ? (src >> 16) : (src & 0xffffu);
-          uint32_t key = (sc << 8) | (uint32_t)(255 - (prow * 16 + pcol0 + i));
-          best_key = max(best_key, key);
-        }
-        best_key = __reduce_max_sync(kFull, best_key);
-        if (lane == 0) {
-          const int best_score = (int)(best_key >> 8);
-          int best_r = -1, best_c = -1;
-          if (best_score > 0) {
-            int idx = 255 - (int)(best_key & 0xffu);
-            best_r = idx >> 4; best_c = idx & 15;
-          }
-          const int nfl = (int)rtp->nf;
-          float sim = __fdiv_rn(__fmul_rn((float)best_score, 100.f), (float)(4 * nfl));
-          s_state[0] = (x / T - 8 + best_c) * T + off;
-          s_state[1] = (y / T - 8 + best_r) * T + off;
-          s_state[2] = (sim < threshold) ? 0 : 1;  // [OCV] remove_if(MatchPredicate(threshold))
-          s_state[3] = best_score;
-        }
-      }
-      __syncthreads();
-      x = s_state[0]; y = s_state[1]; alive = s_state[2] != 0; score = (uint32_t)s_state[3]; nf = rtp->nf;
-      __syncthreads();  // s_state / s_part / s_addr are rewritten by the next level
-    }
-    if (alive && threadIdx.x == 0) {
-      uint32_t idx = atomicAdd(&hdr->count, 1u);
-      if (idx < out_cap) {
-        lm_raw_match r;
-        r.order_key = order; r.coarse_pos = c.pos; r.x = x; r.y = y; r.score = score; r.nf = nf;
-        r.template_id = ctpl[c.tglob].template_id; r.class_index = ctpl[c.tglob].class_index;
-        out[idx] = r;
-      } else hdr->overflow = 1;
-    }
-  }
-}
+constexpr size_t kResultStatsBytes = 16;  // statistics in front of every frame's ResultHeader
 
 // Refinement on nibble-packed planes, ONE BLOCK PER CANDIDATE (few candidates: lowest latency).  A patch row is 16 positions =
 // 8 bytes at an arbitrary nibble offset: lane r (< 16) and lane r + 16 load the two aligned 8-byte chunks the row spans
@@ -777,8 +358,8 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine(const RefineParams
 // three features in the nibble domain before spreading even / odd nibbles into byte accumulators.  Same block / warp
 // decomposition, argmax and bookkeeping as k_refine.
 __device__ __forceinline__ void refine_nib_block(const RefineParams& P, const CoarseTpl* __restrict__ ctpl,
-                                                 const Cand* __restrict__ cand, uint32_t n_cands, ResultHeader* hdr,
-                                                 lm_raw_match* __restrict__ out, uint32_t out_cap, uint32_t* smem) {
+                                                 const Cand* __restrict__ cand, uint32_t n_cands, uint8_t* results,
+                                                 size_t result_stride, uint32_t out_cap, uint32_t* smem) {
   uint32_t (*s_part)[16][4] = reinterpret_cast<uint32_t (*)[16][4]>(smem);                       // [kRefineWarps][16][4]
   uint32_t* s_addr = smem + kRefineWarps * 16 * 4;  // [kRefineMaxFeat] nibble index of each feature's patch origin
   int* s_state = reinterpret_cast<int*>(s_addr + kRefineMaxFeat);  // x, y, alive, best_score
@@ -787,11 +368,14 @@ __device__ __forceinline__ void refine_nib_block(const RefineParams& P, const Co
   for (uint32_t ci = blockIdx.x; ci < n_cands; ci += gridDim.x) {
     const Cand c = cand[ci];
     const uint32_t order = c.order;
+    const uint32_t frame = c.pos >> 24, cpos = c.pos & 0x00ffffffu;
+    ResultHeader* hdr = reinterpret_cast<ResultHeader*>(results + (size_t)frame * result_stride + kResultStatsBytes);
+    lm_raw_match* __restrict__ out = reinterpret_cast<lm_raw_match*>(hdr + 1);
     const float threshold = P.threshold[order >> 28];
     const int cT = P.coarse_T;
     const int coff = cT / 2 + (cT % 2 - 1);
-    int x = (int)(c.pos % (uint32_t)P.coarse_W) * cT + coff;
-    int y = (int)(c.pos / (uint32_t)P.coarse_W) * cT + coff;
+    int x = (int)(cpos % (uint32_t)P.coarse_W) * cT + coff;
+    int y = (int)(cpos / (uint32_t)P.coarse_W) * cT + coff;
     uint32_t score = c.raw_nf & 0xffffu, nf = c.raw_nf >> 16;
     bool alive = true;
     for (int l = P.levels - 2; l >= 0 && alive; --l) {
@@ -823,7 +407,7 @@ __device__ __forceinline__ void refine_nib_block(const RefineParams& P, const Co
       uint32_t tot_e[2] = {0, 0}, tot_o[2] = {0, 0};  // u8 x 4: even / odd columns 0..7 and 8..15 of row prow (<= 16 * 4 per warp)
       int begin = 0;
       for (int m = 0; m < P.M; ++m) {
-        const uint8_t* lmm = L.lmn + (size_t)m * 4 * L.plane_stride;
+        const uint8_t* lmm = L.lmn + (size_t)frame * L.frame_stride + (size_t)m * 4 * L.plane_stride;
         const int n = rtp->cnt[m];  // <= 63: at most 8 features per warp
         uint2 w[8];
         uint32_t sh[8];
@@ -905,11 +489,12 @@ __device__ __forceinline__ void refine_nib_block(const RefineParams& P, const Co
       x = s_state[0]; y = s_state[1]; alive = s_state[2] != 0; score = (uint32_t)s_state[3]; nf = rtp->nf;
       __syncthreads();  // s_state / s_part / s_addr are rewritten by the next level
     }
+    if (threadIdx.x == 0) atomicAdd(&hdr->n_cands, 1u);
     if (alive && threadIdx.x == 0) {
       uint32_t idx = atomicAdd(&hdr->count, 1u);
       if (idx < out_cap) {
         lm_raw_match r;
-        r.order_key = order; r.coarse_pos = c.pos; r.x = x; r.y = y; r.score = score; r.nf = nf;
+        r.order_key = order; r.coarse_pos = cpos; r.x = x; r.y = y; r.score = score; r.nf = nf;
         r.template_id = ctpl[c.tglob].template_id; r.class_index = ctpl[c.tglob].class_index;
         out[idx] = r;
       } else hdr->overflow = 1;
@@ -926,8 +511,8 @@ __device__ __forceinline__ void refine_nib_block(const RefineParams& P, const Co
 // modality: <= 63 features x 4).  The warp first turns the template's features into plane offsets in its slice of shared
 // memory (one lane per feature), then issues eight window loads back to back per step.
 __device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const CoarseTpl* __restrict__ ctpl,
-                                                const Cand* __restrict__ cand, uint32_t n_cands, ResultHeader* hdr,
-                                                lm_raw_match* __restrict__ out, uint32_t out_cap, uint32_t* smem) {
+                                                const Cand* __restrict__ cand, uint32_t n_cands, uint8_t* results,
+                                                size_t result_stride, uint32_t out_cap, uint32_t* smem) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* s_addr = smem + warp * kRefineMaxFeat;  // nibble index of each feature's patch origin (this warp's slice)
   const int prow = lane & 15, half = lane >> 4;
@@ -935,11 +520,14 @@ __device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const Coa
   for (uint32_t ci = (uint32_t)warp * gridDim.x + blockIdx.x; ci < n_cands; ci += gridDim.x * kRefineWarps) {
     const Cand c = cand[ci];
     const uint32_t order = c.order;
+    const uint32_t frame = c.pos >> 24, cpos = c.pos & 0x00ffffffu;
+    ResultHeader* hdr = reinterpret_cast<ResultHeader*>(results + (size_t)frame * result_stride + kResultStatsBytes);
+    lm_raw_match* __restrict__ out = reinterpret_cast<lm_raw_match*>(hdr + 1);
     const float threshold = P.threshold[order >> 28];
     const int cT = P.coarse_T;
     const int coff = cT / 2 + (cT % 2 - 1);
-    int x = (int)(c.pos % (uint32_t)P.coarse_W) * cT + coff;
-    int y = (int)(c.pos / (uint32_t)P.coarse_W) * cT + coff;
+    int x = (int)(cpos % (uint32_t)P.coarse_W) * cT + coff;
+    int y = (int)(cpos / (uint32_t)P.coarse_W) * cT + coff;
     uint32_t score = c.raw_nf & 0xffffu, nf = c.raw_nf >> 16;
     bool alive = true;
     for (int l = P.levels - 2; l >= 0 && alive; --l) {
@@ -975,7 +563,7 @@ __device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const Coa
       for (int j = 0; j < 4; ++j) tot[j][0] = tot[j][1] = 0;
       int begin = 0;
       for (int m = 0; m < P.M; ++m) {
-        const uint8_t* lmm = L.lmn + (size_t)m * 4 * L.plane_stride;
+        const uint8_t* lmm = L.lmn + (size_t)frame * L.frame_stride + (size_t)m * 4 * L.plane_stride;
         const int n = rtp->cnt[m];  // <= 63 features: the u8 sums below cannot overflow
         uint32_t acc[4] = {0, 0, 0, 0};
         for (int f0 = 0; f0 < n; f0 += 8) {
@@ -1039,11 +627,12 @@ __device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const Coa
       alive = !(sim < threshold);  // [OCV] remove_if(MatchPredicate(threshold))
       score = (uint32_t)best_score; nf = rtp->nf;
     }
+    if (lane == 0) atomicAdd(&hdr->n_cands, 1u);
     if (alive && lane == 0) {
       uint32_t idx = atomicAdd(&hdr->count, 1u);
       if (idx < out_cap) {
         lm_raw_match r;
-        r.order_key = order; r.coarse_pos = c.pos; r.x = x; r.y = y; r.score = score; r.nf = nf;
+        r.order_key = order; r.coarse_pos = cpos; r.x = x; r.y = y; r.score = score; r.nf = nf;
         r.template_id = ctpl[c.tglob].template_id; r.class_index = ctpl[c.tglob].class_index;
         out[idx] = r;
       } else hdr->overflow = 1;
@@ -1055,22 +644,25 @@ __device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const Coa
 // candidates (loose thresholds, BASELINE config 3): a warp per candidate keeps every SM's L1 busy without block barriers.
 __global__ void __launch_bounds__(kRefineWarps * 32) k_refine_nib(const RefineParams P, const CoarseTpl* __restrict__ ctpl,
                                                                  const Cand* __restrict__ cand, uint32_t cand_cap,
-                                                                 ResultHeader* hdr, lm_raw_match* __restrict__ out,
+                                                                 BatchCtl* ctl, uint8_t* results, size_t result_stride,
                                                                  uint32_t out_cap) {
   __shared__ uint32_t smem[kRefineWarps * kRefineMaxFeat];
   static_assert(kRefineWarps * kRefineMaxFeat >= kRefineWarps * 16 * 4 + kRefineMaxFeat + 4, "block path fits the warp path's smem");
   cudaGridDependencySynchronize();  // programmatic dependent launch: the coarse kernel's candidates are complete from here on
-  const uint32_t n_cands = min(hdr->n_cands, cand_cap);
-  if (blockIdx.x == 0 && threadIdx.x == 0 && hdr->n_cands > cand_cap) hdr->overflow = 1;  // candidate list truncated
-  if (n_cands <= 2u * gridDim.x) refine_nib_block(P, ctpl, cand, n_cands, hdr, out, out_cap, smem);
-  else refine_nib_warp(P, ctpl, cand, n_cands, hdr, out, out_cap, smem);
+  const uint32_t found = ctl->n_cands;
+  const uint32_t n_cands = min(found, cand_cap);
+  if (blockIdx.x == 0 && found > cand_cap) {  // candidate list truncated: every frame of the chunk is incomplete
+    if ((int)threadIdx.x < ctl->ft.n_frames)
+      reinterpret_cast<ResultHeader*>(results + (size_t)threadIdx.x * result_stride + kResultStatsBytes)->overflow = 1;
+    if (threadIdx.x == 0) ctl->overflow = 1;
+  }
+  if (n_cands <= 2u * gridDim.x) refine_nib_block(P, ctpl, cand, n_cands, results, result_stride, out_cap, smem);
+  else refine_nib_warp(P, ctpl, cand, n_cands, results, result_stride, out_cap, smem);
 }
 
 }  // namespace
 
-int coarse_positions_per_pass(int variant) {
-  return variant == 1 ? kWarpPos : (variant == 2 ? Nib<4>::kWarpPos : kRecWarpPos);
-}
+int coarse_positions_per_pass() { return kRecWarpPos; }
 int coarse_record_header_words() { return kRecHdrWords; }
 int coarse_record_max_words() { return kRecMaxWords; }
 
@@ -1110,47 +702,34 @@ static int resident_ctas(K kernel) {
   return per_sm * sms;
 }
 
-void launch_similarity_coarse(int variant, const uint8_t* lmc, const uint8_t* lmn, const uint32_t* foff,
-                              const CoarseTpl* tpl, const WorkItem* items, const uint2* tiles, const uint32_t* recs,
-                              int rec_words, int n_tiles, const QueryThresholds& thr, int M, int prune, Cand* cand,
-                              ResultHeader* hdr, unsigned long long* touched, uint32_t cand_cap, uint16_t* dump,
-                              int dump_stride, cudaStream_t s, const unsigned int* mod_bits) {
-  if (n_tiles <= 0) return;
-  int blocks = (n_tiles + 7) / 8;
-  if (variant == 1) {  // byte linear memories (A/B reference of the nibble kernels)
-    static const int persistent = resident_ctas(k_similarity_coarse);
-    k_similarity_coarse<<<min(blocks, persistent), 256, 0, s>>>(lmc, foff, tpl, items, tiles, n_tiles, thr, M, cand,
-                                                                hdr, cand_cap, dump, dump_stride);
-  } else if (variant == 2) {  // nibble planes, two overlapping vector loads per feature (A/B reference)
-    static const int persistent = resident_ctas(k_similarity_coarse_nib<4>);
-    k_similarity_coarse_nib<4><<<min(blocks, persistent), 256, 0, s>>>(lmn, foff, tpl, items, tiles, n_tiles, thr, M,
-                                                                       cand, hdr, cand_cap, dump, dump_stride);
-  } else {
-    static const int persistent = resident_ctas(k_similarity_coarse_rec);
-    int grid = min(blocks, persistent);
-    if (g_coarse_grid_limit > 0) grid = min(grid, g_coarse_grid_limit);
-    cudaLaunchConfig_t cfg = pdl_config(grid, 256, s);
-    cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec, lmn, recs, rec_words, n_tiles, thr, M,
-                       dump == nullptr ? prune : 0, cand, hdr, touched, cand_cap, dump, dump_stride, mod_bits);
-  }
+void launch_similarity_coarse(const CoarseParams& p, int max_frames, cudaStream_t s) {
+  if (p.n_tiles <= 0) return;
+  static const int persistent = resident_ctas(k_similarity_coarse_rec);
+  const long long blocks = ((long long)p.n_tiles * max_frames + 7) / 8;
+  int grid = (int)std::min<long long>(blocks, persistent);
+  if (g_coarse_grid_limit > 0) grid = min(grid, g_coarse_grid_limit);
+  CoarseParams q = p;
+  if (q.dump != nullptr) q.prune = 0;
+  cudaLaunchConfig_t cfg = pdl_config(grid, 256, s);
+  cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec, q);
 }
 
-void launch_pack_nibbles(const uint8_t* lm_bytes, uint8_t* lm_nibbles, size_t n_bytes, cudaStream_t s) {
+void launch_pack_nibbles(const uint8_t* lm_bytes, size_t bytes_stride, uint8_t* lm_nibbles, size_t nib_stride, size_t n_bytes,
+                         const BatchCtl* ctl, int n_frames, cudaStream_t s) {
   const size_t n16 = n_bytes / 16;
   if (n16 == 0) return;
-  k_pack_nibbles<<<(unsigned)((n16 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(lm_bytes),
-                                                                reinterpret_cast<uint2*>(lm_nibbles), n16);
+  k_pack_nibbles<<<dim3((unsigned)((n16 + 255) / 256), n_frames), 256, 0, s>>>(lm_bytes, bytes_stride, lm_nibbles, nib_stride, n16, ctl);
 }
 
-void launch_refine(bool nibble_planes, const RefineParams& p, const CoarseTpl* ctpl, const WorkItem* items, const Cand* cand,
-                   uint32_t cand_cap, ResultHeader* hdr, lm_raw_match* out, uint32_t out_cap, cudaStream_t s) {
-  if (nibble_planes) {  // one warp per candidate, 3 resident CTAs per SM
-    cudaLaunchConfig_t cfg = pdl_config(148 * 3, kRefineWarps * 32, s);
-    cudaLaunchKernelEx(&cfg, k_refine_nib, p, ctpl, cand, cand_cap, hdr, out, out_cap);
-  } else {
-    cudaLaunchConfig_t cfg = pdl_config(148 * 4, kRefineWarps * 32, s);
-    cudaLaunchKernelEx(&cfg, k_refine, p, ctpl, items, cand, cand_cap, hdr, out, out_cap);
-  }
+void launch_begin_chunk(const FrameTable& ft, BatchCtl* ctl, uint8_t* results, size_t result_stride, int n_blocks,
+                        cudaStream_t s) {
+  k_begin_chunk<<<1, 256, 0, s>>>(ft, ctl, results, result_stride, n_blocks);
+}
+
+void launch_refine(const RefineParams& p, const CoarseTpl* ctpl, const Cand* cand, uint32_t cand_cap, BatchCtl* ctl,
+                   uint8_t* results, size_t result_stride, uint32_t out_cap, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = pdl_config(148 * 3, kRefineWarps * 32, s);  // 3 resident CTAs per SM
+  cudaLaunchKernelEx(&cfg, k_refine_nib, p, ctpl, cand, cand_cap, ctl, results, result_stride, out_cap);
 }
 
 }  // namespace lmk

@@ -248,9 +248,10 @@ int train_device_batch(lm_detector* d, int rows, int cols, int n, const void* co
   for (int v = 0; v < n; ++v) {
     const int li = v % lanes;
     Lane& ln = d->lane[li];
-    for (int m = 0; m < M; ++m) { ln.src_ptr[m] = d_src[v * M + m]; ln.has_mask[m] = false; }
+    for (int m = 0; m < M; ++m) { ln.src_ptr[0][m] = d_src[v * M + m]; ln.has_mask[m] = false; }
     ln.launches = 0;
-    if (run_quantize(d, ln, ln.stream) != LM_OK) return LM_E_CUDA;
+    if (begin_chunk(d, ln, 1, 0, ln.stream) != LM_OK) return LM_E_CUDA;
+    if (run_quantize(d, ln, 1, ln.stream) != LM_OK) return LM_E_CUDA;
     for (int m = 0; m < M; ++m) {
       const lm_modality_desc& md = d->model.mods[m];
       TrainViewParams tp;

@@ -17,6 +17,7 @@ import torch.distributed as dist
 from ._capi import RAW_DTYPE, RESULT_HEADER_BYTES
 
 RECORD_BYTES = RAW_DTYPE.itemsize
+CANDIDATE_OVERFLOW = 1 << 40   # "records needed" value that stands for: a rank's coarse candidate list was truncated
 
 
 class _DevicePtr:
@@ -49,8 +50,9 @@ def unpack_blocks(gathered, world, capacity):
         blk = gathered[r * stride:(r + 1) * stride]
         hdr = blk[:RESULT_HEADER_BYTES].view(np.uint32)
         count = int(hdr[0])
-        if hdr[2] != 0 and count <= capacity:   # not the record block: the candidate list was truncated
-            raise RuntimeError("rank %d overflowed its device-side candidate list" % r)
+        if hdr[2] != 0 and count <= capacity:   # not the record block: the rank's candidate list was truncated
+            need = max(need, CANDIDATE_OVERFLOW)
+            continue
         if count > capacity:                    # (also when the device block itself overflowed: count keeps counting)
             need = max(need, count)
             continue
@@ -132,7 +134,7 @@ class ShardedMatcher:
             if need == 0:
                 return raws, 0
             if need > (block.numel() - RESULT_HEADER_BYTES) // RECORD_BYTES:
-                return None, need          # the rank-local block itself is too small: the local match must be redone
+                return None, need          # the rank-local block (or candidate list) is too small: redo the local match
             self.capacity = int(need * 1.25) + 64
 
     def grow_local(self, need):
@@ -165,6 +167,10 @@ class ShardedDetector(ShardedMatcher):
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         detector.set_shard(rank, world)
+        # the library's device record blocks must hold at least what one exchange slot carries
+        self._device_cap = max(int(capacity), 2048)
+        self._cand_per_frame = 1 << 16
+        detector.set_option("device_out_cap", self._device_cap)
         self.device = torch.device("cuda", torch.cuda.current_device())
         super().__init__(self._local, detector.finalize_raw, rank, world, group, capacity)
 
@@ -175,7 +181,12 @@ class ShardedDetector(ShardedMatcher):
         return device_view(rec, cap, self.device)
 
     def grow_local(self, need):
-        self.det.set_option("device_out_cap", int(need * 1.25) + 64)   # the library re-allocates its record blocks
+        if need >= CANDIDATE_OVERFLOW:   # a rank's coarse candidate list was truncated: every rank grows it alike
+            self._cand_per_frame *= 4
+            self.det.set_option("cand_per_frame", self._cand_per_frame)
+            return
+        self._device_cap = max(self._device_cap, int(need * 1.25) + 64)
+        self.det.set_option("device_out_cap", self._device_cap)   # the library re-allocates its record blocks
 
     def frame_buffers(self, rows, cols, kinds):
         """Device buffers for one frame: uint8 [rows, cols, 3] for ColorGradient, int16-typed uint16 storage for depth."""
@@ -190,11 +201,11 @@ class ShardedDetector(ShardedMatcher):
         _capi.check(_capi.lib().lm_copy_result_block(self.det._h, lane, self._send_ptrs[slot], nbytes, stream))
 
     # ------------------------------------------------------------------ streamed frames
-    def match_stream(self, host_frames, queries, kinds=("cg", "dn"), chunk=16, lanes=8):
+    def match_stream(self, host_frames, queries, kinds=("cg", "dn"), chunk=16, lanes=4):
         """A stream of frames through the sharded matcher, pipelined: per chunk of `chunk` frames ONE broadcast per
         modality (rank 0 uploads its pinned host frames into a device chunk buffer first) and ONE all-gather of the
-        survivor blocks; within a chunk `lanes` frames are in flight on as many streams; the upload + broadcast of chunk
-        c+1 overlaps the matching of chunk c (two chunk buffers).
+        survivor blocks; within a chunk the library runs launch sets of "batch_frames" frames on `lanes` streams; the
+        upload + broadcast of chunk c+1 overlaps the matching of chunk c (two chunk buffers).
 
         host_frames: list of per-frame lists of numpy arrays (pinned for full copy speed); their contents matter on
         rank 0 only, every rank must pass the same number of frames of the same shape.
@@ -265,29 +276,35 @@ class ShardedDetector(ShardedMatcher):
             st["free"][b] = done
             return host, done, g, lo
 
-        def redo(j, lo):   # rare: this frame again through the per-frame path, which grows its own exchange
+        def redo(frame):   # rare: this frame again through the per-frame path, which grows its own exchange
             keep = self.capacity
             if not hasattr(self, "_redo_bufs") or self._redo_bufs[0].shape[:2] != (rows, cols):
                 self._redo_bufs = self.frame_buffers(rows, cols, kinds)
             if self.rank == 0:
                 for m, k in enumerate(kinds):
-                    a = host_frames[lo + j][m]
+                    a = host_frames[frame][m]
                     self._redo_bufs[m].copy_(torch.from_numpy(a if k == "cg" else a.view(np.int16)))
             res = self.match(self._redo_bufs, queries)
             self.capacity = keep
             return res
+
+        deferred = []   # (index into results, frame) of frames that take the per-frame fallback once the stream has drained:
+                        # the fallback uses lane 0 of the same handle, which frames of later chunks are still using now
 
         def finish(host, done, g, lo):
             done.synchronize()
             arr = host.numpy()                                   # [world][chunk][block bytes]
             world, slots, block_bytes = arr.shape
             hdr = np.ascontiguousarray(arr[:, :g, :RESULT_HEADER_BYTES]).view(np.uint32).reshape(world, g, 4)
-            # every rank sees every header, so all ranks agree on which frames outgrew the staged capacity
-            over = (hdr[:, :, 0] > self.capacity).any(axis=0)
-            if ((hdr[:, :, 2] != 0).any(axis=0) & ~over).any():
-                raise RuntimeError("a rank overflowed its device-side candidate list")
+            # every rank sees every header, so all ranks agree on which frames outgrew the staged capacity (or, flagged by
+            # the device, a rank's candidate list) and defer the same frames in the same order
+            over = (hdr[:, :, 0] > self.capacity).any(axis=0) | (hdr[:, :, 2] != 0).any(axis=0)
+            base = len(results)
+            for j in range(g):
+                if over[j]:
+                    deferred.append((base + j, lo + j))
             if self.rank != 0:
-                return [redo(j, lo) if over[j] else None for j in range(g)]
+                return [None] * g
             # rank 0: the whole chunk is ordered / de-duplicated in one library call (lm_finalize_gathered)
             outp = C.c_void_p()
             offs = (C.c_size_t * (g * n_q + 1))()
@@ -295,12 +312,8 @@ class ShardedDetector(ShardedMatcher):
             _capi.check(lib.lm_finalize_gathered(self.det._h, arr.ctypes.data, world, g, block_bytes, slots * block_bytes,
                                                  self.capacity, n_q, C.byref(outp), offs, status.ctypes.data))
             allm = self.det._take(outp, offs[g * n_q])
-            out = []
-            for j in range(g):
-                if status[j] == 2:
-                    raise RuntimeError("a rank overflowed its device-side candidate list")
-                out.append(redo(j, lo) if status[j] == 1 else [allm[offs[j * n_q + q]:offs[j * n_q + q + 1]] for q in range(n_q)])
-            return out
+            assert all((status[j] != 0) == bool(over[j]) for j in range(g))
+            return [None if over[j] else [allm[offs[j * n_q + q]:offs[j * n_q + q + 1]] for q in range(n_q)] for j in range(g)]
 
         results = []
         stage(0)
@@ -313,4 +326,8 @@ class ShardedDetector(ShardedMatcher):
                 results.extend(finish(*pending))
             pending = cur
         results.extend(finish(*pending))
+        if deferred:
+            torch.cuda.synchronize(self.device)    # every lane stream idle: lane 0 is free for the per-frame path
+            for at, frame in deferred:
+                results[at] = redo(frame)
         return results if self.rank == 0 else None

@@ -26,6 +26,7 @@
 // Build: see oracle/Makefile  (g++ -O3 -msse4.1 -ffp-contract=off -pthread -shared -fPIC)
 // =====================================================================================
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cfloat>
@@ -34,10 +35,18 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
+
+#include <emmintrin.h>
+#include <smmintrin.h>
+#include <tmmintrin.h>
 
 namespace {
 
@@ -401,6 +410,12 @@ static void linearize_T(const uint8_t* resp, int rows, int cols, int T, uint8_t*
 }
 
 // ----------------------------------------------------------------------------- detector state
+class BandPool;
+struct FastScratch {  // working buffers of the baseline front end (linemod_fast.inc), kept between frames
+  std::vector<uint8_t> img, next, sm, qbin, raw, mask;
+  std::vector<uint16_t> depth;
+};
+
 struct LevelMod {  // per (level, modality) products of the front end, kept for the parity taps
   int rows = 0, cols = 0, T = 0, W = 0, H = 0;
   std::vector<uint8_t> quant_raw;  // unmasked quantisation (CG "angle" / DN "normal")
@@ -419,6 +434,9 @@ struct Detector {
   uint8_t sim_lut[256];
   uint8_t normal_lut[8000];
   int threads = 1;
+  bool fast = false;   // front end by linemod_fast.inc (the CPU baseline's SSE / threaded routines) instead of the plain code
+  std::shared_ptr<BandPool> pool;
+  std::vector<FastScratch> scratch;
   // last frame
   std::vector<LevelMod> front;  // index l*M+m
   std::vector<CandRec> last_cands;
@@ -701,7 +719,13 @@ static void similarity(const LevelMod& lm, const Template& t, uint8_t* dst) {
     const Feature& f = t.features[i];
     if (f.x < 0 || f.x >= lm.cols || f.y < 0 || f.y >= lm.rows) continue;
     const uint8_t* p = access_lm(lm, f);
-    for (int j = 0; j < P; ++j) dst[j] = (uint8_t)(dst[j] + p[j]);
+    // [OCV] "dst[j] += lm_ptr[j]" with _mm_add_epi8 over unaligned 16-byte blocks (upstream's HAVE_SSE2 branch), scalar tail
+    int j = 0;
+    for (; j + 16 <= P; j += 16)
+      _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + j),
+                       _mm_add_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i*>(dst + j)),
+                                    _mm_loadu_si128(reinterpret_cast<const __m128i*>(p + j))));
+    for (; j < P; ++j) dst[j] = (uint8_t)(dst[j] + p[j]);
   }
 }
 
@@ -844,6 +868,14 @@ static bool build_front(Detector& det, const Source* srcs, int nsrc, const Sourc
   return true;
 }
 
+#include "linemod_fast.inc"
+
+static bool build_front_any(Detector& det, const Source* srcs, int nsrc, const Source* masks, int nmasks) {
+  if (!det.fast) return build_front(det, srcs, nsrc, masks, nmasks);
+  if (!det.pool || det.pool->size() != det.threads) det.pool.reset(new BandPool(det.threads));
+  return build_front_fast(det, *det.pool, srcs, nsrc, masks, nmasks);
+}
+
 static int class_index_of(const Detector& det, const std::string& id) {
   int i = 0;
   for (auto it = det.classes.begin(); it != det.classes.end(); ++it, ++i)
@@ -944,6 +976,7 @@ void* orc_create(const int32_t* T, int levels, const orc_modality* mods, int M) 
 void orc_destroy(void* h) { delete (Detector*)h; }
 const char* orc_last_error(void* h) { return ((Detector*)h)->err.c_str(); }
 void orc_set_threads(void* h, int n) { ((Detector*)h)->threads = n < 1 ? 1 : n; }
+void orc_set_fast(void* h, int on) { ((Detector*)h)->fast = on != 0; }
 int orc_max_threads() {
   unsigned n = std::thread::hardware_concurrency();
   return n ? (int)n : 1;
@@ -953,30 +986,94 @@ void orc_get_similarity_lut(void* h, uint8_t* lut) { std::memcpy(lut, ((Detector
 void orc_set_normal_lut(void* h, const uint8_t* lut) { std::memcpy(((Detector*)h)->normal_lut, lut, 8000); }
 void orc_get_normal_lut(void* h, uint8_t* lut) { std::memcpy(lut, ((Detector*)h)->normal_lut, 8000); }
 
-// [OCV] Detector::addTemplate.  Returns template_id, -1 if any level lacks candidates, -2 on error.
-int orc_add_template(void* h, const orc_image* srcs, int nsrc, const char* class_id, const orc_image* mask,
-                     int32_t* bb /*nullable [x,y,w,h]*/) {
-  Detector& det = *(Detector*)h;
+// [OCV] Detector::addTemplate up to the point where the pyramid joins the class: quantise, extract per level and
+// modality, cropTemplates.  Reads the detector only (thread-safe).  0 = ok, -1 = some level lacks candidates, -2 = error.
+static int extract_pyramid(const Detector& det, const orc_image* srcs, const orc_image* mask, TemplatePyramid& tp, int box[4],
+                           std::string& err) {
   const int L = det.levels(), M = det.M();
-  if (nsrc != M) { det.err = "sources.size() != modalities.size()"; return -2; }
-  std::vector<TemplatePyramid>& tps = det.classes[class_id];
-  int template_id = (int)tps.size();
-  TemplatePyramid tp((size_t)L * M);
+  tp.assign((size_t)L * M, Template());
   Source msk; if (mask && mask->data) msk = to_source(*mask);
   for (int m = 0; m < M; ++m) {
     QuantPyr q;
-    if (!pyr_process(det, det.mods[m], to_source(srcs[m]), (mask && mask->data) ? &msk : nullptr, q, det.err)) return -2;
+    if (!pyr_process(det, det.mods[m], to_source(srcs[m]), (mask && mask->data) ? &msk : nullptr, q, err)) return -2;
     for (int l = 0; l < L; ++l) {
       if (l > 0) pyr_down(q);
       bool ok = det.mods[m].type == MOD_COLOR_GRADIENT ? cg_extract(q, tp[(size_t)l * M + m]) : dn_extract(q, tp[(size_t)l * M + m]);
       if (!ok) return -1;
     }
   }
-  int box[4];
   crop_templates(tp, box);
+  return 0;
+}
+
+// [OCV] Detector::addTemplate.  Returns template_id, -1 if any level lacks candidates, -2 on error.
+int orc_add_template(void* h, const orc_image* srcs, int nsrc, const char* class_id, const orc_image* mask,
+                     int32_t* bb /*nullable [x,y,w,h]*/) {
+  Detector& det = *(Detector*)h;
+  if (nsrc != det.M()) { det.err = "sources.size() != modalities.size()"; return -2; }
+  std::vector<TemplatePyramid>& tps = det.classes[class_id];
+  int template_id = (int)tps.size();
+  TemplatePyramid tp;
+  int box[4];
+  const int rc = extract_pyramid(det, srcs, mask, tp, box, det.err);
+  if (rc != 0) return rc;
   if (bb) { bb[0] = box[0]; bb[1] = box[1]; bb[2] = box[2]; bb[3] = box[3]; }
   tps.push_back(tp);
   return template_id;
+}
+
+// The trainer's loop (/root/reference/src/renderer.cpp:239-329: render a view, addTemplate) for n views with the scalar
+// rasteriser of render_oracle.cpp, det.threads views at a time; templates join the class in view order, so the result
+// equals n sequential render + orc_add_template calls.  Modalities must be (ColorGradient, DepthNormal) in that order or
+// a prefix / single one of them.  tids[v] = template_id or -1; returns the number of templates added, -2 on error.
+struct OrcCameraDesc { int32_t width, height; double fx, fy, near_, far_; };
+int orc_render(const float* tris, int n_tri, const OrcCameraDesc* cam, const double T[3], const double up[3], uint8_t* bgr,
+               uint16_t* depth, uint8_t* mask, int32_t rect[4]);
+int orc_train_views(void* h, const float* tris, int n_tri, const OrcCameraDesc* cam, const double* T, const double* up, int n_views,
+                    const char* class_id, int32_t* tids) {
+  Detector& det = *(Detector*)h;
+  const int M = det.M();
+  std::vector<TemplatePyramid> pyr((size_t)n_views);
+  std::vector<int> status((size_t)n_views, -2);
+  std::atomic<int> next(0);
+  const size_t px = (size_t)cam->width * cam->height;
+  auto worker = [&]() {
+    std::vector<uint8_t> bgr(px * 3), mask(px);
+    std::vector<uint16_t> depth(px);
+    std::string err;
+    for (;;) {
+      const int v = next.fetch_add(1);
+      if (v >= n_views) break;
+      int32_t rect[4];
+      if (orc_render(tris, n_tri, cam, T + 3 * v, up + 3 * v, bgr.data(), depth.data(), mask.data(), rect) != 0) continue;
+      orc_image srcs[4], mk;
+      mk.data = mask.data(); mk.rows = cam->height; mk.cols = cam->width; mk.type = 2; mk.step = (size_t)cam->width;
+      for (int m = 0; m < M; ++m) {
+        const bool cg = det.mods[m].type == MOD_COLOR_GRADIENT;
+        srcs[m].data = cg ? (const void*)bgr.data() : (const void*)depth.data();
+        srcs[m].rows = cam->height; srcs[m].cols = cam->width; srcs[m].type = cg ? 0 : 1;
+        srcs[m].step = (size_t)cam->width * (cg ? 3 : 2);
+      }
+      int box[4];
+      status[v] = extract_pyramid(det, srcs, &mk, pyr[v], box, err);
+    }
+  };
+  if (det.threads <= 1) worker();
+  else {
+    std::vector<std::thread> pool;
+    for (int w = 0; w < det.threads; ++w) pool.emplace_back(worker);
+    for (auto& th : pool) th.join();
+  }
+  std::vector<TemplatePyramid>& tps = det.classes[class_id];
+  int added = 0;
+  for (int v = 0; v < n_views; ++v) {
+    if (tids) tids[v] = -1;
+    if (status[v] != 0) continue;
+    if (tids) tids[v] = (int)tps.size();
+    tps.push_back(pyr[v]);
+    ++added;
+  }
+  return added;
 }
 
 // [OCV] Detector::addSyntheticTemplate, flat encoding: per template (L*M of them) {width,height,level,nfeat},
@@ -1037,7 +1134,7 @@ int orc_build_front(void* h, const orc_image* srcs, int nsrc, const orc_image* m
   std::vector<Source> s, mk;
   for (int i = 0; i < nsrc; ++i) s.push_back(to_source(srcs[i]));
   for (int i = 0; i < nmasks; ++i) mk.push_back(to_source(masks[i]));
-  return build_front(det, s.data(), nsrc, mk.data(), nmasks) ? 0 : -2;
+  return build_front_any(det, s.data(), nsrc, mk.data(), nmasks) ? 0 : -2;
 }
 
 // Matching only, on the front end of the last orc_build_front / orc_match call.  Returns #matches (or -2);
@@ -1122,6 +1219,7 @@ void orc_prim_phase_deg(const float* x, const float* y, size_t n, float* out) { 
 void orc_prim_pyrdown(const uint8_t* src, int rows, int cols, int ch, uint8_t* dst) { pyrdown_u8(src, rows, cols, ch, dst); }
 void orc_prim_nn_half(const uint8_t* src, int rows, int cols, uint8_t* dst) { nn_half_u8(src, rows, cols, dst); }
 void orc_prim_median5(const uint8_t* src, int rows, int cols, uint8_t* dst) { median5_u8(src, rows, cols, dst); }
+void orc_prim_median5_fast(const uint8_t* src, int rows, int cols, uint8_t* dst) { fast_median5_rows(src, rows, cols, 0, rows, dst); }
 void orc_prim_erode3(const uint8_t* src, int rows, int cols, int iterations, uint8_t* dst) { erode3_u8(src, rows, cols, iterations, dst); }
 void orc_prim_distance_c3(const uint8_t* src, int rows, int cols, float* dst) { distance_transform_c3(src, rows, cols, dst); }
 void orc_prim_cg_quantize(const uint8_t* bgr, int rows, int cols, float weak, float* magnitude, uint8_t* quantized, float* angle) {

@@ -106,6 +106,9 @@ def lib():
                                       C.POINTER(C.c_float)]
         L.orc_view_list.argtypes = [C.POINTER(OrcViewSphere), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_look_at.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_set_fast.argtypes = [C.c_void_p, C.c_int]
+        L.orc_train_views.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OrcCamera), C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_char_p, C.c_void_p]
         L.orc_render.argtypes = [C.c_void_p, C.c_int, C.POINTER(OrcCamera), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]
         L.orc_depth_diff.restype = C.c_double
@@ -171,6 +174,11 @@ class OracleDetector:
     def set_threads(self, n):
         lib().orc_set_threads(self._h, int(n))
 
+    def set_fast(self, on=True):
+        """Front end by the CPU baseline's SSE / threaded routines (linemod_fast.inc) instead of the plain restatement;
+        results are identical (tests/test_oracle_fast.py)."""
+        lib().orc_set_fast(self._h, int(bool(on)))
+
     @staticmethod
     def max_threads():
         return lib().orc_max_threads()
@@ -210,6 +218,18 @@ class OracleDetector:
         if r == -2:
             raise ValueError(self._err())
         return r, tuple(bb)
+
+    def train_views(self, triangles, cam, T, up, class_id):
+        """The trainer's loop (render + addTemplate per view, det threads at a time, templates in view order).
+        -> int32 template ids per view (-1: some level lacked candidates)."""
+        tri = np.ascontiguousarray(triangles, np.float32).reshape(-1, 9)
+        T, up = np.ascontiguousarray(T, np.float64).reshape(-1, 3), np.ascontiguousarray(up, np.float64).reshape(-1, 3)
+        tids = np.zeros(len(T), np.int32)
+        rc = lib().orc_train_views(self._h, tri.ctypes.data, len(tri), C.byref(cam), T.ctypes.data, up.ctypes.data, len(T),
+                                   class_id.encode(), tids.ctypes.data)
+        if rc < 0:
+            raise RuntimeError("orc_train_views failed: " + self._err())
+        return tids
 
     def add_synthetic_template(self, class_id, templates):
         """templates: list (L*M) of (width, height, pyramid_level, features[n,3] int)."""
@@ -387,6 +407,14 @@ def prim_median5(src):
     src = np.ascontiguousarray(src)
     dst = np.empty_like(src)
     lib().orc_prim_median5(_p(src), src.shape[0], src.shape[1], _p(dst))
+    return dst
+
+
+def prim_median5_fast(src):
+    """The CPU baseline's SSE selection network (linemod_fast.inc) on the same input."""
+    src = np.ascontiguousarray(src)
+    dst = np.empty_like(src)
+    lib().orc_prim_median5_fast(_p(src), src.shape[0], src.shape[1], _p(dst))
     return dst
 
 

@@ -53,10 +53,8 @@ def test_front_end_taps_bit_exact(rows, cols, T, kinds):
         bgr, depth, _ = synth.compose_scene(seed, views, rows=rows, cols=cols)
         src = common.sources_for(kinds, bgr, depth)
         orc.build_front(src)
-        for variant in (0, 1):  # 0: fused production kernels, 1: stage-by-stage A/B reference kernels
-            det.set_option("frontend_variant", variant)
-            det.build_front(src)
-            _check_stages(orc, det, len(T), len(kinds), kinds)
+        det.build_front(src)
+        _check_stages(orc, det, len(T), len(kinds), kinds)
         for l in range(len(T)):
             go, gd = orc.geometry(l), det.geometry(l)
             assert go == gd
@@ -108,13 +106,14 @@ def test_coarse_similarity_maps_bit_exact():
         assert np.array_equal(a, b), "coarse map of template %d differs in %d cells" % (tid, np.count_nonzero(a != b))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
-def test_coarse_kernel_variants(variant):
-    """0: nibble-packed linear memories, 128-bit windows (production); 2: nibble-packed, 64-bit windows; 1: byte linear
-    memories.  Every variant must give the oracle's coarse maps and match lists; the packed planes must be the byte
-    planes two positions per byte."""
+@pytest.mark.parametrize("graphs", [1, 0])
+def test_coarse_kernel_maps_lists_and_packed_planes(graphs):
+    """The coarse kernel (nibble-packed linear memories, tile records, exact early termination) must give the oracle's
+    coarse maps and match lists, replayed from the lane's CUDA graph or launched plainly; the packed planes must be the
+    reference's byte planes two positions per byte."""
+    variant = graphs
     orc, det, views = _pair(n_views=8, n_random=90, seed=21, classes=("a", "b"))
-    det.set_option("coarse_variant", variant)
+    det.set_option("graphs", graphs)
     bgr, depth, _ = synth.compose_scene(1003, views[:4])
     orc.build_front([bgr, depth])
     det.build_front([bgr, depth])
@@ -154,13 +153,12 @@ def test_modality_order_of_the_coarse_sum_does_not_change_results(order, kinds):
     assert len(want) > 0
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-def test_refine_kernel_variants(variant):
-    """0: refinement on nibble-packed planes (production when every refinement level has word-aligned rows), 1: on byte
-    planes.  Loose thresholds so that thousands of candidates are refined; both must give the oracle's lists, and the
-    packed planes of the refinement level must be its byte planes two positions per byte."""
+@pytest.mark.parametrize("variant", [0])
+def test_refine_kernel_many_candidates(variant):
+    """Refinement on nibble-packed planes with loose thresholds so that thousands of candidates are refined (warp per
+    candidate) and a tight one (block per candidate); the lists must be the oracle's, and the packed planes of the
+    refinement level must be its byte planes two positions per byte."""
     orc, det, views = _pair(n_views=8, n_random=60, seed=23, classes=("a", "b"))
-    det.set_option("refine_variant", variant)
     for seed, thr in ((1005, 86.0), (1006, 58.0)):
         bgr, depth, _ = synth.compose_scene(seed, views[:5])
         want = orc.match([bgr, depth], thr, keep_candidates=True)
@@ -486,38 +484,65 @@ def test_sharded_stream_single_rank():
     assert total > 0
 
 
-def test_lane_result_blocks_are_one_region():
-    """lm_device_result_region: the record blocks of all lanes are contiguous, lane stride apart, and are the blocks
-    lm_match_device_multi_lane reports; lm_copy_result_block copies a block's head."""
+def test_chunk_result_blocks_are_one_region():
+    """lm_match_device_stream runs a chunk of device-resident frames as ONE launch set on a lane (no copies: the kernels
+    read the caller's buffers through the frame table); lm_device_result_region: the chunk's record blocks lie frame stride
+    apart; lm_copy_result_block copies the first block's head; the staged heads equal the blocks."""
     import ctypes as C
 
     import torch
-    from linemod_pose_estimation_b200 import _capi
-    from linemod_pose_estimation_b200.sharding import device_view
+    from linemod_pose_estimation_b200 import RAW_DTYPE, _capi
     orc, det, views = _pair(n_views=6, n_random=20, seed=97)
-    bgr, depth, _ = synth.compose_scene(6001, views[:4])
     dev = torch.device("cuda", 0)
-    d_bgr, d_depth = torch.from_numpy(bgr).to(dev), torch.from_numpy(depth.view(np.int16)).to(dev)
+    frames = [synth.compose_scene(6001 + i, views[i % 3:i % 3 + 3])[:2] for i in range(5)]
+    d_frames = [(torch.from_numpy(b).to(dev), torch.from_numpy(d.view(np.int16)).to(dev)) for (b, d) in frames]
     lib = _capi.lib()
-    base, stride, n_lanes = C.c_void_p(), C.c_size_t(), C.c_int()
-    _capi.check(lib.lm_device_result_region(det._h, C.byref(base), C.byref(stride), C.byref(n_lanes)))
-    assert n_lanes.value >= 2 and stride.value % 256 == 0
     qarr, _keep = _capi.query_array([(88.0, [])])
-    ptrs = (C.c_void_p * 2)(d_bgr.data_ptr(), d_depth.data_ptr())
+    flat = [p for (b, d) in d_frames for p in (b.data_ptr(), d.data_ptr())]
+    ptrs = (C.c_void_p * len(flat))(*flat)
     s = torch.cuda.current_stream().cuda_stream
-    want = orc.match([bgr, depth], 88.0)   # 364 survivors before sort/unique: inside the 512 records copied below
-    for lane in range(n_lanes.value):
-        rec, cap = C.c_void_p(), C.c_size_t()
-        _capi.check(lib.lm_match_device_multi_lane(det._h, lane, ptrs, 2, 480, 640, qarr, 1, C.c_void_p(s), C.byref(rec), C.byref(cap)))
-        assert rec.value == base.value + lane * stride.value
-        dst = torch.zeros(16 + 512 * 32, dtype=torch.uint8, device=dev)
-        _capi.check(lib.lm_copy_result_block(det._h, lane, dst.data_ptr(), dst.numel(), s))
-        block = dst.cpu().numpy()
+    streams = (C.c_void_p * 1)(s)
+    slot = 16 + 1024 * 32
+    stage = torch.zeros(5 * slot, dtype=torch.uint8, device=dev)
+    _capi.check(lib.lm_match_device_stream(det._h, ptrs, 5, 2, 480, 640, qarr, 1, streams, 1, stage.data_ptr(), slot))
+    base, stride, n_frames = C.c_void_p(), C.c_size_t(), C.c_int()
+    _capi.check(lib.lm_device_result_region(det._h, 0, C.byref(base), C.byref(stride), C.byref(n_frames)))
+    assert n_frames.value >= 5 and stride.value % 256 == 0
+    head = torch.zeros(slot, dtype=torch.uint8, device=dev)
+    _capi.check(lib.lm_copy_result_block(det._h, 0, head.data_ptr(), slot, s))
+    torch.cuda.synchronize()
+    from linemod_pose_estimation_b200.sharding import device_view
+    region = device_view(base.value, stride.value * 5, dev).cpu().numpy()
+    staged = stage.cpu().numpy()
+    assert np.array_equal(head.cpu().numpy()[:16], staged[:16])
+    for f, (bgr, depth) in enumerate(frames):
+        block = staged[f * slot:(f + 1) * slot]
         hdr = block[:16].view(np.uint32)
-        assert hdr[2] == 0 and 0 < hdr[0] <= 512
-        from linemod_pose_estimation_b200 import RAW_DTYPE
-        raw = block[16:16 + int(hdr[0]) * 32].view(RAW_DTYPE).copy()
-        common.assert_matches_equal(det.finalize_raw(raw), want, "lane %d" % lane)
+        assert hdr[2] == 0 and 0 < hdr[0] <= 1024
+        n = int(hdr[0])
+        assert np.array_equal(region[f * stride.value:f * stride.value + 16 + n * 32], block[:16 + n * 32])
+        raw = block[16:16 + n * 32].view(RAW_DTYPE).copy()
+        common.assert_matches_equal(det.finalize_raw(raw), orc.match([bgr, depth], 88.0), "frame %d" % f)
+
+
+@pytest.mark.parametrize("batch_frames,lanes", [(1, 2), (3, 1), (8, 4), (16, 3), (32, 2)])
+def test_chunked_batches_equal_the_oracle(batch_frames, lanes):
+    """lm_match_batch_multi cuts the frames into chunks of `batch_frames` (one launch set per chunk) pipelined over
+    `batch_lanes` lanes: every chunk size, ragged tails included, must give each frame the oracle's lists; a frame whose
+    survivors outgrow its record block (66 % over all classes) is redone alone."""
+    orc, det, views = _pair(n_views=8, n_random=40, seed=89, classes=("cpu_binary", "memoryChip2"))
+    det.set_option("batch_frames", batch_frames)
+    det.set_option("batch_lanes", lanes)
+    queries = [(88.0, ["memoryChip2"]), (66.0, [])]
+    frames = [list(synth.compose_scene(5100 + i, views[i % 4:i % 4 + 4])[:2]) for i in range(21)]
+    got = det.match_batch_multi(frames, queries)
+    assert len(got) == len(frames)
+    total = 0
+    for f, per_query in zip(frames, got):
+        for (thr, ids), g in zip(queries, per_query):
+            common.assert_matches_equal(g, orc.match(f, thr, class_ids=ids), "chunk %d" % batch_frames)
+            total += len(g)
+    assert total > 0
 
 
 def test_config5_64_frame_batch_15_classes():
