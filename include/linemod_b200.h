@@ -394,9 +394,10 @@ long lm_debug_presort(lm_detector* det, lm_match_rec* dst /*nullable*/);
  * the "timing" option on (plain launches with events between the stages instead of the lane's CUDA graph):
  * [0] H2D, [1] front end, [2] coarse similarity, [3] local refinement, [4] D2H; and the kernel launches of the last call. */
 int lm_last_timings(const lm_detector* det, float ms[5], int* kernel_launches);
-/* Algorithmic bytes of the last match: [0] B_front [1] B_coarse [2] B_refine [3] B_out,
- * and [4] coarse candidates, [5] template*position evals, [6] the part of B_coarse the coarse kernel actually gathered
- * (exact early termination skips features of tiles in which no position can reach the threshold any more), [7] 0. */
+/* Algorithmic bytes of the last launch set on lane 0 -- the last lm_match call, or the last chunk of
+ * an lm_match_batch* call that lane 0 processed: [0] B_front per frame, [1] B_coarse [2] B_refine [3] B_out of all its frames,
+ * [4] coarse candidates, [5] template*position evals, [6] the part of B_coarse the coarse kernel actually gathered (exact
+ * early termination skips features of tiles in which no position can reach the threshold any more), [7] frames in the set. */
 int lm_last_work(const lm_detector* det, uint64_t out[8]);
 /* Tuning switches: "batch_frames" (frames per chunk = per launch set on the batched paths, 1..32, default 8),
  * "batch_lanes" (chunks in flight in lm_match_batch*, default 4), "prune" (1 = exact early termination in the coarse

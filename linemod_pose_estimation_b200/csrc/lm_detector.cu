@@ -853,6 +853,7 @@ static int match_one(lm_detector* d, Lane& ln, int frame, const Query* queries, 
   ln.work_stats[5] = (uint64_t)plan->n_items * (uint64_t)(ln.geom.back().W * ln.geom.back().H);
   ln.work_stats[2] = plan->n_items ? (uint64_t)((double)n_cands * (plan->refine_nf_sum / plan->n_items) * 256.0) : 0;
   ln.work_stats[3] = 20ull * raw.size();
+  ln.work_stats[7] = 1;
   finalize_queries(d, ln, raw, n_q, out);
   return LM_OK;
 }
@@ -946,12 +947,9 @@ int lm_create_from_yaml(const char* path, lm_detector** out) {
   *out = nullptr;
   lm_detector* d = new lm_detector();
   std::string err;
-  if (!load_detector_yaml(path, d->model, err)) { delete d; return lm_fail(LM_E_IO, "%s", err.c_str()); }
-  for (auto& kv : d->model.classes)
-    for (auto& tp : kv.second) {
-      if ((int)tp.size() != d->model.levels() * d->model.M()) { delete d; return lm_fail(LM_E_IO, "%s: class '%s' has a template pyramid of the wrong size", path, kv.first.c_str()); }
-      for (auto& t : tp) if (t.features.size() > LM_MAX_FEATURES) { delete d; return lm_fail(LM_E_IO, "%s: features.size() <= 63 violated", path); }
-    }
+  bool ok = false;
+  try { ok = load_detector_yaml(path, d->model, err); } catch (const std::exception& e) { err = std::string(path) + ": " + e.what(); }
+  if (!ok) { delete d; return lm_fail(LM_E_IO, "%s", err.c_str()); }  // every pyramid was validated by the loader
   int rc = create_common(d);
   if (rc != LM_OK) { delete d; return rc; }
   refresh_class_cache(d);
@@ -964,7 +962,9 @@ int lm_create_from_cache(const char* path, lm_detector** out) {
   *out = nullptr;
   lm_detector* d = new lm_detector();
   std::string err;
-  if (!load_model_cache(path, d->model, err)) { delete d; return lm_fail(LM_E_IO, "%s", err.c_str()); }
+  bool ok = false;
+  try { ok = load_model_cache(path, d->model, err); } catch (const std::exception& e) { err = std::string(path) + ": " + e.what(); }
+  if (!ok) { delete d; return lm_fail(LM_E_IO, "%s", err.c_str()); }
   int rc = create_common(d);
   if (rc != LM_OK) { delete d; return rc; }
   refresh_class_cache(d);
@@ -997,7 +997,9 @@ int lm_read_classes(lm_detector* d, const char* const* class_ids, int n_ids, con
   const char* fmt = format ? format : "templates_%s.yml.gz";
   for (int i = 0; i < n_ids; ++i) {
     std::string err;
-    if (!load_class_file(format_name(fmt, class_ids[i]), d->model, err)) return lm_fail(LM_E_IO, "%s", err.c_str());
+    bool ok = false;
+    try { ok = load_class_file(format_name(fmt, class_ids[i]), d->model, err); } catch (const std::exception& e) { err = e.what(); }
+    if (!ok) return lm_fail(LM_E_IO, "%s", err.c_str());
   }
   refresh_class_cache(d);
   return LM_OK;
@@ -1363,21 +1365,31 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
   const int n_chunks = (n_frames + F - 1) / F;
   // per (frame, query) result lists, concatenated at the end (chunks finish in order, but a frame may be redone)
   std::vector<std::vector<lm_match_rec> > lists((size_t)n_frames * n_q);
-  struct Pending { int first = -1, n = 0; } pending[LM_LANES];
+  struct Pending { int first = -1, n = 0; const Pack::Plan* plan = nullptr; } pending[LM_LANES];
   std::vector<lm_raw_match> raw;
   auto finish = [&](int li) -> int {
     Lane& ln = d->lane[li];
     const Pending pd = pending[li];
     pending[li].first = -1;
     CU(cudaEventSynchronize(ln.ev[5]));
+    if (d->timing) collect_timings(ln);  // per-stage events of this chunk (plain launches): lm_last_timings of lane 0
     std::vector<int> redo;
+    uint64_t cands = 0, survivors = 0;
     for (int f = 0; f < pd.n; ++f) {
       bool overflow = false;
       uint32_t n_cands = 0;
       if (collect_records(ln, f, ln.stream, raw, &overflow, &n_cands) != LM_OK) return LM_E_CUDA;
+      cands += n_cands; survivors += raw.size();
       if (overflow) { redo.push_back(f); continue; }
       finalize_queries(d, ln, raw, n_q, &lists[(size_t)(pd.first + f) * n_q]);
     }
+    // work accounting of the chunk (lm_last_work reads lane 0): B_coarse of all its frames, candidates, evals, frames
+    ln.work_stats[1] = pd.plan->coarse_bytes * (uint64_t)pd.n;
+    ln.work_stats[4] = cands;
+    ln.work_stats[5] = (uint64_t)pd.plan->n_items * (uint64_t)(ln.geom.back().W * ln.geom.back().H) * (uint64_t)pd.n;
+    ln.work_stats[2] = pd.plan->n_items ? (uint64_t)((double)cands * (pd.plan->refine_nf_sum / pd.plan->n_items) * 256.0) : 0;
+    ln.work_stats[3] = 20ull * survivors;
+    ln.work_stats[7] = (uint64_t)pd.n;
     for (int f : redo) {  // rare: this frame alone with growing buffers (its sources are still in the lane's slot f)
       int rc = match_one(d, ln, f, qs, n_q, &lists[(size_t)(pd.first + f) * n_q], false);
       if (rc != LM_OK) return rc;
@@ -1404,9 +1416,9 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
     rc = frames_from_host(d, ln, fs, n, n_sources, nullptr, 0);
     if (rc != LM_OK) return rc;
     double t2 = prof ? now() : 0;
-    if (enqueue_chunk(d, ln, *plan, qs, n_q, n, ln.stream) != LM_OK) return LM_E_CUDA;
+    if (enqueue_chunk(d, ln, *plan, qs, n_q, n, ln.stream, d->timing != 0) != LM_OK) return LM_E_CUDA;
     if (enqueue_download(ln, n, ln.stream) != LM_OK) return LM_E_CUDA;
-    pending[li].first = first; pending[li].n = n;
+    pending[li].first = first; pending[li].n = n; pending[li].plan = plan;
     if (prof) { double t3 = now(); t_fin += t1 - t0; t_up += t2 - t1; t_enq += t3 - t2; }
   }
   for (int k = 0; k < NL; ++k) {  // drain in submission order

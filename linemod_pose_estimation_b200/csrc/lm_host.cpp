@@ -259,6 +259,26 @@ bool read_header(const Node& root, HostModel& model, std::string& err) {
   return true;
 }
 
+// Every template pyramid that enters a HostModel from outside (templates.yml, class files, the binary cache) passes this:
+// the packer (ensure_pack) and the kernels rely on pyramid size == levels * M, labels 0..7, |x|, |y| <= 4095 and at most
+// LM_MAX_FEATURES features -- a malformed or foreign file must end in LM_E_IO, never in a device fault or silent garbage.
+bool validate_pyramid(const HostModel& model, const TemplatePyramid& tp, std::string& err) {
+  if (tp.size() != (size_t)model.levels() * (size_t)model.M()) {
+    err = "template pyramid has " + std::to_string(tp.size()) + " templates, expected levels * modalities = " +
+          std::to_string(model.levels() * model.M());
+    return false;
+  }
+  for (const Template& t : tp) {
+    if (t.features.size() > LM_MAX_FEATURES) { err = "features.size() <= 63 violated (" + std::to_string(t.features.size()) + ")"; return false; }
+    if (t.width < 0 || t.height < 0 || t.width > 8191 || t.height > 8191) { err = "template width / height out of range"; return false; }
+    for (const Feature& f : t.features) {
+      if (f.label < 0 || f.label > 7) { err = "feature label " + std::to_string(f.label) + " outside 0..7"; return false; }
+      if (f.x < -4095 || f.x > 4095 || f.y < -4095 || f.y > 4095) { err = "feature coordinate outside +-4095"; return false; }
+    }
+  }
+  return true;
+}
+
 // [OCV] Detector::readClass (class_id_override empty)
 bool read_class(const Node& cn, HostModel& model, std::string& err) {
   const Node& mods = cn["modalities"];
@@ -297,6 +317,7 @@ bool read_class(const Node& cn, HostModel& model, std::string& err) {
         dst.features[k].label = (int)std::lrint(f.num(2));
       }
     }
+    if (!validate_pyramid(model, out[i], err)) { err = "class '" + class_id + "' template " + std::to_string(i) + ": " + err; return false; }
   }
   model.classes[class_id].swap(out);
   ++model.version;
@@ -492,6 +513,8 @@ bool load_model_cache(const std::string& path, HostModel& model, std::string& er
     std::string id(reinterpret_cast<const char*>(c.p), len);
     c.p += len;
     const uint32_t n_templates = c.get<uint32_t>();
+    // a pyramid takes at least 16 bytes per template header: bound the count by what the payload can still hold
+    if (!c.ok || (uint64_t)n_templates * 16ull * levels * M > (uint64_t)(c.end - c.p)) { c.ok = false; break; }
     std::vector<TemplatePyramid>& tps = fresh.classes[id];
     tps.resize(n_templates);
     for (uint32_t t = 0; t < n_templates && c.ok; ++t) {
@@ -507,6 +530,12 @@ bool load_model_cache(const std::string& path, HostModel& model, std::string& er
     }
   }
   if (!c.ok || c.p != c.end) { err = path + ": malformed cache payload"; return false; }
+  for (const auto& kv : fresh.classes)
+    for (size_t t = 0; t < kv.second.size(); ++t)
+      if (!validate_pyramid(fresh, kv.second[t], err)) { err = path + ": class '" + kv.first + "' template " + std::to_string(t) + ": " + err; return false; }
+  for (int T : fresh.T) if (T < 1 || T > 16) { err = path + ": unsupported T"; return false; }
+  for (const lm_modality_desc& md : fresh.mods)
+    if (md.type != LM_COLOR_GRADIENT && md.type != LM_DEPTH_NORMAL) { err = path + ": unknown modality type"; return false; }
   fresh.version = model.version + 1;
   model = fresh;
   return true;

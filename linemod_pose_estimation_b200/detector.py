@@ -385,4 +385,4 @@ class Detector:
         w = (C.c_uint64 * 8)()
         check(lib().lm_last_work(self._h, w))
         return dict(B_front=w[0], B_coarse=w[1], B_refine=w[2], B_out=w[3], candidates=w[4], evals=w[5],
-                    B_coarse_gathered=w[6])
+                    B_coarse_gathered=w[6], frames=w[7])

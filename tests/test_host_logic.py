@@ -140,6 +140,69 @@ def test_read_errors_follow_reference_asserts(tmp_path):
         Detector.read(tmp_path / "does_not_exist.yml")
 
 
+def test_malformed_template_files_end_in_io_errors(tmp_path):
+    """Templates from disk are validated before they reach the packer and the kernels: labels outside 0..7, coordinates
+    beyond +-4095, more than 63 features, pyramids of the wrong size -- in templates.yml, in class files and in the binary
+    cache (valid checksum, bad contents) -- are LM_E_IO, not device faults."""
+    import re
+    import struct
+    det = _random_detector(3)
+    p = tmp_path / "t.yml"
+    det.write(p)
+    text = p.read_text()
+    m = re.search(r"- \[ (-?\d+), (-?\d+), (\d) \]", text)
+    assert m, "feature triple not found in the written file"
+
+    def variant(name, new_triple):
+        (tmp_path / name).write_text(text[:m.start()] + "- [ %d, %d, %d ]" % new_triple + text[m.end():])
+        return tmp_path / name
+    for name, triple, what in (("label.yml", (3, 4, 9), "label"), ("coord.yml", (70000, 4, 1), "coordinate"),
+                               ("neg.yml", (3, -5000, 1), "coordinate")):
+        with pytest.raises(LinemodError) as e:
+            Detector.read(variant(name, triple))
+        assert e.value.code == -3 and what in str(e.value), str(e.value)
+    # too many features: repeat one template's feature list until it exceeds 63
+    feats = re.search(r"features:\n((?: +- \[[^\n]*\n)+)", text)
+    (tmp_path / "many.yml").write_text(text[:feats.end()] + feats.group(1) * 3 + text[feats.end():])
+    with pytest.raises(LinemodError) as e:
+        Detector.read(tmp_path / "many.yml")
+    assert e.value.code == -3 and "63" in str(e.value)
+    # class files take the same path
+    fmt = str(tmp_path / "templates_%s.yml")
+    det.writeClasses(fmt)
+    cls = open(fmt % "obj").read()
+    m2 = re.search(r"- \[ (-?\d+), (-?\d+), (\d) \]", cls)
+    open(fmt % "bad", "w").write((cls[:m2.start()] + "- [ 1, 2, 8 ]" + cls[m2.end():]).replace("class_id: obj", "class_id: bad"))
+    with pytest.raises(LinemodError) as e:
+        Detector().readClasses(["bad"], fmt)
+    assert e.value.code == -3 and "label" in str(e.value)
+    # binary cache with a consistent checksum but a label of 200 / a template count the payload cannot hold
+    cache = str(tmp_path / "t.lmb2")
+    det.write_cache(cache)
+    blob = bytearray(open(cache, "rb").read())
+
+    def fnv1a(b):
+        h = 0xcbf29ce484222325
+        for x in b:
+            h = ((h ^ x) * 0x100000001b3) & 0xffffffffffffffff
+        return h
+    pay = blob[40:]
+    off = 2 * 4 + 2 * 28 + 4 + 3 + 4        # T[2], two modality descriptors, class id "obj", template count
+    assert struct.unpack_from("<i", pay, off + 12)[0] == 63   # first template header: width, height, level, num_features
+    bad = bytearray(pay)
+    bad[off + 16 + 4] = 200                  # first feature: x i16, y i16, label u8
+    open(str(tmp_path / "label.lmb2"), "wb").write(bytes(blob[:32]) + struct.pack("<Q", fnv1a(bad)) + bytes(bad))
+    with pytest.raises(LinemodError) as e:
+        Detector.read_cache(str(tmp_path / "label.lmb2"))
+    assert e.value.code == -3 and "label" in str(e.value)
+    huge = bytearray(pay)
+    struct.pack_into("<I", huge, off - 4, 0x7fffffff)
+    open(str(tmp_path / "count.lmb2"), "wb").write(bytes(blob[:32]) + struct.pack("<Q", fnv1a(huge)) + bytes(huge))
+    with pytest.raises(LinemodError) as e:
+        Detector.read_cache(str(tmp_path / "count.lmb2"))
+    assert e.value.code == -3
+
+
 def test_read_write_classes_gz(tmp_path):
     det = _random_detector(4, classes=("a", "b"))
     fmt = str(tmp_path / "templates_%s.yml.gz")

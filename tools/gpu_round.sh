@@ -1,29 +1,26 @@
 #!/bin/bash
-# One GPU box, one pass: parity tests, smoke, both bench arms, then the ncu evidence (each capture only after its command
-# exited 0 without ncu).  Outputs under gpurun_out/ with the tag given as $1 (default r01n); summarise here with
-# profiles/summarize.py.   usage: gpurun --timeout 2400 -- 'bash tools/gpu_round.sh r01n'
-TAG=${1:-r01n}
+# One GPU box, one pass: parity tests, smoke, both bench arms (driver's arguments and defaults), then the ncu evidence (each
+# capture only after its command exited 0 without ncu).  Outputs under gpurun_out/ with the tag given as $1; summarise here
+# with profiles/summarize.py.   usage: gpurun --timeout 2400 -- 'bash tools/gpu_round.sh r02a [quick]'
+TAG=${1:-r02a}
+QUICK=${2:-}
 O=gpurun_out
 mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $O/gpu_$TAG.txt 2>&1; nproc >> $O/gpu_$TAG.txt
 python -m pytest tests -x -q -m gpu > $O/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_gpu_$TAG.log
 python __graft_entry__.py smoke > $O/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -1 $O/smoke_$TAG.log
+python bench.py --gpus 1 --steps 20 --warmup 5 > $O/bench_driver_$TAG.log 2> $O/bench_driver_$TAG.err; echo "bench (driver args) rc=$?"
 python bench.py > $O/bench_$TAG.log 2> $O/bench_$TAG.err; echo "bench rc=$?"
-python bench.py --impl reference > $O/bench_ref_$TAG.log 2> $O/bench_ref_$TAG.err; echo "reference arm rc=$?"
+python tools/kbench.py > $O/kbench_$TAG.log 2>&1; echo "kbench rc=$?"; cat $O/kbench_$TAG.log
+if [ -z "$QUICK" ]; then
+python bench.py --impl reference --steps 20 --warmup 5 > $O/bench_ref_$TAG.log 2> $O/bench_ref_$TAG.err; echo "reference arm rc=$?"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/launches_$TAG.csv \
+    python bench.py --steps 64 --warmup 8 --no-cpu-baseline > $O/ncu_launch_$TAG.log 2>&1; echo "ncu launch list rc=$?"
+for K in k_similarity_coarse_rec k_cg_fused k_dn_fused k_spread_all k_pyrdown_fast k_refine_nib; do
+ncu --set full --clock-control none --import-source on -k regex:$K -s 12 -c 2 -f -o $O/${K}_$TAG \
+    python bench.py --steps 64 --warmup 8 --no-cpu-baseline > $O/ncu_full_${K}_$TAG.log 2>&1; echo "ncu full $K rc=$?"
+done
 python tools/trainbench.py > $O/trainbench_$TAG.log 2>&1; echo "trainbench rc=$?"; cat $O/trainbench_$TAG.log
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv \
-    python bench.py --steps 64 --warmup 4 --no-cpu-baseline > $O/ncu_launch_$TAG.log 2>&1; echo "ncu launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:k_similarity_coarse_rec -s 20 -c 3 -f -o $O/coarse_$TAG \
-    python bench.py --steps 64 --warmup 4 --no-cpu-baseline > $O/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
-cat > /tmp/train64.py <<'PY'
-import sys, os
-sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
-import numpy as np
-import test_oracle_render as golden
-from linemod_pose_estimation_b200 import Detector, Mesh, training
-views, idx = golden._oracle_views()
-T = np.array([views[i][0] for i in idx[:64]]); up = np.array([views[i][1] for i in idx[:64]])
-print(Detector().trainViews(Mesh(golden.G["triangles"]), golden._golden_camera(training), T, up, "obj")[0])
-PY
-python /tmp/train64.py > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv \
-    --log-file $O/launches_train_$TAG.csv python /tmp/train64.py > $O/ncu_train_$TAG.log 2>&1; echo "ncu trainer launch list rc=$?"
-tail -c 600 $O/bench_$TAG.log
+fi
+tail -c 1500 $O/bench_driver_$TAG.log; echo; tail -c 3000 $O/bench_$TAG.log
+tail -5 $O/bench_$TAG.err

@@ -1,68 +1,122 @@
 #!/usr/bin/env python
-"""Per-stage device timings of the bench workload for every kernel variant (A/B tool for GPU sessions).
+"""A/B tool for GPU sessions: the bench workload (bench.py, configs[1], trained templates) under different chunk sizes /
+lane counts / kernel options.
 
-    python tools/kbench.py [--templates-per-class 2652] [--frames 64] [--variants 0,1,2]
+    python tools/kbench.py [--configs "batch_frames=8,streams=4;batch_frames=1,streams=8;..."] [--frames 1024]
 
-Uses lm_last_timings (CUDA events on the library's stream) around lm_match_multi; prints one line per variant and checks
-that every variant returns the same match lists as variant 0."""
+Per configuration one JSON line: device-resident us per frame (CUDA events around lm_match_device_stream), end-to-end us
+per frame (lm_match_batch_multi from pinned host frames), per-stage us per frame of a chunk (timing option) and the coarse
+kernel's gathered fraction.  Keys other than `streams` are lm_set_option options.  Checks that every configuration returns
+the first one's match lists."""
 import argparse
+import ctypes as C
 import json
 import os
 import sys
+import time
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+
 import bench  # noqa: E402
-from linemod_pose_estimation_b200 import Detector, _capi  # noqa: E402
 
 
 def main():
+    import torch
+    from linemod_pose_estimation_b200 import Detector, Mesh, _capi, training
     ap = argparse.ArgumentParser()
-    ap.add_argument("--templates-per-class", type=int, default=bench.TEMPLATES_PER_CLASS)
-    ap.add_argument("--frames", type=int, default=64)
-    ap.add_argument("--configs", default="coarse_variant=0,prune=1;coarse_variant=0,prune=0;coarse_variant=2;coarse_variant=1",
-                    help="';'-separated configurations, each a ','-separated list of lm_set_option key=value pairs")
-    ap.add_argument("--threshold-scale", type=float, default=1.0, help="scales the queries' thresholds (pruning sensitivity)")
+    ap.add_argument("--configs", default="batch_frames=8,streams=4;batch_frames=1,streams=8;batch_frames=4,streams=4;"
+                                         "batch_frames=16,streams=3;batch_frames=32,streams=2;batch_frames=8,streams=4,prune=0")
+    ap.add_argument("--frames", type=int, default=1024)
+    ap.add_argument("--pool", type=int, default=64)
     args = ap.parse_args()
-    views = bench.rendered_views()
+    dev = torch.device("cuda", 0)
     det = Detector()
-    bench.fill_templates(lambda cid, b, d, m: det.addTemplate([b, d], cid, m)[0],
-                         lambda cid, pyr: det.addSyntheticTemplate(pyr, cid), views, args.templates_per_class)
-    frames = bench.make_frames(views, min(args.frames, 32))
+    cam = training.camera()
+    tri = bench.meshes()
+    mesh = {cid: Mesh(tri[cid]) for cid, _, _ in bench.CLASSES}
+    views = bench.class_views(lambda r0, r1, rs: training.ViewSphere(radius_min=r0, radius_max=r1, radius_step=rs).views())
+    for cid, _, _ in bench.CLASSES:
+        det.trainViews(mesh[cid], cam, views[cid][0], views[cid][1], cid)
+
+    def render(cid, T, up):
+        r = training.render_views(det, mesh[cid], cam, T[None], up[None])
+        return r["bgr"][0], r["depth"][0], r["mask"][0], tuple(int(v) for v in r["rects"][0])
+    frames = bench.make_frames(render, views, args.pool)
+    lib = _capi.lib()
     host = []
     for (b, d) in frames:
         pb, pd = _capi.pinned_empty(b.shape, np.uint8), _capi.pinned_empty(d.shape, np.uint16)
         pb[...] = b
         pd[...] = d
         host.append((pb, pd))
+    dev_frames = [(torch.from_numpy(b).to(dev), torch.from_numpy(d.view(np.int16)).to(dev)) for (b, d) in frames]
+    qarr, _qk = _capi.query_array(bench.QUERIES)
+    n_q = len(bench.QUERIES)
+    flat_dev = [p for (fb, fd) in dev_frames for p in (fb.data_ptr(), fd.data_ptr())]
+    dev_ptrs = (C.c_void_p * len(flat_dev))(*flat_dev)
+    harr, _hk = _capi.image_array([a for fr in host for a in fr])
+    out_p = C.c_void_p()
+    offs = (C.c_size_t * (args.pool * n_q + 1))()
     ref = None
-    queries = [(thr * args.threshold_scale, ids) for thr, ids in bench.QUERIES]
+    defaults = {"batch_frames": 8, "prune": 1, "mod_order": 2, "graphs": 1}
     for cfg in args.configs.split(";"):
-        opts = dict(kv.split("=") for kv in cfg.split(","))
+        opts = dict(defaults)
+        opts.update({k: int(v) for k, v in (kv.split("=") for kv in cfg.split(","))})
+        n_streams = opts.pop("streams", 4)
         for k, v in opts.items():
-            det.set_option(k, int(v))
-        v = cfg
-        res = [det.match_multi(list(host[i % len(host)]), queries) for i in range(len(host))]
+            det.set_option(k, v)
+        det.set_option("batch_lanes", n_streams)
+        streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+        sp = (C.c_void_p * n_streams)(*[s.cuda_stream for s in streams])
+
+        def device_pass():
+            _capi.check(lib.lm_match_device_stream(det._h, dev_ptrs, args.pool, 2, bench.ROWS, bench.COLS, qarr, n_q, sp, n_streams, None, 0))
+        for _ in range(3):
+            device_pass()
+        torch.cuda.synchronize()
+        reps = max(1, args.frames // args.pool)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cur = torch.cuda.current_stream()
+        e0.record(cur)
+        for s in streams:
+            s.wait_stream(cur)
+        for _ in range(reps):
+            device_pass()
+        for s in streams:
+            cur.wait_stream(s)
+        e1.record(cur)
+        torch.cuda.synchronize()
+        dev_us = 1e3 * e0.elapsed_time(e1) / (reps * args.pool)
+
+        def host_pass(keep=False):
+            _capi.check(lib.lm_match_batch_multi(det._h, harr, args.pool, 2, qarr, n_q, C.byref(out_p), offs))
+            if keep:
+                allm = det._take(out_p, offs[args.pool * n_q])
+                return [allm[offs[i]:offs[i + 1]] for i in range(args.pool * n_q)]
+            lib.lm_free_matches(out_p)
+        res = host_pass(True)
         if ref is None:
             ref = res
         else:
-            for a, b in zip(ref, res):
-                for qa, qb in zip(a, b):
-                    assert np.array_equal(qa, qb), "configuration %s disagrees with the first one" % v
-        stages = {k: [] for k in ("h2d", "front", "coarse", "refine", "d2h")}
-        for i in range(args.frames):
-            det.match_multi(list(host[i % len(host)]), queries)
-            t = det.last_timings()
-            for k in stages:
-                stages[k].append(t[k])
-        w = det.last_work()
-        out = {"config": cfg, "templates": det.numTemplates(), "launches": t["launches"], "B_coarse": w["B_coarse"],
-               "gathered_frac": round(w["B_coarse_gathered"] / max(1, w["B_coarse"]), 4), "candidates": w["candidates"],
-               "matches": int(sum(len(q) for q in res[-1]))}
-        out.update({k + "_us": round(1e3 * float(np.median(x)), 2) for k, x in stages.items()})
-        out["coarse_GBps"] = round(w["B_coarse"] / (np.median(stages["coarse"]) * 1e-3) / 1e9, 1)
+            assert all(np.array_equal(a, b) for a, b in zip(ref, res)), "configuration %s disagrees with the first one" % cfg
+        host_pass()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            host_pass()
+        e2e_us = 1e6 * (time.perf_counter() - t0) / (reps * args.pool)
+        det.set_option("timing", 1)
+        host_pass()
+        t, w = det.last_timings(), det.last_work()
+        det.set_option("timing", 0)
+        fr = max(1, w["frames"])
+        out = {"config": cfg, "templates": det.numTemplates(), "device_us_per_frame": round(dev_us, 2), "e2e_us_per_frame": round(e2e_us, 2),
+               "chunk_frames": fr, "launches_per_chunk": t["launches"],
+               "gathered_frac": round(w["B_coarse_gathered"] / max(1, w["B_coarse"]), 4), "candidates_per_frame": w["candidates"] / fr,
+               "matches_per_frame": sum(len(x) for x in res) / args.pool}
+        out.update({k + "_us_per_frame": round(1e3 * t[k] / fr, 2) for k in ("h2d", "front", "coarse", "refine", "d2h")})
         print(json.dumps(out), flush=True)
 
 
