@@ -7,10 +7,10 @@
 Workload (BASELINE.json configs[1], SURVEY.md section 8d "Config 2"): the reference's two-object detector -- classes
 "memoryChip2" and "cpu_binary", thresholds 92 / 94 (/root/reference/launch/start_object_detection.launch:8,19),
 ColorGradient + DepthNormal, T = {5, 8} -- on a synthetic 640x480 Carmine-style RGB-D stream.  Both template sets are
-TRAINED: the reference's trainer loop (src/renderer.cpp:239-329) over every 5th view of its RendererIterator sphere
-(150 points x 17 in-plane angles x 6 radii) of the reference's own meshes (tests/golden/meshes_config2.npz), which
-yields about as many templates per class as the one set the reference ships pose data for (2 652).  Frames are clutter
-with two rendered instances of each object.
+TRAINED: the reference's trainer loop (src/renderer.cpp:239-329) over views of its RendererIterator sphere (150 points x
+17 in-plane angles x 6 radii) of the reference's own meshes (tests/golden/meshes_config2.npz) -- every 3rd of the views
+that see the (flat) part from at least 30 degrees above its plane -- which yields about as many templates per class as
+the one set the reference ships pose data for (2 652).  Frames are clutter with two rendered instances of each object.
 
 A step = one frame: ONE front end (quantise -> spread -> response -> linearize) and one matching pass per class with
 that class's threshold.  Both arms do exactly this work.
@@ -44,10 +44,13 @@ from linemod_pose_estimation_b200 import synth  # noqa: E402
 ROWS, COLS = 480, 640
 COARSE_POSITIONS = (COLS // 2 // 8) * (ROWS // 2 // 8)  # lowest pyramid level 320x240, T = 8 -> 40 x 30
 # class, threshold, view-sphere radii (min, max, step) in metres: the two objects are small parts (133 x 30 x 3 mm and
-# 38 x 38 x 4 mm), trained at the distances at which a 640x480 Carmine sees them 60-200 px wide
-CLASSES = (("memoryChip2", 92.0, (0.35, 0.60, 0.05)), ("cpu_binary", 94.0, (0.18, 0.33, 0.03)))
+# 38 x 38 x 4 mm), trained at the distances at which a 640x480 camera with the reference's Carmine intrinsics sees them
+# 65-290 px long -- the template size range of the set the reference ships pose data for (55-194 px)
+CLASSES = (("memoryChip2", 92.0, (0.25, 0.45, 0.04)), ("cpu_binary", 94.0, (0.15, 0.30, 0.03)))
 QUERIES = [(thr, [cid]) for cid, thr, _ in CLASSES]
-VIEW_STRIDE = 5             # every 5th view of the 15 300-view sphere: 3 060 views per class, ~2 650 trainable
+MIN_ELEVATION_COS = 0.5     # both objects are flat parts: views closer than 30 degrees to the part's plane (edge-on, a
+                            # silhouette a few pixels thin that "matches" every straight edge) are not trained
+VIEW_STRIDE = 3             # every 3rd of the remaining ~7 650 views of the 15 300-view sphere: ~2 550 views per class
 INSTANCES_PER_CLASS = 2
 FRAME_POOL = 128            # 128 x 1.536 MB = 197 MB of distinct input frames > 126 MB L2
 METRIC = "template_pixel_evals_per_sec_640x480"
@@ -64,11 +67,15 @@ def meshes():
     return {cid: np.ascontiguousarray(G[cid], np.float32) for cid, _, _ in CLASSES}
 
 
-def class_views(view_list_of, stride=VIEW_STRIDE):
-    """{class: (T[n,3], up[n,3])}: every `stride`-th view of the class's sphere, in iteration order."""
+def class_views(view_list_of, stride=None):
+    """{class: (T[n,3], up[n,3])}: every `stride`-th view, in iteration order, of the views of the class's sphere that
+    look at the part from at least 30 degrees above its plane (T = camera position in the object frame, z = part normal)."""
     out = {}
+    stride = stride or VIEW_STRIDE
     for cid, _, (r0, r1, rs) in CLASSES:
         T, up = view_list_of(r0, r1, rs)
+        keep = np.abs(T[:, 2]) >= MIN_ELEVATION_COS * np.linalg.norm(T, axis=1)
+        T, up = T[keep], up[keep]
         out[cid] = (np.ascontiguousarray(T[::stride]), np.ascontiguousarray(up[::stride]))
     return out
 
@@ -119,8 +126,8 @@ def workload_config(world, n_templates, per_gpu, mode):
         ("templates sharded x%d by canonical index, frame replicated (broadcast from rank 0 on the e2e path), survivor blocks "
          "all-gathered once per run of frames, rank 0 finalises" % world))
     return {"workload": "configs[1]: two-object detector (memoryChip2 thr 92 + cpu_binary thr 94), ColorGradient+DepthNormal, "
-                        "T={5,8}, TRAINED template sets (every %dth view of the reference's 15 300-view sphere of its own "
-                        "meshes), synthetic 640x480 RGB-D stream with %d rendered instances per class in clutter; step = 1 "
+                        "T={5,8}, TRAINED template sets (every %dth non-edge-on view of the reference's 15 300-view sphere of "
+                        "its own meshes), synthetic 640x480 RGB-D stream with %d rendered instances per class in clutter; step = 1 "
                         "frame = 1 front end + 1 matching pass per class" % (VIEW_STRIDE, INSTANCES_PER_CLASS),
             "templates_total": n_templates, "templates_per_gpu": per_gpu, "classes": len(CLASSES),
             "evals_per_step": n_templates * COARSE_POSITIONS, "frame": "640x480 BGR u8 + depth u16", "mode": mode,

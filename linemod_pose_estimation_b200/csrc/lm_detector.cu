@@ -771,26 +771,38 @@ static int enqueue_download(Lane& ln, int n_frames, cudaStream_t s) {
   return LM_OK;
 }
 
-// Result download, part 2 (after ln.ev[5]): frame f's records out of the staging block; long lists need a second copy.
-static int collect_records(Lane& ln, int f, cudaStream_t s, std::vector<lm_raw_match>& raw, bool* overflow, uint32_t* n_cands) {
+// Result download, part 2 (after ln.ev[5]): the records of the chunk's n frames out of the staging block.  Frames with
+// more survivors than the head holds get the rest with one extra copy each, all enqueued before ONE synchronisation.
+struct FrameRecords {
+  std::vector<lm_raw_match> raw;
+  bool overflow = false;
+  uint32_t n_cands = 0;
+};
+static int collect_chunk(Lane& ln, int n, cudaStream_t s, std::vector<FrameRecords>& out) {
   const size_t first = std::min<size_t>(kFirstChunkRecords, ln.out_cap);
-  const uint8_t* host = ln.stage_out.as<uint8_t>() + (size_t)f * head_bytes(ln);
-  if (f == 0) ln.work_stats[6] = *reinterpret_cast<const unsigned long long*>(host);
-  host += kStatsBytes;
-  ResultHeader h;
-  std::memcpy(&h, host, sizeof(h));
-  *overflow = h.overflow != 0 || h.count > ln.out_cap;
-  *n_cands = h.n_cands;
-  raw.clear();
-  if (*overflow) return LM_OK;
-  const lm_raw_match* recs = reinterpret_cast<const lm_raw_match*>(host + sizeof(ResultHeader));
-  raw.assign(recs, recs + std::min<size_t>(h.count, first));
-  if (h.count > first) {
-    raw.resize(h.count);
-    CU(cudaMemcpyAsync(raw.data() + first, block_ptr(ln, f) + sizeof(ResultHeader) + first * sizeof(lm_raw_match),
-                       (h.count - first) * sizeof(lm_raw_match), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+  const size_t hb = head_bytes(ln);
+  out.resize((size_t)n);
+  ln.work_stats[6] = *reinterpret_cast<const unsigned long long*>(ln.stage_out.as<uint8_t>());
+  bool extra = false;
+  for (int f = 0; f < n; ++f) {
+    const uint8_t* host = ln.stage_out.as<uint8_t>() + (size_t)f * hb + kStatsBytes;
+    ResultHeader h;
+    std::memcpy(&h, host, sizeof(h));
+    FrameRecords& fr = out[(size_t)f];
+    fr.overflow = h.overflow != 0 || h.count > ln.out_cap;
+    fr.n_cands = h.n_cands;
+    fr.raw.clear();
+    if (fr.overflow) continue;
+    const lm_raw_match* recs = reinterpret_cast<const lm_raw_match*>(host + sizeof(ResultHeader));
+    fr.raw.assign(recs, recs + std::min<size_t>(h.count, first));
+    if (h.count > first) {
+      fr.raw.resize(h.count);
+      CU(cudaMemcpyAsync(fr.raw.data() + first, block_ptr(ln, f) + sizeof(ResultHeader) + first * sizeof(lm_raw_match),
+                         (h.count - first) * sizeof(lm_raw_match), cudaMemcpyDeviceToHost, s));
+      extra = true;
+    }
   }
+  if (extra) CU(cudaStreamSynchronize(s));
   return LM_OK;
 }
 
@@ -836,9 +848,11 @@ static int match_one(lm_detector* d, Lane& ln, int frame, const Query* queries, 
     if (enqueue_chunk(d, ln, *plan, queries, n_q, 1, ln.stream, stage_events) != LM_OK) return LM_E_CUDA;
     if (enqueue_download(ln, 1, ln.stream) != LM_OK) return LM_E_CUDA;
     CU(cudaEventSynchronize(ln.ev[5]));
-    bool overflow = false;
-    if (collect_records(ln, 0, ln.stream, raw, &overflow, &n_cands) != LM_OK) return LM_E_CUDA;
-    if (!overflow) break;
+    std::vector<FrameRecords> got;
+    if (collect_chunk(ln, 1, ln.stream, got) != LM_OK) return LM_E_CUDA;
+    raw.swap(got[0].raw);
+    n_cands = got[0].n_cands;
+    if (!got[0].overflow) break;
     if (attempt >= 8) return lm_fail(LM_E_CUDA, "match buffers overflowed repeatedly");
     // the candidate count of a truncated list is the chunk-wide counter: read it back
     BatchCtl ctl_head;
@@ -1366,7 +1380,7 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
   // per (frame, query) result lists, concatenated at the end (chunks finish in order, but a frame may be redone)
   std::vector<std::vector<lm_match_rec> > lists((size_t)n_frames * n_q);
   struct Pending { int first = -1, n = 0; const Pack::Plan* plan = nullptr; } pending[LM_LANES];
-  std::vector<lm_raw_match> raw;
+  std::vector<FrameRecords> got;
   auto finish = [&](int li) -> int {
     Lane& ln = d->lane[li];
     const Pending pd = pending[li];
@@ -1375,13 +1389,11 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
     if (d->timing) collect_timings(ln);  // per-stage events of this chunk (plain launches): lm_last_timings of lane 0
     std::vector<int> redo;
     uint64_t cands = 0, survivors = 0;
+    if (collect_chunk(ln, pd.n, ln.stream, got) != LM_OK) return LM_E_CUDA;
     for (int f = 0; f < pd.n; ++f) {
-      bool overflow = false;
-      uint32_t n_cands = 0;
-      if (collect_records(ln, f, ln.stream, raw, &overflow, &n_cands) != LM_OK) return LM_E_CUDA;
-      cands += n_cands; survivors += raw.size();
-      if (overflow) { redo.push_back(f); continue; }
-      finalize_queries(d, ln, raw, n_q, &lists[(size_t)(pd.first + f) * n_q]);
+      cands += got[(size_t)f].n_cands; survivors += got[(size_t)f].raw.size();
+      if (got[(size_t)f].overflow) { redo.push_back(f); continue; }
+      finalize_queries(d, ln, got[(size_t)f].raw, n_q, &lists[(size_t)(pd.first + f) * n_q]);
     }
     // work accounting of the chunk (lm_last_work reads lane 0): B_coarse of all its frames, candidates, evals, frames
     ln.work_stats[1] = pd.plan->coarse_bytes * (uint64_t)pd.n;

@@ -30,21 +30,37 @@ def main():
     ap.add_argument("--configs", default="batch_frames=8,streams=4;batch_frames=1,streams=8;batch_frames=4,streams=4;"
                                          "batch_frames=16,streams=3;batch_frames=32,streams=2;batch_frames=8,streams=4,prune=0")
     ap.add_argument("--frames", type=int, default=1024)
+    ap.add_argument("--workload", default="trained", choices=["trained", "stress"],
+                    help="trained: bench.py's workload; stress: round 1's (24 extracted + 2 628 random stress templates per class, "
+                         "SURVEY 8d's random-template set) for like-for-like comparisons with profiles/r01_*")
     ap.add_argument("--pool", type=int, default=64)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     det = Detector()
-    cam = training.camera()
-    tri = bench.meshes()
-    mesh = {cid: Mesh(tri[cid]) for cid, _, _ in bench.CLASSES}
-    views = bench.class_views(lambda r0, r1, rs: training.ViewSphere(radius_min=r0, radius_max=r1, radius_step=rs).views())
-    for cid, _, _ in bench.CLASSES:
-        det.trainViews(mesh[cid], cam, views[cid][0], views[cid][1], cid)
+    if args.workload == "trained":
+        cam = training.camera()
+        tri = bench.meshes()
+        mesh = {cid: Mesh(tri[cid]) for cid, _, _ in bench.CLASSES}
+        views = bench.class_views(lambda r0, r1, rs: training.ViewSphere(radius_min=r0, radius_max=r1, radius_step=rs).views())
+        for cid, _, _ in bench.CLASSES:
+            det.trainViews(mesh[cid], cam, views[cid][0], views[cid][1], cid)
 
-    def render(cid, T, up):
-        r = training.render_views(det, mesh[cid], cam, T[None], up[None])
-        return r["bgr"][0], r["depth"][0], r["mask"][0], tuple(int(v) for v in r["rects"][0])
-    frames = bench.make_frames(render, views, args.pool)
+        def render(cid, T, up):
+            r = training.render_views(det, mesh[cid], cam, T[None], up[None])
+            return r["bgr"][0], r["depth"][0], r["mask"][0], tuple(int(v) for v in r["rects"][0])
+        frames = bench.make_frames(render, views, args.pool)
+    else:
+        from linemod_pose_estimation_b200 import synth
+        sv = {}
+        for ci, (cid, _, _) in enumerate(bench.CLASSES):
+            sv[cid] = [synth.render_view(s, scale, rot, canvas=(200, 200), tilt=tilt)
+                       for (s, scale, rot, tilt) in synth.view_params(24, seed=900 + ci)]
+            n_ok = sum(det.addTemplate([b, d], cid, m)[0] >= 0 for (b, d, m) in sv[cid])
+            rng = np.random.default_rng(4242 + ci)
+            for _ in range(2652 - n_ok):
+                det.addSyntheticTemplate(synth.random_pyramid(rng), cid)
+        planted = [sv[cid][k] for cid, _, _ in bench.CLASSES for k in (0, 1)]
+        frames = [synth.compose_scene(2000 + i, planted, rows=bench.ROWS, cols=bench.COLS)[:2] for i in range(args.pool)]
     lib = _capi.lib()
     host = []
     for (b, d) in frames:
@@ -112,7 +128,7 @@ def main():
         t, w = det.last_timings(), det.last_work()
         det.set_option("timing", 0)
         fr = max(1, w["frames"])
-        out = {"config": cfg, "templates": det.numTemplates(), "device_us_per_frame": round(dev_us, 2), "e2e_us_per_frame": round(e2e_us, 2),
+        out = {"workload": args.workload, "config": cfg, "templates": det.numTemplates(), "device_us_per_frame": round(dev_us, 2), "e2e_us_per_frame": round(e2e_us, 2),
                "chunk_frames": fr, "launches_per_chunk": t["launches"],
                "gathered_frac": round(w["B_coarse_gathered"] / max(1, w["B_coarse"]), 4), "candidates_per_frame": w["candidates"] / fr,
                "matches_per_frame": sum(len(x) for x in res) / args.pool}
