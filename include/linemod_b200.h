@@ -330,6 +330,33 @@ int lm_finalize_gathered(const lm_detector* det, const void* blocks, int world, 
  * i % world == rank on this handle; template_id / class_index / order_key stay global. */
 int lm_set_shard(lm_detector* det, int rank, int world);
 
+/* ------------------------------------------------------------------------------------------------ several GPUs, one caller */
+/* The multi-GPU handle for the reference's kind of caller -- ONE process making one call
+ * (rgbdDetector::linemod_detection, src/rgbdDetector.cpp:31-34): the prototype's model (templates, modalities, T, tables,
+ * options) is cloned onto every listed device and each device is driven by its own worker thread.
+ *   LM_GROUP_FRAMES     every device holds all templates; the frames of a batch are dealt out in launch sets ("batch_frames"
+ *                       frames, round robin), each device copies its frames in over its own PCIe link and returns finished
+ *                       lists: no exchange between devices, the end-to-end frame rate scales with the device count.
+ *   LM_GROUP_TEMPLATES  the north-star layout: templates sharded by canonical index, every device sees every frame, the
+ *                       shards' survivors are merged before the reference's sort + unique.  Single-frame latency, or template
+ *                       sets that outgrow one device.
+ * Results are identical to lm_match_batch_multi on the prototype in both modes.  (One process per GPU with an NCCL
+ * exchange instead: linemod_pose_estimation_b200/sharding.py over lm_set_shard / lm_match_device_stream / lm_finalize_gathered.) */
+typedef struct lm_group lm_group;
+#define LM_GROUP_FRAMES 0
+#define LM_GROUP_TEMPLATES 1
+int lm_group_create(const lm_detector* prototype, const int* devices, int n_devices, int mode, lm_group** out);
+void lm_group_destroy(lm_group* group);
+int lm_group_size(const lm_group* group);
+int lm_group_mode(const lm_group* group);
+lm_detector* lm_group_member(lm_group* group, int i);              /* the handle bound to devices[i] (introspection, options) */
+int lm_group_set_option(lm_group* group, const char* key, int value); /* lm_set_option on every member */
+/* lm_match_batch_multi / lm_match across the group's devices; same outputs, released with lm_free_matches */
+int lm_group_match_batch_multi(lm_group* group, const lm_image* sources, int n_frames, int n_sources, const lm_query* queries,
+                               int n_queries, lm_match_rec** out_matches, size_t* out_offsets);
+int lm_group_match(lm_group* group, const lm_image* sources, int n_sources, float threshold, const char* const* class_ids,
+                   int n_ids, lm_match_rec** out_matches, size_t* out_n);
+
 /* ------------------------------------------------------------------------------------------------ match clustering */
 /* The stage right behind Detector::match in the reference's nodes:
  *   rgbdDetector::rcd_voting            src/rgbdDetector.cpp:36-70    bin matches by (y / step, x / step, depth bin of the template)
@@ -362,12 +389,16 @@ int lm_cluster_matches(const lm_match_rec* matches, size_t n_matches, const doub
 void lm_free_clusters(lm_cluster* clusters, uint32_t* match_index);
 
 /* ------------------------------------------------------------------------------------------------ data tables */
-/* SIMILARITY_LUT[256] ([OCV] linemod.cpp) and NORMAL_LUT[20][20][20] ([OCV] normal_lut.i) are data, not code: both
- * are recalled / regenerated here (DESIGN.md "LUTs"), so both are injectable.  Similarity entries must be <= 4. */
+/* SIMILARITY_LUT[256] ([OCV] linemod.cpp) and NORMAL_LUT[20][20][20] ([OCV] normal_lut.i) are data, not code.  The first
+ * is the literal upstream table (tests/golden/similarity_lut_ocv.txt); the second is not recoverable without OpenCV's
+ * sources and a stand-in is shipped (DESIGN.md section 2 "LUTs"), so both are injectable.  Similarity entries must be <= 4. */
 int lm_set_similarity_lut(lm_detector* det, const uint8_t lut[256]);
 int lm_get_similarity_lut(const lm_detector* det, uint8_t lut[256]);
 int lm_set_normal_lut(lm_detector* det, const uint8_t lut[8000]);
 int lm_get_normal_lut(const lm_detector* det, uint8_t lut[8000]);
+/* The same from OpenCV's own text file (modules/objdetect/src/normal_lut.i, a brace-initialised unsigned char
+ * [20][20][20]): every integer after the first '{' is an entry; exactly 8000 entries <= 255 are required (LM_E_IO). */
+int lm_load_normal_lut_file(lm_detector* det, const char* path);
 
 /* ------------------------------------------------------------------------------------------------ parity taps */
 #define LM_STAGE_QUANTIZED 0 /* u8 [rows][cols], after mask                      (QuantizedPyramid::quantize) */
@@ -400,8 +431,8 @@ int lm_last_timings(const lm_detector* det, float ms[5], int* kernel_launches);
  * early termination skips features of tiles in which no position can reach the threshold any more), [7] frames in the set. */
 int lm_last_work(const lm_detector* det, uint64_t out[8]);
 /* Tuning switches: "batch_frames" (frames per chunk = per launch set on the batched paths, 1..32, default 8),
- * "batch_lanes" (chunks in flight in lm_match_batch*, default 4), "prune" (1 = exact early termination in the coarse
- * kernel, default), "mod_order" (order in which the coarse kernel sums the modalities: 0 = template order, 1 = reversed,
+ * "batch_lanes" (chunks in flight in lm_match_batch*, default 4), "prune" (exact early termination: bit 0 = in the coarse
+ * kernel, bit 1 = of hopeless candidates in the refinement kernel; default 3; results do not depend on it), "mod_order" (order in which the coarse kernel sums the modalities: 0 = template order, 1 = reversed,
  * 2 = chosen per frame from the front end's spread-bit counters, default; results do not depend on it), "graphs" (replay
  * a recorded CUDA graph per chunk, default 1), "timing" (per-stage events for lm_last_timings, default 0), "debug_taps",
  * "coarse_grid_limit", "device_out_cap" (records per frame block on the device-resident paths, default 2048),

@@ -358,6 +358,54 @@ class Detector {
   mutable std::map<std::pair<std::string, int>, TemplatePyramid> cache_;
 };
 
+// ------------------------------------------------------------------------------------------------ several GPUs, one caller
+// lm_group: `prototype`'s model cloned onto `devices`, one worker thread per device.  Frames: every device holds all
+// templates and takes its share of a batch's frames over its own PCIe link; Templates: the template set is sharded and every
+// device sees every frame (the north-star layout).  Both return exactly what the prototype would.
+class DetectorGroup {
+ public:
+  enum Mode { Frames = LM_GROUP_FRAMES, Templates = LM_GROUP_TEMPLATES };
+  DetectorGroup(const Detector& prototype, const std::vector<int>& devices, Mode mode = Frames) : g_(nullptr), proto_(prototype.handle()) {
+    detail::check(lm_group_create(prototype.handle(), devices.data(), (int)devices.size(), (int)mode, &g_));
+  }
+  ~DetectorGroup() { lm_group_destroy(g_); }
+  DetectorGroup(const DetectorGroup&) = delete;
+  DetectorGroup& operator=(const DetectorGroup&) = delete;
+  int size() const { return lm_group_size(g_); }
+  void setOption(const std::string& key, int value) { detail::check(lm_group_set_option(g_, key.c_str(), value)); }
+  // Detector::match on a batch of frames (frames[f] = the sources of frame f): matches[f] as Detector::match returns them.
+  void matchBatch(const std::vector<std::vector<Image> >& frames, float threshold, std::vector<std::vector<Match> >& matches,
+                  const std::vector<std::string>& class_ids = std::vector<std::string>()) const {
+    std::vector<lm_image> src;
+    for (size_t f = 0; f < frames.size(); ++f)
+      for (size_t m = 0; m < frames[f].size(); ++m) src.push_back(frames[f][m].c());
+    std::vector<const char*> ids;
+    for (size_t i = 0; i < class_ids.size(); ++i) ids.push_back(class_ids[i].c_str());
+    lm_query q = {threshold, ids.empty() ? nullptr : ids.data(), (int)ids.size()};
+    std::vector<size_t> offs(frames.size() + 1, 0);
+    lm_match_rec* recs = nullptr;
+    lm_image none = {nullptr, 0, 0, 0, 0};
+    detail::check(lm_group_match_batch_multi(g_, src.empty() ? &none : src.data(), (int)frames.size(),
+                                             frames.empty() ? 0 : (int)frames[0].size(), &q, 1, &recs, offs.data()));
+    matches.assign(frames.size(), std::vector<Match>());
+    for (size_t f = 0; f < frames.size(); ++f)
+      for (size_t i = offs[f]; i < offs[f + 1]; ++i)
+        matches[f].push_back(Match(recs[i].x, recs[i].y, recs[i].similarity, lm_class_id(proto_, recs[i].class_index), recs[i].template_id));
+    lm_free_matches(recs);
+  }
+  void match(const std::vector<Image>& sources, float threshold, std::vector<Match>& matches,
+             const std::vector<std::string>& class_ids = std::vector<std::string>()) const {
+    std::vector<std::vector<Match> > out;
+    matchBatch(std::vector<std::vector<Image> >(1, sources), threshold, out, class_ids);
+    matches.swap(out[0]);
+  }
+  lm_group* handle() const { return g_; }
+
+ private:
+  lm_group* g_;
+  const lm_detector* proto_;
+};
+
 // ------------------------------------------------------------------------------------------------ training helpers
 // Renderer3d(stl_file) of the reference's trainer (src/renderer.cpp:239): a triangle mesh in the object frame, metres.
 class Mesh {

@@ -72,10 +72,12 @@ EXPORTS = [
     "lm_num_modalities", "lm_get_modality", "lm_num_classes", "lm_num_templates", "lm_class_id", "lm_get_templates",
     "lm_add_template", "lm_add_template_from_quantized", "lm_add_synthetic_template", "lm_match", "lm_match_multi", "lm_match_batch", "lm_match_batch_multi", "lm_free_matches",
     "lm_match_device", "lm_match_device_multi", "lm_match_device_multi_lane", "lm_device_result_region", "lm_copy_result_block", "lm_match_device_stream", "lm_finalize_raw", "lm_finalize_gathered", "lm_upload_images", "lm_set_shard", "lm_set_similarity_lut", "lm_get_similarity_lut",
-    "lm_set_normal_lut", "lm_get_normal_lut", "lm_debug_fetch", "lm_build_front", "lm_level_geometry",
+    "lm_set_normal_lut", "lm_get_normal_lut", "lm_load_normal_lut_file", "lm_debug_fetch", "lm_build_front", "lm_level_geometry",
     "lm_mesh_create", "lm_mesh_load_stl", "lm_mesh_num_triangles", "lm_mesh_get_triangles", "lm_mesh_destroy", "lm_view_count", "lm_view_params",
     "lm_view_pose", "lm_render_views", "lm_add_templates_batch", "lm_train_views", "lm_depth_diff_batch",
     "lm_write_renderer_params", "lm_read_renderer_params", "lm_free_poses",
+    "lm_group_create", "lm_group_destroy", "lm_group_size", "lm_group_mode", "lm_group_member", "lm_group_set_option",
+    "lm_group_match_batch_multi", "lm_group_match",
     "lm_cluster_matches", "lm_free_clusters", "lm_debug_coarse_map", "lm_debug_presort", "lm_last_timings", "lm_last_work", "lm_set_option",
 ]
 
@@ -151,6 +153,7 @@ def lib():
     L.lm_set_shard.argtypes = [vp, ci, ci]
     for n in ("lm_set_similarity_lut", "lm_get_similarity_lut", "lm_set_normal_lut", "lm_get_normal_lut"):
         getattr(L, n).argtypes = [vp, vp]
+    L.lm_load_normal_lut_file.argtypes = [vp, cp]
     L.lm_mesh_create.argtypes = [vp, ci, C.POINTER(vp)]
     L.lm_mesh_load_stl.argtypes = [cp, C.POINTER(vp)]
     L.lm_mesh_num_triangles.argtypes = [vp]
@@ -169,6 +172,17 @@ def lib():
     L.lm_read_renderer_params.argtypes = [cp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(LmRendererParams)]
     L.lm_free_poses.argtypes = [vp]
     L.lm_free_poses.restype = None
+    L.lm_group_create.argtypes = [vp, C.POINTER(C.c_int), ci, ci, C.POINTER(vp)]
+    L.lm_group_destroy.argtypes = [vp]
+    L.lm_group_destroy.restype = None
+    L.lm_group_size.argtypes = [vp]
+    L.lm_group_mode.argtypes = [vp]
+    L.lm_group_member.argtypes = [vp, ci]
+    L.lm_group_member.restype = vp
+    L.lm_group_set_option.argtypes = [vp, cp, ci]
+    L.lm_group_match_batch_multi.argtypes = [vp, C.POINTER(LmImage), ci, ci, C.POINTER(LmQuery), ci, C.POINTER(vp),
+                                             C.POINTER(C.c_size_t)]
+    L.lm_group_match.argtypes = [vp, C.POINTER(LmImage), ci, C.c_float, C.POINTER(cp), ci, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.lm_cluster_matches.argtypes = [vp, C.c_size_t, vp, vp, C.c_size_t, vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp)]
     L.lm_free_clusters.argtypes = [vp, vp]
     L.lm_free_clusters.restype = None

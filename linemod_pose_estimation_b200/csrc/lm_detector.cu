@@ -7,6 +7,8 @@
 // only stages buffers, packs template records and orders the (few) surviving matches.
 #include "lm_detector_internal.hpp"
 
+#include <cctype>
+
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
 int lm_fail(int code, const char* fmt, ...) {
@@ -640,6 +642,7 @@ static int enqueue_match(lm_detector* d, Lane& ln, const Pack::Plan& plan, const
   if (plan.n_tiles > 0) ++ln.launches;
   if (ev_mid) CU(cudaEventRecord(ev_mid, s));
   rp.levels = L; rp.M = M; rp.coarse_T = gc.T; rp.coarse_W = gc.W;
+  rp.prune = (d->prune & 2) != 0;
   for (int l = 0; l < L - 1; ++l) {
     const LevelGeom& g = ln.geom[l];
     rp.level[l].lmn = ln.lmn[l].as<uint8_t>();
@@ -831,7 +834,7 @@ static const uint32_t kCandPerFrame = 1u << 16, kOutPerFrame = 1u << 12;
 // on overflow (exactness over speed).  The single-frame calls land here, and the batched paths for the rare frame
 // whose survivors did not fit.
 static int match_one(lm_detector* d, Lane& ln, int frame, const Query* queries, int n_q, std::vector<lm_match_rec>* out,
-                     bool stage_events) {
+                     bool stage_events, std::vector<lm_raw_match>* raw_out = nullptr) {
   if (n_q < 1 || n_q > kMaxQueries) return lm_fail(LM_E_INVALID, "number of queries must be 1..%d", kMaxQueries);
   int rc = ensure_pack(d, ln);
   if (rc != LM_OK) return rc;
@@ -868,7 +871,8 @@ static int match_one(lm_detector* d, Lane& ln, int frame, const Query* queries, 
   ln.work_stats[2] = plan->n_items ? (uint64_t)((double)n_cands * (plan->refine_nf_sum / plan->n_items) * 256.0) : 0;
   ln.work_stats[3] = 20ull * raw.size();
   ln.work_stats[7] = 1;
-  finalize_queries(d, ln, raw, n_q, out);
+  if (raw_out) raw_out->swap(raw);
+  else finalize_queries(d, ln, raw, n_q, out);
   return LM_OK;
 }
 
@@ -1231,6 +1235,42 @@ int lm_get_similarity_lut(const lm_detector* d, uint8_t lut[256]) { std::memcpy(
 int lm_set_normal_lut(lm_detector* d, const uint8_t lut[8000]) { std::memcpy(d->normal_lut, lut, 8000); d->luts_dirty = true; return LM_OK; }
 int lm_get_normal_lut(const lm_detector* d, uint8_t lut[8000]) { std::memcpy(lut, d->normal_lut, 8000); return LM_OK; }
 
+// OpenCV ships NORMAL_LUT as text (modules/objdetect/src/normal_lut.i: a brace-initialised unsigned char [20][20][20]); a
+// user who holds OpenCV injects the real table with one call.  Every integer after the first '{' is an entry.
+int lm_load_normal_lut_file(lm_detector* d, const char* path) {
+  if (!d || !path) return lm_fail(LM_E_INVALID, "NULL argument");
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return lm_fail(LM_E_IO, "cannot open '%s'", path);
+  std::string text;
+  char buf[65536];
+  size_t got;
+  while ((got = std::fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, got);
+  std::fclose(f);
+  size_t i = text.find('{');
+  if (i == std::string::npos) return lm_fail(LM_E_IO, "%s: no '{' -- not a brace-initialised table", path);
+  std::vector<uint8_t> v;
+  while (i < text.size()) {
+    const char c = text[i];
+    if (c == '/' && i + 1 < text.size() && text[i + 1] == '/') { while (i < text.size() && text[i] != '\n') ++i; continue; }
+    if (c == '/' && i + 1 < text.size() && text[i + 1] == '*') { const size_t e = text.find("*/", i + 2); i = e == std::string::npos ? text.size() : e + 2; continue; }
+    if (c >= '0' && c <= '9') {
+      unsigned long val = 0;
+      if (c == '0' && i + 1 < text.size() && (text[i + 1] == 'x' || text[i + 1] == 'X')) {
+        i += 2;
+        while (i < text.size() && std::isxdigit((unsigned char)text[i])) { val = val * 16 + (unsigned long)(std::isdigit((unsigned char)text[i]) ? text[i] - '0' : (std::tolower(text[i]) - 'a' + 10)); ++i; }
+      } else {
+        while (i < text.size() && text[i] >= '0' && text[i] <= '9') { val = val * 10 + (unsigned long)(text[i] - '0'); ++i; }
+      }
+      if (val > 255) return lm_fail(LM_E_IO, "%s: entry %zu is %lu (> 255)", path, v.size(), val);
+      v.push_back((uint8_t)val);
+      continue;
+    }
+    ++i;
+  }
+  if (v.size() != 8000) return lm_fail(LM_E_IO, "%s: %zu entries, NORMAL_LUT has 20 * 20 * 20 = 8000", path, v.size());
+  return lm_set_normal_lut(d, v.data());
+}
+
 int lm_set_option(lm_detector* d, const char* key, int value) {
   if (!d || !key) return lm_fail(LM_E_INVALID, "NULL argument");
   std::string k(key);
@@ -1367,12 +1407,17 @@ static int prepare_lane(lm_detector* d, Lane& ln, int rows, int cols, int frames
 // Frames in chunks of `batch_frames`, chunks pipelined over `batch_lanes` workspace lanes: while one chunk's kernels run,
 // the next chunk's frames are copied to the device and the previous chunk's survivors are ordered on the host.  Every
 // kernel launch covers a whole chunk.  out_offsets: n_frames * n_q + 1 prefix offsets, frame-major.
+//
+// raw_frames (nullable): instead of finalised lists, frame f's un-ordered survivor records go to (*raw_frames)[f] -- what a
+// template-sharded caller merges across shards before the reference's sort + unique (out_matches / out_offsets unused).
 static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frames, int n_sources, const Query* qs, int n_q,
-                            lm_match_rec** out_matches, size_t* out_offsets) {
-  *out_matches = nullptr;
+                            lm_match_rec** out_matches, size_t* out_offsets,
+                            std::vector<std::vector<lm_raw_match> >* raw_frames = nullptr) {
+  if (out_matches) *out_matches = nullptr;
   if (n_q < 1 || n_q > kMaxQueries) return lm_fail(LM_E_INVALID, "number of queries must be 1..%d", kMaxQueries);
-  out_offsets[0] = 0;
-  if (n_frames == 0) { size_t n = 0; return copy_out(std::vector<lm_match_rec>(), out_matches, &n); }
+  if (out_offsets) out_offsets[0] = 0;
+  if (raw_frames) raw_frames->assign((size_t)n_frames, std::vector<lm_raw_match>());
+  if (n_frames == 0) { size_t n = 0; return raw_frames ? LM_OK : copy_out(std::vector<lm_match_rec>(), out_matches, &n); }
   if (set_device(d) != LM_OK) return LM_E_CUDA;
   const int F = std::max(1, std::min(d->batch_frames, LM_MAX_BATCH));
   const int NL = std::max(1, std::min(d->batch_lanes, LM_LANES));
@@ -1393,7 +1438,8 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
     for (int f = 0; f < pd.n; ++f) {
       cands += got[(size_t)f].n_cands; survivors += got[(size_t)f].raw.size();
       if (got[(size_t)f].overflow) { redo.push_back(f); continue; }
-      finalize_queries(d, ln, got[(size_t)f].raw, n_q, &lists[(size_t)(pd.first + f) * n_q]);
+      if (raw_frames) (*raw_frames)[(size_t)(pd.first + f)].swap(got[(size_t)f].raw);
+      else finalize_queries(d, ln, got[(size_t)f].raw, n_q, &lists[(size_t)(pd.first + f) * n_q]);
     }
     // work accounting of the chunk (lm_last_work reads lane 0): B_coarse of all its frames, candidates, evals, frames
     ln.work_stats[1] = pd.plan->coarse_bytes * (uint64_t)pd.n;
@@ -1403,7 +1449,8 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
     ln.work_stats[3] = 20ull * survivors;
     ln.work_stats[7] = (uint64_t)pd.n;
     for (int f : redo) {  // rare: this frame alone with growing buffers (its sources are still in the lane's slot f)
-      int rc = match_one(d, ln, f, qs, n_q, &lists[(size_t)(pd.first + f) * n_q], false);
+      int rc = match_one(d, ln, f, qs, n_q, &lists[(size_t)(pd.first + f) * n_q], false,
+                         raw_frames ? &(*raw_frames)[(size_t)(pd.first + f)] : nullptr);
       if (rc != LM_OK) return rc;
     }
     return LM_OK;
@@ -1440,6 +1487,7 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
   if (prof)
     fprintf(stderr, "[lm host profile] per frame us: finish %.1f upload %.1f enqueue %.1f\n", t_fin / n_frames, t_up / n_frames,
             t_enq / n_frames);
+  if (raw_frames) return LM_OK;
   std::vector<lm_match_rec> all;
   for (size_t i = 0; i < lists.size(); ++i) {
     all.insert(all.end(), lists[i].begin(), lists[i].end());
@@ -1447,6 +1495,37 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
   }
   size_t n = 0;
   return copy_out(all, out_matches, &n);
+}
+
+// Internal entry points of lm_group.cu (a handle per device, driven from the group's worker threads).
+int lm_internal_match_batch_raw(lm_detector* d, const lm_image* sources, int n_frames, int n_sources, const lm_query* queries,
+                                int n_queries, std::vector<std::vector<lm_raw_match> >* raw_frames) {
+  Query qs[kMaxQueries];
+  int rc = to_queries(queries, n_queries, qs);
+  if (rc != LM_OK) return rc;
+  return match_batch_impl(d, sources, n_frames, n_sources, qs, n_queries, nullptr, nullptr, raw_frames);
+}
+void lm_internal_finalize(int levels, std::vector<lm_raw_match>& raw, int n_queries, std::vector<lm_match_rec>* out) {
+  std::vector<lm_raw_match> part;
+  std::vector<lm_match_rec> presort;
+  for (int q = 0; q < n_queries; ++q) {
+    part.clear();
+    for (const lm_raw_match& r : raw)
+      if ((int)(r.order_key >> 28) == q) part.push_back(r);
+    finalize_records(levels, part, presort, out[q]);
+  }
+}
+lm_detector* lm_internal_clone(const lm_detector* src) {
+  lm_detector* d = new lm_detector();
+  d->model = src->model;
+  std::memcpy(d->sim_lut, src->sim_lut, sizeof(d->sim_lut));
+  std::memcpy(d->normal_lut, src->normal_lut, sizeof(d->normal_lut));
+  d->luts_dirty = true;
+  d->device_out_cap = src->device_out_cap; d->cand_per_frame = src->cand_per_frame;
+  d->prune = src->prune; d->graphs = src->graphs; d->mod_order = src->mod_order;
+  d->batch_frames = src->batch_frames; d->batch_lanes = src->batch_lanes;
+  refresh_class_cache(d);
+  return d;
 }
 
 int lm_match_batch(lm_detector* d, const lm_image* sources, int n_frames, int n_sources, float threshold,

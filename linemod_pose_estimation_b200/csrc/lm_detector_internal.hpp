@@ -266,7 +266,8 @@ struct lm_detector {
   Lane lane[LM_LANES];
   Pack pack;
   int shard_rank = 0, shard_world = 1;
-  int debug_taps = 0, timing = 0, prune = 1, graphs = 1;
+  int debug_taps = 0, timing = 0, graphs = 1;
+  int prune = 3;         // exact early termination: bit 0 in the coarse kernel, bit 1 in the refinement kernel
   int batch_frames = 8;  // frames per chunk on the batched paths (lm_match_batch*, lm_match_device_stream)
   int batch_lanes = 4;   // chunks in flight on the batched host path
   int mod_order = 2;  // coarse kernel: 0 = modalities in template order, 1 = reversed, 2 = chosen per frame (default)
@@ -288,3 +289,14 @@ bool is_pinned(const void* p);
 size_t src_row_bytes(int type, int cols);
 int expected_src_type(const lm_modality_desc& m);
 void refresh_class_cache(lm_detector* d);
+
+// ------------------------------------------------------------------------------------------------ lm_group.cu <-> lm_detector.cu
+extern "C" {
+// lm_match_batch_multi that hands back every frame's un-ordered survivor records instead of finalised lists
+int lm_internal_match_batch_raw(lm_detector* d, const lm_image* sources, int n_frames, int n_sources, const lm_query* queries,
+                                int n_queries, std::vector<std::vector<lm_raw_match> >* raw_frames);
+// raw records of one frame (all shards) -> per query the reference's sorted / de-duplicated list
+void lm_internal_finalize(int levels, std::vector<lm_raw_match>& raw, int n_queries, std::vector<lm_match_rec>* out);
+// a new handle with the same model (templates, modalities, T), tables and options, not yet bound to a device
+lm_detector* lm_internal_clone(const lm_detector* src);
+}

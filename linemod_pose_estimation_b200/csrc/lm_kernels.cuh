@@ -60,6 +60,7 @@ struct RefineLevel {
 struct RefineParams {
   RefineLevel level[LM_MAX_LEVELS];       // index = pyramid level (only 0 .. L-2 used)
   int levels, M, coarse_T, coarse_W;
+  int prune;                              // exact early termination of hopeless candidates (warp-per-candidate path)
   float threshold[LM_MAX_QUERIES];        // per query of the request
 };
 

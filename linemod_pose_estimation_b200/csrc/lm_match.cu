@@ -351,6 +351,19 @@ constexpr int kRefineWarps = 8;
 constexpr int kRefineMaxFeat = LM_MAX_MODALITIES * 64;
 constexpr size_t kResultStatsBytes = 16;  // statistics in front of every frame's ResultHeader
 
+// [OCV] matchClass drops a refined candidate when best_score * 100.f / (4 * nf) < threshold (f32, two roundings).  The
+// predicate is monotone in the integer score, so there is a smallest passing score: found here with the very same f32
+// operations, it lets the warp-per-candidate kernel stop a candidate exactly as soon as no position of its 16 x 16 window
+// can reach it any more (a response is at most 4 per remaining feature).
+__device__ __forceinline__ int min_passing_score(float threshold, int nf) {
+  const float den = (float)(4 * nf);
+  int s = max(0, __float2int_rd(threshold * den * 0.01f) - 2);
+  const int cap = 4 * nf + 1;  // scores never exceed 4 * nf: `cap` means "cannot pass"
+  while (s < cap && __fdiv_rn(__fmul_rn((float)s, 100.f), den) < threshold) ++s;
+  while (s > 0 && !(__fdiv_rn(__fmul_rn((float)(s - 1), 100.f), den) < threshold)) --s;
+  return s;
+}
+
 // Refinement on nibble-packed planes, ONE BLOCK PER CANDIDATE (few candidates: lowest latency).  A patch row is 16 positions =
 // 8 bytes at an arbitrary nibble offset: lane r (< 16) and lane r + 16 load the two aligned 8-byte chunks the row spans
 // -- one LDG.64 per feature and lane, 16 cache lines per warp instruction instead of the 48 the byte kernel touches --
@@ -562,11 +575,25 @@ __device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const Coa
 #pragma unroll
       for (int j = 0; j < 4; ++j) tot[j][0] = tot[j][1] = 0;
       int begin = 0;
-      for (int m = 0; m < P.M; ++m) {
+      // exact early termination (see min_passing_score): every 16 features the warp checks whether any position can still pass
+      const int need = P.prune ? min_passing_score(threshold, (int)rtp->nf) : 0;
+      int remaining = n_all;
+      bool hopeless = false;
+      for (int m = 0; m < P.M && !hopeless; ++m) {
         const uint8_t* lmm = L.lmn + (size_t)frame * L.frame_stride + (size_t)m * 4 * L.plane_stride;
         const int n = rtp->cnt[m];  // <= 63 features: the u8 sums below cannot overflow
         uint32_t acc[4] = {0, 0, 0, 0};
         for (int f0 = 0; f0 < n; f0 += 8) {
+          if ((f0 & 8) == 0 && f0 > 0 && need > 0) {   // after 16, 32, 48 features of this modality (and see below at its end)
+            uint32_t mx = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              mx = __vmaxu2(mx, __vmaxu2(tot[j][0] + (acc[j] & 0x00ff00ffu), tot[j][1] + ((acc[j] >> 8) & 0x00ff00ffu)));
+            int best = half == 0 ? (int)max(mx & 0xffffu, mx >> 16) : 0;
+            best = __reduce_max_sync(kFull, best);
+            if (best + 4 * remaining < need) { hopeless = true; break; }
+          }
+          remaining -= min(8, n - f0);
           uint2 w[8];
           uint32_t sh[8];
 #pragma unroll
@@ -598,7 +625,16 @@ __device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const Coa
           tot[j][0] += acc[j] & 0x00ff00ffu;
           tot[j][1] += (acc[j] >> 8) & 0x00ff00ffu;
         }
+        if (need > 0 && !hopeless && m + 1 < P.M) {   // between modalities
+          uint32_t mx = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mx = __vmaxu2(mx, __vmaxu2(tot[j][0], tot[j][1]));
+          int best = half == 0 ? (int)max(mx & 0xffffu, mx >> 16) : 0;
+          best = __reduce_max_sync(kFull, best);
+          if (best + 4 * remaining < need) hopeless = true;
+        }
       }
+      if (hopeless) { alive = false; break; }   // [OCV] would finish the sum and drop the candidate: sim < threshold
       // first maximum in raster order: key = score << 8 | (255 - raster index); byte b of word j is column
       // 8 * (j / 2) + 2 * b + (j & 1)
       uint32_t best_key = 0;

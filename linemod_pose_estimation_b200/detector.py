@@ -329,6 +329,10 @@ class Detector:
         assert lut.size == 8000
         check(lib().lm_set_normal_lut(self._h, lut.ctypes.data))
 
+    def load_normal_lut_file(self, path):
+        """NORMAL_LUT from OpenCV's own text file (modules/objdetect/src/normal_lut.i)."""
+        check(lib().lm_load_normal_lut_file(self._h, str(path).encode()))
+
     def normal_lut(self):
         out = np.empty(8000, np.uint8)
         check(lib().lm_get_normal_lut(self._h, out.ctypes.data))
@@ -386,3 +390,51 @@ class Detector:
         check(lib().lm_last_work(self._h, w))
         return dict(B_front=w[0], B_coarse=w[1], B_refine=w[2], B_out=w[3], candidates=w[4], evals=w[5],
                     B_coarse_gathered=w[6], frames=w[7])
+
+
+class DetectorGroup:
+    """Several GPUs behind one caller (lm_group): the prototype detector cloned onto `devices`, one worker thread per
+    device.  mode "frames": every device holds all templates and takes its share of the frames of a batch over its own PCIe
+    link (no exchange between devices); mode "templates": templates sharded by canonical index, every device sees every
+    frame, survivors merged before the reference's sort + unique.  Results equal the prototype's in both modes."""
+    FRAMES, TEMPLATES = 0, 1
+
+    def __init__(self, prototype, devices, mode="frames"):
+        self._h = C.c_void_p()
+        self.proto = prototype
+        dv = (C.c_int * len(devices))(*devices)
+        m = {"frames": self.FRAMES, "templates": self.TEMPLATES}[mode]
+        check(lib().lm_group_create(prototype._h, dv, len(devices), m, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().lm_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return lib().lm_group_size(self._h)
+
+    def set_option(self, key, value):
+        check(lib().lm_group_set_option(self._h, key.encode(), int(value)))
+
+    def match_batch_multi(self, frames, queries):
+        """frames: list of per-frame source lists; queries: [(threshold, [class ids])] -> list (per frame) of lists (per query)."""
+        flat = [s for f in frames for s in f]
+        arr, keep = image_array(flat)
+        qarr, qkeep = _capi.query_array(queries)
+        out = C.c_void_p()
+        n_q = len(queries)
+        offs = (C.c_size_t * (len(frames) * n_q + 1))()
+        check(lib().lm_group_match_batch_multi(self._h, arr, len(frames), len(frames[0]) if frames else 0, qarr, n_q,
+                                               C.byref(out), offs))
+        allm = self.proto._take(out, offs[len(frames) * n_q])
+        return [[allm[offs[f * n_q + q]:offs[f * n_q + q + 1]] for q in range(n_q)] for f in range(len(frames))]
+
+    def match(self, sources, threshold, class_ids=()):
+        return self.match_batch_multi([sources], [(threshold, list(class_ids))])[0][0]

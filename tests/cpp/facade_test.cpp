@@ -215,6 +215,31 @@ static int run_gpu(const std::string& dir) {
   bool self = false;
   for (size_t i = 0; i < found.size() && found[i].similarity == found[0].similarity; ++i) self = self || found[i].template_id == ids[pick];
   REQUIRE(self);
+  // several GPUs behind one caller (lm_group): both modes return the single-handle lists (members share device 0 here)
+  {
+    std::vector<int> devs(3, 0);
+    std::vector<std::vector<lm::Image> > batch(5, rframe);
+    batch[1] = frame; batch[3] = frame;
+    std::vector<lm::Match> want_r, want_f;
+    trained->match(rframe, 90.f, want_r);
+    trained->match(frame, 90.f, want_f);
+    for (int mode = 0; mode < 2; ++mode) {
+      lm::DetectorGroup group(*trained, devs, mode == 0 ? lm::DetectorGroup::Frames : lm::DetectorGroup::Templates);
+      REQUIRE(group.size() == 3);
+      group.setOption("batch_frames", 2);
+      std::vector<std::vector<lm::Match> > got;
+      group.matchBatch(batch, 90.f, got);
+      REQUIRE(got.size() == 5);
+      for (size_t f = 0; f < got.size(); ++f) {
+        const std::vector<lm::Match>& want = (f == 1 || f == 3) ? want_f : want_r;
+        REQUIRE(got[f].size() == want.size());
+        for (size_t i = 0; i < want.size(); ++i) REQUIRE(got[f][i] == want[i] && got[f][i].template_id == want[i].template_id);
+      }
+      std::vector<lm::Match> one;
+      group.match(rframe, 90.f, one);
+      REQUIRE(one.size() == want_r.size());
+    }
+  }
   std::printf("ok gpu (%zu matches, best %.2f at %d,%d)\n", matches.size(), best.similarity, best.x, best.y);
   return 0;
 }

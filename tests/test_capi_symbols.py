@@ -105,3 +105,16 @@ def test_template_generation_fails_loudly_without_gpu():
         with pytest.raises(LinemodError) as e:
             call()
         assert e.value.code == _capi.LM_E_CUDA, str(e.value)
+
+
+def test_device_group_fails_loudly_without_a_gpu():
+    """lm_group_create has no CPU path either: without a CUDA device it returns LM_E_CUDA."""
+    import ctypes as C
+
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from linemod_pose_estimation_b200 import Detector, LinemodError, DetectorGroup
+    with pytest.raises(LinemodError) as e:
+        DetectorGroup(Detector(), [0], "frames")
+    assert e.value.code == -2

@@ -153,12 +153,14 @@ def test_modality_order_of_the_coarse_sum_does_not_change_results(order, kinds):
     assert len(want) > 0
 
 
-@pytest.mark.parametrize("variant", [0])
+@pytest.mark.parametrize("variant", [3, 0])
 def test_refine_kernel_many_candidates(variant):
     """Refinement on nibble-packed planes with loose thresholds so that thousands of candidates are refined (warp per
-    candidate) and a tight one (block per candidate); the lists must be the oracle's, and the packed planes of the
-    refinement level must be its byte planes two positions per byte."""
+    candidate) and a tight one (block per candidate), with the exact early termination of hopeless candidates on
+    (`prune` 3, default) and off (0); the lists must be the oracle's, and the packed planes of the refinement level must
+    be its byte planes two positions per byte."""
     orc, det, views = _pair(n_views=8, n_random=60, seed=23, classes=("a", "b"))
+    det.set_option("prune", variant)
     for seed, thr in ((1005, 86.0), (1006, 58.0)):
         bgr, depth, _ = synth.compose_scene(seed, views[:5])
         want = orc.match([bgr, depth], thr, keep_candidates=True)
@@ -169,7 +171,7 @@ def test_refine_kernel_many_candidates(variant):
     for m in range(2):
         want = orc.fetch(Stage.LINEAR, 0, m)
         assert np.array_equal(det.fetch(Stage.LINEAR, 0, m), want)   # unpacked from the nibble planes when variant == 0
-        if variant == 0:
+        if True:
             packed = det.fetch(Stage.LINEAR_PACKED, 0, m)
             assert np.array_equal(packed & 15, want[:, 0::2]) and np.array_equal(packed >> 4, want[:, 1::2])
 
@@ -563,3 +565,108 @@ def test_config5_64_frame_batch_15_classes():
     sub = [classes[11], classes[3]]
     for f, g in zip(frames[:8], det.match_batch(frames[:8], 80.0, class_ids=sub)):
         common.assert_matches_equal(g, orc.match(f, 80.0, class_ids=sub))
+
+
+def test_cache_loaded_detector_matches_identically(tmp_path):
+    """SURVEY 8f N1 on the GPU: a detector loaded from the binary template cache (lm_create_from_cache) and one loaded
+    from the templates.yml it was written from return the original detector's -- and the oracle's -- match lists."""
+    orc, det, views = _pair(n_views=8, n_random=50, seed=171, classes=("cpu_binary", "memoryChip2"))
+    yml, cache = str(tmp_path / "templates.yml"), str(tmp_path / "templates.lmb2")
+    det.write(yml)
+    det.write_cache(cache)
+    from_cache, from_yaml = Detector.read_cache(cache), Detector.read(yml)
+    total = 0
+    for seed in (8101, 8102, 8103):
+        bgr, depth, _ = synth.compose_scene(seed, views[:5])
+        for thr, ids in ((90.0, []), (72.0, ["memoryChip2"])):
+            want = orc.match([bgr, depth], thr, class_ids=ids)
+            for d in (det, from_cache, from_yaml):
+                common.assert_matches_equal(d.match([bgr, depth], thr, class_ids=ids), want, "thr %g" % thr)
+            total += len(want)
+    assert total > 0
+    # ... and through the chunked batch path of the cache-loaded handle
+    frames = [list(synth.compose_scene(8200 + i, views[:4])[:2]) for i in range(9)]
+    for f, g in zip(frames, from_cache.match_batch(frames, 85.0)):
+        common.assert_matches_equal(g, orc.match(f, 85.0))
+
+
+def test_clusters_of_a_gpu_match_list_equal_the_restatement():
+    """SURVEY 8f N2 behind the real matcher: lm_cluster_matches (rcd_voting, cluster_filter, mean-similarity score, IoU
+    NMS -- /root/reference/src/rgbdDetector.cpp:36-145,462-574) on the match list the GPU returns, against
+    oracle/cluster_oracle.py on the oracle's list; the pose tables are the trainer's (radius and mask rectangle per view)."""
+    from oracle import cluster_oracle as CO
+    from linemod_pose_estimation_b200 import Mesh, training
+    det, orc = Detector(), O.OracleDetector()
+    mesh = Mesh(synth.bracket_mesh())
+    cam = training.camera()
+    sphere = training.ViewSphere(n_points=12, angle_step=40, radius_min=0.5, radius_max=0.7, radius_step=0.1)
+    T, up = sphere.views()
+    radii = np.array([sphere.view(i)[2] for i in range(len(sphere))])
+    tids, bbs, rects = det.trainViews(mesh, cam, T, up, "obj")[:3]
+    ok = tids >= 0
+    assert ok.sum() >= 20
+    common.copy_templates(_DetAsSource(det), _OrcAsSink(orc))
+    dists = radii[ok].astype(np.float64)
+    trects = np.stack([rects["x"][ok], rects["y"][ok], rects["width"][ok], rects["height"][ok]], 1).astype(np.int32)
+    r = training.render_views(det, mesh, cam, T[ok][:3], up[ok][:3])
+    planted = [(r["bgr"][k], r["depth"][k], r["mask"][k]) for k in range(3)]
+    n_clusters = 0
+    for seed in (8301, 8302):
+        bgr, depth, _ = synth.compose_scene(seed, planted, noise=False)
+        got, want = det.match([bgr, depth], 80.0), orc.match([bgr, depth], 80.0)
+        common.assert_matches_equal(got, want)
+        for step, thr in ((8, 2), (16, 0)):
+            a = Detector.cluster_matches(got, dists, trects, step, 0.5, 0.1, cluster_threshold=thr, iou_threshold=0.4)
+            b = CO.cluster_matches(want, dists, trects, step, 0.5, 0.1, cluster_threshold=thr, iou_threshold=0.4)
+            assert len(a) == len(b)
+            for g, w in zip(a, b):
+                assert g["index"] == tuple(w[0]) and g["rect"] == tuple(w[2]) and g["matches"] == list(w[3]) and g["score"] == w[1]
+            n_clusters += len(a)
+    assert n_clusters > 0
+
+
+class _DetAsSource:
+    def __init__(self, det):
+        self.det = det
+
+    def class_ids(self):
+        return self.det.classIds()
+
+    def num_templates(self, cid):
+        return self.det.numTemplates(cid)
+
+    def get_template(self, cid, tid):
+        return self.det.getTemplates(cid, tid)
+
+
+class _OrcAsSink:
+    def __init__(self, orc):
+        self.orc = orc
+
+    def addSyntheticTemplate(self, templates, cid):
+        return self.orc.add_synthetic_template(cid, templates)
+
+
+@pytest.mark.parametrize("mode,members", [("frames", 2), ("frames", 3), ("templates", 2), ("templates", 3)])
+def test_device_group_equals_the_oracle(mode, members):
+    """lm_group (several GPUs behind one C++ caller): frames dealt out in launch sets / templates sharded with the shards'
+    survivors merged on the host.  On a one-GPU box the members share device 0 -- the dealing, the per-member worker
+    threads, the shard merge and the ordering are the same code; bench.py and tools/groupbench.py use distinct devices."""
+    import torch
+    from linemod_pose_estimation_b200 import DetectorGroup
+    orc, det, views = _pair(n_views=8, n_random=40, seed=211, classes=("cpu_binary", "memoryChip2"))
+    det.set_option("batch_frames", 4)
+    n_dev = torch.cuda.device_count()
+    group = DetectorGroup(det, [i % n_dev for i in range(members)], mode)
+    assert len(group) == members
+    queries = [(88.0, ["memoryChip2"]), (70.0, [])]
+    frames = [list(synth.compose_scene(8400 + i, views[i % 3:i % 3 + 4])[:2]) for i in range(19)]
+    got = group.match_batch_multi(frames, queries)
+    total = 0
+    for f, per_query in zip(frames, got):
+        for (thr, ids), g in zip(queries, per_query):
+            common.assert_matches_equal(g, orc.match(f, thr, class_ids=ids), "%s x%d" % (mode, members))
+            total += len(g)
+    assert total > 0
+    common.assert_matches_equal(group.match(frames[0], 85.0), orc.match(frames[0], 85.0))
+    group.close()

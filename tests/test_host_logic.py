@@ -203,6 +203,42 @@ def test_malformed_template_files_end_in_io_errors(tmp_path):
     assert e.value.code == -3
 
 
+def test_similarity_lut_is_the_literal_upstream_table():
+    """The default SIMILARITY_LUT of the product and of the oracle is the literal 256-entry table of OpenCV 2.4's
+    linemod.cpp (tests/golden/similarity_lut_ocv.txt); SURVEY A.5's wrap-around formula is NOT it (6 (i, j) pairs differ)."""
+    text = open(os.path.join(common.GOLDEN, "similarity_lut_ocv.txt")).read()
+    vals = [int(x) for line in text.splitlines() if not line.startswith("#") for x in line.replace(",", " ").split()]
+    want = np.array(vals, np.uint8)
+    assert want.size == 256 and want.max() == 4
+    assert np.array_equal(Detector().similarity_lut(), want)
+    assert np.array_equal(O.OracleDetector().similarity_lut(), want)
+    other = common.survey_similarity_lut()
+    pairs = {(k // 32, 4 * ((k // 16) % 2) + b) for k in np.flatnonzero(other != want) for b in range(4) if (k % 16) == (1 << b)}
+    assert len(pairs) == 6 and all(i - j >= 4 for i, j in pairs)   # orientation i four or more bins above bit j
+
+
+def test_normal_lut_loader_parses_opencv_text(tmp_path):
+    """lm_load_normal_lut_file reads OpenCV's normal_lut.i layout (brace-initialised [20][20][20], comments, dimensions
+    in the declaration) and rejects files with a wrong entry count or entries above 255."""
+    rng = np.random.default_rng(3)
+    lut = (1 << rng.integers(0, 8, 8000)).astype(np.uint8)
+    body = ",\n".join("{" + ", ".join("{" + ", ".join(str(int(v)) for v in lut[(a * 20 + b) * 20:(a * 20 + b) * 20 + 20]) + "}"
+                                      for b in range(20)) + "}" for a in range(20))
+    text = "// generated\nstatic unsigned char NORMAL_LUT[20][20][20] = {\n" + body + "\n}; /* 8000 entries */\n"
+    p = tmp_path / "normal_lut.i"
+    p.write_text(text)
+    det = Detector()
+    det.load_normal_lut_file(p)
+    assert np.array_equal(det.normal_lut(), lut)
+    (tmp_path / "short.i").write_text(text.replace("{" + ", ".join(str(int(v)) for v in lut[:20]) + "}", "{1, 2}", 1))
+    (tmp_path / "big.i").write_text(text.replace("= {\n{{", "= {\n{{ 300, ", 1))
+    (tmp_path / "nobrace.i").write_text("1, 2, 3")
+    for name in ("short.i", "big.i", "nobrace.i", "missing.i"):
+        with pytest.raises(LinemodError) as e:
+            det.load_normal_lut_file(tmp_path / name)
+        assert e.value.code == -3
+
+
 def test_read_write_classes_gz(tmp_path):
     det = _random_detector(4, classes=("a", "b"))
     fmt = str(tmp_path / "templates_%s.yml.gz")
