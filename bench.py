@@ -578,7 +578,8 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peak()
         det.set_option("timing", 1)
-        n_prof = 8 * BATCH_FRAMES * DEVICE_STREAMS
+        det.set_option("batch_lanes", 1)   # one chunk at a time: the per-stage event times are those of the chunk's kernels alone
+        n_prof = 8 * BATCH_FRAMES
         samples = []
         for rep in range(4):
             flat = [a for i in range(n_prof) for a in host[(rep * n_prof + i) % FRAME_POOL]]
@@ -590,7 +591,7 @@ def run_ours(args):
             if w["frames"] == BATCH_FRAMES:
                 samples.append((t, w))
         prune_off = []
-        det.set_option("prune", 0)
+        det.set_option("prune", 2)          # coarse kernel exhaustive, refinement unchanged
         for rep in range(2):
             flat = [a for i in range(n_prof) for a in host[(rep * n_prof + i) % FRAME_POOL]]
             arr, _keep = _capi.image_array(flat)
@@ -598,8 +599,9 @@ def run_ours(args):
             _capi.check(lib.lm_match_batch_multi(det._h, arr, n_prof, 2, qarr, n_q, C.byref(out_p), poffs))
             lib.lm_free_matches(out_p)
             prune_off.append(det.last_timings()["coarse"])
-        det.set_option("prune", 1)
+        det.set_option("prune", 3)
         det.set_option("timing", 0)
+        det.set_option("batch_lanes", DEVICE_STREAMS)
         coarse = np.array([t["coarse"] for t, _ in samples])
         b_alg = float(np.mean([w["B_coarse"] for _, w in samples]))
         b_gat = float(np.mean([w["B_coarse_gathered"] for _, w in samples]))

@@ -98,6 +98,17 @@ int ensure_quant_ws(lm_detector* d, Lane& ln, int rows, int cols, int frames) {
   return LM_OK;
 }
 
+// Everything enqueued with this lane's buffers is done: its own streams and the caller's stream of the last device-resident
+// chunk.  (Not cudaDeviceSynchronize: another handle on the same device may be recording a CUDA graph in another thread,
+// and a device-wide synchronisation is illegal while any stream captures.)
+static int lane_quiesce(Lane& ln) {
+  if (ln.stream) CU(cudaStreamSynchronize(ln.stream));
+  for (int i = 0; i < LM_MAX_MODALITIES - 1; ++i)
+    if (ln.side[i]) CU(cudaStreamSynchronize(ln.side[i]));
+  if (ln.user_stream_valid) CU(cudaStreamSynchronize(ln.user_stream));
+  return LM_OK;
+}
+
 // Does this request need the reference's byte planes of a level (besides the nibble-packed ones the kernels read)?
 static bool level_needs_bytes(const lm_detector* d, const LevelGeom& g) { return d->debug_taps != 0 || !level_nibble_aligned(g); }
 
@@ -123,10 +134,10 @@ static int ensure_lm_ws(lm_detector* d, Lane& ln, int rows, int cols, int frames
     g.W = g.cols / g.T; g.H = g.rows / g.T;
     g.plane_stride = plane_stride_of(g.T, g.W, g.H);
   }
+  // everything that reads or wrote the old buffers must be done (callers' streams included) before they move
+  if (lane_quiesce(ln) != LM_OK) return LM_E_CUDA;
   if (ensure_quant_ws(d, ln, rows, cols, frames) != LM_OK) return LM_E_CUDA;
   frames = ln.frames;
-  // everything that reads or wrote the old planes must be done (callers' streams included) before they move
-  CU(cudaDeviceSynchronize());
   ln.drop_graphs();
   for (int l = 0; l < L; ++l) {
     const size_t bytes = (size_t)M * 8 * geom[l].plane_stride + kLmSlack;
@@ -601,14 +612,14 @@ static size_t head_bytes(const Lane& ln) {
 
 static int ensure_match_buffers(lm_detector* d, Lane& ln, uint32_t cand_cap, uint32_t out_cap, int frames) {
   if (cand_cap > ln.cand_cap) {
-    CU(cudaDeviceSynchronize());  // a previous chunk (possibly on a caller's stream) may still read the list
+    if (lane_quiesce(ln) != LM_OK) return LM_E_CUDA;  // a previous chunk (possibly on a caller's stream) may still read the list
     if (ln.cand.ensure((size_t)cand_cap * sizeof(Cand)) != LM_OK) return LM_E_CUDA;
     ln.cand_cap = cand_cap;
     ln.drop_graphs();
   }
   out_cap = std::max(out_cap, ln.out_cap);
   if (out_cap > ln.out_cap || ln.result.frames < frames) {
-    CU(cudaDeviceSynchronize());
+    if (lane_quiesce(ln) != LM_OK) return LM_E_CUDA;
     bool grew = false;
     if (ln.result.ensure(kStatsBytes + sizeof(ResultHeader) + (size_t)out_cap * sizeof(lm_raw_match), frames, &grew) != LM_OK) return LM_E_CUDA;
     ln.out_cap = out_cap;
@@ -1563,6 +1574,7 @@ static int device_chunk(lm_detector* d, int lane_index, const void* const* d_sou
       ln.src_ptr[f][m] = d_sources[(size_t)f * n_sources + m];
     }
   for (int m = 0; m < n_sources; ++m) ln.has_mask[m] = false;
+  ln.user_stream = s; ln.user_stream_valid = true;
   return enqueue_chunk(d, ln, *plan, qs, n_q, n_frames, s);
 }
 

@@ -108,6 +108,8 @@ static const int LM_GRAPH_SLOTS = 6;  // recorded launch geometries per lane: 1,
 // One in-flight chunk: stream, events, device workspace, pinned staging.
 struct Lane {
   cudaStream_t stream = nullptr;
+  cudaStream_t user_stream = nullptr;   // the caller's stream of the lane's last device-resident chunk
+  bool user_stream_valid = false;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // modalities quantise concurrently: modality m > 0 runs on side[m-1], forked from / joined into the chunk's stream
   cudaStream_t side[LM_MAX_MODALITIES - 1] = {nullptr, nullptr, nullptr};

@@ -67,7 +67,7 @@ def full(src, dst, traffic_json=None):
     hdr, units = rows[0], rows[1]
     with open(dst, "w") as f:
         f.write("Source: `%s` (ncu --set full --clock-control none --import-source on).\n\n" % src)
-        traffic = []
+        traffic, insts = [], []
         for r in rows[2:]:
             f.write("### %s  grid %s block %s\n\n| metric | unit | value |\n|---|---|---|\n" % (
                 r[hdr.index("Kernel Name")].split("(")[0], r[hdr.index("Grid Size")], r[hdr.index("Block Size")]))
@@ -78,8 +78,12 @@ def full(src, dst, traffic_json=None):
             f.write("\n")
             rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
             traffic.append(to_bytes(r[rd], units[rd]) + to_bytes(r[wr], units[wr]))
+            if "smsp__inst_executed.sum" in hdr:
+                insts.append(float(r[hdr.index("smsp__inst_executed.sum")].replace(",", "")))
     if traffic_json:
-        json.dump({"kernel": "k_similarity_coarse", "dram_bytes_per_launch": sum(traffic) / len(traffic),
+        json.dump({"kernel": rows[2][hdr.index("Kernel Name")].split("(")[0].split("::")[-1],
+                   "dram_bytes_per_launch": sum(traffic) / len(traffic),
+                   "warp_instructions_per_launch": (sum(insts) / len(insts)) if insts else None,
                    "launches": len(traffic), "source": src}, open(traffic_json, "w"))
 
 

@@ -77,7 +77,7 @@ def main():
     out_p = C.c_void_p()
     offs = (C.c_size_t * (args.pool * n_q + 1))()
     ref = None
-    defaults = {"batch_frames": 8, "prune": 1, "mod_order": 2, "graphs": 1}
+    defaults = {"batch_frames": 8, "prune": 3, "mod_order": 2, "graphs": 1}
     for cfg in args.configs.split(";"):
         opts = dict(defaults)
         opts.update({k: int(v) for k, v in (kv.split("=") for kv in cfg.split(","))})
@@ -124,6 +124,7 @@ def main():
             host_pass()
         e2e_us = 1e6 * (time.perf_counter() - t0) / (reps * args.pool)
         det.set_option("timing", 1)
+        det.set_option("batch_lanes", 1)    # one chunk at a time: stage times of a chunk's kernels running alone
         host_pass()
         t, w = det.last_timings(), det.last_work()
         det.set_option("timing", 0)
