@@ -185,6 +185,7 @@ struct CoarseParams {
 };
 void set_programmatic_launch(bool enabled);  // per thread; disabled while launches are recorded into a CUDA graph
 void set_coarse_grid_limit(int blocks);     // process-wide; 0 = no limit
+void set_coarse_record_prefetch(int bulk);  // process-wide A/B: 1 = cp.async.bulk + mbarrier (default), 0 = registers
 int coarse_positions_per_pass();
 int coarse_record_header_words();
 int coarse_record_max_words();

@@ -54,8 +54,37 @@ __device__ __forceinline__ void nib_flush(const uint32_t (&nib)[WORDS], uint32_t
 //    Disabled (prune = 0) for the parity tap, which wants every position's full sum.
 constexpr int kRecHdrWords = 12;                      // TileRec header, see lm_kernels.cuh
 constexpr int kRecMaxWords = kRecHdrWords + 256;      // header + LM_MAX_MODALITIES * 64 feature words
-constexpr int kRecPre = (kRecMaxWords + 31) / 32;     // registers per lane holding a prefetched record
 constexpr int kRecWarpPos = 32 * 32;
+
+// ---- bulk asynchronous copy (TMA's linear form) + mbarrier, the mechanism that stages a warp's next tile record in shared
+// memory while the current tile is scored: one elected lane arms the barrier with the byte count and issues
+// cp.async.bulk (SASS: UBLKCP); the copy engine writes shared memory and completes the transaction on the barrier; the warp
+// waits on the barrier's phase.  No registers hold the record in flight and no LDG / STS instructions move it.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LM_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LM_DONE;\n"
+      "bra LM_WAIT;\n"
+      "LM_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
 
 template <int Q>
 __device__ __forceinline__ void rec_window(const uint8_t* __restrict__ lmn, uint32_t v, uint32_t lane_byte,
@@ -168,12 +197,23 @@ __device__ __forceinline__ bool rec_alive(const uint32_t (&tot)[4][4], int thr, 
   return __any_sync(kFull, active && best > need);
 }
 
+constexpr int kRecPre = (kRecMaxWords + 31) / 32;     // registers per lane holding a prefetched record (BULK = false)
+
+template <bool BULK>
 __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarseParams P) {
-  __shared__ uint32_t s_rec[8][kRecMaxWords];
+  __shared__ __align__(16) uint32_t s_rec[8][BULK ? 2 : 1][kRecMaxWords];
+  __shared__ __align__(8) unsigned long long s_bar[8][2];
   __shared__ unsigned long long s_bytes;
   __shared__ uint32_t s_done, s_expected;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t* sr = s_rec[warp];
+  uint32_t* sr = s_rec[warp][0];
+  int buf = 0;
+  uint32_t phases = 0;   // bit b: parity of the next completion of barrier b
+  if (BULK && lane == 0) {
+    mbar_init(&s_bar[warp][0], 1);
+    mbar_init(&s_bar[warp][1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   cudaGridDependencySynchronize();            // linear memories (previous kernel in the stream) are complete
   cudaTriggerProgrammaticLaunchCompletion();  // let k_refine's blocks be scheduled as this grid drains
   BatchCtl* ctl = P.ctl;
@@ -196,7 +236,17 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarsePa
   __syncthreads();
   if (cur >= n_virtual) return;
   uint32_t cur_frame = cur / n_tiles;
-  for (int i = lane; i < rec_words; i += 32) sr[i] = __ldg(recs + (size_t)(cur - cur_frame * n_tiles) * rec_words + i);
+  const uint32_t rec_bytes = (uint32_t)rec_words * 4u;   // a multiple of 16 (records are padded to four words)
+  if (BULK) {
+    if (lane == 0) {
+      mbar_expect_tx(&s_bar[warp][0], rec_bytes);
+      bulk_g2s(sr, recs + (size_t)(cur - cur_frame * n_tiles) * rec_words, rec_bytes, &s_bar[warp][0]);
+    }
+    mbar_wait(&s_bar[warp][0], 0u);
+    phases = 1u;
+  } else {
+    for (int i = lane; i < rec_words; i += 32) sr[i] = __ldg(recs + (size_t)(cur - cur_frame * n_tiles) * rec_words + i);
+  }
   uint32_t nxt = gwarp + n_warps;
   const uint32_t lane_byte = (uint32_t)lane * 16u;
   const int first = lane * 32;  // first position of this lane within the pass
@@ -209,11 +259,19 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarsePa
     const bool has_next = nxt < n_virtual;
     const uint32_t nxt_frame = has_next ? nxt / n_tiles : 0u;
     const uint32_t nxt_tile = nxt - nxt_frame * n_tiles;
-    uint32_t pre[kRecPre];
+    uint32_t pre[BULK ? 1 : kRecPre];
+    if (BULK) {
+      // the other buffer was last read during the previous tile (every lane is past the __syncwarp above): refill it
+      if (has_next && lane == 0) {
+        mbar_expect_tx(&s_bar[warp][buf ^ 1], rec_bytes);
+        bulk_g2s(s_rec[warp][BULK ? (buf ^ 1) : 0], recs + (size_t)nxt_tile * rec_words, rec_bytes, &s_bar[warp][buf ^ 1]);
+      }
+    } else {
 #pragma unroll
-    for (int i = 0; i < kRecPre; ++i) {
-      const int idx = lane + 32 * i;
-      pre[i] = (has_next && idx < rec_words) ? __ldg(recs + (size_t)nxt_tile * rec_words + idx) : 0u;
+      for (int i = 0; i < (BULK ? 1 : kRecPre); ++i) {
+        const int idx = lane + 32 * i;
+        pre[i] = (has_next && idx < rec_words) ? __ldg(recs + (size_t)nxt_tile * rec_words + idx) : 0u;
+      }
     }
     // the ticket of the tile after next: issued now, read at the end of this tile (the atomic's round trip -- long when
     // thousands of warps draw at once -- overlaps the scoring instead of stalling it)
@@ -296,10 +354,17 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarsePa
     }
     if (!has_next) break;
     __syncwarp();
+    if (BULK) {
+      buf ^= 1;
+      sr = s_rec[warp][BULK ? buf : 0];
+      mbar_wait(&s_bar[warp][buf], (phases >> buf) & 1u);
+      phases ^= 1u << buf;
+    } else {
 #pragma unroll
-    for (int i = 0; i < kRecPre; ++i) {
-      const int idx = lane + 32 * i;
-      if (idx < rec_words) sr[idx] = pre[i];
+      for (int i = 0; i < (BULK ? 1 : kRecPre); ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < rec_words) sr[idx] = pre[i];
+      }
     }
     cur_frame = nxt_frame;
     nxt = __shfl_sync(kFull, ticket, 0) + 2u * n_warps;
@@ -579,40 +644,51 @@ __device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const Coa
       const int need = P.prune ? min_passing_score(threshold, (int)rtp->nf) : 0;
       int remaining = n_all;
       bool hopeless = false;
+      // Lanes r and r + 16 share patch row r and split the features between them (even / odd feature of a pair): every
+      // lane fetches the two aligned 8-byte chunks its window spans itself and all 32 lanes do useful arithmetic; the two
+      // halves' partial sums meet (one shuffle per register) only at the pruning checks and at the end.
+      auto best_so_far = [&](const uint32_t (&acc)[4], bool with_acc) -> int {
+        uint32_t mx = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t t0 = tot[j][0] + (with_acc ? (acc[j] & 0x00ff00ffu) : 0u);
+          uint32_t t1 = tot[j][1] + (with_acc ? ((acc[j] >> 8) & 0x00ff00ffu) : 0u);
+          t0 += __shfl_xor_sync(kFull, t0, 16);
+          t1 += __shfl_xor_sync(kFull, t1, 16);
+          mx = __vmaxu2(mx, __vmaxu2(t0, t1));
+        }
+        return (int)__reduce_max_sync(kFull, max(mx & 0xffffu, mx >> 16));
+      };
       for (int m = 0; m < P.M && !hopeless; ++m) {
         const uint8_t* lmm = L.lmn + (size_t)frame * L.frame_stride + (size_t)m * 4 * L.plane_stride;
-        const int n = rtp->cnt[m];  // <= 63 features: the u8 sums below cannot overflow
+        const int n = rtp->cnt[m];  // <= 63 features, 32 per half: the u8 sums below cannot overflow
         uint32_t acc[4] = {0, 0, 0, 0};
         for (int f0 = 0; f0 < n; f0 += 8) {
           if ((f0 & 8) == 0 && f0 > 0 && need > 0) {   // after 16, 32, 48 features of this modality (and see below at its end)
-            uint32_t mx = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              mx = __vmaxu2(mx, __vmaxu2(tot[j][0] + (acc[j] & 0x00ff00ffu), tot[j][1] + ((acc[j] >> 8) & 0x00ff00ffu)));
-            int best = half == 0 ? (int)max(mx & 0xffffu, mx >> 16) : 0;
-            best = __reduce_max_sync(kFull, best);
-            if (best + 4 * remaining < need) { hopeless = true; break; }
+            if (best_so_far(acc, true) + 4 * remaining < need) { hopeless = true; break; }
           }
           remaining -= min(8, n - f0);
-          uint2 w[8];
-          uint32_t sh[8];
+          uint2 c0[4], c1[4];
+          uint32_t sh[4];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint32_t base = f0 + k < n ? s_addr[begin + f0 + k] : zero_run;
+          for (int k = 0; k < 4; ++k) {
+            const int fi = f0 + 2 * k + half;
+            const uint32_t base = fi < n ? s_addr[begin + fi] : zero_run;
             const uint32_t nidx = base + (base == zero_run ? 0u : row_off);   // nibble index of this row's first position
             sh[k] = nidx & 15u;
-            w[k] = ldg64(lmm + (size_t)((nidx >> 4) + (uint32_t)half) * 8u);
+            const uint8_t* p = lmm + (size_t)(nidx >> 4) * 8u;
+            c0[k] = ldg64(p);
+            c1[k] = ldg64(p + 8);
           }
           uint32_t nib0 = 0, nib1 = 0;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint32_t w2 = __shfl_down_sync(kFull, w[k].x, 16), w3 = __shfl_down_sync(kFull, w[k].y, 16);
+          for (int k = 0; k < 4; ++k) {
             const bool hi = sh[k] >= 8u;                 // window starts in the second word of the first chunk
-            const uint32_t a = hi ? w[k].y : w[k].x, b = hi ? w2 : w[k].y, cc = hi ? w3 : w2;
+            const uint32_t a = hi ? c0[k].y : c0[k].x, b = hi ? c1[k].x : c0[k].y, cc = hi ? c1[k].y : c1[k].x;
             const uint32_t bits = (sh[k] & 7u) * 4u;
             nib0 += __funnelshift_r(a, b, bits);
             nib1 += __funnelshift_r(b, cc, bits);
-            if (k == 2 || k == 5 || k == 7) {            // <= 3 features per nibble sum (3 * 4 < 16)
+            if (k == 1 || k == 3) {                      // <= 3 features per nibble sum (3 * 4 < 16); two here
               acc[0] += nib0 & 0x0f0f0f0fu; acc[1] += (nib0 >> 4) & 0x0f0f0f0fu;
               acc[2] += nib1 & 0x0f0f0f0fu; acc[3] += (nib1 >> 4) & 0x0f0f0f0fu;
               nib0 = nib1 = 0;
@@ -626,15 +702,16 @@ __device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const Coa
           tot[j][1] += (acc[j] >> 8) & 0x00ff00ffu;
         }
         if (need > 0 && !hopeless && m + 1 < P.M) {   // between modalities
-          uint32_t mx = 0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) mx = __vmaxu2(mx, __vmaxu2(tot[j][0], tot[j][1]));
-          int best = half == 0 ? (int)max(mx & 0xffffu, mx >> 16) : 0;
-          best = __reduce_max_sync(kFull, best);
-          if (best + 4 * remaining < need) hopeless = true;
+          const uint32_t none[4] = {0, 0, 0, 0};
+          if (best_so_far(none, false) + 4 * remaining < need) hopeless = true;
         }
       }
       if (hopeless) { alive = false; break; }   // [OCV] would finish the sum and drop the candidate: sim < threshold
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // the two halves of a row meet
+        tot[j][0] += __shfl_xor_sync(kFull, tot[j][0], 16);
+        tot[j][1] += __shfl_xor_sync(kFull, tot[j][1], 16);
+      }
       // first maximum in raster order: key = score << 8 | (255 - raster index); byte b of word j is column
       // 8 * (j / 2) + 2 * b + (j & 1)
       uint32_t best_key = 0;
@@ -738,16 +815,20 @@ static int resident_ctas(K kernel) {
   return per_sm * sms;
 }
 
+static int g_rec_prefetch_bulk = 1;
+void set_coarse_record_prefetch(int bulk) { g_rec_prefetch_bulk = bulk; }
+
 void launch_similarity_coarse(const CoarseParams& p, int max_frames, cudaStream_t s) {
   if (p.n_tiles <= 0) return;
-  static const int persistent = resident_ctas(k_similarity_coarse_rec);
+  static const int persistent = std::min(resident_ctas(k_similarity_coarse_rec<true>), resident_ctas(k_similarity_coarse_rec<false>));
   const long long blocks = ((long long)p.n_tiles * max_frames + 7) / 8;
   int grid = (int)std::min<long long>(blocks, persistent);
   if (g_coarse_grid_limit > 0) grid = min(grid, g_coarse_grid_limit);
   CoarseParams q = p;
   if (q.dump != nullptr) q.prune = 0;
   cudaLaunchConfig_t cfg = pdl_config(grid, 256, s);
-  cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec, q);
+  if (g_rec_prefetch_bulk) cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec<true>, q);
+  else cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec<false>, q);
 }
 
 void launch_pack_nibbles(const uint8_t* lm_bytes, size_t bytes_stride, uint8_t* lm_nibbles, size_t nib_stride, size_t n_bytes,
@@ -764,7 +845,7 @@ void launch_begin_chunk(const FrameTable& ft, BatchCtl* ctl, uint8_t* results, s
 
 void launch_refine(const RefineParams& p, const CoarseTpl* ctpl, const Cand* cand, uint32_t cand_cap, BatchCtl* ctl,
                    uint8_t* results, size_t result_stride, uint32_t out_cap, cudaStream_t s) {
-  cudaLaunchConfig_t cfg = pdl_config(148 * 3, kRefineWarps * 32, s);  // 3 resident CTAs per SM
+  cudaLaunchConfig_t cfg = pdl_config(148 * 4, kRefineWarps * 32, s);  // 4 resident CTAs per SM (64 registers)
   cudaLaunchKernelEx(&cfg, k_refine_nib, p, ctpl, cand, cand_cap, ctl, results, result_stride, out_cap);
 }
 
