@@ -18,6 +18,7 @@
 #define LINEMOD_B200_HPP_
 
 #include <cstdint>
+#include <cstring>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -149,6 +150,12 @@ class DepthNormal : public Modality {
   size_t num_features;
   int extract_threshold;
 };
+
+inline std::shared_ptr<Modality> Detector_from_desc_impl(const lm_modality_desc& d) {
+  if (d.type == LM_COLOR_GRADIENT)
+    return std::make_shared<ColorGradient>(d.weak_threshold, (size_t)d.num_features, d.strong_threshold);
+  return std::make_shared<DepthNormal>(d.distance_threshold, d.difference_threshold, (size_t)d.num_features, d.extract_threshold);
+}
 
 inline std::shared_ptr<Modality> Modality::create(const std::string& modality_type) {
   if (modality_type == "ColorGradient") return std::make_shared<ColorGradient>();
@@ -291,11 +298,7 @@ class Detector {
     for (int m = 0; m < lm_num_modalities(h_); ++m) {
       lm_modality_desc d;
       detail::check(lm_get_modality(h_, m, &d));
-      if (d.type == LM_COLOR_GRADIENT)
-        modalities_.push_back(std::make_shared<ColorGradient>(d.weak_threshold, (size_t)d.num_features, d.strong_threshold));
-      else
-        modalities_.push_back(std::make_shared<DepthNormal>(d.distance_threshold, d.difference_threshold,
-                                                            (size_t)d.num_features, d.extract_threshold));
+      modalities_.push_back(from_desc(d));
     }
   }
   // writeLinemod(detector, filename): Detector::write(fs) + "classes" [ { writeClass } ... ].
@@ -314,6 +317,164 @@ class Detector {
   }
 
 #ifdef LINEMOD_B200_WITH_OPENCV
+  // ---- the OpenCV spellings the reference uses, so that its call sites compile unchanged against this class:
+  //   cv::Ptr<cv::linemod::Detector> detector_(new cv::linemod::Detector(modalities, T))      src/renderer.cpp:179-185
+  //   detector->read(fs.root()); detector->readClass(*i)  (readLinemod)                         src/rgbdDetector.cpp:1668-1680
+  //   detector->write(fs); detector->writeClass(ids[i], fs)  (writeLinemod)                     src/renderer.cpp:56-70
+  //   linemod_detector->match(sources, threshold, matches, std::vector<String>(), noArray())   src/rgbdDetector.cpp:33
+  Detector(const std::vector<cv::Ptr<Modality> >& modalities, const std::vector<int>& T_pyramid) : h_(nullptr) {
+    std::vector<lm_modality_desc> mods;
+    for (size_t i = 0; i < modalities.size(); ++i) {
+      mods.push_back(modalities[i]->desc());
+      modalities_.push_back(from_desc(mods.back()));
+    }
+    std::vector<int32_t> T(T_pyramid.begin(), T_pyramid.end());
+    detail::check(lm_create(T.data(), (int)T.size(), mods.data(), (int)mods.size(), &h_));
+  }
+
+  // [OCV] Detector::read: "pyramid_levels", "T", "modalities" [ { type, parameters } ... ] of a templates.yml root node.
+  // Replaces the detector's configuration and drops its classes, like upstream.
+  void read(const cv::FileNode& fn) {
+    const int levels = (int)fn["pyramid_levels"];
+    std::vector<int> T;
+    fn["T"] >> T;
+    if (levels < 1 || (int)T.size() != levels) throw Exception(LM_E_IO, "templates file: pyramid_levels / T mismatch");
+    std::vector<lm_modality_desc> mods;
+    const cv::FileNode mn = fn["modalities"];
+    for (cv::FileNodeIterator it = mn.begin(), e = mn.end(); it != e; ++it) {
+      const cv::FileNode m = *it;
+      const std::string type = (std::string)m["type"];
+      lm_modality_desc d = Modality::create(type)->desc();
+      if (d.type == LM_COLOR_GRADIENT) {
+        if (!m["weak_threshold"].empty()) d.weak_threshold = (float)m["weak_threshold"];
+        if (!m["strong_threshold"].empty()) d.strong_threshold = (float)m["strong_threshold"];
+      } else {
+        if (!m["distance_threshold"].empty()) d.distance_threshold = (int)m["distance_threshold"];
+        if (!m["difference_threshold"].empty()) d.difference_threshold = (int)m["difference_threshold"];
+        if (!m["extract_threshold"].empty()) d.extract_threshold = (int)m["extract_threshold"];
+      }
+      if (!m["num_features"].empty()) d.num_features = (int)m["num_features"];
+      mods.push_back(d);
+    }
+    std::vector<int32_t> T32(T.begin(), T.end());
+    lm_detector* fresh = nullptr;
+    detail::check(lm_create(T32.data(), levels, mods.data(), (int)mods.size(), &fresh));
+    lm_destroy(h_);
+    h_ = fresh;
+    cache_.clear();
+    modalities_.clear();
+    for (size_t i = 0; i < mods.size(); ++i) modalities_.push_back(from_desc(mods[i]));
+  }
+
+  // [OCV] Detector::readClass: one entry of "classes".  The CV_Asserts of upstream (modalities and pyramid_levels match the
+  // detector, the class is new, template ids are consecutive) become Exceptions.  Returns the class id.
+  std::string readClass(const cv::FileNode& fn, const std::string& class_id_override = "") {
+    need_handle();
+    const cv::FileNode mn = fn["modalities"];
+    if (mn.size() != modalities_.size()) throw Exception(LM_E_IO, "class modalities do not match the detector");
+    size_t k = 0;
+    for (cv::FileNodeIterator it = mn.begin(), e = mn.end(); it != e; ++it, ++k)
+      if ((std::string)(*it) != modalities_[k]->name()) throw Exception(LM_E_IO, "class modality '" + (std::string)(*it) + "' does not match the detector");
+    if ((int)fn["pyramid_levels"] != pyramidLevels()) throw Exception(LM_E_IO, "class pyramid_levels does not match the detector");
+    const std::string class_id = class_id_override.empty() ? (std::string)fn["class_id"] : class_id_override;
+    if (numTemplates(class_id) != 0) throw Exception(LM_E_IO, "detector already has class '" + class_id + "'");
+    const cv::FileNode tps = fn["template_pyramids"];
+    int expected_id = 0;
+    for (cv::FileNodeIterator it = tps.begin(), e = tps.end(); it != e; ++it, ++expected_id) {
+      const cv::FileNode tpn = *it;
+      if ((int)tpn["template_id"] != expected_id) throw Exception(LM_E_IO, "template_id out of sequence");
+      std::vector<Template> tp;
+      const cv::FileNode tn = tpn["templates"];
+      for (cv::FileNodeIterator jt = tn.begin(), je = tn.end(); jt != je; ++jt) {
+        const cv::FileNode t = *jt;
+        Template tm;
+        tm.width = (int)t["width"]; tm.height = (int)t["height"]; tm.pyramid_level = (int)t["pyramid_level"];
+        const cv::FileNode feats = t["features"];
+        for (cv::FileNodeIterator ft = feats.begin(), fe = feats.end(); ft != fe; ++ft) {
+          const cv::FileNode f = *ft;
+          tm.features.push_back(Feature((int)f[0], (int)f[1], (int)f[2]));
+        }
+        tp.push_back(tm);
+      }
+      if (addSyntheticTemplate(tp, class_id) != expected_id) throw Exception(LM_E_IO, "template_id out of sequence");
+    }
+    return class_id;
+  }
+
+  // [OCV] Detector::write: the detector's configuration into an open FileStorage (same keys as lm_write_yaml emits).
+  void write(cv::FileStorage& fs) const {
+    need_handle();
+    fs << "pyramid_levels" << pyramidLevels();
+    std::vector<int> T;
+    for (int l = 0; l < pyramidLevels(); ++l) T.push_back(getT(l));
+    fs << "T" << T;
+    fs << "modalities" << "[";
+    for (int m = 0; m < lm_num_modalities(h_); ++m) {
+      lm_modality_desc d;
+      detail::check(lm_get_modality(h_, m, &d));
+      fs << "{";
+      if (d.type == LM_COLOR_GRADIENT) {
+        fs << "type" << "ColorGradient" << "weak_threshold" << d.weak_threshold << "num_features" << (int)d.num_features
+           << "strong_threshold" << d.strong_threshold;
+      } else {
+        fs << "type" << "DepthNormal" << "distance_threshold" << (int)d.distance_threshold << "difference_threshold"
+           << (int)d.difference_threshold << "num_features" << (int)d.num_features << "extract_threshold" << (int)d.extract_threshold;
+      }
+      fs << "}";
+    }
+    fs << "]";
+  }
+
+  // [OCV] Detector::writeClass: class_id, modalities, pyramid_levels, template_pyramids [ { template_id, templates [ ... ] } ]
+  void writeClass(const std::string& class_id, cv::FileStorage& fs) const {
+    need_handle();
+    if (numTemplates(class_id) == 0 && numClasses() == 0) throw Exception(LM_E_NOTFOUND, "unknown class '" + class_id + "'");
+    fs << "class_id" << class_id;
+    fs << "modalities" << "[:";
+    for (size_t i = 0; i < modalities_.size(); ++i) fs << modalities_[i]->name();
+    fs << "]";
+    fs << "pyramid_levels" << pyramidLevels();
+    fs << "template_pyramids" << "[";
+    const int n = numTemplates(class_id);
+    for (int i = 0; i < n; ++i) {
+      const std::vector<Template>& tp = getTemplates(class_id, i);
+      fs << "{";
+      fs << "template_id" << i;
+      fs << "templates" << "[";
+      for (size_t j = 0; j < tp.size(); ++j) {
+        fs << "{";
+        fs << "width" << tp[j].width << "height" << tp[j].height << "pyramid_level" << tp[j].pyramid_level;
+        fs << "features" << "[";
+        for (size_t k = 0; k < tp[j].features.size(); ++k)
+          fs << "[:" << tp[j].features[k].x << tp[j].features[k].y << tp[j].features[k].label << "]";
+        fs << "]";
+        fs << "}";
+      }
+      fs << "]";
+      fs << "}";
+    }
+    fs << "]";
+  }
+
+  // Detector::match with OpenCV's own parameter list (class_ids given, quantized_images as an OutputArrayOfArrays)
+  void match(const std::vector<cv::Mat>& sources, float threshold, std::vector<Match>& matches,
+             const std::vector<std::string>& class_ids, cv::OutputArrayOfArrays quantized_images,
+             const std::vector<cv::Mat>& masks = std::vector<cv::Mat>()) const {
+    std::vector<Image> src(sources.begin(), sources.end()), msk(masks.begin(), masks.end());
+    std::vector<std::vector<uint8_t> > q;
+    match(src, threshold, matches, class_ids, quantized_images.needed() ? &q : nullptr, msk);
+    if (quantized_images.needed()) {
+      const int M = lm_num_modalities(h_);
+      quantized_images.create(1, (int)q.size(), CV_8U);
+      for (size_t i = 0; i < q.size(); ++i) {
+        const int l = (int)i / M, r = sources[0].rows >> l, c = sources[0].cols >> l;
+        quantized_images.create(r, c, CV_8UC1, (int)i);
+        cv::Mat dst = quantized_images.getMat((int)i);
+        for (int y = 0; y < r; ++y) std::memcpy(dst.data + (size_t)y * dst.step[0], q[i].data() + (size_t)y * c, (size_t)c);
+      }
+    }
+  }
+
   // cv::Mat spellings of the two calls the reference makes with images.
   void match(const std::vector<cv::Mat>& sources, float threshold, std::vector<Match>& matches,
              const std::vector<std::string>& class_ids = std::vector<std::string>(),
@@ -350,6 +511,7 @@ class Detector {
   lm_detector* handle() const { return h_; }  // for the batch / multi-query / multi-GPU entry points of the C ABI
 
  private:
+  static std::shared_ptr<Modality> from_desc(const lm_modality_desc& d);
   void need_handle() const {
     if (!h_) throw Exception(LM_E_STATE, "empty Detector: construct it with modalities or read() a templates.yml first");
   }
@@ -357,6 +519,8 @@ class Detector {
   std::vector<std::shared_ptr<Modality> > modalities_;
   mutable std::map<std::pair<std::string, int>, TemplatePyramid> cache_;
 };
+
+inline std::shared_ptr<Modality> Detector::from_desc(const lm_modality_desc& d) { return Detector_from_desc_impl(d); }
 
 // ------------------------------------------------------------------------------------------------ several GPUs, one caller
 // lm_group: `prototype`'s model cloned onto `devices`, one worker thread per device.  Frames: every device holds all

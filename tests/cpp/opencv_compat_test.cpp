@@ -1,0 +1,177 @@
+// opencv_compat_test.cpp -- the reference's own call sites, verbatim, compiled against include/linemod_b200.hpp with
+// LINEMOD_B200_WITH_OPENCV and the OpenCV 2.4 API stub under tests/cpp/opencv_stub (the image has no OpenCV C++):
+//   readLinemod          /root/reference/src/rgbdDetector.cpp:1668-1680   Detector::read(FileNode) + readClass(FileNode)
+//   writeLinemod         /root/reference/src/renderer.cpp:56-70           Detector::write(FileStorage) + writeClass
+//   detector construction  /root/reference/src/renderer.cpp:179-185       cv::Ptr modalities, cv::Ptr<Detector>
+//   linemod_detection    /root/reference/src/rgbdDetector.cpp:31-34       match(sources, threshold, matches, vector<String>(), noArray())
+// The only line a maintainer adds is the namespace alias below.
+//   opencv_compat_test host   persistence round trip through the FileStorage API, no CUDA device needed
+//   opencv_compat_test gpu    linemod_detection on cv::Mat frames
+#define LINEMOD_B200_WITH_OPENCV
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include <opencv2/core/core.hpp>
+
+#include "../../include/linemod_b200.hpp"
+
+namespace cv { namespace linemod = ::linemod_b200; }  // was: OpenCV's own cv::linemod (opencv2/objdetect/objdetect.hpp)
+using namespace cv;
+using namespace std;
+
+#define REQUIRE(cond)                                                             \
+  do {                                                                            \
+    if (!(cond)) { std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); std::exit(1); } \
+  } while (0)
+
+// ---------------------------------------------------------------- verbatim: src/rgbdDetector.cpp:1668-1680 (rgbdDetector:: dropped)
+cv::Ptr<cv::linemod::Detector> readLinemod(const std::string& filename)
+{
+  //cv::Ptr<cv::linemod::Detector> detector = cv::makePtr<cv::linemod::Detector>();
+  cv::Ptr<cv::linemod::Detector> detector(new cv::linemod::Detector);
+  cv::FileStorage fs(filename, cv::FileStorage::READ);
+  detector->read(fs.root());
+
+  cv::FileNode fn = fs["classes"];
+  for (cv::FileNodeIterator i = fn.begin(), iend = fn.end(); i != iend; ++i)
+    detector->readClass(*i);
+
+  return detector;
+}
+
+// ---------------------------------------------------------------- verbatim: src/renderer.cpp:56-70
+static void writeLinemod(const cv::Ptr<cv::linemod::Detector>& detector, const std::string& filename)
+{
+  cv::FileStorage fs(filename, cv::FileStorage::WRITE);
+  detector->write(fs);
+
+  std::vector<cv::String> ids = detector->classIds();
+  fs << "classes" << "[";
+  for (int i = 0; i < (int)ids.size(); ++i)
+  {
+    fs << "{";
+    detector->writeClass(ids[i], fs);
+    fs << "}"; // current class
+  }
+  fs << "]"; // classes
+}
+
+// ---------------------------------------------------------------- verbatim: src/rgbdDetector.cpp:31-34 (rgbdDetector:: dropped)
+void linemod_detection(Ptr<linemod::Detector> linemod_detector,const vector<Mat>& sources,const float& threshold,std::vector<linemod::Match>& matches)
+{
+    linemod_detector->match (sources,threshold,matches,std::vector<String>(),noArray());
+}
+
+static cv::Ptr<cv::linemod::Detector> make_detector() {
+  // ---------------------------------------------------------------- verbatim: src/renderer.cpp:179-185
+    std::vector< cv::Ptr<cv::linemod::Modality> > modalities;
+    modalities.push_back(cv::Ptr<cv::linemod::ColorGradient>(new cv::linemod::ColorGradient));
+    modalities.push_back(cv::Ptr<cv::linemod::DepthNormal>(new cv::linemod::DepthNormal));
+    std::vector<int> ensenso_T;
+    ensenso_T.push_back(5);
+    ensenso_T.push_back(8);
+    cv::Ptr<cv::linemod::Detector> detector_(new cv::linemod::Detector(modalities,ensenso_T));
+  return detector_;
+}
+
+static uint32_t rng_state = 99u;
+static uint32_t rnd() { rng_state = rng_state * 1664525u + 1013904223u; return rng_state >> 8; }
+
+static std::vector<linemod::Template> synthetic_pyramid(int w, int h) {
+  std::vector<linemod::Template> tp(4);
+  for (int l = 0; l < 2; ++l)
+    for (int m = 0; m < 2; ++m) {
+      linemod::Template& t = tp[l * 2 + m];
+      t.width = w >> l; t.height = h >> l; t.pyramid_level = l;
+      const int nf = l == 0 ? 63 : 31;
+      for (int i = 0; i < nf; ++i) t.features.push_back(linemod::Feature((int)(rnd() % (w >> l)), (int)(rnd() % (h >> l)), (int)(rnd() % 8)));
+    }
+  return tp;
+}
+
+static void same_templates(const linemod::Detector& a, const linemod::Detector& b) {
+  REQUIRE(a.classIds() == b.classIds() && a.numTemplates() == b.numTemplates());
+  REQUIRE(a.pyramidLevels() == b.pyramidLevels() && a.getT(0) == b.getT(0) && a.getT(1) == b.getT(1));
+  std::vector<String> ids = a.classIds();
+  for (size_t c = 0; c < ids.size(); ++c)
+    for (int t = 0; t < a.numTemplates(ids[c]); ++t) {
+      const std::vector<linemod::Template>&x = a.getTemplates(ids[c], t), &y = b.getTemplates(ids[c], t);
+      REQUIRE(x.size() == y.size());
+      for (size_t i = 0; i < x.size(); ++i) {
+        REQUIRE(x[i].width == y[i].width && x[i].height == y[i].height && x[i].pyramid_level == y[i].pyramid_level);
+        REQUIRE(x[i].features.size() == y[i].features.size());
+        for (size_t k = 0; k < x[i].features.size(); ++k)
+          REQUIRE(x[i].features[k].x == y[i].features[k].x && x[i].features[k].y == y[i].features[k].y && x[i].features[k].label == y[i].features[k].label);
+      }
+    }
+}
+
+static int run_host(const std::string& dir) {
+  cv::Ptr<cv::linemod::Detector> det = make_detector();
+  REQUIRE(det->getModalities().size() == 2 && det->getModalities()[1]->name() == "DepthNormal");
+  for (int i = 0; i < 5; ++i) REQUIRE(det->addSyntheticTemplate(synthetic_pyramid(100 + 8 * i, 90), "obj") == i);
+  REQUIRE(det->addSyntheticTemplate(synthetic_pyramid(64, 72), "another") == 0);
+  writeLinemod(det, dir + "/templates.yml");
+  cv::Ptr<cv::linemod::Detector> back = readLinemod(dir + "/templates.yml");
+  same_templates(*det, *back);
+  // the same model through the library's own YAML writer / reader (the on-disk format) agrees with the FileStorage walk
+  det->write(dir + "/templates_disk.yml");
+  linemod::Detector disk;
+  disk.read(dir + "/templates_disk.yml");
+  same_templates(*back, disk);
+  // upstream's CV_Asserts: a class may be read once; modalities and pyramid_levels of a class must match the detector
+  cv::FileStorage fs(dir + "/templates.yml", cv::FileStorage::READ);
+  bool threw = false;
+  try { back->readClass(*fs["classes"].begin()); } catch (const linemod::Exception&) { threw = true; }
+  REQUIRE(threw);
+  REQUIRE(back->readClass(*fs["classes"].begin(), "renamed") == "renamed" && back->numTemplates("renamed") == back->numTemplates("another"));
+  std::vector< cv::Ptr<cv::linemod::Modality> > one;
+  one.push_back(cv::Ptr<cv::linemod::ColorGradient>(new cv::linemod::ColorGradient));
+  cv::linemod::Detector rgb_only(one, std::vector<int>(2, 4));
+  threw = false;
+  try { rgb_only.readClass(*fs["classes"].begin()); } catch (const linemod::Exception&) { threw = true; }
+  REQUIRE(threw);
+  std::printf("ok host\n");
+  return 0;
+}
+
+static int run_gpu(const std::string&) {
+  cv::Ptr<cv::linemod::Detector> det = make_detector();
+  // a textured box on a plane, as cv::Mat
+  const int rows = 480, cols = 640;
+  cv::Mat bgr(rows, cols, CV_8UC3), depth(rows, cols, CV_16UC1), mask(rows, cols, CV_8UC1);
+  for (int y = 0; y < rows; ++y)
+    for (int x = 0; x < cols; ++x) {
+      const bool in = x >= 200 && x < 330 && y >= 150 && y < 260;
+      const int v = in ? (((x / 13 + y / 11) & 1) ? 220 : 40) : 110 + ((x * 7 + y * 3) % 9);
+      for (int c = 0; c < 3; ++c) bgr.data[(size_t)y * bgr.step[0] + 3 * x + c] = (uchar)(in ? (c == 1 ? v : 255 - v) : v);
+      reinterpret_cast<unsigned short*>(depth.data + (size_t)y * depth.step[0])[x] = (unsigned short)(in ? 700 + (x - 200) / 4 : 1000 + x / 16);
+      mask.data[(size_t)y * mask.step[0] + x] = in ? 255 : 0;
+    }
+  std::vector<cv::Mat> sources;
+  sources.push_back(bgr);
+  sources.push_back(depth);
+  cv::Rect bb;
+  REQUIRE(det->addTemplate(sources, "obj", mask, &bb) == 0 && bb.width > 60);
+  std::vector<linemod::Match> matches;
+  linemod_detection(det, sources, 90.f, matches);
+  REQUIRE(!matches.empty() && matches[0].class_id == "obj" && matches[0].similarity >= 99.f);
+  // quantized_images as an OutputArrayOfArrays, like OpenCV's signature
+  std::vector<cv::Mat> quantized;
+  std::vector<linemod::Match> again;
+  det->match(sources, 90.f, again, std::vector<String>(), quantized);
+  REQUIRE(again.size() == matches.size() && quantized.size() == 4 && quantized[0].rows == 480 && quantized[2].cols == 320);
+  std::printf("ok gpu (%zu matches)\n", matches.size());
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 3) { std::fprintf(stderr, "usage: opencv_compat_test host|gpu <tmpdir>\n"); return 2; }
+  try {
+    return std::strcmp(argv[1], "gpu") == 0 ? run_gpu(argv[2]) : run_host(argv[2]);
+  } catch (const linemod::Exception& e) {
+    std::fprintf(stderr, "linemod_b200::Exception %d: %s\n", e.code, e.what());
+    return 1;
+  }
+}
