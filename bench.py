@@ -48,10 +48,45 @@ COARSE_POSITIONS = (COLS // 2 // 8) * (ROWS // 2 // 8)  # lowest pyramid level 3
 # 65-290 px long -- the template size range of the set the reference ships pose data for (55-194 px)
 CLASSES = (("memoryChip2", 92.0, (0.25, 0.45, 0.04)), ("cpu_binary", 94.0, (0.15, 0.30, 0.03)))
 QUERIES = [(thr, [cid]) for cid, thr, _ in CLASSES]
-MIN_ELEVATION_COS = 0.5     # both objects are flat parts: views closer than 30 degrees to the part's plane (edge-on, a
-                            # silhouette a few pixels thin that "matches" every straight edge) are not trained
+MESH_OF = {}                # class -> mesh name when it differs from the class id (configs 4 and 5)
+STRIDE_OF = {}              # class -> view stride when it differs from VIEW_STRIDE
+MIN_ELEVATION_COS = 0.5     # memoryChip2 / cpu_binary are flat parts: views closer than 30 degrees to the part's plane (edge-on,
+                            # a silhouette a few pixels thin that "matches" every straight edge) are not trained
 VIEW_STRIDE = 3             # every 3rd of the remaining ~7 650 views of the 15 300-view sphere: ~2 550 views per class
 INSTANCES_PER_CLASS = 2
+CONFIG_NAME = "configs[1]: two-object detector (memoryChip2 thr 92 + cpu_binary thr 94)"
+
+
+def apply_config(n):
+    """BASELINE.json configs[n-1] other than the default (2): rewrites the workload constants above."""
+    global CLASSES, QUERIES, ROWS, COLS, COARSE_POSITIONS, INSTANCES_PER_CLASS, CONFIG_NAME, MESH_OF, STRIDE_OF, E2E_CALL
+    if n == 2:
+        return
+    if n == 3:     # 1280x960 (1280x1024 is not divisible by T = 5), looser threshold: refinement-heavy
+        ROWS, COLS = 960, 1280
+        CLASSES = (("memoryChip2", 88.0, (0.25, 0.45, 0.04)), ("cpu_binary", 88.0, (0.15, 0.30, 0.03)))
+        INSTANCES_PER_CLASS = 6
+        CONFIG_NAME = "configs[2]: 1280x960 Ensenso-resolution frames, dual-modality detector, thr 88, refinement-heavy"
+    elif n == 4:   # ~20 000 templates: every non-edge-on view of both parts + every 3rd view of boxNew's sphere
+        CLASSES = (("memoryChip2", 92.0, (0.25, 0.45, 0.04)), ("cpu_binary", 94.0, (0.15, 0.30, 0.03)), ("boxNew", 92.0, (0.5, 1.0, 0.1)))
+        STRIDE_OF = {"memoryChip2": 1, "cpu_binary": 1, "boxNew": 3}
+        CONFIG_NAME = "configs[3]: ~20 000 renderer-generated templates (dense view sphere x in-plane rotations x scales), 3 objects"
+    elif n == 5:   # 15 classes x ~1 300 templates: three meshes at five distances each, one query over all classes at thr 90
+        cls = []
+        for k in range(5):
+            for mesh, r0, dr, stride in (("memoryChip2", 0.25, 0.05, 1), ("cpu_binary", 0.15, 0.04, 1), ("boxNew", 0.5, 0.1, 2)):
+                cid = "%s_r%d" % (mesh, k)
+                r = r0 + k * dr
+                cls.append((cid, 90.0, (r, r, 1.0)))
+                MESH_OF[cid] = mesh
+                STRIDE_OF[cid] = stride
+        CLASSES = tuple(cls)
+        E2E_CALL = 64
+        CONFIG_NAME = "configs[4]: 64-frame batches of a 640x480 video against 15 object classes (3 meshes x 5 distances)"
+    else:
+        raise SystemExit("unknown --config %d" % n)
+    COARSE_POSITIONS = (COLS // 2 // 8) * (ROWS // 2 // 8)
+    QUERIES = [(CLASSES[0][1], [])] if n == 5 else [(thr, [cid]) for cid, thr, _ in CLASSES]
 FRAME_POOL = 128            # 128 x 1.536 MB = 197 MB of distinct input frames > 126 MB L2
 METRIC = "template_pixel_evals_per_sec_640x480"
 MIN_TIMED_S = float(os.environ.get("LM_BENCH_MIN_TIMED_S", "0.4"))   # lower bound of every timed region
@@ -64,19 +99,22 @@ REFERENCE_BUDGET_S = 60.0   # wall-clock bound of the CPU arm's timed region
 # ------------------------------------------------------------------------------------------------ workload
 def meshes():
     G = np.load(os.path.join(ROOT, "tests", "golden", "meshes_config2.npz"))
-    return {cid: np.ascontiguousarray(G[cid], np.float32) for cid, _, _ in CLASSES}
+    B = np.load(os.path.join(ROOT, "tests", "golden", "renderer_params_boxnew.npz"))
+    src = {"memoryChip2": G["memoryChip2"], "cpu_binary": G["cpu_binary"], "boxNew": B["triangles"]}
+    return {cid: np.ascontiguousarray(src[MESH_OF.get(cid, cid)], np.float32) for cid, _, _ in CLASSES}
 
 
 def class_views(view_list_of, stride=None):
     """{class: (T[n,3], up[n,3])}: every `stride`-th view, in iteration order, of the views of the class's sphere that
     look at the part from at least 30 degrees above its plane (T = camera position in the object frame, z = part normal)."""
     out = {}
-    stride = stride or VIEW_STRIDE
     for cid, _, (r0, r1, rs) in CLASSES:
         T, up = view_list_of(r0, r1, rs)
-        keep = np.abs(T[:, 2]) >= MIN_ELEVATION_COS * np.linalg.norm(T, axis=1)
-        T, up = T[keep], up[keep]
-        out[cid] = (np.ascontiguousarray(T[::stride]), np.ascontiguousarray(up[::stride]))
+        if MESH_OF.get(cid, cid) != "boxNew":   # the flat parts
+            keep = np.abs(T[:, 2]) >= MIN_ELEVATION_COS * np.linalg.norm(T, axis=1)
+            T, up = T[keep], up[keep]
+        st = stride or STRIDE_OF.get(cid, VIEW_STRIDE)
+        out[cid] = (np.ascontiguousarray(T[::st]), np.ascontiguousarray(up[::st]))
     return out
 
 
@@ -125,14 +163,14 @@ def workload_config(world, n_templates, per_gpu, mode):
          "link; no data-path collective" % world) if mode == "frames" else
         ("templates sharded x%d by canonical index, frame replicated (broadcast from rank 0 on the e2e path), survivor blocks "
          "all-gathered once per run of frames, rank 0 finalises" % world))
-    return {"workload": "configs[1]: two-object detector (memoryChip2 thr 92 + cpu_binary thr 94), ColorGradient+DepthNormal, "
-                        "T={5,8}, TRAINED template sets (every %dth non-edge-on view of the reference's 15 300-view sphere of "
-                        "its own meshes), synthetic 640x480 RGB-D stream with %d rendered instances per class in clutter; step = 1 "
-                        "frame = 1 front end + 1 matching pass per class" % (VIEW_STRIDE, INSTANCES_PER_CLASS),
+    return {"workload": CONFIG_NAME + ", ColorGradient+DepthNormal, T={5,8}, TRAINED template sets (views of the reference's "
+                        "RendererIterator sphere of its own meshes, edge-on views of the flat parts left out), synthetic %dx%d RGB-D "
+                        "stream with %d rendered instances per class in clutter; step = 1 frame = 1 front end + 1 matching pass per "
+                        "query (%d)" % (COLS, ROWS, INSTANCES_PER_CLASS, len(QUERIES)),
             "templates_total": n_templates, "templates_per_gpu": per_gpu, "classes": len(CLASSES),
-            "evals_per_step": n_templates * COARSE_POSITIONS, "frame": "640x480 BGR u8 + depth u16", "mode": mode,
+            "evals_per_step": n_templates * COARSE_POSITIONS, "frame": "%dx%d BGR u8 + depth u16" % (COLS, ROWS), "mode": mode,
             "parallelism": par + "; every kernel launch covers a chunk of %d frames, %d chunks in flight" % (BATCH_FRAMES, DEVICE_STREAMS),
-            "l2": "pool of %d distinct frames (%.0f MB > 126 MB L2) cycled; linear memories are produced and consumed inside each step" % (FRAME_POOL, FRAME_POOL * 1.536)}
+            "l2": "pool of %d distinct frames (%.0f MB > 126 MB L2) cycled; linear memories are produced and consumed inside each step" % (FRAME_POOL, FRAME_POOL * ROWS * COLS * 5e-6)}
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -708,7 +746,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="frames", choices=["frames", "templates"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, help="BASELINE.json configs[N-1]: 2 (default, the metric's), 3, 4 or 5")
     args = ap.parse_args()
+    apply_config(args.config)
     if args.impl == "reference":
         run_reference(args)
     else:
