@@ -654,6 +654,7 @@ static int enqueue_match(lm_detector* d, Lane& ln, const Pack::Plan& plan, const
   if (ev_mid) CU(cudaEventRecord(ev_mid, s));
   rp.levels = L; rp.M = M; rp.coarse_T = gc.T; rp.coarse_W = gc.W;
   rp.prune = (d->prune & 2) != 0;
+  rp.mod_order = d->mod_order;
   for (int l = 0; l < L - 1; ++l) {
     const LevelGeom& g = ln.geom[l];
     rp.level[l].lmn = ln.lmn[l].as<uint8_t>();
@@ -1300,10 +1301,6 @@ int lm_set_option(lm_detector* d, const char* key, int value) {
   }
   else if (k == "coarse_grid_limit") {  // process-wide; recorded graphs hold the old grid
     set_coarse_grid_limit(value);
-    for (int i = 0; i < LM_LANES; ++i) d->lane[i].drop_graphs();
-  }
-  else if (k == "rec_prefetch") {  // process-wide A/B switch of the coarse kernel's record staging
-    set_coarse_record_prefetch(value);
     for (int i = 0; i < LM_LANES; ++i) d->lane[i].drop_graphs();
   }
   else if (k == "device_out_cap") d->device_out_cap = (uint32_t)std::max(16, value);

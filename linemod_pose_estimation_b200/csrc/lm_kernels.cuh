@@ -61,6 +61,7 @@ struct RefineParams {
   RefineLevel level[LM_MAX_LEVELS];       // index = pyramid level (only 0 .. L-2 used)
   int levels, M, coarse_T, coarse_W;
   int prune;                              // exact early termination of hopeless candidates (warp-per-candidate path)
+  int mod_order;                          // order of the modalities in the sum: 0 template order, 1 reversed, 2 per frame (mod_bits)
   float threshold[LM_MAX_QUERIES];        // per query of the request
 };
 
@@ -185,7 +186,6 @@ struct CoarseParams {
 };
 void set_programmatic_launch(bool enabled);  // per thread; disabled while launches are recorded into a CUDA graph
 void set_coarse_grid_limit(int blocks);     // process-wide; 0 = no limit
-void set_coarse_record_prefetch(int bulk);  // process-wide A/B: 1 = cp.async.bulk + mbarrier (default), 0 = registers
 int coarse_positions_per_pass();
 int coarse_record_header_words();
 int coarse_record_max_words();

@@ -197,11 +197,9 @@ __device__ __forceinline__ bool rec_alive(const uint32_t (&tot)[4][4], int thr, 
   return __any_sync(kFull, active && best > need);
 }
 
-constexpr int kRecPre = (kRecMaxWords + 31) / 32;     // registers per lane holding a prefetched record (BULK = false)
-
-template <bool BULK>
 __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarseParams P) {
-  __shared__ __align__(16) uint32_t s_rec[8][BULK ? 2 : 1][kRecMaxWords];
+  constexpr bool BULK = true;   // (the register-staged alternative measured 4-6 % slower: profiles/r02_experiments.md)
+  __shared__ __align__(16) uint32_t s_rec[8][2][kRecMaxWords];
   __shared__ __align__(8) unsigned long long s_bar[8][2];
   __shared__ unsigned long long s_bytes;
   __shared__ uint32_t s_done, s_expected;
@@ -244,8 +242,6 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarsePa
     }
     mbar_wait(&s_bar[warp][0], 0u);
     phases = 1u;
-  } else {
-    for (int i = lane; i < rec_words; i += 32) sr[i] = __ldg(recs + (size_t)(cur - cur_frame * n_tiles) * rec_words + i);
   }
   uint32_t nxt = gwarp + n_warps;
   const uint32_t lane_byte = (uint32_t)lane * 16u;
@@ -259,19 +255,10 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarsePa
     const bool has_next = nxt < n_virtual;
     const uint32_t nxt_frame = has_next ? nxt / n_tiles : 0u;
     const uint32_t nxt_tile = nxt - nxt_frame * n_tiles;
-    uint32_t pre[BULK ? 1 : kRecPre];
-    if (BULK) {
-      // the other buffer was last read during the previous tile (every lane is past the __syncwarp above): refill it
-      if (has_next && lane == 0) {
-        mbar_expect_tx(&s_bar[warp][buf ^ 1], rec_bytes);
-        bulk_g2s(s_rec[warp][BULK ? (buf ^ 1) : 0], recs + (size_t)nxt_tile * rec_words, rec_bytes, &s_bar[warp][buf ^ 1]);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < (BULK ? 1 : kRecPre); ++i) {
-        const int idx = lane + 32 * i;
-        pre[i] = (has_next && idx < rec_words) ? __ldg(recs + (size_t)nxt_tile * rec_words + idx) : 0u;
-      }
+    // the other buffer was last read during the previous tile (every lane is past the __syncwarp above): refill it
+    if (has_next && lane == 0) {
+      mbar_expect_tx(&s_bar[warp][buf ^ 1], rec_bytes);
+      bulk_g2s(s_rec[warp][buf ^ 1], recs + (size_t)nxt_tile * rec_words, rec_bytes, &s_bar[warp][buf ^ 1]);
     }
     // the ticket of the tile after next: issued now, read at the end of this tile (the atomic's round trip -- long when
     // thousands of warps draw at once -- overlaps the scoring instead of stalling it)
@@ -354,18 +341,10 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarsePa
     }
     if (!has_next) break;
     __syncwarp();
-    if (BULK) {
-      buf ^= 1;
-      sr = s_rec[warp][BULK ? buf : 0];
-      mbar_wait(&s_bar[warp][buf], (phases >> buf) & 1u);
-      phases ^= 1u << buf;
-    } else {
-#pragma unroll
-      for (int i = 0; i < (BULK ? 1 : kRecPre); ++i) {
-        const int idx = lane + 32 * i;
-        if (idx < rec_words) sr[idx] = pre[i];
-      }
-    }
+    buf ^= 1;
+    sr = s_rec[warp][buf];
+    mbar_wait(&s_bar[warp][buf], (phases >> buf) & 1u);
+    phases ^= 1u << buf;
     cur_frame = nxt_frame;
     nxt = __shfl_sync(kFull, ticket, 0) + 2u * n_warps;
   }
@@ -589,7 +568,7 @@ __device__ __forceinline__ void refine_nib_block(const RefineParams& P, const Co
 // modality: <= 63 features x 4).  The warp first turns the template's features into plane offsets in its slice of shared
 // memory (one lane per feature), then issues eight window loads back to back per step.
 __device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const CoarseTpl* __restrict__ ctpl,
-                                                const Cand* __restrict__ cand, uint32_t n_cands, uint8_t* results,
+                                                const Cand* __restrict__ cand, uint32_t n_cands, const BatchCtl* ctl, uint8_t* results,
                                                 size_t result_stride, uint32_t out_cap, uint32_t* smem) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* s_addr = smem + warp * kRefineMaxFeat;  // nibble index of each feature's patch origin (this warp's slice)
@@ -642,6 +621,7 @@ __device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const Coa
       int begin = 0;
       // exact early termination (see min_passing_score): every 16 features the warp checks whether any position can still pass
       const int need = P.prune ? min_passing_score(threshold, (int)rtp->nf) : 0;
+      const bool mod_reversed = P.M > 1 && (P.mod_order == 2 ? ctl->mod_bits[frame][P.M - 1] < ctl->mod_bits[frame][0] : P.mod_order == 1);
       int remaining = n_all;
       bool hopeless = false;
       // Lanes r and r + 16 share patch row r and split the features between them (even / odd feature of a pair): every
@@ -659,7 +639,12 @@ __device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const Coa
         }
         return (int)__reduce_max_sync(kFull, max(mx & 0xffffu, mx >> 16));
       };
-      for (int m = 0; m < P.M && !hopeless; ++m) {
+      for (int mi = 0; mi < P.M && !hopeless; ++mi) {
+        // like the coarse kernel: the modality the front end found more discriminative on this frame goes first (the sum
+        // does not depend on the order; hopeless candidates are recognised sooner)
+        const int m = mod_reversed ? P.M - 1 - mi : mi;
+        begin = 0;
+        for (int k = 0; k < m; ++k) begin += rtp->cnt[k];
         const uint8_t* lmm = L.lmn + (size_t)frame * L.frame_stride + (size_t)m * 4 * L.plane_stride;
         const int n = rtp->cnt[m];  // <= 63 features, 32 per half: the u8 sums below cannot overflow
         uint32_t acc[4] = {0, 0, 0, 0};
@@ -695,13 +680,12 @@ __device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const Coa
             }
           }
         }
-        begin += n;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {  // [OCV] similarityLocal totals are u16: widen this modality's u8 sums
           tot[j][0] += acc[j] & 0x00ff00ffu;
           tot[j][1] += (acc[j] >> 8) & 0x00ff00ffu;
         }
-        if (need > 0 && !hopeless && m + 1 < P.M) {   // between modalities
+        if (need > 0 && !hopeless && mi + 1 < P.M) {   // between modalities
           const uint32_t none[4] = {0, 0, 0, 0};
           if (best_so_far(none, false) + 4 * remaining < need) hopeless = true;
         }
@@ -770,7 +754,7 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine_nib(const RefinePa
     if (threadIdx.x == 0) ctl->overflow = 1;
   }
   if (n_cands <= 2u * gridDim.x) refine_nib_block(P, ctpl, cand, n_cands, results, result_stride, out_cap, smem);
-  else refine_nib_warp(P, ctpl, cand, n_cands, results, result_stride, out_cap, smem);
+  else refine_nib_warp(P, ctpl, cand, n_cands, ctl, results, result_stride, out_cap, smem);
 }
 
 }  // namespace
@@ -815,20 +799,16 @@ static int resident_ctas(K kernel) {
   return per_sm * sms;
 }
 
-static int g_rec_prefetch_bulk = 1;
-void set_coarse_record_prefetch(int bulk) { g_rec_prefetch_bulk = bulk; }
-
 void launch_similarity_coarse(const CoarseParams& p, int max_frames, cudaStream_t s) {
   if (p.n_tiles <= 0) return;
-  static const int persistent = std::min(resident_ctas(k_similarity_coarse_rec<true>), resident_ctas(k_similarity_coarse_rec<false>));
+  static const int persistent = resident_ctas(k_similarity_coarse_rec);
   const long long blocks = ((long long)p.n_tiles * max_frames + 7) / 8;
   int grid = (int)std::min<long long>(blocks, persistent);
   if (g_coarse_grid_limit > 0) grid = min(grid, g_coarse_grid_limit);
   CoarseParams q = p;
   if (q.dump != nullptr) q.prune = 0;
   cudaLaunchConfig_t cfg = pdl_config(grid, 256, s);
-  if (g_rec_prefetch_bulk) cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec<true>, q);
-  else cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec<false>, q);
+  cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec, q);
 }
 
 void launch_pack_nibbles(const uint8_t* lm_bytes, size_t bytes_stride, uint8_t* lm_nibbles, size_t nib_stride, size_t n_bytes,

@@ -141,13 +141,21 @@ static int run_gpu(const std::string&) {
   // a textured box on a plane, as cv::Mat
   const int rows = 480, cols = 640;
   cv::Mat bgr(rows, cols, CV_8UC3), depth(rows, cols, CV_16UC1), mask(rows, cols, CV_8UC1);
+  const int ox = 200, oy = 150, bw = 130, bh = 110;
   for (int y = 0; y < rows; ++y)
     for (int x = 0; x < cols; ++x) {
-      const bool in = x >= 200 && x < 330 && y >= 150 && y < 260;
-      const int v = in ? (((x / 13 + y / 11) & 1) ? 220 : 40) : 110 + ((x * 7 + y * 3) % 9);
-      for (int c = 0; c < 3; ++c) bgr.data[(size_t)y * bgr.step[0] + 3 * x + c] = (uchar)(in ? (c == 1 ? v : 255 - v) : v);
-      reinterpret_cast<unsigned short*>(depth.data + (size_t)y * depth.step[0])[x] = (unsigned short)(in ? 700 + (x - 200) / 4 : 1000 + x / 16);
-      mask.data[(size_t)y * mask.step[0] + x] = in ? 255 : 0;
+      uchar* p = bgr.data + (size_t)y * bgr.step[0] + 3 * x;
+      unsigned short* d = reinterpret_cast<unsigned short*>(depth.data + (size_t)y * depth.step[0]) + x;
+      p[0] = (uchar)(90 + (x * 40) / cols); p[1] = (uchar)(100 + (y * 30) / rows); p[2] = 110;
+      *d = (unsigned short)(900 + y / 4);
+      mask.data[(size_t)y * mask.step[0] + x] = 0;
+      const int u = x - ox, v = y - oy;
+      if (u >= 0 && u < bw && v >= 0 && v < bh) {   // a textured box with two depth facets on a tilted ground plane
+        mask.data[(size_t)y * mask.step[0] + x] = 255;
+        const int cell = ((u / 12) + (v / 12)) & 1, stripe = (u / 7) % 3;
+        p[0] = (uchar)(cell ? 30 : 10); p[1] = (uchar)(stripe == 0 ? 250 : 225); p[2] = (uchar)(cell ? 20 : 40);
+        *d = (unsigned short)(600 + (u * 3) / 2 + ((v / 20) % 2 ? v : -v) / 2);
+      }
     }
   std::vector<cv::Mat> sources;
   sources.push_back(bgr);

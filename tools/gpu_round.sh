@@ -12,7 +12,7 @@ python __graft_entry__.py smoke > $O/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; ta
 python bench.py --gpus 1 --steps 20 --warmup 5 > $O/bench_driver_$TAG.log 2> $O/bench_driver_$TAG.err; echo "bench (driver args) rc=$?"
 python bench.py > $O/bench_$TAG.log 2> $O/bench_$TAG.err; echo "bench rc=$?"
 python tools/kbench.py > $O/kbench_$TAG.log 2>&1; echo "kbench rc=$?"; cat $O/kbench_$TAG.log
-python tools/kbench.py --workload stress --configs "batch_frames=8,streams=4;batch_frames=8,streams=4,rec_prefetch=0;batch_frames=1,streams=8;batch_frames=16,streams=3" > $O/kbench_stress_$TAG.log 2>&1; echo "kbench stress rc=$?"; cat $O/kbench_stress_$TAG.log
+python tools/kbench.py --workload stress --configs "batch_frames=8,streams=4;batch_frames=8,streams=4,mod_order=0;batch_frames=1,streams=8;batch_frames=16,streams=3" > $O/kbench_stress_$TAG.log 2>&1; echo "kbench stress rc=$?"; cat $O/kbench_stress_$TAG.log
 if [ -z "$QUICK" ]; then
 python bench.py --impl reference --steps 20 --warmup 5 > $O/bench_ref_$TAG.log 2> $O/bench_ref_$TAG.err; echo "reference arm rc=$?"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/launches_$TAG.csv \

@@ -28,7 +28,7 @@ def main():
     from linemod_pose_estimation_b200 import Detector, Mesh, _capi, training
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="batch_frames=8,streams=4;batch_frames=1,streams=8;batch_frames=4,streams=4;"
-                                         "batch_frames=16,streams=3;batch_frames=8,streams=4,rec_prefetch=0;batch_frames=8,streams=4,prune=0")
+                                         "batch_frames=16,streams=3;batch_frames=8,streams=4,mod_order=0;batch_frames=8,streams=4,prune=0")
     ap.add_argument("--frames", type=int, default=1024)
     ap.add_argument("--workload", default="trained", choices=["trained", "stress"],
                     help="trained: bench.py's workload; stress: round 1's (24 extracted + 2 628 random stress templates per class, "
@@ -77,7 +77,7 @@ def main():
     out_p = C.c_void_p()
     offs = (C.c_size_t * (args.pool * n_q + 1))()
     ref = None
-    defaults = {"batch_frames": 8, "prune": 3, "mod_order": 2, "graphs": 1, "rec_prefetch": 1}
+    defaults = {"batch_frames": 8, "prune": 3, "mod_order": 2, "graphs": 1}
     for cfg in args.configs.split(";"):
         opts = dict(defaults)
         opts.update({k: int(v) for k, v in (kv.split("=") for kv in cfg.split(","))})
