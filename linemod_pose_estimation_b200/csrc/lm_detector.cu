@@ -605,9 +605,11 @@ static int get_plan(lm_detector* d, const Query* qs, int n_q, Pack::Plan** out) 
 static const size_t kStatsBytes = 16;
 static size_t result_bytes(const Lane& ln) { return sizeof(ResultHeader) + (size_t)ln.out_cap * sizeof(lm_raw_match); }
 static uint8_t* block_ptr(const Lane& ln, int frame = 0) { return ln.result.as<uint8_t>(frame) + kStatsBytes; }
-static const size_t kFirstChunkRecords = 256;  // records fetched together with the header in one D2H copy
+// Records fetched together with the header in one D2H copy: 256 to start with, then what the lane's recent frames needed
+// (ln.head_records follows the largest survivor count seen, so that a workload with long lists settles on one copy per chunk).
+static size_t head_records(const Lane& ln) { return std::min<size_t>(std::max<uint32_t>(ln.head_records, 256u), ln.out_cap); }
 static size_t head_bytes(const Lane& ln) {
-  return (kStatsBytes + sizeof(ResultHeader) + std::min<size_t>(kFirstChunkRecords, ln.out_cap) * sizeof(lm_raw_match) + 255) & ~(size_t)255;
+  return (kStatsBytes + sizeof(ResultHeader) + head_records(ln) * sizeof(lm_raw_match) + 255) & ~(size_t)255;
 }
 
 static int ensure_match_buffers(lm_detector* d, Lane& ln, uint32_t cand_cap, uint32_t out_cap, int frames) {
@@ -626,7 +628,8 @@ static int ensure_match_buffers(lm_detector* d, Lane& ln, uint32_t cand_cap, uin
     CU(cudaMemset(ln.result.buf.p, 0, ln.result.bytes()));
     ln.drop_graphs();
   }
-  if (ln.stage_out.ensure(std::max(head_bytes(ln) * (size_t)ln.result.frames, kStatsBytes + result_bytes(ln))) != LM_OK) return LM_E_CUDA;
+  // pinned staging for the heads of a whole chunk at the largest head size (the head follows the survivor counts)
+  if (ln.stage_out.ensure((kStatsBytes + result_bytes(ln) + 256) * (size_t)ln.result.frames) != LM_OK) return LM_E_CUDA;
   return LM_OK;
 }
 
@@ -794,8 +797,9 @@ struct FrameRecords {
   uint32_t n_cands = 0;
 };
 static int collect_chunk(Lane& ln, int n, cudaStream_t s, std::vector<FrameRecords>& out) {
-  const size_t first = std::min<size_t>(kFirstChunkRecords, ln.out_cap);
+  const size_t first = head_records(ln);
   const size_t hb = head_bytes(ln);
+  uint32_t longest = 0;
   out.resize((size_t)n);
   ln.work_stats[6] = *reinterpret_cast<const unsigned long long*>(ln.stage_out.as<uint8_t>());
   bool extra = false;
@@ -807,6 +811,7 @@ static int collect_chunk(Lane& ln, int n, cudaStream_t s, std::vector<FrameRecor
     fr.overflow = h.overflow != 0 || h.count > ln.out_cap;
     fr.n_cands = h.n_cands;
     fr.raw.clear();
+    longest = std::max(longest, std::min(h.count, ln.out_cap));
     if (fr.overflow) continue;
     const lm_raw_match* recs = reinterpret_cast<const lm_raw_match*>(host + sizeof(ResultHeader));
     fr.raw.assign(recs, recs + std::min<size_t>(h.count, first));
@@ -818,6 +823,9 @@ static int collect_chunk(Lane& ln, int n, cudaStream_t s, std::vector<FrameRecor
     }
   }
   if (extra) CU(cudaStreamSynchronize(s));
+  // the next chunk's head: room for the longest list just seen plus a quarter, in steps of 256 records; shrinks slowly
+  const uint32_t want = ((longest + longest / 4 + 255u) / 256u) * 256u;
+  ln.head_records = want > ln.head_records ? want : std::max(want, ln.head_records - 256u * (ln.head_records > 256u));
   return LM_OK;
 }
 

@@ -156,6 +156,7 @@ struct Lane {
   DevBuf cand, work, work_order, dump, dbg_recs;
   FrameBuf result;            // per frame: [16 B statistics][ResultHeader][out_cap x lm_raw_match]
   uint32_t cand_cap = 0, out_cap = 0;
+  uint32_t head_records = 256;  // records downloaded together with each frame's header (follows the survivor counts)
   PinBuf stage_in, stage_out;
   // last-call bookkeeping (frame 0 of the last chunk)
   float ms[5] = {0, 0, 0, 0, 0};
