@@ -15,12 +15,16 @@ python tools/kbench.py > $O/kbench_$TAG.log 2>&1; echo "kbench rc=$?"; cat $O/kb
 python tools/kbench.py --workload stress --configs "batch_frames=8,streams=4;batch_frames=8,streams=4,mod_order=0;batch_frames=1,streams=8;batch_frames=16,streams=3" > $O/kbench_stress_$TAG.log 2>&1; echo "kbench stress rc=$?"; cat $O/kbench_stress_$TAG.log
 if [ -z "$QUICK" ]; then
 python bench.py --impl reference --steps 20 --warmup 5 > $O/bench_ref_$TAG.log 2> $O/bench_ref_$TAG.err; echo "reference arm rc=$?"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/launches_$TAG.csv \
+# the profiled runs load the trained template set from a cache written by a plain run: no trainer launches in the lists
+export LM_BENCH_TEMPLATE_CACHE=/tmp/lm_bench_templates.lmb2
+python bench.py --steps 64 --warmup 8 --no-cpu-baseline > $O/bench_cache_$TAG.log 2>&1; echo "cache-writing run rc=$?"
+ncu --metrics gpu__time_duration.sum --clock-control none -s 1500 -c 500 --csv --log-file $O/launches_$TAG.csv \
     python bench.py --steps 64 --warmup 8 --no-cpu-baseline > $O/ncu_launch_$TAG.log 2>&1; echo "ncu launch list rc=$?"
 for K in k_similarity_coarse_rec k_cg_fused k_dn_fused k_spread_all k_pyrdown_fast k_refine_nib; do
 ncu --set full --clock-control none --import-source on -k regex:$K -s 12 -c 2 -f -o $O/${K}_$TAG \
     python bench.py --steps 64 --warmup 8 --no-cpu-baseline > $O/ncu_full_${K}_$TAG.log 2>&1; echo "ncu full $K rc=$?"
 done
+unset LM_BENCH_TEMPLATE_CACHE
 python tools/trainbench.py > $O/trainbench_$TAG.log 2>&1; echo "trainbench rc=$?"; cat $O/trainbench_$TAG.log
 fi
 tail -c 1500 $O/bench_driver_$TAG.log; echo; tail -c 3000 $O/bench_$TAG.log
