@@ -1445,7 +1445,16 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
   if (set_device(d) != LM_OK) return LM_E_CUDA;
   const int F = std::max(1, std::min(d->batch_frames, LM_MAX_BATCH));
   const int NL = std::max(1, std::min(d->batch_lanes, LM_LANES));
-  const int n_chunks = (n_frames + F - 1) / F;
+  // Chunk boundaries.  The first chunks of a call ramp up (2, 2, 4, ... frames): the GPU starts on the call's first frames
+  // after two frames' worth of host->device copy instead of a whole chunk's, which is the bubble between two calls.
+  std::vector<int> chunk_first;
+  for (int at = 0, step = std::min(F, 2), k = 0; at < n_frames; ++k) {
+    chunk_first.push_back(at);
+    at += std::min(step, n_frames - at);
+    if (k >= 1 && step < F) step = std::min(F, step * 2);
+  }
+  chunk_first.push_back(n_frames);
+  const int n_chunks = (int)chunk_first.size() - 1;
   // per (frame, query) result lists, concatenated at the end (chunks finish in order, but a frame may be redone)
   std::vector<std::vector<lm_match_rec> > lists((size_t)n_frames * n_q);
   struct Pending { int first = -1, n = 0; const Pack::Plan* plan = nullptr; } pending[LM_LANES];
@@ -1485,7 +1494,7 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
   for (int c = 0; c < n_chunks; ++c) {
     const int li = c % NL;
     Lane& ln = d->lane[li];
-    const int first = c * F, n = std::min(F, n_frames - first);
+    const int first = chunk_first[(size_t)c], n = chunk_first[(size_t)c + 1] - first;
     double t0 = prof ? now() : 0;
     // the lane's previous chunk must be done before its source slots and pinned staging are overwritten
     if (pending[li].first >= 0) { int rc = finish(li); if (rc != LM_OK) return rc; }
