@@ -589,7 +589,17 @@ def run_ours(args):
     dt = max_over_ranks(timed_e2e(R_e2e))
     s_per_step_e2e = dt / (K * R_e2e)
     e2e_value = evals_per_frame * frames_per_step / s_per_step_e2e
-    launches_e2e = det.last_timings()["launches"] * ((K + BATCH_FRAMES - 1) // BATCH_FRAMES) * R_e2e
+    def chunks_of_call(n):   # lm_match_batch*: the first chunks of a call ramp up (2, 2, 4, ...) to the chunk size
+        k, at, step = 0, 0, min(BATCH_FRAMES, 2)
+        while at < n:
+            at += min(step, n - at)
+            if k >= 1 and step < BATCH_FRAMES:
+                step = min(BATCH_FRAMES, step * 2)
+            k += 1
+        return k
+    total_frames = K * R_e2e
+    n_chunks_e2e = (total_frames // E2E_CALL) * chunks_of_call(E2E_CALL) + chunks_of_call(total_frames % E2E_CALL)
+    launches_e2e = det.last_timings()["launches"] * n_chunks_e2e
     matches_per_frame = n_matches / max(1, K * R_e2e)
 
     # blocking single-frame calls (lm_match_multi, what /root/reference/src/rgbdDetector.cpp:33 makes): latency-oriented

@@ -1315,6 +1315,7 @@ int lm_set_option(lm_detector* d, const char* key, int value) {
     set_coarse_ctas(value);
     for (int i = 0; i < LM_LANES; ++i) d->lane[i].drop_graphs();
   }
+  else if (k == "finalize_threads") d->finalize_threads = std::max(0, std::min(value, 16));
   else if (k == "device_out_cap") d->device_out_cap = (uint32_t)std::max(16, value);
   else if (k == "cand_per_frame") d->cand_per_frame = (uint32_t)std::max(1024, value);
   else return lm_fail(LM_E_INVALID, "unknown option '%s'", key);
@@ -1459,6 +1460,12 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
   std::vector<std::vector<lm_match_rec> > lists((size_t)n_frames * n_q);
   struct Pending { int first = -1, n = 0; const Pack::Plan* plan = nullptr; } pending[LM_LANES];
   std::vector<FrameRecords> got;
+  const bool use_pool = !raw_frames && d->finalize_threads > 0 && n_frames > 1;
+  if (use_pool) d->finalizers.start(std::min(d->finalize_threads, 16));
+  struct PoolGuard {  // every job writes into `lists`: none may outlive this call, whichever way it returns
+    FinalizePool* p;
+    ~PoolGuard() { if (p) p->wait_all(); }
+  } pool_guard = {use_pool ? &d->finalizers : nullptr};
   auto finish = [&](int li) -> int {
     Lane& ln = d->lane[li];
     const Pending pd = pending[li];
@@ -1472,7 +1479,13 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
       cands += got[(size_t)f].n_cands; survivors += got[(size_t)f].raw.size();
       if (got[(size_t)f].overflow) { redo.push_back(f); continue; }
       if (raw_frames) (*raw_frames)[(size_t)(pd.first + f)].swap(got[(size_t)f].raw);
-      else finalize_queries(d, ln, got[(size_t)f].raw, n_q, &lists[(size_t)(pd.first + f) * n_q]);
+      else if (use_pool) {  // ordered on a finalizer thread while this thread goes on feeding the device
+        std::shared_ptr<std::vector<lm_raw_match> > raw = std::make_shared<std::vector<lm_raw_match> >();
+        raw->swap(got[(size_t)f].raw);
+        std::vector<lm_match_rec>* dst = &lists[(size_t)(pd.first + f) * n_q];
+        const int levels = d->model.levels();
+        d->finalizers.submit([raw, dst, levels, n_q]() { lm_internal_finalize(levels, *raw, n_q, dst); });
+      } else finalize_queries(d, ln, got[(size_t)f].raw, n_q, &lists[(size_t)(pd.first + f) * n_q]);
     }
     // work accounting of the chunk (lm_last_work reads lane 0): B_coarse of all its frames, candidates, evals, frames
     ln.work_stats[1] = pd.plan->coarse_bytes * (uint64_t)pd.n;
@@ -1521,6 +1534,7 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
     fprintf(stderr, "[lm host profile] per frame us: finish %.1f upload %.1f enqueue %.1f\n", t_fin / n_frames, t_up / n_frames,
             t_enq / n_frames);
   if (raw_frames) return LM_OK;
+  if (use_pool) d->finalizers.wait_all();
   std::vector<lm_match_rec> all;
   for (size_t i = 0; i < lists.size(); ++i) {
     all.insert(all.end(), lists[i].begin(), lists[i].end());
@@ -1556,7 +1570,7 @@ lm_detector* lm_internal_clone(const lm_detector* src) {
   d->luts_dirty = true;
   d->device_out_cap = src->device_out_cap; d->cand_per_frame = src->cand_per_frame;
   d->prune = src->prune; d->graphs = src->graphs; d->mod_order = src->mod_order;
-  d->batch_frames = src->batch_frames; d->batch_lanes = src->batch_lanes;
+  d->batch_frames = src->batch_frames; d->batch_lanes = src->batch_lanes; d->finalize_threads = src->finalize_threads;
   refresh_class_cache(d);
   return d;
 }

@@ -8,8 +8,13 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include "lm_host.hpp"
 #include "lm_kernels.cuh"
@@ -255,8 +260,55 @@ struct TrainWs {
   }
 };
 
+// Host threads that turn downloaded survivor records into the reference's ordered match lists (two std::sort passes per
+// frame and query) while the calling thread keeps the copy engine and the launch queue fed.  Started on first use.
+struct FinalizePool {
+  std::vector<std::thread> threads;
+  std::mutex mu;
+  std::condition_variable wake, idle;
+  std::deque<std::function<void()> > jobs;
+  int busy = 0;
+  bool stop = false;
+  void start(int n) {
+    while ((int)threads.size() < n)
+      threads.emplace_back([this]() {
+        for (;;) {
+          std::function<void()> job;
+          {
+            std::unique_lock<std::mutex> lk(mu);
+            wake.wait(lk, [this]() { return stop || !jobs.empty(); });
+            if (stop && jobs.empty()) return;
+            job.swap(jobs.front());
+            jobs.pop_front();
+            ++busy;
+          }
+          job();
+          {
+            std::lock_guard<std::mutex> lk(mu);
+            if (--busy == 0 && jobs.empty()) idle.notify_all();
+          }
+        }
+      });
+  }
+  void submit(std::function<void()> job) {
+    { std::lock_guard<std::mutex> lk(mu); jobs.push_back(std::move(job)); }
+    wake.notify_one();
+  }
+  void wait_all() {
+    std::unique_lock<std::mutex> lk(mu);
+    idle.wait(lk, [this]() { return busy == 0 && jobs.empty(); });
+  }
+  ~FinalizePool() {
+    { std::lock_guard<std::mutex> lk(mu); stop = true; }
+    wake.notify_all();
+    for (auto& t : threads) t.join();
+  }
+};
+
 struct lm_detector {
   HostModel model;
+  FinalizePool finalizers;
+  int finalize_threads = 2;  // host threads ordering the match lists of batched calls (0: on the calling thread)
   TrainWs train;
   int device = -1;
   bool cuda_ready = false;
