@@ -1311,10 +1311,6 @@ int lm_set_option(lm_detector* d, const char* key, int value) {
     set_coarse_grid_limit(value);
     for (int i = 0; i < LM_LANES; ++i) d->lane[i].drop_graphs();
   }
-  else if (k == "coarse_ctas") {  // process-wide experiment switch
-    set_coarse_ctas(value);
-    for (int i = 0; i < LM_LANES; ++i) d->lane[i].drop_graphs();
-  }
   else if (k == "finalize_threads") d->finalize_threads = std::max(0, std::min(value, 16));
   else if (k == "device_out_cap") d->device_out_cap = (uint32_t)std::max(16, value);
   else if (k == "cand_per_frame") d->cand_per_frame = (uint32_t)std::max(1024, value);

@@ -186,7 +186,6 @@ struct CoarseParams {
 };
 void set_programmatic_launch(bool enabled);  // per thread; disabled while launches are recorded into a CUDA graph
 void set_coarse_grid_limit(int blocks);     // process-wide; 0 = no limit
-void set_coarse_ctas(int per_sm);           // process-wide experiment switch: register budget for 2 (default) or 3 CTAs per SM
 int coarse_positions_per_pass();
 int coarse_record_header_words();
 int coarse_record_max_words();

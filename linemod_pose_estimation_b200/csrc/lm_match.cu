@@ -197,8 +197,8 @@ __device__ __forceinline__ bool rec_alive(const uint32_t (&tot)[4][4], int thr, 
   return __any_sync(kFull, active && best > need);
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB) k_similarity_coarse_rec(const CoarseParams P) {
+// (2 CTAs per SM: a 3-CTA register budget -- 80 registers -- measured no faster, profiles/r02_experiments.md)
+__global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarseParams P) {
   constexpr bool BULK = true;   // (the register-staged alternative measured 4-6 % slower: profiles/r02_experiments.md)
   __shared__ __align__(16) uint32_t s_rec[8][2][kRecMaxWords];
   __shared__ __align__(8) unsigned long long s_bar[8][2];
@@ -799,21 +799,16 @@ static int resident_ctas(K kernel) {
   return per_sm * sms;
 }
 
-static int g_coarse_ctas = 2;
-void set_coarse_ctas(int n) { g_coarse_ctas = n; }
-
 void launch_similarity_coarse(const CoarseParams& p, int max_frames, cudaStream_t s) {
   if (p.n_tiles <= 0) return;
-  static const int persistent2 = resident_ctas(k_similarity_coarse_rec<2>), persistent3 = resident_ctas(k_similarity_coarse_rec<3>);
-  const int persistent = g_coarse_ctas == 3 ? persistent3 : persistent2;
+  static const int persistent = resident_ctas(k_similarity_coarse_rec);
   const long long blocks = ((long long)p.n_tiles * max_frames + 7) / 8;
   int grid = (int)std::min<long long>(blocks, persistent);
   if (g_coarse_grid_limit > 0) grid = min(grid, g_coarse_grid_limit);
   CoarseParams q = p;
   if (q.dump != nullptr) q.prune = 0;
   cudaLaunchConfig_t cfg = pdl_config(grid, 256, s);
-  if (g_coarse_ctas == 3) cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec<3>, q);
-  else cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec<2>, q);
+  cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec, q);
 }
 
 void launch_pack_nibbles(const uint8_t* lm_bytes, size_t bytes_stride, uint8_t* lm_nibbles, size_t nib_stride, size_t n_bytes,
