@@ -486,6 +486,31 @@ def test_sharded_stream_single_rank():
     assert total > 0
 
 
+def test_sharded_stream_large_chunks_forced_fallback_and_defaults():
+    """(i) the per-frame fallback of frames whose survivors outgrow the exchange slot runs only after the stream
+    has drained (it uses lane 0, which later chunks are still using while their predecessors finish) -- large chunks, several
+    chunks in flight, most frames forced into the fallback; (ii) the default capacity (4 096) works on a fresh detector:
+    the library's device record blocks follow the exchange capacity."""
+    from linemod_pose_estimation_b200.sharding import ShardedDetector
+    orc, det, views = _pair(n_views=8, n_random=40, seed=89, classes=("cpu_binary", "memoryChip2"))
+    queries = [(88.0, ["memoryChip2"]), (60.0, [])]
+    frames = [list(synth.compose_scene(5200 + i, views[i % 4:i % 4 + 4])[:2]) for i in range(40)]
+    want = [det.match_multi(f, queries) for f in frames]
+    assert max(len(w[1]) for w in want) > 64            # the loose query outgrows a 64-record slot
+    sd = ShardedDetector(det, capacity=64)
+    got = sd.match_stream(frames, queries, chunk=16, lanes=4)
+    for g, w in zip(got, want):
+        for a, b in zip(g, w):
+            common.assert_matches_equal(a, b, "forced fallback")
+    fresh = Detector()
+    common.copy_templates(orc, fresh)
+    sd2 = ShardedDetector(fresh)                        # defaults
+    got = sd2.match_stream(frames[:9], queries)
+    for g, w in zip(got, want[:9]):
+        for a, b in zip(g, w):
+            common.assert_matches_equal(a, b, "defaults")
+
+
 def test_chunk_result_blocks_are_one_region():
     """lm_match_device_stream runs a chunk of device-resident frames as ONE launch set on a lane (no copies: the kernels
     read the caller's buffers through the frame table); lm_device_result_region: the chunk's record blocks lie frame stride
