@@ -11,7 +11,7 @@ nvidia-smi --query-gpu=index,name --format=csv > $O/gpus_$TAG.txt 2>&1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
 $TR bench.py --gpus $N --steps 256 --warmup 32 > $O/bench_n${N}_frames_$TAG.log 2> $O/bench_n${N}_frames_$TAG.err; echo "bench frames N=$N rc=$?"
 $TR bench.py --gpus $N --steps 256 --warmup 32 --mode templates > $O/bench_n${N}_templates_$TAG.log 2> $O/bench_n${N}_templates_$TAG.err; echo "bench templates N=$N rc=$?"
-python tools/groupbench.py > $O/groupbench_n${N}_$TAG.log 2> $O/groupbench_n${N}_$TAG.err; echo "groupbench rc=$?"; cat $O/groupbench_n${N}_$TAG.log
+python tools/groupbench.py --frames 2048 --reps 4 > $O/groupbench_n${N}_$TAG.log 2> $O/groupbench_n${N}_$TAG.err; echo "groupbench rc=$?"; cat $O/groupbench_n${N}_$TAG.log
 if [ -n "$FULL" ]; then
 $TR bench.py --gpus $N --steps 128 --warmup 32 --config 4 --mode templates > $O/bench_n${N}_config4_templates_$TAG.log 2> $O/bench_n${N}_config4_templates_$TAG.err; echo "config 4 templates N=$N rc=$?"
 $TR bench.py --gpus $N --steps 128 --warmup 32 --config 4 > $O/bench_n${N}_config4_frames_$TAG.log 2> $O/bench_n${N}_config4_frames_$TAG.err; echo "config 4 frames N=$N rc=$?"
