@@ -89,7 +89,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 template <int Q>
 __device__ __forceinline__ void rec_window(const uint8_t* __restrict__ lmn, uint32_t v, uint32_t lane_byte,
                                            uint32_t (&n)[4]) {
-  const uint8_t* p = lmn + (v & ~15u) + lane_byte;
+  const uint8_t* p = lmn + (v & ~15u);   // lmn already points at this lane's first chunk (plane base + 16 * lane)
   const uint32_t sh = v << 2;  // funnel shifts use the low five bits: 4 * (v & 7)
   uint32_t w[8];
   const uint4 c = ldg128(p);
@@ -110,7 +110,7 @@ __device__ __forceinline__ void rec_window(const uint8_t* __restrict__ lmn, uint
 // The five words w[Q .. Q+4] a window of class Q needs (the rest of the second vector load is dropped at once).
 template <int Q>
 __device__ __forceinline__ void rec_load(const uint8_t* __restrict__ lmn, uint32_t v, uint32_t lane_byte, uint32_t (&x)[5]) {
-  const uint8_t* p = lmn + (v & ~15u) + lane_byte;
+  const uint8_t* p = lmn + (v & ~15u);   // lmn already points at this lane's first chunk (plane base + 16 * lane)
   const uint4 c = ldg128(p);
   if (Q == 0) {
     x[0] = c.x; x[1] = c.y; x[2] = c.z; x[3] = c.w; x[4] = ldg32(p + 16);
@@ -250,11 +250,21 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarsePa
   const bool do_prune = (prune & 1) != 0;
   const uint32_t zero = n_tiles >> 31;  // n_tiles > 0: zero, but only at run time (see rec_group)
   unsigned long long bytes = 0;  // (feature, position) pairs actually gathered by this warp
+  uint32_t thr_key = 0xffffffffu;
+  int thr_val = 0;
+  // frame of a virtual tile without a division: v / n_tiles = umulhi(v, floor(2^32 / n_tiles)) or one more
+  const uint32_t inv_tiles = (uint32_t)(0x100000000ull / n_tiles);
+  auto frame_of = [&](uint32_t v) -> uint32_t {
+    if (n_tiles == 1u) return v;   // 2^32 / 1 does not fit the multiplier
+    uint32_t q = __umulhi(v, inv_tiles);
+    if (v - q * n_tiles >= n_tiles) ++q;
+    return q;
+  };
   for (;;) {
     __syncwarp();
     // prefetch the next tile's record into registers and draw the tile after it
     const bool has_next = nxt < n_virtual;
-    const uint32_t nxt_frame = has_next ? nxt / n_tiles : 0u;
+    const uint32_t nxt_frame = has_next ? frame_of(nxt) : 0u;
     const uint32_t nxt_tile = nxt - nxt_frame * n_tiles;
     // the other buffer was last read during the previous tile (every lane is past the __syncwarp above): refill it
     if (has_next && lane == 0) {
@@ -266,16 +276,21 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarsePa
     uint32_t ticket = 0;
     if (has_next && lane == 0) ticket = atomicAdd(&ctl->next_tile, 1u);
 
-    const uint8_t* __restrict__ lmn = P.lmn + (size_t)cur_frame * P.lmn_stride;
+    const uint8_t* __restrict__ lmn = P.lmn + (size_t)cur_frame * P.lmn_stride + lane_byte;  // this lane's chunk of every window
     // bit 8 of `prune`: sum the modalities in reverse order; bit 9: decide per frame from the front end's counters
     const bool mod_reversed = (prune & 0x200) ? (ctl->mod_bits[cur_frame][M - 1] < ctl->mod_bits[cur_frame][0]) : (prune & 0x100) != 0;
     const uint32_t item = sr[0], tg = sr[1], nfq = sr[2], order = sr[6];
     const int n_feat = (int)sr[3], j0 = (int)sr[4], rem = (int)sr[5];
     const bool active = first < rem;
-    // [OCV] matchClass: raw_threshold = (int)(2*nf + (threshold / 100.f) * (2*nf) + 0.5f), same f32 roundings
-    const float threshold = P.thr.v[nfq >> 28];
-    const float two_nf = (float)(2 * (int)(nfq & 0x0fffffffu));
-    const int thr = __float2int_rz(__fadd_rn(__fadd_rn(two_nf, __fmul_rn(__fdiv_rn(threshold, 100.f), two_nf)), 0.5f));
+    // [OCV] matchClass: raw_threshold = (int)(2*nf + (threshold / 100.f) * (2*nf) + 0.5f), same f32 roundings; consecutive
+    // tiles nearly always share the query and the feature count, so the division is redone only when they change
+    if (nfq != thr_key) {
+      const float threshold = P.thr.v[nfq >> 28];
+      const float two_nf = (float)(2 * (int)(nfq & 0x0fffffffu));
+      thr_val = __float2int_rz(__fadd_rn(__fadd_rn(two_nf, __fmul_rn(__fdiv_rn(threshold, 100.f), two_nf)), 0.5f));
+      thr_key = nfq;
+    }
+    const int thr = thr_val;
     uint32_t tot[4][4];  // u16 x 2 per register: [k][r], r = (i & 1) * 2 + ((i >> 1) & 1) for position 8k + i
 #pragma unroll
     for (int k = 0; k < 4; ++k) tot[k][0] = tot[k][1] = tot[k][2] = tot[k][3] = 0;
@@ -291,15 +306,15 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarsePa
       const uint32_t c4 = sr[8 + m];  // 4 class sizes, one word
       const int n0 = c4 & 255, n1 = (c4 >> 8) & 255, n2 = (c4 >> 16) & 255, n3 = c4 >> 24;
       if (active) {
-        rec_group<0>(lmn, fw, n0, lane_byte, acc_e, acc_o, zero);
-        rec_group<1>(lmn, fw + n0, n1, lane_byte, acc_e, acc_o, zero);
+        rec_group<0>(lmn, fw, n0, 0u, acc_e, acc_o, zero);
+        rec_group<1>(lmn, fw + n0, n1, 0u, acc_e, acc_o, zero);
       }
       fw += n0 + n1; done += n0 + n1;
       rec_widen(acc_e, acc_o, tot);
       if (do_prune && !rec_alive(tot, thr, n_feat - done, active)) { alive = false; break; }
       if (active) {
-        rec_group<2>(lmn, fw, n2, lane_byte, acc_e, acc_o, zero);
-        rec_group<3>(lmn, fw + n2, n3, lane_byte, acc_e, acc_o, zero);
+        rec_group<2>(lmn, fw, n2, 0u, acc_e, acc_o, zero);
+        rec_group<3>(lmn, fw + n2, n3, 0u, acc_e, acc_o, zero);
       }
       done += n2 + n3;
       rec_widen(acc_e, acc_o, tot);
