@@ -64,11 +64,10 @@ def apply_config(n):
     CONFIG_ID = n
     if n == 2:
         return
-    if n == 3:     # 1280x960 (1280x1024 is not divisible by T = 5), looser threshold: refinement-heavy
-        ROWS, COLS = 960, 1280
-        CLASSES = (("memoryChip2", 88.0, (0.25, 0.45, 0.04)), ("cpu_binary", 88.0, (0.15, 0.30, 0.03)))
+    if n == 3:     # 1280x960 (1280x1024 is not divisible by T = 5): four times the positions, four times the candidates to refine
+        ROWS, COLS = 960, 1280                     # (at thr 88 these parts give 118 000 matches per frame: the list is the work)
         INSTANCES_PER_CLASS = 6
-        CONFIG_NAME = "configs[2]: 1280x960 Ensenso-resolution frames, dual-modality detector, thr 88, refinement-heavy"
+        CONFIG_NAME = "configs[2]: 1280x960 Ensenso-resolution frames, dual-modality detector (thr 92 / 94), refinement-heavy"
     elif n == 4:   # ~20 000 templates: every non-edge-on view of both parts + every 3rd view of boxNew's sphere
         CLASSES = (("memoryChip2", 92.0, (0.25, 0.45, 0.04)), ("cpu_binary", 94.0, (0.15, 0.30, 0.03)), ("boxNew", 92.0, (0.5, 1.0, 0.1)))
         STRIDE_OF = {"memoryChip2": 1, "cpu_binary": 1, "boxNew": 3}
