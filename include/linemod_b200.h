@@ -408,7 +408,7 @@ int lm_load_normal_lut_file(lm_detector* det, const char* path);
 #define LM_STAGE_MAGNITUDE 4 /* f32 [rows][cols], ColorGradient only             (quantizedOrientations) */
 #define LM_STAGE_QUANT_RAW 5 /* u8 [rows][cols], before mask */
 #define LM_STAGE_LINEAR_PACKED 6 /* u8 [8][plane_stride / 2]: the coarsest level's LM_STAGE_LINEAR packed two positions
-                                    per byte (position p = nibble p), the layout k_similarity_coarse_nib reads */
+                                    per byte (position p = nibble p), the layout the matching kernels read */
 /* Copies a stage of the LAST lm_match / lm_build_front call to host memory. dst NULL = size query. Returns bytes. */
 long lm_debug_fetch(lm_detector* det, int stage, int level, int modality, void* dst);
 /* Front end only (quantise -> spread -> response -> linearize) without matching. */

@@ -3,7 +3,7 @@
 //
 // Reference surface mirrored: cv::linemod::Detector as driven by /root/reference/src/rgbdDetector.cpp:31-34 (match),
 // src/renderer.cpp:179-185,308 (construction, addTemplate), src/rgbdDetector.cpp:1668-1680 / src/renderer.cpp:56-70
-// (persistence).  Everything that touches pixels runs in the CUDA kernels of lm_frontend.cu / lm_match.cu; the host
+// (persistence).  Everything that touches pixels runs in the CUDA kernels of lm_frontend_fused.cu / lm_match.cu; the host
 // only stages buffers, packs template records and orders the (few) surviving matches.
 #include "lm_detector_internal.hpp"
 

@@ -1,15 +1,16 @@
 // lm_match.cu -- the template-matching kernels of the LINEMOD hot path (sm_100a).
 //
-// k_similarity_coarse restates [OCV] similarity + addSimilarities + the coarse scan of Detector::matchClass
-// (OpenCV 2.4.x objdetect/linemod.cpp, reached from /root/reference/src/rgbdDetector.cpp:33); k_refine restates
-// [OCV] similarityLocal and matchClass's refinement loop.  Spec: SURVEY.md App. A.7-A.9, quirks App. D.
+// k_similarity_coarse_rec restates [OCV] similarity + addSimilarities + the coarse scan of Detector::matchClass
+// (OpenCV 2.4.x objdetect/linemod.cpp, reached from /root/reference/src/rgbdDetector.cpp:33); k_refine_nib restates
+// [OCV] similarityLocal and matchClass's refinement loop.  Spec: SURVEY.md App. A.7-A.9, quirks App. D.  Both take a
+// CHUNK of frames per launch (frame table + per-frame strides, lm_kernels.cuh); k_begin_chunk installs the table.
 //
-// The work is a byte gather-accumulate: S_t[j] = sum_f LM[a_f + j].  The linear memories of a frame (0.6 MB per
-// modality at 640x480) are shared by every template and stay L2/L1 resident; HBM only sees the template records.
-// Hence no tensor cores: the binding resources are L2->SM bandwidth and LSU issue, which the kernel feeds with
-// 128-bit loads.  Responses are <= 4 and a template has <= 63 features per modality, so four byte lanes packed in
-// a 32-bit register never carry into each other: plain integer adds are bit-identical to the reference's
-// _mm_add_epi8 (and to __vaddus4) at a quarter of the instruction count.
+// The work is a byte gather-accumulate: S_t[j] = sum_f LM[a_f + j].  The linear memories of a frame (nibble-packed,
+// 0.3 MB per modality at the coarsest level of 640x480) are shared by every template and stay L2/L1 resident; HBM only
+// sees the template records.  Hence no tensor cores: the binding resources are instruction issue, L1 wavefronts and load
+// latency.  Responses are <= 4 and a template has <= 63 features per modality, so byte lanes packed in a 32-bit
+// register never carry into each other: plain integer adds are bit-identical to the reference's _mm_add_epi8 (and to
+// __vaddus4) at a quarter of the instruction count.
 #include <string.h>
 
 #include <algorithm>

@@ -2,7 +2,7 @@
 // (Devillard-style selection network, 99 exchanges.)  Correctness does not rest on recall: by the zero-one principle
 // a min/max network selects the median of every input iff it does so for every 0/1 input, and
 // tests/test_median_network.py checks all 2^25 of those against this very list (parsed from this file).
-// Used by k_dn_median (lm_frontend.cu) for [OCV] medianBlur(dst, dst, 5) inside quantizedNormals.
+// Used by k_dn_fused (lm_frontend_fused.cu) for [OCV] medianBlur(dst, dst, 5) inside quantizedNormals.
 #pragma once
 #define LM_MEDIAN25_NET(X) \
   X(0, 1) X(3, 4) X(2, 4) X(2, 3) X(6, 7) X(5, 7) X(5, 6) X(9, 10) X(8, 10) X(8, 9) X(12, 13) X(11, 13) \

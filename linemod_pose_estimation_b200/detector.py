@@ -236,7 +236,7 @@ class Detector:
         return rec.value, cap.value
 
     def match_batch(self, frames, threshold, class_ids=()):
-        """frames: list of per-frame source lists.  -> list of match arrays (pipelined over two streams)."""
+        """frames: list of per-frame source lists.  -> list of match arrays (chunks of "batch_frames" frames per launch set, chunks pipelined)."""
         flat = [s for f in frames for s in f]
         arr, keep = image_array(flat)
         ids, n_ids = self._ids(class_ids)
@@ -249,7 +249,7 @@ class Detector:
 
     def match_batch_multi(self, frames, queries):
         """frames: list of per-frame source lists; queries: [(threshold, [class ids])].
-        -> list (per frame) of lists (per query) of match arrays; frames are pipelined over two streams."""
+        -> list (per frame) of lists (per query) of match arrays; chunks of frames per launch set, chunks pipelined."""
         flat = [s for f in frames for s in f]
         arr, keep = image_array(flat)
         qarr, qkeep = _capi.query_array(queries)
