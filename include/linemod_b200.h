@@ -346,6 +346,10 @@ typedef struct lm_group lm_group;
 #define LM_GROUP_FRAMES 0
 #define LM_GROUP_TEMPLATES 1
 int lm_group_create(const lm_detector* prototype, const int* devices, int n_devices, int mode, lm_group** out);
+/* Both at once (a 2-D grid): the devices form n_devices / template_shards sets of `template_shards` template shards
+ * (device i = shard i % S of set i / S); launch sets of frames are dealt out to the sets, the devices of a set see the set's
+ * frames and their survivors are merged.  template_shards = 1 is LM_GROUP_FRAMES, = n_devices is LM_GROUP_TEMPLATES. */
+int lm_group_create_grid(const lm_detector* prototype, const int* devices, int n_devices, int template_shards, lm_group** out);
 void lm_group_destroy(lm_group* group);
 int lm_group_size(const lm_group* group);
 int lm_group_mode(const lm_group* group);

@@ -532,6 +532,10 @@ class DetectorGroup {
   DetectorGroup(const Detector& prototype, const std::vector<int>& devices, Mode mode = Frames) : g_(nullptr), proto_(prototype.handle()) {
     detail::check(lm_group_create(prototype.handle(), devices.data(), (int)devices.size(), (int)mode, &g_));
   }
+  // the 2-D grid: devices.size() / template_shards sets of `template_shards` template shards, frames dealt out to the sets
+  DetectorGroup(const Detector& prototype, const std::vector<int>& devices, int template_shards) : g_(nullptr), proto_(prototype.handle()) {
+    detail::check(lm_group_create_grid(prototype.handle(), devices.data(), (int)devices.size(), template_shards, &g_));
+  }
   ~DetectorGroup() { lm_group_destroy(g_); }
   DetectorGroup(const DetectorGroup&) = delete;
   DetectorGroup& operator=(const DetectorGroup&) = delete;

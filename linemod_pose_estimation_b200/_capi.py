@@ -76,7 +76,7 @@ EXPORTS = [
     "lm_mesh_create", "lm_mesh_load_stl", "lm_mesh_num_triangles", "lm_mesh_get_triangles", "lm_mesh_destroy", "lm_view_count", "lm_view_params",
     "lm_view_pose", "lm_render_views", "lm_add_templates_batch", "lm_train_views", "lm_depth_diff_batch",
     "lm_write_renderer_params", "lm_read_renderer_params", "lm_free_poses",
-    "lm_group_create", "lm_group_destroy", "lm_group_size", "lm_group_mode", "lm_group_member", "lm_group_set_option",
+    "lm_group_create", "lm_group_create_grid", "lm_group_destroy", "lm_group_size", "lm_group_mode", "lm_group_member", "lm_group_set_option",
     "lm_group_match_batch_multi", "lm_group_match",
     "lm_cluster_matches", "lm_free_clusters", "lm_debug_coarse_map", "lm_debug_presort", "lm_last_timings", "lm_last_work", "lm_set_option",
 ]
@@ -173,6 +173,7 @@ def lib():
     L.lm_free_poses.argtypes = [vp]
     L.lm_free_poses.restype = None
     L.lm_group_create.argtypes = [vp, C.POINTER(C.c_int), ci, ci, C.POINTER(vp)]
+    L.lm_group_create_grid.argtypes = [vp, C.POINTER(C.c_int), ci, ci, C.POINTER(vp)]
     L.lm_group_destroy.argtypes = [vp]
     L.lm_group_destroy.restype = None
     L.lm_group_size.argtypes = [vp]

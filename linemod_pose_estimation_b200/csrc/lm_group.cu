@@ -13,6 +13,11 @@
 //                       (std::unique acts across templates, App. D-7).  For the single-frame latency case and for template
 //                       sets that outgrow one device.
 //
+//   grid (lm_group_create_grid)  both at once: the devices form N / S sets of S template shards; frames are dealt out to the
+//                       sets, the S devices of a set see the set's frames and their survivors are merged.  S = 1 is the
+//                       frames mode, S = N the templates mode; in between, a template set too large (or a latency target
+//                       too tight) for one GPU still scales its frame rate with the number of sets.
+//
 // In one process the host is both the source of the frames and the consumer of the matches, so neither mode has a
 // device-to-device exchange step: every device copies in over its own link and its (few hundred bytes of) survivors go
 // straight back to the host thread that merges them.  The NCCL exchange (frame broadcast + survivor all-gather over
@@ -26,6 +31,7 @@
 
 struct lm_group {
   int mode = LM_GROUP_FRAMES;
+  int shards = 1;  // template shards per set of devices; the group has det.size() / shards sets
   std::vector<lm_detector*> det;
   std::vector<int> device;
   std::vector<std::thread> worker;
@@ -82,9 +88,11 @@ struct lm_group {
 
 extern "C" {
 
-int lm_group_create(const lm_detector* prototype, const int* devices, int n_devices, int mode, lm_group** out) {
+int lm_group_create_grid(const lm_detector* prototype, const int* devices, int n_devices, int template_shards, lm_group** out) {
   if (!prototype || !devices || !out || n_devices < 1) return lm_fail(LM_E_INVALID, "bad argument");
-  if (mode != LM_GROUP_FRAMES && mode != LM_GROUP_TEMPLATES) return lm_fail(LM_E_INVALID, "unknown group mode %d", mode);
+  if (template_shards < 1 || n_devices % template_shards != 0)
+    return lm_fail(LM_E_INVALID, "template_shards (%d) must divide the number of devices (%d)", template_shards, n_devices);
+  const int mode = template_shards == 1 ? LM_GROUP_FRAMES : LM_GROUP_TEMPLATES;
   *out = nullptr;
   int have = 0;
   if (cudaGetDeviceCount(&have) != cudaSuccess || have == 0) {
@@ -95,17 +103,23 @@ int lm_group_create(const lm_detector* prototype, const int* devices, int n_devi
     if (devices[i] < 0 || devices[i] >= have) return lm_fail(LM_E_INVALID, "device %d does not exist (%d devices)", devices[i], have);
   lm_group* g = new lm_group();
   g->mode = mode;
+  g->shards = template_shards;
   g->device.assign(devices, devices + n_devices);
   g->rc.assign((size_t)n_devices, LM_OK);
   g->err.assign((size_t)n_devices, std::string());
   for (int i = 0; i < n_devices; ++i) {
     lm_detector* d = lm_internal_clone(prototype);
-    if (mode == LM_GROUP_TEMPLATES) lm_set_shard(d, i, n_devices);
+    if (template_shards > 1) lm_set_shard(d, i % template_shards, template_shards);   // device i = shard i % S of set i / S
     g->det.push_back(d);
   }
   for (int i = 0; i < n_devices; ++i) g->worker.emplace_back([g, i]() { g->loop(i); });
   *out = g;
   return LM_OK;
+}
+
+int lm_group_create(const lm_detector* prototype, const int* devices, int n_devices, int mode, lm_group** out) {
+  if (mode != LM_GROUP_FRAMES && mode != LM_GROUP_TEMPLATES) return lm_fail(LM_E_INVALID, "unknown group mode %d", mode);
+  return lm_group_create_grid(prototype, devices, n_devices, mode == LM_GROUP_FRAMES ? 1 : n_devices, out);
 }
 
 void lm_group_destroy(lm_group* g) {
@@ -141,18 +155,22 @@ int lm_group_match_batch_multi(lm_group* g, const lm_image* sources, int n_frame
     return lm_fail(LM_E_INVALID, "bad argument");
   *out_matches = nullptr;
   out_offsets[0] = 0;
-  const int N = (int)g->det.size(), M = n_sources, Q = n_queries;
+  const int N = (int)g->det.size(), M = n_sources, Q = n_queries, S = g->shards, SETS = N / S;
   std::vector<lm_match_rec> all;
-  if (g->mode == LM_GROUP_FRAMES) {
-    // launch sets dealt round robin: device i takes frames [c * F, (c + 1) * F) for c % N == i
-    const int F = std::max(1, std::min(g->det[0]->batch_frames, LM_MAX_BATCH));
-    std::vector<std::vector<lm_image> > mine((size_t)N);
-    std::vector<std::vector<int> > frame_of((size_t)N);
-    for (int f = 0; f < n_frames; ++f) {
-      const int i = (f / F) % N;
-      for (int m = 0; m < M; ++m) mine[(size_t)i].push_back(sources[(size_t)f * M + m]);
-      frame_of[(size_t)i].push_back(f);
-    }
+  // launch sets dealt round robin over the sets of devices: set k takes frames [c * F, (c + 1) * F) for c % SETS == k
+  const int F = std::max(1, std::min(g->det[0]->batch_frames, LM_MAX_BATCH));
+  std::vector<std::vector<lm_image> > mine((size_t)SETS);
+  std::vector<std::vector<int> > frame_of((size_t)SETS);
+  for (int f = 0; f < n_frames; ++f) {
+    const int k = (f / F) % SETS;
+    for (int m = 0; m < M; ++m) mine[(size_t)k].push_back(sources[(size_t)f * M + m]);
+    frame_of[(size_t)k].push_back(f);
+  }
+  std::vector<std::pair<int, int> > where((size_t)n_frames);  // frame -> (set, index within the set's frames)
+  for (int k = 0; k < SETS; ++k)
+    for (size_t j = 0; j < frame_of[(size_t)k].size(); ++j) where[(size_t)frame_of[(size_t)k][j]] = std::make_pair(k, (int)j);
+  if (S == 1) {
+    // every device holds all templates: finished lists per device, put back into frame order
     std::vector<lm_match_rec*> part((size_t)N, nullptr);
     std::vector<std::vector<size_t> > offs((size_t)N);
     int rc = g->run([&](int i) -> int {
@@ -162,10 +180,6 @@ int lm_group_match_batch_multi(lm_group* g, const lm_image* sources, int n_frame
       return lm_match_batch_multi(g->det[(size_t)i], mine[(size_t)i].data(), n, M, queries, Q, &part[(size_t)i], offs[(size_t)i].data());
     });
     if (rc == LM_OK) {
-      // back into frame order
-      std::vector<std::pair<int, int> > where((size_t)n_frames);  // frame -> (device, local index)
-      for (int i = 0; i < N; ++i)
-        for (size_t k = 0; k < frame_of[(size_t)i].size(); ++k) where[(size_t)frame_of[(size_t)i][k]] = std::make_pair(i, (int)k);
       for (int f = 0; f < n_frames; ++f) {
         const int i = where[(size_t)f].first, k = where[(size_t)f].second;
         for (int q = 0; q < Q; ++q) {
@@ -178,18 +192,21 @@ int lm_group_match_batch_multi(lm_group* g, const lm_image* sources, int n_frame
     for (lm_match_rec* p : part) lm_free_matches(p);
     if (rc != LM_OK) return rc;
   } else {
-    // every device matches every frame against its template shard; the shards' survivors are merged per frame
+    // every device of a set matches the set's frames against its template shard; the shards' survivors are merged per frame
     std::vector<std::vector<std::vector<lm_raw_match> > > raw((size_t)N);
     int rc = g->run([&](int i) -> int {
-      return lm_internal_match_batch_raw(g->det[(size_t)i], sources, n_frames, M, queries, Q, &raw[(size_t)i]);
+      const int k = i / S, n = (int)frame_of[(size_t)k].size();
+      if (n == 0) { raw[(size_t)i].clear(); return LM_OK; }
+      return lm_internal_match_batch_raw(g->det[(size_t)i], mine[(size_t)k].data(), n, M, queries, Q, &raw[(size_t)i]);
     });
     if (rc != LM_OK) return rc;
     const int levels = lm_pyramid_levels(g->det[0]);
     std::vector<lm_raw_match> merged;
     std::vector<lm_match_rec> out[LM_MAX_QUERIES];
     for (int f = 0; f < n_frames; ++f) {
+      const int k = where[(size_t)f].first, j = where[(size_t)f].second;
       merged.clear();
-      for (int i = 0; i < N; ++i) merged.insert(merged.end(), raw[(size_t)i][(size_t)f].begin(), raw[(size_t)i][(size_t)f].end());
+      for (int i = k * S; i < (k + 1) * S; ++i) merged.insert(merged.end(), raw[(size_t)i][(size_t)j].begin(), raw[(size_t)i][(size_t)j].end());
       lm_internal_finalize(levels, merged, Q, out);
       for (int q = 0; q < Q; ++q) {
         all.insert(all.end(), out[q].begin(), out[q].end());

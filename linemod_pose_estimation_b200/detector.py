@@ -399,10 +399,14 @@ class DetectorGroup:
     frame, survivors merged before the reference's sort + unique.  Results equal the prototype's in both modes."""
     FRAMES, TEMPLATES = 0, 1
 
-    def __init__(self, prototype, devices, mode="frames"):
+    def __init__(self, prototype, devices, mode="frames", template_shards=None):
+        """mode "frames" / "templates", or template_shards = S for the 2-D grid: len(devices) / S sets of S shards."""
         self._h = C.c_void_p()
         self.proto = prototype
         dv = (C.c_int * len(devices))(*devices)
+        if template_shards is not None:
+            check(lib().lm_group_create_grid(prototype._h, dv, len(devices), int(template_shards), C.byref(self._h)))
+            return
         m = {"frames": self.FRAMES, "templates": self.TEMPLATES}[mode]
         check(lib().lm_group_create(prototype._h, dv, len(devices), m, C.byref(self._h)))
 

@@ -672,7 +672,7 @@ class _OrcAsSink:
         return self.orc.add_synthetic_template(cid, templates)
 
 
-@pytest.mark.parametrize("mode,members", [("frames", 2), ("frames", 3), ("templates", 2), ("templates", 3)])
+@pytest.mark.parametrize("mode,members", [("frames", 2), ("frames", 3), ("templates", 2), ("templates", 3), ("grid2", 4), ("grid3", 6)])
 def test_device_group_equals_the_oracle(mode, members):
     """lm_group (several GPUs behind one C++ caller): frames dealt out in launch sets / templates sharded with the shards'
     survivors merged on the host.  On a one-GPU box the members share device 0 -- the dealing, the per-member worker
@@ -682,7 +682,10 @@ def test_device_group_equals_the_oracle(mode, members):
     orc, det, views = _pair(n_views=8, n_random=40, seed=211, classes=("cpu_binary", "memoryChip2"))
     det.set_option("batch_frames", 4)
     n_dev = torch.cuda.device_count()
-    group = DetectorGroup(det, [i % n_dev for i in range(members)], mode)
+    if mode.startswith("grid"):   # 2-D: members / S sets of S template shards
+        group = DetectorGroup(det, [i % n_dev for i in range(members)], template_shards=int(mode[4:]))
+    else:
+        group = DetectorGroup(det, [i % n_dev for i in range(members)], mode)
     assert len(group) == members
     queries = [(88.0, ["memoryChip2"]), (70.0, [])]
     frames = [list(synth.compose_scene(8400 + i, views[i % 3:i % 3 + 4])[:2]) for i in range(19)]

@@ -123,6 +123,15 @@ def main():
         for _ in range(reps):
             host_pass()
         e2e_us = 1e6 * (time.perf_counter() - t0) / (reps * args.pool)
+        one, _k1 = _capi.image_array(list(host[0]))
+        offs1 = (C.c_size_t * (n_q + 1))()
+        lat = []
+        for i in range(60):     # one blocking call per frame: the ROS service's shape
+            t0 = time.perf_counter()
+            _capi.check(lib.lm_match_batch_multi(det._h, one, 1, 2, qarr, n_q, C.byref(out_p), offs1))
+            lat.append(time.perf_counter() - t0)
+            lib.lm_free_matches(out_p)
+        single_us = 1e6 * float(np.median(lat[10:]))
         det.set_option("timing", 1)
         det.set_option("batch_lanes", 1)    # one chunk at a time: stage times of a chunk's kernels running alone
         host_pass()
@@ -130,7 +139,7 @@ def main():
         det.set_option("timing", 0)
         fr = max(1, w["frames"])
         out = {"workload": args.workload, "config": cfg, "templates": det.numTemplates(), "device_us_per_frame": round(dev_us, 2), "e2e_us_per_frame": round(e2e_us, 2),
-               "chunk_frames": fr, "launches_per_chunk": t["launches"],
+               "single_call_us": round(single_us, 1), "chunk_frames": fr, "launches_per_chunk": t["launches"],
                "gathered_frac": round(w["B_coarse_gathered"] / max(1, w["B_coarse"]), 4), "candidates_per_frame": w["candidates"] / fr,
                "matches_per_frame": sum(len(x) for x in res) / args.pool}
         out.update({k + "_us_per_frame": round(1e3 * t[k] / fr, 2) for k in ("h2d", "front", "coarse", "refine", "d2h")})
