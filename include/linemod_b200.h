@@ -144,6 +144,24 @@ int lm_add_template_from_quantized(lm_detector* det, const lm_image* quantized, 
 int lm_add_synthetic_template(lm_detector* det, const char* class_id, int n_templates, const lm_template_hdr* hdr,
                               const int32_t* feats);
 
+/* cv::linemod::Modality::process(src, mask) -> Ptr<QuantizedPyramid>, and QuantizedPyramid::{quantize, extractTemplate,
+ * pyrDown}  ([OCV] linemod.cpp: ColorGradientPyramid / DepthNormalPyramid; the surface behind Detector::addTemplate and
+ * Detector::match).  lm_modality_process quantises `src` (CV_8UC3 for ColorGradient, CV_16UC1 for DepthNormal) on
+ * the current CUDA device for `levels` pyramid levels at once -- level l is the reference's object after l pyrDown() calls --
+ * and keeps the result on the host.  normal_lut: nullable 8000-byte NORMAL_LUT (see lm_set_normal_lut).
+ *   lm_qpyramid_quantize(q, l, dst)     quantize(dst): dst caller-allocated CV_8UC1 of lm_qpyramid_size(q, l), masked
+ *   lm_qpyramid_extract(q, l, hdr, f)   extractTemplate(templ): 1 = ok, hdr = {-1, -1, l, n} and f (nullable, room for
+ *                                       3 * LM_MAX_FEATURES ints) = n (x, y, label) triples in level-l coordinates; 0 = the
+ *                                       level lacks candidates (the reference returns false); < 0 = LM_E_*          */
+typedef struct lm_qpyramid lm_qpyramid;
+int lm_modality_process(const lm_modality_desc* modality, const lm_image* src, const lm_image* mask /*nullable*/, int levels,
+                        const uint8_t* normal_lut /*nullable*/, lm_qpyramid** out);
+void lm_qpyramid_destroy(lm_qpyramid* q);
+int lm_qpyramid_levels(const lm_qpyramid* q);
+int lm_qpyramid_size(const lm_qpyramid* q, int level, int* rows, int* cols);
+int lm_qpyramid_quantize(const lm_qpyramid* q, int level, lm_image* dst);
+int lm_qpyramid_extract(const lm_qpyramid* q, int level, lm_template_hdr* hdr, int32_t* features /*nullable*/);
+
 /* ------------------------------------------------------------------------------------------------ template generation */
 /* Training at scale: the loop of /root/reference/src/renderer.cpp:239-329 --
  *     for every view of RendererIterator: render(image, depth, mask, rect); detector->addTemplate(sources, "obj", mask)

@@ -112,13 +112,89 @@ struct Image {
   }
 };
 
-// cv::linemod::Modality and its two implementations: parameter carriers here, the processing is in the CUDA kernels.
+// cv::linemod::QuantizedPyramid, the object Modality::process returns ([OCV] linemod.cpp ColorGradientPyramid /
+// DepthNormalPyramid): quantize(dst), extractTemplate(templ), pyrDown().  All pyramid levels the image allows (up to
+// LM_MAX_LEVELS) were quantised by the CUDA front end when process() ran; pyrDown() steps to the next one.
+class QuantizedPyramid {
+ public:
+  explicit QuantizedPyramid(lm_qpyramid* q) : q_(q), level_(0) {}
+  ~QuantizedPyramid() { lm_qpyramid_destroy(q_); }
+  QuantizedPyramid(const QuantizedPyramid&) = delete;
+  QuantizedPyramid& operator=(const QuantizedPyramid&) = delete;
+
+  // size of the current level (what quantize() writes)
+  void size(int& rows, int& cols) const { detail::check(lm_qpyramid_size(q_, level_, &rows, &cols)); }
+  // quantize into caller-owned CV_8UC1 memory of size()
+  void quantize(uint8_t* dst, size_t step = 0) const {
+    int r = 0, c = 0;
+    size(r, c);
+    lm_image im;
+    im.data = dst; im.rows = r; im.cols = c; im.type = LM_8UC1; im.step = step ? step : (size_t)c;
+    detail::check(lm_qpyramid_quantize(q_, level_, &im));
+  }
+  void quantize(std::vector<uint8_t>& dst) const {
+    int r = 0, c = 0;
+    size(r, c);
+    dst.assign((size_t)r * c, 0);
+    quantize(dst.data());
+  }
+#ifdef LINEMOD_B200_WITH_OPENCV
+  void quantize(cv::Mat& dst) const {
+    int r = 0, c = 0;
+    size(r, c);
+    dst.create(r, c, CV_8UC1);
+    quantize(dst.data, dst.step[0]);
+  }
+#endif
+  bool extractTemplate(Template& templ) const {
+    lm_template_hdr hdr;
+    int32_t f[3 * LM_MAX_FEATURES];
+    const int ok = detail::check(lm_qpyramid_extract(q_, level_, &hdr, f));
+    if (!ok) return false;
+    templ.width = hdr.width; templ.height = hdr.height; templ.pyramid_level = hdr.pyramid_level;
+    templ.features.resize((size_t)hdr.num_features);
+    for (int j = 0; j < hdr.num_features; ++j) templ.features[(size_t)j] = Feature(f[3 * j], f[3 * j + 1], f[3 * j + 2]);
+    return true;
+  }
+  void pyrDown() {
+    if (level_ + 1 >= lm_qpyramid_levels(q_)) throw Exception(LM_E_INVALID, "QuantizedPyramid: no further level (image too small or LM_MAX_LEVELS reached)");
+    ++level_;
+  }
+
+ private:
+  lm_qpyramid* q_;
+  int level_;
+};
+
+// cv::linemod::Modality and its two implementations: parameter carriers; process() runs the CUDA front end.
 class Modality {
  public:
   virtual ~Modality() {}
   virtual std::string name() const = 0;
   virtual lm_modality_desc desc() const = 0;
+  // Modality::process(src, mask): src CV_8UC3 (ColorGradient) / CV_16UC1 (DepthNormal), mask CV_8UC1 or empty
+#ifdef LINEMOD_B200_WITH_OPENCV
+  typedef cv::Ptr<QuantizedPyramid> PyramidPtr;
+#else
+  typedef std::shared_ptr<QuantizedPyramid> PyramidPtr;
+#endif
+  PyramidPtr process(const Image& src, const Image& mask = Image()) const {
+    const lm_modality_desc d = desc();
+    const lm_image s = src.c(), m = mask.c();
+    int levels = LM_MAX_LEVELS;
+    while (levels > 1 && ((src.rows >> (levels - 1)) < 16 || (src.cols >> (levels - 1)) < 16)) --levels;
+    lm_qpyramid* q = nullptr;
+    detail::check(lm_modality_process(&d, &s, mask.empty() ? nullptr : &m, levels, nullptr, &q));
+    return PyramidPtr(new QuantizedPyramid(q));
+  }
   static std::shared_ptr<Modality> create(const std::string& modality_type);
+#ifdef LINEMOD_B200_WITH_OPENCV
+  // Modality::read / write / create(FileNode): { type: "ColorGradient", weak_threshold, num_features, strong_threshold } or
+  // { type: "DepthNormal", distance_threshold, difference_threshold, num_features, extract_threshold }
+  virtual void read(const cv::FileNode& fn) = 0;
+  virtual void write(cv::FileStorage& fs) const = 0;
+  static cv::Ptr<Modality> create(const cv::FileNode& fn);
+#endif
 };
 
 class ColorGradient : public Modality {
@@ -130,6 +206,17 @@ class ColorGradient : public Modality {
     lm_modality_desc d = {LM_COLOR_GRADIENT, weak_threshold, strong_threshold, 2000, 50, 2, (int32_t)num_features};
     return d;
   }
+#ifdef LINEMOD_B200_WITH_OPENCV
+  void read(const cv::FileNode& fn) override {
+    if ((std::string)fn["type"] != name()) throw Exception(LM_E_IO, "modality node is not a ColorGradient");
+    weak_threshold = (float)fn["weak_threshold"];
+    num_features = (size_t)(int)fn["num_features"];
+    strong_threshold = (float)fn["strong_threshold"];
+  }
+  void write(cv::FileStorage& fs) const override {
+    fs << "type" << name() << "weak_threshold" << weak_threshold << "num_features" << (int)num_features << "strong_threshold" << strong_threshold;
+  }
+#endif
   float weak_threshold;
   size_t num_features;
   float strong_threshold;
@@ -146,6 +233,19 @@ class DepthNormal : public Modality {
                           (int32_t)num_features};
     return d;
   }
+#ifdef LINEMOD_B200_WITH_OPENCV
+  void read(const cv::FileNode& fn) override {
+    if ((std::string)fn["type"] != name()) throw Exception(LM_E_IO, "modality node is not a DepthNormal");
+    distance_threshold = (int)fn["distance_threshold"];
+    difference_threshold = (int)fn["difference_threshold"];
+    num_features = (size_t)(int)fn["num_features"];
+    extract_threshold = (int)fn["extract_threshold"];
+  }
+  void write(cv::FileStorage& fs) const override {
+    fs << "type" << name() << "distance_threshold" << distance_threshold << "difference_threshold" << difference_threshold
+       << "num_features" << (int)num_features << "extract_threshold" << extract_threshold;
+  }
+#endif
   int distance_threshold, difference_threshold;
   size_t num_features;
   int extract_threshold;
@@ -162,6 +262,18 @@ inline std::shared_ptr<Modality> Modality::create(const std::string& modality_ty
   if (modality_type == "DepthNormal") return std::make_shared<DepthNormal>();
   throw Exception(LM_E_INVALID, "unknown modality '" + modality_type + "'");
 }
+
+#ifdef LINEMOD_B200_WITH_OPENCV
+inline cv::Ptr<Modality> Modality::create(const cv::FileNode& fn) {
+  const std::string type = (std::string)fn["type"];
+  cv::Ptr<Modality> m;
+  if (type == "ColorGradient") m = cv::Ptr<Modality>(new ColorGradient());
+  else if (type == "DepthNormal") m = cv::Ptr<Modality>(new DepthNormal());
+  else throw Exception(LM_E_INVALID, "unknown modality '" + type + "'");
+  m->read(fn);
+  return m;
+}
+#endif
 
 // cv::linemod::Detector
 class Detector {

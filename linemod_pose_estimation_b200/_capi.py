@@ -70,6 +70,7 @@ EXPORTS = [
     "lm_create", "lm_create_from_yaml", "lm_write_yaml", "lm_create_from_cache", "lm_write_cache", "lm_read_classes", "lm_write_classes", "lm_destroy",
     "lm_last_error", "lm_alloc_pinned", "lm_free_pinned", "lm_device", "lm_pyramid_levels", "lm_get_T",
     "lm_num_modalities", "lm_get_modality", "lm_num_classes", "lm_num_templates", "lm_class_id", "lm_get_templates",
+    "lm_modality_process", "lm_qpyramid_destroy", "lm_qpyramid_levels", "lm_qpyramid_size", "lm_qpyramid_quantize", "lm_qpyramid_extract",
     "lm_add_template", "lm_add_template_from_quantized", "lm_add_synthetic_template", "lm_match", "lm_match_multi", "lm_match_batch", "lm_match_batch_multi", "lm_free_matches",
     "lm_match_device", "lm_match_device_multi", "lm_match_device_multi_lane", "lm_device_result_region", "lm_copy_result_block", "lm_match_device_stream", "lm_finalize_raw", "lm_finalize_gathered", "lm_upload_images", "lm_set_shard", "lm_set_similarity_lut", "lm_get_similarity_lut",
     "lm_set_normal_lut", "lm_get_normal_lut", "lm_load_normal_lut_file", "lm_debug_fetch", "lm_build_front", "lm_level_geometry",
@@ -126,6 +127,13 @@ def lib():
     L.lm_add_template_from_quantized.argtypes = [vp, C.POINTER(LmImage), C.POINTER(vp), cp, C.POINTER(LmImage),
                                                  C.POINTER(LmRect)]
     L.lm_add_synthetic_template.argtypes = [vp, cp, ci, vp, vp]
+    L.lm_modality_process.argtypes = [C.POINTER(LmModalityDesc), C.POINTER(LmImage), C.POINTER(LmImage), ci, vp, C.POINTER(vp)]
+    L.lm_qpyramid_destroy.argtypes = [vp]
+    L.lm_qpyramid_destroy.restype = None
+    L.lm_qpyramid_levels.argtypes = [vp]
+    L.lm_qpyramid_size.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci)]
+    L.lm_qpyramid_quantize.argtypes = [vp, ci, C.POINTER(LmImage)]
+    L.lm_qpyramid_extract.argtypes = [vp, ci, vp, vp]
     L.lm_match.argtypes = [vp, C.POINTER(LmImage), ci, C.c_float, C.POINTER(cp), ci, C.POINTER(LmImage), ci,
                            C.POINTER(LmImage), C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.lm_match_multi.argtypes = [vp, C.POINTER(LmImage), ci, C.POINTER(LmQuery), ci, C.POINTER(LmImage), ci,

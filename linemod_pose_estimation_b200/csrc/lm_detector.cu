@@ -1134,56 +1134,171 @@ int lm_add_synthetic_template(lm_detector* d, const char* class_id, int n_templa
   return (int)tps.size() - 1;
 }
 
+// Quantised maps (+ ColorGradient magnitudes) of every pyramid level of ONE frame: upload, quantisation kernels, download
+// into the lane's pinned staging buffer.  Image l*M+m at host + qoff / moff.
+struct QuantHost {
+  uint8_t* host = nullptr;
+  std::vector<size_t> qoff, moff;
+};
+static int quantize_to_host(lm_detector* d, const lm_image* sources, int n_sources, QuantHost& qh) {
+  if (set_device(d) != LM_OK) return LM_E_CUDA;
+  const int L = d->model.levels(), M = d->model.M();
+  int rc = check_sources(d, sources, n_sources, nullptr, 0);
+  if (rc != LM_OK) return rc;
+  const int rows = sources[0].rows, cols = sources[0].cols;
+  Lane& ln = d->lane[0];
+  if (upload_luts(d) != LM_OK) return LM_E_CUDA;
+  if (ensure_quant_ws(d, ln, rows, cols) != LM_OK) return LM_E_CUDA;
+  ln.lm_ready = false; ln.front_valid = false;
+  if (upload_frames(d, ln, sources, 1, nullptr, 0) != LM_OK) return LM_E_CUDA;
+  ln.launches = 0;
+  if (begin_chunk(d, ln, 1, 0, ln.stream) != LM_OK) return LM_E_CUDA;
+  if (run_quantize(d, ln, 1, ln.stream) != LM_OK) return LM_E_CUDA;
+  size_t total = 0;
+  qh.qoff.assign((size_t)L * M, 0); qh.moff.assign((size_t)L * M, 0);
+  for (int l = 0; l < L; ++l)
+    for (int m = 0; m < M; ++m) {
+      size_t n = (size_t)(rows >> l) * (cols >> l);
+      qh.qoff[l * M + m] = total; total += (n + 255) & ~(size_t)255;
+      if (d->model.mods[m].type == LM_COLOR_GRADIENT) { qh.moff[l * M + m] = total; total += (n * 4 + 255) & ~(size_t)255; }
+    }
+  if (ln.stage_out.ensure(total) != LM_OK) return LM_E_CUDA;
+  qh.host = ln.stage_out.as<uint8_t>();
+  for (int l = 0; l < L; ++l)
+    for (int m = 0; m < M; ++m) {
+      size_t n = (size_t)(rows >> l) * (cols >> l);
+      if (cudaMemcpyAsync(qh.host + qh.qoff[l * M + m], ln.quant_raw[l][m].buf.p, n, cudaMemcpyDeviceToHost, ln.stream) != cudaSuccess) return lm_fail(LM_E_CUDA, "D2H failed");
+      if (d->model.mods[m].type == LM_COLOR_GRADIENT &&
+          cudaMemcpyAsync(qh.host + qh.moff[l * M + m], ln.mag[l][m].buf.p, n * 4, cudaMemcpyDeviceToHost, ln.stream) != cudaSuccess)
+        return lm_fail(LM_E_CUDA, "D2H failed");
+    }
+  if (cudaStreamSynchronize(ln.stream) != cudaSuccess) return lm_fail(LM_E_CUDA, "quantisation kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return LM_OK;
+}
+
 int lm_add_template(lm_detector* d, const lm_image* sources, int n_sources, const char* class_id,
                     const lm_image* object_mask, lm_rect* bounding_box) {
   if (!d || !sources || !class_id) return lm_fail(LM_E_INVALID, "NULL argument") - 100;
-  if (set_device(d) != LM_OK) return LM_E_CUDA - 100;
   const int L = d->model.levels(), M = d->model.M();
-  int rc = check_sources(d, sources, n_sources, nullptr, 0);
+  const bool has_mask = object_mask && object_mask->data;
+  if (has_mask && n_sources > 0 && (object_mask->type != LM_8UC1 || object_mask->rows != sources[0].rows || object_mask->cols != sources[0].cols))
+    return lm_fail(LM_E_INVALID, "object_mask size/type mismatch") - 100;
+  QuantHost qh;
+  int rc = quantize_to_host(d, sources, n_sources, qh);
   if (rc != LM_OK) return rc - 100;
   const int rows = sources[0].rows, cols = sources[0].cols;
-  const bool has_mask = object_mask && object_mask->data;
-  if (has_mask && (object_mask->type != LM_8UC1 || object_mask->rows != rows || object_mask->cols != cols))
-    return lm_fail(LM_E_INVALID, "object_mask size/type mismatch") - 100;
-  Lane& ln = d->lane[0];
-  if (upload_luts(d) != LM_OK) return LM_E_CUDA - 100;
-  if (ensure_quant_ws(d, ln, rows, cols) != LM_OK) return LM_E_CUDA - 100;
-  ln.lm_ready = false; ln.front_valid = false;
-  if (upload_frames(d, ln, sources, 1, nullptr, 0) != LM_OK) return LM_E_CUDA - 100;
-  ln.launches = 0;
-  if (begin_chunk(d, ln, 1, 0, ln.stream) != LM_OK) return LM_E_CUDA - 100;
-  if (run_quantize(d, ln, 1, ln.stream) != LM_OK) return LM_E_CUDA - 100;
-  // download quantised maps (+ CG magnitudes) of every level
-  size_t total = 0;
-  std::vector<size_t> qoff((size_t)L * M), moff((size_t)L * M, 0);
-  for (int l = 0; l < L; ++l)
-    for (int m = 0; m < M; ++m) {
-      size_t n = (size_t)(rows >> l) * (cols >> l);
-      qoff[l * M + m] = total; total += (n + 255) & ~(size_t)255;
-      if (d->model.mods[m].type == LM_COLOR_GRADIENT) { moff[l * M + m] = total; total += (n * 4 + 255) & ~(size_t)255; }
-    }
-  if (ln.stage_out.ensure(total) != LM_OK) return LM_E_CUDA - 100;
-  uint8_t* host = ln.stage_out.as<uint8_t>();
-  for (int l = 0; l < L; ++l)
-    for (int m = 0; m < M; ++m) {
-      size_t n = (size_t)(rows >> l) * (cols >> l);
-      if (cudaMemcpyAsync(host + qoff[l * M + m], ln.quant_raw[l][m].buf.p, n, cudaMemcpyDeviceToHost, ln.stream) != cudaSuccess) return lm_fail(LM_E_CUDA, "D2H failed") - 100;
-      if (d->model.mods[m].type == LM_COLOR_GRADIENT &&
-          cudaMemcpyAsync(host + moff[l * M + m], ln.mag[l][m].buf.p, n * 4, cudaMemcpyDeviceToHost, ln.stream) != cudaSuccess)
-        return lm_fail(LM_E_CUDA, "D2H failed") - 100;
-    }
-  if (cudaStreamSynchronize(ln.stream) != cudaSuccess) return lm_fail(LM_E_CUDA, "quantisation kernels failed: %s", cudaGetErrorString(cudaGetLastError())) - 100;
-
   std::vector<lm_image> qimgs((size_t)L * M);
   std::vector<const float*> mags((size_t)L * M, nullptr);
   for (int l = 0; l < L; ++l)
     for (int m = 0; m < M; ++m) {
       lm_image& q = qimgs[l * M + m];
-      q.data = host + qoff[l * M + m]; q.rows = rows >> l; q.cols = cols >> l; q.type = LM_8UC1; q.step = (size_t)(cols >> l);
-      if (d->model.mods[m].type == LM_COLOR_GRADIENT) mags[l * M + m] = reinterpret_cast<const float*>(host + moff[l * M + m]);
+      q.data = qh.host + qh.qoff[l * M + m]; q.rows = rows >> l; q.cols = cols >> l; q.type = LM_8UC1; q.step = (size_t)(cols >> l);
+      if (d->model.mods[m].type == LM_COLOR_GRADIENT) mags[l * M + m] = reinterpret_cast<const float*>(qh.host + qh.moff[l * M + m]);
     }
   int tid = lm_add_template_from_quantized(d, qimgs.data(), mags.data(), class_id, object_mask, bounding_box);
   return tid < -1 ? tid - 100 : tid;
+}
+
+// ---- cv::linemod::Modality::process / QuantizedPyramid ([OCV] linemod.cpp: ColorGradientPyramid, DepthNormalPyramid).
+// Host-side state of one processed image: per level the unmasked quantisation (+ magnitude) the CUDA front end produced
+// and the decimated mask; quantize() and extractTemplate() of the reference read exactly these.
+struct lm_qpyramid {
+  lm_modality_desc mod;
+  int rows = 0, cols = 0, levels = 0;
+  std::vector<std::vector<uint8_t> > quant, mask;  // [level]; mask[level] empty when process() got no mask
+  std::vector<std::vector<float> > mag;            // [level], ColorGradient only
+};
+
+int lm_modality_process(const lm_modality_desc* mod, const lm_image* src, const lm_image* mask, int levels,
+                        const uint8_t* normal_lut, lm_qpyramid** out) {
+  if (!mod || !src || !out) return lm_fail(LM_E_INVALID, "NULL argument");
+  *out = nullptr;
+  if (levels < 1 || levels > LM_MAX_LEVELS) return lm_fail(LM_E_INVALID, "levels must be 1..%d", LM_MAX_LEVELS);
+  const bool has_mask = mask && mask->data;
+  if (has_mask && (mask->type != LM_8UC1 || mask->rows != src->rows || mask->cols != src->cols))
+    return lm_fail(LM_E_INVALID, "mask size/type mismatch (mask.size() == src.size())");
+  if ((src->rows >> (levels - 1)) < 1 || (src->cols >> (levels - 1)) < 1) return lm_fail(LM_E_INVALID, "image too small for %d levels", levels);
+  // a private single-modality detector carries the parameters, the LUT and the quantisation workspace of this call
+  int32_t T[LM_MAX_LEVELS] = {1, 1, 1, 1};
+  lm_detector* d = nullptr;
+  int rc = lm_create(T, levels, mod, 1, &d);
+  if (rc != LM_OK) return rc;
+  if (normal_lut) lm_set_normal_lut(d, normal_lut);
+  QuantHost qh;
+  rc = quantize_to_host(d, src, 1, qh);
+  if (rc != LM_OK) { lm_destroy(d); return rc; }
+  lm_qpyramid* q = new lm_qpyramid();
+  q->mod = *mod; q->rows = src->rows; q->cols = src->cols; q->levels = levels;
+  q->quant.resize((size_t)levels); q->mask.resize((size_t)levels); q->mag.resize((size_t)levels);
+  for (int l = 0; l < levels; ++l) {
+    const size_t n = (size_t)(q->rows >> l) * (q->cols >> l);
+    q->quant[(size_t)l].assign(qh.host + qh.qoff[(size_t)l], qh.host + qh.qoff[(size_t)l] + n);
+    if (mod->type == LM_COLOR_GRADIENT) {
+      const float* mg = reinterpret_cast<const float*>(qh.host + qh.moff[(size_t)l]);
+      q->mag[(size_t)l].assign(mg, mg + n);
+    }
+  }
+  lm_destroy(d);
+  if (has_mask) {  // [OCV] pyrDown(): the mask is NN-resized, i.e. plain index decimation
+    q->mask[0].resize((size_t)q->rows * q->cols);
+    for (int y = 0; y < q->rows; ++y) std::memcpy(&q->mask[0][(size_t)y * q->cols], (const uint8_t*)mask->data + (size_t)y * mask->step, (size_t)q->cols);
+    for (int l = 1; l < levels; ++l) {
+      const int pc = q->cols >> (l - 1), r = q->rows >> l, c = q->cols >> l;
+      q->mask[(size_t)l].resize((size_t)r * c);
+      for (int y = 0; y < r; ++y)
+        for (int x = 0; x < c; ++x) q->mask[(size_t)l][(size_t)y * c + x] = q->mask[(size_t)l - 1][(size_t)(2 * y) * pc + 2 * x];
+    }
+  }
+  *out = q;
+  return LM_OK;
+}
+
+void lm_qpyramid_destroy(lm_qpyramid* q) { delete q; }
+int lm_qpyramid_levels(const lm_qpyramid* q) { return q ? q->levels : 0; }
+
+int lm_qpyramid_size(const lm_qpyramid* q, int level, int* rows, int* cols) {
+  if (!q || level < 0 || level >= q->levels) return lm_fail(LM_E_INVALID, "level out of range");
+  if (rows) *rows = q->rows >> level;
+  if (cols) *cols = q->cols >> level;
+  return LM_OK;
+}
+
+// [OCV] {ColorGradient,DepthNormal}Pyramid::quantize: dst = zeros; quantised.copyTo(dst, mask)
+int lm_qpyramid_quantize(const lm_qpyramid* q, int level, lm_image* dst) {
+  if (!q || !dst || !dst->data) return lm_fail(LM_E_INVALID, "NULL argument");
+  if (level < 0 || level >= q->levels) return lm_fail(LM_E_INVALID, "level out of range");
+  const int r = q->rows >> level, c = q->cols >> level;
+  if (dst->type != LM_8UC1 || dst->rows != r || dst->cols != c || dst->step < (size_t)c) return lm_fail(LM_E_INVALID, "dst must be a %dx%d CV_8UC1 image", c, r);
+  const uint8_t* src = q->quant[(size_t)level].data();
+  const uint8_t* mk = q->mask[(size_t)level].empty() ? nullptr : q->mask[(size_t)level].data();
+  for (int y = 0; y < r; ++y) {
+    uint8_t* o = (uint8_t*)dst->data + (size_t)y * dst->step;
+    for (int x = 0; x < c; ++x) o[x] = (!mk || mk[(size_t)y * c + x]) ? src[(size_t)y * c + x] : 0;
+  }
+  return LM_OK;
+}
+
+// [OCV] QuantizedPyramid::extractTemplate after `level` pyrDown() calls (num_features and extract_threshold halved per
+// level).  Returns 1 (hdr = {-1, -1, level, n}, features = n (x, y, label) triples in level coordinates), 0 when the
+// level lacks candidates (the reference returns false), < 0 = LM_E_*.
+int lm_qpyramid_extract(const lm_qpyramid* q, int level, lm_template_hdr* hdr, int32_t* features) {
+  if (!q || !hdr) return lm_fail(LM_E_INVALID, "NULL argument");
+  if (level < 0 || level >= q->levels) return lm_fail(LM_E_INVALID, "level out of range");
+  int nf = q->mod.num_features, ext = q->mod.extract_threshold;
+  for (int l = 0; l < level; ++l) { nf /= 2; ext /= 2; }
+  const int r = q->rows >> level, c = q->cols >> level;
+  const uint8_t* mk = q->mask[(size_t)level].empty() ? nullptr : q->mask[(size_t)level].data();
+  Template t;
+  const bool ok = q->mod.type == LM_COLOR_GRADIENT
+                      ? extract_color_gradient(q->quant[(size_t)level].data(), q->mag[(size_t)level].data(), mk, r, c, q->mod.strong_threshold, nf, level, t)
+                      : extract_depth_normal(q->quant[(size_t)level].data(), mk, r, c, nf, ext, level, t);
+  hdr->width = -1; hdr->height = -1; hdr->pyramid_level = level; hdr->num_features = ok ? (int)t.features.size() : 0;
+  if (!ok) return 0;
+  if (features)
+    for (size_t j = 0; j < t.features.size(); ++j) {
+      features[3 * j] = t.features[j].x; features[3 * j + 1] = t.features[j].y; features[3 * j + 2] = t.features[j].label;
+    }
+  return 1;
 }
 
 int lm_add_template_from_quantized(lm_detector* d, const lm_image* quantized, const float* const* magnitudes,

@@ -31,6 +31,59 @@ def DepthNormal(distance_threshold=2000, difference_threshold=50, num_features=6
                           num_features)
 
 
+class QuantizedPyramid:
+    """cv::linemod::QuantizedPyramid as returned by Modality::process ([OCV] linemod.cpp): quantize(), extractTemplate(),
+    pyrDown().  The quantisation of all `levels` ran on the GPU when the object was made."""
+
+    def __init__(self, modality, src, mask=None, levels=4, normal_lut=None):
+        self._h = C.c_void_p()
+        self.level = 0
+        simg, sk = image(src)
+        mptr = None
+        if mask is not None:
+            mimg, mk = image(mask)
+            mptr = C.pointer(mimg)
+        rows, cols = src.shape[:2]
+        while levels > 1 and min(rows >> (levels - 1), cols >> (levels - 1)) < 16:
+            levels -= 1
+        lut = None
+        if normal_lut is not None:
+            lut = np.ascontiguousarray(normal_lut, np.uint8).reshape(8000)
+        check(lib().lm_modality_process(C.byref(modality), C.byref(simg), mptr, levels, None if lut is None else lut.ctypes.data,
+                                        C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().lm_qpyramid_destroy(self._h)
+            self._h = None
+
+    def pyrDown(self):
+        if self.level + 1 >= lib().lm_qpyramid_levels(self._h):
+            raise LinemodError(-1, "pyramid has %d levels" % lib().lm_qpyramid_levels(self._h))
+        self.level += 1
+
+    def quantize(self):
+        r, c = C.c_int(), C.c_int()
+        check(lib().lm_qpyramid_size(self._h, self.level, C.byref(r), C.byref(c)))
+        dst = np.zeros((r.value, c.value), np.uint8)
+        dimg, dk = image(dst)
+        check(lib().lm_qpyramid_quantize(self._h, self.level, C.byref(dimg)))
+        return dst
+
+    def extractTemplate(self):
+        """-> (ok, (width, height, pyramid_level, features[n,3]))"""
+        hdr = np.zeros(1, HDR_DTYPE)
+        feats = np.zeros((63, 3), np.int32)
+        ok = check(lib().lm_qpyramid_extract(self._h, self.level, hdr.ctypes.data, feats.ctypes.data))
+        h = hdr[0]
+        return bool(ok), (int(h[0]), int(h[1]), int(h[2]), feats[:int(h[3])].copy())
+
+
+def process(modality, src, mask=None, levels=4, normal_lut=None):
+    """cv::linemod::Modality::process(src, mask) for a ColorGradient() / DepthNormal() descriptor."""
+    return QuantizedPyramid(modality, src, mask, levels, normal_lut)
+
+
 class Stage:
     QUANTIZED, SPREAD, RESPONSE, LINEAR, MAGNITUDE, QUANT_RAW, LINEAR_PACKED = range(7)
 

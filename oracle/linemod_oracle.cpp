@@ -1006,6 +1006,30 @@ static int extract_pyramid(const Detector& det, const orc_image* srcs, const orc
   return 0;
 }
 
+// [OCV] Modality::process(src, mask) of modality m, `level` pyrDown() calls, then QuantizedPyramid::quantize(dst) and
+// extractTemplate(templ): quant_out (nullable) rows>>level x cols>>level; hdr = {width, height, level, n}; feats (nullable)
+// n (x, y, label) triples.  Returns 1 / 0 = extractTemplate's bool, -2 on error.
+int orc_modality_process(void* h, int m, const orc_image* src, const orc_image* mask, int level, uint8_t* quant_out,
+                         int32_t* hdr, int32_t* feats) {
+  Detector& det = *(Detector*)h;
+  if (m < 0 || m >= det.M() || level < 0) { det.err = "modality / level out of range"; return -2; }
+  Source msk; if (mask && mask->data) msk = to_source(*mask);
+  QuantPyr q;
+  if (!pyr_process(det, det.mods[m], to_source(*src), (mask && mask->data) ? &msk : nullptr, q, det.err)) return -2;
+  for (int l = 0; l < level; ++l) pyr_down(q);
+  if (quant_out) {
+    std::vector<uint8_t> dst;
+    pyr_quantize(q, dst);
+    std::memcpy(quant_out, dst.data(), dst.size());
+  }
+  Template t;
+  const bool ok = det.mods[m].type == MOD_COLOR_GRADIENT ? cg_extract(q, t) : dn_extract(q, t);
+  hdr[0] = t.width; hdr[1] = t.height; hdr[2] = t.pyramid_level; hdr[3] = ok ? (int)t.features.size() : 0;
+  if (ok && feats)
+    for (size_t j = 0; j < t.features.size(); ++j) { feats[3 * j] = t.features[j].x; feats[3 * j + 1] = t.features[j].y; feats[3 * j + 2] = t.features[j].label; }
+  return ok ? 1 : 0;
+}
+
 // [OCV] Detector::addTemplate.  Returns template_id, -1 if any level lacks candidates, -2 on error.
 int orc_add_template(void* h, const orc_image* srcs, int nsrc, const char* class_id, const orc_image* mask,
                      int32_t* bb /*nullable [x,y,w,h]*/) {

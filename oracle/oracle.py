@@ -74,6 +74,9 @@ def lib():
         L.orc_add_template.restype = C.c_int
         L.orc_add_template.argtypes = [C.c_void_p, C.POINTER(OrcImage), C.c_int, C.c_char_p, C.POINTER(OrcImage),
                                        C.POINTER(C.c_int32)]
+        L.orc_modality_process.restype = C.c_int
+        L.orc_modality_process.argtypes = [C.c_void_p, C.c_int, C.POINTER(OrcImage), C.POINTER(OrcImage), C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]
         L.orc_add_synthetic_template.restype = C.c_int
         L.orc_add_synthetic_template.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_num_classes.argtypes = [C.c_void_p]
@@ -218,6 +221,23 @@ class OracleDetector:
         if r == -2:
             raise ValueError(self._err())
         return r, tuple(bb)
+
+    def modality_process(self, m, src, mask, level):
+        """Modality::process(src, mask) of modality m, `level` pyrDown()s, then quantize() and extractTemplate()
+        -> (quantized u8 image, ok, (width, height, pyramid_level, features[n,3]))."""
+        simg, sk = _img(src)
+        mimg = None
+        if mask is not None:
+            mm, mk = _img(mask)
+            mimg = C.pointer(mm)
+        r, c = src.shape[0] >> level, src.shape[1] >> level
+        q = np.zeros((r, c), np.uint8)
+        hdr = np.zeros(4, np.int32)
+        feats = np.zeros((63, 3), np.int32)
+        rc = lib().orc_modality_process(self._h, m, C.byref(simg), mimg, level, q.ctypes.data, hdr.ctypes.data, feats.ctypes.data)
+        if rc == -2:
+            raise ValueError(self._err())
+        return q, bool(rc), (int(hdr[0]), int(hdr[1]), int(hdr[2]), feats[:int(hdr[3])].copy())
 
     def train_views(self, triangles, cam, T, up, class_id):
         """The trainer's loop (render + addTemplate per view, det threads at a time, templates in view order).

@@ -136,7 +136,7 @@ static int run_host(const std::string& dir) {
   return 0;
 }
 
-static int run_gpu(const std::string&) {
+static int run_gpu(const std::string& dir) {
   cv::Ptr<cv::linemod::Detector> det = make_detector();
   // a textured box on a plane, as cv::Mat
   const int rows = 480, cols = 640;
@@ -170,6 +170,41 @@ static int run_gpu(const std::string&) {
   std::vector<linemod::Match> again;
   det->match(sources, 90.f, again, std::vector<String>(), quantized);
   REQUIRE(again.size() == matches.size() && quantized.size() == 4 && quantized[0].rows == 480 && quantized[2].cols == 320);
+  // [OCV] Detector::addTemplate spelled out through Modality::process / QuantizedPyramid, the way upstream implements it:
+  // the extracted templates are the stored ones before cropTemplates shifted them by the bounding-box origin, and
+  // quantize() is the (masked) quantised image match() reports for the same mask.
+  std::vector<cv::Mat> masks(2, mask), masked_q;
+  det->match(sources, 90.f, again, std::vector<String>(), masked_q, masks);
+  const size_t M = det->getModalities().size();
+  for (size_t m = 0; m < M; ++m) {
+    cv::Ptr<cv::linemod::QuantizedPyramid> qp = det->getModalities()[m]->process(sources[m], mask);
+    for (int l = 0; l < det->pyramidLevels(); ++l) {
+      if (l > 0) qp->pyrDown();
+      cv::Mat q;
+      qp->quantize(q);
+      const cv::Mat& want = masked_q[(size_t)l * M + m];
+      REQUIRE(q.rows == (rows >> l) && q.cols == (cols >> l) && want.rows == q.rows && want.cols == q.cols);
+      for (int y = 0; y < q.rows; ++y) REQUIRE(std::memcmp(q.data + (size_t)y * q.step[0], want.data + (size_t)y * want.step[0], (size_t)q.cols) == 0);
+      cv::linemod::Template t;
+      REQUIRE(qp->extractTemplate(t) && t.width == -1 && t.height == -1 && t.pyramid_level == l);
+      const cv::linemod::Template& stored = det->getTemplates("obj", 0)[(size_t)l * M + m];
+      REQUIRE(t.features.size() == stored.features.size() && !t.features.empty());
+      for (size_t k = 0; k < t.features.size(); ++k)
+        REQUIRE(t.features[k].x == stored.features[k].x + (bb.x >> l) && t.features[k].y == stored.features[k].y + (bb.y >> l) &&
+                t.features[k].label == stored.features[k].label);
+    }
+  }
+  // Modality::write / create(FileNode) round trip
+  {
+    cv::FileStorage out(dir + "/modality.yml", cv::FileStorage::WRITE);
+    out << "m" << "{";
+    det->getModalities()[1]->write(out);
+    out << "}";
+    out.release();
+    cv::FileStorage in(dir + "/modality.yml", cv::FileStorage::READ);
+    cv::Ptr<cv::linemod::Modality> back = cv::linemod::Modality::create(in["m"]);
+    REQUIRE(back->name() == "DepthNormal" && back->desc().extract_threshold == det->getModalities()[1]->desc().extract_threshold);
+  }
   std::printf("ok gpu (%zu matches)\n", matches.size());
   return 0;
 }

@@ -69,6 +69,10 @@ class Mat {
   Mat(int r, int c, int type, void* ext, size_t st = 0) : data(static_cast<uchar*>(ext)), rows(r), cols(c), type_(type) {
     step.s = st ? st : (size_t)c * elemSize();
   }
+  void create(int r, int c, int type) {
+    if (data && r == rows && c == cols && type == type_) return;
+    *this = Mat(r, c, type);
+  }
   int type() const { return type_; }
   bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
   size_t elemSize() const { return (size_t)(((type_ >> 3) & 7) + 1) * ((type_ & 7) == CV_16U ? 2 : 1); }

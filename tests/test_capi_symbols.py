@@ -107,6 +107,31 @@ def test_template_generation_fails_loudly_without_gpu():
         assert e.value.code == _capi.LM_E_CUDA, str(e.value)
 
 
+def test_modality_process_fails_loudly_without_a_gpu_and_checks_arguments():
+    """Modality::process quantises on the GPU: no CPU path; argument errors are reported before any device work."""
+    import torch
+    from linemod_pose_estimation_b200 import ColorGradient, DepthNormal, process
+    bgr = np.zeros((96, 128, 3), np.uint8)
+    with pytest.raises(LinemodError) as e:
+        process(ColorGradient(), bgr, np.zeros((90, 128), np.uint8))       # mask.size() != src.size()
+    assert e.value.code == _capi.LM_E_INVALID
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    for mod, src in ((ColorGradient(), bgr), (DepthNormal(), np.zeros((96, 128), np.uint16))):
+        with pytest.raises(LinemodError) as e:
+            process(mod, src)
+        assert e.value.code == _capi.LM_E_CUDA, str(e.value)
+
+
+def test_device_group_grid_argument_check():
+    import ctypes as C
+    det = Detector()
+    h = C.c_void_p()
+    devs = (C.c_int * 3)(0, 0, 0)
+    assert _capi.lib().lm_group_create_grid(det._h, devs, 3, 2, C.byref(h)) == _capi.LM_E_INVALID   # 2 does not divide 3
+    assert b"divide" in _capi.lib().lm_last_error()
+
+
 def test_device_group_fails_loudly_without_a_gpu():
     """lm_group_create has no CPU path either: without a CUDA device it returns LM_E_CUDA."""
     import ctypes as C

@@ -342,6 +342,42 @@ def test_add_template_on_gpu_matches_oracle():
             assert np.array_equal(a[3], b[3])
 
 
+def test_modality_process_and_quantized_pyramid_equal_the_oracle():
+    """cv::linemod::Modality::process -> QuantizedPyramid::{quantize, extractTemplate, pyrDown} ([OCV] linemod.cpp), the
+    surface under addTemplate and match: per level the masked quantised image and the uncropped template."""
+    from linemod_pose_estimation_b200 import ColorGradient, DepthNormal, process
+    kinds, T = ("cg", "dn"), (5, 8, 8)
+    orc = O.OracleDetector(common.oracle_modalities(kinds), T)
+    mods = (ColorGradient(), DepthNormal())
+    cases = [(b, d, m) for (b, d, m) in common.rendered_views(4, 77, canvas=(240, 256))]
+    scene_b, scene_d, _ = synth.compose_scene(11, [], rows=120, cols=160)
+    cases.append((scene_b, scene_d, None))                            # no mask: the whole image
+    flat = (np.full((96, 128, 3), 90, np.uint8), np.full((96, 128), 800, np.uint16), None)
+    cases.append(flat)                                                # nothing to extract: extractTemplate returns false
+    extracted = 0
+    for (bgr, depth, mask) in cases:
+        for m, src in enumerate((bgr, depth)):
+            qp = process(mods[m], src, mask, levels=3)
+            for level in range(3):
+                if level > 0:
+                    qp.pyrDown()
+                want_q, want_ok, want_t = orc.modality_process(m, src, mask, level)
+                got_q = qp.quantize()
+                assert got_q.shape == want_q.shape and np.array_equal(got_q, want_q), (m, level)
+                ok, t = qp.extractTemplate()
+                assert ok == want_ok, (m, level)
+                if ok:
+                    extracted += 1
+                    assert t[:3] == want_t[:3] == (-1, -1, level) and np.array_equal(t[3], want_t[3]), (m, level)
+    assert extracted >= 16
+    qp = process(mods[0], flat[0], None, levels=2)
+    qp.pyrDown()
+    with pytest.raises(LinemodError):
+        qp.pyrDown()
+    with pytest.raises(LinemodError):
+        process(mods[1], flat[0])                                    # DepthNormal needs CV_16UC1
+
+
 def test_batch_equals_single_and_quantized_images(tmp_path):
     orc, det, views = _pair(n_views=6, n_random=40, seed=59)
     frames = [list(synth.compose_scene(2000 + i, views[:4])[:2]) for i in range(5)]

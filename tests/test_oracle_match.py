@@ -151,3 +151,25 @@ def test_wraparound_positions_are_scored():
         a = ((y % 8) * 8 + x % 8) * W * H + (y // 8) * W + x // 8
         want += int(lm[label, a + j])
     assert flat[j] == want
+
+
+def test_modality_process_is_add_template_before_cropping():
+    """orc_modality_process (Modality::process + pyrDown + quantize / extractTemplate) against orc_add_template: the stored
+    templates are the extracted ones shifted by the bounding-box origin, and quantize() is the masked QUANTIZED tap."""
+    kinds, T = ("cg", "dn"), (5, 8)
+    det = O.OracleDetector(common.oracle_modalities(kinds), T)
+    checked = 0
+    for (bgr, depth, mask) in common.rendered_views(4, 91, canvas=(240, 240)):
+        tid, bb = det.add_template([bgr, depth], "obj", mask)
+        det.build_front([bgr, depth], [mask, mask])
+        for m, src in enumerate((bgr, depth)):
+            for level in range(2):
+                q, ok, t = det.modality_process(m, src, mask, level)
+                assert np.array_equal(q, det.fetch(O.Stage.QUANTIZED, level, m))
+                assert ok == (tid >= 0) or tid < 0
+                if tid >= 0:
+                    stored = det.get_template("obj", tid)[level * 2 + m]
+                    assert t[:3] == (-1, -1, level)
+                    assert np.array_equal(t[3] - np.array([bb[0] >> level, bb[1] >> level, 0]), stored[3])
+                    checked += 1
+    assert checked >= 8
