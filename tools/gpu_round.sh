@@ -25,6 +25,9 @@ ncu --set full --clock-control none --import-source on -k regex:$K -s 12 -c 2 -f
     python bench.py --steps 64 --warmup 8 --no-cpu-baseline > $O/ncu_full_${K}_$TAG.log 2>&1; echo "ncu full $K rc=$?"
 done
 unset LM_BENCH_TEMPLATE_CACHE
+for C in 3 4 5; do
+python bench.py --config $C --steps 64 --warmup 8 --no-cpu-baseline > $O/bench_c${C}_$TAG.log 2> $O/bench_c${C}_$TAG.err; echo "config $C rc=$?"; tail -c 600 $O/bench_c${C}_$TAG.log; echo
+done
 python tools/trainbench.py > $O/trainbench_$TAG.log 2>&1; echo "trainbench rc=$?"; cat $O/trainbench_$TAG.log
 fi
 tail -c 1500 $O/bench_driver_$TAG.log; echo; tail -c 3000 $O/bench_$TAG.log
