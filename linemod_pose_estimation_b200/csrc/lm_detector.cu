@@ -116,9 +116,13 @@ static bool level_needs_bytes(const lm_detector* d, const LevelGeom& g) { return
 static int ensure_lm_ws(lm_detector* d, Lane& ln, int rows, int cols, int frames) {
   const int L = d->model.levels(), M = d->model.M();
   bool bytes_ok = true;
+  // refinement levels (every level above the coarsest) are column-blocked when their geometry allows it
+  auto tiled_level = [&](int l, int W, int H) { return d->refine_tiled != 0 && l < L - 1 && W % 16 == 0 && H >= 16; };
   if (ln.lm_ready && ln.rows == rows && ln.cols == cols && (int)ln.geom.size() == L)
-    for (int l = 0; l < L; ++l)
+    for (int l = 0; l < L; ++l) {
       if (level_needs_bytes(d, ln.geom[l]) && ln.lmem[l].frames < (level_nibble_aligned(ln.geom[l]) ? 1 : ln.frames)) bytes_ok = false;
+      if ((ln.geom[l].Hh != 0) != tiled_level(l, ln.geom[l].W, ln.geom[l].H)) bytes_ok = false;   // option changed: rebuild
+    }
   if (ln.lm_ready && ln.rows == rows && ln.cols == cols && (int)ln.geom.size() == L && ln.frames >= frames && bytes_ok) return LM_OK;
   std::vector<LevelGeom> geom(L);
   for (int l = 0; l < L; ++l) {
@@ -133,6 +137,8 @@ static int ensure_lm_ws(lm_detector* d, Lane& ln, int rows, int cols, int frames
     if (g.cols > 4095 || g.rows > 4095) return lm_fail(LM_E_INVALID, "images larger than 4095 px are not supported");
     g.W = g.cols / g.T; g.H = g.rows / g.T;
     g.plane_stride = plane_stride_of(g.T, g.W, g.H);
+    g.Hh = tiled_level(l, g.W, g.H) ? g.H + 16 : 0;
+    g.nib_plane = g.Hh ? lmk::tiled_plane_stride(g.T, g.W, g.H) : g.plane_stride;
   }
   // everything that reads or wrote the old buffers must be done (callers' streams included) before they move
   if (lane_quiesce(ln) != LM_OK) return LM_E_CUDA;
@@ -146,8 +152,8 @@ static int ensure_lm_ws(lm_detector* d, Lane& ln, int rows, int cols, int frames
       if (ln.lmem[l].ensure(bytes, level_nibble_aligned(geom[l]) ? 1 : frames) != LM_OK) return LM_E_CUDA;
       CU(cudaMemsetAsync(ln.lmem[l].buf.p, 0, ln.lmem[l].bytes(), ln.stream));  // zero tails (and slack) once per geometry
     }
-    if (ln.lmn[l].ensure(bytes / 2, frames) != LM_OK) return LM_E_CUDA;
-    CU(cudaMemsetAsync(ln.lmn[l].buf.p, 0, ln.lmn[l].bytes(), ln.stream));
+    if (ln.lmn[l].ensure(((size_t)M * 8 * geom[l].nib_plane + kLmSlack) / 2, frames) != LM_OK) return LM_E_CUDA;
+    CU(cudaMemsetAsync(ln.lmn[l].buf.p, 0, ln.lmn[l].bytes(), ln.stream));   // zero tails, halo rows of the last phase, slack
   }
   CU(cudaStreamSynchronize(ln.stream));
   ln.geom.swap(geom);
@@ -339,8 +345,9 @@ static int run_front(lm_detector* d, Lane& ln, int grid_frames, cudaStream_t s) 
       e.response = taps ? ln.response[l][m].as<uint8_t>() : nullptr;
       e.lm = byt[l] ? ln.lmem[l].as<uint8_t>() + (size_t)m * 8 * g.plane_stride : nullptr;
       e.lm_stride = ln.lmem[l].frames > 1 ? ln.lmem[l].stride : 0;
-      e.lm_nib = direct[l] ? ln.lmn[l].as<uint8_t>() + (size_t)m * 4 * g.plane_stride : nullptr;
+      e.lm_nib = direct[l] ? ln.lmn[l].as<uint8_t>() + (size_t)m * 4 * g.nib_plane : nullptr;
       e.lm_nib_stride = ln.lmn[l].stride;
+      e.nib_plane = g.nib_plane; e.tiled_Hh = g.Hh;
       e.count_bits = l == L - 1;
       e.plane_stride = g.plane_stride;
       e.rows = g.rows; e.cols = g.cols; e.T = g.T; e.W = g.W; e.H = g.H; e.level = l; e.modality = m; e.mask_cols0 = ln.cols;
@@ -664,8 +671,8 @@ static int enqueue_match(lm_detector* d, Lane& ln, const Pack::Plan& plan, const
     rp.level[l].frame_stride = ln.lmn[l].stride;
     rp.level[l].tpl = pk.rtpl[l].as<RefineTpl>();
     rp.level[l].feats = pk.rfeats[l].as<uint32_t>();
-    rp.level[l].plane_stride = g.plane_stride;
-    rp.level[l].rows = g.rows; rp.level[l].cols = g.cols; rp.level[l].T = g.T; rp.level[l].W = g.W;
+    rp.level[l].plane_stride = g.nib_plane;
+    rp.level[l].rows = g.rows; rp.level[l].cols = g.cols; rp.level[l].T = g.T; rp.level[l].W = g.W; rp.level[l].Hh = g.Hh;
   }
   launch_refine(rp, pk.ctpl.as<CoarseTpl>(), ln.cand.as<Cand>(), ln.cand_cap, ln.ctl.as<BatchCtl>(), ln.result.as<uint8_t>(),
                 ln.result.stride, ln.out_cap, s);
@@ -1413,6 +1420,7 @@ int lm_set_option(lm_detector* d, const char* key, int value) {
   else if (k == "timing") d->timing = value;
   else if (k == "prune") d->prune = value;
   else if (k == "mod_order") d->mod_order = value & 3;
+  else if (k == "refine_tiled") d->refine_tiled = value != 0;   // takes effect with the next request (workspace rebuilt)
   else if (k == "graphs") d->graphs = value;
   else if (k == "batch_frames") {
     if (value < 1 || value > LM_MAX_BATCH) return lm_fail(LM_E_INVALID, "batch_frames must be 1..%d", LM_MAX_BATCH);
@@ -1971,6 +1979,53 @@ int lm_level_geometry(lm_detector* d, int level, int32_t out[5], size_t* plane_s
   return LM_OK;
 }
 
+// The nibble planes of (level, modality) of frame 0 in the reference's flat order, two positions per byte: a plain download,
+// or -- for a column-blocked refinement level -- a download put back into linearize's order on the host (parity taps only).
+static int fetch_flat_nibbles(Lane& ln, int level, int modality, std::vector<uint8_t>& flat) {
+  const LevelGeom& g = ln.geom[level];
+  flat.assign(4 * g.plane_stride, 0);
+  if (cudaStreamSynchronize(ln.stream) != cudaSuccess) return lm_fail(LM_E_CUDA, "debug fetch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  const uint8_t* src = ln.lmn[level].as<uint8_t>() + (size_t)modality * 4 * g.nib_plane;
+  if (!g.Hh) {
+    if (cudaMemcpy(flat.data(), src, flat.size(), cudaMemcpyDeviceToHost) != cudaSuccess)
+      return lm_fail(LM_E_CUDA, "debug fetch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return LM_OK;
+  }
+  std::vector<uint8_t> blocked(4 * g.nib_plane);
+  if (cudaMemcpy(blocked.data(), src, blocked.size(), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return lm_fail(LM_E_CUDA, "debug fetch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  const size_t WH = (size_t)g.W * g.H;
+  for (int o = 0; o < 8; ++o) {
+    const uint8_t* b = blocked.data() + (size_t)o * (g.nib_plane / 2);
+    uint8_t* f = flat.data() + (size_t)o * (g.plane_stride / 2);
+    for (int ph = 0; ph < g.T * g.T; ++ph)
+      for (int r = 0; r < g.H; ++r)
+        for (int c = 0; c < g.W; ++c) {
+          const size_t ti = tiled_nibble_index(g.W, g.Hh, ph, r, c), fi = (size_t)ph * WH + (size_t)r * g.W + c;
+          const uint8_t v = (uint8_t)((b[ti >> 1] >> (4 * (ti & 1))) & 15);
+          f[fi >> 1] |= (uint8_t)(v << (4 * (fi & 1)));
+        }
+    // the halo rows must repeat the next phase's first rows (zero below the last phase) and the plane must end in zeros:
+    // a violation is reported as a value no response can have, so that the parity tests see it
+    bool ok = true;
+    for (int ph = 0; ph < g.T * g.T && ok; ++ph)
+      for (int r = 0; r < 16 && ok; ++r)
+        for (int c = 0; c < g.W && ok; ++c) {
+          const size_t hi = tiled_nibble_index(g.W, g.Hh, ph, g.H + r, c);
+          const uint8_t hv = (uint8_t)((b[hi >> 1] >> (4 * (hi & 1))) & 15);
+          uint8_t want = 0;
+          if (ph + 1 < g.T * g.T) {
+            const size_t ni = tiled_nibble_index(g.W, g.Hh, ph + 1, r, c);
+            want = (uint8_t)((b[ni >> 1] >> (4 * (ni & 1))) & 15);
+          }
+          ok = hv == want;
+        }
+    for (size_t i = (size_t)g.T * g.T * g.W * g.Hh; i < g.nib_plane && ok; ++i) ok = ((b[i >> 1] >> (4 * (i & 1))) & 15) == 0;
+    if (!ok) f[0] |= 0x0f;
+  }
+  return LM_OK;
+}
+
 long lm_debug_fetch(lm_detector* d, int stage, int level, int modality, void* dst) {
   Lane& ln = d->lane[0];
   if (!ln.front_valid) return lm_fail(LM_E_STATE, "no front end built");
@@ -1995,10 +2050,8 @@ long lm_debug_fetch(lm_detector* d, int stage, int level, int modality, void* ds
       bytes = 8 * g.plane_stride;
       if (!ln.bytes_valid[level]) {  // only the packed planes exist: unpack them
         if (dst) {
-          std::vector<uint8_t> packed(bytes / 2);
-          if (cudaStreamSynchronize(ln.stream) != cudaSuccess ||
-              cudaMemcpy(packed.data(), ln.lmn[level].as<uint8_t>() + (size_t)modality * 4 * g.plane_stride, bytes / 2, cudaMemcpyDeviceToHost) != cudaSuccess)
-            return lm_fail(LM_E_CUDA, "debug fetch failed: %s", cudaGetErrorString(cudaGetLastError()));
+          std::vector<uint8_t> packed;
+          if (fetch_flat_nibbles(ln, level, modality, packed) != LM_OK) return LM_E_CUDA;
           uint8_t* o = static_cast<uint8_t*>(dst);
           for (size_t i = 0; i < bytes / 2; ++i) { o[2 * i] = packed[i] & 15; o[2 * i + 1] = packed[i] >> 4; }
         }
@@ -2007,7 +2060,16 @@ long lm_debug_fetch(lm_detector* d, int stage, int level, int modality, void* ds
       src = ln.lmem[level].as<uint8_t>() + (size_t)modality * 8 * g.plane_stride; break;
     case LM_STAGE_LINEAR_PACKED:
       if (!ln.nibbles_valid[level]) return lm_fail(LM_E_STATE, "level %d has no packed planes", level);
-      src = ln.lmn[level].as<uint8_t>() + (size_t)modality * 4 * g.plane_stride; bytes = 4 * g.plane_stride; break;
+      bytes = 4 * g.plane_stride;
+      if (g.Hh) {   // column-blocked on the device: handed out in the reference's flat order
+        if (dst) {
+          std::vector<uint8_t> packed;
+          if (fetch_flat_nibbles(ln, level, modality, packed) != LM_OK) return LM_E_CUDA;
+          std::memcpy(dst, packed.data(), bytes);
+        }
+        return (long)bytes;
+      }
+      src = ln.lmn[level].as<uint8_t>() + (size_t)modality * 4 * g.plane_stride; break;
     default: return lm_fail(LM_E_INVALID, "unknown stage %d", stage);
   }
   if (dst) {

@@ -92,7 +92,9 @@ struct FrameBuf {
 
 struct LevelGeom {
   int rows = 0, cols = 0, T = 0, W = 0, H = 0;
-  size_t plane_stride = 0;
+  size_t plane_stride = 0;   // positions per orientation plane in the reference's flat order (byte planes, parity taps)
+  int Hh = 0;                // != 0: the level's nibble planes are column-blocked (lm_kernels.cuh tiled_nibble_index), H + 16
+  size_t nib_plane = 0;      // positions per orientation plane of the nibble planes (plane_stride, or tiled_plane_stride)
 };
 // Nibble-packed rows of a level start on 32-bit words when W and W*H are multiples of 8 (one word = 8 positions).
 static inline bool level_nibble_aligned(const LevelGeom& g) { return (g.W % 8) == 0 && ((size_t)g.W * g.H) % 8 == 0; }
@@ -326,6 +328,7 @@ struct lm_detector {
   int batch_frames = 8;  // frames per chunk on the batched paths (lm_match_batch*, lm_match_device_stream)
   int batch_lanes = 4;   // chunks in flight on the batched host path
   int mod_order = 2;  // coarse kernel: 0 = modalities in template order, 1 = reversed, 2 = chosen per frame (default)
+  int refine_tiled = 1;  // refinement levels with W % 16 == 0 and H >= 16 keep their nibble planes column-blocked
   std::vector<std::string> class_id_cache;
 };
 

@@ -578,8 +578,9 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
   const int row_bytes = NWO * 4;
   const size_t WH = (size_t)W * H;
   const int ncell = min(SP_CW, W - c0);
-  if (E.lm_nib != nullptr) {  // coarsest level, nibble-packed: one word = 8 consecutive cells of one (orientation, phase) row
-    const size_t nib_stride = (size_t)E.plane_stride / 2;
+  if (E.lm_nib != nullptr) {  // nibble-packed planes: one word = 8 consecutive cells of one (orientation, phase) row
+    const size_t nib_stride = (size_t)E.nib_plane / 2;
+    const int Hh = E.tiled_Hh;  // refinement levels: column-blocked layout (lm_kernels.cuh tiled_nibble_index)
     for (int it = tid; it < T * T * (SP_CW / 8); it += 256) {
       const int b8 = it & (SP_CW / 8 - 1), g = it / (SP_CW / 8);
       if (b8 * 8 >= ncell) continue;
@@ -595,12 +596,21 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
       uint32_t oe[4], oo[4];
       transpose4x4(ev, oe);  // oe[k]: orientation 2k, nibbles = cells 0..7
       transpose4x4(od, oo);  // oo[k]: orientation 2k+1
-      const size_t n0 = (size_t)g * WH + (size_t)a * W + c0 + b8 * 8;  // nibble index inside the plane (multiple of 8)
+      // nibble index inside the plane (multiple of 8)
+      const size_t n0 = Hh ? tiled_nibble_index(W, Hh, g, a, c0 + b8 * 8) : (size_t)g * WH + (size_t)a * W + c0 + b8 * 8;
       uint8_t* dst = E.lm_nib + (size_t)frame * E.lm_nib_stride + n0 / 2;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         *reinterpret_cast<uint32_t*>(dst + (size_t)(2 * k) * nib_stride) = oe[k];
         *reinterpret_cast<uint32_t*>(dst + (size_t)(2 * k + 1) * nib_stride) = oo[k];
+      }
+      if (Hh && a < 16 && g > 0) {  // rows 0..15 of a phase are also the rows H..H+15 below the previous phase
+        uint8_t* halo = dst - ((size_t)W * Hh - (size_t)H * 16) / 2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          *reinterpret_cast<uint32_t*>(halo + (size_t)(2 * k) * nib_stride) = oe[k];
+          *reinterpret_cast<uint32_t*>(halo + (size_t)(2 * k + 1) * nib_stride) = oo[k];
+        }
       }
     }
   }

@@ -53,9 +53,25 @@ struct RefineLevel {
   unsigned long long frame_stride;        // bytes between the planes of consecutive frames of the chunk
   const RefineTpl* tpl;
   const uint32_t* feats;                  // (x + 4096) | (y + 4096) << 13 | label << 26
-  unsigned long long plane_stride;
+  unsigned long long plane_stride;        // positions (nibbles) per orientation plane, in the layout the level is stored in
   int rows, cols, T, W;
+  int Hh;                                 // 0: flat planes (the reference's linearize order).  Otherwise the COLUMN-BLOCKED
+                                          // layout of refinement levels (see tiled_nibble_index): rows per column block
 };
+
+// Column-blocked layout of a refinement level's nibble planes (levels with W % 16 == 0 and H >= 16).  similarityLocal
+// reads 16 x 16 windows: in the reference's flat order the 16 rows of a window lie W/2 bytes apart (16 cache lines per
+// feature); here a (T^2 phase) matrix is cut into blocks of 16 columns and the rows of a block are stored back to back,
+// 8 bytes each, so the 16 rows of a window's 16-column chunk are 128 contiguous bytes.  A phase holds W/16 column blocks of
+// Hh = H + 16 rows: rows H .. H+15 repeat rows 0 .. 15 of the NEXT phase (zero after the last one), which is what the
+// reference's flat over-read past the bottom of a phase matrix sees; a window's second chunk past the
+// last column block is column block 0 one row down, again the flat order's successor.
+__host__ __device__ inline size_t tiled_nibble_index(int W, int Hh, int phase, int row, int col) {
+  return (size_t)phase * ((size_t)W * Hh) + (size_t)(col >> 4) * ((size_t)Hh * 16) + (size_t)row * 16 + (size_t)(col & 15);
+}
+static inline size_t tiled_plane_stride(int T, int W, int H) {   // nibbles per orientation plane incl. a 256-nibble zero run
+  return ((size_t)T * T * W * (size_t)(H + 16) + 256 + 31) & ~(size_t)31;
+}
 
 struct RefineParams {
   RefineLevel level[LM_MAX_LEVELS];       // index = pyramid level (only 0 .. L-2 used)
@@ -132,7 +148,9 @@ struct SpreadEntry {
   uint8_t* spread;       // parity tap or null (frame 0 only)
   uint8_t* response;     // parity tap or null (frame 0 only)
   uint8_t* lm;           // this modality's 8 orientation byte planes, or null when only lm_nib is needed
-  uint8_t* lm_nib;       // this modality's 8 nibble-packed planes (plane_stride / 2 bytes each), or null
+  uint8_t* lm_nib;       // this modality's 8 nibble-packed planes (nib_plane / 2 bytes each), or null
+  unsigned long long nib_plane;  // positions per orientation plane of lm_nib (plane_stride, or tiled_plane_stride)
+  int tiled_Hh;          // lm_nib is column-blocked with this many rows per block (0: flat), see tiled_nibble_index
   int count_bits;        // coarsest level: ctl->mod_bits[frame][modality] += orientation bits set in the spread image;
                          // the coarse kernel starts with the modality that has fewer (lower responses, earlier pruning)
   unsigned long long plane_stride;

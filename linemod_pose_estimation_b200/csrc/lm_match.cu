@@ -277,7 +277,11 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarsePa
     uint32_t ticket = 0;
     if (has_next && lane == 0) ticket = atomicAdd(&ctl->next_tile, 1u);
 
-    const uint8_t* __restrict__ lmn = P.lmn + (size_t)cur_frame * P.lmn_stride + lane_byte;  // this lane's chunk of every window
+    // this lane's chunk of every window.  The empty asm pins the pointer in a register pair: left alone, ptxas recomputes
+    // frame * stride + lane offset + base for every feature (six address instructions per window instead of three).
+    unsigned long long lane_base = (unsigned long long)P.lmn + (unsigned long long)cur_frame * P.lmn_stride + lane_byte;
+    asm volatile("" : "+l"(lane_base));
+    const uint8_t* __restrict__ lmn = reinterpret_cast<const uint8_t*>(lane_base);
     // bit 8 of `prune`: sum the modalities in reverse order; bit 9: decide per frame from the front end's counters
     const bool mod_reversed = (prune & 0x200) ? (ctl->mod_bits[cur_frame][M - 1] < ctl->mod_bits[cur_frame][0]) : (prune & 0x100) != 0;
     const uint32_t item = sr[0], tg = sr[1], nfq = sr[2], order = sr[6];
@@ -425,20 +429,155 @@ __device__ __forceinline__ int min_passing_score(float threshold, int nf) {
   return s;
 }
 
+// Where a feature's 16 x 16 window starts, for one lane of the address phase.  Flat planes: the nibble index of the
+// window's first position (rows W apart).  Column-blocked planes (RefineLevel::Hh != 0): two words -- byte offsets of the
+// window's two 16-column chunks at row 0 (rows 8 bytes apart) with the nibble shift (0..15) in their low bits:
+// w0 = offset0 | (shift & 7), w1 = offset1 | (shift >> 3).  Features outside the image point at the plane's zero run.
+template <bool TILED>
+__device__ __forceinline__ void refine_feature_address(const RefineLevel& L, uint32_t pk, int offset_x, int offset_y, uint32_t WH,
+                                                       uint32_t zero_run, uint32_t* s_addr, int i) {
+  const int T = L.T, W = L.W;
+  const int fx = (int)(pk & 0x1fffu) - 4096 + offset_x, fy = (int)((pk >> 13) & 0x1fffu) - 4096 + offset_y;
+  const bool inside = fx >= 0 && fy >= 0 && fx < L.cols && fy < L.rows;  // "Discard feature if out of bounds"
+  const uint32_t label = pk >> 26;
+  if (!TILED) {
+    const uint32_t addr = label * (uint32_t)L.plane_stride + (uint32_t)((fy % T) * T + (fx % T)) * WH +
+                          (uint32_t)(fy / T) * (uint32_t)W + (uint32_t)(fx / T);
+    s_addr[i] = inside ? addr : zero_run;
+  } else {
+    const uint32_t Hh = (uint32_t)L.Hh, block_bytes = Hh * 8u, phase_bytes = (uint32_t)W * Hh / 2u;
+    const uint32_t col = (uint32_t)(fx / T), row = (uint32_t)(fy / T), cb = col >> 4, sh = col & 15u;
+    const uint32_t phase0 = label * (uint32_t)(L.plane_stride / 2) + (uint32_t)((fy % T) * T + (fx % T)) * phase_bytes;
+    uint32_t b0 = phase0 + cb * block_bytes + row * 8u;
+    // second chunk: the next column block, or -- past the last one -- column block 0 one row down (the flat order's successor)
+    uint32_t b1 = (cb + 1u < ((uint32_t)W >> 4)) ? b0 + block_bytes : phase0 + (row + 1u) * 8u;
+    uint32_t s = sh;
+    if (!inside) { b0 = b1 = zero_run; s = 0; }
+    s_addr[2 * i] = b0 | (s & 7u);
+    s_addr[2 * i + 1] = b1 | (s >> 3);
+  }
+}
+
 // Refinement on nibble-packed planes, ONE BLOCK PER CANDIDATE (few candidates: lowest latency).  A patch row is 16 positions =
 // 8 bytes at an arbitrary nibble offset: lane r (< 16) and lane r + 16 load the two aligned 8-byte chunks the row spans
-// -- one LDG.64 per feature and lane, 16 cache lines per warp instruction instead of the 48 the byte kernel touches --
-// lane r takes the second chunk from its partner with two shuffles, realigns with two funnel shifts and sums up to
-// three features in the nibble domain before spreading even / odd nibbles into byte accumulators.  Same block / warp
-// decomposition, argmax and bookkeeping as k_refine.
+// -- one LDG.64 per feature and lane -- lane r takes the second chunk from its partner with two shuffles, realigns with two
+// funnel shifts and sums up to three features in the nibble domain before spreading even / odd nibbles into byte
+// accumulators.  One level of one candidate; returns through s_state (x, y, alive, best_score).
+template <bool TILED>
+__device__ __forceinline__ void refine_block_level(const RefineParams& P, const RefineLevel& L, const RefineTpl* rtp, uint32_t frame,
+                                                   float threshold, int x, int y, uint32_t (*s_part)[16][4], uint32_t* s_addr,
+                                                   int* s_state) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int prow = lane & 15, half = lane >> 4;
+  const int T = L.T, W = L.W;
+  const int off = T / 2 + (T % 2 - 1);
+  const int offset_x = (x / T - 8) * T, offset_y = (y / T - 8) * T;
+  const uint32_t WH = (uint32_t)W * (uint32_t)(L.rows / T);
+  // the tail of every plane is zero (App. D-2 padding; 128 zero bytes close a column-blocked plane)
+  const uint32_t zero_run = TILED ? (uint32_t)(L.plane_stride / 2) - 128u : (uint32_t)L.plane_stride - 32u;
+  int n_all = 0;
+  for (int m = 0; m < P.M; ++m) n_all += rtp->cnt[m];
+  const uint32_t* fp = L.feats + rtp->feat_begin;
+  for (int i = threadIdx.x; i < n_all; i += kRefineWarps * 32)
+    refine_feature_address<TILED>(L, fp[i], offset_x, offset_y, WH, zero_run, s_addr, i);
+  __syncthreads();
+  const uint32_t row_off = (uint32_t)(prow * W);
+  uint32_t tot_e[2] = {0, 0}, tot_o[2] = {0, 0};  // u8 x 4: even / odd columns 0..7 and 8..15 of row prow (<= 16 * 4 per warp)
+  int begin = 0;
+  for (int m = 0; m < P.M; ++m) {
+    const uint8_t* lmm = L.lmn + (size_t)frame * L.frame_stride + (size_t)m * 4 * L.plane_stride + (TILED ? prow * 8 : 0);
+    const int n = rtp->cnt[m];  // <= 63: at most 8 features per warp
+    uint2 w[8];
+    uint32_t sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int f = warp + kRefineWarps * k;
+      if (TILED) {
+        const uint2 a = f < n ? reinterpret_cast<const uint2*>(s_addr)[begin + f] : make_uint2(zero_run, zero_run);
+        sh[k] = (a.x & 7u) | ((a.y & 1u) << 3);
+        w[k] = ldg64(lmm + ((half ? a.y : a.x) & ~7u));
+      } else {
+        const uint32_t base = f < n ? s_addr[begin + f] : zero_run;
+        const uint32_t nidx = base + (base == zero_run ? 0u : row_off);   // nibble index of this row's first position
+        sh[k] = nidx & 15u;
+        w[k] = ldg64(lmm + (size_t)((nidx >> 4) + (uint32_t)half) * 8u);
+      }
+    }
+    uint32_t nib0 = 0, nib1 = 0;
+    int in_group = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t w2 = __shfl_down_sync(kFull, w[k].x, 16), w3 = __shfl_down_sync(kFull, w[k].y, 16);
+      const bool hi = sh[k] >= 8u;                 // window starts in the second word of the first chunk
+      const uint32_t a = hi ? w[k].y : w[k].x, b = hi ? w2 : w[k].y, cc = hi ? w3 : w2;
+      const uint32_t bits = (sh[k] & 7u) * 4u;
+      nib0 += __funnelshift_r(a, b, bits);
+      nib1 += __funnelshift_r(b, cc, bits);
+      if (++in_group == 3 || k == 7) {             // <= 3 features per nibble sum (3 * 4 < 16)
+        tot_e[0] += nib0 & 0x0f0f0f0fu; tot_o[0] += (nib0 >> 4) & 0x0f0f0f0fu;
+        tot_e[1] += nib1 & 0x0f0f0f0fu; tot_o[1] += (nib1 >> 4) & 0x0f0f0f0fu;
+        nib0 = nib1 = 0; in_group = 0;
+      }
+    }
+    begin += n;
+  }
+  if (half == 0) {
+    s_part[warp][prow][0] = tot_e[0]; s_part[warp][prow][1] = tot_o[0];
+    s_part[warp][prow][2] = tot_e[1]; s_part[warp][prow][3] = tot_o[1];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t best_key = 0;
+    if (half == 0) {
+      // u16 totals over the 8 warps: [j][0] = bytes 0, 2 of word j, [j][1] = bytes 1, 3
+      uint32_t sum[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { sum[j][0] = 0; sum[j][1] = 0; }
+#pragma unroll
+      for (int w2 = 0; w2 < kRefineWarps; ++w2)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t v = s_part[w2][prow][j];
+          sum[j][0] += v & 0x00ff00ffu;
+          sum[j][1] += (v >> 8) & 0x00ff00ffu;
+        }
+      // word j: j = 0 even columns 0..7, 1 odd columns 0..7, 2 even columns 8..15, 3 odd columns 8..15;
+      // byte b of a word is column 8 * (j / 2) + 2 * b + (j & 1)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t src = sum[j][b & 1];
+          const uint32_t sc = (b & 2) ? (src >> 16) : (src & 0xffffu);
+          const int col = 8 * (j >> 1) + 2 * b + (j & 1);
+          best_key = max(best_key, (sc << 8) | (uint32_t)(255 - (prow * 16 + col)));
+        }
+    }
+    best_key = __reduce_max_sync(kFull, best_key);  // first maximum in raster order
+    if (lane == 0) {
+      const int best_score = (int)(best_key >> 8);
+      int best_r = -1, best_c = -1;
+      if (best_score > 0) {
+        int idx = 255 - (int)(best_key & 0xffu);
+        best_r = idx >> 4; best_c = idx & 15;
+      }
+      const int nfl = (int)rtp->nf;
+      float sim = __fdiv_rn(__fmul_rn((float)best_score, 100.f), (float)(4 * nfl));
+      s_state[0] = (x / T - 8 + best_c) * T + off;
+      s_state[1] = (y / T - 8 + best_r) * T + off;
+      s_state[2] = (sim < threshold) ? 0 : 1;  // [OCV] remove_if(MatchPredicate(threshold))
+      s_state[3] = best_score;
+    }
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ void refine_nib_block(const RefineParams& P, const CoarseTpl* __restrict__ ctpl,
                                                  const Cand* __restrict__ cand, uint32_t n_cands, uint8_t* results,
                                                  size_t result_stride, uint32_t out_cap, uint32_t* smem) {
   uint32_t (*s_part)[16][4] = reinterpret_cast<uint32_t (*)[16][4]>(smem);                       // [kRefineWarps][16][4]
-  uint32_t* s_addr = smem + kRefineWarps * 16 * 4;  // [kRefineMaxFeat] nibble index of each feature's patch origin
-  int* s_state = reinterpret_cast<int*>(s_addr + kRefineMaxFeat);  // x, y, alive, best_score
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int prow = lane & 15, half = lane >> 4;
+  uint32_t* s_addr = smem + kRefineWarps * 16 * 4;  // [2 * kRefineMaxFeat] window address words of each feature
+  int* s_state = reinterpret_cast<int*>(s_addr + 2 * kRefineMaxFeat);  // x, y, alive, best_score
   for (uint32_t ci = blockIdx.x; ci < n_cands; ci += gridDim.x) {
     const Cand c = cand[ci];
     const uint32_t order = c.order;
@@ -455,111 +594,13 @@ __device__ __forceinline__ void refine_nib_block(const RefineParams& P, const Co
     for (int l = P.levels - 2; l >= 0 && alive; --l) {
       const RefineLevel& L = P.level[l];
       const RefineTpl* rtp = L.tpl + c.tglob;
-      const int T = L.T, W = L.W;
-      const int border = 8 * T, off = T / 2 + (T % 2 - 1);
+      const int border = 8 * L.T;
       const int max_x = L.cols - rtp->width - border, max_y = L.rows - rtp->height - border;
       x = x * 2 + 1; y = y * 2 + 1;
       x = max(x, border); y = max(y, border);
       x = min(x, max_x); y = min(y, max_y);
-      const int offset_x = (x / T - 8) * T, offset_y = (y / T - 8) * T;
-      const uint32_t WH = (uint32_t)W * (uint32_t)(L.rows / T);
-      const uint32_t zero_run = (uint32_t)L.plane_stride - 32u;  // the tail of every plane is zero (App. D-2 padding)
-      int n_all = 0;
-      for (int m = 0; m < P.M; ++m) n_all += rtp->cnt[m];
-      const uint32_t* fp = L.feats + rtp->feat_begin;
-      for (int i = threadIdx.x; i < n_all; i += kRefineWarps * 32) {
-        const uint32_t pk = fp[i];
-        const int fx = (int)(pk & 0x1fffu) - 4096 + offset_x, fy = (int)((pk >> 13) & 0x1fffu) - 4096 + offset_y;
-        const bool inside = fx >= 0 && fy >= 0 && fx < L.cols && fy < L.rows;  // "Discard feature if out of bounds"
-        const uint32_t label = pk >> 26;
-        const uint32_t addr = label * (uint32_t)L.plane_stride + (uint32_t)((fy % T) * T + (fx % T)) * WH +
-                              (uint32_t)(fy / T) * (uint32_t)W + (uint32_t)(fx / T);
-        s_addr[i] = inside ? addr : zero_run;
-      }
-      __syncthreads();
-      const uint32_t row_off = (uint32_t)(prow * W);
-      uint32_t tot_e[2] = {0, 0}, tot_o[2] = {0, 0};  // u8 x 4: even / odd columns 0..7 and 8..15 of row prow (<= 16 * 4 per warp)
-      int begin = 0;
-      for (int m = 0; m < P.M; ++m) {
-        const uint8_t* lmm = L.lmn + (size_t)frame * L.frame_stride + (size_t)m * 4 * L.plane_stride;
-        const int n = rtp->cnt[m];  // <= 63: at most 8 features per warp
-        uint2 w[8];
-        uint32_t sh[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int f = warp + kRefineWarps * k;
-          const uint32_t base = f < n ? s_addr[begin + f] : zero_run;
-          const uint32_t nidx = base + (base == zero_run ? 0u : row_off);   // nibble index of this row's first position
-          sh[k] = nidx & 15u;
-          w[k] = ldg64(lmm + (size_t)((nidx >> 4) + (uint32_t)half) * 8u);
-        }
-        uint32_t nib0 = 0, nib1 = 0;
-        int in_group = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t w2 = __shfl_down_sync(kFull, w[k].x, 16), w3 = __shfl_down_sync(kFull, w[k].y, 16);
-          const bool hi = sh[k] >= 8u;                 // window starts in the second word of the first chunk
-          const uint32_t a = hi ? w[k].y : w[k].x, b = hi ? w2 : w[k].y, cc = hi ? w3 : w2;
-          const uint32_t bits = (sh[k] & 7u) * 4u;
-          nib0 += __funnelshift_r(a, b, bits);
-          nib1 += __funnelshift_r(b, cc, bits);
-          if (++in_group == 3 || k == 7) {             // <= 3 features per nibble sum (3 * 4 < 16)
-            tot_e[0] += nib0 & 0x0f0f0f0fu; tot_o[0] += (nib0 >> 4) & 0x0f0f0f0fu;
-            tot_e[1] += nib1 & 0x0f0f0f0fu; tot_o[1] += (nib1 >> 4) & 0x0f0f0f0fu;
-            nib0 = nib1 = 0; in_group = 0;
-          }
-        }
-        begin += n;
-      }
-      if (half == 0) {
-        s_part[warp][prow][0] = tot_e[0]; s_part[warp][prow][1] = tot_o[0];
-        s_part[warp][prow][2] = tot_e[1]; s_part[warp][prow][3] = tot_o[1];
-      }
-      __syncthreads();
-      if (warp == 0) {
-        uint32_t best_key = 0;
-        if (half == 0) {
-          // u16 totals over the 8 warps: [j][0] = bytes 0, 2 of word j, [j][1] = bytes 1, 3
-          uint32_t sum[4][2];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { sum[j][0] = 0; sum[j][1] = 0; }
-#pragma unroll
-          for (int w2 = 0; w2 < kRefineWarps; ++w2)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t v = s_part[w2][prow][j];
-              sum[j][0] += v & 0x00ff00ffu;
-              sum[j][1] += (v >> 8) & 0x00ff00ffu;
-            }
-          // word j: j = 0 even columns 0..7, 1 odd columns 0..7, 2 even columns 8..15, 3 odd columns 8..15;
-          // byte b of a word is column 8 * (j / 2) + 2 * b + (j & 1)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const uint32_t src = sum[j][b & 1];
-              const uint32_t sc = (b & 2) ? (src >> 16) : (src & 0xffffu);
-              const int col = 8 * (j >> 1) + 2 * b + (j & 1);
-              best_key = max(best_key, (sc << 8) | (uint32_t)(255 - (prow * 16 + col)));
-            }
-        }
-        best_key = __reduce_max_sync(kFull, best_key);  // first maximum in raster order
-        if (lane == 0) {
-          const int best_score = (int)(best_key >> 8);
-          int best_r = -1, best_c = -1;
-          if (best_score > 0) {
-            int idx = 255 - (int)(best_key & 0xffu);
-            best_r = idx >> 4; best_c = idx & 15;
-          }
-          const int nfl = (int)rtp->nf;
-          float sim = __fdiv_rn(__fmul_rn((float)best_score, 100.f), (float)(4 * nfl));
-          s_state[0] = (x / T - 8 + best_c) * T + off;
-          s_state[1] = (y / T - 8 + best_r) * T + off;
-          s_state[2] = (sim < threshold) ? 0 : 1;  // [OCV] remove_if(MatchPredicate(threshold))
-          s_state[3] = best_score;
-        }
-      }
-      __syncthreads();
+      if (L.Hh) refine_block_level<true>(P, L, rtp, frame, threshold, x, y, s_part, s_addr, s_state);
+      else refine_block_level<false>(P, L, rtp, frame, threshold, x, y, s_part, s_addr, s_state);
       x = s_state[0]; y = s_state[1]; alive = s_state[2] != 0; score = (uint32_t)s_state[3]; nf = rtp->nf;
       __syncthreads();  // s_state / s_part / s_addr are rewritten by the next level
     }
@@ -576,20 +617,152 @@ __device__ __forceinline__ void refine_nib_block(const RefineParams& P, const Co
   }
 }
 
-// Refinement on nibble-packed planes (every refinement level has word-aligned rows), ONE WARP PER CANDIDATE: no block
-// barriers, candidates of a frame are refined by up to 148 x 64 warps at once.  A patch row is 16 positions = 8 bytes
-// at an arbitrary nibble offset: lane r (< 16) and lane r + 16 load the two aligned 8-byte chunks the row spans -- one
-// LDG.64 per feature and lane, 16 cache lines per warp instruction instead of the 48 the byte kernel touches -- lane r
-// takes the second chunk from its partner with two shuffles, realigns with two funnel shifts and sums up to three
-// features in the nibble domain before spreading even / odd nibbles into byte accumulators (widened to u16 after each
-// modality: <= 63 features x 4).  The warp first turns the template's features into plane offsets in its slice of shared
-// memory (one lane per feature), then issues eight window loads back to back per step.
+// Refinement on nibble-packed planes, ONE WARP PER CANDIDATE: no block barriers, candidates of a frame are refined by up to
+// 148 x 32 warps at once.  A patch row is 16 positions = 8 bytes at an arbitrary nibble offset.  Lanes r and r + 16 share
+// patch row r and split the features between them (even / odd feature of a pair): every lane fetches the two aligned
+// 8-byte chunks its window spans itself (2 LDG.64), realigns with two funnel shifts and sums pairs of features in the
+// nibble domain before spreading even / odd nibbles into byte accumulators (widened to u16 after each modality: <= 63
+// features x 4); the two halves' partial sums meet (one shuffle per register) only at the pruning checks and at the end.
+// The warp first turns the template's features into window addresses in its slice of shared memory (one lane per
+// feature).  On column-blocked planes (TILED) the 16 rows of a chunk are 128 contiguous bytes: a warp-wide load touches
+// two to four cache lines instead of 32.  One level of one candidate; returns false when the candidate is dropped.
+template <bool TILED>
+__device__ __forceinline__ bool refine_warp_level(const RefineParams& P, const RefineLevel& L, const RefineTpl* rtp, uint32_t frame,
+                                                  float threshold, const BatchCtl* ctl, uint32_t* s_addr, int& x, int& y,
+                                                  uint32_t& score, uint32_t& nf) {
+  const int lane = threadIdx.x & 31;
+  const int prow = lane & 15, half = lane >> 4;
+  const int T = L.T, W = L.W;
+  const int off = T / 2 + (T % 2 - 1);
+  const int offset_x = (x / T - 8) * T, offset_y = (y / T - 8) * T;
+  const uint32_t WH = (uint32_t)W * (uint32_t)(L.rows / T);
+  const uint32_t zero_run = TILED ? (uint32_t)(L.plane_stride / 2) - 128u : (uint32_t)L.plane_stride - 32u;
+  int n_all = 0;
+  for (int m = 0; m < P.M; ++m) n_all += rtp->cnt[m];
+  const uint32_t* fp = L.feats + rtp->feat_begin;
+  __syncwarp();
+  for (int i = lane; i < n_all; i += 32) refine_feature_address<TILED>(L, fp[i], offset_x, offset_y, WH, zero_run, s_addr, i);
+  __syncwarp();
+  const uint32_t row_off = (uint32_t)(prow * W);
+  // u16 totals of row prow: [j][h], word j: 0 even columns 0..7, 1 odd 0..7, 2 even 8..15, 3 odd 8..15; h: bytes (0,2) / (1,3)
+  uint32_t tot[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tot[j][0] = tot[j][1] = 0;
+  int begin = 0;
+  // exact early termination (see min_passing_score): every 16 features the warp checks whether any position can still pass
+  const int need = P.prune ? min_passing_score(threshold, (int)rtp->nf) : 0;
+  const bool mod_reversed = P.M > 1 && (P.mod_order == 2 ? ctl->mod_bits[frame][P.M - 1] < ctl->mod_bits[frame][0] : P.mod_order == 1);
+  int remaining = n_all;
+  bool hopeless = false;
+  auto best_so_far = [&](const uint32_t (&acc)[4], bool with_acc) -> int {
+    uint32_t mx = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t t0 = tot[j][0] + (with_acc ? (acc[j] & 0x00ff00ffu) : 0u);
+      uint32_t t1 = tot[j][1] + (with_acc ? ((acc[j] >> 8) & 0x00ff00ffu) : 0u);
+      t0 += __shfl_xor_sync(kFull, t0, 16);
+      t1 += __shfl_xor_sync(kFull, t1, 16);
+      mx = __vmaxu2(mx, __vmaxu2(t0, t1));
+    }
+    return (int)__reduce_max_sync(kFull, max(mx & 0xffffu, mx >> 16));
+  };
+  for (int mi = 0; mi < P.M && !hopeless; ++mi) {
+    // the sum does not depend on the order of the modalities; template order unless the host asks for the reverse
+    const int m = mod_reversed ? P.M - 1 - mi : mi;
+    begin = 0;
+    for (int k = 0; k < m; ++k) begin += rtp->cnt[k];
+    const uint8_t* lmm = L.lmn + (size_t)frame * L.frame_stride + (size_t)m * 4 * L.plane_stride + (TILED ? prow * 8 : 0);
+    const int n = rtp->cnt[m];  // <= 63 features, 32 per half: the u8 sums below cannot overflow
+    uint32_t acc[4] = {0, 0, 0, 0};
+    for (int f0 = 0; f0 < n; f0 += 8) {
+      if ((f0 & 8) == 0 && f0 > 0 && need > 0) {   // after 16, 32, 48 features of this modality (and see below at its end)
+        if (best_so_far(acc, true) + 4 * remaining < need) { hopeless = true; break; }
+      }
+      remaining -= min(8, n - f0);
+      uint2 c0[4], c1[4];
+      uint32_t sh[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int fi = f0 + 2 * k + half;
+        if (TILED) {
+          const uint2 a = fi < n ? reinterpret_cast<const uint2*>(s_addr)[begin + fi] : make_uint2(zero_run, zero_run);
+          sh[k] = (a.x & 7u) | ((a.y & 1u) << 3);
+          c0[k] = ldg64(lmm + (a.x & ~7u));
+          c1[k] = ldg64(lmm + (a.y & ~7u));
+        } else {
+          const uint32_t base = fi < n ? s_addr[begin + fi] : zero_run;
+          const uint32_t nidx = base + (base == zero_run ? 0u : row_off);   // nibble index of this row's first position
+          sh[k] = nidx & 15u;
+          const uint8_t* p = lmm + (size_t)(nidx >> 4) * 8u;
+          c0[k] = ldg64(p);
+          c1[k] = ldg64(p + 8);
+        }
+      }
+      uint32_t nib0 = 0, nib1 = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool hi = sh[k] >= 8u;                 // window starts in the second word of the first chunk
+        const uint32_t a = hi ? c0[k].y : c0[k].x, b = hi ? c1[k].x : c0[k].y, cc = hi ? c1[k].y : c1[k].x;
+        const uint32_t bits = (sh[k] & 7u) * 4u;
+        nib0 += __funnelshift_r(a, b, bits);
+        nib1 += __funnelshift_r(b, cc, bits);
+        if (k == 1 || k == 3) {                      // <= 3 features per nibble sum (3 * 4 < 16); two here
+          acc[0] += nib0 & 0x0f0f0f0fu; acc[1] += (nib0 >> 4) & 0x0f0f0f0fu;
+          acc[2] += nib1 & 0x0f0f0f0fu; acc[3] += (nib1 >> 4) & 0x0f0f0f0fu;
+          nib0 = nib1 = 0;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // [OCV] similarityLocal totals are u16: widen this modality's u8 sums
+      tot[j][0] += acc[j] & 0x00ff00ffu;
+      tot[j][1] += (acc[j] >> 8) & 0x00ff00ffu;
+    }
+    if (need > 0 && !hopeless && mi + 1 < P.M) {   // between modalities
+      const uint32_t none[4] = {0, 0, 0, 0};
+      if (best_so_far(none, false) + 4 * remaining < need) hopeless = true;
+    }
+  }
+  if (hopeless) return false;   // [OCV] would finish the sum and drop the candidate: sim < threshold
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {  // the two halves of a row meet
+    tot[j][0] += __shfl_xor_sync(kFull, tot[j][0], 16);
+    tot[j][1] += __shfl_xor_sync(kFull, tot[j][1], 16);
+  }
+  // first maximum in raster order: key = score << 8 | (255 - raster index); byte b of word j is column
+  // 8 * (j / 2) + 2 * b + (j & 1)
+  uint32_t best_key = 0;
+  if (half == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t src = tot[j][b & 1];
+        const uint32_t sc = (b & 2) ? (src >> 16) : (src & 0xffffu);
+        const int col = 8 * (j >> 1) + 2 * b + (j & 1);
+        best_key = max(best_key, (sc << 8) | (uint32_t)(255 - (prow * 16 + col)));
+      }
+  }
+  best_key = __reduce_max_sync(kFull, best_key);
+  const int best_score = (int)(best_key >> 8);
+  int best_r = -1, best_c = -1;
+  if (best_score > 0) {
+    const int idx = 255 - (int)(best_key & 0xffu);
+    best_r = idx >> 4; best_c = idx & 15;
+  }
+  const int nfl = (int)rtp->nf;
+  const float sim = __fdiv_rn(__fmul_rn((float)best_score, 100.f), (float)(4 * nfl));
+  x = (x / T - 8 + best_c) * T + off;
+  y = (y / T - 8 + best_r) * T + off;
+  score = (uint32_t)best_score; nf = rtp->nf;
+  return !(sim < threshold);  // [OCV] remove_if(MatchPredicate(threshold))
+}
+
 __device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const CoarseTpl* __restrict__ ctpl,
                                                 const Cand* __restrict__ cand, uint32_t n_cands, const BatchCtl* ctl, uint8_t* results,
                                                 size_t result_stride, uint32_t out_cap, uint32_t* smem) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t* s_addr = smem + warp * kRefineMaxFeat;  // nibble index of each feature's patch origin (this warp's slice)
-  const int prow = lane & 15, half = lane >> 4;
+  uint32_t* s_addr = smem + warp * 2 * kRefineMaxFeat;  // window address words of each feature (this warp's slice)
   // consecutive candidates go to different CTAs (SMs): a handful of candidates must not queue on one SM's L1
   for (uint32_t ci = (uint32_t)warp * gridDim.x + blockIdx.x; ci < n_cands; ci += gridDim.x * kRefineWarps) {
     const Cand c = cand[ci];
@@ -607,138 +780,13 @@ __device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const Coa
     for (int l = P.levels - 2; l >= 0 && alive; --l) {
       const RefineLevel& L = P.level[l];
       const RefineTpl* rtp = L.tpl + c.tglob;
-      const int T = L.T, W = L.W;
-      const int border = 8 * T, off = T / 2 + (T % 2 - 1);
+      const int border = 8 * L.T;
       const int max_x = L.cols - rtp->width - border, max_y = L.rows - rtp->height - border;
       x = x * 2 + 1; y = y * 2 + 1;
       x = max(x, border); y = max(y, border);
       x = min(x, max_x); y = min(y, max_y);
-      const int offset_x = (x / T - 8) * T, offset_y = (y / T - 8) * T;
-      const uint32_t WH = (uint32_t)W * (uint32_t)(L.rows / T);
-      const uint32_t zero_run = (uint32_t)L.plane_stride - 32u;  // the tail of every plane is zero (App. D-2 padding)
-      int n_all = 0;
-      for (int m = 0; m < P.M; ++m) n_all += rtp->cnt[m];
-      const uint32_t* fp = L.feats + rtp->feat_begin;
-      __syncwarp();
-      for (int i = lane; i < n_all; i += 32) {
-        const uint32_t pk = fp[i];
-        const int fx = (int)(pk & 0x1fffu) - 4096 + offset_x, fy = (int)((pk >> 13) & 0x1fffu) - 4096 + offset_y;
-        const bool inside = fx >= 0 && fy >= 0 && fx < L.cols && fy < L.rows;  // "Discard feature if out of bounds"
-        const uint32_t label = pk >> 26;
-        const uint32_t addr = label * (uint32_t)L.plane_stride + (uint32_t)((fy % T) * T + (fx % T)) * WH +
-                              (uint32_t)(fy / T) * (uint32_t)W + (uint32_t)(fx / T);
-        s_addr[i] = inside ? addr : zero_run;
-      }
-      __syncwarp();
-      const uint32_t row_off = (uint32_t)(prow * W);
-      // u16 totals of row prow: [j][h], word j: 0 even columns 0..7, 1 odd 0..7, 2 even 8..15, 3 odd 8..15; h: bytes (0,2) / (1,3)
-      uint32_t tot[4][2];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) tot[j][0] = tot[j][1] = 0;
-      int begin = 0;
-      // exact early termination (see min_passing_score): every 16 features the warp checks whether any position can still pass
-      const int need = P.prune ? min_passing_score(threshold, (int)rtp->nf) : 0;
-      const bool mod_reversed = P.M > 1 && (P.mod_order == 2 ? ctl->mod_bits[frame][P.M - 1] < ctl->mod_bits[frame][0] : P.mod_order == 1);
-      int remaining = n_all;
-      bool hopeless = false;
-      // Lanes r and r + 16 share patch row r and split the features between them (even / odd feature of a pair): every
-      // lane fetches the two aligned 8-byte chunks its window spans itself and all 32 lanes do useful arithmetic; the two
-      // halves' partial sums meet (one shuffle per register) only at the pruning checks and at the end.
-      auto best_so_far = [&](const uint32_t (&acc)[4], bool with_acc) -> int {
-        uint32_t mx = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t t0 = tot[j][0] + (with_acc ? (acc[j] & 0x00ff00ffu) : 0u);
-          uint32_t t1 = tot[j][1] + (with_acc ? ((acc[j] >> 8) & 0x00ff00ffu) : 0u);
-          t0 += __shfl_xor_sync(kFull, t0, 16);
-          t1 += __shfl_xor_sync(kFull, t1, 16);
-          mx = __vmaxu2(mx, __vmaxu2(t0, t1));
-        }
-        return (int)__reduce_max_sync(kFull, max(mx & 0xffffu, mx >> 16));
-      };
-      for (int mi = 0; mi < P.M && !hopeless; ++mi) {
-        // the sum does not depend on the order of the modalities; template order unless the host asks for the reverse
-        const int m = mod_reversed ? P.M - 1 - mi : mi;
-        begin = 0;
-        for (int k = 0; k < m; ++k) begin += rtp->cnt[k];
-        const uint8_t* lmm = L.lmn + (size_t)frame * L.frame_stride + (size_t)m * 4 * L.plane_stride;
-        const int n = rtp->cnt[m];  // <= 63 features, 32 per half: the u8 sums below cannot overflow
-        uint32_t acc[4] = {0, 0, 0, 0};
-        for (int f0 = 0; f0 < n; f0 += 8) {
-          if ((f0 & 8) == 0 && f0 > 0 && need > 0) {   // after 16, 32, 48 features of this modality (and see below at its end)
-            if (best_so_far(acc, true) + 4 * remaining < need) { hopeless = true; break; }
-          }
-          remaining -= min(8, n - f0);
-          uint2 c0[4], c1[4];
-          uint32_t sh[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int fi = f0 + 2 * k + half;
-            const uint32_t base = fi < n ? s_addr[begin + fi] : zero_run;
-            const uint32_t nidx = base + (base == zero_run ? 0u : row_off);   // nibble index of this row's first position
-            sh[k] = nidx & 15u;
-            const uint8_t* p = lmm + (size_t)(nidx >> 4) * 8u;
-            c0[k] = ldg64(p);
-            c1[k] = ldg64(p + 8);
-          }
-          uint32_t nib0 = 0, nib1 = 0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const bool hi = sh[k] >= 8u;                 // window starts in the second word of the first chunk
-            const uint32_t a = hi ? c0[k].y : c0[k].x, b = hi ? c1[k].x : c0[k].y, cc = hi ? c1[k].y : c1[k].x;
-            const uint32_t bits = (sh[k] & 7u) * 4u;
-            nib0 += __funnelshift_r(a, b, bits);
-            nib1 += __funnelshift_r(b, cc, bits);
-            if (k == 1 || k == 3) {                      // <= 3 features per nibble sum (3 * 4 < 16); two here
-              acc[0] += nib0 & 0x0f0f0f0fu; acc[1] += (nib0 >> 4) & 0x0f0f0f0fu;
-              acc[2] += nib1 & 0x0f0f0f0fu; acc[3] += (nib1 >> 4) & 0x0f0f0f0fu;
-              nib0 = nib1 = 0;
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {  // [OCV] similarityLocal totals are u16: widen this modality's u8 sums
-          tot[j][0] += acc[j] & 0x00ff00ffu;
-          tot[j][1] += (acc[j] >> 8) & 0x00ff00ffu;
-        }
-        if (need > 0 && !hopeless && mi + 1 < P.M) {   // between modalities
-          const uint32_t none[4] = {0, 0, 0, 0};
-          if (best_so_far(none, false) + 4 * remaining < need) hopeless = true;
-        }
-      }
-      if (hopeless) { alive = false; break; }   // [OCV] would finish the sum and drop the candidate: sim < threshold
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {  // the two halves of a row meet
-        tot[j][0] += __shfl_xor_sync(kFull, tot[j][0], 16);
-        tot[j][1] += __shfl_xor_sync(kFull, tot[j][1], 16);
-      }
-      // first maximum in raster order: key = score << 8 | (255 - raster index); byte b of word j is column
-      // 8 * (j / 2) + 2 * b + (j & 1)
-      uint32_t best_key = 0;
-      if (half == 0) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const uint32_t src = tot[j][b & 1];
-            const uint32_t sc = (b & 2) ? (src >> 16) : (src & 0xffffu);
-            const int col = 8 * (j >> 1) + 2 * b + (j & 1);
-            best_key = max(best_key, (sc << 8) | (uint32_t)(255 - (prow * 16 + col)));
-          }
-      }
-      best_key = __reduce_max_sync(kFull, best_key);
-      const int best_score = (int)(best_key >> 8);
-      int best_r = -1, best_c = -1;
-      if (best_score > 0) {
-        const int idx = 255 - (int)(best_key & 0xffu);
-        best_r = idx >> 4; best_c = idx & 15;
-      }
-      const int nfl = (int)rtp->nf;
-      const float sim = __fdiv_rn(__fmul_rn((float)best_score, 100.f), (float)(4 * nfl));
-      x = (x / T - 8 + best_c) * T + off;
-      y = (y / T - 8 + best_r) * T + off;
-      alive = !(sim < threshold);  // [OCV] remove_if(MatchPredicate(threshold))
-      score = (uint32_t)best_score; nf = rtp->nf;
+      alive = L.Hh ? refine_warp_level<true>(P, L, rtp, frame, threshold, ctl, s_addr, x, y, score, nf)
+                   : refine_warp_level<false>(P, L, rtp, frame, threshold, ctl, s_addr, x, y, score, nf);
     }
     if (lane == 0) atomicAdd(&hdr->n_cands, 1u);
     if (alive && lane == 0) {
@@ -759,8 +807,8 @@ __global__ void __launch_bounds__(kRefineWarps * 32) k_refine_nib(const RefinePa
                                                                  const Cand* __restrict__ cand, uint32_t cand_cap,
                                                                  BatchCtl* ctl, uint8_t* results, size_t result_stride,
                                                                  uint32_t out_cap) {
-  __shared__ uint32_t smem[kRefineWarps * kRefineMaxFeat];
-  static_assert(kRefineWarps * kRefineMaxFeat >= kRefineWarps * 16 * 4 + kRefineMaxFeat + 4, "block path fits the warp path's smem");
+  __shared__ __align__(8) uint32_t smem[kRefineWarps * 2 * kRefineMaxFeat];
+  static_assert(kRefineWarps * 2 * kRefineMaxFeat >= kRefineWarps * 16 * 4 + 2 * kRefineMaxFeat + 4, "block path fits the warp path's smem");
   cudaGridDependencySynchronize();  // programmatic dependent launch: the coarse kernel's candidates are complete from here on
   const uint32_t found = ctl->n_cands;
   const uint32_t n_cands = min(found, cand_cap);

@@ -153,14 +153,16 @@ def test_modality_order_of_the_coarse_sum_does_not_change_results(order, kinds):
     assert len(want) > 0
 
 
-@pytest.mark.parametrize("variant", [3, 0])
-def test_refine_kernel_many_candidates(variant):
+@pytest.mark.parametrize("variant,tiled", [(3, 1), (0, 1), (3, 0)])
+def test_refine_kernel_many_candidates(variant, tiled):
     """Refinement on nibble-packed planes with loose thresholds so that thousands of candidates are refined (warp per
     candidate) and a tight one (block per candidate), with the exact early termination of hopeless candidates on
-    (`prune` 3, default) and off (0); the lists must be the oracle's, and the packed planes of the refinement level must
-    be its byte planes two positions per byte."""
+    (`prune` 3, default) and off (0), on column-blocked planes (`refine_tiled` 1, default) and on flat ones (0); the lists
+    must be the oracle's, and the packed planes of the refinement level -- handed out in the reference's flat order, with the
+    column-blocked layout's halo rows and zero run verified on the way -- must be its byte planes two positions per byte."""
     orc, det, views = _pair(n_views=8, n_random=60, seed=23, classes=("a", "b"))
     det.set_option("prune", variant)
+    det.set_option("refine_tiled", tiled)
     for seed, thr in ((1005, 86.0), (1006, 58.0)):
         bgr, depth, _ = synth.compose_scene(seed, views[:5])
         want = orc.match([bgr, depth], thr, keep_candidates=True)
@@ -232,10 +234,17 @@ def test_single_modality_and_single_level():
 
 
 def test_three_levels():
+    """Two refinement levels: level 0 (W = 240) is column-blocked, level 1 (W = 60, not a multiple of 16) stays flat; switching
+    the layout off between two calls rebuilds the workspace and returns the same lists."""
     orc, det, views = _pair(T=(2, 4, 8), n_views=6, n_random=20, seed=29, canvas=(160, 160))
     bgr, depth, _ = synth.compose_scene(3, views[:3], rows=320, cols=480)
-    common.assert_matches_equal(det.match([bgr, depth], 70.0), orc.match([bgr, depth], 70.0))
-    common.assert_matches_equal(det.last_presort(), orc.last_presort(), "pre-sort")
+    for tiled in (1, 0, 1):
+        det.set_option("refine_tiled", tiled)
+        common.assert_matches_equal(det.match([bgr, depth], 70.0), orc.match([bgr, depth], 70.0))
+        common.assert_matches_equal(det.last_presort(), orc.last_presort(), "pre-sort")
+        for l in range(3):
+            for m in range(2):
+                assert np.array_equal(det.fetch(Stage.LINEAR, l, m), orc.fetch(Stage.LINEAR, l, m)), (tiled, l, m)
 
 
 def test_edge_templates():
