@@ -352,14 +352,14 @@ static int run_front(lm_detector* d, Lane& ln, int grid_frames, cudaStream_t s) 
       e.plane_stride = g.plane_stride;
       e.rows = g.rows; e.cols = g.cols; e.T = g.T; e.W = g.W; e.H = g.H; e.level = l; e.modality = m; e.mask_cols0 = ln.cols;
       e.block_begin = total;
-      total += spread_all_blocks(g.W, g.H, &e.blocks_x);
+      total += spread_all_blocks(g.T, g.W, g.H, &e.blocks_x);
     }
   }
   // byte planes that hold one frame only (taps on an aligned level) can be written by a single-frame launch only
   for (int l = 0; l < L; ++l)
     if (byt[l] && ln.lmem[l].frames < grid_frames && grid_frames > 1)
       return lm_fail(LM_E_STATE, "parity taps are available for single-frame requests only");
-  if (!launch_spread_all(sp, total, max_T, grid_frames, s)) return lm_fail(LM_E_INVALID, "T=%d needs too much shared memory", max_T);
+  if (!launch_spread_all(sp, total, grid_frames, s)) return lm_fail(LM_E_INVALID, "T=%d needs too much shared memory", max_T);
   ++ln.launches;
   for (int l = 0; l < L; ++l) {
     if (!direct[l]) {

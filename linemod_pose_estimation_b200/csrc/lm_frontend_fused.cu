@@ -465,15 +465,22 @@ __global__ void __launch_bounds__(256) k_dn_fused(const DnParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------- spread -> LM
-// One CTA = one row of T-cells x SP_CW cells of one (level, modality).  Everything is done on 32-bit words (four
-// pixels): masked quantisation -> separable OR (T-1 funnel shifts along x, T-1 word ORs along y) -> one LUT word per
-// spread byte (8 response nibbles) -> 4x4 byte transposes (PRMT) so that every store is a full word of one
-// (orientation, T^2 phase) row of the linear memories.  The coarsest level is written nibble-packed directly (an 8x8
-// nibble transpose: one word = 8 consecutive cells) when its rows are word-aligned.
+// One CTA = R rows of T-cells x SP_CW cells of one (level, modality); R = 4 when the staging fits (T <= 8), else 2 or 1.
+// Everything is done on 32-bit words (four pixels): masked quantisation -> separable OR (T-1 funnel shifts along x, T-1
+// word ORs along y; with R cell rows the halo of the OR is (R+1)T-1 pixel rows for R*T) -> one LUT word per spread byte
+// (8 response nibbles) -> 4x4 byte transposes (PRMT) so that every store is a full word of one (orientation, T^2 phase)
+// row of the linear memories.  Nibble planes are written directly (an 8x8 nibble transpose: one word = 8 consecutive
+// cells) when the level's rows are word-aligned: flat for the coarsest level, column-blocked for refinement levels, where
+// the R rows of a 16-column block are 8R contiguous bytes (a full 32-byte sector at R = 4).
 constexpr int SP_CW = 32;  // grid cells per block along x
 
 __host__ __device__ inline int sp_nwo(int T) { return SP_CW * T / 4; }
 __host__ __device__ inline int sp_nwq(int T) { return (SP_CW * T + T - 1 + 3) / 4 + 1; }
+__host__ __device__ inline size_t sp_smem(int T, int R) {
+  const int IH = (R + 1) * T - 1;
+  return 1024 + (size_t)4 * (IH * sp_nwq(T) + IH * sp_nwo(T) + R * T * sp_nwo(T));
+}
+__host__ __device__ inline int sp_rows_per_block(int T) { return sp_smem(T, 4) <= 48 * 1024 ? 4 : (sp_smem(T, 2) <= 48 * 1024 ? 2 : 1); }
 
 // 4x4 byte transpose: in[j] = bytes (k = 0..3) of item j  ->  out[k] = bytes (j = 0..3)
 __device__ __forceinline__ void transpose4x4(const uint32_t (&in)[4], uint32_t (&out)[4]) {
@@ -486,15 +493,17 @@ __device__ __forceinline__ void transpose4x4(const uint32_t (&in)[4], uint32_t (
 template <int TT>
 __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadEntry& E, uint8_t* smem, int frame) {
   const int T = TT ? TT : E.T;
+  const int R = sp_rows_per_block(T);
   const int W = E.W, H = E.H, rows = E.rows, cols = E.cols;
-  const int IH = 2 * T - 1, NWO = sp_nwo(T), NWQ = sp_nwq(T);
+  const int OH = R * T, IH = OH + T - 1, NWO = sp_nwo(T), NWQ = sp_nwq(T);
   uint32_t* s_resp = reinterpret_cast<uint32_t*>(smem);
   uint32_t* sq = s_resp + 256;
   uint32_t* sh = sq + IH * NWQ;
   uint32_t* sp = sh + IH * NWO;
   const int b = blockIdx.x - E.block_begin;
-  const int c0 = (b % E.blocks_x) * SP_CW, a = b / E.blocks_x;
-  const int px0 = c0 * T, py0 = a * T;
+  const int c0 = (b % E.blocks_x) * SP_CW, a0 = (b / E.blocks_x) * R;   // first cell column / cell row of this block
+  const int nr = min(R, H - a0);                                        // cell rows of this block inside the image
+  const int px0 = c0 * T, py0 = a0 * T;
   const int tid = threadIdx.x;
   const uint8_t* __restrict__ qraw = E.qraw + (size_t)frame * E.qraw_stride;
   uint8_t* __restrict__ quantized = E.quantized + (size_t)frame * E.quantized_stride;
@@ -508,7 +517,7 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
     const int r = i / NWQ, wi = i - r * NWQ;
     const int gy = py0 + r, gx = px0 + 4 * wi;
     uint32_t v = 0;
-    const bool own = r < T && wi < NWO;  // inside the block's own T x (SP_CW*T) pixels: write Detector::match's quantized image
+    const bool own = r < OH && wi < NWO;  // inside the block's own pixels: write Detector::match's quantized image
     if (fast) {
       if (gy < rows && gx < cols) {
         v = __ldg(reinterpret_cast<const uint32_t*>(qraw + (size_t)gy * cols + gx));
@@ -548,7 +557,7 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
   __syncthreads();
   // ---- OR over T rows
   unsigned int n_bits = 0;
-  for (int i = tid; i < T * NWO; i += 256) {
+  for (int i = tid; i < OH * NWO; i += 256) {
     const int r = i / NWO, wi = i - r * NWO;
     uint32_t v = 0;
     if (TT) {
@@ -581,11 +590,16 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
   if (E.lm_nib != nullptr) {  // nibble-packed planes: one word = 8 consecutive cells of one (orientation, phase) row
     const size_t nib_stride = (size_t)E.nib_plane / 2;
     const int Hh = E.tiled_Hh;  // refinement levels: column-blocked layout (lm_kernels.cuh tiled_nibble_index)
-    for (int it = tid; it < T * T * (SP_CW / 8); it += 256) {
-      const int b8 = it & (SP_CW / 8 - 1), g = it / (SP_CW / 8);
-      if (b8 * 8 >= ncell) continue;
+    for (int it = tid; it < T * T * R * (SP_CW / 8); it += 256) {
+      // consecutive threads write consecutive words: flat planes -- the four words of a cell row; column-blocked planes --
+      // the two words of a block row, then the block's next rows (8R contiguous bytes), then the second block
+      int b8, ra, g;
+      if (Hh) { b8 = (it & 1) | (((it / (2 * R)) & 1) << 1); ra = (it >> 1) % R; g = it / (4 * R); }
+      else { b8 = it & 3; ra = (it >> 2) % R; g = it / (4 * R); }
+      if (b8 * 8 >= ncell || ra >= nr) continue;
+      const int a = a0 + ra;
       const int rs = g / T, cs = g - rs * T;
-      const uint8_t* p = spb + rs * row_bytes + cs + T * (b8 * 8);
+      const uint8_t* p = spb + (ra * T + rs) * row_bytes + cs + T * (b8 * 8);
       uint32_t ev[4], od[4];  // pixel pair (2p, 2p+1): even / odd orientations, one byte per orientation pair
 #pragma unroll
       for (int pr = 0; pr < 4; ++pr) {
@@ -617,11 +631,11 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
   uint8_t* __restrict__ lm = E.lm ? E.lm + (size_t)frame * E.lm_stride : nullptr;
   if (lm != nullptr) {
     if ((W & 3) == 0) {
-      for (int it = tid; it < T * T * (SP_CW / 4); it += 256) {
-        const int b4 = it & (SP_CW / 4 - 1), g = it / (SP_CW / 4);
-        if (b4 * 4 >= ncell) continue;
+      for (int it = tid; it < T * T * R * (SP_CW / 4); it += 256) {
+        const int b4 = it & (SP_CW / 4 - 1), ra = (it / (SP_CW / 4)) % R, g = it / ((SP_CW / 4) * R);
+        if (b4 * 4 >= ncell || ra >= nr) continue;
         const int rs = g / T, cs = g - rs * T;
-        const uint8_t* p = spb + rs * row_bytes + cs + T * (b4 * 4);
+        const uint8_t* p = spb + (ra * T + rs) * row_bytes + cs + T * (b4 * 4);
         uint32_t ev[4], od[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -632,7 +646,7 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
         uint32_t oe[4], oo[4];
         transpose4x4(ev, oe);
         transpose4x4(od, oo);
-        uint8_t* dst = lm + (size_t)g * WH + (size_t)a * W + c0 + b4 * 4;
+        uint8_t* dst = lm + (size_t)g * WH + (size_t)(a0 + ra) * W + c0 + b4 * 4;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           *reinterpret_cast<uint32_t*>(dst + (size_t)(2 * k) * E.plane_stride) = oe[k];
@@ -640,19 +654,19 @@ __device__ __forceinline__ void spread_tile(const SpreadParams& P, const SpreadE
         }
       }
     } else {
-      for (int it = tid; it < T * T * SP_CW; it += 256) {
-        const int bb = it & (SP_CW - 1), g = it / SP_CW;
-        if (bb >= ncell) continue;
+      for (int it = tid; it < T * T * R * SP_CW; it += 256) {
+        const int bb = it & (SP_CW - 1), ra = (it / SP_CW) % R, g = it / (SP_CW * R);
+        if (bb >= ncell || ra >= nr) continue;
         const int rs = g / T, cs = g - rs * T;
-        const uint32_t r0 = s_resp[spb[rs * row_bytes + cs + T * bb]];
-        const size_t o = (size_t)g * WH + (size_t)a * W + c0 + bb;
+        const uint32_t r0 = s_resp[spb[(ra * T + rs) * row_bytes + cs + T * bb]];
+        const size_t o = (size_t)g * WH + (size_t)(a0 + ra) * W + c0 + bb;
 #pragma unroll
         for (int ori = 0; ori < 8; ++ori) lm[ori * E.plane_stride + o] = (uint8_t)((r0 >> (4 * ori)) & 15);
       }
     }
   }
   if (tap_response) {
-    for (int i = tid; i < T * NWO * 4; i += 256) {
+    for (int i = tid; i < OH * NWO * 4; i += 256) {
       const int r = i / (NWO * 4), x = i - r * (NWO * 4);
       const int gy = py0 + r, gx = px0 + x;
       if (gy < rows && gx < cols) {
@@ -677,10 +691,7 @@ __global__ void __launch_bounds__(256) k_spread_all(const SpreadParams P) {
   else spread_tile<0>(P, E, smem, frame);
 }
 
-size_t spread_all_smem(int T) {
-  const int IH = 2 * T - 1;
-  return 1024 + (size_t)4 * (IH * sp_nwq(T) + IH * sp_nwo(T) + T * sp_nwo(T));
-}
+size_t spread_all_smem(int T) { return sp_smem(T, sp_rows_per_block(T)); }
 
 }  // namespace
 
@@ -701,13 +712,15 @@ void launch_pyrdown_fast(const BatchCtl* ctl, int modality, const uint8_t* src, 
   dim3 grid((cols / 2 + Y_TW - 1) / Y_TW, (rows / 2 + Y_TH - 1) / Y_TH, n_frames);
   k_pyrdown_fast<<<grid, 256, 0, s>>>(ctl, modality, src, src_stride, rows, cols, dst, dst_stride);
 }
-int spread_all_blocks(int W, int H, int* blocks_x) {
+int spread_all_blocks(int T, int W, int H, int* blocks_x) {
+  const int R = sp_rows_per_block(T);
   *blocks_x = (W + SP_CW - 1) / SP_CW;
-  return *blocks_x * H;
+  return *blocks_x * ((H + R - 1) / R);
 }
-bool launch_spread_all(const SpreadParams& p, int total_blocks, int max_T, int n_frames, cudaStream_t s) {
-  size_t smem = spread_all_smem(max_T);
-  if (smem > 48 * 1024) return false;  // T <= 16 (checked by the host) needs 41 KB
+bool launch_spread_all(const SpreadParams& p, int total_blocks, int n_frames, cudaStream_t s) {
+  size_t smem = 0;
+  for (int i = 0; i < p.n; ++i) smem = std::max(smem, spread_all_smem(p.e[i].T));
+  if (smem > 48 * 1024) return false;  // T <= 16 (checked by the host) needs 41 KB at one cell row per block
   k_spread_all<<<dim3(total_blocks, n_frames), 256, smem, s>>>(p);
   return true;
 }

@@ -173,8 +173,8 @@ void launch_pyrdown_fast(const BatchCtl* ctl, int modality, const uint8_t* src, 
 int cg_fused_blocks(int rows, int cols, int* blocks_x);
 void launch_cg_fused(const CgParams& p, int total_blocks, int n_frames, cudaStream_t s);
 void launch_dn_fused(const DnParams& p, int n_frames, cudaStream_t s);
-int spread_all_blocks(int W, int H, int* blocks_x);
-bool launch_spread_all(const SpreadParams& p, int total_blocks, int max_T, int n_frames, cudaStream_t s);
+int spread_all_blocks(int T, int W, int H, int* blocks_x);
+bool launch_spread_all(const SpreadParams& p, int total_blocks, int n_frames, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------ matching
 // Coarse similarity of a chunk of frames against the request's tile records, one launch.  Virtual tile v = frame *

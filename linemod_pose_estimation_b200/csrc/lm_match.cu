@@ -431,8 +431,10 @@ __device__ __forceinline__ int min_passing_score(float threshold, int nf) {
 
 // Where a feature's 16 x 16 window starts, for one lane of the address phase.  Flat planes: the nibble index of the
 // window's first position (rows W apart).  Column-blocked planes (RefineLevel::Hh != 0): two words -- byte offsets of the
-// window's two 16-column chunks at row 0 (rows 8 bytes apart) with the nibble shift (0..15) in their low bits:
-// w0 = offset0 | (shift & 7), w1 = offset1 | (shift >> 3).  Features outside the image point at the plane's zero run.
+// window's two 16-column chunks at row 0 (rows 8 bytes apart; offsets are multiples of 8 below 2^31) with the nibble shift
+// (0..15) in the first one's spare bits: w0 = offset0 | (shift & 7) | (shift >> 3) << 31, w1 = offset1.  Features outside
+// the image (and the padding slots of the warp path, pk = kNoFeature) point at the plane's zero run.
+constexpr uint32_t kNoFeature = 0u;   // packed feature (x, y) = (-4096, -4096): outside every image
 template <bool TILED>
 __device__ __forceinline__ void refine_feature_address(const RefineLevel& L, uint32_t pk, int offset_x, int offset_y, uint32_t WH,
                                                        uint32_t zero_run, uint32_t* s_addr, int i) {
@@ -453,8 +455,8 @@ __device__ __forceinline__ void refine_feature_address(const RefineLevel& L, uin
     uint32_t b1 = (cb + 1u < ((uint32_t)W >> 4)) ? b0 + block_bytes : phase0 + (row + 1u) * 8u;
     uint32_t s = sh;
     if (!inside) { b0 = b1 = zero_run; s = 0; }
-    s_addr[2 * i] = b0 | (s & 7u);
-    s_addr[2 * i + 1] = b1 | (s >> 3);
+    s_addr[2 * i] = b0 | (s & 7u) | ((s >> 3) << 31);
+    s_addr[2 * i + 1] = b1;
   }
 }
 
@@ -494,8 +496,8 @@ __device__ __forceinline__ void refine_block_level(const RefineParams& P, const 
       const int f = warp + kRefineWarps * k;
       if (TILED) {
         const uint2 a = f < n ? reinterpret_cast<const uint2*>(s_addr)[begin + f] : make_uint2(zero_run, zero_run);
-        sh[k] = (a.x & 7u) | ((a.y & 1u) << 3);
-        w[k] = ldg64(lmm + ((half ? a.y : a.x) & ~7u));
+        sh[k] = (a.x & 7u) | ((a.x >> 31) << 3);
+        w[k] = ldg64(lmm + (half ? a.y : (a.x & 0x7ffffff8u)));
       } else {
         const uint32_t base = f < n ? s_addr[begin + f] : zero_run;
         const uint32_t nidx = base + (base == zero_run ? 0u : row_off);   // nibble index of this row's first position
@@ -626,8 +628,7 @@ __device__ __forceinline__ void refine_nib_block(const RefineParams& P, const Co
 // The warp first turns the template's features into window addresses in its slice of shared memory (one lane per
 // feature).  On column-blocked planes (TILED) the 16 rows of a chunk are 128 contiguous bytes: a warp-wide load touches
 // two to four cache lines instead of 32.  One level of one candidate; returns false when the candidate is dropped.
-template <bool TILED>
-__device__ __forceinline__ bool refine_warp_level(const RefineParams& P, const RefineLevel& L, const RefineTpl* rtp, uint32_t frame,
+__device__ __forceinline__ bool refine_warp_level_flat(const RefineParams& P, const RefineLevel& L, const RefineTpl* rtp, uint32_t frame,
                                                   float threshold, const BatchCtl* ctl, uint32_t* s_addr, int& x, int& y,
                                                   uint32_t& score, uint32_t& nf) {
   const int lane = threadIdx.x & 31;
@@ -636,12 +637,12 @@ __device__ __forceinline__ bool refine_warp_level(const RefineParams& P, const R
   const int off = T / 2 + (T % 2 - 1);
   const int offset_x = (x / T - 8) * T, offset_y = (y / T - 8) * T;
   const uint32_t WH = (uint32_t)W * (uint32_t)(L.rows / T);
-  const uint32_t zero_run = TILED ? (uint32_t)(L.plane_stride / 2) - 128u : (uint32_t)L.plane_stride - 32u;
+  const uint32_t zero_run = (uint32_t)L.plane_stride - 32u;   // the tail of every plane is zero (App. D-2 padding)
   int n_all = 0;
   for (int m = 0; m < P.M; ++m) n_all += rtp->cnt[m];
   const uint32_t* fp = L.feats + rtp->feat_begin;
   __syncwarp();
-  for (int i = lane; i < n_all; i += 32) refine_feature_address<TILED>(L, fp[i], offset_x, offset_y, WH, zero_run, s_addr, i);
+  for (int i = lane; i < n_all; i += 32) refine_feature_address<false>(L, fp[i], offset_x, offset_y, WH, zero_run, s_addr, i);
   __syncwarp();
   const uint32_t row_off = (uint32_t)(prow * W);
   // u16 totals of row prow: [j][h], word j: 0 even columns 0..7, 1 odd 0..7, 2 even 8..15, 3 odd 8..15; h: bytes (0,2) / (1,3)
@@ -671,7 +672,7 @@ __device__ __forceinline__ bool refine_warp_level(const RefineParams& P, const R
     const int m = mod_reversed ? P.M - 1 - mi : mi;
     begin = 0;
     for (int k = 0; k < m; ++k) begin += rtp->cnt[k];
-    const uint8_t* lmm = L.lmn + (size_t)frame * L.frame_stride + (size_t)m * 4 * L.plane_stride + (TILED ? prow * 8 : 0);
+    const uint8_t* lmm = L.lmn + (size_t)frame * L.frame_stride + (size_t)m * 4 * L.plane_stride;
     const int n = rtp->cnt[m];  // <= 63 features, 32 per half: the u8 sums below cannot overflow
     uint32_t acc[4] = {0, 0, 0, 0};
     for (int f0 = 0; f0 < n; f0 += 8) {
@@ -684,19 +685,12 @@ __device__ __forceinline__ bool refine_warp_level(const RefineParams& P, const R
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int fi = f0 + 2 * k + half;
-        if (TILED) {
-          const uint2 a = fi < n ? reinterpret_cast<const uint2*>(s_addr)[begin + fi] : make_uint2(zero_run, zero_run);
-          sh[k] = (a.x & 7u) | ((a.y & 1u) << 3);
-          c0[k] = ldg64(lmm + (a.x & ~7u));
-          c1[k] = ldg64(lmm + (a.y & ~7u));
-        } else {
-          const uint32_t base = fi < n ? s_addr[begin + fi] : zero_run;
-          const uint32_t nidx = base + (base == zero_run ? 0u : row_off);   // nibble index of this row's first position
-          sh[k] = nidx & 15u;
-          const uint8_t* p = lmm + (size_t)(nidx >> 4) * 8u;
-          c0[k] = ldg64(p);
-          c1[k] = ldg64(p + 8);
-        }
+        const uint32_t base = fi < n ? s_addr[begin + fi] : zero_run;
+        const uint32_t nidx = base + (base == zero_run ? 0u : row_off);   // nibble index of this row's first position
+        sh[k] = nidx & 15u;
+        const uint8_t* p = lmm + (size_t)(nidx >> 4) * 8u;
+        c0[k] = ldg64(p);
+        c1[k] = ldg64(p + 8);
       }
       uint32_t nib0 = 0, nib1 = 0;
 #pragma unroll
@@ -710,6 +704,147 @@ __device__ __forceinline__ bool refine_warp_level(const RefineParams& P, const R
           acc[0] += nib0 & 0x0f0f0f0fu; acc[1] += (nib0 >> 4) & 0x0f0f0f0fu;
           acc[2] += nib1 & 0x0f0f0f0fu; acc[3] += (nib1 >> 4) & 0x0f0f0f0fu;
           nib0 = nib1 = 0;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // [OCV] similarityLocal totals are u16: widen this modality's u8 sums
+      tot[j][0] += acc[j] & 0x00ff00ffu;
+      tot[j][1] += (acc[j] >> 8) & 0x00ff00ffu;
+    }
+    if (need > 0 && !hopeless && mi + 1 < P.M) {   // between modalities
+      const uint32_t none[4] = {0, 0, 0, 0};
+      if (best_so_far(none, false) + 4 * remaining < need) hopeless = true;
+    }
+  }
+  if (hopeless) return false;   // [OCV] would finish the sum and drop the candidate: sim < threshold
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {  // the two halves of a row meet
+    tot[j][0] += __shfl_xor_sync(kFull, tot[j][0], 16);
+    tot[j][1] += __shfl_xor_sync(kFull, tot[j][1], 16);
+  }
+  // first maximum in raster order: key = score << 8 | (255 - raster index); byte b of word j is column
+  // 8 * (j / 2) + 2 * b + (j & 1)
+  uint32_t best_key = 0;
+  if (half == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t src = tot[j][b & 1];
+        const uint32_t sc = (b & 2) ? (src >> 16) : (src & 0xffffu);
+        const int col = 8 * (j >> 1) + 2 * b + (j & 1);
+        best_key = max(best_key, (sc << 8) | (uint32_t)(255 - (prow * 16 + col)));
+      }
+  }
+  best_key = __reduce_max_sync(kFull, best_key);
+  const int best_score = (int)(best_key >> 8);
+  int best_r = -1, best_c = -1;
+  if (best_score > 0) {
+    const int idx = 255 - (int)(best_key & 0xffu);
+    best_r = idx >> 4; best_c = idx & 15;
+  }
+  const int nfl = (int)rtp->nf;
+  const float sim = __fdiv_rn(__fmul_rn((float)best_score, 100.f), (float)(4 * nfl));
+  x = (x / T - 8 + best_c) * T + off;
+  y = (y / T - 8 + best_r) * T + off;
+  score = (uint32_t)best_score; nf = rtp->nf;
+  return !(sim < threshold);  // [OCV] remove_if(MatchPredicate(threshold))
+}
+
+// The same level on COLUMN-BLOCKED planes (RefineLevel::Hh != 0; lm_kernels.cuh tiled_nibble_index): the 16 rows of a window
+// chunk are 128 contiguous bytes, so a warp-wide load touches two to four cache lines instead of 32, and -- W being a
+// multiple of 16 -- a feature's shift is the same in every row: the address phase leaves (offset0 | shift, offset1) per
+// feature, a modality's slots padded to a multiple of 16 with zero-run entries, and a step of the sum is eight features per
+// lane (sixteen per warp) without a bounds test: LDS.64, two LDG.64, three selects, two funnel shifts, nibble sums of
+// 3 + 3 + 2 features between the even / odd splits.
+__device__ __forceinline__ bool refine_warp_level_tiled(const RefineParams& P, const RefineLevel& L, const RefineTpl* rtp, uint32_t frame,
+                                                        float threshold, const BatchCtl* ctl, uint32_t* s_addr, int& x, int& y,
+                                                        uint32_t& score, uint32_t& nf) {
+  const int lane = threadIdx.x & 31;
+  const int prow = lane & 15, half = lane >> 4;
+  const int T = L.T;
+  const int off = T / 2 + (T % 2 - 1);
+  const int offset_x = (x / T - 8) * T, offset_y = (y / T - 8) * T;
+  const uint32_t zero_run = (uint32_t)(L.plane_stride / 2) - 128u;   // 128 zero bytes close every plane
+  const uint32_t* fp = L.feats + rtp->feat_begin;
+  int n_all = 0;
+  __syncwarp();
+  {   // address phase: modality m's features go to slots seg .. seg + cnt[m], the rest of its 16-slot groups is padding
+    int seg = 0, first = 0;
+    for (int m = 0; m < P.M; ++m) {
+      const int n = rtp->cnt[m], padded = (n + 15) & ~15;
+      for (int i = lane; i < padded; i += 32)
+        refine_feature_address<true>(L, i < n ? fp[first + i] : kNoFeature, offset_x, offset_y, 0u, zero_run, s_addr, seg + i);
+      seg += padded; first += n; n_all += n;
+    }
+  }
+  __syncwarp();
+  const uint2* s_pair = reinterpret_cast<const uint2*>(s_addr);
+  // u16 totals of row prow: [j][h], word j: 0 even columns 0..7, 1 odd 0..7, 2 even 8..15, 3 odd 8..15; h: bytes (0,2) / (1,3)
+  uint32_t tot[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tot[j][0] = tot[j][1] = 0;
+  // exact early termination (see min_passing_score): every 16 features the warp checks whether any position can still pass
+  const int need = P.prune ? min_passing_score(threshold, (int)rtp->nf) : 0;
+  const bool mod_reversed = P.M > 1 && (P.mod_order == 2 ? ctl->mod_bits[frame][P.M - 1] < ctl->mod_bits[frame][0] : P.mod_order == 1);
+  int remaining = n_all;
+  bool hopeless = false;
+  auto best_so_far = [&](const uint32_t (&acc)[4], bool with_acc) -> int {
+    uint32_t mx = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t t0 = tot[j][0] + (with_acc ? (acc[j] & 0x00ff00ffu) : 0u);
+      uint32_t t1 = tot[j][1] + (with_acc ? ((acc[j] >> 8) & 0x00ff00ffu) : 0u);
+      t0 += __shfl_xor_sync(kFull, t0, 16);
+      t1 += __shfl_xor_sync(kFull, t1, 16);
+      mx = __vmaxu2(mx, __vmaxu2(t0, t1));
+    }
+    return (int)__reduce_max_sync(kFull, max(mx & 0xffffu, mx >> 16));
+  };
+  for (int mi = 0; mi < P.M && !hopeless; ++mi) {
+    // the sum does not depend on the order of the modalities; template order unless the host asks for the reverse
+    const int m = mod_reversed ? P.M - 1 - mi : mi;
+    int seg = 0;
+    for (int k = 0; k < m; ++k) seg += (rtp->cnt[k] + 15) & ~15;
+    // this lane's row of every window chunk of modality m; pinned in a register pair (see the coarse kernel)
+    unsigned long long lane_base = (unsigned long long)L.lmn + (unsigned long long)frame * L.frame_stride +
+                                   (unsigned long long)m * 4ull * L.plane_stride + (unsigned long long)(prow * 8);
+    asm volatile("" : "+l"(lane_base));
+    const uint8_t* lmm = reinterpret_cast<const uint8_t*>(lane_base);
+    const int n = rtp->cnt[m];  // <= 63 features, 32 per half: the u8 sums below cannot overflow
+    uint32_t acc[4] = {0, 0, 0, 0};
+    for (int f0 = 0; f0 < n; f0 += 16) {
+      if (f0 > 0 && need > 0) {   // after 16, 32, 48 features of this modality (and see below at its end)
+        if (best_so_far(acc, true) + 4 * remaining < need) { hopeless = true; break; }
+      }
+      remaining -= min(16, n - f0);
+      const uint2* sp = s_pair + seg + f0 + half;
+      uint32_t nib0 = 0, nib1 = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {   // two batches of four features per lane: eight loads in flight each
+        uint2 c0[4], c1[4];
+        uint32_t key[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint2 a = sp[2 * (4 * h + k)];
+          key[k] = a.x;
+          c0[k] = ldg64(lmm + (a.x & 0x7ffffff8u));
+          c1[k] = ldg64(lmm + a.y);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool hi = (int)key[k] < 0;               // window starts in the second word of the first chunk
+          const uint32_t a = hi ? c0[k].y : c0[k].x, b = hi ? c1[k].x : c0[k].y, cc = hi ? c1[k].y : c1[k].x;
+          const uint32_t bits = key[k] << 2;             // funnel shifts use the low five bits: 4 * (shift & 7)
+          nib0 += __funnelshift_r(a, b, bits);
+          nib1 += __funnelshift_r(b, cc, bits);
+          const int j = 4 * h + k;
+          if (j == 2 || j == 5 || j == 7) {              // <= 3 features per nibble sum (3 * 4 < 16): 3 + 3 + 2
+            acc[0] += nib0 & 0x0f0f0f0fu; acc[1] += (nib0 >> 4) & 0x0f0f0f0fu;
+            acc[2] += nib1 & 0x0f0f0f0fu; acc[3] += (nib1 >> 4) & 0x0f0f0f0fu;
+            nib0 = nib1 = 0;
+          }
         }
       }
     }
@@ -785,8 +920,8 @@ __device__ __forceinline__ void refine_nib_warp(const RefineParams& P, const Coa
       x = x * 2 + 1; y = y * 2 + 1;
       x = max(x, border); y = max(y, border);
       x = min(x, max_x); y = min(y, max_y);
-      alive = L.Hh ? refine_warp_level<true>(P, L, rtp, frame, threshold, ctl, s_addr, x, y, score, nf)
-                   : refine_warp_level<false>(P, L, rtp, frame, threshold, ctl, s_addr, x, y, score, nf);
+      alive = L.Hh ? refine_warp_level_tiled(P, L, rtp, frame, threshold, ctl, s_addr, x, y, score, nf)
+                   : refine_warp_level_flat(P, L, rtp, frame, threshold, ctl, s_addr, x, y, score, nf);
     }
     if (lane == 0) atomicAdd(&hdr->n_cands, 1u);
     if (alive && lane == 0) {
