@@ -496,7 +496,7 @@ static const int kMaxQueries = LM_MAX_QUERIES;  // (class list, threshold) queri
 
 // Self-contained tile records of the production coarse kernel (layout: lm_kernels.cuh).
 static int build_tile_records(const Pack& pk, const std::vector<WorkItem>& items, const std::vector<uint2>& tiles,
-                              int pass_pos, int M, std::vector<uint32_t>& recs, int* rec_words) {
+                              int pass_pos, int M, std::vector<uint32_t>& recs, int* rec_words, int* max_feat_out) {
   const int hdr = coarse_record_header_words();
   int max_feat = 0;
   for (const WorkItem& it : items) {
@@ -508,6 +508,7 @@ static int build_tile_records(const Pack& pk, const std::vector<WorkItem>& items
   const int words = (hdr + max_feat + 3) & ~3;
   if (words > coarse_record_max_words()) return lm_fail(LM_E_INVALID, "template with too many features for a tile record");
   *rec_words = words;
+  *max_feat_out = max_feat;
   recs.assign((size_t)words * tiles.size(), 0u);
   for (size_t t = 0; t < tiles.size(); ++t) {
     uint32_t* r = &recs[t * (size_t)words];
@@ -596,7 +597,7 @@ static int get_plan(lm_detector* d, const Query* qs, int n_q, Pack::Plan** out) 
   plan.n_tiles = (int)tl.size();
   plan.evals = (uint64_t)items.size();
   std::vector<uint32_t> recs;
-  if (build_tile_records(pk, items, tl, pass_pos, d->model.M(), recs, &plan.rec_words) != LM_OK) return LM_E_INVALID;
+  if (build_tile_records(pk, items, tl, pass_pos, d->model.M(), recs, &plan.rec_words, &plan.max_feat) != LM_OK) return LM_E_INVALID;
   Pack::Plan& dst = pk.plans[key];
   dst = plan;
   if (dst.recs.ensure(recs.size() * 4 + 64) != LM_OK) return LM_E_CUDA;
@@ -654,7 +655,7 @@ static int enqueue_match(lm_detector* d, Lane& ln, const Pack::Plan& plan, const
   std::memset(&cp, 0, sizeof(cp));
   for (int q = 0; q < n_q; ++q) { cp.thr.v[q] = qs[q].threshold; rp.threshold[q] = qs[q].threshold; }
   cp.lmn = ln.lmn[L - 1].as<uint8_t>(); cp.lmn_stride = ln.lmn[L - 1].stride;
-  cp.recs = plan.recs.as<uint32_t>(); cp.rec_words = plan.rec_words; cp.n_tiles = plan.n_tiles;
+  cp.recs = plan.recs.as<uint32_t>(); cp.rec_words = plan.rec_words; cp.n_tiles = plan.n_tiles; cp.max_feat = plan.max_feat;
   cp.ctl = ln.ctl.as<BatchCtl>();
   cp.cand = ln.cand.as<Cand>(); cp.cand_cap = ln.cand_cap;
   cp.touched = ln.result.as<unsigned long long>();
@@ -1434,6 +1435,10 @@ int lm_set_option(lm_detector* d, const char* key, int value) {
     set_coarse_grid_limit(value);
     for (int i = 0; i < LM_LANES; ++i) d->lane[i].drop_graphs();
   }
+  else if (k == "coarse_narrow") {      // process-wide A/B switch; recorded graphs hold the old kernel
+    set_coarse_narrow(value < 0 || value > 2 ? 1 : value);
+    for (int i = 0; i < LM_LANES; ++i) d->lane[i].drop_graphs();
+  }
   else if (k == "finalize_threads") d->finalize_threads = std::max(0, std::min(value, 16));
   else if (k == "device_out_cap") d->device_out_cap = (uint32_t)std::max(16, value);
   else if (k == "cand_per_frame") d->cand_per_frame = (uint32_t)std::max(1024, value);
@@ -2104,9 +2109,9 @@ int lm_debug_coarse_map(lm_detector* d, const char* class_id, int template_id, u
   CU(cudaMemsetAsync(ln.dump.p, 0, (size_t)WH * 2, ln.stream));
   if (begin_chunk(d, ln, 1, 1, ln.stream) != LM_OK) return LM_E_CUDA;  // frame 0 = the front end built last
   std::vector<uint32_t> recs;
-  int rec_words = 0;
+  int rec_words = 0, max_feat = 0;
   std::vector<WorkItem> one(1, it);
-  if (build_tile_records(pk, one, tl, pass_pos, d->model.M(), recs, &rec_words) != LM_OK) return LM_E_INVALID;
+  if (build_tile_records(pk, one, tl, pass_pos, d->model.M(), recs, &rec_words, &max_feat) != LM_OK) return LM_E_INVALID;
   if (ln.dbg_recs.ensure(recs.size() * 4 + 64) != LM_OK) return LM_E_CUDA;
   if (!recs.empty()) CU(cudaMemcpyAsync(ln.dbg_recs.p, recs.data(), recs.size() * 4, cudaMemcpyHostToDevice, ln.stream));
   // threshold 1e30 -> raw threshold saturates: nothing becomes a candidate, the kernel only dumps its accumulators
@@ -2114,7 +2119,7 @@ int lm_debug_coarse_map(lm_detector* d, const char* class_id, int template_id, u
   std::memset(&cp, 0, sizeof(cp));
   for (int q = 0; q < LM_MAX_QUERIES; ++q) cp.thr.v[q] = 1e30f;
   cp.lmn = ln.lmn[d->model.levels() - 1].as<uint8_t>(); cp.lmn_stride = ln.lmn[d->model.levels() - 1].stride;
-  cp.recs = ln.dbg_recs.as<uint32_t>(); cp.rec_words = rec_words; cp.n_tiles = (int)tl.size();
+  cp.recs = ln.dbg_recs.as<uint32_t>(); cp.rec_words = rec_words; cp.n_tiles = (int)tl.size(); cp.max_feat = max_feat;
   cp.ctl = ln.ctl.as<BatchCtl>(); cp.cand = ln.cand.as<Cand>(); cp.cand_cap = 0; cp.M = d->model.M();
   cp.dump = ln.dump.as<uint16_t>(); cp.dump_stride = WH;
   launch_similarity_coarse(cp, 1, ln.stream);

@@ -228,7 +228,7 @@ struct Pack {
   struct ClassRange { std::string id; int class_index; std::vector<uint32_t> local; std::vector<uint32_t> global_pos; };
   std::vector<ClassRange> classes;      // canonical order
   // Device-side description of one (multi-query) request: work items and coarse tiles.  Cached by the class lists.
-  struct Plan { DevBuf items, recs; int n_items = 0, n_tiles = 0, rec_words = 0; uint64_t coarse_bytes = 0, evals = 0; double refine_nf_sum = 0; };
+  struct Plan { DevBuf items, recs; int n_items = 0, n_tiles = 0, rec_words = 0, max_feat = 0; uint64_t coarse_bytes = 0, evals = 0; double refine_nf_sum = 0; };
   std::map<std::string, Plan> plans;
   void clear_filtered() {
     for (auto& kv : plans) { kv.second.items.release(); kv.second.recs.release(); }

@@ -201,9 +201,11 @@ struct CoarseParams {
   QueryThresholds thr;
   uint32_t cand_cap;
   int rec_words, n_tiles, M, prune, dump_stride;
+  int max_feat;                           // largest feature count of a tile: <= 63 selects the u8-only kernel
 };
 void set_programmatic_launch(bool enabled);  // per thread; disabled while launches are recorded into a CUDA graph
 void set_coarse_grid_limit(int blocks);     // process-wide; 0 = no limit
+void set_coarse_narrow(int mode);           // process-wide A/B switch: 0 general kernel only, 1 u8-only kernel (default), 2 u8-only at 2 CTAs/SM
 int coarse_positions_per_pass();
 int coarse_record_header_words();
 int coarse_record_max_words();

@@ -172,6 +172,9 @@ __device__ __forceinline__ void rec_group(const uint8_t* __restrict__ lmn, const
     nib_flush<4>(a0, acc_e, acc_o);
   }
 }
+// (Code size matters here: the SM's instruction cache holds 32 KB and the warps of a CTA are at different places of the
+// loop.  A variant with one batch template per tail length 1..5 -- one round trip fewer for n = 4, 5, 10, 11 -- grew the hot
+// code from about 21 KB to 32 KB and measured 40 % SLOWER, profiles/r02_experiments.md.)
 
 // u8 sums of at most 63 features -> added to the u16 totals ([OCV] addSimilarities widening), accumulators cleared.
 __device__ __forceinline__ void rec_widen(uint32_t (&acc_e)[4], uint32_t (&acc_o)[4], uint32_t (&tot)[4][4]) {
@@ -198,8 +201,29 @@ __device__ __forceinline__ bool rec_alive(const uint32_t (&tot)[4][4], int thr, 
   return __any_sync(kFull, active && best > need);
 }
 
-// (2 CTAs per SM: a 3-CTA register budget -- 80 registers -- measured no faster, profiles/r02_experiments.md)
-__global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarseParams P) {
+// NARROW tiles (at most 63 features in all: the reference's two-modality detector has 31 + 31 at its coarsest level) never
+// leave the u8 accumulators: 63 * 4 < 256.  Largest of the lane's 32 sums: bytes 0, 2 and 1, 3 of every register as u16 pairs.
+__device__ __forceinline__ uint32_t rec_max_narrow(const uint32_t (&acc_e)[4], const uint32_t (&acc_o)[4]) {
+  uint32_t mx = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    mx = __vmaxu2(mx, __vmaxu2(acc_e[k] & 0x00ff00ffu, __byte_perm(acc_e[k], 0u, 0x4341)));
+    mx = __vmaxu2(mx, __vmaxu2(acc_o[k] & 0x00ff00ffu, __byte_perm(acc_o[k], 0u, 0x4341)));
+  }
+  return max(mx & 0xffffu, mx >> 16);
+}
+__device__ __forceinline__ bool rec_alive_narrow(const uint32_t (&acc_e)[4], const uint32_t (&acc_o)[4], int thr, int remaining,
+                                                 bool active) {
+  const int need = thr - 4 * remaining;  // a position passes only if partial > need
+  if (need < 0) return true;             // warp-uniform
+  return __any_sync(kFull, active && (int)rec_max_narrow(acc_e, acc_o) > need);
+}
+
+// One kernel body, two instantiations: NARROW (every tile of the request has at most 63 features: u8 sums only, no u16
+// totals -- sixteen registers fewer, three CTAs per SM) and the general one (u8 sums widened into u16 totals every half
+// modality, two CTAs per SM).
+template <bool NARROW>
+__device__ __forceinline__ void similarity_coarse_body(const CoarseParams& P) {
   constexpr bool BULK = true;   // (the register-staged alternative measured 4-6 % slower: profiles/r02_experiments.md)
   __shared__ __align__(16) uint32_t s_rec[8][2][kRecMaxWords];
   __shared__ __align__(8) unsigned long long s_bar[8][2];
@@ -296,10 +320,11 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarsePa
       thr_key = nfq;
     }
     const int thr = thr_val;
-    uint32_t tot[4][4];  // u16 x 2 per register: [k][r], r = (i & 1) * 2 + ((i >> 1) & 1) for position 8k + i
+    // u16 x 2 per register: [k][r], r = (i & 1) * 2 + ((i >> 1) & 1) for position 8k + i (general tiles only)
+    uint32_t tot[4][4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) tot[k][0] = tot[k][1] = tot[k][2] = tot[k][3] = 0;
-    uint32_t acc_e[4] = {0, 0, 0, 0}, acc_o[4] = {0, 0, 0, 0};
+    uint32_t acc_e[4] = {0, 0, 0, 0}, acc_o[4] = {0, 0, 0, 0};  // u8 x 4: position 8k + i is byte i / 2 of (i & 1 ? acc_o : acc_e)[k]
     int done = 0;
     bool alive = true;
     for (int mi = 0; mi < M && alive; ++mi) {
@@ -315,27 +340,39 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarsePa
         rec_group<1>(lmn, fw + n0, n1, 0u, acc_e, acc_o, zero);
       }
       fw += n0 + n1; done += n0 + n1;
-      rec_widen(acc_e, acc_o, tot);
-      if (do_prune && !rec_alive(tot, thr, n_feat - done, active)) { alive = false; break; }
+      if constexpr (NARROW) {
+        if (do_prune && !rec_alive_narrow(acc_e, acc_o, thr, n_feat - done, active)) { alive = false; break; }
+      } else {
+        rec_widen(acc_e, acc_o, tot);
+        if (do_prune && !rec_alive(tot, thr, n_feat - done, active)) { alive = false; break; }
+      }
       if (active) {
         rec_group<2>(lmn, fw, n2, 0u, acc_e, acc_o, zero);
         rec_group<3>(lmn, fw + n2, n3, 0u, acc_e, acc_o, zero);
       }
       done += n2 + n3;
-      rec_widen(acc_e, acc_o, tot);
-      if (do_prune && !rec_alive(tot, thr, n_feat - done, active)) alive = false;
+      if constexpr (NARROW) {
+        if (do_prune && !rec_alive_narrow(acc_e, acc_o, thr, n_feat - done, active)) alive = false;
+      } else {
+        rec_widen(acc_e, acc_o, tot);
+        if (do_prune && !rec_alive(tot, thr, n_feat - done, active)) alive = false;
+      }
     }
     bytes += (unsigned long long)done * (unsigned)rem;
     if (alive && active) {
       bool hit = thr < 0;
       if (!hit) {
-        const uint32_t thr2 = (uint32_t)min(thr, 0xffff) * 0x00010001u;
-        uint32_t any = 0;
+        if constexpr (NARROW) {
+          hit = (int)rec_max_narrow(acc_e, acc_o) > thr;
+        } else {
+          const uint32_t thr2 = (uint32_t)min(thr, 0xffff) * 0x00010001u;
+          uint32_t any = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+          for (int k = 0; k < 4; ++k)
 #pragma unroll
-          for (int r = 0; r < 4; ++r) any |= __vcmpgtu2(tot[k][r], thr2);
-        hit = any != 0;
+            for (int r = 0; r < 4; ++r) any |= __vcmpgtu2(tot[k][r], thr2);
+          hit = any != 0;
+        }
       }
       if (P.dump != nullptr || hit) {  // rare: [OCV] matchClass raster scan, "raw_score > raw_threshold"
 #pragma unroll
@@ -343,8 +380,13 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarsePa
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int p = first + 8 * k + i;
-            const uint32_t src = tot[k][(i & 1) * 2 + ((i >> 1) & 1)];
-            const int raw = (int)((i & 4) ? (src >> 16) : (src & 0xffffu));
+            int raw;
+            if constexpr (NARROW) {
+              raw = (int)((((i & 1) ? acc_o[k] : acc_e[k]) >> (8 * (i >> 1))) & 0xffu);
+            } else {
+              const uint32_t src = tot[k][(i & 1) * 2 + ((i >> 1) & 1)];
+              raw = (int)((i & 4) ? (src >> 16) : (src & 0xffffu));
+            }
             if (p < rem) {
               if (P.dump != nullptr) P.dump[(size_t)item * P.dump_stride + j0 + p] = (uint16_t)raw;
               if (raw > thr) {
@@ -377,6 +419,11 @@ __global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarsePa
     if (atomicAdd(&s_done, 1u) + 1u == s_expected) atomicAdd(P.touched, s_bytes);
   }
 }
+
+__global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec(const CoarseParams P) { similarity_coarse_body<false>(P); }
+__global__ void __launch_bounds__(256, 3) k_similarity_coarse_rec63(const CoarseParams P) { similarity_coarse_body<true>(P); }
+// (A/B: the u8-only body at two CTAs per SM, to tell the gain of the leaner body from that of the third CTA)
+__global__ void __launch_bounds__(256, 2) k_similarity_coarse_rec63_2cta(const CoarseParams P) { similarity_coarse_body<true>(P); }
 
 // Byte linear memories -> nibble-packed copy (two positions per byte), 16 bytes in / 8 bytes out per thread; blockIdx.y = frame.
 __global__ void __launch_bounds__(256) k_pack_nibbles(const uint8_t* __restrict__ src0, size_t src_stride,
@@ -985,6 +1032,9 @@ void set_programmatic_launch(bool enabled) { g_pdl_enabled = enabled; }
 // flight a smaller grid per frame lets the coarse kernels of consecutive frames share the SMs instead of queueing.
 static int g_coarse_grid_limit = 0;
 void set_coarse_grid_limit(int blocks) { g_coarse_grid_limit = blocks; }
+// A/B switch: 0 sends requests whose tiles all have <= 63 features through the general kernel too
+static int g_coarse_narrow = 1;   // 1: u8-only kernel, three CTAs per SM; 2: the same body at two CTAs per SM (A/B)
+void set_coarse_narrow(int mode) { g_coarse_narrow = mode; }
 
 template <class K>
 static int resident_ctas(K kernel) {
@@ -1000,14 +1050,18 @@ static int resident_ctas(K kernel) {
 
 void launch_similarity_coarse(const CoarseParams& p, int max_frames, cudaStream_t s) {
   if (p.n_tiles <= 0) return;
-  static const int persistent = resident_ctas(k_similarity_coarse_rec);
+  static const int persistent = resident_ctas(k_similarity_coarse_rec), persistent63 = resident_ctas(k_similarity_coarse_rec63),
+                   persistent63_2 = resident_ctas(k_similarity_coarse_rec63_2cta);
+  const int narrow = p.max_feat <= 63 ? g_coarse_narrow : 0;   // u8 sums cannot overflow: 63 * 4 < 256
   const long long blocks = ((long long)p.n_tiles * max_frames + 7) / 8;
-  int grid = (int)std::min<long long>(blocks, persistent);
+  int grid = (int)std::min<long long>(blocks, narrow == 1 ? persistent63 : (narrow == 2 ? persistent63_2 : persistent));
   if (g_coarse_grid_limit > 0) grid = min(grid, g_coarse_grid_limit);
   CoarseParams q = p;
   if (q.dump != nullptr) q.prune = 0;
   cudaLaunchConfig_t cfg = pdl_config(grid, 256, s);
-  cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec, q);
+  if (narrow == 1) cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec63, q);
+  else if (narrow == 2) cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec63_2cta, q);
+  else cudaLaunchKernelEx(&cfg, k_similarity_coarse_rec, q);
 }
 
 void launch_pack_nibbles(const uint8_t* lm_bytes, size_t bytes_stride, uint8_t* lm_nibbles, size_t nib_stride, size_t n_bytes,

@@ -106,14 +106,16 @@ def test_coarse_similarity_maps_bit_exact():
         assert np.array_equal(a, b), "coarse map of template %d differs in %d cells" % (tid, np.count_nonzero(a != b))
 
 
-@pytest.mark.parametrize("graphs", [1, 0])
-def test_coarse_kernel_maps_lists_and_packed_planes(graphs):
+@pytest.mark.parametrize("graphs,narrow", [(1, 1), (0, 1), (1, 0)])
+def test_coarse_kernel_maps_lists_and_packed_planes(graphs, narrow):
     """The coarse kernel (nibble-packed linear memories, tile records, exact early termination) must give the oracle's
-    coarse maps and match lists, replayed from the lane's CUDA graph or launched plainly; the packed planes must be the
-    reference's byte planes two positions per byte."""
-    variant = graphs
+    coarse maps and match lists, replayed from the lane's CUDA graph or launched plainly, by the u8-only kernel of requests
+    whose tiles have at most 63 features (31 + 31 here; `coarse_narrow` 1, default) and by the general one; the packed
+    planes must be the reference's byte planes two positions per byte."""
+    variant = 2 * graphs + narrow
     orc, det, views = _pair(n_views=8, n_random=90, seed=21, classes=("a", "b"))
     det.set_option("graphs", graphs)
+    det.set_option("coarse_narrow", narrow)
     bgr, depth, _ = synth.compose_scene(1003, views[:4])
     orc.build_front([bgr, depth])
     det.build_front([bgr, depth])
@@ -130,6 +132,7 @@ def test_coarse_kernel_maps_lists_and_packed_planes(graphs):
         got = det.match([bgr, depth], thr)
         common.assert_matches_equal(got, want, "variant %d thr %g" % (variant, thr))
         assert det.last_work()["candidates"] == len(orc.last_candidates())
+    det.set_option("coarse_narrow", 1)   # process-wide switch: back to the default
     assert len(want) > 0
 
 
