@@ -570,24 +570,83 @@ def run_ours(args):
                         keep.extend(res)
             done += n
 
+    # The headline e2e of a frame STREAM (configs 2, 3, 4) goes through lm_stream: the same chunked pipeline kept alive between
+    # pushes of E2E_CALL frames, so the device does not drain and refill at every call boundary; results are popped as they
+    # become ready and the timed region ends when the last frame's lists are on the host.  Config 5 IS 64-frame batches:
+    # there (and in the templates-sharded mode) the blocking batch call stays the e2e.
+    use_stream = sharded is None and CONFIG_ID != 5
+    POP_CAP = 4 * E2E_CALL
+    poffs_s = (C.c_size_t * (POP_CAP * n_q + 1))()
+    n_pop = C.c_int()
+    stream_chunks = 0
+
+    def stream_frames(first, count, keep=None):
+        nonlocal n_matches, stream_chunks
+        sh = C.c_void_p()
+        _capi.check(lib.lm_stream_open(det._h, qarr, n_q, C.byref(sh)))
+
+        def pop(wait):
+            nonlocal n_matches
+            _capi.check(lib.lm_stream_pop(sh, wait, POP_CAP, C.byref(out_p), poffs_s, C.byref(n_pop)))
+            n = n_pop.value
+            n_matches += poffs_s[n * n_q]
+            if keep is not None:
+                allm = det._take(out_p, poffs_s[n * n_q])
+                keep.extend([[allm[poffs_s[f * n_q + q]:poffs_s[f * n_q + q + 1]] for q in range(n_q)] for f in range(n)])
+            else:
+                lib.lm_free_matches(out_p)
+        try:
+            done, chunk_no = 0, 0
+            while done < count:
+                n = min(E2E_CALL, count - done)
+                arr, _keep = call_desc[((first + done) // E2E_CALL) % len(call_desc)]
+                _capi.check(lib.lm_stream_push(sh, arr, n, 2))
+                at = 0
+                while at < n:      # the library's chunking of a push (the first three chunks of a stream ramp up: 2, 2, 4)
+                    c = min(BATCH_FRAMES, n - at, 2 if chunk_no < 2 else (4 if chunk_no == 2 else BATCH_FRAMES))
+                    at += c
+                    chunk_no += 1
+                done += n
+                pop(0)
+            while lib.lm_stream_in_flight(sh) > 0:
+                pop(1)
+            stream_chunks += chunk_no
+        finally:
+            lib.lm_stream_close(sh)
+
     checked = []
-    e2e_frames(0, max(args.warmup, E2E_CALL), keep=checked)   # every lane's buffers grown, graphs recorded; kept for the parity check
+    e2e_frames(0, max(args.warmup, E2E_CALL), keep=None if use_stream else checked)   # every lane's buffers grown, graphs recorded
     if K % E2E_CALL:
         e2e_frames(0, K % E2E_CALL)
+    if use_stream:
+        stream_frames(0, max(args.warmup, E2E_CALL), keep=checked)   # kept for the parity check
+        if K % E2E_CALL:
+            stream_frames(0, K % E2E_CALL)
     barrier()
 
-    def timed_e2e(repeats):
+    def timed_e2e(repeats, fn):
         nonlocal n_matches
         n_matches = 0
         barrier()
         t0 = time.perf_counter()
-        e2e_frames(0, K * repeats)                   # R back-to-back repeats of the K steps, cut into E2E_CALL-frame calls
+        fn(0, K * repeats)                           # R back-to-back repeats of the K steps, cut into E2E_CALL-frame calls / pushes
         barrier()
         return time.perf_counter() - t0
 
-    probe = max_over_ranks(timed_e2e(1))
+    e2e_batch = None
+    if use_stream:   # secondary figure: the blocking batch call, one pipeline fill and drain per E2E_CALL frames
+        probe = max_over_ranks(timed_e2e(1, e2e_frames))
+        R_b = max(1, int(np.ceil(MIN_TIMED_S / max(probe, 1e-6))))
+        dt_b = max_over_ranks(timed_e2e(R_b, e2e_frames))
+        e2e_batch = {"value": evals_per_frame * frames_per_step / (dt_b / (K * R_b)), "unit": "evals/s",
+                     "fps": frames_per_step * K * R_b / dt_b, "ms_per_step": 1e3 * dt_b / (K * R_b), "timed_repeats": R_b,
+                     "what": "blocking lm_match_batch_multi calls of %d pinned host frames (the pipeline fills and drains in every call)" % E2E_CALL}
+    e2e_fn = stream_frames if use_stream else e2e_frames
+    stream_chunks = 0
+    probe = max_over_ranks(timed_e2e(1, e2e_fn))
     R_e2e = max(1, int(np.ceil(MIN_TIMED_S / max(probe, 1e-6))))
-    dt = max_over_ranks(timed_e2e(R_e2e))
+    stream_chunks = 0
+    dt = max_over_ranks(timed_e2e(R_e2e, e2e_fn))
     s_per_step_e2e = dt / (K * R_e2e)
     e2e_value = evals_per_frame * frames_per_step / s_per_step_e2e
     def chunks_of_call(n):   # lm_match_batch*: the first chunks of a call ramp up (2, 2, 4, ...) to the chunk size
@@ -599,7 +658,8 @@ def run_ours(args):
             k += 1
         return k
     total_frames = K * R_e2e
-    n_chunks_e2e = (total_frames // E2E_CALL) * chunks_of_call(E2E_CALL) + chunks_of_call(total_frames % E2E_CALL)
+    n_chunks_e2e = stream_chunks if use_stream else \
+        (total_frames // E2E_CALL) * chunks_of_call(E2E_CALL) + chunks_of_call(total_frames % E2E_CALL)
     launches_e2e = det.last_timings()["launches"] * n_chunks_e2e
     matches_per_frame = n_matches / max(1, K * R_e2e)
 
@@ -746,12 +806,16 @@ def run_ours(args):
                     "matches_per_step": matches_per_frame,
                     "h2d_gbs_measured": h2d_gbs,
                     "h2d_floor_ms_per_step": (ROWS * COLS * 5) / (h2d_gbs * 1e9) * 1e3 if h2d_gbs else None,
-                    "what": ("lm_match_batch_multi in calls of %d pinned host frames on every rank's own frames: chunks of %d frames "
-                             "(one launch set each), %d chunks in flight -- H2D, kernels, D2H + finalisation overlap"
+                    "what": (("lm_stream (C ABI): pushes of %d pinned host frames on every rank's own frames, finished frames popped as "
+                              "they become ready, the region ends when the last frame's lists are on the host: chunks of %d frames (one "
+                              "launch set each), %d chunks in flight -- H2D, kernels, D2H + finalisation overlap across pushes"
+                              if use_stream else
+                              "lm_match_batch_multi in calls of %d pinned host frames on every rank's own frames: chunks of %d frames "
+                              "(one launch set each), %d chunks in flight -- H2D, kernels, D2H + finalisation overlap")
                              % (E2E_CALL, BATCH_FRAMES, DEVICE_STREAMS)) if sharded is None else
                             "ShardedDetector.match_stream: per run of frames H2D on rank 0 + one NCCL broadcast per modality, local "
                             "matching in chunks on the handle's lanes, one NCCL all-gather of the survivor blocks, D2H + finalise on rank 0"},
-            "e2e_single_call": e2e_single,
+            "e2e_batch_calls": e2e_batch, "e2e_single_call": e2e_single,
             "gpu_launches": int(launches_device + launches_e2e + launches_single), "clocks": clock_info,
             "stage_ms_per_frame": stage_ms, "train_s": train_s,
         }

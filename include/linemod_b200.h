@@ -283,6 +283,29 @@ int lm_match_batch_multi(lm_detector* det, const lm_image* sources, int n_frames
                          int n_queries, lm_match_rec** out_matches, size_t* out_offsets);
 void lm_free_matches(lm_match_rec* matches);
 
+/* A continuous stream of HOST frames: the same chunked pipeline as lm_match_batch_multi, kept alive between calls, so that
+ * the device does not drain and refill at every call boundary (a 64-frame lm_match_batch_multi call spends about a fifth of
+ * its time filling and draining the pipeline).  The reference's service calls Detector::match once per camera frame
+ * (src/rgbdDetector.cpp:31-34); this is the same call for a caller that has the next frames already.
+ *   lm_stream_open   fixes the queries (class ids are copied) and takes over the handle's workspace lanes: other matching
+ *                    calls on the handle return LM_E_STATE until lm_stream_close.
+ *   lm_stream_push   enqueues n_frames frames (sources[f*n_sources + m]) in chunks of "batch_frames"; returns once the
+ *                    copies and kernels are enqueued, blocking only while all "batch_lanes" lanes are busy.  Pinned source
+ *                    buffers are read asynchronously: they must stay unchanged until lm_stream_pop has returned their frames
+ *                    (pageable ones are staged during the call).
+ *   lm_stream_pop    hands out finished frames in push order: at most max_frames of them; wait_all = 0 returns what is ready
+ *                    without blocking, wait_all = 1 first waits for everything pushed.  out_offsets (max_frames * n_queries
+ *                    + 1 entries) and *out_matches as in lm_match_batch_multi (release with lm_free_matches); the lists are
+ *                    identical to lm_match_multi's of the same frames.
+ *   lm_stream_in_flight   frames pushed and not yet popped. */
+typedef struct lm_stream lm_stream;
+int lm_stream_open(lm_detector* det, const lm_query* queries, int n_queries, lm_stream** out);
+int lm_stream_push(lm_stream* stream, const lm_image* sources, int n_frames, int n_sources);
+int lm_stream_pop(lm_stream* stream, int wait_all, int max_frames, lm_match_rec** out_matches, size_t* out_offsets,
+                  int* n_frames_out);
+int lm_stream_in_flight(const lm_stream* stream);
+void lm_stream_close(lm_stream* stream);
+
 /* Device-resident variant for multi-GPU sharding and for callers that already hold the frame in HBM:
  * sources are DEVICE pointers (tightly packed rows), work is enqueued on `stream` (a cudaStream_t) and nothing is
  * synchronised.  The un-ordered survivor records stay in device memory: *d_records points at a header

@@ -17,6 +17,7 @@
 #ifndef LINEMOD_B200_HPP_
 #define LINEMOD_B200_HPP_
 
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -684,6 +685,47 @@ class DetectorGroup {
  private:
   lm_group* g_;
   const lm_detector* proto_;
+};
+
+// lm_stream: Detector::match over a continuous stream of host frames.  push() enqueues frames (their buffers must stay
+// unchanged until pop() has returned them), pop() hands out finished frames in push order, each as Detector::match would
+// return it.  While a FrameStream lives, its detector refuses other matching calls.
+class FrameStream {
+ public:
+  FrameStream(const Detector& det, float threshold, const std::vector<std::string>& class_ids = std::vector<std::string>())
+      : s_(nullptr), det_(det.handle()) {
+    std::vector<const char*> ids;
+    for (size_t i = 0; i < class_ids.size(); ++i) ids.push_back(class_ids[i].c_str());
+    lm_query q = {threshold, ids.empty() ? nullptr : ids.data(), (int)ids.size()};
+    detail::check(lm_stream_open(det.handle(), &q, 1, &s_));
+  }
+  ~FrameStream() { lm_stream_close(s_); }
+  FrameStream(const FrameStream&) = delete;
+  FrameStream& operator=(const FrameStream&) = delete;
+  void push(const std::vector<std::vector<Image> >& frames) {
+    std::vector<lm_image> src;
+    for (size_t f = 0; f < frames.size(); ++f)
+      for (size_t m = 0; m < frames[f].size(); ++m) src.push_back(frames[f][m].c());
+    if (!frames.empty()) detail::check(lm_stream_push(s_, src.data(), (int)frames.size(), (int)frames[0].size()));
+  }
+  int inFlight() const { return lm_stream_in_flight(s_); }
+  // finished frames, oldest first; wait_all: everything pushed so far
+  void pop(std::vector<std::vector<Match> >& matches, bool wait_all = false) {
+    const int cap = std::max(1, inFlight());
+    std::vector<size_t> offs((size_t)cap + 1, 0);
+    lm_match_rec* recs = nullptr;
+    int n = 0;
+    detail::check(lm_stream_pop(s_, wait_all ? 1 : 0, cap, &recs, offs.data(), &n));
+    matches.assign((size_t)n, std::vector<Match>());
+    for (int f = 0; f < n; ++f)
+      for (size_t i = offs[(size_t)f]; i < offs[(size_t)f + 1]; ++i)
+        matches[(size_t)f].push_back(Match(recs[i].x, recs[i].y, recs[i].similarity, lm_class_id(det_, recs[i].class_index), recs[i].template_id));
+    lm_free_matches(recs);
+  }
+
+ private:
+  lm_stream* s_;
+  const lm_detector* det_;
 };
 
 // ------------------------------------------------------------------------------------------------ training helpers

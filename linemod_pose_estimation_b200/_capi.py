@@ -72,6 +72,7 @@ EXPORTS = [
     "lm_num_modalities", "lm_get_modality", "lm_num_classes", "lm_num_templates", "lm_class_id", "lm_get_templates",
     "lm_modality_process", "lm_qpyramid_destroy", "lm_qpyramid_levels", "lm_qpyramid_size", "lm_qpyramid_quantize", "lm_qpyramid_extract",
     "lm_add_template", "lm_add_template_from_quantized", "lm_add_synthetic_template", "lm_match", "lm_match_multi", "lm_match_batch", "lm_match_batch_multi", "lm_free_matches",
+    "lm_stream_open", "lm_stream_push", "lm_stream_pop", "lm_stream_in_flight", "lm_stream_close",
     "lm_match_device", "lm_match_device_multi", "lm_match_device_multi_lane", "lm_device_result_region", "lm_copy_result_block", "lm_match_device_stream", "lm_finalize_raw", "lm_finalize_gathered", "lm_upload_images", "lm_set_shard", "lm_set_similarity_lut", "lm_get_similarity_lut",
     "lm_set_normal_lut", "lm_get_normal_lut", "lm_load_normal_lut_file", "lm_debug_fetch", "lm_build_front", "lm_level_geometry",
     "lm_mesh_create", "lm_mesh_load_stl", "lm_mesh_num_triangles", "lm_mesh_get_triangles", "lm_mesh_destroy", "lm_view_count", "lm_view_params",
@@ -151,6 +152,12 @@ def lib():
     L.lm_match_batch_multi.argtypes = [vp, C.POINTER(LmImage), ci, ci, C.POINTER(LmQuery), ci, C.POINTER(vp),
                                        C.POINTER(C.c_size_t)]
     L.lm_free_matches.argtypes = [vp]
+    L.lm_stream_open.argtypes = [vp, C.POINTER(LmQuery), ci, C.POINTER(vp)]
+    L.lm_stream_push.argtypes = [vp, C.POINTER(LmImage), ci, ci]
+    L.lm_stream_pop.argtypes = [vp, ci, ci, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(ci)]
+    L.lm_stream_in_flight.argtypes = [vp]
+    L.lm_stream_close.argtypes = [vp]
+    L.lm_stream_close.restype = None
     L.lm_free_matches.restype = None
     L.lm_match_device.argtypes = [vp, C.POINTER(vp), ci, ci, ci, C.c_float, C.POINTER(cp), ci, vp, C.POINTER(vp),
                                   C.POINTER(C.c_size_t)]

@@ -8,6 +8,8 @@
 #include "lm_detector_internal.hpp"
 
 #include <cctype>
+#include <deque>
+#include <memory>
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -1473,6 +1475,7 @@ static int frames_from_host(lm_detector* d, Lane& ln, const lm_image* sources, i
 
 int lm_build_front(lm_detector* d, const lm_image* sources, int n_sources, const lm_image* masks, int n_masks) {
   if (!d || !sources) return lm_fail(LM_E_INVALID, "NULL argument");
+  if (d->stream_open) return lm_fail(LM_E_STATE, "the handle has an open lm_stream: close it before other matching calls");
   Lane& ln = d->lane[0];
   int rc = frames_from_host(d, ln, sources, 1, n_sources, masks, n_masks);
   if (rc != LM_OK) return rc;
@@ -1496,6 +1499,7 @@ int lm_match_multi(lm_detector* d, const lm_image* sources, int n_sources, const
                    const lm_image* masks, int n_masks, lm_image_out* quantized_out, lm_match_rec** out_matches,
                    size_t* out_offsets) {
   if (!d || !sources || !out_matches || !out_offsets) return lm_fail(LM_E_INVALID, "NULL argument");
+  if (d->stream_open) return lm_fail(LM_E_STATE, "the handle has an open lm_stream: close it before other matching calls");
   *out_matches = nullptr;
   Query qs[kMaxQueries];
   int rc = to_queries(queries, n_queries, qs);
@@ -1555,42 +1559,42 @@ static int prepare_lane(lm_detector* d, Lane& ln, int rows, int cols, int frames
 
 // Frames in chunks of `batch_frames`, chunks pipelined over `batch_lanes` workspace lanes: while one chunk's kernels run,
 // the next chunk's frames are copied to the device and the previous chunk's survivors are ordered on the host.  Every
-// kernel launch covers a whole chunk.  out_offsets: n_frames * n_q + 1 prefix offsets, frame-major.
-//
-// raw_frames (nullable): instead of finalised lists, frame f's un-ordered survivor records go to (*raw_frames)[f] -- what a
-// template-sharded caller merges across shards before the reference's sort + unique (out_matches / out_offsets unused).
-static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frames, int n_sources, const Query* qs, int n_q,
-                            lm_match_rec** out_matches, size_t* out_offsets,
-                            std::vector<std::vector<lm_raw_match> >* raw_frames = nullptr) {
-  if (out_matches) *out_matches = nullptr;
-  if (n_q < 1 || n_q > kMaxQueries) return lm_fail(LM_E_INVALID, "number of queries must be 1..%d", kMaxQueries);
-  if (out_offsets) out_offsets[0] = 0;
-  if (raw_frames) raw_frames->assign((size_t)n_frames, std::vector<lm_raw_match>());
-  if (n_frames == 0) { size_t n = 0; return raw_frames ? LM_OK : copy_out(std::vector<lm_match_rec>(), out_matches, &n); }
-  if (set_device(d) != LM_OK) return LM_E_CUDA;
-  const int F = std::max(1, std::min(d->batch_frames, LM_MAX_BATCH));
-  const int NL = std::max(1, std::min(d->batch_lanes, LM_LANES));
-  // Chunk boundaries.  The first chunks of a call ramp up (2, 2, 4, ... frames): the GPU starts on the call's first frames
-  // after two frames' worth of host->device copy instead of a whole chunk's, which is the bubble between two calls.
-  std::vector<int> chunk_first;
-  for (int at = 0, step = std::min(F, 2), k = 0; at < n_frames; ++k) {
-    chunk_first.push_back(at);
-    at += std::min(step, n_frames - at);
-    if (k >= 1 && step < F) step = std::min(F, step * 2);
-  }
-  chunk_first.push_back(n_frames);
-  const int n_chunks = (int)chunk_first.size() - 1;
-  // per (frame, query) result lists, concatenated at the end (chunks finish in order, but a frame may be redone)
-  std::vector<std::vector<lm_match_rec> > lists((size_t)n_frames * n_q);
-  struct Pending { int first = -1, n = 0; const Pack::Plan* plan = nullptr; } pending[LM_LANES];
+// kernel launch covers a whole chunk.  BatchPipe is that pipeline: lm_match_batch* runs one to completion per call,
+// lm_stream keeps one alive between calls so that the device never drains at a call boundary.
+struct BatchPipe {
+  lm_detector* d = nullptr;
+  Query qs[kMaxQueries];
+  int n_q = 0, F = 8, NL = 4, ws_frames = 8;
+  bool use_pool = false;
+  // raw mode (nullable): instead of finalised lists, frame f's un-ordered survivor records go to (*raw_frames)[f] -- what a
+  // template-sharded caller merges across shards before the reference's sort + unique
+  std::vector<std::vector<lm_raw_match> >* raw_frames = nullptr;
+  // per frame the n_q result lists (contiguous: the finalisers write lists[q]) of the frames [base, base + lists.size()).
+  // A deque: finalizer jobs hold pointers into its elements, which stay put while the container grows at the back and
+  // shrinks at the front.
+  std::deque<std::vector<std::vector<lm_match_rec> > > lists;
+  long long base = 0, submitted = 0, finished = 0, chunks = 0;   // frame / chunk counters since the pipe was set up
+  struct Pending { long long first = -1; int n = 0; const Pack::Plan* plan = nullptr; } pending[LM_LANES];
   std::vector<FrameRecords> got;
-  const bool use_pool = !raw_frames && d->finalize_threads > 0 && n_frames > 1;
-  if (use_pool) d->finalizers.start(std::min(d->finalize_threads, 16));
-  struct PoolGuard {  // every job writes into `lists`: none may outlive this call, whichever way it returns
-    FinalizePool* p;
-    ~PoolGuard() { if (p) p->wait_all(); }
-  } pool_guard = {use_pool ? &d->finalizers : nullptr};
-  auto finish = [&](int li) -> int {
+  bool prof = false;
+  double t_fin = 0, t_up = 0, t_enq = 0;
+  static double now() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+  int setup(lm_detector* det, const Query* queries, int n_queries, int total_frames, bool pool) {
+    d = det; n_q = n_queries;
+    for (int q = 0; q < n_q; ++q) qs[q] = queries[q];
+    F = std::max(1, std::min(d->batch_frames, LM_MAX_BATCH));
+    NL = std::max(1, std::min(d->batch_lanes, LM_LANES));
+    ws_frames = total_frames > 0 ? std::min(F, total_frames) : F;
+    use_pool = pool && d->finalize_threads > 0;
+    if (use_pool) d->finalizers.start(std::min(d->finalize_threads, 16));
+    prof = getenv("LM_HOST_PROFILE") != nullptr;
+    return LM_OK;
+  }
+  std::vector<lm_match_rec>* list_of(long long frame) { return lists[(size_t)(frame - base)].data(); }
+
+  // The lane's chunk is complete on the device: its survivors become lists (ordered here or on a finalizer thread).
+  int finish(int li) {
     Lane& ln = d->lane[li];
     const Pending pd = pending[li];
     pending[li].first = -1;
@@ -1606,10 +1610,10 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
       else if (use_pool) {  // ordered on a finalizer thread while this thread goes on feeding the device
         std::shared_ptr<std::vector<lm_raw_match> > raw = std::make_shared<std::vector<lm_raw_match> >();
         raw->swap(got[(size_t)f].raw);
-        std::vector<lm_match_rec>* dst = &lists[(size_t)(pd.first + f) * n_q];
-        const int levels = d->model.levels();
-        d->finalizers.submit([raw, dst, levels, n_q]() { lm_internal_finalize(levels, *raw, n_q, dst); });
-      } else finalize_queries(d, ln, got[(size_t)f].raw, n_q, &lists[(size_t)(pd.first + f) * n_q]);
+        std::vector<lm_match_rec>* dst = list_of(pd.first + f);
+        const int levels = d->model.levels(), nq = n_q;
+        d->finalizers.submit([raw, dst, levels, nq]() { lm_internal_finalize(levels, *raw, nq, dst); });
+      } else finalize_queries(d, ln, got[(size_t)f].raw, n_q, list_of(pd.first + f));
     }
     // work accounting of the chunk (lm_last_work reads lane 0): B_coarse of all its frames, candidates, evals, frames
     ln.work_stats[1] = pd.plan->coarse_bytes * (uint64_t)pd.n;
@@ -1619,53 +1623,194 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
     ln.work_stats[3] = 20ull * survivors;
     ln.work_stats[7] = (uint64_t)pd.n;
     for (int f : redo) {  // rare: this frame alone with growing buffers (its sources are still in the lane's slot f)
-      int rc = match_one(d, ln, f, qs, n_q, &lists[(size_t)(pd.first + f) * n_q], false,
+      int rc = match_one(d, ln, f, qs, n_q, raw_frames ? nullptr : list_of(pd.first + f), false,
                          raw_frames ? &(*raw_frames)[(size_t)(pd.first + f)] : nullptr);
       if (rc != LM_OK) return rc;
     }
+    finished = pd.first + pd.n;   // chunks finish in submission order
     return LM_OK;
-  };
-  const bool prof = getenv("LM_HOST_PROFILE") != nullptr;
-  double t_fin = 0, t_up = 0, t_enq = 0;
-  auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  for (int c = 0; c < n_chunks; ++c) {
-    const int li = c % NL;
+  }
+
+  // One chunk of n <= F host frames (fs[f * n_sources + m]): waits for the lane's previous chunk, uploads, enqueues.
+  int submit(const lm_image* fs, int n, int n_sources) {
+    const int li = (int)(chunks % NL);
     Lane& ln = d->lane[li];
-    const int first = chunk_first[(size_t)c], n = chunk_first[(size_t)c + 1] - first;
     double t0 = prof ? now() : 0;
     // the lane's previous chunk must be done before its source slots and pinned staging are overwritten
     if (pending[li].first >= 0) { int rc = finish(li); if (rc != LM_OK) return rc; }
     double t1 = prof ? now() : 0;
-    const lm_image* fs = sources + (size_t)first * n_sources;
     int rc = check_sources(d, fs, n_sources, nullptr, 0);
     if (rc != LM_OK) return rc;
     Pack::Plan* plan = nullptr;
-    rc = prepare_lane(d, ln, fs[0].rows, fs[0].cols, std::min(F, n_frames), qs, n_q, kOutPerFrame, &plan);
+    rc = prepare_lane(d, ln, fs[0].rows, fs[0].cols, ws_frames, qs, n_q, kOutPerFrame, &plan);
     if (rc != LM_OK) return rc;
     rc = frames_from_host(d, ln, fs, n, n_sources, nullptr, 0);
     if (rc != LM_OK) return rc;
     double t2 = prof ? now() : 0;
+    if (!raw_frames)
+      for (int f = 0; f < n; ++f) lists.emplace_back((size_t)n_q);
     if (enqueue_chunk(d, ln, *plan, qs, n_q, n, ln.stream, d->timing != 0) != LM_OK) return LM_E_CUDA;
     if (enqueue_download(ln, n, ln.stream) != LM_OK) return LM_E_CUDA;
-    pending[li].first = first; pending[li].n = n; pending[li].plan = plan;
+    pending[li].first = submitted; pending[li].n = n; pending[li].plan = plan;
+    submitted += n; ++chunks;
     if (prof) { double t3 = now(); t_fin += t1 - t0; t_up += t2 - t1; t_enq += t3 - t2; }
+    return LM_OK;
   }
-  for (int k = 0; k < NL; ++k) {  // drain in submission order
-    const int li = (n_chunks + k) % NL;
-    if (pending[li].first >= 0) { int rc = finish(li); if (rc != LM_OK) return rc; }
+  // the oldest chunk in flight, or -1
+  int oldest() const {
+    int best = -1;
+    for (int li = 0; li < LM_LANES; ++li)
+      if (pending[li].first >= 0 && (best < 0 || pending[li].first < pending[best].first)) best = li;
+    return best;
   }
-  if (prof)
-    fprintf(stderr, "[lm host profile] per frame us: finish %.1f upload %.1f enqueue %.1f\n", t_fin / n_frames, t_up / n_frames,
-            t_enq / n_frames);
+  int drain() {   // in submission order
+    for (int li = oldest(); li >= 0; li = oldest()) { int rc = finish(li); if (rc != LM_OK) return rc; }
+    return LM_OK;
+  }
+  int finish_ready() {   // without blocking: the oldest chunks whose survivors have already reached the host
+    for (int li = oldest(); li >= 0; li = oldest()) {
+      const cudaError_t e = cudaEventQuery(d->lane[li].ev[5]);
+      if (e == cudaErrorNotReady) break;
+      if (e != cudaSuccess) return lm_fail(LM_E_CUDA, "CUDA error: %s", cudaGetErrorString(e));
+      int rc = finish(li);
+      if (rc != LM_OK) return rc;
+    }
+    return LM_OK;
+  }
+  void abandon() {   // error paths: nothing of this pipe may stay in flight or keep pointers into `lists`
+    for (int li = 0; li < LM_LANES; ++li)
+      if (pending[li].first >= 0) { lane_quiesce(d->lane[li]); pending[li].first = -1; }
+    if (use_pool) d->finalizers.wait_all();
+  }
+};
+
+// out_offsets: n_frames * n_q + 1 prefix offsets, frame-major.  raw_frames: see BatchPipe.
+static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frames, int n_sources, const Query* qs, int n_q,
+                            lm_match_rec** out_matches, size_t* out_offsets,
+                            std::vector<std::vector<lm_raw_match> >* raw_frames = nullptr) {
+  if (out_matches) *out_matches = nullptr;
+  if (n_q < 1 || n_q > kMaxQueries) return lm_fail(LM_E_INVALID, "number of queries must be 1..%d", kMaxQueries);
+  if (out_offsets) out_offsets[0] = 0;
+  if (raw_frames) raw_frames->assign((size_t)n_frames, std::vector<lm_raw_match>());
+  if (n_frames == 0) { size_t n = 0; return raw_frames ? LM_OK : copy_out(std::vector<lm_match_rec>(), out_matches, &n); }
+  if (d->stream_open) return lm_fail(LM_E_STATE, "the handle has an open lm_stream: close it before other matching calls");
+  if (set_device(d) != LM_OK) return LM_E_CUDA;
+  BatchPipe pipe;
+  pipe.raw_frames = raw_frames;
+  pipe.setup(d, qs, n_q, n_frames, !raw_frames && n_frames > 1);
+  struct Guard {  // nothing may outlive this call, whichever way it returns
+    BatchPipe* p;
+    ~Guard() { p->abandon(); }
+  } guard = {&pipe};
+  // Chunk boundaries.  The first chunks of a call ramp up (2, 2, 4, ... frames): the GPU starts on the call's first frames
+  // after two frames' worth of host->device copy instead of a whole chunk's, which is the bubble between two calls.
+  const int F = pipe.F;
+  for (int at = 0, step = std::min(F, 2), k = 0; at < n_frames; ++k) {
+    const int n = std::min(step, n_frames - at);
+    int rc = pipe.submit(sources + (size_t)at * n_sources, n, n_sources);
+    if (rc != LM_OK) return rc;
+    at += n;
+    if (k >= 1 && step < F) step = std::min(F, step * 2);
+  }
+  int rc = pipe.drain();
+  if (rc != LM_OK) return rc;
+  if (pipe.prof)
+    fprintf(stderr, "[lm host profile] per frame us: finish %.1f upload %.1f enqueue %.1f\n", pipe.t_fin / n_frames, pipe.t_up / n_frames,
+            pipe.t_enq / n_frames);
   if (raw_frames) return LM_OK;
-  if (use_pool) d->finalizers.wait_all();
+  if (pipe.use_pool) d->finalizers.wait_all();
   std::vector<lm_match_rec> all;
-  for (size_t i = 0; i < lists.size(); ++i) {
-    all.insert(all.end(), lists[i].begin(), lists[i].end());
-    out_offsets[i + 1] = all.size();
-  }
+  for (size_t f = 0; f < pipe.lists.size(); ++f)
+    for (int q = 0; q < n_q; ++q) {
+      all.insert(all.end(), pipe.lists[f][(size_t)q].begin(), pipe.lists[f][(size_t)q].end());
+      out_offsets[f * (size_t)n_q + (size_t)q + 1] = all.size();
+    }
   size_t n = 0;
   return copy_out(all, out_matches, &n);
+}
+
+// ---------------------------------------------------------------------------------------------- streams of host frames
+struct lm_stream {
+  lm_detector* d = nullptr;
+  BatchPipe pipe;
+  std::vector<std::vector<std::string> > ids;       // the queries' class ids, owned
+  std::vector<std::vector<const char*> > id_ptrs;
+  int n_sources = 0;
+  bool failed = false;
+};
+
+int lm_stream_open(lm_detector* d, const lm_query* queries, int n_queries, lm_stream** out) {
+  if (!d || !out) return lm_fail(LM_E_INVALID, "NULL argument");
+  *out = nullptr;
+  if (d->stream_open) return lm_fail(LM_E_STATE, "the handle already has an open lm_stream");
+  Query qs[kMaxQueries];
+  int rc = to_queries(queries, n_queries, qs);
+  if (rc != LM_OK) return rc;
+  if (set_device(d) != LM_OK) return LM_E_CUDA;
+  std::unique_ptr<lm_stream> s(new lm_stream());
+  s->d = d;
+  s->ids.resize((size_t)n_queries); s->id_ptrs.resize((size_t)n_queries);
+  for (int q = 0; q < n_queries; ++q) {
+    for (int i = 0; i < qs[q].n_ids; ++i) {
+      if (!qs[q].class_ids[i]) return lm_fail(LM_E_INVALID, "class_ids[%d] is NULL", i);
+      s->ids[(size_t)q].push_back(qs[q].class_ids[i]);
+    }
+    for (const std::string& id : s->ids[(size_t)q]) s->id_ptrs[(size_t)q].push_back(id.c_str());
+    qs[q].class_ids = s->id_ptrs[(size_t)q].data();
+  }
+  s->pipe.setup(d, qs, n_queries, 0, true);
+  d->stream_open = true;
+  *out = s.release();
+  return LM_OK;
+}
+
+int lm_stream_push(lm_stream* s, const lm_image* sources, int n_frames, int n_sources) {
+  if (!s || (!sources && n_frames > 0) || n_frames < 0) return lm_fail(LM_E_INVALID, "NULL argument");
+  if (s->failed) return lm_fail(LM_E_STATE, "the stream failed earlier: close it");
+  if (set_device(s->d) != LM_OK) return LM_E_CUDA;
+  for (int at = 0; at < n_frames;) {
+    // a stream's very first chunks ramp up like a batch call's; after that every chunk is full
+    int n = std::min(s->pipe.F, n_frames - at);
+    if (s->pipe.chunks < 2) n = std::min(n, 2);
+    else if (s->pipe.chunks == 2) n = std::min(n, 4);
+    int rc = s->pipe.submit(sources + (size_t)at * n_sources, n, n_sources);
+    if (rc != LM_OK) { s->failed = true; s->pipe.abandon(); return rc; }
+    at += n;
+  }
+  return LM_OK;
+}
+
+int lm_stream_pop(lm_stream* s, int wait_all, int max_frames, lm_match_rec** out_matches, size_t* out_offsets, int* n_frames_out) {
+  if (!s || !out_matches || !out_offsets || !n_frames_out) return lm_fail(LM_E_INVALID, "NULL argument");
+  *out_matches = nullptr; *n_frames_out = 0; out_offsets[0] = 0;
+  if (s->failed) return lm_fail(LM_E_STATE, "the stream failed earlier: close it");
+  if (set_device(s->d) != LM_OK) return LM_E_CUDA;
+  BatchPipe& p = s->pipe;
+  int rc = wait_all ? p.drain() : p.finish_ready();
+  if (rc != LM_OK) { s->failed = true; p.abandon(); return rc; }
+  if (p.use_pool) s->d->finalizers.wait_all();
+  const long long ready = std::min<long long>(p.finished - p.base, std::max(0, max_frames));
+  std::vector<lm_match_rec> all;
+  for (long long f = 0; f < ready; ++f)
+    for (int q = 0; q < p.n_q; ++q) {
+      const std::vector<lm_match_rec>& l = p.lists[(size_t)f][(size_t)q];
+      all.insert(all.end(), l.begin(), l.end());
+      out_offsets[f * p.n_q + q + 1] = all.size();
+    }
+  p.lists.erase(p.lists.begin(), p.lists.begin() + (size_t)ready);
+  p.base += ready;
+  *n_frames_out = (int)ready;
+  size_t n = 0;
+  return copy_out(all, out_matches, &n);
+}
+
+int lm_stream_in_flight(const lm_stream* s) { return s ? (int)(s->pipe.submitted - s->pipe.base) : 0; }
+
+void lm_stream_close(lm_stream* s) {
+  if (!s) return;
+  if (set_device(s->d) == LM_OK) s->pipe.abandon();
+  s->d->stream_open = false;
+  delete s;
 }
 
 // Internal entry points of lm_group.cu (a handle per device, driven from the group's worker threads).
@@ -1695,6 +1840,7 @@ lm_detector* lm_internal_clone(const lm_detector* src) {
   d->device_out_cap = src->device_out_cap; d->cand_per_frame = src->cand_per_frame;
   d->prune = src->prune; d->graphs = src->graphs; d->mod_order = src->mod_order;
   d->batch_frames = src->batch_frames; d->batch_lanes = src->batch_lanes; d->finalize_threads = src->finalize_threads;
+  d->refine_tiled = src->refine_tiled;
   refresh_class_cache(d);
   return d;
 }
@@ -1720,6 +1866,7 @@ void lm_free_matches(lm_match_rec* m) { std::free(m); }
 // A chunk of device-resident frames on one lane and the caller's stream: nothing is uploaded, copied or synchronised.
 static int device_chunk(lm_detector* d, int lane_index, const void* const* d_sources, int n_frames, int n_sources, int rows,
                         int cols, const Query* qs, int n_q, int ws_frames, cudaStream_t s) {
+  if (d->stream_open) return lm_fail(LM_E_STATE, "the handle has an open lm_stream: close it before other matching calls");
   if (lane_index < 0 || lane_index >= LM_LANES) return lm_fail(LM_E_INVALID, "lane must be 0..%d", LM_LANES - 1);
   if (n_sources != d->model.M()) return lm_fail(LM_E_INVALID, "sources.size() (%d) != modalities.size() (%d)", n_sources, d->model.M());
   if (n_frames < 1 || n_frames > LM_MAX_BATCH) return lm_fail(LM_E_INVALID, "a chunk holds 1..%d frames", LM_MAX_BATCH);

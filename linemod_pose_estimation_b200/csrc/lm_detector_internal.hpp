@@ -329,6 +329,7 @@ struct lm_detector {
   int batch_lanes = 4;   // chunks in flight on the batched host path
   int mod_order = 2;  // coarse kernel: 0 = modalities in template order, 1 = reversed, 2 = chosen per frame (default)
   int refine_tiled = 1;  // refinement levels with W % 16 == 0 and H >= 16 keep their nibble planes column-blocked
+  bool stream_open = false;  // an lm_stream owns the lanes: other matching calls are refused until it is closed
   std::vector<std::string> class_id_cache;
 };
 

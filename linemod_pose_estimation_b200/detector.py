@@ -314,6 +314,10 @@ class Detector:
         allm = self._take(out, offs[len(frames) * n_q])
         return [[allm[offs[f * n_q + q]:offs[f * n_q + q + 1]] for q in range(n_q)] for f in range(len(frames))]
 
+    def open_stream(self, queries):
+        """A continuous stream of host frames answered for `queries` [(threshold, [class ids])]: see FrameStream."""
+        return FrameStream(self, queries)
+
     def match_device(self, d_ptrs, rows, cols, threshold, stream=0, class_ids=()):
         """Device-resident sources (tightly packed), asynchronous on `stream`.  -> (device pointer of the record
         block {count, capacity, overflow, n_cands} + raw records, capacity in bytes)."""
@@ -495,3 +499,64 @@ class DetectorGroup:
 
     def match(self, sources, threshold, class_ids=()):
         return self.match_batch_multi([sources], [(threshold, list(class_ids))])[0][0]
+
+
+class FrameStream:
+    """lm_stream: the chunked pipeline of match_batch_multi kept alive between calls (the device never drains at a call
+    boundary).  push() enqueues frames and returns; pop() hands out finished frames in push order as
+    [per frame [per query match array]].  The arrays passed to push() must stay unchanged until pop() has returned their
+    frames.  While the stream is open the detector refuses other matching calls."""
+
+    def __init__(self, det, queries):
+        self._det = det
+        self._n_q = len(queries)
+        qarr, self._qkeep = _capi.query_array(queries)
+        self._h = C.c_void_p()
+        check(lib().lm_stream_open(det._h, qarr, self._n_q, C.byref(self._h)))
+        self._keep = []   # (frames still in flight, image array + numpy buffers) per push
+
+    def push(self, frames):
+        flat = [s for f in frames for s in f]
+        arr, keep = image_array(flat)
+        self._keep.append([len(frames), (arr, keep, flat)])
+        check(lib().lm_stream_push(self._h, arr, len(frames), len(frames[0]) if frames else 0))
+
+    def push_array(self, arr, n_frames, n_sources):
+        """A prebuilt lm_image array (image_array of pinned buffers the caller keeps alive): no per-call marshalling."""
+        check(lib().lm_stream_push(self._h, arr, n_frames, n_sources))
+
+    def in_flight(self):
+        return lib().lm_stream_in_flight(self._h)
+
+    def pop(self, wait_all=False, max_frames=None):
+        cap = max(1, self.in_flight() if max_frames is None else max_frames)
+        out, n = C.c_void_p(), C.c_int()
+        offs = (C.c_size_t * (cap * self._n_q + 1))()
+        check(lib().lm_stream_pop(self._h, 1 if wait_all else 0, cap, C.byref(out), offs, C.byref(n)))
+        allm = self._det._take(out, offs[n.value * self._n_q])
+        left = n.value
+        while left > 0 and self._keep:
+            take = min(left, self._keep[0][0])
+            self._keep[0][0] -= take
+            left -= take
+            if self._keep[0][0] == 0:
+                self._keep.pop(0)
+        return [[allm[offs[f * self._n_q + q]:offs[f * self._n_q + q + 1]] for q in range(self._n_q)] for f in range(n.value)]
+
+    def close(self):
+        if self._h:
+            lib().lm_stream_close(self._h)
+            self._h = C.c_void_p()
+            self._keep = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

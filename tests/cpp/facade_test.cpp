@@ -240,6 +240,41 @@ static int run_gpu(const std::string& dir) {
       REQUIRE(one.size() == want_r.size());
     }
   }
+  // a stream of host frames (lm_stream): frames pushed in pieces, finished frames popped in order, equal to match() per frame;
+  // while the stream is open the detector refuses other matching calls
+  {
+    std::vector<std::vector<lm::Image> > batch(11, rframe);
+    batch[1] = frame; batch[3] = frame; batch[10] = frame;
+    std::vector<lm::Match> want_r, want_f;
+    trained->match(rframe, 90.f, want_r);
+    trained->match(frame, 90.f, want_f);
+    REQUIRE(lm_set_option(trained->handle(), "batch_frames", 4) == LM_OK);
+    {
+      lm::FrameStream stream(*trained, 90.f);
+      bool refused = false;
+      try { std::vector<lm::Match> tmp; trained->match(rframe, 90.f, tmp); } catch (const lm::Exception& e) { refused = e.code == LM_E_STATE; }
+      REQUIRE(refused);
+      std::vector<std::vector<lm::Match> > got, part;
+      stream.push(std::vector<std::vector<lm::Image> >(batch.begin(), batch.begin() + 3));
+      stream.push(std::vector<std::vector<lm::Image> >(batch.begin() + 3, batch.begin() + 9));
+      stream.pop(part);                       // whatever is ready
+      got.insert(got.end(), part.begin(), part.end());
+      stream.push(std::vector<std::vector<lm::Image> >(batch.begin() + 9, batch.end()));
+      REQUIRE(stream.inFlight() == (int)(batch.size() - got.size()));
+      stream.pop(part, true);                 // the rest
+      got.insert(got.end(), part.begin(), part.end());
+      REQUIRE(got.size() == batch.size() && stream.inFlight() == 0);
+      for (size_t f = 0; f < got.size(); ++f) {
+        const std::vector<lm::Match>& want = (f == 1 || f == 3 || f == 10) ? want_f : want_r;
+        REQUIRE(got[f].size() == want.size());
+        for (size_t i = 0; i < want.size(); ++i) REQUIRE(got[f][i] == want[i] && got[f][i].template_id == want[i].template_id);
+      }
+    }
+    std::vector<lm::Match> again;
+    trained->match(rframe, 90.f, again);      // the stream is closed: the handle answers again
+    REQUIRE(again.size() == want_r.size());
+    REQUIRE(lm_set_option(trained->handle(), "batch_frames", 8) == LM_OK);
+  }
   std::printf("ok gpu (%zu matches, best %.2f at %d,%d)\n", matches.size(), best.similarity, best.x, best.y);
   return 0;
 }

@@ -516,6 +516,44 @@ def test_batch_multi_equals_per_frame_multi():
     assert det.match_batch_multi([], queries) == []
 
 
+@pytest.mark.parametrize("batch_frames,lanes", [(8, 4), (3, 2), (1, 1)])
+def test_frame_stream_equals_the_oracle(batch_frames, lanes):
+    """lm_stream: frames pushed in uneven pieces with pops in between (blocking and not) come back in push order with the
+    oracle's lists for every query; a frame whose survivors outgrow the head of its result block is redone inside the stream;
+    the detector refuses other matching calls while the stream is open and answers again after close()."""
+    orc, det, views = _pair(n_views=8, n_random=40, seed=79, classes=("cpu_binary", "memoryChip2"))
+    det.set_option("batch_frames", batch_frames)
+    det.set_option("batch_lanes", lanes)
+    queries = [(90.0, ["memoryChip2"]), (62.0, [])]
+    frames = []
+    for seed in range(3100, 3123):
+        bgr, depth, _ = synth.compose_scene(seed, views[:5])
+        frames.append([bgr, depth])
+    want = [[orc.match(f, thr, class_ids=ids) for thr, ids in queries] for f in frames]
+    got = []
+    with det.open_stream(queries) as st:
+        with pytest.raises(LinemodError):
+            det.match(frames[0], 90.0)
+        at = 0
+        for piece in (1, 5, 2, 9, 6):
+            st.push(frames[at:at + piece])
+            at += piece
+            assert st.in_flight() == at - len(got)
+            got += st.pop()                      # what is ready, without blocking
+        assert at == len(frames)
+        got += st.pop(wait_all=True, max_frames=2)   # at most two of the rest ...
+        got += st.pop(wait_all=True)                 # ... then all of it
+        assert st.in_flight() == 0 and st.pop() == []
+    assert len(got) == len(frames)
+    total = 0
+    for f, (g, w) in enumerate(zip(got, want)):
+        for q in range(len(queries)):
+            common.assert_matches_equal(g[q], w[q], "frame %d query %d" % (f, q))
+            total += len(g[q])
+    assert total > 0
+    common.assert_matches_equal(det.match(frames[0], 62.0), want[0][1], "after close")
+
+
 def test_sharded_stream_single_rank():
     """ShardedDetector.match_stream (chunked upload, lanes, staged survivor exchange) at world size 1 == lm_match_multi per
     frame; the collectives themselves are exercised at world size 2 on CPU (tests/test_sharding_gloo.py) and by bench.py."""

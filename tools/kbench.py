@@ -123,6 +123,25 @@ def main():
         for _ in range(reps):
             host_pass()
         e2e_us = 1e6 * (time.perf_counter() - t0) / (reps * args.pool)
+        # the same through lm_stream: the pipeline stays alive between pushes of `pool` frames
+        sh = C.c_void_p()
+        _capi.check(lib.lm_stream_open(det._h, qarr, n_q, C.byref(sh)))
+        soffs = (C.c_size_t * (4 * args.pool * n_q + 1))()
+        n_pop = C.c_int()
+
+        def stream_pass(n_push):
+            for _ in range(n_push):
+                _capi.check(lib.lm_stream_push(sh, harr, args.pool, 2))
+                _capi.check(lib.lm_stream_pop(sh, 0, 4 * args.pool, C.byref(out_p), soffs, C.byref(n_pop)))
+                lib.lm_free_matches(out_p)
+            while lib.lm_stream_in_flight(sh) > 0:
+                _capi.check(lib.lm_stream_pop(sh, 1, 4 * args.pool, C.byref(out_p), soffs, C.byref(n_pop)))
+                lib.lm_free_matches(out_p)
+        stream_pass(1)
+        t0 = time.perf_counter()
+        stream_pass(reps)
+        stream_us = 1e6 * (time.perf_counter() - t0) / (reps * args.pool)
+        lib.lm_stream_close(sh)
         one, _k1 = _capi.image_array(list(host[0]))
         offs1 = (C.c_size_t * (n_q + 1))()
         lat = []
@@ -138,7 +157,7 @@ def main():
         t, w = det.last_timings(), det.last_work()
         det.set_option("timing", 0)
         fr = max(1, w["frames"])
-        out = {"workload": args.workload, "config": cfg, "templates": det.numTemplates(), "device_us_per_frame": round(dev_us, 2), "e2e_us_per_frame": round(e2e_us, 2),
+        out = {"workload": args.workload, "config": cfg, "templates": det.numTemplates(), "device_us_per_frame": round(dev_us, 2), "e2e_us_per_frame": round(e2e_us, 2), "stream_e2e_us_per_frame": round(stream_us, 2),
                "single_call_us": round(single_us, 1), "chunk_frames": fr, "launches_per_chunk": t["launches"],
                "gathered_frac": round(w["B_coarse_gathered"] / max(1, w["B_coarse"]), 4), "candidates_per_frame": w["candidates"] / fr,
                "matches_per_frame": sum(len(x) for x in res) / args.pool}
