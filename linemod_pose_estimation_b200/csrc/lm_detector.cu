@@ -551,7 +551,7 @@ static int get_plan(lm_detector* d, const Query* qs, int n_q, Pack::Plan** out) 
   auto hit = pk.plans.find(key);
   if (hit != pk.plans.end()) { *out = &hit->second; return LM_OK; }
   std::vector<WorkItem> items;
-  struct Tile { uint2 t; uint64_t cost; };
+  struct Tile { uint2 t; uint64_t cost; int positions; };
   std::vector<Tile> tiles;
   Pack::Plan plan;
   const int pass_pos = coarse_positions_per_pass();
@@ -567,7 +567,8 @@ static int get_plan(lm_detector* d, const Query* qs, int n_q, Pack::Plan** out) 
       for (int pass = 0; pass * pass_pos < ct.P; ++pass) {
         Tile t;
         t.t.x = (uint32_t)items.size(); t.t.y = (uint32_t)pass;
-        t.cost = nfeat * (uint64_t)std::min(pass_pos, ct.P - pass * pass_pos);
+        t.positions = std::min(pass_pos, ct.P - pass * pass_pos);
+        t.cost = nfeat * (uint64_t)t.positions;
         tiles.push_back(t);
       }
       items.push_back(it);
@@ -592,9 +593,19 @@ static int get_plan(lm_detector* d, const Query* qs, int n_q, Pack::Plan** out) 
     }
   }
   if (items.size() >= (1u << 28)) return lm_fail(LM_E_INVALID, "too many templates in one request");
-  std::stable_sort(tiles.begin(), tiles.end(), [](const Tile& a, const Tile& b) { return a.cost > b.cost; });
+  // full tiles first, heaviest first; then the tiles of at most 128 positions (the tail pass of templates whose span exceeds
+  // one pass), which the coarse kernel scores for eight frames per warp
+  const bool share = d->coarse_share != 0;
+  std::stable_sort(tiles.begin(), tiles.end(), [share](const Tile& a, const Tile& b) {
+    const bool sa = share && a.positions <= 128, sb = share && b.positions <= 128;
+    if (sa != sb) return sb;
+    return a.cost > b.cost;
+  });
   std::vector<uint2> tl(tiles.size());
-  for (size_t i = 0; i < tiles.size(); ++i) tl[i] = tiles[i].t;
+  for (size_t i = 0; i < tiles.size(); ++i) {
+    tl[i] = tiles[i].t;
+    if (!(share && tiles[i].positions <= 128)) plan.n_full = (int)i + 1;
+  }
   plan.n_items = (int)items.size();
   plan.n_tiles = (int)tl.size();
   plan.evals = (uint64_t)items.size();
@@ -657,7 +668,7 @@ static int enqueue_match(lm_detector* d, Lane& ln, const Pack::Plan& plan, const
   std::memset(&cp, 0, sizeof(cp));
   for (int q = 0; q < n_q; ++q) { cp.thr.v[q] = qs[q].threshold; rp.threshold[q] = qs[q].threshold; }
   cp.lmn = ln.lmn[L - 1].as<uint8_t>(); cp.lmn_stride = ln.lmn[L - 1].stride;
-  cp.recs = plan.recs.as<uint32_t>(); cp.rec_words = plan.rec_words; cp.n_tiles = plan.n_tiles; cp.max_feat = plan.max_feat;
+  cp.recs = plan.recs.as<uint32_t>(); cp.rec_words = plan.rec_words; cp.n_tiles = plan.n_tiles; cp.max_feat = plan.max_feat; cp.n_full = plan.n_full;
   cp.ctl = ln.ctl.as<BatchCtl>();
   cp.cand = ln.cand.as<Cand>(); cp.cand_cap = ln.cand_cap;
   cp.touched = ln.result.as<unsigned long long>();
@@ -1424,6 +1435,11 @@ int lm_set_option(lm_detector* d, const char* key, int value) {
   else if (k == "prune") d->prune = value;
   else if (k == "mod_order") d->mod_order = value & 3;
   else if (k == "refine_tiled") d->refine_tiled = value != 0;   // takes effect with the next request (workspace rebuilt)
+  else if (k == "coarse_share") {       // A/B switch: tail passes of <= 128 positions scored for eight frames per warp
+    d->coarse_share = value != 0;
+    d->pack.plans.clear();              // plans order their tiles by it (the lanes' graphs are keyed by the plan)
+    for (int i = 0; i < LM_LANES; ++i) d->lane[i].drop_graphs();
+  }
   else if (k == "graphs") d->graphs = value;
   else if (k == "batch_frames") {
     if (value < 1 || value > LM_MAX_BATCH) return lm_fail(LM_E_INVALID, "batch_frames must be 1..%d", LM_MAX_BATCH);
@@ -1840,7 +1856,7 @@ lm_detector* lm_internal_clone(const lm_detector* src) {
   d->device_out_cap = src->device_out_cap; d->cand_per_frame = src->cand_per_frame;
   d->prune = src->prune; d->graphs = src->graphs; d->mod_order = src->mod_order;
   d->batch_frames = src->batch_frames; d->batch_lanes = src->batch_lanes; d->finalize_threads = src->finalize_threads;
-  d->refine_tiled = src->refine_tiled;
+  d->refine_tiled = src->refine_tiled; d->coarse_share = src->coarse_share;
   refresh_class_cache(d);
   return d;
 }
@@ -2266,7 +2282,7 @@ int lm_debug_coarse_map(lm_detector* d, const char* class_id, int template_id, u
   std::memset(&cp, 0, sizeof(cp));
   for (int q = 0; q < LM_MAX_QUERIES; ++q) cp.thr.v[q] = 1e30f;
   cp.lmn = ln.lmn[d->model.levels() - 1].as<uint8_t>(); cp.lmn_stride = ln.lmn[d->model.levels() - 1].stride;
-  cp.recs = ln.dbg_recs.as<uint32_t>(); cp.rec_words = rec_words; cp.n_tiles = (int)tl.size(); cp.max_feat = max_feat;
+  cp.recs = ln.dbg_recs.as<uint32_t>(); cp.rec_words = rec_words; cp.n_tiles = (int)tl.size(); cp.max_feat = max_feat; cp.n_full = cp.n_tiles;
   cp.ctl = ln.ctl.as<BatchCtl>(); cp.cand = ln.cand.as<Cand>(); cp.cand_cap = 0; cp.M = d->model.M();
   cp.dump = ln.dump.as<uint16_t>(); cp.dump_stride = WH;
   launch_similarity_coarse(cp, 1, ln.stream);

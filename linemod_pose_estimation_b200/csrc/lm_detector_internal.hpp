@@ -228,7 +228,7 @@ struct Pack {
   struct ClassRange { std::string id; int class_index; std::vector<uint32_t> local; std::vector<uint32_t> global_pos; };
   std::vector<ClassRange> classes;      // canonical order
   // Device-side description of one (multi-query) request: work items and coarse tiles.  Cached by the class lists.
-  struct Plan { DevBuf items, recs; int n_items = 0, n_tiles = 0, rec_words = 0, max_feat = 0; uint64_t coarse_bytes = 0, evals = 0; double refine_nf_sum = 0; };
+  struct Plan { DevBuf items, recs; int n_items = 0, n_tiles = 0, n_full = 0, rec_words = 0, max_feat = 0; uint64_t coarse_bytes = 0, evals = 0; double refine_nf_sum = 0; };
   std::map<std::string, Plan> plans;
   void clear_filtered() {
     for (auto& kv : plans) { kv.second.items.release(); kv.second.recs.release(); }
@@ -329,6 +329,7 @@ struct lm_detector {
   int batch_lanes = 4;   // chunks in flight on the batched host path
   int mod_order = 2;  // coarse kernel: 0 = modalities in template order, 1 = reversed, 2 = chosen per frame (default)
   int refine_tiled = 1;  // refinement levels with W % 16 == 0 and H >= 16 keep their nibble planes column-blocked
+  int coarse_share = 1;  // coarse tail passes of <= 128 positions are scored for eight frames per warp
   bool stream_open = false;  // an lm_stream owns the lanes: other matching calls are refused until it is closed
   std::vector<std::string> class_id_cache;
 };

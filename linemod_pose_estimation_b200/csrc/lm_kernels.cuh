@@ -202,6 +202,8 @@ struct CoarseParams {
   uint32_t cand_cap;
   int rec_words, n_tiles, M, prune, dump_stride;
   int max_feat;                           // largest feature count of a tile: <= 63 selects the u8-only kernel
+  int n_full;                             // records [0, n_full) are full tiles (a frame per warp); [n_full, n_tiles) are
+                                          // shared tiles of at most 128 positions (eight frames per warp, four lanes each)
 };
 void set_programmatic_launch(bool enabled);  // per thread; disabled while launches are recorded into a CUDA graph
 void set_coarse_grid_limit(int blocks);     // process-wide; 0 = no limit

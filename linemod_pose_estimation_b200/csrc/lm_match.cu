@@ -243,9 +243,14 @@ __device__ __forceinline__ void similarity_coarse_body(const CoarseParams& P) {
   BatchCtl* ctl = P.ctl;
   const uint32_t* __restrict__ recs = P.recs;
   const int rec_words = P.rec_words, M = P.M, prune = P.prune;
-  const uint32_t n_tiles = (uint32_t)P.n_tiles;
-  // virtual tiles of the chunk, frame-major: v = frame * n_tiles + tile
-  const uint32_t n_virtual = n_tiles * (uint32_t)ctl->ft.n_frames;
+  // Virtual tiles of the chunk.  The first n_full records are FULL tiles, one (frame, tile) per warp, frame-major:
+  // v = frame * n_full + tile.  The rest are SHARED tiles -- passes of at most 128 positions (the tail of a template whose
+  // span exceeds one 1 024-position pass): one warp scores the tile for EIGHT frames at once, four lanes per frame, instead
+  // of eight warps with four busy lanes each; v = n_full * F + frame group * n_shared + (tile - n_full).
+  const uint32_t n_tiles = (uint32_t)P.n_tiles, n_full = (uint32_t)P.n_full, n_shared = n_tiles - n_full;
+  const uint32_t n_frames = (uint32_t)ctl->ft.n_frames;
+  const uint32_t v_full = n_full * n_frames;
+  const uint32_t n_virtual = v_full + n_shared * ((n_frames + 7u) >> 3);
   // Tile hand-out: the first two tiles of every warp are static (tile = global warp index, then + number of warps) --
   // thousands of warps drawing from one counter at kernel start serialise on that address -- and only the rest comes from
   // the atomic dispenser (tiles are sorted heaviest first, so the dynamic part balances the light tail).
@@ -259,38 +264,36 @@ __device__ __forceinline__ void similarity_coarse_body(const CoarseParams& P) {
   }
   __syncthreads();
   if (cur >= n_virtual) return;
-  uint32_t cur_frame = cur / n_tiles;
+  // virtual tile -> (record, first frame, shared?)
+  auto decode = [&](uint32_t v, uint32_t& tile, uint32_t& frame0) -> bool {
+    if (v < v_full) { frame0 = v / n_full; tile = v - frame0 * n_full; return false; }
+    const uint32_t u = v - v_full, fg = u / n_shared;
+    tile = n_full + (u - fg * n_shared); frame0 = fg * 8u;
+    return true;
+  };
+  uint32_t cur_tile, cur_frame;
+  bool cur_shared = decode(cur, cur_tile, cur_frame);
   const uint32_t rec_bytes = (uint32_t)rec_words * 4u;   // a multiple of 16 (records are padded to four words)
   if (BULK) {
     if (lane == 0) {
       mbar_expect_tx(&s_bar[warp][0], rec_bytes);
-      bulk_g2s(sr, recs + (size_t)(cur - cur_frame * n_tiles) * rec_words, rec_bytes, &s_bar[warp][0]);
+      bulk_g2s(sr, recs + (size_t)cur_tile * rec_words, rec_bytes, &s_bar[warp][0]);
     }
     mbar_wait(&s_bar[warp][0], 0u);
     phases = 1u;
   }
   uint32_t nxt = gwarp + n_warps;
-  const uint32_t lane_byte = (uint32_t)lane * 16u;
-  const int first = lane * 32;  // first position of this lane within the pass
   const bool do_prune = (prune & 1) != 0;
   const uint32_t zero = n_tiles >> 31;  // n_tiles > 0: zero, but only at run time (see rec_group)
   unsigned long long bytes = 0;  // (feature, position) pairs actually gathered by this warp
   uint32_t thr_key = 0xffffffffu;
   int thr_val = 0;
-  // frame of a virtual tile without a division: v / n_tiles = umulhi(v, floor(2^32 / n_tiles)) or one more
-  const uint32_t inv_tiles = (uint32_t)(0x100000000ull / n_tiles);
-  auto frame_of = [&](uint32_t v) -> uint32_t {
-    if (n_tiles == 1u) return v;   // 2^32 / 1 does not fit the multiplier
-    uint32_t q = __umulhi(v, inv_tiles);
-    if (v - q * n_tiles >= n_tiles) ++q;
-    return q;
-  };
   for (;;) {
     __syncwarp();
     // prefetch the next tile's record into registers and draw the tile after it
     const bool has_next = nxt < n_virtual;
-    const uint32_t nxt_frame = has_next ? frame_of(nxt) : 0u;
-    const uint32_t nxt_tile = nxt - nxt_frame * n_tiles;
+    uint32_t nxt_tile = 0, nxt_frame = 0;
+    const bool nxt_shared = has_next ? decode(nxt, nxt_tile, nxt_frame) : false;
     // the other buffer was last read during the previous tile (every lane is past the __syncwarp above): refill it
     if (has_next && lane == 0) {
       mbar_expect_tx(&s_bar[warp][buf ^ 1], rec_bytes);
@@ -303,14 +306,18 @@ __device__ __forceinline__ void similarity_coarse_body(const CoarseParams& P) {
 
     // this lane's chunk of every window.  The empty asm pins the pointer in a register pair: left alone, ptxas recomputes
     // frame * stride + lane offset + base for every feature (six address instructions per window instead of three).
-    unsigned long long lane_base = (unsigned long long)P.lmn + (unsigned long long)cur_frame * P.lmn_stride + lane_byte;
+    // a full tile: 32 lanes x 32 positions of frame cur_frame; a shared tile: lanes 4f .. 4f+3 take frame cur_frame + f
+    const uint32_t lane_frame = cur_shared ? cur_frame + ((uint32_t)lane >> 2) : cur_frame;
+    const uint32_t lane_slot = cur_shared ? ((uint32_t)lane & 3u) : (uint32_t)lane;
+    const int first = (int)lane_slot * 32;  // first position of this lane within the pass
+    unsigned long long lane_base = (unsigned long long)P.lmn + (unsigned long long)lane_frame * P.lmn_stride + lane_slot * 16u;
     asm volatile("" : "+l"(lane_base));
     const uint8_t* __restrict__ lmn = reinterpret_cast<const uint8_t*>(lane_base);
     // bit 8 of `prune`: sum the modalities in reverse order; bit 9: decide per frame from the front end's counters
     const bool mod_reversed = (prune & 0x200) ? (ctl->mod_bits[cur_frame][M - 1] < ctl->mod_bits[cur_frame][0]) : (prune & 0x100) != 0;
     const uint32_t item = sr[0], tg = sr[1], nfq = sr[2], order = sr[6];
     const int n_feat = (int)sr[3], j0 = (int)sr[4], rem = (int)sr[5];
-    const bool active = first < rem;
+    const bool active = first < rem && lane_frame < n_frames;
     // [OCV] matchClass: raw_threshold = (int)(2*nf + (threshold / 100.f) * (2*nf) + 0.5f), same f32 roundings; consecutive
     // tiles nearly always share the query and the feature count, so the division is redone only when they change
     if (nfq != thr_key) {
@@ -358,7 +365,7 @@ __device__ __forceinline__ void similarity_coarse_body(const CoarseParams& P) {
         if (do_prune && !rec_alive(tot, thr, n_feat - done, active)) alive = false;
       }
     }
-    bytes += (unsigned long long)done * (unsigned)rem;
+    bytes += (unsigned long long)done * (unsigned)rem * (cur_shared ? min(8u, n_frames - cur_frame) : 1u);
     if (alive && active) {
       bool hit = thr < 0;
       if (!hit) {
@@ -393,7 +400,7 @@ __device__ __forceinline__ void similarity_coarse_body(const CoarseParams& P) {
                 uint32_t idx = atomicAdd(&ctl->n_cands, 1u);
                 if (idx < P.cand_cap) {
                   Cand c;
-                  c.tglob = tg; c.pos = (uint32_t)(j0 + p) | (cur_frame << 24);
+                  c.tglob = tg; c.pos = (uint32_t)(j0 + p) | (lane_frame << 24);
                   c.raw_nf = (uint32_t)raw | ((nfq & 0xffffu) << 16); c.order = order;
                   P.cand[idx] = c;
                 }
@@ -408,7 +415,7 @@ __device__ __forceinline__ void similarity_coarse_body(const CoarseParams& P) {
     sr = s_rec[warp][buf];
     mbar_wait(&s_bar[warp][buf], (phases >> buf) & 1u);
     phases ^= 1u << buf;
-    cur_frame = nxt_frame;
+    cur_frame = nxt_frame; cur_shared = nxt_shared;
     nxt = __shfl_sync(kFull, ticket, 0) + 2u * n_warps;
   }
   // gathered-bytes statistic: summed per CTA in shared memory, one global atomic per CTA by the warp that finishes last

@@ -658,6 +658,40 @@ def test_chunked_batches_equal_the_oracle(batch_frames, lanes):
     assert total > 0
 
 
+@pytest.mark.parametrize("share", [1, 0])
+def test_shared_tail_tiles_equal_the_oracle(share):
+    """Templates small enough that their coarse span exceeds one 1 024-position pass leave a tail pass of a few dozen positions;
+    the coarse kernel scores such tails for eight frames per warp (`coarse_share` 1, default) or like any other tile (0).
+    Chunks of 8, 3 and 1 frames (all, some and one of a warp's frame slots in use), loose thresholds so that tail positions
+    become candidates: every frame must get the oracle's lists and candidate counts."""
+    kinds, T = ("cg", "dn"), (5, 8)
+    orc = O.OracleDetector(common.oracle_modalities(kinds), T)
+    det = Detector(common.product_modalities(kinds), T)
+    rng = np.random.default_rng(97)
+    for i in range(70):
+        pyr = synth.random_pyramid(rng, T=T, M=2, wh_range=(24, 90) if i % 3 else (100, 190))
+        orc.add_synthetic_template("small", pyr)
+        det.addSyntheticTemplate(pyr, "small")
+    det.set_option("coarse_share", share)
+    views = common.rendered_views(4, 53)
+    frames = [list(synth.compose_scene(6100 + i, views)[:2]) for i in range(12)]
+    n_tail, want = 0, []
+    for f in frames:
+        want.append([orc.match(f, thr, keep_candidates=True) for thr in (75.0, 68.0)])
+        n_tail += int(np.count_nonzero(orc.last_candidates()["pos"] >= 1024))   # candidates of the loose query in tail passes
+    assert n_tail > 0
+    for bf in (8, 3, 1):
+        det.set_option("batch_frames", bf)
+        got = det.match_batch_multi(frames, [(75.0, []), (68.0, [])])
+        for f, (g, w) in enumerate(zip(got, want)):
+            for q in range(2):
+                common.assert_matches_equal(g[q], w[q], "share %d, chunks of %d, frame %d query %d" % (share, bf, f, q))
+    single = det.match(frames[0], 68.0)
+    common.assert_matches_equal(single, orc.match(frames[0], 68.0, keep_candidates=True), "single frame")
+    assert det.last_work()["candidates"] == len(orc.last_candidates())
+    det.set_option("coarse_share", 1)
+
+
 def test_config5_64_frame_batch_15_classes():
     """BASELINE configs[4] at test scale: a 64-frame synthetic 640x480 video against 15 object classes, end to end
     (quantise -> spread -> response -> match) through lm_match_batch; every frame's match list equals the oracle's."""
