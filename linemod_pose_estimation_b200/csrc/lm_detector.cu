@@ -1445,6 +1445,10 @@ int lm_set_option(lm_detector* d, const char* key, int value) {
     if (value < 1 || value > LM_MAX_BATCH) return lm_fail(LM_E_INVALID, "batch_frames must be 1..%d", LM_MAX_BATCH);
     d->batch_frames = value;
   }
+  else if (k == "stream_frames") {      // frames per chunk of an lm_stream opened afterwards
+    if (value < 1 || value > LM_MAX_BATCH) return lm_fail(LM_E_INVALID, "stream_frames must be 1..%d", LM_MAX_BATCH);
+    d->stream_frames = value;
+  }
   else if (k == "batch_lanes") {
     if (value < 1 || value > LM_LANES) return lm_fail(LM_E_INVALID, "batch_lanes must be 1..%d", LM_LANES);
     d->batch_lanes = value;
@@ -1596,10 +1600,10 @@ struct BatchPipe {
   double t_fin = 0, t_up = 0, t_enq = 0;
   static double now() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-  int setup(lm_detector* det, const Query* queries, int n_queries, int total_frames, bool pool) {
+  int setup(lm_detector* det, const Query* queries, int n_queries, int total_frames, bool pool, int chunk_frames) {
     d = det; n_q = n_queries;
     for (int q = 0; q < n_q; ++q) qs[q] = queries[q];
-    F = std::max(1, std::min(d->batch_frames, LM_MAX_BATCH));
+    F = std::max(1, std::min(chunk_frames, LM_MAX_BATCH));
     NL = std::max(1, std::min(d->batch_lanes, LM_LANES));
     ws_frames = total_frames > 0 ? std::min(F, total_frames) : F;
     use_pool = pool && d->finalize_threads > 0;
@@ -1713,7 +1717,7 @@ static int match_batch_impl(lm_detector* d, const lm_image* sources, int n_frame
   if (set_device(d) != LM_OK) return LM_E_CUDA;
   BatchPipe pipe;
   pipe.raw_frames = raw_frames;
-  pipe.setup(d, qs, n_q, n_frames, !raw_frames && n_frames > 1);
+  pipe.setup(d, qs, n_q, n_frames, !raw_frames && n_frames > 1, d->batch_frames);
   struct Guard {  // nothing may outlive this call, whichever way it returns
     BatchPipe* p;
     ~Guard() { p->abandon(); }
@@ -1774,7 +1778,7 @@ int lm_stream_open(lm_detector* d, const lm_query* queries, int n_queries, lm_st
     for (const std::string& id : s->ids[(size_t)q]) s->id_ptrs[(size_t)q].push_back(id.c_str());
     qs[q].class_ids = s->id_ptrs[(size_t)q].data();
   }
-  s->pipe.setup(d, qs, n_queries, 0, true);
+  s->pipe.setup(d, qs, n_queries, 0, true, d->stream_frames);
   d->stream_open = true;
   *out = s.release();
   return LM_OK;
@@ -1856,7 +1860,7 @@ lm_detector* lm_internal_clone(const lm_detector* src) {
   d->device_out_cap = src->device_out_cap; d->cand_per_frame = src->cand_per_frame;
   d->prune = src->prune; d->graphs = src->graphs; d->mod_order = src->mod_order;
   d->batch_frames = src->batch_frames; d->batch_lanes = src->batch_lanes; d->finalize_threads = src->finalize_threads;
-  d->refine_tiled = src->refine_tiled; d->coarse_share = src->coarse_share;
+  d->refine_tiled = src->refine_tiled; d->coarse_share = src->coarse_share; d->stream_frames = src->stream_frames;
   refresh_class_cache(d);
   return d;
 }

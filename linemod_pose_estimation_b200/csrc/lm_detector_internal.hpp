@@ -327,6 +327,7 @@ struct lm_detector {
   int prune = 3;         // exact early termination: bit 0 in the coarse kernel, bit 1 in the refinement kernel
   int batch_frames = 8;  // frames per chunk on the batched paths (lm_match_batch*, lm_match_device_stream)
   int batch_lanes = 4;   // chunks in flight on the batched host path
+  int stream_frames = 16;  // frames per chunk of an lm_stream: no fill and drain per call to pay, so larger launch sets win
   int mod_order = 2;  // coarse kernel: 0 = modalities in template order, 1 = reversed, 2 = chosen per frame (default)
   int refine_tiled = 1;  // refinement levels with W % 16 == 0 and H >= 16 keep their nibble planes column-blocked
   int coarse_share = 1;  // coarse tail passes of <= 128 positions are scored for eight frames per warp

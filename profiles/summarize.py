@@ -2,7 +2,7 @@
 """Turns ncu exports brought back from the GPU box (gpurun_out/) into the small tracked summaries under profiles/.
 
     python profiles/summarize.py launches gpurun_out/launches_r01c.csv profiles/r01_launches.md
-    python profiles/summarize.py full gpurun_out/coarse_r01c.ncu-rep profiles/r01_coarse_full.md [traffic.json]
+    python profiles/summarize.py full gpurun_out/coarse_r01c.ncu-rep profiles/r01_coarse_full.md [traffic.json [frames per launch]]
 
 `launches`: the `ncu --metrics gpu__time_duration.sum --clock-control none --csv` launch list of `python bench.py`.
 `full`: one `ncu --set full` capture; needs the `ncu` binary (reads the report with --page raw --csv).
@@ -61,7 +61,7 @@ def to_bytes(value, unit):
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
 
 
-def full(src, dst, traffic_json=None):
+def full(src, dst, traffic_json=None, launch_frames=None):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
@@ -84,7 +84,8 @@ def full(src, dst, traffic_json=None):
         json.dump({"kernel": rows[2][hdr.index("Kernel Name")].split("(")[0].split("::")[-1],
                    "dram_bytes_per_launch": sum(traffic) / len(traffic),
                    "warp_instructions_per_launch": (sum(insts) / len(insts)) if insts else None,
-                   "launches": len(traffic), "source": src}, open(traffic_json, "w"))
+                   "launches": len(traffic), "launch_frames": int(launch_frames) if launch_frames else 8, "source": src},
+                  open(traffic_json, "w"))
 
 
 if __name__ == "__main__":

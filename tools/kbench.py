@@ -85,6 +85,7 @@ def main():
         for k, v in opts.items():
             det.set_option(k, v)
         det.set_option("batch_lanes", n_streams)
+        det.set_option("stream_frames", opts["batch_frames"])
         streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
         sp = (C.c_void_p * n_streams)(*[s.cuda_stream for s in streams])
 
