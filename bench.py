@@ -21,8 +21,10 @@ templates sharded by canonical index (2 x ~2 650 per GPU), frame broadcast from 
 rank 0 finalises.
 
 Prints ONE JSON line (rank 0).  `value` is device-timed with the frames already in HBM; `e2e` goes through the public
-C ABI with pinned HOST frames, copies inside the timed region.  Both time R back-to-back repeats of the K steps (R so
-that the region lasts >= MIN_TIMED_S) and report the per-step time of the whole region.
+C ABI with pinned HOST frames, copies inside the timed region: lm_stream (the chunk pipeline kept alive between pushes of
+64 frames) for the frame-stream configs, the blocking 64-frame batch call for config 5 and as the secondary
+`e2e_batch_calls`.  Every timed region is R back-to-back repeats of the K steps (R raised until the region lasts >=
+MIN_TIMED_S) and reports the per-step time of the whole region.
 1 eval = one (template, coarse position) score: 1 200 per template at 640x480.
 """
 import argparse

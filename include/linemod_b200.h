@@ -297,7 +297,8 @@ void lm_free_matches(lm_match_rec* matches);
  *                    without blocking, wait_all = 1 first waits for everything pushed.  out_offsets (max_frames * n_queries
  *                    + 1 entries) and *out_matches as in lm_match_batch_multi (release with lm_free_matches); the lists are
  *                    identical to lm_match_multi's of the same frames.
- *   lm_stream_in_flight   frames pushed and not yet popped. */
+ *   lm_stream_in_flight   frames pushed and not yet popped.
+ * A stream must be closed before its detector is destroyed. */
 typedef struct lm_stream lm_stream;
 int lm_stream_open(lm_detector* det, const lm_query* queries, int n_queries, lm_stream** out);
 int lm_stream_push(lm_stream* stream, const lm_image* sources, int n_frames, int n_sources);
@@ -481,6 +482,11 @@ int lm_last_work(const lm_detector* det, uint64_t out[8]);
  * kernel, bit 1 = of hopeless candidates in the refinement kernel; default 3; results do not depend on it), "mod_order" (order in which the coarse kernel sums the modalities: 0 = template order, 1 = reversed,
  * 2 = chosen per frame from the front end's spread-bit counters, default; results do not depend on it), "graphs" (replay
  * a recorded CUDA graph per chunk, default 1), "timing" (per-stage events for lm_last_timings, default 0), "debug_taps",
+ * "stream_frames" (frames per chunk of an lm_stream opened afterwards, 1..32, default 16), "refine_tiled" (refinement levels
+ * keep their nibble planes column-blocked, default 1), "coarse_narrow" (requests whose tiles have at most 63 features use the
+ * u8-only coarse kernel: 1 default, 0 the general kernel, 2 the u8-only body at two CTAs per SM; process-wide),
+ * "coarse_share" (coarse tail passes of at most 128 positions are scored for eight frames per warp, default 1) -- A/B
+ * switches, results do not depend on them --
  * "coarse_grid_limit", "device_out_cap" (records per frame block on the device-resident paths, default 2048),
  * "cand_per_frame" (coarse candidates a chunk may produce per frame on the device-resident paths, default 65536; the
  * host paths grow both by themselves). */
