@@ -282,6 +282,32 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "source": self.source}
 
 
+def bind_to_gpu_numa_node(index):
+    """N > 1: every rank pins itself to the CPU cores NVML names as local to its GPU BEFORE it allocates its pinned frames
+    (first touch puts them on that NUMA node): with eight ranks streaming 1.5 MB frames, host-memory reads that cross the
+    socket interconnect are the first thing to saturate.  Returns a description for the JSON line, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = index
+        if visible:
+            ids = [v for v in visible.split(",") if v.strip() != ""]
+            if index < len(ids) and ids[index].strip().isdigit():
+                phys = int(ids[index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_cpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(c for c in range(n_cpu) if (int(words[c // 64]) >> (c % 64)) & 1 and c in allowed)
+        if len(cpus) >= 4:       # never squeeze a rank (main thread + finalizer threads) onto a handful of cores
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": len(cpus), "first": cpus[0], "last": cpus[-1]}
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------ the CPU arm (oracle/)
 def oracle_setup(n_frames, threads=None, train=True):
     """The CPU implementation with its own trained templates and frames (no GPU involved): oracle/ is the restatement of
@@ -412,6 +438,7 @@ def run_ours(args):
     if world != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torchrun --nproc-per-node %d" % (args.gpus, world, args.gpus))
     mode = args.mode if world > 1 else "frames"
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -436,6 +463,8 @@ def run_ours(args):
     det.set_option("batch_frames", BATCH_FRAMES)
     det.set_option("stream_frames", BATCH_FRAMES)
     det.set_option("batch_lanes", DEVICE_STREAMS)
+    if os.environ.get("LM_BENCH_FINALIZE_THREADS"):   # A/B: host threads ordering the match lists (library default otherwise)
+        det.set_option("finalize_threads", int(os.environ["LM_BENCH_FINALIZE_THREADS"]))
     n_t = det.numTemplates()
 
     def render(cid, T, up):
@@ -840,7 +869,7 @@ def run_ours(args):
                             "matching in chunks on the handle's lanes, one NCCL all-gather of the survivor blocks, D2H + finalise on rank 0"},
             "e2e_batch_calls": e2e_batch, "e2e_single_call": e2e_single,
             "gpu_launches": int(launches_device + launches_e2e + launches_single), "clocks": clock_info,
-            "stage_ms_per_frame": stage_ms, "train_s": train_s,
+            "stage_ms_per_frame": stage_ms, "train_s": train_s, "cpu_affinity_rank0": numa,
         }
         print(json.dumps(line))
     if world > 1:

@@ -478,7 +478,7 @@ int lm_last_timings(const lm_detector* det, float ms[5], int* kernel_launches);
 int lm_last_work(const lm_detector* det, uint64_t out[8]);
 /* Tuning switches: "batch_frames" (frames per chunk = per launch set on the batched paths, 1..32, default 8),
  * "batch_lanes" (chunks in flight in lm_match_batch*, default 4), "finalize_threads" (host threads that order the match
- * lists of batched calls while the calling thread feeds the device, default 2; 0 = on the calling thread), "prune" (exact early termination: bit 0 = in the coarse
+ * lists of batched calls while the calling thread feeds the device, default 4; 0 = on the calling thread), "prune" (exact early termination: bit 0 = in the coarse
  * kernel, bit 1 = of hopeless candidates in the refinement kernel; default 3; results do not depend on it), "mod_order" (order in which the coarse kernel sums the modalities: 0 = template order, 1 = reversed,
  * 2 = chosen per frame from the front end's spread-bit counters, default; results do not depend on it), "graphs" (replay
  * a recorded CUDA graph per chunk, default 1), "timing" (per-stage events for lm_last_timings, default 0), "debug_taps",

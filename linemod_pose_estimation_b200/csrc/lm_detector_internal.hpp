@@ -310,7 +310,7 @@ struct FinalizePool {
 struct lm_detector {
   HostModel model;
   FinalizePool finalizers;
-  int finalize_threads = 2;  // host threads ordering the match lists of batched calls (0: on the calling thread)
+  int finalize_threads = 4;  // host threads ordering the match lists of batched calls (0: on the calling thread)
   TrainWs train;
   int device = -1;
   bool cuda_ready = false;
