@@ -248,7 +248,7 @@ static int run_gpu(const std::string& dir) {
     std::vector<lm::Match> want_r, want_f;
     trained->match(rframe, 90.f, want_r);
     trained->match(frame, 90.f, want_f);
-    REQUIRE(lm_set_option(trained->handle(), "batch_frames", 4) == LM_OK);
+    REQUIRE(lm_set_option(trained->handle(), "stream_frames", 4) == LM_OK);
     {
       lm::FrameStream stream(*trained, 90.f);
       bool refused = false;
@@ -273,7 +273,7 @@ static int run_gpu(const std::string& dir) {
     std::vector<lm::Match> again;
     trained->match(rframe, 90.f, again);      // the stream is closed: the handle answers again
     REQUIRE(again.size() == want_r.size());
-    REQUIRE(lm_set_option(trained->handle(), "batch_frames", 8) == LM_OK);
+    REQUIRE(lm_set_option(trained->handle(), "stream_frames", 16) == LM_OK);
   }
   std::printf("ok gpu (%zu matches, best %.2f at %d,%d)\n", matches.size(), best.similarity, best.x, best.y);
   return 0;

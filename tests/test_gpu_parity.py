@@ -516,13 +516,13 @@ def test_batch_multi_equals_per_frame_multi():
     assert det.match_batch_multi([], queries) == []
 
 
-@pytest.mark.parametrize("batch_frames,lanes", [(8, 4), (3, 2), (1, 1)])
+@pytest.mark.parametrize("batch_frames,lanes", [(16, 4), (8, 4), (3, 2), (1, 1)])
 def test_frame_stream_equals_the_oracle(batch_frames, lanes):
     """lm_stream: frames pushed in uneven pieces with pops in between (blocking and not) come back in push order with the
     oracle's lists for every query; a frame whose survivors outgrow the head of its result block is redone inside the stream;
     the detector refuses other matching calls while the stream is open and answers again after close()."""
     orc, det, views = _pair(n_views=8, n_random=40, seed=79, classes=("cpu_binary", "memoryChip2"))
-    det.set_option("batch_frames", batch_frames)
+    det.set_option("stream_frames", batch_frames)    # frames per chunk of the stream (default 16)
     det.set_option("batch_lanes", lanes)
     queries = [(90.0, ["memoryChip2"]), (62.0, [])]
     frames = []
