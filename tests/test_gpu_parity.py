@@ -250,6 +250,22 @@ def test_three_levels():
                 assert np.array_equal(det.fetch(Stage.LINEAR, l, m), orc.fetch(Stage.LINEAR, l, m)), (tiled, l, m)
 
 
+def test_refinement_level_too_short_for_column_blocks_stays_flat():
+    """150x320 with T = (10, 5): the refinement level has W/T = 32 columns (a multiple of 16) but only H/T = 15 rows -- fewer
+    than a window -- so its planes stay in the reference's flat order (and T = 10 takes the spread kernel's generic path).
+    Linear memories, candidate counts and the (empty: no 16-cell window fits the image) match lists equal the oracle's."""
+    orc, det, views = _pair(T=(10, 5), n_views=8, n_random=12, seed=31, canvas=(96, 96))
+    bgr, depth, _ = synth.compose_scene(77, views[:3], rows=150, cols=320)
+    for thr in (60.0, 40.0):
+        want = orc.match([bgr, depth], thr, keep_candidates=True)
+        got = det.match([bgr, depth], thr)
+        common.assert_matches_equal(got, want, "thr %g" % thr)
+        assert det.last_work()["candidates"] == len(orc.last_candidates()) > 0
+    for l in range(2):
+        for m in range(2):
+            assert np.array_equal(det.fetch(Stage.LINEAR, l, m), orc.fetch(Stage.LINEAR, l, m)), (l, m)
+
+
 def test_edge_templates():
     """Template larger than the image (P <= 0), features outside the image, the (width, height) spill corner,
     negative coordinates, a template with one feature, an empty class."""
