@@ -738,7 +738,7 @@ def run_ours(args):
         launches_single = 0
     clock_info = clocks.stop() if clocks else None
 
-    # ---- the dominant kernel (k_similarity_coarse_rec), timed live: per-launch CUDA-event duration on the library's own
+    # ---- the dominant kernel (k_similarity_coarse_rec63), timed live: per-launch CUDA-event duration on the library's own
     # stream, of the same launch the timed step makes (one launch per chunk of BATCH_FRAMES frames, all queries in it)
     roofline = None
     stage_ms = {}

@@ -7,7 +7,8 @@
 //   k_cg_fused                                  [OCV] quantizedOrientations + hysteresisGradient, all levels (a1, a2)
 //   k_dn_fused                                  [OCV] quantizedNormals + medianBlur(5) + DepthNormalPyramid::pyrDown (a4, a5)
 //   k_spread_all                                [OCV] quantize(mask) + spread + computeResponseMaps + linearize (a6-a8)
-//   k_similarity_coarse_rec                     [OCV] similarity + addSimilarities + matchClass coarse scan  (a9-a12)
+//   k_similarity_coarse_rec63 / _rec            [OCV] similarity + addSimilarities + matchClass coarse scan  (a9-a12); _rec63: requests
+//                                               whose tiles have <= 63 features (u8 sums only), _rec: the general body (u16 totals)
 //   k_refine_nib                                [OCV] similarityLocal + matchClass refinement loop          (a13)
 //   template generation (/root/reference/src/renderer.cpp:239-329, src/rgbdDetector.cpp:147-283)
 //   k_raster_tris, k_raster_resolve             RendererIterator::render / renderDepthOnly (ORK) per oracle/render_oracle.cpp

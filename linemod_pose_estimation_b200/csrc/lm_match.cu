@@ -1,6 +1,6 @@
 // lm_match.cu -- the template-matching kernels of the LINEMOD hot path (sm_100a).
 //
-// k_similarity_coarse_rec restates [OCV] similarity + addSimilarities + the coarse scan of Detector::matchClass
+// k_similarity_coarse_rec63 / k_similarity_coarse_rec restate [OCV] similarity + addSimilarities + the coarse scan of Detector::matchClass
 // (OpenCV 2.4.x objdetect/linemod.cpp, reached from /root/reference/src/rgbdDetector.cpp:33); k_refine_nib restates
 // [OCV] similarityLocal and matchClass's refinement loop.  Spec: SURVEY.md App. A.7-A.9, quirks App. D.  Both take a
 // CHUNK of frames per launch (frame table + per-frame strides, lm_kernels.cuh); k_begin_chunk installs the table.
@@ -41,7 +41,8 @@ __device__ __forceinline__ void nib_flush(const uint32_t (&nib)[WORDS], uint32_t
 }
 
 // ------------------------------------------------------------------------------------------------ production coarse
-// k_similarity_coarse_rec: nibble-packed linear memories + self-contained tile records + exact early termination.
+// similarity_coarse_body (k_similarity_coarse_rec63 / k_similarity_coarse_rec): nibble-packed linear memories + self-contained
+// tile records + exact early termination.
 //
 //  * The host plan stores one record per (template, 1024-position pass) tile: a 48-byte header followed by the feature
 //    words (aligned chunk byte offset of lane 0's window | nibble shift).  A warp prefetches the record of its next tile
@@ -51,7 +52,8 @@ __device__ __forceinline__ void nib_flush(const uint32_t (&nib)[WORDS], uint32_t
 //    after `done` of the tile's n features a position can still pass only if partial + 4 * (n - done) > raw_threshold.
 //    The warp stops as soon as none of its 1024 positions can.  Tiles that survive are summed to the end, so every
 //    reported raw score is the complete sum: the candidate list is bit-identical to the exhaustive scan.  At the
-//    reference's thresholds (92 / 94) nearly every tile stops after the first quarter of its features.
+//    reference's thresholds (92 / 94) random templates stop after a third of their features; trained ones gather 65 %
+//    (most of a frame scores high for most of a template: DepthNormal on flat background).
 //    Disabled (prune = 0) for the parity tap, which wants every position's full sum.
 constexpr int kRecHdrWords = 12;                      // TileRec header, see lm_kernels.cuh
 constexpr int kRecMaxWords = kRecHdrWords + 256;      // header + LM_MAX_MODALITIES * 64 feature words
