@@ -175,10 +175,21 @@ static int ensure_tap_ws(lm_detector* d, Lane& ln) {
 }
 
 // ------------------------------------------------------------------------------------------------ uploads
+// cudaPointerGetAttributes costs a microsecond or two and the batched paths ask four times per frame, nearly always about the
+// same few buffers: a small per-thread cache in front of it.  A stale entry (the address freed and handed out again with the
+// other kind of memory) only picks the other copy path -- cudaMemcpyAsync is correct from pageable memory too, and staging
+// pinned memory is merely slower.
 bool is_pinned(const void* p) {
+  struct Entry { const void* p; bool pinned; };
+  static thread_local Entry cache[64] = {};
+  Entry& e = cache[(reinterpret_cast<uintptr_t>(p) >> 12) & 63u];
+  if (p != nullptr && e.p == p) return e.pinned;
   cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-  return a.type == cudaMemoryTypeHost;
+  bool pinned = false;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) cudaGetLastError();
+  else pinned = a.type == cudaMemoryTypeHost;
+  e.p = p; e.pinned = pinned;
+  return pinned;
 }
 
 // Host image -> tightly packed device buffer.  Pinned sources go straight to the copy engine; pageable ones are
