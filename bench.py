@@ -828,20 +828,35 @@ def run_ours(args):
         if not same:
             raise SystemExit("bench: the e2e path's match lists differ from the oracle's")
 
-    # what bounds e2e: the host -> device copy of the frame.  Pinned H2D rate of this box, measured on a 64 MB block.
+    # what bounds e2e: the host -> device copy of the frame.  Pinned H2D rate of this box with as many copies in flight as the
+    # pipeline has lanes (one stream each, 16 MB blocks), best of three trials.
     h2d_gbs = None
     if rank == 0:
-        hbuf = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
-        dbuf = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
-        for _ in range(2):
-            dbuf.copy_(hbuf, non_blocking=True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(8):
-            dbuf.copy_(hbuf, non_blocking=True)
-        e1.record()
+        blk = 16 << 20
+        hbuf = torch.empty(DEVICE_STREAMS * blk, dtype=torch.uint8).pin_memory()
+        dbuf = torch.empty(DEVICE_STREAMS * blk, dtype=torch.uint8, device=dev)
+
+        def copies(rounds):
+            for _ in range(rounds):
+                for i, st in enumerate(streams):
+                    with torch.cuda.stream(st):
+                        dbuf[i * blk:(i + 1) * blk].copy_(hbuf[i * blk:(i + 1) * blk], non_blocking=True)
+        copies(2)
         torch.cuda.synchronize()
-        h2d_gbs = 8 * (64 << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        best = 0.0
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            cur = torch.cuda.current_stream()
+            e0.record(cur)
+            for st in streams:
+                st.wait_stream(cur)
+            copies(4)
+            for st in streams:
+                cur.wait_stream(st)
+            e1.record(cur)
+            torch.cuda.synchronize()
+            best = max(best, 4 * DEVICE_STREAMS * blk / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        h2d_gbs = best
         del hbuf, dbuf
 
     if rank == 0:
@@ -856,8 +871,9 @@ def run_ours(args):
                     "h2d_bytes_per_step": ROWS * COLS * 3 + ROWS * COLS * 2,
                     "d2h_bytes_per_step": 8448 if sharded is None else (16 + sharded.capacity * 32) * world,
                     "matches_per_step": matches_per_frame,
-                    "h2d_gbs_measured": h2d_gbs,
-                    "h2d_floor_ms_per_step": (ROWS * COLS * 5) / (h2d_gbs * 1e9) * 1e3 if h2d_gbs else None,
+                    # context: the rate the e2e path moves its frames at, next to a plain pinned copy loop (one 16 MB block per
+                    # pipeline lane in flight) on the same box -- the PCIe link is what the e2e rate runs into
+                    "h2d_gbs_e2e_per_gpu": (ROWS * COLS * 5) / s_per_step_e2e / 1e9, "h2d_gbs_copy_loop": h2d_gbs,
                     "what": (("lm_stream (C ABI): pushes of %d pinned host frames on every rank's own frames, finished frames popped as "
                               "they become ready, the region ends when the last frame's lists are on the host: chunks of %d frames (one "
                               "launch set each), %d chunks in flight -- H2D, kernels, D2H + finalisation overlap across pushes"
