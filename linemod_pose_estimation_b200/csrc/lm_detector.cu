@@ -60,9 +60,16 @@ int upload_luts(lm_detector* d) {
     resp_all[v] = packed;
   }
   if (d->d_resp_all.ensure(sizeof(resp_all)) != LM_OK) return LM_E_CUDA;
-  if (d->d_normal_lut.ensure(8000) != LM_OK) return LM_E_CUDA;
+  // byte 8000 behind the table: every entry is 0 or a single bit, so k_dn_fused may take medianBlur(5) by counting (it reads
+  // the verdict on the device: recorded CUDA graphs stay valid across lm_set_normal_lut)
+  uint8_t lut_and_flag[8004] = {0};
+  std::memcpy(lut_and_flag, d->normal_lut, 8000);
+  bool one_hot = d->dn_count != 0;
+  for (int i = 0; i < 8000 && one_hot; ++i) one_hot = (d->normal_lut[i] & (d->normal_lut[i] - 1)) == 0;
+  lut_and_flag[8000] = one_hot ? 1 : 0;
+  if (d->d_normal_lut.ensure(sizeof(lut_and_flag)) != LM_OK) return LM_E_CUDA;
   CU(cudaMemcpy(d->d_resp_all.p, resp_all, sizeof(resp_all), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(d->d_normal_lut.p, d->normal_lut, 8000, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d->d_normal_lut.p, lut_and_flag, sizeof(lut_and_flag), cudaMemcpyHostToDevice));
   d->luts_dirty = false;
   for (int i = 0; i < LM_LANES; ++i) d->lane[i].front_valid = false;
   return LM_OK;
@@ -1459,6 +1466,10 @@ int lm_set_option(lm_detector* d, const char* key, int value) {
   else if (k == "prune") d->prune = value;
   else if (k == "mod_order") d->mod_order = value & 3;
   else if (k == "refine_tiled") d->refine_tiled = value != 0;   // takes effect with the next request (workspace rebuilt)
+  else if (k == "dn_count") {           // A/B switch: 0 keeps the 99-exchange median network for one-hot tables too
+    d->dn_count = value != 0;
+    d->luts_dirty = true;
+  }
   else if (k == "coarse_share") {       // A/B switch: tail passes of <= 128 positions scored for eight frames per warp
     d->coarse_share = value != 0;
     d->pack.plans.clear();              // plans order their tiles by it (the lanes' graphs are keyed by the plan)
@@ -1884,7 +1895,7 @@ lm_detector* lm_internal_clone(const lm_detector* src) {
   d->device_out_cap = src->device_out_cap; d->cand_per_frame = src->cand_per_frame;
   d->prune = src->prune; d->graphs = src->graphs; d->mod_order = src->mod_order;
   d->batch_frames = src->batch_frames; d->batch_lanes = src->batch_lanes; d->finalize_threads = src->finalize_threads;
-  d->refine_tiled = src->refine_tiled; d->coarse_share = src->coarse_share; d->stream_frames = src->stream_frames;
+  d->refine_tiled = src->refine_tiled; d->coarse_share = src->coarse_share; d->stream_frames = src->stream_frames; d->dn_count = src->dn_count;
   refresh_class_cache(d);
   return d;
 }

@@ -331,6 +331,7 @@ struct lm_detector {
   int mod_order = 2;  // coarse kernel: 0 = modalities in template order, 1 = reversed, 2 = chosen per frame (default)
   int refine_tiled = 1;  // refinement levels with W % 16 == 0 and H >= 16 keep their nibble planes column-blocked
   int coarse_share = 1;  // coarse tail passes of <= 128 positions are scored for eight frames per warp
+  int dn_count = 1;      // DepthNormal's medianBlur(5) by counting when the NORMAL_LUT is one-hot (A/B switch)
   bool stream_open = false;  // an lm_stream owns the lanes: other matching calls are refused until it is closed
   std::vector<std::string> class_id_cache;
 };

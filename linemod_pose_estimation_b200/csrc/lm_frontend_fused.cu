@@ -87,10 +87,13 @@ __global__ void __launch_bounds__(C_THREADS) k_cg_fused(const CgParams P) {
   // ---- A: source tile
   if ((cols & 3) == 0 && x0 >= C_TW && x0 + 71 <= cols && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
     const uint8_t* base = src + (size_t)3 * x0 - 16;  // 4-byte aligned: cols % 4 == 0 and x0 % 64 == 0
-    for (int i = tid; i < C_SRC_ROWS * C_SRC_WORDS; i += C_THREADS) {
-      const int r = i / C_SRC_WORDS, w = i - r * C_SRC_WORDS;
+    // item i = r * C_SRC_WORDS + w, i += C_THREADS: (r, w) advanced without a division per item
+    constexpr int kDr = C_THREADS / C_SRC_WORDS, kDw = C_THREADS % C_SRC_WORDS;
+    for (int r = tid / C_SRC_WORDS, w = tid % C_SRC_WORDS; r < C_SRC_ROWS;) {
       const int gy = clampi(y0 - 5 + r, 0, rows - 1);
       s_src[r][w] = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)gy * cols * 3) + w);
+      r += kDr; w += kDw;
+      if (w >= C_SRC_WORDS) { w -= C_SRC_WORDS; ++r; }
     }
   } else {
     uint8_t* sb = reinterpret_cast<uint8_t*>(&s_src[0][0]);
@@ -127,9 +130,8 @@ __global__ void __launch_bounds__(C_THREADS) k_cg_fused(const CgParams P) {
   __syncthreads();
 
   // ---- C: horizontal blur, item = (row, channel, run of 4 pixels); smoothed ix uses source pixels ix .. ix+6
-  for (int it = tid; it < C_V_ROWS * 3 * 17; it += C_THREADS) {
-    const int run = it % 17, rc = it / 17;
-    const int c = rc % 3, r = rc / 3;
+  // item it = (r * 3 + c) * 17 + run, it += C_THREADS = 18 * 17 + 14: (r, c, run) advanced without divisions per item
+  for (int run = tid % 17, c = (tid / 17) % 3, r = tid / 51; r < C_V_ROWS;) {
     const uint16_t* v = &s_v[r][1 + 12 * run + c];
     uint32_t t[10];
 #pragma unroll
@@ -141,17 +143,35 @@ __global__ void __launch_bounds__(C_THREADS) k_cg_fused(const CgParams P) {
       out |= ((sum + 32768u) >> 16) << (8 * k);
     }
     *reinterpret_cast<uint32_t*>(&s_sm[c][r][4 * run]) = out;
+    static_assert(C_THREADS == 18 * 17 + 14, "stage C's index update assumes 320 threads");
+    run += 14; r += 6;                       // + 18 (row, channel) pairs = + 6 rows ...
+    if (run >= 17) { run -= 17; ++c; }       // ... + 1 pair when the run index wraps
+    if (c >= 3) { c -= 3; ++r; }
   }
   __syncthreads();
 
   // ---- C': Sobel's BORDER_REPLICATE acts on the smoothed image (only tiles that touch the image border)
   if (y0 < 2 || y0 + C_TH + 2 > rows || x0 < 2 || x0 + C_TW + 2 > cols) {
-    for (int i = tid; i < 3 * C_V_ROWS * 68; i += C_THREADS) {
-      const int ix = i % 68, rc = i / 68;
+    // only the entries outside the image are touched: columns left of x = 0 / right of x = cols - 1 (all 20 rows, corners
+    // included), then rows above y = 0 / below y = rows - 1 (in-image columns).  Every source entry is in-image: never rewritten.
+    const int n_left = max(0, 2 - x0), n_right = max(0, min(68, x0 - 2 + 68 - cols));
+    const int n_top = max(0, 2 - y0), n_bot = max(0, min(C_V_ROWS, y0 - 2 + C_V_ROWS - rows));
+    const int nc = n_left + n_right, nr = n_top + n_bot;
+    for (int i = tid; i < 3 * C_V_ROWS * nc; i += C_THREADS) {
+      const int j = i % nc, rc = i / nc;
       const int r = rc % C_V_ROWS, c = rc / C_V_ROWS;
-      const int gy = y0 - 2 + r, gx = x0 - 2 + ix;
-      const int cy = clampi(gy, 0, rows - 1), cx = clampi(gx, 0, cols - 1);
-      if (cy != gy || cx != gx) s_sm[c][r][ix] = s_sm[c][cy - (y0 - 2)][cx - (x0 - 2)];  // source entry is in-image: never rewritten
+      const int ix = j < n_left ? j : 68 - n_right + (j - n_left);
+      const int cy = clampi(y0 - 2 + r, 0, rows - 1), cx = clampi(x0 - 2 + ix, 0, cols - 1);
+      s_sm[c][r][ix] = s_sm[c][cy - (y0 - 2)][cx - (x0 - 2)];
+    }
+    const int w_in = 68 - nc;   // in-image columns: ix in [n_left, 68 - n_right)
+    for (int i = tid; i < 3 * nr * w_in; i += C_THREADS) {
+      const int k = i % w_in, rc = i / w_in;
+      const int j = rc % nr, c = rc / nr;
+      const int r = j < n_top ? j : C_V_ROWS - n_bot + (j - n_top);
+      const int ix = n_left + k;
+      const int cy = clampi(y0 - 2 + r, 0, rows - 1);
+      s_sm[c][r][ix] = s_sm[c][cy - (y0 - 2)][ix];
     }
     __syncthreads();
   }
@@ -403,9 +423,12 @@ __device__ __forceinline__ void cswap_u16x2(uint32_t& a, uint32_t& b) {
   a = lo; b = hi;
 }
 
+constexpr int D_RW = D_TW + 4;                                           // tile columns incl. halo 2
+constexpr int D_COUNT_WORDS = 2 * (D_TH + 4) * D_RW + 2 * D_TH * (D_RW + 4);   // staging of the counting median (20 KB)
+
 template <bool FAST>
-__device__ __forceinline__ void dn_tile(const DnParams& P, int bx, int by, int frame) {
-  __shared__ __align__(4) uint8_t s_raw[D_TH + 4][D_TW + 8];
+__device__ __forceinline__ void dn_tile(const DnParams& P, int bx, int by, int frame, uint32_t* smem) {
+  uint8_t (*s_raw)[D_TW + 8] = reinterpret_cast<uint8_t (*)[D_TW + 8]>(smem);   // [D_TH + 4][D_TW + 8]
   const int rows = P.rows, cols = P.cols;
   const uint16_t* __restrict__ depth = static_cast<const uint16_t*>(P.ctl->ft.src[frame][P.modality]);
   const int x0 = bx * D_TW, y0 = by * D_TH;
@@ -457,11 +480,113 @@ __device__ __forceinline__ void dn_tile(const DnParams& P, int bx, int by, int f
   }
 }
 
+// medianBlur(5) by COUNTING, for one-hot normal codes (every NORMAL_LUT entry is 0 or a single bit: true of upstream's table
+// and of the stand-in; the host checks the table and leaves the verdict behind it, byte 8000).  A code is one of nine values
+// 0 < 1 < 2 < 4 < ... < 128 = rank k 0..8; the median of a 5 x 5 window is the smallest rank whose cumulative count reaches
+// 13.  Per pixel one 5-bit counter per rank (25 fits), ranks 0..5 in one word and 6..8 in a second; the 25-fold sum is
+// separable (five rows, then five columns, sliding); prefix sums of the counters are ONE multiplication by 0x02108421 (no
+// field overflows: every prefix is <= 25), "prefix >= 13" is bit 4 of (prefix + 3), the first such field is the median's
+// rank.  About a third of the instructions of the 99-exchange network (which stays for injected tables that are not one-hot).
+template <bool FAST>
+__device__ __forceinline__ void dn_tile_count(const DnParams& P, int bx, int by, int frame, uint32_t* smem) {
+  constexpr int RW = D_RW;
+  uint32_t (*s_vs)[D_TH][RW + 4] = reinterpret_cast<uint32_t (*)[D_TH][RW + 4]>(smem);                        // [2]: sums over five rows
+  uint32_t (*s_inc)[D_TH + 4][RW] = reinterpret_cast<uint32_t (*)[D_TH + 4][RW]>(smem + 2 * D_TH * (RW + 4));  // [2]: 1 << 5k in word k / 6
+  const int rows = P.rows, cols = P.cols;
+  const uint16_t* __restrict__ depth = static_cast<const uint16_t*>(P.ctl->ft.src[frame][P.modality]);
+  const int x0 = bx * D_TW, y0 = by * D_TH;
+  const int tid = threadIdx.x;
+  // raw quantised normals for the tile + halo 2; medianBlur's BORDER_REPLICATE = value at the clamped coordinate
+  for (int i = tid; i < (D_TH + 4) * RW; i += 256) {
+    const int r = i / RW, c = i - r * RW;
+    const int gy = clampi(y0 - 2 + r, 0, rows - 1), gx = clampi(x0 - 2 + c, 0, cols - 1);
+    const uint32_t code = dn_normal_at<FAST>(depth, rows, cols, gy, gx, P.distance_threshold, P.difference_threshold, P.lut);
+    const int k = __ffs((int)code);                          // 0 for code 0, j + 1 for 1 << j
+    s_inc[0][r][c] = k < 6 ? 1u << (5 * k) : 0u;
+    s_inc[1][r][c] = k < 6 ? 0u : 1u << (5 * (k - 6));
+  }
+  __syncthreads();
+  // five-row sums, sliding down a column: task = (word, column, half of the 16 output rows)
+  for (int t = tid; t < 2 * 2 * RW; t += 256) {
+    const int half = t / (2 * RW), rem = t - half * (2 * RW);
+    const int w = rem / RW, c = rem - w * RW;
+    const int r0 = 8 * half;
+    uint32_t a[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) a[j] = s_inc[w][r0 + j][c];
+    uint32_t sum = a[0] + a[1] + a[2] + a[3] + a[4];
+    s_vs[w][r0][c] = sum;
+#pragma unroll
+    for (int o = 1; o < 8; ++o) {
+      sum += a[o + 4] - a[o - 1];
+      s_vs[w][r0 + o][c] = sum;
+    }
+  }
+  __syncthreads();
+  // four consecutive pixels of a row per thread: five-column sums (sliding), then the median's rank
+  const int r = tid >> 4, c = (tid & 15) * 4;
+  uint32_t h[2][4];
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {
+    const uint4 v0 = *reinterpret_cast<const uint4*>(&s_vs[w][r][c]);
+    const uint4 v1 = *reinterpret_cast<const uint4*>(&s_vs[w][r][c + 4]);
+    h[w][0] = v0.x + v0.y + v0.z + v0.w + v1.x;
+    h[w][1] = h[w][0] - v0.x + v1.y;
+    h[w][2] = h[w][1] - v0.y + v1.z;
+    h[w][3] = h[w][2] - v0.z + v1.w;
+  }
+  const int gy = y0 + r;
+  uint32_t packed = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t p0 = h[0][k] * 0x02108421u;               // field j: count of ranks <= j (j = 0..5)
+    const uint32_t t0 = (p0 + 0x06318C63u) & 0x21084210u;    // bit 5j+4: that count >= 13
+    uint32_t rank;
+    if (t0) rank = ((uint32_t)(__ffs((int)t0) - 1) * 13u) >> 6;             // 4, 9, .. 29 -> 0 .. 5
+    else {
+      const uint32_t p1 = (h[1][k] + ((p0 >> 25) & 31u)) * 0x421u;         // ranks 6..8 on top of the count of ranks <= 5
+      const uint32_t t1 = (p1 + 0xC63u) & 0x4210u;
+      rank = 6u + (((uint32_t)(__ffs((int)t1) - 1) * 13u) >> 6);
+    }
+    packed |= (rank ? 1u << (rank - 1) : 0u) << (8 * k);
+  }
+  if (gy < rows) {
+    uint8_t* q0 = P.quant[0] + (size_t)frame * P.quant_stride[0] + (size_t)gy * cols;
+    const int gx0 = x0 + c;
+    if ((cols & 3) == 0 && gx0 + 3 < cols) *reinterpret_cast<uint32_t*>(q0 + gx0) = packed;   // quant strides are multiples of 4
+    else
+      for (int k = 0; k < 4; ++k)
+        if (gx0 + k < cols) q0[gx0 + k] = (uint8_t)(packed >> (8 * k));
+    // [OCV] DepthNormalPyramid::pyrDown: level l is the NN decimation src(2^l y, 2^l x) of the level-0 map
+#pragma unroll
+    for (int k = 0; k < 4; k += 2) {                          // odd columns never survive a decimation
+      const int gx = gx0 + k;
+      if (gx >= cols) continue;
+      const uint8_t v = (uint8_t)(packed >> (8 * k));
+#pragma unroll
+      for (int l = 1; l < LM_MAX_LEVELS; ++l) {
+        const int mask = (1 << l) - 1;
+        if (l >= P.n_levels || (gy & mask) || (gx & mask)) break;
+        const int lr = rows >> l, lc = cols >> l;
+        if ((gy >> l) < lr && (gx >> l) < lc) P.quant[l][(size_t)frame * P.quant_stride[l] + (size_t)(gy >> l) * lc + (gx >> l)] = v;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) k_dn_fused(const DnParams P) {
   const int frame = blockIdx.z;
   if (frame >= P.ctl->ft.n_frames) return;
-  if (P.difference_threshold <= 200) dn_tile<true>(P, blockIdx.x, blockIdx.y, frame);
-  else dn_tile<false>(P, blockIdx.x, blockIdx.y, frame);
+  __shared__ __align__(16) uint32_t smem[D_COUNT_WORDS];
+  static_assert(sizeof(uint32_t) * D_COUNT_WORDS >= (D_TH + 4) * (D_TW + 8), "the network path's byte tile fits");
+  const bool fast = P.difference_threshold <= 200;
+  if (P.lut[8000]) {   // one-hot table (checked by the host at upload): median by counting
+    if (fast) dn_tile_count<true>(P, blockIdx.x, blockIdx.y, frame, smem);
+    else dn_tile_count<false>(P, blockIdx.x, blockIdx.y, frame, smem);
+  } else {
+    if (fast) dn_tile<true>(P, blockIdx.x, blockIdx.y, frame, smem);
+    else dn_tile<false>(P, blockIdx.x, blockIdx.y, frame, smem);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- spread -> LM

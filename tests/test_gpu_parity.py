@@ -80,13 +80,21 @@ def test_front_end_with_masks_and_strided_roi():
     _check_stages(orc, det, 2, 2, kinds)
 
 
-def test_alternative_luts():
+@pytest.mark.parametrize("table,dn_count", [("one_hot", 1), ("one_hot", 0), ("any", 1)])
+def test_alternative_luts(table, dn_count):
+    """Injected tables: the survey's similarity LUT and a random NORMAL_LUT.  A one-hot normal table (every entry 0 or a
+    single bit, like upstream's) lets k_dn_fused take medianBlur(5) by counting (`dn_count` 1, default) -- compared here with
+    the 99-exchange network (`dn_count` 0) -- and a table with arbitrary bytes must fall back to the network by itself."""
     lut = common.survey_similarity_lut()
     orc, det, views = _pair(lut=lut, n_views=4, n_random=12)
     rng = np.random.default_rng(0)
-    nlut = (1 << rng.integers(0, 8, 8000)).astype(np.uint8)
+    if table == "one_hot":
+        nlut = np.where(rng.random(8000) < 0.1, 0, 1 << rng.integers(0, 8, 8000)).astype(np.uint8)
+    else:
+        nlut = rng.integers(0, 256, 8000).astype(np.uint8)
     orc.set_normal_lut(nlut)
     det.set_normal_lut(nlut)
+    det.set_option("dn_count", dn_count)
     det.set_option("debug_taps", 1)
     bgr, depth, _ = synth.compose_scene(11, views[:3])
     common.assert_matches_equal(det.match([bgr, depth], 80.0), orc.match([bgr, depth], 80.0))

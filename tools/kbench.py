@@ -77,7 +77,7 @@ def main():
     out_p = C.c_void_p()
     offs = (C.c_size_t * (args.pool * n_q + 1))()
     ref = None
-    defaults = {"batch_frames": 8, "prune": 3, "mod_order": 2, "graphs": 1, "coarse_grid_limit": 0, "refine_tiled": 1, "coarse_narrow": 1, "coarse_share": 1}
+    defaults = {"batch_frames": 8, "prune": 3, "mod_order": 2, "graphs": 1, "coarse_grid_limit": 0, "refine_tiled": 1, "coarse_narrow": 1, "coarse_share": 1, "dn_count": 1}
     for cfg in args.configs.split(";"):
         opts = dict(defaults)
         opts.update({k: int(v) for k, v in (kv.split("=") for kv in cfg.split(","))})
