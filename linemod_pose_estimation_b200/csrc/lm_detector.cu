@@ -705,6 +705,7 @@ static int enqueue_match(lm_detector* d, Lane& ln, const Pack::Plan& plan, const
     rp.level[l].feats = pk.rfeats[l].as<uint32_t>();
     rp.level[l].plane_stride = g.nib_plane;
     rp.level[l].rows = g.rows; rp.level[l].cols = g.cols; rp.level[l].T = g.T; rp.level[l].W = g.W; rp.level[l].Hh = g.Hh;
+    rp.level[l].inv_T = g.T >= 2 ? 0xffffffffu / (unsigned)g.T + 1u : 0u;
   }
   launch_refine(rp, pk.ctpl.as<CoarseTpl>(), ln.cand.as<Cand>(), ln.cand_cap, ln.ctl.as<BatchCtl>(), ln.result.as<uint8_t>(),
                 ln.result.stride, ln.out_cap, s);

@@ -56,7 +56,8 @@ struct RefineLevel {
   const uint32_t* feats;                  // (x + 4096) | (y + 4096) << 13 | label << 26
   unsigned long long plane_stride;        // positions (nibbles) per orientation plane, in the layout the level is stored in
   int rows, cols, T, W;
-  int Hh;                                 // 0: flat planes (the reference's linearize order).  Otherwise the COLUMN-BLOCKED
+  unsigned int inv_T;                     // ceil(2^32 / T) for T >= 2: x / T = umulhi(x, inv_T) for the coordinates that occur
+  int Hh;                              // 0: flat planes (the reference's linearize order).  Otherwise the COLUMN-BLOCKED
                                           // layout of refinement levels (see tiled_nibble_index): rows per column block
 };
 

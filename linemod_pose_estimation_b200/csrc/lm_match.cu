@@ -476,10 +476,20 @@ constexpr size_t kResultStatsBytes = 16;  // statistics in front of every frame'
 // predicate is monotone in the integer score, so there is a smallest passing score: found here with the very same f32
 // operations, it lets the warp-per-candidate kernel stop a candidate exactly as soon as no position of its 16 x 16 window
 // can reach it any more (a response is at most 4 per remaining feature).
+// Called by a whole (converged) warp: the lanes test the 32 scores from an estimate two below the threshold at once and the
+// first passing one is the answer; the sequential search remains for the cases the estimate does not settle.
 __device__ __forceinline__ int min_passing_score(float threshold, int nf) {
   const float den = (float)(4 * nf);
-  int s = max(0, __float2int_rd(threshold * den * 0.01f) - 2);
+  const int s0 = max(0, __float2int_rd(threshold * den * 0.01f) - 2);
   const int cap = 4 * nf + 1;  // scores never exceed 4 * nf: `cap` means "cannot pass"
+  {
+    const int t = s0 + (int)(threadIdx.x & 31u);
+    const bool pass = t >= cap || !(__fdiv_rn(__fmul_rn((float)t, 100.f), den) < threshold);
+    const unsigned m = __ballot_sync(kFull, pass);
+    // lane 0 failing (or s0 = 0) means no smaller score passes: the predicate is monotone in the score
+    if (m != 0u && ((m & 1u) == 0u || s0 == 0)) return min(cap, s0 + __ffs((int)m) - 1);
+  }
+  int s = s0;
   while (s < cap && __fdiv_rn(__fmul_rn((float)s, 100.f), den) < threshold) ++s;
   while (s > 0 && !(__fdiv_rn(__fmul_rn((float)(s - 1), 100.f), den) < threshold)) --s;
   return s;
@@ -494,21 +504,25 @@ constexpr uint32_t kNoFeature = 0u;   // packed feature (x, y) = (-4096, -4096):
 template <bool TILED>
 __device__ __forceinline__ void refine_feature_address(const RefineLevel& L, uint32_t pk, int offset_x, int offset_y, uint32_t WH,
                                                        uint32_t zero_run, uint32_t* s_addr, int i) {
-  const int T = L.T, W = L.W;
+  const uint32_t T = (uint32_t)L.T, W = (uint32_t)L.W;
   const int fx = (int)(pk & 0x1fffu) - 4096 + offset_x, fy = (int)((pk >> 13) & 0x1fffu) - 4096 + offset_y;
   const bool inside = fx >= 0 && fy >= 0 && fx < L.cols && fy < L.rows;  // "Discard feature if out of bounds"
   const uint32_t label = pk >> 26;
+  // fx / T, fx % T (and fy) without integer divisions: coordinates are < 8192 and T <= 16, so the high word of the product
+  // with ceil(2^32 / T) is the exact quotient; coordinates outside the image are never used
+  const uint32_t ux = (uint32_t)fx, uy = (uint32_t)fy;
+  const uint32_t col = T == 1u ? ux : __umulhi(ux, L.inv_T), row = T == 1u ? uy : __umulhi(uy, L.inv_T);
+  const uint32_t phase = (uy - row * T) * T + (ux - col * T);
   if (!TILED) {
-    const uint32_t addr = label * (uint32_t)L.plane_stride + (uint32_t)((fy % T) * T + (fx % T)) * WH +
-                          (uint32_t)(fy / T) * (uint32_t)W + (uint32_t)(fx / T);
+    const uint32_t addr = label * (uint32_t)L.plane_stride + phase * WH + row * W + col;
     s_addr[i] = inside ? addr : zero_run;
   } else {
-    const uint32_t Hh = (uint32_t)L.Hh, block_bytes = Hh * 8u, phase_bytes = (uint32_t)W * Hh / 2u;
-    const uint32_t col = (uint32_t)(fx / T), row = (uint32_t)(fy / T), cb = col >> 4, sh = col & 15u;
-    const uint32_t phase0 = label * (uint32_t)(L.plane_stride / 2) + (uint32_t)((fy % T) * T + (fx % T)) * phase_bytes;
+    const uint32_t Hh = (uint32_t)L.Hh, block_bytes = Hh * 8u, phase_bytes = W * Hh / 2u;
+    const uint32_t cb = col >> 4, sh = col & 15u;
+    const uint32_t phase0 = label * (uint32_t)(L.plane_stride / 2) + phase * phase_bytes;
     uint32_t b0 = phase0 + cb * block_bytes + row * 8u;
     // second chunk: the next column block, or -- past the last one -- column block 0 one row down (the flat order's successor)
-    uint32_t b1 = (cb + 1u < ((uint32_t)W >> 4)) ? b0 + block_bytes : phase0 + (row + 1u) * 8u;
+    uint32_t b1 = (cb + 1u < (W >> 4)) ? b0 + block_bytes : phase0 + (row + 1u) * 8u;
     uint32_t s = sh;
     if (!inside) { b0 = b1 = zero_run; s = 0; }
     s_addr[2 * i] = b0 | (s & 7u) | ((s >> 3) << 31);
