@@ -1792,6 +1792,7 @@ struct lm_stream {
   std::vector<std::vector<std::string> > ids;       // the queries' class ids, owned
   std::vector<std::vector<const char*> > id_ptrs;
   int n_sources = 0;
+  int rows = 0, cols = 0;   // geometry of the frames in flight
   bool failed = false;
 };
 
@@ -1823,7 +1824,18 @@ int lm_stream_open(lm_detector* d, const lm_query* queries, int n_queries, lm_st
 int lm_stream_push(lm_stream* s, const lm_image* sources, int n_frames, int n_sources) {
   if (!s || (!sources && n_frames > 0) || n_frames < 0) return lm_fail(LM_E_INVALID, "NULL argument");
   if (s->failed) return lm_fail(LM_E_STATE, "the stream failed earlier: close it");
+  if (n_sources != s->d->model.M())
+    return lm_fail(LM_E_INVALID, "sources.size() (%d) != modalities.size() (%d)", n_sources, s->d->model.M());
   if (set_device(s->d) != LM_OK) return LM_E_CUDA;
+  if (n_frames > 0 && (sources[0].rows != s->rows || sources[0].cols != s->cols)) {
+    // another frame size re-packs the templates and rebuilds the lanes' workspaces: nothing of the old size may be in flight
+    int rc = s->pipe.drain();
+    if (rc != LM_OK) { s->failed = true; s->pipe.abandon(); return rc; }
+    s->rows = sources[0].rows; s->cols = sources[0].cols;
+  }
+  for (int f = 1; f < n_frames; ++f)
+    if (sources[(size_t)f * n_sources].rows != sources[0].rows || sources[(size_t)f * n_sources].cols != sources[0].cols)
+      return lm_fail(LM_E_INVALID, "frames of a push differ in size");
   for (int at = 0; at < n_frames;) {
     // a stream's very first chunks ramp up like a batch call's; after that every chunk is full
     int n = std::min(s->pipe.F, n_frames - at);
