@@ -289,7 +289,7 @@ void lm_free_matches(lm_match_rec* matches);
  * (src/rgbdDetector.cpp:31-34); this is the same call for a caller that has the next frames already.
  *   lm_stream_open   fixes the queries (class ids are copied) and takes over the handle's workspace lanes: other matching
  *                    calls on the handle return LM_E_STATE until lm_stream_close.
- *   lm_stream_push   enqueues n_frames frames (sources[f*n_sources + m]) in chunks of "batch_frames"; returns once the
+ *   lm_stream_push   enqueues n_frames frames (sources[f*n_sources + m]) in chunks of "stream_frames" (default 16); returns once the
  *                    copies and kernels are enqueued, blocking only while all "batch_lanes" lanes are busy.  Pinned source
  *                    buffers are read asynchronously: they must stay unchanged until lm_stream_pop has returned their frames
  *                    (pageable ones are staged during the call).
@@ -485,7 +485,8 @@ int lm_last_work(const lm_detector* det, uint64_t out[8]);
  * "stream_frames" (frames per chunk of an lm_stream opened afterwards, 1..32, default 16), "refine_tiled" (refinement levels
  * keep their nibble planes column-blocked, default 1), "coarse_narrow" (requests whose tiles have at most 63 features use the
  * u8-only coarse kernel: 1 default, 0 the general kernel, 2 the u8-only body at two CTAs per SM; process-wide),
- * "coarse_share" (coarse tail passes of at most 128 positions are scored for eight frames per warp, default 1) -- A/B
+ * "coarse_share" (coarse tail passes of at most 128 positions are scored for eight frames per warp, default 1), "dn_count"
+ * (DepthNormal's medianBlur(5) by counting when the NORMAL_LUT is one-hot, default 1; 0 keeps the median network) -- A/B
  * switches, results do not depend on them --
  * "coarse_grid_limit", "device_out_cap" (records per frame block on the device-resident paths, default 2048),
  * "cand_per_frame" (coarse candidates a chunk may produce per frame on the device-resident paths, default 65536; the
