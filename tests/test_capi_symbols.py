@@ -58,6 +58,12 @@ def test_compute_entry_points_fail_loudly_without_gpu():
     with pytest.raises(LinemodError) as e:
         det.addTemplate([bgr, depth], "obj", np.full((480, 640), 255, np.uint8))
     assert e.value.code == _capi.LM_E_CUDA
+    with pytest.raises(LinemodError) as e:
+        det.open_stream([(90.0, [])])
+    assert e.value.code == _capi.LM_E_CUDA
+    with pytest.raises(LinemodError) as e:
+        det.match_batch_multi([[bgr, depth]] * 3, [(90.0, [])])
+    assert e.value.code == _capi.LM_E_CUDA
     with pytest.raises(LinemodError):
         det.build_front([bgr, depth])
 
